@@ -1,0 +1,147 @@
+/* slow5b200.h -- C-ABI of the B200-native BLOW5 per-record codec (libslow5b200.so).
+ *
+ * This is the drop-in boundary for the reference's per-record compress/decompress path.  Plain
+ * pointers and sizes only; no C++/torch types.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree, slow5tools @ c114858 / slow5lib @ c13c4b8).
+ *
+ * Three levels, narrow to wide:
+ *   1. per-buffer   s5b_ptr_compress_solo / s5b_ptr_depress_solo
+ *                   == slow5_ptr_compress_solo / slow5_ptr_depress_solo
+ *                      (slow5lib/include/slow5/slow5_press.h:118,122; slow5lib/src/slow5_press.c:330,439)
+ *   2. host batch   s5b_*_batch_host: arrays of record buffers in, malloc'd buffers out -- the slot
+ *                   `work_db(&core,&db,func)` fills at src/view.c:292 and the body of
+ *                   slow5_get_next_batch / slow5_encode_batch (slow5lib/src/slow5_mt.c:336,353)
+ *   3. device batch s5b_*_dev: slabs already resident in HBM, used by the batch scheduler and bench.
+ *
+ * Error convention (slow5lib/include/slow5/slow5_defs.h:137-154): 0 on success, negative on failure;
+ * the codes below reuse the reference's values where one exists.
+ * There is NO CPU fallback: every compute entry point returns S5B_ERR_DEVICE when no CUDA device /
+ * kernel image is usable.
+ */
+#ifndef SLOW5B200_H
+#define SLOW5B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S5B_OK            0
+#define S5B_ERR_ARG      (-2)   /* == SLOW5_ERR_ARG   (slow5_defs.h) bad argument                  */
+#define S5B_ERR_MEM      (-10)  /* == SLOW5_ERR_MEM   allocation failure (host or device)          */
+#define S5B_ERR_PRESS    (-13)  /* == SLOW5_ERR_PRESS stream is not a valid svb-zd / zlib stream   */
+#define S5B_ERR_NOSPACE  (-40)  /* output slot smaller than the worst case for that read           */
+#define S5B_ERR_DEVICE   (-41)  /* no CUDA device, no sm_100a image, or a CUDA runtime error       */
+
+/* enum slow5_press_method (slow5_press.h:61-67): library enum, NOT the file byte */
+#define S5B_COMPRESS_NONE   0
+#define S5B_COMPRESS_ZLIB   1
+#define S5B_COMPRESS_SVB_ZD 2
+#define S5B_COMPRESS_ZSTD   3
+#define S5B_COMPRESS_EX_ZD  4
+
+typedef struct s5b_ctx s5b_ctx_t;   /* one per (host thread, GPU): stream, scratch, pinned staging */
+
+/* ---- library / context ------------------------------------------------------------------ */
+const char *s5b_version(void);
+const char *s5b_strerror(int err);
+/* number of CUDA devices visible (0 when none; never fails) */
+int  s5b_device_count(void);
+/* Replaces slow5_press_init / slow5_init_mt (slow5_press.c:174, slow5_mt.c:257) as the holder of
+ * per-worker codec state.  device < 0 selects the current device. */
+int  s5b_ctx_create(int device, s5b_ctx_t **ctx);
+void s5b_ctx_destroy(s5b_ctx_t *ctx);
+/* last CUDA error string seen by this context ("" if none) */
+const char *s5b_ctx_last_cuda_error(const s5b_ctx_t *ctx);
+/* kernels launched through this context since creation (bench.py's gpu_launches) */
+uint64_t s5b_ctx_launch_count(const s5b_ctx_t *ctx);
+
+/* ---- sizes ------------------------------------------------------------------------------- */
+/* Worst-case svb-zd bytes for n int16 samples INCLUDING the 4-byte length header:
+ * 4 + ceil(n/4) + 3n.  (int16 deltas zigzag to < 2^24, so the 4-byte code of
+ * streamvbyte.h:31-37's 4n bound is unreachable from slow5_press.c:1082.) */
+uint64_t s5b_svbzd_bound(uint32_t n_samples);
+/* s5b_svbzd_bound rounded up to the 16-byte slot granule used by the device layout */
+uint64_t s5b_svbzd_slot(uint32_t n_samples);
+
+/* ---- level 3: device-resident batches ------------------------------------------------------
+ * All d_* pointers are device pointers; `stream` is a cudaStream_t (NULL = the context's stream).
+ * Calls are asynchronous with respect to the host: results are valid once `stream` is synced.
+ *
+ * Layout contract ("slab + offsets", the device twin of slow5_batch_t's mem_records[]/mem_bytes[],
+ * slow5_mt.h:23-33):
+ *   d_sig        int16 slab; read r's samples start at sample index d_sig_off[r]; d_sig_off has
+ *                n_reads+1 entries, every entry a multiple of 8 samples (16-byte TMA granule), and
+ *                d_sig_off[r+1]-d_sig_off[r] >= n_samples[r]; the slab base is 16-byte aligned.
+ *   d_svb        byte slab; read r's stream occupies [d_svb_off[r], d_svb_off[r]+d_svb_len[r]);
+ *                d_svb_off has n_reads+1 entries (entry r+1 bounds slot r); any byte alignment.
+ *                The slab allocation must be a multiple of 16 bytes (svb_capacity says how long).
+ */
+
+/* Replaces ptr_compress_svb_zd (slow5_press.c:1082-1115) for a whole batch: int16 -> svb-zd stream
+ * [u32 N][keys ceil(N/4)][data].  d_status[r] = 0 or S5B_ERR_*; on error d_svb_len[r] = 0.
+ * Requires slot r >= s5b_svbzd_bound(n_samples[r]) else S5B_ERR_NOSPACE for that read. */
+int s5b_svbzd_encode_dev(s5b_ctx_t *ctx,
+                         const int16_t *d_sig, const uint64_t *d_sig_off, const uint32_t *d_n_samples,
+                         uint64_t n_reads,
+                         uint8_t *d_svb, const uint64_t *d_svb_off, uint32_t *d_svb_len,
+                         int32_t *d_status, void *stream);
+
+/* Replaces ptr_depress_svb_zd (slow5_press.c:1143-1173).  d_n_samples[r] receives the header count,
+ * d_status[r] = 0, S5B_ERR_PRESS (stream does not consume exactly d_svb_len[r]-4 bytes,
+ * slow5_press.c:1130-1136), or S5B_ERR_ARG / S5B_ERR_NOSPACE (len < 4 / signal slot too small). */
+int s5b_svbzd_decode_dev(s5b_ctx_t *ctx,
+                         const uint8_t *d_svb, const uint64_t *d_svb_off, const uint32_t *d_svb_len,
+                         uint64_t svb_capacity, uint64_t n_reads,
+                         int16_t *d_sig, const uint64_t *d_sig_off, uint32_t *d_n_samples,
+                         int32_t *d_status, void *stream);
+
+/* Reads only the u32 headers: d_n_samples[r] = N of stream r (0 when len < 4). */
+int s5b_svbzd_peek_dev(s5b_ctx_t *ctx, const uint8_t *d_svb, const uint64_t *d_svb_off,
+                       const uint32_t *d_svb_len, uint64_t n_reads, uint32_t *d_n_samples, void *stream);
+
+/* Gathers slotted streams into a dense slab: d_dst_off[r] (n_reads+1 entries, exclusive scan of
+ * len rounded up to `align`, align in {1,16}) and the copied bytes.  d_dst capacity is checked
+ * against dst_capacity (S5B_ERR_NOSPACE is reported through the return of the host wrappers). */
+int s5b_compact_dev(s5b_ctx_t *ctx, const uint8_t *d_src, const uint64_t *d_src_off,
+                    const uint32_t *d_len, uint64_t n_reads, uint32_t align,
+                    uint8_t *d_dst, uint64_t *d_dst_off, void *stream);
+
+/* ---- level 2: host batches (the work_db / slow5_mt slot) ----------------------------------- */
+/* Slab form: h_sig/h_sig_off/h_n_samples as in the device contract but in host memory (pinned or
+ * pageable; pinned avoids a staging copy).  h_svb receives the DENSE streams, stream r at
+ * h_svb_off[r] (n_reads+1 entries written by the call, 16-byte granule), h_svb_len[r] bytes.
+ * Returns 0, or the first non-zero per-read status / a call-level error. */
+int s5b_svbzd_encode_host(s5b_ctx_t *ctx,
+                          const int16_t *h_sig, const uint64_t *h_sig_off, const uint32_t *h_n_samples,
+                          uint64_t n_reads,
+                          uint8_t *h_svb, uint64_t h_svb_capacity, uint64_t *h_svb_off, uint32_t *h_svb_len,
+                          int32_t *h_status);
+int s5b_svbzd_decode_host(s5b_ctx_t *ctx,
+                          const uint8_t *h_svb, const uint64_t *h_svb_off, const uint32_t *h_svb_len,
+                          uint64_t n_reads,
+                          int16_t *h_sig, uint64_t h_sig_capacity /*samples*/, uint64_t *h_sig_off,
+                          uint32_t *h_n_samples, int32_t *h_status);
+
+/* Pointer-array form, the exact shape of db_t / slow5_batch_t: n buffers in, n malloc()'d buffers
+ * out (caller free()s each), NULL + out_n[i]=0 for a failed record.  `method` is a
+ * S5B_COMPRESS_* value; SVB_ZD and ZLIB are accelerated, NONE is a copy. */
+int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
+                            size_t n, void **out_ptrs, size_t *out_n);
+int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
+                           size_t n, void **out_ptrs, size_t *out_n);
+
+/* ---- level 1: single buffers ---------------------------------------------------------------
+ * Same contract as slow5_ptr_compress_solo / slow5_ptr_depress_solo: returns a malloc()'d buffer,
+ * *n its size; NULL and *n = 0 on failure (s5b_last_error() holds the code, the twin of the
+ * reference's thread-local slow5_errno).  A batch of one: correct but latency-bound; callers that
+ * care about throughput use the batch forms.  Uses a lazily created per-thread context. */
+void *s5b_ptr_compress_solo(int method, const void *ptr, size_t count, size_t *n);
+void *s5b_ptr_depress_solo(int method, const void *ptr, size_t count, size_t *n);
+int   s5b_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLOW5B200_H */

@@ -1,0 +1,164 @@
+"""Host mirror of the reference's batch codec slot (src/view.c:292 work_db; slow5_mt.c:336-359)
+over the C-ABI: torch tensors carry the slabs, the library does all the work."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import lib, S5BError, METHOD
+
+
+def sig_layout(n_samples):
+    """Signal slab layout: read r starts at a multiple of 8 samples (16-byte TMA granule).
+    Returns uint64 offsets with len(n_samples)+1 entries."""
+    n = np.asarray(n_samples, dtype=np.uint64)
+    pad = (n + np.uint64(7)) // np.uint64(8) * np.uint64(8)
+    off = np.zeros(len(n) + 1, dtype=np.uint64)
+    np.cumsum(pad, out=off[1:])
+    return off
+
+
+def svb_slot_layout(n_samples):
+    """Slot layout for encode output: slot r = worst-case svb-zd size of read r rounded to 16 bytes
+    (s5b_svbzd_slot)."""
+    n = np.asarray(n_samples, dtype=np.uint64)
+    bound = np.uint64(4) + (n + np.uint64(3)) // np.uint64(4) + np.uint64(3) * n
+    slot = (bound + np.uint64(15)) // np.uint64(16) * np.uint64(16)
+    off = np.zeros(len(n) + 1, dtype=np.uint64)
+    np.cumsum(slot, out=off[1:])
+    return off
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    raise TypeError(type(t))
+
+
+class Codec:
+    """One per (process, GPU).  Wraps s5b_ctx_t."""
+
+    def __init__(self, device=None):
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = lib.s5b_ctx_create(self.device, C.byref(h))
+        if rc != 0:
+            raise S5BError(rc, "s5b_ctx_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.s5b_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, where):
+        if rc != 0:
+            raise S5BError(rc, where, lib.s5b_ctx_last_cuda_error(self._h).decode())
+
+    @property
+    def launches(self):
+        return int(lib.s5b_ctx_launch_count(self._h))
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ---- device-resident ---------------------------------------------------------------------
+    def svbzd_encode_dev(self, sig, sig_off, n_samples, svb, svb_off, svb_len, status):
+        self._check(lib.s5b_svbzd_encode_dev(self._h, _ptr(sig), _ptr(sig_off), _ptr(n_samples), n_samples.numel(),
+                                             _ptr(svb), _ptr(svb_off), _ptr(svb_len), _ptr(status), self._stream()),
+                    "s5b_svbzd_encode_dev")
+
+    def svbzd_decode_dev(self, svb, svb_off, svb_len, sig, sig_off, n_samples, status):
+        self._check(lib.s5b_svbzd_decode_dev(self._h, _ptr(svb), _ptr(svb_off), _ptr(svb_len), svb.numel(),
+                                             svb_len.numel(), _ptr(sig), _ptr(sig_off), _ptr(n_samples), _ptr(status),
+                                             self._stream()),
+                    "s5b_svbzd_decode_dev")
+
+    def svbzd_peek_dev(self, svb, svb_off, svb_len, n_samples):
+        self._check(lib.s5b_svbzd_peek_dev(self._h, _ptr(svb), _ptr(svb_off), _ptr(svb_len), svb_len.numel(),
+                                           _ptr(n_samples), self._stream()), "s5b_svbzd_peek_dev")
+
+    def compact_dev(self, src, src_off, length, dst, dst_off, align=16):
+        self._check(lib.s5b_compact_dev(self._h, _ptr(src), _ptr(src_off), _ptr(length), length.numel(), align,
+                                        _ptr(dst), _ptr(dst_off), self._stream()), "s5b_compact_dev")
+
+    # ---- host slabs ---------------------------------------------------------------------------
+    def svbzd_encode_host(self, sig, sig_off, n_samples, svb, svb_off, svb_len, status, check=True):
+        """sig/svb: host tensors or arrays (pinned for speed); returns the call's return code."""
+        n = len(n_samples)
+        rc = lib.s5b_svbzd_encode_host(self._h, _ptr(sig), _ptr(sig_off), _ptr(n_samples), n, _ptr(svb),
+                                       svb.numel() if isinstance(svb, torch.Tensor) else svb.size,
+                                       _ptr(svb_off), _ptr(svb_len), _ptr(status))
+        if check:
+            self._check(rc, "s5b_svbzd_encode_host")
+        return rc
+
+    def svbzd_decode_host(self, svb, svb_off, svb_len, sig, sig_off, n_samples, status, check=True):
+        n = len(svb_len)
+        rc = lib.s5b_svbzd_decode_host(self._h, _ptr(svb), _ptr(svb_off), _ptr(svb_len), n, _ptr(sig),
+                                       sig.numel() if isinstance(sig, torch.Tensor) else sig.size,
+                                       _ptr(sig_off), _ptr(n_samples), _ptr(status))
+        if check:
+            self._check(rc, "s5b_svbzd_decode_host")
+        return rc
+
+    # ---- pointer arrays (db_t shape): list of bytes-like in, list of bytes out -----------------
+    def _batch(self, fn, method, bufs):
+        n = len(bufs)
+        keep = [np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, np.uint8) for b in bufs]
+        ptrs = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+        counts = (C.c_size_t * n)(*[len(b) for b in bufs])
+        outp = (C.c_void_p * n)()
+        outn = (C.c_size_t * n)()
+        rc = fn(self._h, method, ptrs, counts, n, outp, outn)
+        res = []
+        for i in range(n):
+            if outp[i]:
+                res.append(C.string_at(outp[i], outn[i]))
+                _capi.free(outp[i])
+            else:
+                res.append(None)
+        return rc, res
+
+    def compress_batch(self, method, bufs):
+        return self._batch(lib.s5b_compress_batch_host, method, bufs)
+
+    def depress_batch(self, method, bufs):
+        return self._batch(lib.s5b_depress_batch_host, method, bufs)
+
+
+def ptr_compress_solo(method, data):
+    """slow5_ptr_compress_solo twin: bytes in, bytes out (None on failure; see s5b_last_error)."""
+    buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+    n = C.c_size_t()
+    p = lib.s5b_ptr_compress_solo(method, buf.ctypes.data, len(data), C.byref(n))
+    if not p:
+        return None
+    out = C.string_at(p, n.value)
+    _capi.free(p)
+    return out
+
+
+def ptr_depress_solo(method, data):
+    buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+    n = C.c_size_t()
+    p = lib.s5b_ptr_depress_solo(method, buf.ctypes.data, len(data), C.byref(n))
+    if not p:
+        return None
+    out = C.string_at(p, n.value)
+    _capi.free(p)
+    return out

@@ -1,0 +1,720 @@
+// s5b_capi.cu -- C-ABI (include/slow5b200.h) over the codec kernels, plus the CUDA-stream batch
+// scheduler that replaces the reference's fork-join pthread pool for this path
+// (src/thread.c:19-114 work_db/pthread_db/pthread_single; slow5lib/src/slow5_mt.c:202-316).
+//
+// Scheduler shape: a host batch is cut into sub-batches of ~S5B_CHUNK_MB of payload; sub-batch i runs
+// on pipeline slot i % 2, each slot owning a stream, device slabs and pinned metadata, so the H2D copy
+// of sub-batch i+1, the kernels of sub-batch i and the D2H copy of sub-batch i-1 overlap.  There is no
+// CPU codec in this file: if CUDA is unusable every entry point reports S5B_ERR_DEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/slow5b200.h"
+#include "s5b_kernels.h"
+
+using namespace s5b;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        want = (want + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int NSLOT = 2;
+
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf d_a, d_b, d_c;       // payload in / slotted out / dense out
+    DevBuf d_meta;              // offsets, lengths, statuses
+    DevBuf d_scratch;           // scan scratch
+    PinBuf h_meta;              // pinned mirror of d_meta (both directions)
+    unsigned long long *d_counter = nullptr;
+};
+
+}  // namespace
+
+struct s5b_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int enc_bps = 0, dec_bps = 0;
+    cudaStream_t stream = nullptr;  // default stream for *_dev calls
+    unsigned long long *d_counter = nullptr;
+    DevBuf d_scratch;
+    PipeSlot slot[NSLOT];
+    PinBuf h_stage_in, h_stage_out;  // pointer-array forms
+    uint64_t launches = 0;
+    size_t chunk_bytes = 64u << 20;
+    std::string last_cuda_error;
+};
+
+namespace {
+
+thread_local int tl_last_error = 0;
+
+int cuda_fail(s5b_ctx *c, cudaError_t e) {
+    if (c) c->last_cuda_error = cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? S5B_ERR_MEM : S5B_ERR_DEVICE;
+}
+#define CU(call)                                  \
+    do {                                          \
+        cudaError_t e__ = (call);                 \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+const char *s5b_version(void) { return "slow5b200 0.1.0 (sm_100a)"; }
+
+const char *s5b_strerror(int err) {
+    switch (err) {
+        case S5B_OK: return "ok";
+        case S5B_ERR_ARG: return "bad argument";
+        case S5B_ERR_MEM: return "out of memory";
+        case S5B_ERR_PRESS: return "malformed compressed stream";
+        case S5B_ERR_NOSPACE: return "output slot too small";
+        case S5B_ERR_DEVICE: return "CUDA device unavailable or CUDA error";
+        default: return "unknown error";
+    }
+}
+
+int s5b_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint64_t s5b_svbzd_bound(uint32_t n) { return 4ull + ((uint64_t)n + 3) / 4 + 3ull * n; }
+uint64_t s5b_svbzd_slot(uint32_t n) { return round_up(s5b_svbzd_bound(n), 16); }
+
+int s5b_ctx_create(int device, s5b_ctx_t **out) {
+    if (!out) return S5B_ERR_ARG;
+    *out = nullptr;
+    int ndev = s5b_device_count();
+    if (ndev <= 0) return S5B_ERR_DEVICE;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return S5B_ERR_DEVICE;
+    }
+    if (device >= ndev) return S5B_ERR_ARG;
+    s5b_ctx *ctx = new (std::nothrow) s5b_ctx();
+    if (!ctx) return S5B_ERR_MEM;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return S5B_ERR_DEVICE;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->enc_bps = svbzd_encode_blocks_per_sm();
+    ctx->dec_bps = svbzd_decode_blocks_per_sm();
+    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0) {  // no sm_100a image for this device
+        (void)cudaGetLastError();
+        delete ctx;
+        return S5B_ERR_DEVICE;
+    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counter, 256) == cudaSuccess;
+    for (int i = 0; ok && i < NSLOT; ++i) {
+        ok = ok && cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->slot[i].d_counter, 256) == cudaSuccess;
+    }
+    if (const char *e = getenv("S5B_CHUNK_MB")) {
+        long v = atol(e);
+        if (v > 0) ctx->chunk_bytes = (size_t)v << 20;
+    }
+    if (!ok) {
+        s5b_ctx_destroy(ctx);
+        return S5B_ERR_DEVICE;
+    }
+    *out = ctx;
+    return S5B_OK;
+}
+
+void s5b_ctx_destroy(s5b_ctx_t *ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < NSLOT; ++i) {
+        PipeSlot &s = ctx->slot[i];
+        s.d_a.release();
+        s.d_b.release();
+        s.d_c.release();
+        s.d_meta.release();
+        s.d_scratch.release();
+        s.h_meta.release();
+        if (s.d_counter) cudaFree(s.d_counter);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    ctx->d_scratch.release();
+    ctx->h_stage_in.release();
+    ctx->h_stage_out.release();
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+const char *s5b_ctx_last_cuda_error(const s5b_ctx_t *ctx) { return ctx ? ctx->last_cuda_error.c_str() : ""; }
+uint64_t s5b_ctx_launch_count(const s5b_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// device-resident batches
+// ---------------------------------------------------------------------------------------------
+int s5b_svbzd_encode_dev(s5b_ctx_t *ctx, const int16_t *d_sig, const uint64_t *d_sig_off, const uint32_t *d_n_samples,
+                         uint64_t n_reads, uint8_t *d_svb, const uint64_t *d_svb_off, uint32_t *d_svb_len,
+                         int32_t *d_status, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_sig || !d_sig_off || !d_n_samples || !d_svb || !d_svb_off || !d_svb_len || !d_status) return S5B_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_sig) & 15u) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    SvbEncodeArgs a{d_sig, d_sig_off, d_n_samples, n_reads, d_svb, d_svb_off, d_svb_len, d_status, ctx->d_counter};
+    CU(launch_svbzd_encode(a, ctx->num_sms, ctx->enc_bps, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+int s5b_svbzd_decode_dev(s5b_ctx_t *ctx, const uint8_t *d_svb, const uint64_t *d_svb_off, const uint32_t *d_svb_len,
+                         uint64_t svb_capacity, uint64_t n_reads, int16_t *d_sig, const uint64_t *d_sig_off,
+                         uint32_t *d_n_samples, int32_t *d_status, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_svb || !d_svb_off || !d_svb_len || !d_sig || !d_sig_off || !d_n_samples || !d_status) return S5B_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_svb) & 15u) || (reinterpret_cast<uintptr_t>(d_sig) & 15u) || (svb_capacity & 15u))
+        return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    // the decode kernel's work counter must not alias an encode still in flight on another stream
+    SvbDecodeArgs a{d_svb, d_svb_off, d_svb_len, svb_capacity, n_reads, d_sig, d_sig_off, d_n_samples, d_status,
+                    ctx->d_counter + 8};
+    CU(launch_svbzd_decode(a, ctx->num_sms, ctx->dec_bps, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+int s5b_svbzd_peek_dev(s5b_ctx_t *ctx, const uint8_t *d_svb, const uint64_t *d_svb_off, const uint32_t *d_svb_len,
+                       uint64_t n_reads, uint32_t *d_n_samples, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_svb || !d_svb_off || !d_svb_len || !d_n_samples) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    CU(launch_svbzd_peek(d_svb, d_svb_off, d_svb_len, n_reads, d_n_samples, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+int s5b_compact_dev(s5b_ctx_t *ctx, const uint8_t *d_src, const uint64_t *d_src_off, const uint32_t *d_len,
+                    uint64_t n_reads, uint32_t align, uint8_t *d_dst, uint64_t *d_dst_off, void *stream) {
+    if (!ctx || !d_dst_off) return S5B_ERR_ARG;
+    if (align != 1 && align != 16) return S5B_ERR_ARG;
+    if (n_reads && (!d_src || !d_src_off || !d_len || !d_dst)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    CU(ctx->d_scratch.reserve(compact_scratch_bytes(n_reads)));
+    int nl = 0;
+    CU(launch_compact(d_src, d_src_off, d_len, n_reads, align, d_dst, d_dst_off, ctx->d_scratch.p, st, &nl));
+    ctx->launches += nl;
+    return S5B_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host batches: slab form
+// ---------------------------------------------------------------------------------------------
+// Cuts [0, n) into runs whose payload stays under `budget` bytes (at least one read per run).
+static void cut_runs(const uint64_t *off, uint64_t n, uint64_t unit, uint64_t budget,
+                     std::vector<uint64_t> &cuts) {
+    cuts.clear();
+    cuts.push_back(0);
+    uint64_t start = 0;
+    for (uint64_t r = 1; r <= n; ++r) {
+        if (r == n) break;
+        if ((off[r + 1] - off[start]) * unit > budget && r > start) {
+            cuts.push_back(r);
+            start = r;
+        }
+    }
+    cuts.push_back(n);
+}
+
+int s5b_svbzd_encode_host(s5b_ctx_t *ctx, const int16_t *h_sig, const uint64_t *h_sig_off, const uint32_t *h_n_samples,
+                          uint64_t n_reads, uint8_t *h_svb, uint64_t h_svb_capacity, uint64_t *h_svb_off,
+                          uint32_t *h_svb_len, int32_t *h_status) {
+    if (!ctx || !h_svb_off) return S5B_ERR_ARG;
+    h_svb_off[0] = 0;
+    if (n_reads == 0) return S5B_OK;
+    if (!h_sig || !h_sig_off || !h_n_samples || !h_svb || !h_svb_len || !h_status) return S5B_ERR_ARG;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        if ((h_sig_off[r] & 7) || h_sig_off[r + 1] < h_sig_off[r] || h_sig_off[r + 1] - h_sig_off[r] < h_n_samples[r])
+            return S5B_ERR_ARG;
+    }
+    DeviceGuard g(ctx->device);
+    std::vector<uint64_t> cuts;
+    cut_runs(h_sig_off, n_reads, 2, ctx->chunk_bytes, cuts);
+    const size_t nrun = cuts.size() - 1;
+
+    struct Pending {
+        bool active = false;
+        uint64_t r0 = 0, r1 = 0;
+        uint64_t host_base = 0;
+    } pend[NSLOT];
+    uint64_t host_total = 0;
+    int first_err = S5B_OK;
+
+    // finish(): wait for the slot's kernels, learn the dense size, queue the payload D2H, fix up offsets
+    auto finish = [&](int si) -> int {
+        PipeSlot &s = ctx->slot[si];
+        Pending &p = pend[si];
+        if (!p.active) return S5B_OK;
+        p.active = false;
+        const uint64_t m = p.r1 - p.r0;
+        CU(cudaEventSynchronize(s.done));
+        // pinned meta layout (written by the D2H below): [dense_off (m+1) u64][len m u32][status m i32]
+        const uint64_t *dense_off = static_cast<const uint64_t *>(s.h_meta.p);
+        const uint32_t *len = reinterpret_cast<const uint32_t *>(dense_off + (m + 1));
+        const int32_t *status = reinterpret_cast<const int32_t *>(len + m);
+        const uint64_t dense_total = dense_off[m];
+        if (host_total + dense_total > h_svb_capacity) return S5B_ERR_NOSPACE;
+        CU(cudaMemcpyAsync(h_svb + host_total, s.d_c.p, dense_total, cudaMemcpyDeviceToHost, s.stream));
+        for (uint64_t i = 0; i < m; ++i) {
+            h_svb_off[p.r0 + i] = host_total + dense_off[i];
+            h_svb_len[p.r0 + i] = len[i];
+            h_status[p.r0 + i] = status[i];
+            if (status[i] != S5B_OK && first_err == S5B_OK) first_err = status[i];
+        }
+        host_total += dense_total;
+        h_svb_off[p.r1] = host_total;
+        CU(cudaEventRecord(s.done, s.stream));
+        return S5B_OK;
+    };
+
+    for (size_t run = 0; run < nrun; ++run) {
+        const int si = (int)(run % NSLOT);
+        PipeSlot &s = ctx->slot[si];
+        int rc = finish(si);
+        if (rc != S5B_OK) return rc;
+        CU(cudaEventSynchronize(s.done));  // previous payload D2H of this slot has landed; buffers are free
+        const uint64_t r0 = cuts[run], r1 = cuts[run + 1], m = r1 - r0;
+        const uint64_t s0 = h_sig_off[r0], s1 = h_sig_off[r1];
+        const uint64_t sig_bytes = round_up((s1 - s0) * 2, 16);
+        // host-side metadata for this run, rebased to the run's slabs
+        // layout in h_meta (up): [sig_off (m+1) u64][slot_off (m+1) u64][n m u32]
+        const size_t up_bytes = (2 * (m + 1)) * 8 + m * 4;
+        const size_t down_bytes = (m + 1) * 8 + m * 8;
+        CU(s.h_meta.reserve(up_bytes > down_bytes ? up_bytes : down_bytes));
+        uint64_t *u_sig_off = static_cast<uint64_t *>(s.h_meta.p);
+        uint64_t *u_slot_off = u_sig_off + (m + 1);
+        uint32_t *u_n = reinterpret_cast<uint32_t *>(u_slot_off + (m + 1));
+        uint64_t slot_total = 0;
+        for (uint64_t i = 0; i < m; ++i) {
+            u_sig_off[i] = h_sig_off[r0 + i] - s0;
+            u_slot_off[i] = slot_total;
+            u_n[i] = h_n_samples[r0 + i];
+            slot_total += s5b_svbzd_slot(u_n[i]);
+        }
+        u_sig_off[m] = sig_bytes / 2;  // padded: the last read may be bulk-copied in whole granules
+        u_slot_off[m] = slot_total;
+        // device meta layout: [sig_off][slot_off][n] | [dense_off (m+1) u64][len m u32][status m i32]
+        const size_t d_down_at = round_up(up_bytes, 16);
+        CU(s.d_meta.reserve(d_down_at + down_bytes));
+        CU(s.d_a.reserve(sig_bytes + 16));
+        CU(s.d_b.reserve(slot_total + 16));
+        CU(s.d_c.reserve(slot_total + 16));
+        CU(s.d_scratch.reserve(compact_scratch_bytes(m)));
+        uint8_t *dm = static_cast<uint8_t *>(s.d_meta.p);
+        uint64_t *d_sig_off = reinterpret_cast<uint64_t *>(dm);
+        uint64_t *d_slot_off = d_sig_off + (m + 1);
+        uint32_t *d_n = reinterpret_cast<uint32_t *>(d_slot_off + (m + 1));
+        uint64_t *d_dense_off = reinterpret_cast<uint64_t *>(dm + d_down_at);
+        uint32_t *d_len = reinterpret_cast<uint32_t *>(d_dense_off + (m + 1));
+        int32_t *d_status = reinterpret_cast<int32_t *>(d_len + m);
+
+        CU(cudaMemcpyAsync(dm, s.h_meta.p, up_bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_a.p, h_sig + s0, (s1 - s0) * 2, cudaMemcpyHostToDevice, s.stream));
+        SvbEncodeArgs a{static_cast<const int16_t *>(s.d_a.p), d_sig_off, d_n, m, static_cast<uint8_t *>(s.d_b.p),
+                        d_slot_off, d_len, d_status, s.d_counter};
+        CU(launch_svbzd_encode(a, ctx->num_sms, ctx->enc_bps, s.stream));
+        int nl = 0;
+        CU(launch_compact(static_cast<const uint8_t *>(s.d_b.p), d_slot_off, d_len, m, 16,
+                          static_cast<uint8_t *>(s.d_c.p), d_dense_off, s.d_scratch.p, s.stream, &nl));
+        ctx->launches += 1 + nl;
+        // the up-metadata in h_meta has been consumed by the H2D above once the stream reaches here;
+        // the same pinned block receives the down-metadata
+        CU(cudaMemcpyAsync(s.h_meta.p, d_dense_off, down_bytes, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
+        pend[si].active = true;
+        pend[si].r0 = r0;
+        pend[si].r1 = r1;
+    }
+    // drain in submission order so host offsets stay monotone
+    for (size_t k = 0; k < NSLOT; ++k) {
+        const int si = (int)((nrun + k) % NSLOT);
+        int rc = finish(si);
+        if (rc != S5B_OK) return rc;
+    }
+    for (int si = 0; si < NSLOT; ++si) CU(cudaEventSynchronize(ctx->slot[si].done));
+    return first_err;
+}
+
+int s5b_svbzd_decode_host(s5b_ctx_t *ctx, const uint8_t *h_svb, const uint64_t *h_svb_off, const uint32_t *h_svb_len,
+                          uint64_t n_reads, int16_t *h_sig, uint64_t h_sig_capacity, uint64_t *h_sig_off,
+                          uint32_t *h_n_samples, int32_t *h_status) {
+    if (!ctx || !h_sig_off) return S5B_ERR_ARG;
+    h_sig_off[0] = 0;
+    if (n_reads == 0) return S5B_OK;
+    if (!h_svb || !h_svb_off || !h_svb_len || !h_sig || !h_n_samples || !h_status) return S5B_ERR_ARG;
+    // sample counts come from the stream headers (slow5_press.c:1120); the signal layout follows from them
+    uint64_t sig_total = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        if (h_svb_off[r + 1] < h_svb_off[r] || h_svb_off[r + 1] - h_svb_off[r] < h_svb_len[r]) return S5B_ERR_ARG;
+        uint32_t n = 0;
+        if (h_svb_len[r] >= 4) memcpy(&n, h_svb + h_svb_off[r], 4);
+        h_n_samples[r] = n;
+        h_sig_off[r] = sig_total;
+        sig_total += round_up(n, 8);
+    }
+    h_sig_off[n_reads] = sig_total;
+    if (sig_total > h_sig_capacity) return S5B_ERR_NOSPACE;
+    DeviceGuard g(ctx->device);
+    // cut by output payload (the larger side)
+    std::vector<uint64_t> cuts;
+    cut_runs(h_sig_off, n_reads, 2, ctx->chunk_bytes, cuts);
+    const size_t nrun = cuts.size() - 1;
+    struct Pending {
+        bool active = false;
+        uint64_t r0 = 0, r1 = 0;
+    } pend[NSLOT];
+    int first_err = S5B_OK;
+    auto finish = [&](int si) -> int {
+        PipeSlot &s = ctx->slot[si];
+        Pending &p = pend[si];
+        if (!p.active) return S5B_OK;
+        p.active = false;
+        CU(cudaEventSynchronize(s.done));
+        const uint64_t m = p.r1 - p.r0;
+        // pinned down-meta: [n m u32][status m i32]
+        const uint32_t *n = static_cast<const uint32_t *>(s.h_meta.p);
+        const int32_t *status = reinterpret_cast<const int32_t *>(n + m);
+        for (uint64_t i = 0; i < m; ++i) {
+            h_status[p.r0 + i] = status[i];
+            if (status[i] != S5B_OK && first_err == S5B_OK) first_err = status[i];
+        }
+        return S5B_OK;
+    };
+    for (size_t run = 0; run < nrun; ++run) {
+        const int si = (int)(run % NSLOT);
+        PipeSlot &s = ctx->slot[si];
+        int rc = finish(si);
+        if (rc != S5B_OK) return rc;
+        const uint64_t r0 = cuts[run], r1 = cuts[run + 1], m = r1 - r0;
+        // input byte range, widened to 16-byte granules of the HOST slab offsets so relative alignment
+        // of every stream is preserved on the device
+        const uint64_t b0 = h_svb_off[r0] & ~15ull;
+        const uint64_t b1 = h_svb_off[r1 - 1] + h_svb_len[r1 - 1];
+        const uint64_t in_bytes = round_up(b1 - b0, 16);
+        const uint64_t s0 = h_sig_off[r0], s1 = h_sig_off[r1];
+        const size_t up_bytes = 2 * (m + 1) * 8 + m * 4;
+        const size_t down_bytes = m * 8;
+        CU(s.h_meta.reserve(up_bytes > down_bytes ? up_bytes : down_bytes));
+        uint64_t *u_svb_off = static_cast<uint64_t *>(s.h_meta.p);
+        uint64_t *u_sig_off = u_svb_off + (m + 1);
+        uint32_t *u_len = reinterpret_cast<uint32_t *>(u_sig_off + (m + 1));
+        for (uint64_t i = 0; i < m; ++i) {
+            u_svb_off[i] = h_svb_off[r0 + i] - b0;
+            u_sig_off[i] = h_sig_off[r0 + i] - s0;
+            u_len[i] = h_svb_len[r0 + i];
+        }
+        u_svb_off[m] = in_bytes;
+        u_sig_off[m] = s1 - s0;
+        const size_t d_down_at = round_up(up_bytes, 16);
+        CU(s.d_meta.reserve(d_down_at + down_bytes));
+        CU(s.d_a.reserve(in_bytes + 16));
+        CU(s.d_b.reserve((s1 - s0) * 2 + 16));
+        uint8_t *dm = static_cast<uint8_t *>(s.d_meta.p);
+        uint64_t *d_svb_off = reinterpret_cast<uint64_t *>(dm);
+        uint64_t *d_sig_off = d_svb_off + (m + 1);
+        uint32_t *d_len = reinterpret_cast<uint32_t *>(d_sig_off + (m + 1));
+        uint32_t *d_n = reinterpret_cast<uint32_t *>(dm + d_down_at);
+        int32_t *d_status = reinterpret_cast<int32_t *>(d_n + m);
+        CU(cudaMemcpyAsync(dm, s.h_meta.p, up_bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_a.p, h_svb + b0, b1 - b0, cudaMemcpyHostToDevice, s.stream));
+        SvbDecodeArgs a{static_cast<const uint8_t *>(s.d_a.p), d_svb_off, d_len, in_bytes, m,
+                        static_cast<int16_t *>(s.d_b.p), d_sig_off, d_n, d_status, s.d_counter};
+        CU(launch_svbzd_decode(a, ctx->num_sms, ctx->dec_bps, s.stream));
+        ctx->launches += 1;
+        CU(cudaMemcpyAsync(h_sig + s0, s.d_b.p, (s1 - s0) * 2, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_meta.p, d_n, down_bytes, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
+        pend[si].active = true;
+        pend[si].r0 = r0;
+        pend[si].r1 = r1;
+    }
+    for (size_t k = 0; k < NSLOT; ++k) {
+        int rc = finish((int)((nrun + k) % NSLOT));
+        if (rc != S5B_OK) return rc;
+    }
+    return first_err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host batches: pointer-array form (db_t / slow5_batch_t shape)
+// ---------------------------------------------------------------------------------------------
+static int svbzd_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, size_t n,
+                               void **out_ptrs, size_t *out_n) {
+    std::vector<uint64_t> sig_off(n + 1), svb_off(n + 1);
+    std::vector<uint32_t> ns(n), lens(n);
+    std::vector<int32_t> status(n);
+    uint64_t tot = 0, bound = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (!ptrs[i] && counts[i]) return S5B_ERR_ARG;
+        if (counts[i] / 2 > 0xffffffffull) return S5B_ERR_ARG;
+        ns[i] = (uint32_t)(counts[i] / 2);  // count is BYTES, slow5_press.c:1088
+        sig_off[i] = tot;
+        tot += round_up(ns[i], 8);
+        bound += s5b_svbzd_slot(ns[i]);
+    }
+    sig_off[n] = tot;
+    CU(ctx->h_stage_in.reserve(tot * 2 + 16));
+    CU(ctx->h_stage_out.reserve(bound + 16));
+    int16_t *hin = static_cast<int16_t *>(ctx->h_stage_in.p);
+    for (size_t i = 0; i < n; ++i) memcpy(hin + sig_off[i], ptrs[i], (size_t)ns[i] * 2);
+    int rc = s5b_svbzd_encode_host(ctx, hin, sig_off.data(), ns.data(), n, static_cast<uint8_t *>(ctx->h_stage_out.p),
+                                   bound + 16, svb_off.data(), lens.data(), status.data());
+    if (rc != S5B_OK && rc != S5B_ERR_PRESS && rc != S5B_ERR_NOSPACE && rc != S5B_ERR_ARG) return rc;
+    const uint8_t *hout = static_cast<const uint8_t *>(ctx->h_stage_out.p);
+    int first = S5B_OK;
+    for (size_t i = 0; i < n; ++i) {
+        out_ptrs[i] = nullptr;
+        out_n[i] = 0;
+        if (status[i] != S5B_OK) {
+            if (first == S5B_OK) first = status[i];
+            continue;
+        }
+        void *m = malloc(lens[i] ? lens[i] : 1);
+        if (!m) {
+            if (first == S5B_OK) first = S5B_ERR_MEM;
+            continue;
+        }
+        memcpy(m, hout + svb_off[i], lens[i]);
+        out_ptrs[i] = m;
+        out_n[i] = lens[i];
+    }
+    return first;
+}
+
+static int svbzd_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, size_t n,
+                              void **out_ptrs, size_t *out_n) {
+    std::vector<uint64_t> svb_off(n + 1), sig_off(n + 1);
+    std::vector<uint32_t> lens(n), ns(n);
+    std::vector<int32_t> status(n);
+    uint64_t tot = 0, sig_tot = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (!ptrs[i] && counts[i]) return S5B_ERR_ARG;
+        if (counts[i] > 0xffffffffull) return S5B_ERR_ARG;
+        lens[i] = (uint32_t)counts[i];
+        svb_off[i] = tot;
+        tot += round_up(lens[i], 16);
+        uint32_t nn = 0;
+        if (counts[i] >= 4) memcpy(&nn, ptrs[i], 4);
+        sig_tot += round_up(nn, 8);
+    }
+    svb_off[n] = tot;
+    CU(ctx->h_stage_in.reserve(tot + 16));
+    CU(ctx->h_stage_out.reserve(sig_tot * 2 + 16));
+    uint8_t *hin = static_cast<uint8_t *>(ctx->h_stage_in.p);
+    for (size_t i = 0; i < n; ++i) memcpy(hin + svb_off[i], ptrs[i], lens[i]);
+    int rc = s5b_svbzd_decode_host(ctx, hin, svb_off.data(), lens.data(), n, static_cast<int16_t *>(ctx->h_stage_out.p),
+                                   sig_tot, sig_off.data(), ns.data(), status.data());
+    if (rc != S5B_OK && rc != S5B_ERR_PRESS && rc != S5B_ERR_NOSPACE && rc != S5B_ERR_ARG) return rc;
+    const int16_t *hout = static_cast<const int16_t *>(ctx->h_stage_out.p);
+    int first = S5B_OK;
+    for (size_t i = 0; i < n; ++i) {
+        out_ptrs[i] = nullptr;
+        out_n[i] = 0;
+        if (status[i] != S5B_OK) {
+            if (first == S5B_OK) first = status[i];
+            continue;
+        }
+        const size_t bytes = (size_t)ns[i] * 2;
+        void *m = malloc(bytes ? bytes : 1);
+        if (!m) {
+            if (first == S5B_OK) first = S5B_ERR_MEM;
+            continue;
+        }
+        memcpy(m, hout + sig_off[i], bytes);
+        out_ptrs[i] = m;
+        out_n[i] = bytes;
+    }
+    return first;
+}
+
+static int copy_ptrs(const void *const *ptrs, const size_t *counts, size_t n, void **out_ptrs, size_t *out_n) {
+    // SLOW5_COMPRESS_NONE: malloc + memcpy (slow5_press.c:340-350, :449-459)
+    int first = S5B_OK;
+    for (size_t i = 0; i < n; ++i) {
+        out_ptrs[i] = malloc(counts[i] ? counts[i] : 1);
+        if (!out_ptrs[i]) {
+            out_n[i] = 0;
+            if (first == S5B_OK) first = S5B_ERR_MEM;
+            continue;
+        }
+        memcpy(out_ptrs[i], ptrs[i], counts[i]);
+        out_n[i] = counts[i];
+    }
+    return first;
+}
+
+int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts, size_t n,
+                            void **out_ptrs, size_t *out_n) {
+    if (!ctx || (n && (!ptrs || !counts || !out_ptrs || !out_n))) return S5B_ERR_ARG;
+    if (n == 0) return S5B_OK;
+    switch (method) {
+        case S5B_COMPRESS_NONE: return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);
+        case S5B_COMPRESS_SVB_ZD: return svbzd_compress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        default: return S5B_ERR_ARG;
+    }
+}
+
+int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts, size_t n,
+                           void **out_ptrs, size_t *out_n) {
+    if (!ctx || (n && (!ptrs || !counts || !out_ptrs || !out_n))) return S5B_ERR_ARG;
+    if (n == 0) return S5B_OK;
+    switch (method) {
+        case S5B_COMPRESS_NONE: return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);
+        case S5B_COMPRESS_SVB_ZD: return svbzd_depress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        default: return S5B_ERR_ARG;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// single buffers
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct TlCtx {
+    s5b_ctx_t *ctx = nullptr;
+    ~TlCtx() {
+        if (ctx) s5b_ctx_destroy(ctx);
+    }
+};
+s5b_ctx_t *thread_ctx(int *err) {
+    static thread_local TlCtx t;
+    if (!t.ctx) {
+        int rc = s5b_ctx_create(-1, &t.ctx);
+        if (rc != S5B_OK) {
+            *err = rc;
+            return nullptr;
+        }
+    }
+    return t.ctx;
+}
+}  // namespace
+
+void *s5b_ptr_compress_solo(int method, const void *ptr, size_t count, size_t *n) {
+    void *out = nullptr;
+    size_t out_n = 0;
+    int rc = S5B_OK;
+    if (!ptr || !n) {
+        rc = S5B_ERR_ARG;  // slow5_press.c:334-338
+    } else if (s5b_ctx_t *ctx = thread_ctx(&rc)) {
+        const void *ptrs[1] = {ptr};
+        size_t counts[1] = {count};
+        rc = s5b_compress_batch_host(ctx, method, ptrs, counts, 1, &out, &out_n);
+    }
+    tl_last_error = rc;
+    if (rc != S5B_OK) {
+        free(out);
+        out = nullptr;
+        out_n = 0;
+    }
+    if (n) *n = out_n;
+    return out;
+}
+
+void *s5b_ptr_depress_solo(int method, const void *ptr, size_t count, size_t *n) {
+    void *out = nullptr;
+    size_t out_n = 0;
+    int rc = S5B_OK;
+    if (!ptr || !n) {
+        rc = S5B_ERR_ARG;  // slow5_press.c:443-447
+    } else if (s5b_ctx_t *ctx = thread_ctx(&rc)) {
+        const void *ptrs[1] = {ptr};
+        size_t counts[1] = {count};
+        rc = s5b_depress_batch_host(ctx, method, ptrs, counts, 1, &out, &out_n);
+    }
+    tl_last_error = rc;
+    if (rc != S5B_OK) {
+        free(out);
+        out = nullptr;
+        out_n = 0;
+    }
+    if (n) *n = out_n;
+    return out;
+}
+
+int s5b_last_error(void) { return tl_last_error; }
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// s5b_kernels.h -- internal launcher interface between the C-ABI (s5b_capi.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace s5b {
+
+struct SvbEncodeArgs {
+    const int16_t *sig;
+    const uint64_t *sig_off;    // n_reads + 1, samples, multiples of 8
+    const uint32_t *n_samples;  // n_reads
+    uint64_t n_reads;
+    uint8_t *svb;
+    const uint64_t *svb_off;  // n_reads + 1, bytes
+    uint32_t *svb_len;        // n_reads
+    int32_t *status;          // n_reads
+    unsigned long long *work_counter;  // zeroed before launch
+};
+
+struct SvbDecodeArgs {
+    const uint8_t *svb;
+    const uint64_t *svb_off;  // n_reads + 1
+    const uint32_t *svb_len;  // n_reads
+    uint64_t svb_capacity;    // bytes, multiple of 16
+    uint64_t n_reads;
+    int16_t *sig;
+    const uint64_t *sig_off;  // n_reads + 1
+    uint32_t *n_samples;      // out
+    int32_t *status;          // out
+    unsigned long long *work_counter;
+};
+
+// grid sizing helpers (queried once per context)
+int svbzd_encode_blocks_per_sm();
+int svbzd_decode_blocks_per_sm();
+
+cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
+cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
+cudaError_t launch_svbzd_peek(const uint8_t *svb, const uint64_t *svb_off, const uint32_t *svb_len, uint64_t n_reads,
+                              uint32_t *n_samples, cudaStream_t st);
+
+// dense gather: scratch must hold >= compact_scratch_bytes(n_reads)
+size_t compact_scratch_bytes(uint64_t n_reads);
+cudaError_t launch_compact(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n_reads,
+                           uint32_t align, uint8_t *dst, uint64_t *dst_off, void *scratch, cudaStream_t st,
+                           int *n_launches);
+
+}  // namespace s5b

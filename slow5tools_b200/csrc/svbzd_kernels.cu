@@ -1,0 +1,678 @@
+// svbzd_kernels.cu -- sm_100a kernels for the svb-zd signal codec (StreamVByte "1234" coding of
+// zigzag-delta values, u32 sample-count header), one warp per read.
+//
+// Replaces, for whole batches, the reference CPU routines
+//   ptr_compress_svb_zd / ptr_compress_svb      slow5lib/src/slow5_press.c:1082-1115 / :1062-1079
+//   ptr_depress_svb_zd  / ptr_depress_svb       slow5lib/src/slow5_press.c:1143-1173 / :1118-1140
+//   __slow5_zigzag_delta_encode / _decode       thirdparty/streamvbyte/src/streamvbyte_zigzag.c:15-40
+//   __slow5_streamvbyte_encode / _decode        thirdparty/streamvbyte/src/streamvbyte_{en,de}code.c
+// Output bytes are identical to the reference's (tests/test_svbzd_gpu.py checks against the oracle).
+//
+// Data movement (both kernels are HBM-streaming, integer-only, no tensor cores):
+//   * each warp owns one read at a time (dynamic work counter), loops over 256-sample iterations
+//     (8 samples / lane, one 128-bit shared-memory load per lane);
+//   * encode: the int16 signal is staged HBM->smem by 1-D bulk async copies (TMA engine, UBLKCP)
+//     into a 2-stage per-warp pipeline guarded by mbarriers; a warp prefix scan over the per-lane
+//     byte counts gives every lane its data offset; key and data bytes are assembled in smem and
+//     leave as 128-bit coalesced stores;
+//   * decode: the variable-length data stream is staged by bulk async copies into a 4 x 1 KiB
+//     per-warp ring; a warp prefix scan over the control-byte lengths resolves the per-lane data
+//     offsets, a second scan rebuilds the running sum; samples leave as 128-bit coalesced stores.
+#include "s5b_kernels.h"
+#include "s5b_ptx.cuh"
+#include "../../include/slow5b200.h"
+
+namespace s5b {
+
+// ------------------------------------------------------------------------------------------------
+// common helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// next read index for this warp (uniform across lanes)
+__device__ __forceinline__ uint64_t next_work(unsigned long long *counter, int lane) {
+    unsigned long long r = 0;
+    if (lane == 0) r = atomicAdd(counter, 1ULL);
+    return __shfl_sync(FULL, r, 0);
+}
+
+// Byte-stream writer: a warp appends bytes to a small smem buffer whose index 0 corresponds to a
+// 16-byte aligned global address, and drains complete 16-byte segments with 128-bit stores.  The
+// ragged first / last segment of a stream leaves as single-byte stores so neighbouring streams in
+// the slab are never touched.  All members are warp-uniform.
+struct StreamWriter {
+    uint8_t *buf;    // smem, 16-byte aligned
+    uint8_t *gbase;  // global, 16-byte aligned, corresponds to buf[0]
+    uint32_t pend;   // bytes [head, pend) of buf are valid, not yet stored
+    uint32_t head;   // non-zero only before the first drain of a stream that starts unaligned
+
+    __device__ __forceinline__ void begin(uint8_t *smem_buf, uint8_t *dst) {
+        buf = smem_buf;
+        uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
+        gbase = dst - mis;
+        head = pend = mis;
+    }
+    // caller has __syncwarp()'d after the appends
+    __device__ __forceinline__ void drain(int lane) {
+        const uint32_t nseg = pend >> 4;
+        if (nseg == 0) return;
+        uint32_t first = 0;
+        if (head) {
+            if (lane >= (int)head && lane < 16) gbase[lane] = buf[lane];
+            first = 1;
+            head = 0;
+        }
+        const uint4 *s = reinterpret_cast<const uint4 *>(buf);
+        uint4 *g = reinterpret_cast<uint4 *>(gbase);
+        for (uint32_t seg = first + lane; seg < nseg; seg += 32) g[seg] = s[seg];
+        const uint32_t rem = pend & 15u;
+        uint8_t t = 0;
+        if (lane < (int)rem) t = buf[nseg * 16 + lane];
+        __syncwarp();
+        if (lane < (int)rem) buf[lane] = t;
+        gbase += nseg * 16;
+        pend = rem;
+        __syncwarp();
+    }
+    // end of stream: everything still pending (< 16 bytes after drain) leaves as byte stores
+    __device__ __forceinline__ void finish(int lane) {
+        drain(lane);
+        if (lane >= (int)head && lane < (int)pend) gbase[lane] = buf[lane];
+        __syncwarp();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// encode
+// ------------------------------------------------------------------------------------------------
+constexpr int ENC_WARPS = 8;
+constexpr int ENC_CH_SAMPLES = 1024;  // samples per bulk-copy chunk (4 iterations of 256)
+constexpr int ENC_CH_BYTES = ENC_CH_SAMPLES * 2;
+constexpr int ENC_STAGES = 2;
+
+struct __align__(128) EncWarpSmem {
+    uint8_t in[ENC_STAGES][ENC_CH_BYTES];  // staged signal
+    uint8_t dbuf[16 + 768 + 16];           // data bytes of one iteration (+ carried partial segment)
+    uint8_t kbuf[16 + 64 + 16];            // header + key bytes
+    unsigned long long bar[ENC_STAGES];
+};
+
+template <bool PARTIAL>
+__device__ __forceinline__ void enc_iteration(const uint4 w, int &carry, const int lane, const int nvalid,
+                                              StreamWriter &kw, StreamWriter &dw) {
+    // widen (slow5_press.c:1095-1097)
+    int x[8];
+    x[0] = (int)(w.x << 16) >> 16;
+    x[1] = (int)w.x >> 16;
+    x[2] = (int)(w.y << 16) >> 16;
+    x[3] = (int)w.y >> 16;
+    x[4] = (int)(w.z << 16) >> 16;
+    x[5] = (int)w.z >> 16;
+    x[6] = (int)(w.w << 16) >> 16;
+    x[7] = (int)w.w >> 16;
+    const int up = __shfl_up_sync(FULL, (int)w.w, 1);
+    int prev = lane ? (up >> 16) : carry;
+    carry = __shfl_sync(FULL, (int)w.w, 31) >> 16;
+
+    uint32_t z[8], c[8];
+    uint32_t key = 0, lane_len = 0, any3 = 0;
+    uint32_t off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = x[j] - prev;  // zigzag-delta, streamvbyte_zigzag.c:4-6,15-20
+        prev = x[j];
+        z[j] = ((uint32_t)d << 1) ^ (uint32_t)(d >> 31);
+        c[j] = (z[j] > 0xFFu) + (z[j] > 0xFFFFu);  // svb code, streamvbyte_encode.c:31-54 (code 3 unreachable)
+        uint32_t len = 1 + c[j];
+        if (PARTIAL) {
+            const bool valid = lane * 8 + j < nvalid;
+            if (!valid) {
+                c[j] = 0;
+                len = 0;
+            }
+        }
+        off[j] = lane_len;
+        lane_len += len;
+        key |= c[j] << (2 * j);
+        any3 |= c[j];
+    }
+    const uint32_t incl = warp_incl_scan(lane_len, lane);
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    const uint32_t base = dw.pend + incl - lane_len;
+    uint8_t *db = dw.buf + base;
+    const bool three = __any_sync(FULL, (any3 & 2u) != 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        bool valid = true;
+        if (PARTIAL) valid = lane * 8 + j < nvalid;
+        if (valid) {
+            db[off[j]] = (uint8_t)z[j];
+            if (c[j] >= 1) db[off[j] + 1] = (uint8_t)(z[j] >> 8);
+        }
+    }
+    if (three) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c[j] == 2) db[off[j] + 2] = (uint8_t)(z[j] >> 16);
+    }
+    // keys: 2 bits per value, value i -> byte i/4, shift 2*(i%4) (streamvbyte_encode.c:56-79)
+    uint8_t *kb = kw.buf + kw.pend + 2 * lane;
+    if (PARTIAL) {
+        if (lane * 8 < nvalid) kb[0] = (uint8_t)key;
+        if (lane * 8 + 4 < nvalid) kb[1] = (uint8_t)(key >> 8);
+        kw.pend += (nvalid + 3) >> 2;
+    } else {
+        kb[0] = (uint8_t)key;
+        kb[1] = (uint8_t)(key >> 8);
+        kw.pend += 64;
+    }
+    dw.pend += total;
+    __syncwarp();
+    dw.drain(lane);
+    kw.drain(lane);
+}
+
+__global__ void __launch_bounds__(ENC_WARPS * 32) svbzd_encode_kernel(const SvbEncodeArgs a) {
+    __shared__ EncWarpSmem smem[ENC_WARPS];
+    const int lane = threadIdx.x & 31;
+    EncWarpSmem &ws = smem[threadIdx.x >> 5];
+    const uint32_t bar0 = smem_u32(&ws.bar[0]);
+    const uint32_t in0 = smem_u32(&ws.in[0][0]);
+    if (lane == 0) {
+        for (int s = 0; s < ENC_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t q = 0;  // chunks consumed by this warp so far (stage = q & 1, parity = (q >> 1) & 1)
+
+    for (;;) {
+        const uint64_t r = next_work(a.work_counter, lane);
+        if (r >= a.n_reads) break;
+        const uint32_t n = a.n_samples[r];
+        const uint64_t soff = a.sig_off[r];
+        const uint64_t scap = a.sig_off[r + 1] - soff;
+        const uint64_t ooff = a.svb_off[r];
+        const uint64_t ocap = a.svb_off[r + 1] - ooff;
+        const uint32_t nkeys = (n + 3) >> 2;
+        int32_t st = S5B_OK;
+        if ((soff & 7) || scap < n) st = S5B_ERR_ARG;
+        else if (ocap < 4ull + nkeys + 3ull * n) st = S5B_ERR_NOSPACE;
+        if (st != S5B_OK) {
+            if (lane == 0) {
+                a.status[r] = st;
+                a.svb_len[r] = 0;
+            }
+            continue;
+        }
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.sig + soff);
+        uint8_t *dst = a.svb + ooff;
+        // bytes that may be bulk-copied for this read: whole 16-byte granules inside the read's slot
+        // (the slot is a multiple of 8 samples except possibly the last one of the slab)
+        const uint64_t slot_bytes16 = (scap * 2) & ~15ull;
+        const uint64_t n_bytes = (uint64_t)n * 2;
+
+        StreamWriter kw, dw;
+        kw.begin(ws.kbuf, dst);
+        dw.begin(ws.dbuf, dst + 4 + nkeys);
+        if (lane < 4) kw.buf[kw.pend + lane] = (uint8_t)(n >> (8 * lane));  // u32 LE header, slow5_press.c:1074
+        kw.pend += 4;
+        __syncwarp();
+
+        const uint32_t nchunks = (n + ENC_CH_SAMPLES - 1) / ENC_CH_SAMPLES;
+        auto issue = [&](uint32_t k, uint32_t qq) {
+            // chunk k of this read -> stage qq & 1
+            const uint64_t b0 = (uint64_t)k * ENC_CH_BYTES;
+            uint64_t want = n_bytes - b0;
+            if (want > ENC_CH_BYTES) want = ENC_CH_BYTES;
+            want = (want + 15) & ~15ull;
+            uint64_t can = slot_bytes16 > b0 ? slot_bytes16 - b0 : 0;
+            const uint32_t bytes = (uint32_t)(want < can ? want : can);
+            const uint32_t stage = qq & 1;
+            if (lane == 0) {
+                if (bytes) {
+                    mbar_arrive_expect_tx(bar0 + 8 * stage, bytes);
+                    bulk_g2s(in0 + stage * ENC_CH_BYTES, src + b0, bytes, bar0 + 8 * stage);
+                } else {
+                    // nothing bulk-copyable (a < 8-sample tail in the last slot): complete the phase by hand
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * stage) : "memory");
+                }
+            }
+            // the (< 16 byte) part of the chunk the bulk copy could not take is fetched with plain loads
+            // after the wait, see below
+            return bytes;
+        };
+        int carry = 0;  // prev = 0 for the first sample, slow5_press.c:1106
+        uint32_t bytes_cur = nchunks ? issue(0, q) : 0;
+        for (uint32_t k = 0; k < nchunks; ++k) {
+            uint32_t bytes_next = 0;
+            if (k + 1 < nchunks) bytes_next = issue(k + 1, q + 1);
+            const uint32_t stage = q & 1;
+            mbar_wait(bar0 + 8 * stage, (q >> 1) & 1);
+            const uint32_t chunk_samples = min((uint32_t)ENC_CH_SAMPLES, n - k * ENC_CH_SAMPLES);
+            if (bytes_cur < chunk_samples * 2) {
+                // ragged end of the slab: copy the uncovered samples by hand
+                const int16_t *g = a.sig + soff + (uint64_t)k * ENC_CH_SAMPLES;
+                int16_t *s = reinterpret_cast<int16_t *>(ws.in[stage]);
+                for (uint32_t i = bytes_cur / 2 + lane; i < chunk_samples; i += 32) s[i] = g[i];
+                __syncwarp();
+            }
+            const uint4 *in4 = reinterpret_cast<const uint4 *>(ws.in[stage]);
+            const uint32_t full_iters = chunk_samples >> 8;
+            for (uint32_t it = 0; it < full_iters; ++it)
+                enc_iteration<false>(in4[it * 32 + lane], carry, lane, 256, kw, dw);
+            const int tail = chunk_samples & 255;
+            if (tail) enc_iteration<true>(in4[full_iters * 32 + lane], carry, lane, tail, kw, dw);
+            ++q;
+            bytes_cur = bytes_next;
+            __syncwarp();  // every lane is done with this stage before it is refilled
+        }
+        // total = 4 + keys + data; data bytes written = (global bytes drained) + pending
+        const uint64_t data_bytes = (uint64_t)((dw.gbase + dw.pend) - (dst + 4 + nkeys));
+        kw.finish(lane);
+        dw.finish(lane);
+        if (lane == 0) {
+            a.svb_len[r] = (uint32_t)(4 + nkeys + data_bytes);
+            a.status[r] = S5B_OK;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+constexpr int DEC_WARPS = 8;
+constexpr int DEC_BLK = 1024;  // bytes per bulk copy
+constexpr int DEC_NB = 4;      // ring blocks per warp
+constexpr int DEC_RING = DEC_BLK * DEC_NB;
+
+struct __align__(128) DecWarpSmem {
+    uint8_t ring[DEC_RING];
+    unsigned long long bar[DEC_NB];
+};
+
+__device__ __forceinline__ uint32_t zz_dec(uint32_t v) { return (v >> 1) ^ (0u - (v & 1u)); }
+
+template <bool PARTIAL, bool WRAP>
+__device__ __forceinline__ void dec_gather(const uint8_t *ring, uint32_t ri, const uint32_t (&c)[8],
+                                           const uint32_t (&off)[8], const int lane, const int nvalid,
+                                           const bool wide, uint32_t (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        bool valid = true;
+        if (PARTIAL) valid = lane * 8 + j < nvalid;
+        v[j] = 0;
+        if (valid) {
+            const uint32_t p = ri + off[j];
+            if (WRAP) {
+                v[j] = ring[p & (DEC_RING - 1)];
+                if (c[j] >= 1) v[j] |= (uint32_t)ring[(p + 1) & (DEC_RING - 1)] << 8;
+            } else {
+                v[j] = ring[p];
+                if (c[j] >= 1) v[j] |= (uint32_t)ring[p + 1] << 8;
+            }
+        }
+    }
+    if (wide) {  // 3- and 4-byte codes: rare (|delta| >= 32768, or a foreign encoder)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            bool valid = true;
+            if (PARTIAL) valid = lane * 8 + j < nvalid;
+            if (valid && c[j] >= 2) {
+                const uint32_t p = ri + off[j];
+                v[j] |= (uint32_t)ring[(p + 2) & (DEC_RING - 1)] << 16;
+                if (c[j] == 3) v[j] |= (uint32_t)ring[(p + 3) & (DEC_RING - 1)] << 24;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DEC_WARPS * 32) svbzd_decode_kernel(const SvbDecodeArgs a) {
+    __shared__ DecWarpSmem smem[DEC_WARPS];
+    const int lane = threadIdx.x & 31;
+    DecWarpSmem &ws = smem[threadIdx.x >> 5];
+    const uint32_t bar0 = smem_u32(&ws.bar[0]);
+    const uint32_t ring0 = smem_u32(&ws.ring[0]);
+    if (lane == 0) {
+        for (int s = 0; s < DEC_NB; ++s) mbar_init(bar0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase_bits = 0;  // per ring slot: parity of the next completion to wait for
+
+    for (;;) {
+        const uint64_t r = next_work(a.work_counter, lane);
+        if (r >= a.n_reads) break;
+        const uint64_t ioff = a.svb_off[r];
+        const uint32_t ilen = a.svb_len[r];
+        const uint8_t *p = a.svb + ioff;
+        int32_t st = S5B_OK;
+        uint32_t n = 0;
+        if (ilen < 4 || ioff + ilen > a.svb_capacity) {
+            st = S5B_ERR_ARG;
+        } else {
+            n = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);  // :1120
+        }
+        const uint64_t soff = a.sig_off[r];
+        const uint64_t scap = a.sig_off[r + 1] - soff;
+        const uint32_t nkeys = (uint32_t)(((uint64_t)n + 3) >> 2);
+        if (st == S5B_OK) {
+            if (soff & 7) st = S5B_ERR_ARG;
+            else if (4ull + nkeys > ilen) st = S5B_ERR_PRESS;  // keys alone overrun the stream
+            else if (scap < n) st = S5B_ERR_NOSPACE;
+        }
+        if (st != S5B_OK) {
+            if (lane == 0) {
+                a.status[r] = st;
+                a.n_samples[r] = n;
+            }
+            continue;
+        }
+        const uint32_t D = ilen - 4 - nkeys;  // data bytes the stream must consume exactly (:1130-1136)
+        const uint8_t *keys = p + 4;
+        const uint8_t *data = keys + nkeys;
+        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 15u);
+        const uint8_t *data16 = data - skew;
+        // bytes of [data16, ...) that may be bulk-copied: up to the 16-byte granule covering the stream end,
+        // never past the slab
+        uint64_t lim = ((uint64_t)skew + D + 15) & ~15ull;
+        {
+            const uint64_t room = a.svb_capacity - (uint64_t)(data16 - a.svb);
+            if (lim > room) lim = room & ~15ull;
+        }
+        const uint32_t nblk = D ? (uint32_t)((lim + DEC_BLK - 1) / DEC_BLK) : 0;
+        uint32_t issued = 0, waited = 0;
+        auto issue_block = [&]() {
+            const uint32_t slot = issued % DEC_NB;
+            const uint64_t b0 = (uint64_t)issued * DEC_BLK;
+            uint64_t bytes = lim - b0;
+            if (bytes > DEC_BLK) bytes = DEC_BLK;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar0 + 8 * slot, (uint32_t)bytes);
+                bulk_g2s(ring0 + slot * DEC_BLK, data16 + b0, (uint32_t)bytes, bar0 + 8 * slot);
+            }
+            ++issued;
+        };
+        while (issued < nblk && issued < DEC_NB) issue_block();
+
+        int16_t *out = a.sig + soff;
+        uint32_t pos = 0;  // data bytes consumed
+        uint32_t acc = 0;  // running sum, prev = 0 (slow5_press.c:1162)
+        const uint32_t iters = (n + 255) >> 8;
+        // keys of the first iteration
+        uint32_t kk = 0;
+        {
+            const uint32_t ki = 2 * lane;
+            if (ki < nkeys) kk = __ldg(keys + ki);
+            if (ki + 1 < nkeys) kk |= (uint32_t)__ldg(keys + ki + 1) << 8;
+        }
+        bool bad = false;
+        for (uint32_t it = 0; it < iters; ++it) {
+            const uint32_t k_now = kk;
+            {  // prefetch the next iteration's control bytes
+                const uint32_t ki = (it + 1) * 64 + 2 * lane;
+                kk = 0;
+                if (ki < nkeys) kk = __ldg(keys + ki);
+                if (ki + 1 < nkeys) kk |= (uint32_t)__ldg(keys + ki + 1) << 8;
+            }
+            const int nvalid = (int)min(256u, n - it * 256);
+            const bool partial = nvalid < 256;
+            uint32_t c[8], off[8];
+            uint32_t lane_len = 0, anyc = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = (k_now >> (2 * j)) & 3u;
+                uint32_t len = 1 + c[j];
+                if (partial && lane * 8 + j >= nvalid) {
+                    len = 0;
+                    c[j] = 0;
+                }
+                off[j] = lane_len;
+                lane_len += len;
+                anyc |= c[j];
+            }
+            // prefix scan over the control-byte lengths -> per-lane data offsets
+            const uint32_t incl = warp_incl_scan(lane_len, lane);
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (pos + total > D) {  // stream claims more data than it holds
+                bad = true;
+                break;
+            }
+            const uint32_t need = (skew + pos + total + DEC_BLK - 1) / DEC_BLK;
+            while (waited < need) {
+                const uint32_t slot = waited % DEC_NB;
+                mbar_wait(bar0 + 8 * slot, (phase_bits >> slot) & 1u);
+                phase_bits ^= 1u << slot;
+                ++waited;
+            }
+            const uint32_t ri = (skew + pos + incl - lane_len) & (DEC_RING - 1);
+            const bool wrap = __any_sync(FULL, ri + lane_len > DEC_RING);
+            const bool wide = __any_sync(FULL, (anyc & 2u) != 0);
+            uint32_t v[8];
+            if (partial) {
+                dec_gather<true, true>(ws.ring, ri, c, off, lane, nvalid, wide, v);
+            } else if (wrap) {
+                dec_gather<false, true>(ws.ring, ri, c, off, lane, nvalid, wide, v);
+            } else {
+                dec_gather<false, false>(ws.ring, ri, c, off, lane, nvalid, wide, v);
+            }
+            // zigzag decode + running sum (streamvbyte_zigzag.c:23-25,34-40); mod 2^32 arithmetic, the
+            // truncating int16 store keeps the low 16 bits
+            uint32_t s[8];
+            uint32_t run = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                run += zz_dec(v[j]);
+                s[j] = run;
+            }
+            const uint32_t incl_sum = warp_incl_scan(run, lane);
+            const uint32_t base = acc + incl_sum - run;
+            acc += __shfl_sync(FULL, incl_sum, 31);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += base;
+            int16_t *o = out + (uint64_t)it * 256 + lane * 8;
+            if (!partial) {
+                uint4 w;
+                w.x = __byte_perm(s[0], s[1], 0x5410);
+                w.y = __byte_perm(s[2], s[3], 0x5410);
+                w.z = __byte_perm(s[4], s[5], 0x5410);
+                w.w = __byte_perm(s[6], s[7], 0x5410);
+                *reinterpret_cast<uint4 *>(o) = w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (lane * 8 + j < nvalid) o[j] = (int16_t)(uint16_t)s[j];
+            }
+            pos += total;
+            __syncwarp();  // all lanes have finished reading the ring before blocks are recycled
+            const uint32_t done_blocks = (skew + pos) / DEC_BLK;
+            while (issued < nblk && issued < done_blocks + DEC_NB) issue_block();
+        }
+        // drain copies that were issued but never needed (only possible for a malformed stream)
+        while (waited < issued) {
+            const uint32_t slot = waited % DEC_NB;
+            mbar_wait(bar0 + 8 * slot, (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            ++waited;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            a.n_samples[r] = n;
+            a.status[r] = (bad || pos != D) ? S5B_ERR_PRESS : S5B_OK;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// peek: u32 headers only
+// ------------------------------------------------------------------------------------------------
+__global__ void svbzd_peek_kernel(const uint8_t *svb, const uint64_t *svb_off, const uint32_t *svb_len,
+                                  uint64_t n_reads, uint32_t *n_samples) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint32_t n = 0;
+    if (svb_len[r] >= 4) {
+        const uint8_t *p = svb + svb_off[r];
+        n = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+    n_samples[r] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense gather (slot layout -> packed slab): three-kernel exclusive scan of the rounded lengths,
+// then one warp per stream copies it
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 1024;
+
+__device__ __forceinline__ uint64_t round_up_u64(uint64_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+__device__ uint64_t block_incl_scan(uint64_t v, uint64_t *warp_sums /*[32]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_sums[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = warp_sums[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t t = __shfl_up_sync(FULL, w, d);
+            if (lane >= d) w += t;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    if (wid > 0) v += warp_sums[wid - 1];
+    return v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_block_sums_kernel(const uint32_t *len, uint64_t n, uint32_t align,
+                                                                 uint64_t *block_sums) {
+    __shared__ uint64_t ws[32];
+    const uint64_t i = (uint64_t)blockIdx.x * SCAN_T + threadIdx.x;
+    uint64_t v = i < n ? round_up_u64(len[i], align) : 0;
+    v = block_incl_scan(v, ws);
+    if (threadIdx.x == SCAN_T - 1) block_sums[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(SCAN_T) scan_top_kernel(uint64_t *block_sums, uint64_t nblocks) {
+    __shared__ uint64_t ws[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < nblocks; base += SCAN_T) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < nblocks ? block_sums[i] : 0;
+        const uint64_t incl = block_incl_scan(v, ws);
+        const uint64_t carry = carry_s;
+        if (i < nblocks) block_sums[i] = carry + incl - v;  // exclusive
+        __syncthreads();
+        if (threadIdx.x == SCAN_T - 1) carry_s = carry + incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SCAN_T) scan_write_kernel(const uint32_t *len, uint64_t n, uint32_t align,
+                                                            const uint64_t *block_sums, uint64_t *off) {
+    __shared__ uint64_t ws[32];
+    const uint64_t i = (uint64_t)blockIdx.x * SCAN_T + threadIdx.x;
+    const uint64_t v = i < n ? round_up_u64(len[i], align) : 0;
+    const uint64_t incl = block_incl_scan(v, ws) + block_sums[blockIdx.x];
+    if (i < n) {
+        off[i] = incl - v;
+        if (i == n - 1) off[n] = incl;
+    }
+}
+
+constexpr int COPY_WARPS = 8;
+__global__ void __launch_bounds__(COPY_WARPS * 32) gather_copy_kernel(const uint8_t *src, const uint64_t *src_off,
+                                                                      const uint32_t *len, uint64_t n_reads,
+                                                                      uint8_t *dst, const uint64_t *dst_off) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * COPY_WARPS + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * COPY_WARPS;
+    for (uint64_t r = warp; r < n_reads; r += nwarps) {
+        const uint8_t *s = src + src_off[r];
+        uint8_t *d = dst + dst_off[r];
+        const uint32_t n = len[r];
+        if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15u) == 0) {
+            const uint32_t n16 = n >> 4;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+            uint4 *d4 = reinterpret_cast<uint4 *>(d);
+            for (uint32_t i = lane; i < n16; i += 32) d4[i] = s4[i];
+            for (uint32_t i = (n16 << 4) + lane; i < n; i += 32) d[i] = s[i];
+        } else {
+            for (uint32_t i = lane; i < n; i += 32) d[i] = s[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int svbzd_encode_blocks_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, svbzd_encode_kernel, ENC_WARPS * 32, 0) != cudaSuccess)
+        return 0;
+    return n;
+}
+int svbzd_decode_blocks_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, svbzd_decode_kernel, DEC_WARPS * 32, 0) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+static unsigned persistent_grid(uint64_t n_reads, int warps, int num_sms, int blocks_per_sm) {
+    uint64_t want = (n_reads + warps - 1) / warps;
+    uint64_t cap = (uint64_t)num_sms * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+    uint64_t g = want < cap ? want : cap;
+    return (unsigned)(g ? g : 1);
+}
+
+cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    svbzd_encode_kernel<<<persistent_grid(a.n_reads, ENC_WARPS, num_sms, blocks_per_sm), ENC_WARPS * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    svbzd_decode_kernel<<<persistent_grid(a.n_reads, DEC_WARPS, num_sms, blocks_per_sm), DEC_WARPS * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_svbzd_peek(const uint8_t *svb, const uint64_t *svb_off, const uint32_t *svb_len, uint64_t n_reads,
+                              uint32_t *n_samples, cudaStream_t st) {
+    if (n_reads == 0) return cudaSuccess;
+    svbzd_peek_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(svb, svb_off, svb_len, n_reads, n_samples);
+    return cudaGetLastError();
+}
+
+size_t compact_scratch_bytes(uint64_t n_reads) { return ((n_reads + SCAN_T - 1) / SCAN_T + 1) * sizeof(uint64_t); }
+
+cudaError_t launch_compact(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n_reads,
+                           uint32_t align, uint8_t *dst, uint64_t *dst_off, void *scratch, cudaStream_t st,
+                           int *n_launches) {
+    *n_launches = 0;
+    if (n_reads == 0) return cudaMemsetAsync(dst_off, 0, sizeof(uint64_t), st);
+    uint64_t *block_sums = static_cast<uint64_t *>(scratch);
+    const uint64_t nblocks = (n_reads + SCAN_T - 1) / SCAN_T;
+    scan_block_sums_kernel<<<(unsigned)nblocks, SCAN_T, 0, st>>>(len, n_reads, align, block_sums);
+    scan_top_kernel<<<1, SCAN_T, 0, st>>>(block_sums, nblocks);
+    scan_write_kernel<<<(unsigned)nblocks, SCAN_T, 0, st>>>(len, n_reads, align, block_sums, dst_off);
+    uint64_t g = (n_reads + COPY_WARPS - 1) / COPY_WARPS;
+    if (g > 148ull * 8 * 4) g = 148ull * 8 * 4;
+    gather_copy_kernel<<<(unsigned)g, COPY_WARPS * 32, 0, st>>>(src, src_off, len, n_reads, dst, dst_off);
+    *n_launches = 4;
+    return cudaGetLastError();
+}
+
+}  // namespace s5b
