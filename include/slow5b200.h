@@ -66,7 +66,8 @@ uint64_t s5b_svbzd_bound(uint32_t n_samples);
 uint64_t s5b_svbzd_slot(uint32_t n_samples);
 
 /* ---- level 3: device-resident batches ------------------------------------------------------
- * All d_* pointers are device pointers; `stream` is a cudaStream_t (NULL = the context's stream).
+ * All d_* pointers are device pointers; `stream` is a cudaStream_t.  NULL selects the context's own
+ * (non-blocking) stream; pass cudaStreamLegacy ((void*)0x1) to run on the legacy default stream.
  * Calls are asynchronous with respect to the host: results are valid once `stream` is synced.
  *
  * Layout contract ("slab + offsets", the device twin of slow5_batch_t's mem_records[]/mem_bytes[],

@@ -74,7 +74,11 @@ class Codec:
 
     @staticmethod
     def _stream():
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # torch's default stream has handle 0, which the C-ABI reads as "use the context's own stream";
+        # name the legacy default stream explicitly (cudaStreamLegacy == 0x1) so launches are ordered with
+        # torch's work and visible to torch.cuda.Event
+        h = torch.cuda.current_stream().cuda_stream
+        return C.c_void_p(h if h else 1)
 
     # ---- device-resident ---------------------------------------------------------------------
     def svbzd_encode_dev(self, sig, sig_off, n_samples, svb, svb_off, svb_len, status):
