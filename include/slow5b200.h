@@ -102,6 +102,16 @@ int s5b_svbzd_decode_dev(s5b_ctx_t *ctx,
 int s5b_svbzd_peek_dev(s5b_ctx_t *ctx, const uint8_t *d_svb, const uint64_t *d_svb_off,
                        const uint32_t *d_svb_len, uint64_t n_reads, uint32_t *d_n_samples, void *stream);
 
+/* Replaces ptr_depress_zlib_solo (slow5_press.c:973-1010: inflateInit2(15) + inflate loop) for a batch of
+ * independent zlib streams (one per record, slow5.c:4046).  Stream r = d_in[d_in_off[r] .. +d_in_len[r])
+ * (any alignment; d_in base 16-byte aligned, in_capacity a multiple of 16); its output goes to the slot
+ * [d_out_off[r], d_out_off[r+1]).  d_status[r]: 0; S5B_ERR_PRESS for what zlib reports as Z_DATA_ERROR /
+ * Z_NEED_DICT; S5B_ERR_NOSPACE when the slot is too small -- d_out_len[r] then holds the size the stream
+ * needs.  As in the reference, input that ends early is not an error: the bytes decoded so far are returned. */
+int s5b_zlib_inflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                         uint64_t in_capacity, uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off,
+                         uint32_t *d_out_len, int32_t *d_status, void *stream);
+
 /* Gathers slotted streams into a dense slab: d_dst_off[r] (n_reads+1 entries, exclusive scan of
  * len rounded up to `align`, align in {1,16}) and the copied bytes.  d_dst capacity is checked
  * against dst_capacity (S5B_ERR_NOSPACE is reported through the return of the host wrappers). */

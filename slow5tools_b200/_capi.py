@@ -87,3 +87,6 @@ def free(ptr):
 
 def strerror(code):
     return lib.s5b_strerror(int(code)).decode()
+
+lib.s5b_zlib_inflate_dev.restype = C.c_int
+lib.s5b_zlib_inflate_dev.argtypes = [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]

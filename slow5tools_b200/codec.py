@@ -96,6 +96,11 @@ class Codec:
         self._check(lib.s5b_svbzd_peek_dev(self._h, _ptr(svb), _ptr(svb_off), _ptr(svb_len), svb_len.numel(),
                                            _ptr(n_samples), self._stream()), "s5b_svbzd_peek_dev")
 
+    def zlib_inflate_dev(self, zin, in_off, in_len, out, out_off, out_len, status):
+        self._check(lib.s5b_zlib_inflate_dev(self._h, _ptr(zin), _ptr(in_off), _ptr(in_len), zin.numel(),
+                                             in_len.numel(), _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status),
+                                             self._stream()), "s5b_zlib_inflate_dev")
+
     def compact_dev(self, src, src_off, length, dst, dst_off, align=16):
         self._check(lib.s5b_compact_dev(self._h, _ptr(src), _ptr(src_off), _ptr(length), length.numel(), align,
                                         _ptr(dst), _ptr(dst_off), self._stream()), "s5b_compact_dev")

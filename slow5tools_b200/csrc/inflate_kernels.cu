@@ -1,0 +1,771 @@
+// inflate_kernels.cu -- sm_100a zlib/DEFLATE decoder, one warp per record stream.
+//
+// Replaces, for whole batches, ptr_depress_zlib_solo (slow5lib/src/slow5_press.c:973-1010), i.e.
+// inflateInit2(15) + inflate(Z_NO_FLUSH) loop + inflateEnd from system zlib, with the same observable
+// behaviour: RFC 1950 header check, stored / fixed / dynamic blocks, 32 KiB window, Adler-32 check;
+// malformed data -> S5B_ERR_PRESS (zlib's Z_DATA_ERROR / Z_NEED_DICT arms, :993-999); input that ends
+// early is NOT an error there (Z_BUF_ERROR / Z_OK fall through, :1001-1003) and yields the bytes decoded
+// so far -- mirrored here; bytes after the Adler-32 trailer are ignored.
+//
+// Every record is an independent complete zlib stream (slow5.c:4046, slow5_press.c:868-871), so the
+// parallelism is across records: one warp per stream.  Within a warp lane 0 runs the serial Huffman
+// decode out of shared memory (input staged by 1-D bulk async copies into a per-warp ring, 10-bit /
+// 8-bit first-level lookup tables built cooperatively per block); all lanes cooperate on table
+// construction, long LZ77 copies, the Adler-32 and the 128-bit coalesced stores of the output staging
+// buffer.  Latency/issue bound, far from the HBM roofline by nature -- see DESIGN.md.
+#include "s5b_kernels.h"
+#include "s5b_ptx.cuh"
+#include "../../include/slow5b200.h"
+
+namespace s5b {
+
+namespace {
+
+constexpr int INF_WARPS = 4;
+constexpr int INF_BLK = 1024;  // input ring block
+constexpr int INF_NB = 2;
+constexpr int INF_RING = INF_BLK * INF_NB;
+constexpr int INF_STAGE = 4096;  // output staging bytes (a multiple of 16)
+constexpr int LIT_FAST_BITS = 10;
+constexpr int DIST_FAST_BITS = 8;
+constexpr uint32_t ADLER_MOD = 65521u;
+
+struct __align__(128) InfWarpSmem {
+    uint8_t ring[INF_RING];
+    uint8_t stage[INF_STAGE + 16];
+    uint16_t lit_fast[1 << LIT_FAST_BITS];    // (symbol << 4) | code length, 0 = not a short code
+    uint16_t dist_fast[1 << DIST_FAST_BITS];
+    uint16_t lit_sorted[288];                 // symbols ordered by (length, symbol)
+    uint16_t dist_sorted[32];
+    uint16_t lit_count[16];
+    uint16_t dist_count[16];
+    uint16_t cl_fast[128];
+    uint16_t cl_sorted[20];
+    uint16_t cl_count[16];
+    uint16_t tmp_base[16];
+    uint8_t lens[384];                        // code lengths: lit/len at 0, dist at 288; scratch from 32
+    unsigned long long bar[INF_NB];
+};
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31,
+                                        35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+                                         1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8,
+                                         9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// events lane 0 raises for the whole warp
+enum : uint32_t { EV_FLUSH = 1, EV_MATCH = 2, EV_TABLES = 3, EV_END = 4 };
+// how a stream ended
+enum : int32_t { END_OK = 0, END_TRUNC = 1, END_ERR = 2 };
+
+// ---- input side (lane 0 only) ----------------------------------------------------------------
+struct BitReader {
+    const uint8_t *ring;     // smem
+    const uint8_t *src16;    // 16-byte aligned global address of ring position 0
+    uint64_t lim;            // bulk-copyable bytes from src16
+    uint32_t bar0, ring0;    // smem addresses
+    uint32_t nblk, issued, waited, phase_bits;
+    uint32_t skew;           // stream byte 0 is at ring position skew
+    uint32_t in_len;         // stream bytes
+    uint32_t ipos;           // stream bytes moved into the bit buffer
+    uint64_t bb;
+    uint32_t nb;
+
+    __device__ __forceinline__ void issue_block() {
+        const uint32_t slot = issued % INF_NB;
+        const uint64_t b0 = (uint64_t)issued * INF_BLK;
+        uint64_t bytes = lim - b0;
+        if (bytes > INF_BLK) bytes = INF_BLK;
+        mbar_arrive_expect_tx(bar0 + 8 * slot, (uint32_t)bytes);
+        bulk_g2s(ring0 + slot * INF_BLK, src16 + b0, (uint32_t)bytes, bar0 + 8 * slot);
+        ++issued;
+    }
+    // a ring block may only be overwritten once every byte of it has been moved into bb
+    __device__ __forceinline__ void recycle() {
+        const uint32_t done = (skew + ipos) / INF_BLK;
+        while (issued < nblk && issued < done + INF_NB) issue_block();
+    }
+    // make ring position rp readable
+    __device__ __forceinline__ void ensure(uint32_t rp) {
+        const uint32_t need = rp / INF_BLK + 1;
+        while (waited < need) {
+            recycle();
+            const uint32_t slot = waited % INF_NB;
+            mbar_wait(bar0 + 8 * slot, (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            ++waited;
+        }
+    }
+    __device__ __forceinline__ void refill() {
+        if (nb > 32) return;
+        uint32_t rp = skew + ipos;
+        if ((rp & 3u) == 0 && ipos + 4 <= in_len) {
+            ensure(rp + 3);
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(ring + (rp & (INF_RING - 1)));
+            bb |= (uint64_t)w << nb;
+            nb += 32;
+            ipos += 4;
+            if (((skew + ipos) & (INF_BLK - 1)) == 0) recycle();
+        } else {
+            while (nb <= 56 && ipos < in_len) {
+                ensure(rp);
+                bb |= (uint64_t)ring[rp & (INF_RING - 1)] << nb;
+                nb += 8;
+                ++ipos;
+                ++rp;
+            }
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)bb & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(uint32_t n) {
+        bb >>= n;
+        nb -= n;
+    }
+    // drain copies that were issued but never consumed (stream ended early / trailing bytes)
+    __device__ __forceinline__ void drain() {
+        while (waited < issued) {
+            const uint32_t slot = waited % INF_NB;
+            mbar_wait(bar0 + 8 * slot, (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            ++waited;
+        }
+    }
+};
+
+// canonical (bit-serial) decode for codes longer than the fast table; returns symbol or -1 (invalid code)
+// or -2 (ran out of bits)
+__device__ __forceinline__ int slow_decode(const BitReader &br, const uint16_t *count, const uint16_t *sorted,
+                                           uint32_t *used) {
+    uint32_t code = 0, first = 0, index = 0;
+    uint64_t b = br.bb;
+    for (uint32_t len = 1; len <= 15; ++len) {
+        if (len > br.nb) return -2;
+        code |= (uint32_t)(b & 1u);
+        b >>= 1;
+        const uint32_t cnt = count[len];
+        if (code < first + cnt) {  // first <= code always holds here
+            *used = len;
+            return sorted[index + (code - first)];
+        }
+        index += cnt;
+        first += cnt;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+// ---- Huffman table construction (whole warp) ----------------------------------------------------
+// lens[0..n): code lengths (0 = unused).  Builds count[], sorted[] (canonical order) and the first-level
+// table fast[] of 2^fast_bits entries.  Returns 0 ok, 1 over-subscribed, 2 incomplete (caller decides,
+// zlib's inflate_table rules: inftrees.c).
+__device__ int build_table(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *fast,
+                           int fast_bits, uint16_t *base /*[16] scratch*/, int lane, int *max_len_out) {
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) {
+        const uint32_t l = lens[s];
+        if (l) atomicAdd(reinterpret_cast<unsigned int *>(count) + (l >> 1), (l & 1) ? 0x10000u : 1u);
+    }
+    __syncwarp();
+    // Kraft check + first index per length (serial over 15 lengths; every lane computes the same values)
+    int left = 1, status = 0, maxl = 0;
+    uint32_t idx = 0;
+    uint32_t first_idx[16];
+    uint32_t first_code[16];
+    uint32_t code = 0;
+    first_idx[0] = 0;
+    first_code[0] = 0;
+#pragma unroll
+    for (int l = 1; l <= 15; ++l) {
+        const int c = count[l];
+        left <<= 1;
+        left -= c;
+        if (left < 0) status = 1;
+        if (c) maxl = l;
+        first_idx[l] = idx;
+        first_code[l] = code;
+        idx += c;
+        code = (code + c) << 1;
+    }
+    if (status == 0 && left > 0) status = 2;
+    *max_len_out = maxl;
+    if (status == 1) return 1;
+    if (lane < 16) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int l = 1; l <= 15; ++l)
+            if (l == lane) v = first_idx[l];
+        base[lane] = (uint16_t)v;
+    }
+    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    __syncwarp();
+    // rank of each symbol inside its length class, in symbol order, 32 symbols at a time
+    for (int s0 = 0; s0 < n; s0 += 32) {
+        const int s = s0 + lane;
+        const uint32_t l = s < n ? lens[s] : 0;
+        const unsigned same = __match_any_sync(FULL, l);
+        if (l) {
+            const uint32_t rank = base[l] + __popc(same & ((1u << lane) - 1u));
+            sorted[rank] = (uint16_t)s;
+            if ((int)l <= fast_bits) {
+                uint32_t fc = 0, fi = 0;
+#pragma unroll
+                for (int k = 1; k <= 15; ++k)
+                    if (k == (int)l) {
+                        fc = first_code[k];
+                        fi = first_idx[k];
+                    }
+                const uint32_t cw = fc + (rank - fi);           // canonical code, MSB first
+                const uint32_t rev = __brev(cw) >> (32 - l);    // as it appears in the LSB-first bit stream
+                const uint16_t e = (uint16_t)((s << 4) | l);
+                for (uint32_t i = rev; i < (1u << fast_bits); i += (1u << l)) fast[i] = e;
+            }
+        }
+        __syncwarp();
+        if (l && __ffs(same) - 1 == lane) base[l] += (uint16_t)__popc(same);  // one leader per length class
+        __syncwarp();
+    }
+    return status;
+}
+
+// ---- Adler-32 over n staged bytes (whole warp) -----------------------------------------------
+__device__ __forceinline__ void adler_update(uint32_t &a, uint32_t &b, const uint8_t *p, uint32_t n, int lane) {
+    const uint32_t per = (n + 31) / 32;
+    const uint32_t start = min(n, per * lane), end = min(n, start + per);
+    uint32_t s1 = 0, s2 = 0;
+    for (uint32_t i = start; i < end; ++i) {
+        const uint32_t d = p[i];
+        s1 += d;
+        s2 += (end - i) * d;
+    }
+    uint32_t contrib = (uint32_t)(((uint64_t)(n - end) * s1 + s2) % ADLER_MOD);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        s1 += __shfl_xor_sync(FULL, s1, d);
+        contrib += __shfl_xor_sync(FULL, contrib, d);
+    }
+    b = (uint32_t)((b + (uint64_t)n * a + contrib) % ADLER_MOD);
+    a = (a + s1) % ADLER_MOD;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    InfWarpSmem &ws = reinterpret_cast<InfWarpSmem *>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(&ws.bar[0]);
+    if (lane == 0) {
+        for (int s = 0; s < INF_NB; ++s) mbar_init(bar0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase_bits = 0;
+
+    for (;;) {
+        unsigned long long r = 0;
+        if (lane == 0) r = atomicAdd(a.work_counter, 1ULL);
+        r = __shfl_sync(FULL, r, 0);
+        if (r >= a.n_reads) break;
+        const uint64_t ioff = a.in_off[r];
+        const uint32_t ilen = a.in_len[r];
+        const uint64_t ooff = a.out_off[r];
+        const uint64_t ocap = a.out_off[r + 1] - ooff;
+        if (ioff + ilen > a.in_capacity) {
+            if (lane == 0) {
+                a.status[r] = S5B_ERR_ARG;
+                a.out_len[r] = 0;
+            }
+            continue;
+        }
+        uint8_t *dst = a.out + ooff;
+
+        // ---- input side: only lane 0 ever advances it
+        BitReader br;
+        {
+            const uint8_t *p = a.in + ioff;
+            br.ring = ws.ring;
+            br.skew = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+            br.src16 = p - br.skew;
+            br.lim = ((uint64_t)br.skew + ilen + 15) & ~15ull;
+            const uint64_t room = a.in_capacity - (uint64_t)(br.src16 - a.in);
+            if (br.lim > room) br.lim = room & ~15ull;
+            br.bar0 = bar0;
+            br.ring0 = smem_u32(&ws.ring[0]);
+            br.nblk = ilen ? (uint32_t)((br.lim + INF_BLK - 1) / INF_BLK) : 0;
+            br.issued = br.waited = 0;
+            br.phase_bits = phase_bits;
+            br.in_len = ilen;
+            br.ipos = 0;
+            br.bb = 0;
+            br.nb = 0;
+            if (lane == 0) br.recycle();
+        }
+        // ---- output staging (warp-uniform): stage[i] <-> global gbase[i], gbase 16-byte aligned.
+        //   [vstart, spos) valid bytes not yet stored, [astart, spos) not yet counted in total / Adler-32.
+        //   absolute output position of stage[i] = total - astart + i.
+        uint32_t vstart = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+        uint8_t *gbase = dst - vstart;
+        uint32_t astart = vstart, spos = vstart;
+        uint64_t total = 0;
+        bool store = true;  // false once the slot overflowed: count only
+        uint32_t ad_a = 1, ad_b = 0;
+        int32_t end_kind = END_OK;
+        bool stream_done = false;
+        // lane-0 block state
+        bool last_block = false, in_block = false;
+        uint32_t stored_left = 0, btype = 0;
+
+        // ---- zlib header (RFC 1950), lane 0
+        if (lane == 0) {
+            br.refill();
+            if (br.nb < 16) {
+                end_kind = END_TRUNC;
+            } else {
+                const uint32_t cmf = br.peek(8), flg = br.peek(16) >> 8;
+                br.drop(16);
+                if (((cmf << 8) | flg) % 31u != 0 || (cmf & 15u) != 8 || (cmf >> 4) > 7 || (flg & 0x20u)) end_kind = END_ERR;
+            }
+        }
+        end_kind = __shfl_sync(FULL, end_kind, 0);
+        stream_done = end_kind != END_OK;
+
+        while (!stream_done) {
+            uint32_t ev = 0, ev_a = 0, ev_b = 0;
+            if (lane == 0) {
+                // ---- decode until something needs the whole warp
+                for (;;) {
+                    if (!in_block) {
+                        if (last_block) {
+                            // Adler-32 trailer: big endian, byte aligned, after the final block
+                            ev = EV_END;
+                            ev_a = END_OK;
+                            br.drop(br.nb & 7u);
+                            br.refill();
+                            if (br.nb < 32) {
+                                ev_a = END_TRUNC;
+                            } else {
+                                ev_b = __byte_perm((uint32_t)br.bb, 0, 0x0123);
+                                br.drop(32);
+                            }
+                            break;
+                        }
+                        br.refill();
+                        if (br.nb < 3) {
+                            ev = EV_END;
+                            ev_a = END_TRUNC;
+                            break;
+                        }
+                        last_block = br.peek(1);
+                        btype = br.peek(3) >> 1;
+                        br.drop(3);
+                        if (btype == 3) {  // "invalid block type"
+                            ev = EV_END;
+                            ev_a = END_ERR;
+                            break;
+                        }
+                        if (btype == 0) {
+                            br.drop(br.nb & 7u);
+                            br.refill();
+                            if (br.nb < 32) {
+                                ev = EV_END;
+                                ev_a = END_TRUNC;
+                                break;
+                            }
+                            const uint32_t len = br.peek(16), nlen = (uint32_t)(br.bb >> 16) & 0xffffu;
+                            br.drop(32);
+                            if ((len ^ 0xffffu) != nlen) {  // "invalid stored block lengths"
+                                ev = EV_END;
+                                ev_a = END_ERR;
+                                break;
+                            }
+                            stored_left = len;
+                            in_block = true;
+                            continue;
+                        }
+                        ev = EV_TABLES;  // fixed or dynamic: the warp builds the tables
+                        break;
+                    }
+                    if (btype == 0) {
+                        // stored bytes travel through the bit buffer like literals (rare path)
+                        if (stored_left == 0) {
+                            in_block = false;
+                            continue;
+                        }
+                        br.refill();
+                        if (br.nb < 8) {
+                            ev = EV_END;
+                            ev_a = END_TRUNC;
+                            break;
+                        }
+                        if (store) ws.stage[spos] = (uint8_t)br.peek(8);
+                        br.drop(8);
+                        ++spos;
+                        --stored_left;
+                        if (spos >= INF_STAGE) {
+                            ev = EV_FLUSH;
+                            break;
+                        }
+                        continue;
+                    }
+                    // ---- Huffman-coded symbol
+                    br.refill();
+                    uint32_t e = ws.lit_fast[br.peek(LIT_FAST_BITS)];
+                    uint32_t l = e & 15u;
+                    int sym = (int)(e >> 4);
+                    if (l == 0) {
+                        sym = slow_decode(br, ws.lit_count, ws.lit_sorted, &l);
+                        if (sym < 0) {
+                            ev = EV_END;
+                            ev_a = sym == -2 ? END_TRUNC : END_ERR;
+                            break;
+                        }
+                    } else if (l > br.nb) {
+                        ev = EV_END;
+                        ev_a = END_TRUNC;
+                        break;
+                    }
+                    if (sym < 256) {
+                        br.drop(l);
+                        if (store) ws.stage[spos] = (uint8_t)sym;
+                        ++spos;
+                        if (spos >= INF_STAGE) {
+                            ev = EV_FLUSH;
+                            break;
+                        }
+                        continue;
+                    }
+                    if (sym == 256) {
+                        br.drop(l);
+                        in_block = false;
+                        continue;
+                    }
+                    if (sym > 285) {  // "invalid literal/length code"
+                        ev = EV_END;
+                        ev_a = END_ERR;
+                        break;
+                    }
+                    // length / distance pair: nothing is consumed for good until the whole pair is available
+                    const uint64_t save_bb = br.bb;
+                    const uint32_t save_nb = br.nb, save_ipos = br.ipos;
+                    br.drop(l);
+                    const uint32_t li = (uint32_t)sym - 257u;
+                    const uint32_t lx = c_len_extra[li];
+                    bool trunc = br.nb < lx;
+                    uint32_t mlen = 0;
+                    int dsym = 0;
+                    uint32_t dl = 0, dist = 0;
+                    bool err = false;
+                    if (!trunc) {
+                        mlen = c_len_base[li] + br.peek(lx);
+                        br.drop(lx);
+                        br.refill();
+                        const uint32_t de = ws.dist_fast[br.peek(DIST_FAST_BITS)];
+                        dl = de & 15u;
+                        dsym = (int)(de >> 4);
+                        if (dl == 0) {
+                            dsym = slow_decode(br, ws.dist_count, ws.dist_sorted, &dl);
+                            if (dsym == -1) err = true;
+                            if (dsym == -2) trunc = true;
+                        } else if (dl > br.nb) {
+                            trunc = true;
+                        }
+                    }
+                    if (!trunc && !err) {
+                        if (dsym > 29) {  // "invalid distance code"
+                            err = true;
+                        } else {
+                            br.drop(dl);
+                            const uint32_t dx = c_dist_extra[dsym];
+                            if (br.nb < dx) {
+                                trunc = true;
+                            } else {
+                                dist = c_dist_base[dsym] + br.peek(dx);
+                                br.drop(dx);
+                            }
+                        }
+                    }
+                    if (err) {
+                        ev = EV_END;
+                        ev_a = END_ERR;
+                        break;
+                    }
+                    if (trunc) {
+                        // (the refill above may have advanced ipos; the saved buffer is a prefix of the new one,
+                        //  so only bb/nb/ipos need restoring and the stream simply ends here)
+                        br.bb = save_bb;
+                        br.nb = save_nb;
+                        br.ipos = save_ipos;
+                        ev = EV_END;
+                        ev_a = END_TRUNC;
+                        break;
+                    }
+                    if ((uint64_t)dist > total + (spos - astart)) {  // "invalid distance too far back"
+                        ev = EV_END;
+                        ev_a = END_ERR;
+                        break;
+                    }
+                    if (!store) {
+                        spos += mlen;  // counting only; folded into `total` at the next flush event
+                        if (spos >= INF_STAGE) {
+                            ev = EV_FLUSH;
+                            break;
+                        }
+                        continue;
+                    }
+                    if (mlen <= 12 && dist <= spos - vstart && spos + mlen <= INF_STAGE) {
+                        // short, near match: lane 0 copies it byte by byte (overlap-safe)
+                        for (uint32_t i = 0; i < mlen; ++i) ws.stage[spos + i] = ws.stage[spos - dist + i];
+                        spos += mlen;
+                        if (spos >= INF_STAGE) {
+                            ev = EV_FLUSH;
+                            break;
+                        }
+                        continue;
+                    }
+                    ev = EV_MATCH;
+                    ev_a = mlen;
+                    ev_b = dist;
+                    break;
+                }
+            }
+            __syncwarp();
+            ev = __shfl_sync(FULL, ev, 0);
+            ev_a = __shfl_sync(FULL, ev_a, 0);
+            ev_b = __shfl_sync(FULL, ev_b, 0);
+            spos = __shfl_sync(FULL, spos, 0);
+
+            if (ev == EV_TABLES) {
+                // ---- fixed (btype 1) or dynamic (btype 2) code tables
+                const uint32_t bt = __shfl_sync(FULL, btype, 0);
+                int hlit = 288, hdist = 30, bad = 0;  // bad: 2 = data error, 3 = input ended
+                if (bt == 1) {
+                    for (int s = lane; s < 288; s += 32) ws.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+                    if (lane < 30) ws.lens[288 + lane] = 5;
+                    __syncwarp();
+                } else {
+                    if (lane == 0) {
+                        uint32_t hclen = 0;
+                        br.refill();
+                        if (br.nb < 14) {
+                            bad = 3;
+                        } else {
+                            hlit = br.peek(5) + 257;
+                            hdist = (br.peek(10) >> 5) + 1;
+                            hclen = (br.peek(14) >> 10) + 4;
+                            br.drop(14);
+                            if (hlit > 286 || hdist > 30) bad = 2;  // "too many length or distance symbols"
+                        }
+                        for (int i = 0; i < 19; ++i) ws.lens[i] = 0;
+                        for (uint32_t i = 0; i < hclen && !bad; ++i) {
+                            br.refill();
+                            if (br.nb < 3) {
+                                bad = 3;
+                                break;
+                            }
+                            ws.lens[c_cl_order[i]] = (uint8_t)br.peek(3);
+                            br.drop(3);
+                        }
+                    }
+                    bad = __shfl_sync(FULL, bad, 0);
+                    hlit = __shfl_sync(FULL, hlit, 0);
+                    hdist = __shfl_sync(FULL, hdist, 0);
+                    __syncwarp();
+                    int maxl = 0;
+                    if (!bad) {
+                        // "invalid code lengths set": the code-length code must be complete (inftrees.c, type CODES)
+                        if (build_table(ws.lens, 19, ws.cl_count, ws.cl_sorted, ws.cl_fast, 7, ws.tmp_base, lane, &maxl) != 0) bad = 2;
+                    }
+                    __syncwarp();
+                    // the hlit + hdist code lengths, run-length coded, lane 0 -> lens[32 ..)
+                    if (lane == 0 && !bad) {
+                        int i = 0;
+                        const int nsym = hlit + hdist;
+                        while (i < nsym) {
+                            br.refill();
+                            const uint32_t e = ws.cl_fast[br.peek(7)];
+                            const uint32_t l = e & 15u;
+                            const uint32_t sym = e >> 4;
+                            if (l == 0 || l > br.nb) {
+                                bad = 3;  // complete 7-bit code: a miss can only mean the bits ran out
+                                break;
+                            }
+                            if (sym < 16) {
+                                br.drop(l);
+                                ws.lens[32 + i++] = (uint8_t)sym;
+                                continue;
+                            }
+                            const uint32_t need = sym == 16 ? 2 : sym == 17 ? 3 : 7;
+                            if (br.nb < l + need) {
+                                bad = 3;
+                                break;
+                            }
+                            br.drop(l);
+                            uint32_t rep, val = 0;
+                            if (sym == 16) {
+                                if (i == 0) {
+                                    bad = 2;  // "invalid bit length repeat"
+                                    break;
+                                }
+                                val = ws.lens[32 + i - 1];
+                                rep = 3 + br.peek(2);
+                            } else if (sym == 17) {
+                                rep = 3 + br.peek(3);
+                            } else {
+                                rep = 11 + br.peek(7);
+                            }
+                            br.drop(need);
+                            if (i + (int)rep > nsym) {
+                                bad = 2;  // "invalid bit length repeat"
+                                break;
+                            }
+                            while (rep--) ws.lens[32 + i++] = (uint8_t)val;
+                        }
+                        if (!bad && ws.lens[32 + 256] == 0) bad = 2;  // "invalid code -- missing end-of-block"
+                    }
+                    bad = __shfl_sync(FULL, bad, 0);
+                    __syncwarp();
+                    if (!bad) {
+                        // canonical places: lit/len at lens[0..hlit), dist at lens[288..288+hdist)
+                        uint8_t tmp[10];
+#pragma unroll
+                        for (int k = 0; k < 10; ++k) {
+                            const int i = lane + 32 * k;
+                            tmp[k] = i < hlit + hdist ? ws.lens[32 + i] : 0;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 10; ++k) {
+                            const int i = lane + 32 * k;
+                            if (i < hlit) ws.lens[i] = tmp[k];
+                            else if (i < hlit + hdist) ws.lens[288 + (i - hlit)] = tmp[k];
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (!bad) {
+                    int maxl = 0;
+                    int st = build_table(ws.lens, hlit, ws.lit_count, ws.lit_sorted, ws.lit_fast, LIT_FAST_BITS, ws.tmp_base, lane, &maxl);
+                    // inftrees.c: over-subscribed never; incomplete only for a single 1-bit code
+                    if (st == 1 || (st == 2 && maxl != 1)) bad = 2;  // "invalid literal/lengths set"
+                    __syncwarp();
+                    if (!bad) {
+                        st = build_table(ws.lens + 288, hdist, ws.dist_count, ws.dist_sorted, ws.dist_fast, DIST_FAST_BITS, ws.tmp_base, lane, &maxl);
+                        if (st == 1 || (st == 2 && maxl > 1)) bad = 2;  // "invalid distances set"
+                    }
+                    __syncwarp();
+                }
+                if (bad) {
+                    ev = EV_END;
+                    ev_a = bad == 3 ? END_TRUNC : END_ERR;
+                } else {
+                    in_block = true;
+                }
+            }
+
+            // ---- flush the staging buffer: complete 16-byte segments, everything at the end of the stream
+            const bool final = ev == EV_END;
+            if (ev == EV_FLUSH || final || (ev == EV_MATCH && spos + ev_a > INF_STAGE)) {
+                const uint32_t nnew = spos - astart;
+                if (store && total + nnew > ocap) store = false;  // slot overflow: only count from here on
+                if (!store) {
+                    total += nnew;
+                    spos = astart = vstart = 0;
+                } else {
+                    adler_update(ad_a, ad_b, ws.stage + astart, nnew, lane);
+                    total += nnew;
+                    const uint32_t wseg = final ? (spos + 15) >> 4 : spos >> 4;
+                    const uint4 *s4 = reinterpret_cast<const uint4 *>(ws.stage);
+                    uint4 *g4 = reinterpret_cast<uint4 *>(gbase);
+                    for (uint32_t seg = lane; seg < wseg; seg += 32) {
+                        const uint32_t lo = seg * 16, hi = lo + 16;
+                        if (lo >= vstart && hi <= spos) {
+                            g4[seg] = s4[seg];
+                        } else {  // ragged first / last segment of the stream
+                            for (uint32_t i = max(lo, vstart); i < min(hi, spos); ++i) gbase[i] = ws.stage[i];
+                        }
+                    }
+                    if (wseg) {
+                        const uint32_t full = final ? spos : wseg * 16;
+                        const uint32_t keep = spos - full;
+                        uint8_t t = 0;
+                        if (lane < (int)keep) t = ws.stage[full + lane];
+                        __syncwarp();
+                        if (lane < (int)keep) ws.stage[lane] = t;
+                        gbase += wseg * 16;
+                        vstart = 0;
+                        astart = spos = keep;
+                    } else {
+                        astart = spos;  // fewer than 16 bytes so far: counted, still waiting to be stored
+                    }
+                    __syncwarp();
+                }
+            }
+            if (ev == EV_MATCH) {
+                const uint32_t mlen = ev_a, dist = ev_b;
+                if (store) {
+                    // out[pos+k] = out[pos-dist+(k mod dist)]; sources that already left the stage are read back
+                    // from global memory through L2 (this warp stored them earlier in this launch)
+                    const int64_t stage0 = (int64_t)total - (int64_t)astart;  // absolute position of stage[0]
+                    const int64_t pos = stage0 + spos;
+                    __threadfence_block();
+                    for (uint32_t k = lane; k < mlen; k += 32) {
+                        const int64_t sp = pos - dist + (k % dist);
+                        const int64_t si = sp - stage0;
+                        ws.stage[spos + k] = si >= (int64_t)vstart ? ws.stage[si] : __ldcg(dst + sp);
+                    }
+                    __syncwarp();
+                }
+                spos += mlen;
+            }
+            if (final) {
+                stream_done = true;
+                end_kind = (int32_t)ev_a;
+                if (end_kind == END_OK && store && ((ad_b << 16) | ad_a) != ev_b) end_kind = END_ERR;  // "incorrect data check"
+            }
+        }
+        // ---- epilogue
+        if (lane == 0) {
+            br.drain();
+            phase_bits = br.phase_bits;
+        }
+        phase_bits = __shfl_sync(FULL, phase_bits, 0);
+        __syncwarp();
+        if (lane == 0) {
+            int32_t st = S5B_OK;
+            if (end_kind == END_ERR) st = S5B_ERR_PRESS;
+            else if (!store) st = S5B_ERR_NOSPACE;
+            a.status[r] = st;
+            // on overflow out_len reports the size the stream needs (the caller retries with a larger slot)
+            a.out_len[r] = end_kind == END_ERR ? 0u : (uint32_t)total;
+        }
+    }
+}
+
+int inflate_blocks_per_sm() {
+    int n = 0;
+    if (cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(InfWarpSmem) * INF_WARPS)) != cudaSuccess)
+        return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, inflate_kernel, INF_WARPS * 32,
+                                                      sizeof(InfWarpSmem) * INF_WARPS) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+cudaError_t launch_inflate(const InflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    uint64_t want = (a.n_reads + INF_WARPS - 1) / INF_WARPS;
+    uint64_t cap = (uint64_t)num_sms * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (!grid) grid = 1;
+    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InfWarpSmem) * INF_WARPS, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace s5b

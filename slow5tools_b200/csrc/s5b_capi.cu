@@ -77,7 +77,7 @@ struct PipeSlot {
 struct s5b_ctx {
     int device = 0;
     int num_sms = 0;
-    int enc_bps = 0, dec_bps = 0;
+    int enc_bps = 0, dec_bps = 0, inf_bps = 0;
     cudaStream_t stream = nullptr;  // default stream for *_dev calls
     unsigned long long *d_counter = nullptr;
     DevBuf d_scratch;
@@ -168,7 +168,8 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
     ctx->num_sms = prop.multiProcessorCount;
     ctx->enc_bps = svbzd_encode_blocks_per_sm();
     ctx->dec_bps = svbzd_decode_blocks_per_sm();
-    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0) {  // no sm_100a image for this device
+    ctx->inf_bps = inflate_blocks_per_sm();
+    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0 || ctx->inf_bps <= 0) {  // no sm_100a image for this device
         (void)cudaGetLastError();
         delete ctx;
         return S5B_ERR_DEVICE;
@@ -264,6 +265,22 @@ int s5b_svbzd_peek_dev(s5b_ctx_t *ctx, const uint8_t *d_svb, const uint64_t *d_s
     DeviceGuard g(ctx->device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     CU(launch_svbzd_peek(d_svb, d_svb_off, d_svb_len, n_reads, d_n_samples, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+int s5b_zlib_inflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                         uint64_t in_capacity, uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off,
+                         uint32_t *d_out_len, int32_t *d_status, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_len || !d_status) return S5B_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (in_capacity & 15u)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    InflateArgs a{d_in, d_in_off, d_in_len, in_capacity, n_reads, d_out, d_out_off, d_out_len, d_status,
+                  ctx->d_counter + 16};
+    CU(launch_inflate(a, ctx->num_sms, ctx->inf_bps, st));
     ctx->launches += 1;
     return S5B_OK;
 }
@@ -612,6 +629,126 @@ static int svbzd_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const siz
     return first;
 }
 
+// zlib streams: the inflated size is not stored anywhere (slow5_press.c:985-1003 grows its buffer in 256 KiB
+// steps), so slots are sized from a guess and the (rare) streams that overflow are run again with the exact
+// size the first pass reported.
+static int zlib_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, size_t n,
+                             void **out_ptrs, size_t *out_n) {
+    std::vector<uint64_t> in_off(n + 1), out_off(n + 1);
+    std::vector<uint32_t> in_len(n), out_len(n);
+    std::vector<int32_t> status(n);
+    uint64_t tot = 0, otot = 0;
+    for (size_t i = 0; i < n; ++i) {
+        out_ptrs[i] = nullptr;
+        out_n[i] = 0;
+        if (!ptrs[i] && counts[i]) return S5B_ERR_ARG;
+        if (counts[i] > 0xffffffffull) return S5B_ERR_ARG;
+        in_len[i] = (uint32_t)counts[i];
+        in_off[i] = tot;
+        tot += round_up(in_len[i], 16);
+        out_off[i] = otot;
+        otot += round_up(4ull * in_len[i] + 1024, 16);
+    }
+    in_off[n] = tot;
+    out_off[n] = otot;
+    PipeSlot &s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    CU(ctx->h_stage_in.reserve(tot + 16));
+    uint8_t *hin = static_cast<uint8_t *>(ctx->h_stage_in.p);
+    for (size_t i = 0; i < n; ++i) memcpy(hin + in_off[i], ptrs[i], in_len[i]);
+    const size_t meta_bytes = 2 * (n + 1) * 8 + 2 * n * 4;
+    CU(s.d_meta.reserve(meta_bytes + 64));
+    CU(s.d_a.reserve(tot + 16));
+    CU(s.d_b.reserve(otot + 16));
+    uint64_t *d_in_off = static_cast<uint64_t *>(s.d_meta.p);
+    uint64_t *d_out_off = d_in_off + (n + 1);
+    uint32_t *d_in_len = reinterpret_cast<uint32_t *>(d_out_off + (n + 1));
+    uint32_t *d_out_len = d_in_len + n;
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    CU(s.d_meta.reserve(meta_bytes + n * 4 + 64));
+    d_in_off = static_cast<uint64_t *>(s.d_meta.p);
+    d_out_off = d_in_off + (n + 1);
+    d_in_len = reinterpret_cast<uint32_t *>(d_out_off + (n + 1));
+    d_out_len = d_in_len + n;
+    d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    CU(cudaMemcpyAsync(s.d_a.p, hin, tot, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_in_off, in_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_out_off, out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_in_len, in_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+    InflateArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), n,
+                  static_cast<uint8_t *>(s.d_b.p), d_out_off, d_out_len, d_status, s.d_counter};
+    CU(launch_inflate(a, ctx->num_sms, ctx->inf_bps, st));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(out_len.data(), d_out_len, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status.data(), d_status, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // second pass for the streams whose slot was too small
+    std::vector<size_t> redo;
+    for (size_t i = 0; i < n; ++i)
+        if (status[i] == S5B_ERR_NOSPACE) redo.push_back(i);
+    std::vector<uint64_t> r_out_off;
+    if (!redo.empty()) {
+        const size_t m = redo.size();
+        std::vector<uint64_t> r_in_off(m + 1);
+        std::vector<uint32_t> r_in_len(m), r_out_len(m);
+        std::vector<int32_t> r_status(m);
+        r_out_off.resize(m + 1);
+        uint64_t ro = 0;
+        for (size_t k = 0; k < m; ++k) {
+            // the input ranges are not contiguous any more: give every redo stream its own [off, off+len) and let
+            // the entry after it bound nothing (capacity is checked against the whole slab)
+            r_in_off[k] = in_off[redo[k]];
+            r_in_len[k] = in_len[redo[k]];
+            r_out_off[k] = ro;
+            ro += round_up((uint64_t)out_len[redo[k]] + 16, 16);
+        }
+        r_in_off[m] = tot;
+        r_out_off[m] = ro;
+        CU(s.d_c.reserve(ro + 16));
+        CU(cudaMemcpyAsync(d_in_off, r_in_off.data(), (m + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_out_off, r_out_off.data(), (m + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_in_len, r_in_len.data(), m * 4, cudaMemcpyHostToDevice, st));
+        InflateArgs b{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), m,
+                      static_cast<uint8_t *>(s.d_c.p), d_out_off, d_out_len, d_status, s.d_counter};
+        CU(launch_inflate(b, ctx->num_sms, ctx->inf_bps, st));
+        ctx->launches += 1;
+        CU(cudaMemcpyAsync(r_out_len.data(), d_out_len, m * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(r_status.data(), d_status, m * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t k = 0; k < m; ++k) {
+            status[redo[k]] = r_status[k] == S5B_OK ? 1 /* marker: result lives in d_c */ : r_status[k];
+            out_len[redo[k]] = r_out_len[k];
+        }
+    }
+    // results back: pass-1 slots are sparse, copy each stream on its own range of one bulk D2H
+    CU(ctx->h_stage_out.reserve(otot + 16));
+    uint8_t *hout = static_cast<uint8_t *>(ctx->h_stage_out.p);
+    CU(cudaMemcpyAsync(hout, s.d_b.p, otot, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int first = S5B_OK;
+    std::vector<uint8_t> tmp;
+    for (size_t i = 0; i < n; ++i) {
+        if (status[i] != S5B_OK && status[i] != 1) {
+            if (first == S5B_OK) first = status[i];
+            continue;
+        }
+        void *mem = malloc(out_len[i] ? out_len[i] : 1);
+        if (!mem) {
+            if (first == S5B_OK) first = S5B_ERR_MEM;
+            continue;
+        }
+        if (status[i] == S5B_OK) memcpy(mem, hout + out_off[i], out_len[i]);
+        out_ptrs[i] = mem;
+        out_n[i] = out_len[i];
+    }
+    for (size_t k = 0; k < redo.size(); ++k) {
+        const size_t i = redo[k];
+        if (status[i] == 1 && out_ptrs[i])
+            CU(cudaMemcpy(out_ptrs[i], static_cast<uint8_t *>(s.d_c.p) + r_out_off[k], out_len[i], cudaMemcpyDeviceToHost));
+    }
+    return first;
+}
+
 static int copy_ptrs(const void *const *ptrs, const size_t *counts, size_t n, void **out_ptrs, size_t *out_n) {
     // SLOW5_COMPRESS_NONE: malloc + memcpy (slow5_press.c:340-350, :449-459)
     int first = S5B_OK;
@@ -646,6 +783,10 @@ int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, 
     switch (method) {
         case S5B_COMPRESS_NONE: return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_SVB_ZD: return svbzd_depress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        case S5B_COMPRESS_ZLIB: {
+            DeviceGuard g(ctx->device);
+            return zlib_depress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        }
         default: return S5B_ERR_ARG;
     }
 }

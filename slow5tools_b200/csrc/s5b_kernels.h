@@ -30,7 +30,22 @@ struct SvbDecodeArgs {
     unsigned long long *work_counter;
 };
 
+struct InflateArgs {
+    const uint8_t *in;
+    const uint64_t *in_off;  // n_reads + 1
+    const uint32_t *in_len;  // n_reads
+    uint64_t in_capacity;    // bytes, multiple of 16
+    uint64_t n_reads;
+    uint8_t *out;
+    const uint64_t *out_off;  // n_reads + 1 (slot bounds)
+    uint32_t *out_len;        // bytes produced (bytes NEEDED when status is S5B_ERR_NOSPACE)
+    int32_t *status;
+    unsigned long long *work_counter;
+};
+
 // grid sizing helpers (queried once per context)
+int inflate_blocks_per_sm();
+cudaError_t launch_inflate(const InflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
 int svbzd_encode_blocks_per_sm();
 int svbzd_decode_blocks_per_sm();
 
