@@ -545,7 +545,8 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                 int hlit = 288, hdist = 30, bad = 0;  // bad: 2 = data error, 3 = input ended
                 if (bt == 1) {
                     for (int s = lane; s < 288; s += 32) ws.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
-                    if (lane < 30) ws.lens[288 + lane] = 5;
+                    ws.lens[288 + lane] = 5;  // all 32 five-bit codes (30 and 31 decode to "invalid distance code")
+                    hdist = 32;
                     __syncwarp();
                 } else {
                     if (lane == 0) {
