@@ -112,6 +112,18 @@ int s5b_zlib_inflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_
                          uint64_t in_capacity, uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off,
                          uint32_t *d_out_len, int32_t *d_status, void *stream);
 
+/* Replaces ptr_compress_zlib / ptr_compress_zlib_solo (slow5_press.c:837-913: deflate at level 6 with
+ * Z_FINISH) for a batch: record r = d_in[d_in_off[r] .. +d_in_len[r]) becomes one complete zlib stream
+ * (78 9C .. Adler-32) in the slot [d_out_off[r], d_out_off[r+1]), which must hold s5b_zlib_bound(len).
+ * The bytes differ from zlib's (dynamic Huffman + distance-1 run matches); any zlib inflates them to the
+ * exact input.  d_split (optional, may be NULL): byte offset inside record r where a new Huffman block
+ * should start -- for BLOW5 records the start of the svb-zd data bytes, whose statistics differ from the
+ * header + key bytes before them. */
+uint64_t s5b_zlib_bound(uint64_t len);
+int s5b_zlib_deflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                         uint64_t in_capacity, const uint32_t *d_split, uint64_t n_reads, uint8_t *d_out,
+                         const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream);
+
 /* Gathers slotted streams into a dense slab: d_dst_off[r] (n_reads+1 entries, exclusive scan of
  * len rounded up to `align`, align in {1,16}) and the copied bytes.  d_dst capacity is checked
  * against dst_capacity (S5B_ERR_NOSPACE is reported through the return of the host wrappers). */

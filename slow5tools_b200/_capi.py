@@ -90,3 +90,7 @@ def strerror(code):
 
 lib.s5b_zlib_inflate_dev.restype = C.c_int
 lib.s5b_zlib_inflate_dev.argtypes = [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]
+lib.s5b_zlib_bound.restype = _u64
+lib.s5b_zlib_bound.argtypes = [_u64]
+lib.s5b_zlib_deflate_dev.restype = C.c_int
+lib.s5b_zlib_deflate_dev.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]

@@ -77,7 +77,7 @@ struct PipeSlot {
 struct s5b_ctx {
     int device = 0;
     int num_sms = 0;
-    int enc_bps = 0, dec_bps = 0, inf_bps = 0;
+    int enc_bps = 0, dec_bps = 0, inf_bps = 0, def_bps = 0;
     cudaStream_t stream = nullptr;  // default stream for *_dev calls
     unsigned long long *d_counter = nullptr;
     DevBuf d_scratch;
@@ -169,7 +169,8 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
     ctx->enc_bps = svbzd_encode_blocks_per_sm();
     ctx->dec_bps = svbzd_decode_blocks_per_sm();
     ctx->inf_bps = inflate_blocks_per_sm();
-    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0 || ctx->inf_bps <= 0) {  // no sm_100a image for this device
+    ctx->def_bps = deflate_blocks_per_sm();
+    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0 || ctx->inf_bps <= 0 || ctx->def_bps <= 0) {  // no sm_100a image for this device
         (void)cudaGetLastError();
         delete ctx;
         return S5B_ERR_DEVICE;
@@ -281,6 +282,24 @@ int s5b_zlib_inflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_
     InflateArgs a{d_in, d_in_off, d_in_len, in_capacity, n_reads, d_out, d_out_off, d_out_len, d_status,
                   ctx->d_counter + 16};
     CU(launch_inflate(a, ctx->num_sms, ctx->inf_bps, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+uint64_t s5b_zlib_bound(uint64_t len) { return round_up(deflate_bound(len), 16); }
+
+int s5b_zlib_deflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                         uint64_t in_capacity, const uint32_t *d_split, uint64_t n_reads, uint8_t *d_out,
+                         const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_len || !d_status) return S5B_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (in_capacity & 15u)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    DeflateArgs a{d_in, d_in_off, d_in_len, in_capacity, d_split, n_reads, d_out, d_out_off, d_out_len, d_status,
+                  ctx->d_counter + 24};
+    CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
     ctx->launches += 1;
     return S5B_OK;
 }
@@ -749,6 +768,70 @@ static int zlib_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size
     return first;
 }
 
+static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, size_t n,
+                              void **out_ptrs, size_t *out_n) {
+    std::vector<uint64_t> in_off(n + 1), out_off(n + 1);
+    std::vector<uint32_t> in_len(n), out_len(n);
+    std::vector<int32_t> status(n);
+    uint64_t tot = 0, otot = 0;
+    for (size_t i = 0; i < n; ++i) {
+        out_ptrs[i] = nullptr;
+        out_n[i] = 0;
+        if (!ptrs[i] && counts[i]) return S5B_ERR_ARG;
+        if (counts[i] > 0xfffffff0ull) return S5B_ERR_ARG;
+        in_len[i] = (uint32_t)counts[i];
+        in_off[i] = tot;
+        tot += round_up(in_len[i], 16);
+        out_off[i] = otot;
+        otot += s5b_zlib_bound(in_len[i]);
+    }
+    in_off[n] = tot;
+    out_off[n] = otot;
+    PipeSlot &s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    CU(ctx->h_stage_in.reserve(tot + 16));
+    CU(ctx->h_stage_out.reserve(otot + 16));
+    uint8_t *hin = static_cast<uint8_t *>(ctx->h_stage_in.p);
+    for (size_t i = 0; i < n; ++i) memcpy(hin + in_off[i], ptrs[i], in_len[i]);
+    CU(s.d_meta.reserve(2 * (n + 1) * 8 + 3 * n * 4 + 64));
+    CU(s.d_a.reserve(tot + 16));
+    CU(s.d_b.reserve(otot + 16));
+    uint64_t *d_in_off = static_cast<uint64_t *>(s.d_meta.p);
+    uint64_t *d_out_off = d_in_off + (n + 1);
+    uint32_t *d_in_len = reinterpret_cast<uint32_t *>(d_out_off + (n + 1));
+    uint32_t *d_out_len = d_in_len + n;
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    CU(cudaMemcpyAsync(s.d_a.p, hin, tot, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_in_off, in_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_out_off, out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_in_len, in_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+    DeflateArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), nullptr, n,
+                  static_cast<uint8_t *>(s.d_b.p), d_out_off, d_out_len, d_status, s.d_counter};
+    CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(out_len.data(), d_out_len, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status.data(), d_status, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_stage_out.p, s.d_b.p, otot, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint8_t *hout = static_cast<const uint8_t *>(ctx->h_stage_out.p);
+    int first = S5B_OK;
+    for (size_t i = 0; i < n; ++i) {
+        if (status[i] != S5B_OK) {
+            if (first == S5B_OK) first = status[i];
+            continue;
+        }
+        void *mem = malloc(out_len[i] ? out_len[i] : 1);
+        if (!mem) {
+            if (first == S5B_OK) first = S5B_ERR_MEM;
+            continue;
+        }
+        memcpy(mem, hout + out_off[i], out_len[i]);
+        out_ptrs[i] = mem;
+        out_n[i] = out_len[i];
+    }
+    return first;
+}
+
 static int copy_ptrs(const void *const *ptrs, const size_t *counts, size_t n, void **out_ptrs, size_t *out_n) {
     // SLOW5_COMPRESS_NONE: malloc + memcpy (slow5_press.c:340-350, :449-459)
     int first = S5B_OK;
@@ -772,6 +855,10 @@ int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs,
     switch (method) {
         case S5B_COMPRESS_NONE: return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_SVB_ZD: return svbzd_compress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        case S5B_COMPRESS_ZLIB: {
+            DeviceGuard g(ctx->device);
+            return zlib_compress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        }
         default: return S5B_ERR_ARG;
     }
 }

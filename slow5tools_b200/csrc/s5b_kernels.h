@@ -43,6 +43,23 @@ struct InflateArgs {
     unsigned long long *work_counter;
 };
 
+struct DeflateArgs {
+    const uint8_t *in;
+    const uint64_t *in_off;  // n_reads + 1
+    const uint32_t *in_len;  // n_reads
+    uint64_t in_capacity;    // bytes, multiple of 16
+    const uint32_t *split;   // optional: byte offset inside record r where a new Huffman block should start
+    uint64_t n_reads;
+    uint8_t *out;
+    const uint64_t *out_off;  // n_reads + 1 (slot bounds, >= deflate_bound(len))
+    uint32_t *out_len;
+    int32_t *status;
+    unsigned long long *work_counter;
+};
+int deflate_blocks_per_sm();
+uint64_t deflate_bound(uint64_t len);
+cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
+
 // grid sizing helpers (queried once per context)
 int inflate_blocks_per_sm();
 cudaError_t launch_inflate(const InflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
