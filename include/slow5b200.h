@@ -154,6 +154,11 @@ int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs,
                             size_t n, void **out_ptrs, size_t *out_n);
 int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
                            size_t n, void **out_ptrs, size_t *out_n);
+/* zlib record compression (the slow5_ptr_compress(record_press) call of slow5_rec_to_mem, slow5.c:4050) for a
+ * batch of packed records, with the per-record Huffman-block split hint of s5b_zlib_deflate_dev (splits may
+ * be NULL). */
+int s5b_compress_records_host(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, const uint32_t *splits,
+                              size_t n, void **out_ptrs, size_t *out_n);
 
 /* ---- level 1: single buffers ---------------------------------------------------------------
  * Same contract as slow5_ptr_compress_solo / slow5_ptr_depress_solo: returns a malloc()'d buffer,

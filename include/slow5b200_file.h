@@ -1,0 +1,95 @@
+/* slow5b200_file.h -- the slice of the slow5lib C API that the per-record codec path lives behind, provided by
+ * libslow5b200.so with the codec work done on the GPU.  Names mirror the reference one-to-one (s5b_ for
+ * slow5_); `#define S5B_SLOW5_COMPAT` before including maps the slow5_* spellings onto them so code written
+ * against slow5lib's low-level API (slow5lib/examples/adv/sequential_read_pthreads.c) compiles unchanged.
+ *
+ *   s5b_open            slow5_open            slow5lib/include/slow5/slow5.h:345   (slow5.c:295)
+ *   s5b_close           slow5_close           slow5.h:354                            (slow5.c:505)
+ *   s5b_get_next_mem    slow5_get_next_mem    slow5_extra.h                          (slow5.c:3206)
+ *   s5b_get_next_bytes  slow5_get_next_bytes  slow5.h:656                            (slow5.c:3302)
+ *   s5b_decode          slow5_decode          slow5.h:658                            (slow5.c:2613)
+ *   s5b_encode          slow5_encode          slow5.h:660                            (slow5.c:4083)
+ *   s5b_write_bytes     slow5_write_bytes     slow5.h:662                            (slow5.c:3785)
+ *   s5b_rec_free        slow5_rec_free        slow5.h:454
+ *   s5b_set_press       slow5_set_press       slow5.h:612
+ *   s5b_hdr_write       slow5_hdr_write       slow5.h:586
+ *   s5b_decode_batch / s5b_encode_batch       the worker bodies of slow5_get_next_batch / slow5_encode_batch
+ *                                             (slow5_mt.c:124-181), one GPU batch instead of a pthread pool
+ *
+ * Differences a caller can see: slow5_rec_t's aux_map (a khash) is replaced by the record's binary auxiliary
+ * section kept as-is (aux / aux_len); the leading fields have the reference's names, types and order
+ * (slow5.h:274-287).  Ownership rules are the reference's: s5b_decode frees *mem and replaces it when the
+ * record was compressed (slow5.c:2595-2597); s5b_encode output carries the 8-byte size prefix, s5b_get_next_mem
+ * output does not; everything returned is malloc()'d.
+ */
+#ifndef SLOW5B200_FILE_H
+#define SLOW5B200_FILE_H
+#include <stddef.h>
+#include <stdint.h>
+#include "slow5b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S5B_ERR_EOF       (-1)   /* == SLOW5_ERR_EOF */
+#define S5B_ERR_IO        (-5)   /* == SLOW5_ERR_IO */
+#define S5B_ERR_RECPARSE  (-7)   /* == SLOW5_ERR_RECPARSE */
+
+typedef struct s5b_rec {
+    uint16_t read_id_len;
+    char *read_id;
+    uint32_t read_group;
+    double digitisation;
+    double offset;
+    double range;
+    double sampling_rate;
+    uint64_t len_raw_signal;
+    int16_t *raw_signal;
+    uint8_t *aux;      /* binary auxiliary section of the record, header order (slow5.c:3993-4044) */
+    uint64_t aux_len;
+} s5b_rec_t;
+
+typedef struct s5b_file s5b_file_t;
+
+extern int s5b_errno_value(void);   /* the twin of the thread-local slow5_errno */
+
+s5b_file_t *s5b_open(const char *pathname, const char *mode /* "r" or "w" */);
+int s5b_close(s5b_file_t *fp);                     /* "w": appends the end-of-file marker first */
+/* "w" files: take the header (attributes, aux columns, version) from an opened input, choose the methods */
+int s5b_hdr_copy(s5b_file_t *dst, const s5b_file_t *src);
+int s5b_set_press(s5b_file_t *fp, int rec_press /*S5B_COMPRESS_*/, int sig_press);
+int s5b_hdr_write(s5b_file_t *fp);
+int s5b_file_record_press(const s5b_file_t *fp);
+int s5b_file_signal_press(const s5b_file_t *fp);
+
+void *s5b_get_next_mem(size_t *n, s5b_file_t *fp);
+int s5b_get_next_bytes(char **mem, size_t *bytes, s5b_file_t *fp);
+int s5b_decode(char **mem, size_t *bytes, s5b_rec_t **read, s5b_file_t *fp);
+int s5b_encode(char **mem, size_t *bytes, s5b_rec_t *read, s5b_file_t *fp);
+int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *fp);
+void s5b_rec_free(s5b_rec_t *read);
+
+/* n records at once: mems[i]/bytes[i] as returned by s5b_get_next_mem; reads[i] allocated when NULL */
+int s5b_decode_batch(s5b_file_t *fp, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads);
+int s5b_encode_batch(s5b_file_t *fp, s5b_rec_t **reads, size_t n, char **mems, size_t *bytes);
+
+#ifdef S5B_SLOW5_COMPAT
+#define slow5_file_t s5b_file_t
+#define slow5_rec_t s5b_rec_t
+#define slow5_open s5b_open
+#define slow5_close s5b_close
+#define slow5_get_next_mem s5b_get_next_mem
+#define slow5_get_next_bytes s5b_get_next_bytes
+#define slow5_decode s5b_decode
+#define slow5_encode s5b_encode
+#define slow5_write_bytes s5b_write_bytes
+#define slow5_rec_free s5b_rec_free
+#define slow5_set_press s5b_set_press
+#define slow5_hdr_write s5b_hdr_write
+#define slow5_errno (s5b_errno_value())
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,313 @@
+// s5b_file_api.cpp -- the slow5lib low-level API slice (include/slow5b200_file.h) over blow5_io + the GPU
+// batch codec.  Every codec call goes through the C-ABI of include/slow5b200.h; nothing is computed here.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/slow5b200_file.h"
+#include "blow5_io.hpp"
+
+using namespace s5b;
+
+struct s5b_file {
+    Reader rd;          // "r"
+    FILE *out = nullptr;  // "w"
+    bool writing = false;
+    bool hdr_written = false;
+    Header hdr;         // "w": header to emit
+    int rec_press = PRESS_ZLIB, sig_press = PRESS_SVB_ZD;
+    s5b_ctx_t *gpu = nullptr;
+};
+
+namespace {
+thread_local int tl_errno = 0;
+int fail(int code) {
+    tl_errno = code;
+    return code;
+}
+int ensure_gpu(s5b_file *f) {
+    if (f->gpu) return S5B_OK;
+    return s5b_ctx_create(-1, &f->gpu);
+}
+}  // namespace
+
+extern "C" {
+
+int s5b_errno_value(void) { return tl_errno; }
+
+s5b_file_t *s5b_open(const char *pathname, const char *mode) {
+    if (!pathname || !mode) {
+        fail(S5B_ERR_ARG);
+        return nullptr;
+    }
+    s5b_file *f = new s5b_file();
+    if (mode[0] == 'r') {
+        if (!reader_open(f->rd, pathname, FMT_UNKNOWN)) {
+            fail(S5B_ERR_IO);
+            reader_close(f->rd);
+            delete f;
+            return nullptr;
+        }
+        f->rec_press = f->rd.hdr.record_method;
+        f->sig_press = f->rd.hdr.signal_method;
+        return f;
+    }
+    if (mode[0] == 'w' && fmt_from_path(pathname) == FMT_BINARY) {
+        f->out = fopen(pathname, "wb");
+        if (f->out) {
+            f->writing = true;
+            return f;
+        }
+    }
+    fail(S5B_ERR_IO);
+    delete f;
+    return nullptr;
+}
+
+int s5b_close(s5b_file_t *f) {
+    if (!f) return fail(S5B_ERR_ARG);
+    int rc = 0;
+    if (f->writing) {
+        if (fwrite("5WOLB", 1, 5, f->out) != 5) rc = S5B_ERR_IO;  // slow5.c:522-531
+        if (fclose(f->out) != 0) rc = S5B_ERR_IO;
+    } else {
+        reader_close(f->rd);
+    }
+    if (f->gpu) s5b_ctx_destroy(f->gpu);
+    delete f;
+    return rc ? fail(rc) : 0;
+}
+
+int s5b_hdr_copy(s5b_file_t *dst, const s5b_file_t *src) {
+    if (!dst || !src || !dst->writing) return fail(S5B_ERR_ARG);
+    dst->hdr = src->rd.hdr;
+    return 0;
+}
+int s5b_set_press(s5b_file_t *f, int rec_press, int sig_press) {
+    if (!f || !f->writing || f->hdr_written) return fail(S5B_ERR_ARG);
+    if ((rec_press != PRESS_NONE && rec_press != PRESS_ZLIB) || (sig_press != PRESS_NONE && sig_press != PRESS_SVB_ZD))
+        return fail(S5B_ERR_ARG);  // zstd / ex-zd: not in this build (slow5_press.c:282-290 behaves alike without zstd)
+    f->rec_press = rec_press;
+    f->sig_press = sig_press;
+    return 0;
+}
+int s5b_hdr_write(s5b_file_t *f) {
+    if (!f || !f->writing) return fail(S5B_ERR_ARG);
+    const std::string h = header_to_mem(f->hdr, FMT_BINARY, f->rec_press, f->sig_press);
+    if (fwrite(h.data(), 1, h.size(), f->out) != h.size()) return fail(S5B_ERR_IO);
+    f->hdr_written = true;
+    return (int)h.size();
+}
+int s5b_file_record_press(const s5b_file_t *f) { return f ? f->rec_press : S5B_ERR_ARG; }
+int s5b_file_signal_press(const s5b_file_t *f) { return f ? f->sig_press : S5B_ERR_ARG; }
+
+void *s5b_get_next_mem(size_t *n, s5b_file_t *f) {
+    if (!f || !n || f->writing || f->rd.fmt != FMT_BINARY) {
+        fail(S5B_ERR_ARG);
+        return nullptr;
+    }
+    std::vector<uint8_t> mem;
+    const int rc = reader_next_mem(f->rd, mem);
+    if (rc <= 0) {
+        fail(rc == 0 ? S5B_ERR_EOF : S5B_ERR_IO);
+        *n = 0;
+        return nullptr;
+    }
+    void *out = malloc(mem.size() ? mem.size() : 1);
+    if (!out) {
+        fail(S5B_ERR_MEM);
+        return nullptr;
+    }
+    memcpy(out, mem.data(), mem.size());
+    *n = mem.size();
+    return out;
+}
+
+int s5b_get_next_bytes(char **mem, size_t *bytes, s5b_file_t *f) {
+    if (!mem || !bytes) return fail(S5B_ERR_ARG);
+    *mem = static_cast<char *>(s5b_get_next_mem(bytes, f));
+    return *mem ? 0 : tl_errno;
+}
+
+void s5b_rec_free(s5b_rec_t *r) {
+    if (!r) return;
+    free(r->read_id);
+    free(r->raw_signal);
+    free(r->aux);
+    free(r);
+}
+
+int s5b_decode_batch(s5b_file_t *f, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads) {
+    if (!f || !mems || !bytes || !reads) return fail(S5B_ERR_ARG);
+    if (n == 0) return 0;
+    const Header &h = f->rd.hdr;
+    if (h.record_method != PRESS_NONE || h.signal_method != PRESS_NONE) {
+        const int rc = ensure_gpu(f);
+        if (rc != S5B_OK) return fail(rc);
+    }
+    std::vector<const void *> ptrs(n);
+    std::vector<size_t> counts(n);
+    if (h.record_method == PRESS_ZLIB) {
+        std::vector<void *> out(n, nullptr);
+        std::vector<size_t> out_n(n, 0);
+        for (size_t i = 0; i < n; ++i) {
+            ptrs[i] = mems[i];
+            counts[i] = bytes[i];
+        }
+        const int rc = s5b_depress_batch_host(f->gpu, S5B_COMPRESS_ZLIB, ptrs.data(), counts.data(), n, out.data(), out_n.data());
+        if (rc != S5B_OK) {
+            for (void *p : out) free(p);
+            return fail(rc == S5B_ERR_PRESS ? S5B_ERR_PRESS : rc);
+        }
+        for (size_t i = 0; i < n; ++i) {  // the decompressed record replaces *mem (slow5.c:2595-2597)
+            free(mems[i]);
+            mems[i] = static_cast<char *>(out[i]);
+            bytes[i] = out_n[i];
+        }
+    } else if (h.record_method != PRESS_NONE) {
+        return fail(S5B_ERR_ARG);
+    }
+    std::vector<Record> rec(n);
+    std::string err;
+    for (size_t i = 0; i < n; ++i)
+        if (!record_parse_binary(reinterpret_cast<const uint8_t *>(mems[i]), bytes[i], h, h.signal_method, rec[i], err))
+            return fail(S5B_ERR_RECPARSE);
+    std::vector<void *> sig(n, nullptr);
+    std::vector<size_t> sig_n(n, 0);
+    if (h.signal_method == PRESS_SVB_ZD) {
+        for (size_t i = 0; i < n; ++i) {
+            ptrs[i] = rec[i].sig_bytes;
+            counts[i] = rec[i].sig_nbytes;
+        }
+        const int rc = s5b_depress_batch_host(f->gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, sig.data(), sig_n.data());
+        if (rc != S5B_OK) {
+            for (void *p : sig) free(p);
+            return fail(rc);
+        }
+    } else if (h.signal_method == PRESS_NONE) {
+        for (size_t i = 0; i < n; ++i) {
+            sig_n[i] = rec[i].sig_nbytes;
+            sig[i] = malloc(sig_n[i] ? sig_n[i] : 1);
+            if (sig[i]) memcpy(sig[i], rec[i].sig_bytes, sig_n[i]);
+        }
+    } else {
+        return fail(S5B_ERR_ARG);
+    }
+    for (size_t i = 0; i < n; ++i) {
+        s5b_rec_t *r = reads[i];
+        if (!r) {
+            r = static_cast<s5b_rec_t *>(calloc(1, sizeof *r));
+            reads[i] = r;
+        } else {  // reuse the struct, rebuild its members (slow5.c:2626-2639)
+            free(r->read_id);
+            free(r->raw_signal);
+            free(r->aux);
+        }
+        r->read_id_len = (uint16_t)rec[i].read_id.size();
+        r->read_id = strndup(rec[i].read_id.data(), rec[i].read_id.size());
+        r->read_group = rec[i].read_group;
+        r->digitisation = rec[i].digitisation;
+        r->offset = rec[i].offset;
+        r->range = rec[i].range;
+        r->sampling_rate = rec[i].sampling_rate;
+        r->len_raw_signal = sig_n[i] / 2;
+        r->raw_signal = static_cast<int16_t *>(sig[i]);
+        r->aux_len = rec[i].aux_nbytes;
+        r->aux = static_cast<uint8_t *>(malloc(r->aux_len ? r->aux_len : 1));
+        if (r->aux_len) memcpy(r->aux, rec[i].aux_bytes, r->aux_len);
+    }
+    return 0;
+}
+
+int s5b_decode(char **mem, size_t *bytes, s5b_rec_t **read, s5b_file_t *f) {
+    if (!mem || !*mem || !bytes || !read) return fail(S5B_ERR_ARG);
+    return s5b_decode_batch(f, mem, bytes, 1, read);
+}
+
+int s5b_encode_batch(s5b_file_t *f, s5b_rec_t **reads, size_t n, char **mems, size_t *bytes) {
+    if (!f || !reads || !mems || !bytes) return fail(S5B_ERR_ARG);
+    if (n == 0) return 0;
+    if (f->rec_press != PRESS_NONE || f->sig_press != PRESS_NONE) {
+        const int rc = ensure_gpu(f);
+        if (rc != S5B_OK) return fail(rc);
+    }
+    std::vector<const void *> ptrs(n);
+    std::vector<size_t> counts(n);
+    std::vector<void *> svb(n, nullptr);
+    std::vector<size_t> svb_n(n, 0);
+    if (f->sig_press == PRESS_SVB_ZD) {
+        for (size_t i = 0; i < n; ++i) {
+            ptrs[i] = reads[i]->raw_signal;
+            counts[i] = reads[i]->len_raw_signal * 2;
+        }
+        const int rc = s5b_compress_batch_host(f->gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
+        if (rc != S5B_OK) {
+            for (void *p : svb) free(p);
+            return fail(rc);
+        }
+    }
+    std::vector<std::vector<uint8_t>> packed(n);
+    std::vector<uint32_t> splits(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        s5b_rec_t *r = reads[i];
+        Record rec;
+        rec.read_id.assign(r->read_id ? r->read_id : "", r->read_id ? r->read_id_len : 0);
+        rec.read_group = r->read_group;
+        rec.digitisation = r->digitisation;
+        rec.offset = r->offset;
+        rec.range = r->range;
+        rec.sampling_rate = r->sampling_rate;
+        rec.aux_bytes = r->aux;
+        rec.aux_nbytes = r->aux_len;
+        uint64_t at = 0;
+        if (f->sig_press == PRESS_SVB_ZD) {
+            record_to_binary(rec, static_cast<const uint8_t *>(svb[i]), svb_n[i], true, packed[i], &at);
+            splits[i] = (uint32_t)(at + 4 + (r->len_raw_signal + 3) / 4);
+            // destructive like the reference: the record now owns the compressed signal (slow5.c:3982-3984)
+            free(r->raw_signal);
+            r->raw_signal = static_cast<int16_t *>(svb[i]);
+            r->len_raw_signal = svb_n[i];
+        } else {
+            record_to_binary(rec, reinterpret_cast<const uint8_t *>(r->raw_signal), r->len_raw_signal * 2, false, packed[i], &at);
+        }
+    }
+    std::vector<void *> z(n, nullptr);
+    std::vector<size_t> z_n(n, 0);
+    if (f->rec_press == PRESS_ZLIB) {
+        for (size_t i = 0; i < n; ++i) {
+            ptrs[i] = packed[i].data();
+            counts[i] = packed[i].size();
+        }
+        const int rc = s5b_compress_records_host(f->gpu, ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
+        if (rc != S5B_OK) {
+            for (void *p : z) free(p);
+            return fail(rc);
+        }
+    }
+    for (size_t i = 0; i < n; ++i) {
+        const void *p = f->rec_press == PRESS_ZLIB ? z[i] : packed[i].data();
+        const uint64_t sz = f->rec_press == PRESS_ZLIB ? z_n[i] : packed[i].size();
+        char *m = static_cast<char *>(malloc(8 + sz));
+        if (!m) return fail(S5B_ERR_MEM);
+        memcpy(m, &sz, 8);  // size prefix, slow5.c:4055-4060
+        memcpy(m + 8, p, sz);
+        mems[i] = m;
+        bytes[i] = 8 + sz;
+        free(z[i]);
+    }
+    return 0;
+}
+
+int s5b_encode(char **mem, size_t *bytes, s5b_rec_t *read, s5b_file_t *f) {
+    if (!mem || !bytes || !read) return fail(S5B_ERR_ARG);
+    return s5b_encode_batch(f, &read, 1, mem, bytes) == 0 ? 0 : -1;
+}
+
+int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *f) {
+    if (!f || !f->writing || !mem) return fail(S5B_ERR_ARG);
+    if (fwrite(mem, 1, bytes, f->out) != bytes) return fail(S5B_ERR_IO);
+    return (int)bytes;
+}
+
+}  // extern "C"

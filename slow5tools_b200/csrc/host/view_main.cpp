@@ -1,0 +1,415 @@
+// view_main.cpp -- `slow5tools-b200 view`: the reference's `slow5tools view` (src/view.c:59-323) with the
+// per-record codec work of its worker (depress_parse_rec_to_mem, src/view.c:35-57) moved out of the pthread
+// pool (src/thread.c:114 work_db) into batch calls on the GPU through the C-ABI (include/slow5b200.h).
+//
+// Per batch of -K records:   serial read (as the reference, view.c:265-278)
+//   -> s5b_depress_batch_host(ZLIB)      record decompression         (slow5.c:2586)
+//   -> host: parse fixed fields, locate the signal bytes               (slow5.c:2811-2950), -t threads
+//   -> s5b_depress_batch_host(SVB_ZD)    signal decompression          (slow5.c:2915)
+//   -> SLOW5 ASCII formatting on -t threads, or
+//      s5b_compress_batch_host(SVB_ZD) -> host: pack records -> s5b_compress_records_host (zlib) (slow5.c:3973,4050)
+//   -> serial write (view.c:296-299), end-of-file marker (view.c:313).
+// Same flags, defaults and failure behaviour (any record error -> message on stderr, exit status 1).
+// There is no CPU codec here: without a CUDA device the command fails.
+#include <getopt.h>
+
+#include <atomic>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/slow5b200.h"
+#include "blow5_io.hpp"
+
+using namespace s5b;
+
+namespace {
+
+int g_verbose = 3;
+#define ERROR(fmt, ...) fprintf(stderr, "[%s::ERROR]\033[1;31m " fmt "\033[0m\n", __func__, __VA_ARGS__)
+#define INFO(fmt, ...)                                                         \
+    do {                                                                       \
+        if (g_verbose >= 3) fprintf(stderr, "[%s::INFO] " fmt "\n", __func__, __VA_ARGS__); \
+    } while (0)
+
+void parallel_for(size_t n, int threads, const std::function<void(size_t)> &fn) {
+    if (threads <= 1 || n < 64) {
+        for (size_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const size_t i0 = next.fetch_add(16);
+                if (i0 >= n) break;
+                const size_t i1 = i0 + 16 < n ? i0 + 16 : n;
+                for (size_t i = i0; i < i1; ++i) fn(i);
+            }
+        });
+    for (auto &th : pool) th.join();
+}
+
+void usage(FILE *f) {
+    fprintf(f,
+            "Usage: slow5tools-b200 view [OPTIONS] [SLOW5_FILE/BLOW5_FILE]\n"
+            "View a SLOW5/BLOW5 file or convert between the two (GPU codec).\n\n"
+            "OPTIONS:\n"
+            "    --to FORMAT                   specify output file format (slow5 or blow5)\n"
+            "    -o, --output [FILE]           output contents to FILE [stdout]\n"
+            "    -c, --compress REC_MTD        record compression method [zlib] (only for blow5 format)\n"
+            "    -s, --sig-compress SIG_MTD    signal compression method [svb-zd] (only for blow5 format)\n"
+            "    -t, --threads INT             number of host threads for parsing/formatting [8]\n"
+            "    -K, --batchsize INT           number of records loaded to the memory at once [4096]\n"
+            "    --from FORMAT                 specify input file format (slow5 or blow5)\n"
+            "    -h, --help                    display this message and exit\n"
+            "REC_MTD: none, zlib      SIG_MTD: none, svb-zd      (zstd / ex-zd: not in this build)\n");
+}
+
+struct Batch {
+    std::vector<std::vector<uint8_t>> mem;     // as read from the file
+    std::vector<void *> inflated;              // malloc'd by the library (record method zlib)
+    std::vector<size_t> inflated_n;
+    std::vector<Record> rec;
+    std::vector<std::vector<uint8_t>> aux_store;  // ASCII input: binary form of the aux columns
+    std::vector<void *> sig;                   // malloc'd decoded signals
+    std::vector<size_t> sig_n;
+    void free_all() {
+        for (void *p : inflated) free(p);
+        for (void *p : sig) free(p);
+        inflated.clear();
+        sig.clear();
+    }
+};
+
+}  // namespace
+
+extern "C" int s5b_compress_records_host(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts,
+                                         const uint32_t *splits, size_t n, void **out_ptrs, size_t *out_n);
+
+int view_main(int argc, char **argv) {
+    static const struct option long_opts[] = {
+        {"sig-compress", required_argument, nullptr, 's'}, {"compress", required_argument, nullptr, 'c'},
+        {"from", required_argument, nullptr, 'f'},         {"help", no_argument, nullptr, 'h'},
+        {"output", required_argument, nullptr, 'o'},       {"to", required_argument, nullptr, 'b'},
+        {"threads", required_argument, nullptr, 't'},      {"batchsize", required_argument, nullptr, 'K'},
+        {nullptr, 0, nullptr, 0}};
+    const char *arg_sig = nullptr, *arg_rec = nullptr, *arg_from = nullptr, *arg_to = nullptr, *arg_out = nullptr;
+    int threads = 8;
+    long batch = 4096;
+    int opt;
+    optind = 1;
+    while ((opt = getopt_long(argc, argv, "s:c:f:ho:b:t:K:", long_opts, nullptr)) != -1) {
+        switch (opt) {
+            case 's': arg_sig = optarg; break;
+            case 'c': arg_rec = optarg; break;
+            case 'f': arg_from = optarg; break;
+            case 'b': arg_to = optarg; break;
+            case 'o': arg_out = optarg; break;
+            case 't': threads = atoi(optarg); break;
+            case 'K': batch = atol(optarg); break;
+            case 'h': usage(stdout); return 0;
+            default: usage(stderr); return 1;
+        }
+    }
+    if (threads < 1 || batch < 1) {
+        ERROR("%s", "invalid -t / -K value");
+        return 1;
+    }
+    if (optind >= argc) {
+        ERROR("missing input file%s", "");
+        usage(stderr);
+        return 1;
+    }
+    if (optind != argc - 1) {
+        ERROR("more than 1 input file is given%s", "");
+        return 1;
+    }
+    const char *in_path = argv[optind];
+    Fmt fmt_in = FMT_UNKNOWN, fmt_out = FMT_UNKNOWN;
+    if (arg_from && (fmt_in = fmt_from_name(arg_from)) == FMT_UNKNOWN) {
+        ERROR("invalid input format '%s'", arg_from);
+        return 1;
+    }
+    if (arg_to && (fmt_out = fmt_from_name(arg_to)) == FMT_UNKNOWN) {
+        ERROR("invalid output format '%s'", arg_to);
+        return 1;
+    }
+    if (arg_out) {
+        const Fmt by_ext = fmt_from_path(arg_out);
+        if (fmt_out == FMT_UNKNOWN) {
+            fmt_out = by_ext;
+            if (fmt_out == FMT_UNKNOWN) {
+                ERROR("cannot detect the output format from the file extension of '%s'", arg_out);
+                return 1;
+            }
+        } else if (by_ext != FMT_UNKNOWN && by_ext != fmt_out) {
+            ERROR("output file extension '%s' does not match the output format '%s'", arg_out, arg_to);
+            return 1;
+        }
+    }
+    if (fmt_out == FMT_UNKNOWN) fmt_out = FMT_ASCII;  // view.c:160-162
+    if (fmt_out == FMT_ASCII && (arg_rec || arg_sig)) {  // misc.c:219-249
+        ERROR("%s", "compression options (-c / -s) are only valid for blow5 output");
+        return 1;
+    }
+    int rec_out = PRESS_ZLIB, sig_out = PRESS_SVB_ZD;  // misc.c:54-55
+    if (arg_rec && (rec_out = press_from_name(arg_rec)) == PRESS_BAD) {
+        ERROR("invalid record compression method '%s'", arg_rec);
+        return 1;
+    }
+    if (arg_sig && (sig_out = press_from_name(arg_sig)) == PRESS_BAD) {
+        ERROR("invalid signal compression method '%s'", arg_sig);
+        return 1;
+    }
+    if (fmt_out == FMT_ASCII) rec_out = sig_out = PRESS_NONE;
+    if ((rec_out != PRESS_NONE && rec_out != PRESS_ZLIB) || (sig_out != PRESS_NONE && sig_out != PRESS_SVB_ZD)) {
+        ERROR("%s", "this build supports record compression none/zlib and signal compression none/svb-zd only");
+        return 1;
+    }
+
+    Reader rd;
+    if (!reader_open(rd, in_path, fmt_in)) {
+        ERROR("File '%s' could not be opened - %s.", in_path, rd.err.c_str());
+        return 1;
+    }
+    const Header &hdr = rd.hdr;
+    if ((hdr.record_method != PRESS_NONE && hdr.record_method != PRESS_ZLIB) ||
+        (hdr.signal_method != PRESS_NONE && hdr.signal_method != PRESS_SVB_ZD)) {
+        ERROR("%s", "input uses a compression method this build does not support (zstd / ex-zd)");
+        return 1;
+    }
+    FILE *fout = stdout;
+    if (arg_out && !(fout = fopen(arg_out, "wb"))) {
+        ERROR("File '%s' could not be opened - %s.", arg_out, strerror(errno));
+        return 1;
+    }
+    setvbuf(fout, nullptr, _IOFBF, 1 << 20);
+
+    const bool need_gpu = hdr.record_method != PRESS_NONE || hdr.signal_method != PRESS_NONE || rec_out != PRESS_NONE ||
+                          sig_out != PRESS_NONE;
+    s5b_ctx_t *gpu = nullptr;
+    if (need_gpu) {
+        const int rc = s5b_ctx_create(-1, &gpu);
+        if (rc != S5B_OK) {
+            ERROR("cannot initialise the GPU codec: %s", s5b_strerror(rc));
+            return 1;
+        }
+    }
+    {
+        const std::string h = header_to_mem(hdr, fmt_out, rec_out, sig_out);
+        if (fwrite(h.data(), 1, h.size(), fout) != h.size()) {
+            ERROR("%s", "could not write the header");
+            return 1;
+        }
+    }
+
+    int ret = 0;
+    Batch b;
+    std::string err;
+    bool eof = false;
+    while (!eof && ret == 0) {
+        // ---- load (serial)
+        b.mem.clear();
+        while ((long)b.mem.size() < batch) {
+            b.mem.emplace_back();
+            const int rc = reader_next_mem(rd, b.mem.back());
+            if (rc <= 0) {
+                b.mem.pop_back();
+                if (rc < 0) {
+                    ERROR("%s", rd.err.c_str());
+                    ret = 1;
+                }
+                eof = true;
+                break;
+            }
+        }
+        const size_t n = b.mem.size();
+        if (n == 0 || ret) break;
+        b.rec.assign(n, Record());
+        b.aux_store.assign(n, std::vector<uint8_t>());
+        std::vector<const void *> ptrs(n);
+        std::vector<size_t> counts(n);
+
+        // ---- record decompression
+        std::vector<const uint8_t *> packed(n);
+        std::vector<size_t> packed_n(n);
+        if (rd.fmt == FMT_BINARY && hdr.record_method == PRESS_ZLIB) {
+            for (size_t i = 0; i < n; ++i) {
+                ptrs[i] = b.mem[i].data();
+                counts[i] = b.mem[i].size();
+            }
+            b.inflated.assign(n, nullptr);
+            b.inflated_n.assign(n, 0);
+            const int rc = s5b_depress_batch_host(gpu, S5B_COMPRESS_ZLIB, ptrs.data(), counts.data(), n, b.inflated.data(),
+                                                  b.inflated_n.data());
+            if (rc != S5B_OK) {
+                ERROR("record decompression failed: %s", s5b_strerror(rc));
+                ret = 1;
+                break;
+            }
+            for (size_t i = 0; i < n; ++i) {
+                packed[i] = static_cast<const uint8_t *>(b.inflated[i]);
+                packed_n[i] = b.inflated_n[i];
+            }
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                packed[i] = b.mem[i].data();
+                packed_n[i] = b.mem[i].size();
+            }
+        }
+        // ---- parse
+        std::atomic<int> bad(0);
+        if (rd.fmt == FMT_BINARY) {
+            parallel_for(n, threads, [&](size_t i) {
+                std::string e;
+                if (!record_parse_binary(packed[i], packed_n[i], hdr, hdr.signal_method, b.rec[i], e)) bad = 1;
+            });
+        } else {
+            parallel_for(n, threads, [&](size_t i) {
+                std::string e;
+                if (!record_parse_ascii(reinterpret_cast<const char *>(packed[i]), packed_n[i], hdr, b.rec[i], b.aux_store[i], e)) bad = 1;
+            });
+        }
+        if (bad) {
+            ERROR("%s", "a record could not be parsed");
+            ret = 1;
+            break;
+        }
+        // ---- signal decompression
+        std::vector<const int16_t *> sig(n);
+        if (rd.fmt == FMT_BINARY && hdr.signal_method == PRESS_SVB_ZD) {
+            for (size_t i = 0; i < n; ++i) {
+                ptrs[i] = b.rec[i].sig_bytes;
+                counts[i] = b.rec[i].sig_nbytes;
+            }
+            b.sig.assign(n, nullptr);
+            b.sig_n.assign(n, 0);
+            const int rc = s5b_depress_batch_host(gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, b.sig.data(),
+                                                  b.sig_n.data());
+            if (rc != S5B_OK) {
+                ERROR("signal decompression failed: %s", s5b_strerror(rc));
+                ret = 1;
+                break;
+            }
+            for (size_t i = 0; i < n; ++i) {
+                sig[i] = static_cast<const int16_t *>(b.sig[i]);
+                b.rec[i].len_raw_signal = b.sig_n[i] / 2;
+            }
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                sig[i] = reinterpret_cast<const int16_t *>(b.rec[i].sig_bytes);  // memcpy'd below where alignment matters
+                b.rec[i].len_raw_signal = b.rec[i].sig_nbytes / 2;
+            }
+        }
+
+        // ---- output
+        if (fmt_out == FMT_ASCII) {
+            std::vector<std::string> lines(n);
+            parallel_for(n, threads, [&](size_t i) {
+                Record &r = b.rec[i];
+                r.raw_signal.resize(r.len_raw_signal);
+                if (r.len_raw_signal) memcpy(r.raw_signal.data(), sig[i], r.len_raw_signal * 2);
+                record_to_ascii(r, hdr, lines[i]);
+                std::vector<int16_t>().swap(r.raw_signal);
+            });
+            for (size_t i = 0; i < n && ret == 0; ++i)
+                if (fwrite(lines[i].data(), 1, lines[i].size(), fout) != lines[i].size()) ret = 1;
+        } else {
+            // signal compression
+            std::vector<void *> svb(n, nullptr);
+            std::vector<size_t> svb_n(n, 0);
+            std::vector<const uint8_t *> store(n);
+            std::vector<size_t> store_n(n);
+            if (sig_out == PRESS_SVB_ZD) {
+                for (size_t i = 0; i < n; ++i) {
+                    ptrs[i] = sig[i];
+                    counts[i] = b.rec[i].len_raw_signal * 2;
+                }
+                const int rc = s5b_compress_batch_host(gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
+                if (rc != S5B_OK) {
+                    ERROR("signal compression failed: %s", s5b_strerror(rc));
+                    ret = 1;
+                }
+                for (size_t i = 0; i < n; ++i) {
+                    store[i] = static_cast<const uint8_t *>(svb[i]);
+                    store_n[i] = svb_n[i];
+                }
+            } else {
+                for (size_t i = 0; i < n; ++i) {
+                    store[i] = reinterpret_cast<const uint8_t *>(sig[i]);
+                    store_n[i] = b.rec[i].len_raw_signal * 2;
+                }
+            }
+            std::vector<std::vector<uint8_t>> rec_mem(n);
+            std::vector<uint32_t> splits(n, 0);
+            if (ret == 0) {
+                parallel_for(n, threads, [&](size_t i) {
+                    uint64_t at = 0;
+                    record_to_binary(b.rec[i], store[i], store_n[i], sig_out != PRESS_NONE, rec_mem[i], &at);
+                    // Huffman block split for the zlib encoder: where the svb-zd data bytes start
+                    if (sig_out == PRESS_SVB_ZD) splits[i] = (uint32_t)(at + 4 + (b.rec[i].len_raw_signal + 3) / 4);
+                });
+            }
+            for (void *p : svb) free(p);
+            std::vector<void *> z(n, nullptr);
+            std::vector<size_t> z_n(n, 0);
+            if (ret == 0 && rec_out == PRESS_ZLIB) {
+                for (size_t i = 0; i < n; ++i) {
+                    ptrs[i] = rec_mem[i].data();
+                    counts[i] = rec_mem[i].size();
+                }
+                const int rc = s5b_compress_records_host(gpu, ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
+                if (rc != S5B_OK) {
+                    ERROR("record compression failed: %s", s5b_strerror(rc));
+                    ret = 1;
+                }
+            }
+            for (size_t i = 0; i < n && ret == 0; ++i) {
+                const void *p = rec_out == PRESS_ZLIB ? z[i] : rec_mem[i].data();
+                const uint64_t sz = rec_out == PRESS_ZLIB ? z_n[i] : rec_mem[i].size();
+                if (fwrite(&sz, 8, 1, fout) != 1 || (sz && fwrite(p, 1, sz, fout) != sz)) ret = 1;  // slow5.c:4055-4060
+            }
+            for (void *p : z) free(p);
+        }
+        if (ret) ERROR("%s", "writing the output failed");
+        b.free_all();
+    }
+    b.free_all();
+    if (ret == 0 && fmt_out == FMT_BINARY && fwrite("5WOLB", 1, 5, fout) != 5) ret = 1;  // view.c:313
+    if (fout != stdout) {
+        if (fclose(fout) != 0) ret = 1;
+    } else {
+        fflush(fout);
+    }
+    reader_close(rd);
+    if (gpu) s5b_ctx_destroy(gpu);
+    return ret;
+}
+
+int main(int argc, char **argv) {
+    if (argc >= 2 && (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V"))) {
+        printf("slow5tools-b200 %s\n", s5b_version());
+        return 0;
+    }
+    if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
+        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n");
+        return argc < 2 ? 1 : 0;
+    }
+    if (!strcmp(argv[1], "view")) {
+        const int rc = view_main(argc - 1, argv + 1);
+        if (rc != 0) {
+            fprintf(stderr, "[main::ERROR] view failed\n");
+            return EXIT_FAILURE;
+        }
+        return 0;
+    }
+    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view)\n", argv[1]);
+    return EXIT_FAILURE;
+}

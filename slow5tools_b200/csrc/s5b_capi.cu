@@ -768,8 +768,8 @@ static int zlib_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size
     return first;
 }
 
-static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, size_t n,
-                              void **out_ptrs, size_t *out_n) {
+static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, const uint32_t *splits,
+                              size_t n, void **out_ptrs, size_t *out_n) {
     std::vector<uint64_t> in_off(n + 1), out_off(n + 1);
     std::vector<uint32_t> in_len(n), out_len(n);
     std::vector<int32_t> status(n);
@@ -793,7 +793,7 @@ static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const siz
     CU(ctx->h_stage_out.reserve(otot + 16));
     uint8_t *hin = static_cast<uint8_t *>(ctx->h_stage_in.p);
     for (size_t i = 0; i < n; ++i) memcpy(hin + in_off[i], ptrs[i], in_len[i]);
-    CU(s.d_meta.reserve(2 * (n + 1) * 8 + 3 * n * 4 + 64));
+    CU(s.d_meta.reserve(2 * (n + 1) * 8 + 4 * n * 4 + 64));
     CU(s.d_a.reserve(tot + 16));
     CU(s.d_b.reserve(otot + 16));
     uint64_t *d_in_off = static_cast<uint64_t *>(s.d_meta.p);
@@ -801,11 +801,13 @@ static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const siz
     uint32_t *d_in_len = reinterpret_cast<uint32_t *>(d_out_off + (n + 1));
     uint32_t *d_out_len = d_in_len + n;
     int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    uint32_t *d_split = reinterpret_cast<uint32_t *>(d_status + n);
+    if (splits) CU(cudaMemcpyAsync(d_split, splits, n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s.d_a.p, hin, tot, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_in_off, in_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_out_off, out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_in_len, in_len.data(), n * 4, cudaMemcpyHostToDevice, st));
-    DeflateArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), nullptr, n,
+    DeflateArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), splits ? d_split : nullptr, n,
                   static_cast<uint8_t *>(s.d_b.p), d_out_off, d_out_len, d_status, s.d_counter};
     CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
     ctx->launches += 1;
@@ -857,10 +859,18 @@ int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs,
         case S5B_COMPRESS_SVB_ZD: return svbzd_compress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_ZLIB: {
             DeviceGuard g(ctx->device);
-            return zlib_compress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+            return zlib_compress_ptrs(ctx, ptrs, counts, nullptr, n, out_ptrs, out_n);
         }
         default: return S5B_ERR_ARG;
     }
+}
+
+int s5b_compress_records_host(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, const uint32_t *splits,
+                              size_t n, void **out_ptrs, size_t *out_n) {
+    if (!ctx || (n && (!ptrs || !counts || !out_ptrs || !out_n))) return S5B_ERR_ARG;
+    if (n == 0) return S5B_OK;
+    DeviceGuard g(ctx->device);
+    return zlib_compress_ptrs(ctx, ptrs, counts, splits, n, out_ptrs, out_n);
 }
 
 int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts, size_t n,

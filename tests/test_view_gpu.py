@@ -1,0 +1,122 @@
+"""`slow5tools-b200 view` with the codec on the GPU against the reference binary and its goldens
+(test/test_view.sh:90-200): SLOW5 text and uncompressed BLOW5 byte-identical; GPU-compressed BLOW5 must be
+read back by the REFERENCE to the identical SLOW5 and stay within the size tolerance."""
+import ctypes as C
+import filecmp
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIX = os.path.join(ROOT, "tests", "golden", "fixtures")
+CLI = os.path.join(ROOT, "slow5tools_b200", "bin", "slow5tools-b200")
+REF = os.path.join(ROOT, "oracle", "_ref", "slow5tools_ref")
+have_ref = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/slow5tools_ref not present")
+
+
+def ours(*args):
+    r = subprocess.run([CLI, "view"] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    return r
+
+
+def ref(*args):
+    subprocess.check_call([REF, "view"] + list(args), stderr=subprocess.DEVNULL)
+
+
+def test_zlib_svb_to_slow5_matches_reference_golden(tmp_path):
+    out = tmp_path / "a.slow5"
+    ours(os.path.join(FIX, "exp_1_lossless_zlib_svb_v0.2.0.blow5"), "-o", str(out))
+    assert filecmp.cmp(out, os.path.join(FIX, "exp_1_lossless_v0.2.0.slow5"), shallow=False)   # test_view.sh golden
+    for name in ("zlib_svb-zd_multi_rg_v0.2.0", "exp_1_lossy_zlib"):
+        out = tmp_path / (name + ".slow5")
+        ours(os.path.join(FIX, name + ".blow5"), "-o", str(out), "-t", "4", "-K", "3")
+        assert filecmp.cmp(out, os.path.join(FIX, name + ".expected.slow5"), shallow=False), name
+
+
+@have_ref
+def test_to_uncompressed_blow5_byte_identical(tmp_path):
+    for name in ("exp_1_lossless_zlib_svb_v0.2.0", "zlib_svb-zd_multi_rg_v0.2.0", "zlib_svb-zd_v0.2.0"):
+        a, b = tmp_path / "ours.blow5", tmp_path / "ref.blow5"
+        ours(os.path.join(FIX, name + ".blow5"), "-o", str(a), "-c", "none", "-s", "none")
+        ref(os.path.join(FIX, name + ".blow5"), "-o", str(b), "-c", "none", "-s", "none")
+        assert filecmp.cmp(a, b, shallow=False), name
+        # svb-zd only: bit-exact signal codec, no zlib involved -> byte-identical file
+        ours(str(b), "-o", str(a), "-c", "none", "-s", "svb-zd")
+        c = tmp_path / "ref_svb.blow5"
+        ref(str(b), "-o", str(c), "-c", "none", "-s", "svb-zd")
+        assert filecmp.cmp(a, c, shallow=False), name
+
+
+@have_ref
+@pytest.mark.parametrize("flags", [[], ["-c", "zlib", "-s", "none"], ["-c", "zlib", "-s", "svb-zd", "-K", "2", "-t", "2"]])
+def test_gpu_compressed_files_are_read_by_the_reference(tmp_path, flags):
+    for name in ("exp_1_lossless_zlib_svb_v0.2.0", "zlib_svb-zd_multi_rg_v0.2.0"):
+        src = os.path.join(FIX, name + ".blow5")
+        mine, theirs = tmp_path / "mine.blow5", tmp_path / "theirs.blow5"
+        ours(src, "-o", str(mine), *flags)
+        ref(src, "-o", str(theirs), *[f for f in flags if f not in ("-K", "2", "-t")])
+        back, want = tmp_path / "back.slow5", tmp_path / "want.slow5"
+        ref(str(mine), "-o", str(back))            # the REFERENCE decodes the GPU-written file
+        ref(src, "-o", str(want))
+        assert filecmp.cmp(back, want, shallow=False), (name, flags)
+        assert os.path.getsize(mine) <= 1.03 * os.path.getsize(theirs), (os.path.getsize(mine), os.path.getsize(theirs))
+        again = tmp_path / "again.slow5"
+        ours(str(mine), "-o", str(again))          # and so does our own reader
+        assert filecmp.cmp(again, want, shallow=False)
+
+
+def test_slow5_input_to_compressed_blow5_roundtrip(tmp_path):
+    src = os.path.join(FIX, "exp_1_lossless_v0.2.0.slow5")
+    z, back = tmp_path / "z.blow5", tmp_path / "back.slow5"
+    ours(src, "-o", str(z))
+    ours(str(z), "-o", str(back))
+    assert filecmp.cmp(back, src, shallow=False)
+
+
+def test_low_level_file_api_roundtrip(tmp_path):
+    """slow5_open / slow5_get_next_mem / slow5_decode / slow5_encode / slow5_write_bytes twins."""
+    L = C.CDLL(os.path.join(ROOT, "slow5tools_b200", "libslow5b200.so"))
+    vp, sz = C.c_void_p, C.c_size_t
+    L.s5b_open.restype = vp
+    L.s5b_open.argtypes = [C.c_char_p, C.c_char_p]
+    L.s5b_get_next_mem.restype = vp
+    L.s5b_get_next_mem.argtypes = [C.POINTER(sz), vp]
+    L.s5b_decode.argtypes = [C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), vp]
+    L.s5b_encode.argtypes = [C.POINTER(vp), C.POINTER(sz), vp, vp]
+    L.s5b_write_bytes.argtypes = [vp, sz, vp]
+    for f in (L.s5b_close, L.s5b_hdr_write, L.s5b_rec_free):
+        f.argtypes = [vp]
+    L.s5b_hdr_copy.argtypes = [vp, vp]
+    L.s5b_set_press.argtypes = [vp, C.c_int, C.c_int]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [vp]
+    src = os.path.join(FIX, "zlib_svb-zd_multi_rg_v0.2.0.blow5")
+    out = tmp_path / "api.blow5"
+    fin = L.s5b_open(src.encode(), b"r")
+    fout = L.s5b_open(str(out).encode(), b"w")
+    assert fin and fout
+    assert L.s5b_hdr_copy(fout, fin) == 0 and L.s5b_set_press(fout, 1, 2) == 0 and L.s5b_hdr_write(fout) > 0
+    n_rec = 0
+    while True:
+        n = sz()
+        mem = vp(L.s5b_get_next_mem(C.byref(n), fin))
+        if not mem:
+            assert L.s5b_errno_value() == -1      # SLOW5_ERR_EOF
+            break
+        rec = vp()
+        assert L.s5b_decode(C.byref(mem), C.byref(n), C.byref(rec), fin) == 0
+        libc.free(mem)
+        enc, en = vp(), sz()
+        assert L.s5b_encode(C.byref(enc), C.byref(en), rec, fout) == 0
+        assert L.s5b_write_bytes(enc, en, fout) == en.value
+        libc.free(enc)
+        L.s5b_rec_free(rec)
+        n_rec += 1
+    assert n_rec == 7
+    assert L.s5b_close(fin) == 0 and L.s5b_close(fout) == 0
+    back = tmp_path / "api.slow5"
+    ours(str(out), "-o", str(back))
+    assert filecmp.cmp(back, os.path.join(FIX, "zlib_svb-zd_multi_rg_v0.2.0.expected.slow5"), shallow=False)
