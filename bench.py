@@ -166,6 +166,7 @@ def run_ours(args):
     import torch.distributed as dist
     import slow5tools_b200 as s5
     from slow5tools_b200 import synth
+    from slow5tools_b200.dist import max_over_ranks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,6 +232,54 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, enc_ms_max, dec_ms_max = t.tolist()
+
+    # ---- extras: the zlib record stage on the same batch (BASELINE config[2] shape at this batch size):
+    # deflate of every svb-zd stream (split hint = start of the data bytes) and inflate of the result, then the
+    # svb-zd decode of the inflated bytes must give back the signal (round-trip property at full size).
+    zx = None
+    if not args.no_zlib:
+        zslot = int(s5.lib.s5b_zlib_bound(slot))
+        zoff = torch.arange(R + 1, dtype=torch.int64, device="cuda") * zslot
+        zbuf = torch.zeros(R * zslot + 16, dtype=torch.uint8, device="cuda")
+        zlen = torch.zeros(R, dtype=torch.int32, device="cuda")
+        zst = torch.ones(R, dtype=torch.int32, device="cuda")
+        split = torch.full((R,), 4 + (N + 3) // 4, dtype=torch.int32, device="cuda")
+        svb2 = torch.zeros_like(svb)
+        svb2_len = torch.zeros_like(svb_len)
+        ist = torch.ones(R, dtype=torch.int32, device="cuda")
+        KZ = max(2, min(K, 5))
+        def z_step():
+            cdc.zlib_deflate_dev(svb, ooff, svb_len, zbuf, zoff, zlen, zst, split=split)
+            cdc.zlib_inflate_dev(zbuf, zoff, zlen, svb2, ooff, svb2_len, ist)
+        for _ in range(2):
+            z_step()
+        barrier()
+        zev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KZ)]
+        for k in range(KZ):
+            zev[k][0].record()
+            cdc.zlib_deflate_dev(svb, ooff, svb_len, zbuf, zoff, zlen, zst, split=split)
+            zev[k][1].record()
+            cdc.zlib_inflate_dev(zbuf, zoff, zlen, svb2, ooff, svb2_len, ist)
+            zev[k][2].record()
+        barrier()
+        def_ms = sum(e[0].elapsed_time(e[1]) for e in zev) / KZ
+        inf_ms = sum(e[1].elapsed_time(e[2]) for e in zev) / KZ
+        assert int(zst.abs().sum()) == 0 and int(ist.abs().sum()) == 0 and torch.equal(svb2_len, svb_len), "zlib stage failed"
+        cdc.svbzd_decode_dev(svb2, ooff, svb2_len, back, soff, n2, st_d)
+        torch.cuda.synchronize()
+        assert int(st_d.abs().sum()) == 0 and torch.equal(back, sig), "zlib round trip failed"
+        zbytes = int(zlen.sum())
+        def_ms, inf_ms = max_over_ranks([def_ms, inf_ms])
+        zx = {"deflate_ms": def_ms, "inflate_ms": inf_ms, "zlib_bytes_per_read": zbytes / R,
+              "zlib_ratio_on_svb_stream": zbytes / svb_bytes,
+              "deflate_reads_per_s": R / (def_ms * 1e-3), "inflate_reads_per_s": R / (inf_ms * 1e-3),
+              "deflate_GBps_in_plus_out": (svb_bytes + zbytes) / (def_ms * 1e-3) / 1e9,
+              "inflate_GBps_in_plus_out": (svb_bytes + zbytes) / (inf_ms * 1e-3) / 1e9,
+              "full_encode_reads_per_s": R / ((enc_ms_max + def_ms) * 1e-3),
+              "full_decode_reads_per_s": R / ((dec_ms_max + inf_ms) * 1e-3),
+              "note": "zlib stage run on the svb-zd streams of the same batch (a BLOW5 record minus ~70 B of fixed fields); "
+                      "latency/issue bound kernels, HBM fraction reported for completeness"}
+        del zbuf, svb2
 
     if args.profile:
         if rank == 0:
@@ -302,6 +351,7 @@ def run_ours(args):
             "e2e": {"value": R * world * KE / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": KE, "api": "s5b_svbzd_encode_host + s5b_svbzd_decode_host (pinned host slabs)"},
             "gpu_launches": int(launches),
+            "zlib_stage": zx,
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
@@ -319,6 +369,7 @@ def main():
     ap.add_argument("--reads", type=int, default=100000, help="reads per GPU")
     ap.add_argument("--samples", type=int, default=4096)
     ap.add_argument("--profile", action="store_true", help="device-resident loop only (for runs under ncu)")
+    ap.add_argument("--no-zlib", action="store_true", help="skip the zlib-stage extras")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

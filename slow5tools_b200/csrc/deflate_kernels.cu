@@ -139,26 +139,31 @@ __device__ void huffman_lengths(uint32_t *hist, int n, int limit, uint8_t *len, 
         const int root = next - 1;
         weight[root] = 0;
         for (int v = root - 1; v >= 0; --v) weight[v] = weight[parent[v]] + 1;
-        // length limiting (the bl_count fix-up zlib's gen_bitlen does when the tree is too deep)
+        // length limiting: clamp the depths to `limit`, measure by how much the Kraft sum now exceeds 1 (in units
+        // of 2^-limit), and repair it one unit at a time the way zlib's gen_bitlen does: push a leaf from the
+        // deepest level above the limit one level down and hang one clamped leaf next to it.
         for (int b = 0; b <= 15; ++b) bl_count[b] = 0;
-        int overflow = 0;
+        bool clamped = false;
+        uint32_t kraft = 0;
         for (int i = 0; i < used; ++i) {
             int dpt = (int)weight[i];
             if (dpt > limit) {
                 dpt = limit;
-                ++overflow;
+                clamped = true;
             }
             bl_count[dpt]++;
+            kraft += 1u << (limit - dpt);
         }
-        if (overflow > 0) {
-            do {
+        if (clamped) {
+            int excess = (int)kraft - (1 << limit);
+            while (excess > 0) {
                 int bits = limit - 1;
                 while (bl_count[bits] == 0) --bits;
                 bl_count[bits]--;
                 bl_count[bits + 1] += 2;
                 bl_count[limit]--;
-                overflow -= 2;
-            } while (overflow > 0);
+                --excess;
+            }
             // hand the lengths out again: longest codes to the rarest symbols (leaves are sorted by weight)
             int i = 0;
             for (int bits = limit; bits >= 1; --bits)

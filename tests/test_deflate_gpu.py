@@ -109,6 +109,21 @@ def test_skewed_frequencies_hit_the_length_limit(cdc):
     assert zlib.decompress(res[0]) == data and zlib.decompress(res[1]) == data * 3
 
 
+def test_code_length_alphabet_hits_its_7_bit_limit(cdc):
+    """The 19-symbol code-length code is limited to 7 bits; skewed header statistics must still give a complete
+    code (regression: 1 stream in 100k was rejected by zlib with 'invalid code lengths set')."""
+    rng = np.random.default_rng(17)
+    bufs = []
+    for k in range(400):
+        # byte distributions that give literal code lengths spread over many different values
+        p = rng.dirichlet(np.full(256, 0.05 + 0.02 * (k % 7)))
+        bufs.append(rng.choice(256, size=int(rng.integers(200, 6000)), p=p).astype(np.uint8).tobytes())
+    res, st = gpu_deflate(cdc, bufs)
+    assert (st == 0).all()
+    for z, raw in zip(res, bufs):
+        assert zlib.decompress(z) == raw
+
+
 def test_ratio_within_tolerance_of_zlib_level6(cdc, oracle):
     recs, splits = svb_records(oracle, 300, 4096, seed=42)
     ref = sum(len(zlib.compress(r, 6)) for r in recs)
