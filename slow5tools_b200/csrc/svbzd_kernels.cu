@@ -327,7 +327,9 @@ struct __align__(128) DecWarpSmem {
     unsigned long long bar[DEC_NB];
 };
 
-__device__ __forceinline__ uint32_t zz_dec(uint32_t v) { return (v >> 1) ^ (0u - (v & 1u)); }
+// zigzag decode (streamvbyte_zigzag.c:23-25): (v >> 1) ^ -(v & 1) == (v >> 1) - (v & 1) * v, which is one
+// instruction shorter (LOP, SHF, IMAD)
+__device__ __forceinline__ uint32_t zz_dec(uint32_t v) { return (v >> 1) - (v & 1u) * v; }
 
 // Per-read decode state (warp-uniform unless noted).
 struct DecState {
@@ -451,7 +453,7 @@ __device__ __forceinline__ bool dec_iteration(DecState &s, const uint8_t *ring, 
     return true;
 }
 
-__global__ void __launch_bounds__(DEC_WARPS * 32) svbzd_decode_kernel(const SvbDecodeArgs a) {
+__global__ void __launch_bounds__(DEC_WARPS * 32, 5) svbzd_decode_kernel(const SvbDecodeArgs a) {
     __shared__ DecWarpSmem smem[DEC_WARPS];
     const int lane = threadIdx.x & 31;
     DecWarpSmem &ws = smem[threadIdx.x >> 5];
