@@ -43,6 +43,9 @@ struct __align__(128) InfWarpSmem {
     uint16_t cl_sorted[20];
     uint16_t cl_count[16];
     uint16_t tmp_base[16];
+    uint16_t lit_fcode[16], lit_fidx[16];    // canonical first code / first sorted index per length
+    uint16_t dist_fcode[16], dist_fidx[16];
+    uint16_t cl_fcode[16], cl_fidx[16];
     uint8_t lens[384];                        // code lengths: lit/len at 0, dist at 288; scratch from 32
     unsigned long long bar[INF_NB];
 };
@@ -135,27 +138,25 @@ struct BitReader {
     }
 };
 
-// canonical (bit-serial) decode for codes longer than the fast table; returns symbol or -1 (invalid code)
-// or -2 (ran out of bits)
+// canonical decode for codes longer than the first-level table: the first `fast_bits` bits are already known
+// not to form a code, so the walk starts at length fast_bits + 1 with the per-length first code / first index
+// that build_table left in shared memory.  Returns the symbol, -1 (no such code) or -2 (ran out of bits).
 __device__ __forceinline__ int slow_decode(const BitReader &br, const uint16_t *count, const uint16_t *sorted,
+                                           const uint16_t *fcode, const uint16_t *fidx, const int fast_bits,
                                            uint32_t *used) {
-    uint32_t code = 0, first = 0, index = 0;
-    uint64_t b = br.bb;
-    for (uint32_t len = 1; len <= 15; ++len) {
+    uint32_t code = __brev((uint32_t)br.bb) >> (32 - fast_bits);  // stream bits are the code MSB first
+    uint64_t b = br.bb >> fast_bits;
+    for (uint32_t len = fast_bits + 1; len <= 15; ++len) {
         if (len > br.nb) return -2;
-        code |= (uint32_t)(b & 1u);
+        code = (code << 1) | (uint32_t)(b & 1u);
         b >>= 1;
-        const uint32_t cnt = count[len];
-        if (code < first + cnt) {  // first <= code always holds here
+        const uint32_t d = code - fcode[len];
+        if (d < count[len]) {
             *used = len;
-            return sorted[index + (code - first)];
+            return sorted[fidx[len] + d];
         }
-        index += cnt;
-        first += cnt;
-        first <<= 1;
-        code <<= 1;
     }
-    return -1;
+    return br.nb < 15 ? -2 : -1;
 }
 
 // ---- Huffman table construction (whole warp) ----------------------------------------------------
@@ -163,7 +164,8 @@ __device__ __forceinline__ int slow_decode(const BitReader &br, const uint16_t *
 // table fast[] of 2^fast_bits entries.  Returns 0 ok, 1 over-subscribed, 2 incomplete (caller decides,
 // zlib's inflate_table rules: inftrees.c).
 __device__ int build_table(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *fast,
-                           int fast_bits, uint16_t *base /*[16] scratch*/, int lane, int *max_len_out) {
+                           int fast_bits, uint16_t *base /*[16] scratch*/, uint16_t *fcode, uint16_t *fidx, int lane,
+                           int *max_len_out) {
     if (lane < 16) count[lane] = 0;
     __syncwarp();
     for (int s = lane; s < n; s += 32) {
@@ -195,11 +197,16 @@ __device__ int build_table(const uint8_t *lens, int n, uint16_t *count, uint16_t
     *max_len_out = maxl;
     if (status == 1) return 1;
     if (lane < 16) {
-        uint32_t v = 0;
+        uint32_t v = 0, fc = 0;
 #pragma unroll
         for (int l = 1; l <= 15; ++l)
-            if (l == lane) v = first_idx[l];
+            if (l == lane) {
+                v = first_idx[l];
+                fc = first_code[l];
+            }
         base[lane] = (uint16_t)v;
+        fidx[lane] = (uint16_t)v;
+        fcode[lane] = (uint16_t)fc;
     }
     for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
     __syncwarp();
@@ -412,13 +419,54 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                         }
                         continue;
                     }
-                    // ---- Huffman-coded symbol
+                    // ---- Huffman-coded symbols.  Fast loop first: literals with short codes, everything in registers.
+                    // A table entry is (symbol << 4) | length: 1..4095 means "literal, length known"; 0 (long code)
+                    // and >= 4096 (end of block / length symbol) leave the loop for the general code below.
+                    if (store) {
+                        uint64_t bb = br.bb;
+                        uint32_t nb = br.nb, sp = spos;
+                        const uint16_t *fast = ws.lit_fast;
+                        uint8_t *stage = ws.stage;
+                        for (;;) {
+                            if (nb <= 32) {
+                                br.bb = bb;
+                                br.nb = nb;
+                                br.refill();
+                                bb = br.bb;
+                                nb = br.nb;
+                                if (nb < 15) break;  // input nearly exhausted: let the careful path decide
+                            }
+                            uint32_t e = fast[(uint32_t)bb & ((1u << LIT_FAST_BITS) - 1u)];
+                            if (sp >= (uint32_t)INF_STAGE) break;
+                            if (e - 1u >= 4095u) {
+                                if (e != 0) break;  // end of block or a length symbol
+                                // code longer than the table: short canonical walk (nb >= 15 here)
+                                br.bb = bb;
+                                br.nb = nb;
+                                uint32_t l2 = 0;
+                                const int s2 = slow_decode(br, ws.lit_count, ws.lit_sorted, ws.lit_fcode, ws.lit_fidx, LIT_FAST_BITS, &l2);
+                                if (s2 < 0 || s2 >= 256) break;  // invalid or non-literal: the careful path redoes it
+                                e = ((uint32_t)s2 << 4) | l2;
+                            }
+                            const uint32_t l = e & 15u;
+                            stage[sp++] = (uint8_t)(e >> 4);
+                            bb >>= l;
+                            nb -= l;
+                        }
+                        br.bb = bb;
+                        br.nb = nb;
+                        spos = sp;
+                        if (spos >= INF_STAGE) {
+                            ev = EV_FLUSH;
+                            break;
+                        }
+                    }
                     br.refill();
                     uint32_t e = ws.lit_fast[br.peek(LIT_FAST_BITS)];
                     uint32_t l = e & 15u;
                     int sym = (int)(e >> 4);
                     if (l == 0) {
-                        sym = slow_decode(br, ws.lit_count, ws.lit_sorted, &l);
+                        sym = slow_decode(br, ws.lit_count, ws.lit_sorted, ws.lit_fcode, ws.lit_fidx, LIT_FAST_BITS, &l);
                         if (sym < 0) {
                             ev = EV_END;
                             ev_a = sym == -2 ? END_TRUNC : END_ERR;
@@ -468,7 +516,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                         dl = de & 15u;
                         dsym = (int)(de >> 4);
                         if (dl == 0) {
-                            dsym = slow_decode(br, ws.dist_count, ws.dist_sorted, &dl);
+                            dsym = slow_decode(br, ws.dist_count, ws.dist_sorted, ws.dist_fcode, ws.dist_fidx, DIST_FAST_BITS, &dl);
                             if (dsym == -1) err = true;
                             if (dsym == -2) trunc = true;
                         } else if (dl > br.nb) {
@@ -579,7 +627,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                     int maxl = 0;
                     if (!bad) {
                         // "invalid code lengths set": the code-length code must be complete (inftrees.c, type CODES)
-                        if (build_table(ws.lens, 19, ws.cl_count, ws.cl_sorted, ws.cl_fast, 7, ws.tmp_base, lane, &maxl) != 0) bad = 2;
+                        if (build_table(ws.lens, 19, ws.cl_count, ws.cl_sorted, ws.cl_fast, 7, ws.tmp_base, ws.cl_fcode, ws.cl_fidx, lane, &maxl) != 0) bad = 2;
                     }
                     __syncwarp();
                     // the hlit + hdist code lengths, run-length coded, lane 0 -> lens[32 ..)
@@ -650,12 +698,12 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                 }
                 if (!bad) {
                     int maxl = 0;
-                    int st = build_table(ws.lens, hlit, ws.lit_count, ws.lit_sorted, ws.lit_fast, LIT_FAST_BITS, ws.tmp_base, lane, &maxl);
+                    int st = build_table(ws.lens, hlit, ws.lit_count, ws.lit_sorted, ws.lit_fast, LIT_FAST_BITS, ws.tmp_base, ws.lit_fcode, ws.lit_fidx, lane, &maxl);
                     // inftrees.c: over-subscribed never; incomplete only for a single 1-bit code
                     if (st == 1 || (st == 2 && maxl != 1)) bad = 2;  // "invalid literal/lengths set"
                     __syncwarp();
                     if (!bad) {
-                        st = build_table(ws.lens + 288, hdist, ws.dist_count, ws.dist_sorted, ws.dist_fast, DIST_FAST_BITS, ws.tmp_base, lane, &maxl);
+                        st = build_table(ws.lens + 288, hdist, ws.dist_count, ws.dist_sorted, ws.dist_fast, DIST_FAST_BITS, ws.tmp_base, ws.dist_fcode, ws.dist_fidx, lane, &maxl);
                         if (st == 1 || (st == 2 && maxl > 1)) bad = 2;  // "invalid distances set"
                     }
                     __syncwarp();
