@@ -160,6 +160,21 @@ int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, 
 int s5b_compress_records_host(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, const uint32_t *splits,
                               size_t n, void **out_ptrs, size_t *out_n);
 
+/* Whole-batch BLOW5 record transcoding with everything between the two copies on the device: the body of
+ * slow5_convert_parallel's batch loop (src/view.c:254-301: work_db over depress_parse_rec_to_mem) for
+ * blow5 -> blow5 conversions.  h_in holds n packed records exactly as stored in the file (record i =
+ * h_in[rec_off[i] .. +rec_len[i]), size prefixes excluded), compressed with (in_rec, in_sig); h_out receives the
+ * output FILE IMAGE -- [u64 size][record bytes] per record, in order -- compressed with (out_rec, out_sig), ready
+ * for one fwrite.  Methods: S5B_COMPRESS_NONE / ZLIB for records, NONE / SVB_ZD for signals.  Pinned h_in / h_out
+ * (s5b_host_alloc) avoid staging copies.  Returns 0, the first per-record error, or S5B_ERR_NOSPACE with *out_bytes =
+ * bytes needed when out_cap is too small. */
+int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
+                          uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
+                          uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes);
+/* page-locked host memory for the slab entry points (cudaHostAlloc / cudaFreeHost) */
+void *s5b_host_alloc(size_t bytes);
+void s5b_host_free(void *p);
+
 /* ---- level 1: single buffers ---------------------------------------------------------------
  * Same contract as slow5_ptr_compress_solo / slow5_ptr_depress_solo: returns a malloc()'d buffer,
  * *n its size; NULL and *n = 0 on failure (s5b_last_error() holds the code, the twin of the

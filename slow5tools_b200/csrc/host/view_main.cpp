@@ -12,9 +12,15 @@
 // Same flags, defaults and failure behaviour (any record error -> message on stderr, exit status 1).
 // There is no CPU codec here: without a CUDA device the command fails.
 #include <getopt.h>
+#include <unistd.h>
+#include <cerrno>
 
 #include <atomic>
+#include <chrono>
 #include <cinttypes>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -87,6 +93,235 @@ struct Batch {
         sig.clear();
     }
 };
+
+// ---- blow5 -> blow5: three-stage pipeline (read | GPU transcode | write) over pinned chunks -------------------
+// The reader fills a pinned chunk with packed records straight from the file (one record-boundary walk, no
+// per-record allocation); the GPU stage is one s5b_blow5_recode_host call per chunk (one H2D, kernels, one D2H of
+// the finished file image); the writer issues one fwrite per chunk.  Replaces the per-record
+// malloc/fread ... fwrite/free loops of src/view.c:265-299.
+struct Chunk {
+    uint8_t *in = nullptr, *out = nullptr;
+    uint64_t in_cap = 0, out_cap = 0, in_bytes = 0, out_bytes = 0;
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> len;
+    bool eof = false;
+    int err = 0;
+};
+struct ChunkQueue {
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<Chunk *> q;
+    void push(Chunk *c) {
+        {
+            std::lock_guard<std::mutex> l(m);
+            q.push_back(c);
+        }
+        cv.notify_one();
+    }
+    Chunk *pop() {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return !q.empty(); });
+        Chunk *c = q.front();
+        q.pop_front();
+        return c;
+    }
+};
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int sig_out, long batch) {
+    (void)batch;
+    const Header &hdr = rd.hdr;
+    const bool timing = getenv("S5B_TIMING") != nullptr;
+    const double t_begin = now_s();
+    double t_gpu = 0, t_wait = 0;
+    const uint64_t target = 32ull << 20;
+    const int NCH = 3;
+    Chunk chunks[NCH];
+    ChunkQueue free_q, full_q, done_q;
+    // output is at most ~2.4x the input when decompressing zlib+svb-zd records and smaller when compressing; a
+    // chunk whose image does not fit is retried with a larger buffer
+    const bool expanding = hdr.record_method != PRESS_NONE || hdr.signal_method != PRESS_NONE;
+    for (int i = 0; i < NCH; ++i) {
+        chunks[i].in_cap = target + (8u << 20);
+        chunks[i].in = static_cast<uint8_t *>(s5b_host_alloc(chunks[i].in_cap));
+        chunks[i].out_cap = (expanding ? 3 : 1) * target + (8u << 20);
+        chunks[i].out = static_cast<uint8_t *>(s5b_host_alloc(chunks[i].out_cap));
+        if (!chunks[i].in || !chunks[i].out) {
+            ERROR("%s", "cannot allocate pinned staging memory");
+            return 1;
+        }
+        free_q.push(&chunks[i]);
+    }
+    if (timing) fprintf(stderr, "[timing] pinned alloc %.3f s\n", now_s() - t_begin);
+    // the header was consumed through stdio; continue with plain read() from the same position
+    const int fd = fileno(rd.fp);
+    const off_t start = ftello(rd.fp);
+    if (lseek(fd, start, SEEK_SET) < 0) {
+        ERROR("%s", "cannot seek in the input file");
+        return 1;
+    }
+    std::string rerr;
+    std::thread reader([&] {
+        // big sequential read()s straight into the pinned chunk; records are walked in place (u64 size chain,
+        // slow5.c:3237-3271) and a record cut by the end of the chunk is carried over to the next one
+        std::vector<uint8_t> carry;
+        bool eof = false;
+        while (!eof) {
+            Chunk *c = free_q.pop();
+            c->off.clear();
+            c->len.clear();
+            c->eof = false;
+            c->err = 0;
+            uint64_t filled = carry.size();
+            if (filled > c->in_cap) {  // one record larger than a chunk: grow
+                s5b_host_free(c->in);
+                c->in_cap = filled + target;
+                c->in = static_cast<uint8_t *>(s5b_host_alloc(c->in_cap));
+            }
+            if (!c->in) {
+                rerr = "cannot allocate pinned staging memory";
+                c->err = 1;
+                c->eof = true;
+                full_q.push(c);
+                break;
+            }
+            if (filled) memcpy(c->in, carry.data(), filled);
+            carry.clear();
+            bool file_end = false;
+            while (filled < c->in_cap) {
+                const ssize_t got = read(fd, c->in + filled, c->in_cap - filled);
+                if (got < 0) {
+                    rerr = std::string("read failed: ") + strerror(errno);
+                    c->err = 1;
+                    file_end = true;
+                    break;
+                }
+                if (got == 0) {
+                    file_end = true;
+                    break;
+                }
+                filled += (uint64_t)got;
+            }
+            uint64_t pos = 0;
+            while (!c->err) {
+                const uint64_t left = filled - pos;
+                if (file_end && left == 5 && memcmp(c->in + pos, "5WOLB", 5) == 0) {  // end-of-file marker
+                    pos += 5;
+                    eof = true;
+                    break;
+                }
+                if (left < 8) {
+                    if (file_end) {
+                        rerr = "blow5 file is truncated or has no end-of-file marker";
+                        c->err = 1;
+                    }
+                    break;
+                }
+                uint64_t size;
+                memcpy(&size, c->in + pos, 8);
+                if (size > (1ull << 32) - 64) {
+                    rerr = "implausible record size (corrupt file?)";
+                    c->err = 1;
+                    break;
+                }
+                if (left < 8 + size) {
+                    if (file_end) {
+                        rerr = "blow5 record is truncated";
+                        c->err = 1;
+                    }
+                    break;
+                }
+                c->off.push_back(pos + 8);
+                c->len.push_back((uint32_t)size);
+                pos += 8 + size;
+            }
+            if (c->err) eof = true;
+            if (!eof) {
+                if (pos == 0 && !file_end && filled == c->in_cap) {
+                    // not even one whole record fits: carry everything, the next round grows the buffer
+                    carry.assign(c->in, c->in + filled);
+                    uint64_t size;
+                    memcpy(&size, c->in, 8);
+                    carry.reserve(size + 8);
+                } else {
+                    carry.assign(c->in + pos, c->in + filled);
+                }
+                if (file_end && carry.empty() && c->len.empty()) {  // file ended without a marker
+                    rerr = "blow5 file is truncated or has no end-of-file marker";
+                    c->err = 1;
+                    eof = true;
+                }
+            }
+            c->in_bytes = pos;
+            c->eof = eof;
+            full_q.push(c);
+        }
+    });
+    int wret = 0;
+    const int ofd = fileno(fout);
+    fflush(fout);
+    std::thread writer([&] {
+        for (;;) {
+            Chunk *c = done_q.pop();
+            if (!c) break;
+            uint64_t done = 0;
+            while (!wret && done < c->out_bytes) {
+                const ssize_t w = write(ofd, c->out + done, c->out_bytes - done);
+                if (w <= 0) wret = 1;
+                else done += (uint64_t)w;
+            }
+            free_q.push(c);
+        }
+    });
+    int ret = 0;
+    for (;;) {
+        const double tw = now_s();
+        Chunk *c = full_q.pop();
+        t_wait += now_s() - tw;
+        const double tg = now_s();
+        const bool last = c->eof;
+        if (c->err && ret == 0) {
+            ERROR("%s", rerr.c_str());
+            ret = 1;
+        }
+        c->out_bytes = 0;
+        if (ret == 0 && !c->len.empty()) {
+            int rc = s5b_blow5_recode_host(gpu, hdr.record_method, hdr.signal_method, rec_out, sig_out, c->in, c->in_bytes,
+                                           c->off.data(), c->len.data(), c->len.size(), c->out, c->out_cap, &c->out_bytes);
+            if (rc == S5B_ERR_NOSPACE && c->out_bytes > c->out_cap) {  // image larger than the staging buffer: grow, retry
+                s5b_host_free(c->out);
+                c->out_cap = c->out_bytes + (8u << 20);
+                c->out = static_cast<uint8_t *>(s5b_host_alloc(c->out_cap));
+                rc = c->out ? s5b_blow5_recode_host(gpu, hdr.record_method, hdr.signal_method, rec_out, sig_out, c->in, c->in_bytes,
+                                                    c->off.data(), c->len.data(), c->len.size(), c->out, c->out_cap, &c->out_bytes)
+                            : S5B_ERR_MEM;
+            }
+            if (rc != S5B_OK) {
+                ERROR("record conversion failed: %s", s5b_strerror(rc));
+                ret = 1;
+                c->out_bytes = 0;
+            }
+        }
+        t_gpu += now_s() - tg;
+        done_q.push(c);
+        if (last) break;
+    }
+    reader.join();
+    done_q.push(nullptr);
+    writer.join();
+    if (wret) {
+        ERROR("%s", "writing the output failed");
+        ret = 1;
+    }
+    if (timing)
+        fprintf(stderr, "[timing] fast path total %.3f s: gpu calls %.3f s, waiting for the reader %.3f s\n", now_s() - t_begin,
+                t_gpu, t_wait);
+    // the pinned chunks are left to process teardown (freeing ~0.5 GB of page-locked memory costs more than it is worth)
+    return ret;
+}
 
 }  // namespace
 
@@ -195,6 +430,7 @@ int view_main(int argc, char **argv) {
     const bool need_gpu = hdr.record_method != PRESS_NONE || hdr.signal_method != PRESS_NONE || rec_out != PRESS_NONE ||
                           sig_out != PRESS_NONE;
     s5b_ctx_t *gpu = nullptr;
+    const double t_ctx = now_s();
     if (need_gpu) {
         const int rc = s5b_ctx_create(-1, &gpu);
         if (rc != S5B_OK) {
@@ -202,6 +438,7 @@ int view_main(int argc, char **argv) {
             return 1;
         }
     }
+    if (getenv("S5B_TIMING")) fprintf(stderr, "[timing] context create %.3f s\n", now_s() - t_ctx);
     {
         const std::string h = header_to_mem(hdr, fmt_out, rec_out, sig_out);
         if (fwrite(h.data(), 1, h.size(), fout) != h.size()) {
@@ -214,6 +451,11 @@ int view_main(int argc, char **argv) {
     Batch b;
     std::string err;
     bool eof = false;
+    if (rd.fmt == FMT_BINARY && fmt_out == FMT_BINARY && need_gpu && !getenv("S5B_VIEW_SLOW_PATH")) {
+        // blow5 -> blow5: whole batches stay on the device (pinned chunk pipeline)
+        ret = view_fast_binary(rd, fout, gpu, rec_out, sig_out, batch);
+        eof = true;
+    }
     while (!eof && ret == 0) {
         // ---- load (serial)
         b.mem.clear();
@@ -382,14 +624,16 @@ int view_main(int argc, char **argv) {
         b.free_all();
     }
     b.free_all();
-    if (ret == 0 && fmt_out == FMT_BINARY && fwrite("5WOLB", 1, 5, fout) != 5) ret = 1;  // view.c:313
+    fflush(fout);
+    if (ret == 0 && fmt_out == FMT_BINARY && write(fileno(fout), "5WOLB", 5) != 5) ret = 1;  // view.c:313
     if (fout != stdout) {
         if (fclose(fout) != 0) ret = 1;
     } else {
         fflush(fout);
     }
     reader_close(rd);
-    if (gpu) s5b_ctx_destroy(gpu);
+    // the context (streams, device slabs) is left to process teardown: an orderly destroy costs ~0.1 s for nothing
+    if (gpu && getenv("S5B_ORDERLY_EXIT")) s5b_ctx_destroy(gpu);
     return ret;
 }
 

@@ -1,0 +1,208 @@
+// record_kernels.cu -- the glue kernels that keep a whole BLOW5 batch on the device between the codec kernels:
+// find the signal inside packed records (binary record layout, slow5.c:2811-2950 / :3928-4074), size the next
+// stage's slots, gather packed records, and build the output file image ([u64 size][record]..., slow5.c:4055-4060)
+// so the host only does one H2D, one D2H and one fwrite per batch.  Plain byte moving: one warp per record.
+#include "s5b_kernels.h"
+#include "s5b_ptx.cuh"
+#include "../../include/slow5b200.h"
+
+namespace s5b {
+
+namespace {
+
+__device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+
+// warp-cooperative copy of n bytes, any alignment on either side
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    const uintptr_t ds = reinterpret_cast<uintptr_t>(dst), ss = reinterpret_cast<uintptr_t>(src);
+    if (((ds ^ ss) & 15u) == 0) {
+        // same phase: byte head, 128-bit body, byte tail
+        uint32_t head = (uint32_t)((16u - (ds & 15u)) & 15u);
+        if (head > n) head = n;
+        if (lane < (int)head) dst[lane] = src[lane];
+        const uint32_t body = (n - head) >> 4;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+        for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
+        for (uint32_t i = head + (body << 4) + lane; i < n; i += 32) dst[i] = src[i];
+    } else if (((ds ^ ss) & 3u) == 0) {
+        uint32_t head = (uint32_t)((4u - (ds & 3u)) & 3u);
+        if (head > n) head = n;
+        if (lane < (int)head) dst[lane] = src[lane];
+        const uint32_t body = (n - head) >> 2;
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src + head);
+        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+        for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
+        for (uint32_t i = head + (body << 2) + lane; i < n; i += 32) dst[i] = src[i];
+    } else {
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+}
+
+constexpr int RK_WARPS = 8;
+
+__global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
+                                  int sig_is_svb, RecArrays a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint8_t *p = rec + rec_off[r];
+    const uint64_t len = rec_len[r];
+    int32_t st = S5B_OK;
+    uint32_t head = 0, ns = 0, sig_at = 0, sig_bytes = 0, aux = 0;
+    if (len < 2) {
+        st = S5B_ERR_PRESS;
+    } else {
+        const uint32_t rid = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+        head = 2 + rid + 4 + 32;
+        if ((uint64_t)head + 8 > len) {
+            st = S5B_ERR_PRESS;
+        } else {
+            const uint64_t lrs = ld_u64_unaligned(p + head);
+            sig_at = head + 8;
+            // the field counts samples for a raw signal and bytes for a compressed one (slow5.c:3983-3987)
+            const uint64_t sb = sig_is_svb ? lrs : lrs * 2;
+            if (sb > len - sig_at || (sig_is_svb && sb < 4)) {
+                st = S5B_ERR_PRESS;
+            } else {
+                sig_bytes = (uint32_t)sb;
+                if (sig_is_svb) {
+                    const uint8_t *q = p + sig_at;
+                    ns = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+                } else {
+                    ns = (uint32_t)lrs;
+                }
+                aux = (uint32_t)(len - sig_at - sb);
+            }
+        }
+    }
+    a.head_len[r] = head;
+    a.n_samples[r] = st == S5B_OK ? ns : 0;
+    a.sig_at[r] = sig_at;
+    a.sig_bytes[r] = sig_bytes;
+    a.aux_len[r] = aux;
+    a.status[r] = st;
+}
+
+__global__ void rec_plan_kernel(int mode, uint64_t n, RecArrays a, const uint32_t *aux_in, uint32_t param, uint32_t *out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t v = 0;
+    const uint32_t ns = a.n_samples[r];
+    switch (mode) {
+        case PLAN_SIG_SAMPLES: v = ns; break;                                       // scanned with align 8 (samples)
+        case PLAN_SVB_BOUND: v = 4u + (ns + 3u) / 4u + 3u * ns; break;              // s5b_svbzd_bound
+        case PLAN_PACKED_LEN: v = a.head_len[r] + 8u + aux_in[r] + a.aux_len[r]; break;  // aux_in = signal bytes to store
+        case PLAN_ZLIB_BOUND: v = aux_in[r] + 6u * (aux_in[r] / 6144u + 2u) + 8u; break; // == deflate_bound() (DEF_BLOCK 6144)
+        case PLAN_IMAGE_LEN: v = aux_in[r] + 8u; break;
+        case PLAN_INFLATE_GUESS: v = aux_in[r] * param + 1024u; break;
+        case PLAN_SPLIT: v = a.head_len[r] + 8u + 4u + (ns + 3u) / 4u; break;       // start of the svb-zd data bytes
+        case PLAN_SIG_BYTES_RAW: v = 2u * ns; break;
+    }
+    out[r] = v;
+}
+
+__global__ void __launch_bounds__(RK_WARPS * 32) sig_extract_kernel(const uint8_t *rec, const uint64_t *rec_off, RecArrays a,
+                                                                    uint64_t n, int16_t *sig, const uint64_t *sig_off) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * RK_WARPS + (threadIdx.x >> 5), nw = (uint64_t)gridDim.x * RK_WARPS;
+    for (uint64_t r = warp; r < n; r += nw) {
+        if (a.status[r] != S5B_OK) continue;
+        warp_copy(reinterpret_cast<uint8_t *>(sig + sig_off[r]), rec + rec_off[r] + a.sig_at[r], a.sig_bytes[r], lane);
+    }
+}
+
+__global__ void __launch_bounds__(RK_WARPS * 32) rec_pack_kernel(const uint8_t *rec, const uint64_t *rec_off, RecArrays a,
+                                                                 uint64_t n, const uint8_t *sig_src,
+                                                                 const uint64_t *sig_src_off, const uint32_t *sig_src_len,
+                                                                 int sig_src_is_samples, int sig_out_compressed, uint8_t *out,
+                                                                 const uint64_t *out_off) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * RK_WARPS + (threadIdx.x >> 5), nw = (uint64_t)gridDim.x * RK_WARPS;
+    for (uint64_t r = warp; r < n; r += nw) {
+        if (a.status[r] != S5B_OK) continue;
+        const uint8_t *in = rec + rec_off[r];
+        uint8_t *o = out + out_off[r];
+        const uint32_t head = a.head_len[r];
+        warp_copy(o, in, head, lane);
+        // signal source: the input record itself (pass-through, sig_src == NULL), a byte slab (svb slots, offsets in
+        // bytes) or the int16 signal slab (offsets in samples)
+        const uint8_t *sbase = sig_src ? sig_src : in;
+        const uint64_t soff = !sig_src ? a.sig_at[r] : sig_src_is_samples ? sig_src_off[r] * 2 : sig_src_off[r];
+        const uint32_t sbytes = !sig_src ? a.sig_bytes[r] : sig_src_is_samples ? a.n_samples[r] * 2 : sig_src_len[r];
+        const uint64_t lrs = sig_out_compressed ? (uint64_t)sbytes : (uint64_t)a.n_samples[r];  // slow5.c:3983-3987
+        if (lane < 8) o[head + lane] = (uint8_t)(lrs >> (8 * lane));
+        warp_copy(o + head + 8, sbase + soff, sbytes, lane);
+        warp_copy(o + head + 8 + sbytes, in + a.sig_at[r] + a.sig_bytes[r], a.aux_len[r], lane);
+    }
+}
+
+__global__ void __launch_bounds__(RK_WARPS * 32) image_gather_kernel(const uint8_t *src, const uint64_t *src_off,
+                                                                     const uint32_t *len, uint64_t n, uint8_t *img,
+                                                                     const uint64_t *img_off) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * RK_WARPS + (threadIdx.x >> 5), nw = (uint64_t)gridDim.x * RK_WARPS;
+    for (uint64_t r = warp; r < n; r += nw) {
+        uint8_t *o = img + img_off[r];
+        const uint64_t sz = len[r];
+        if (lane < 8) o[lane] = (uint8_t)(sz >> (8 * lane));  // record size prefix, slow5.c:4055-4060
+        warp_copy(o + 8, src + src_off[r], len[r], lane);
+    }
+}
+
+__global__ void rec_sig_abs_kernel(const uint64_t *rec_off, RecArrays a, uint64_t n, uint64_t *out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = rec_off[r] + a.sig_at[r];
+    if (r == n) out[n] = 0;
+}
+
+unsigned rk_grid(uint64_t n) {
+    uint64_t g = (n + RK_WARPS - 1) / RK_WARPS;
+    if (g > 148ull * 8) g = 148ull * 8;
+    return (unsigned)(g ? g : 1);
+}
+
+}  // namespace
+
+cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
+                              int sig_is_svb, RecArrays a, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    rec_locate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, rec_off, rec_len, n, sig_is_svb, a);
+    return cudaGetLastError();
+}
+cudaError_t launch_rec_sig_abs(const uint64_t *rec_off, RecArrays a, uint64_t n, uint64_t *out, cudaStream_t st) {
+    rec_sig_abs_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(rec_off, a, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_rec_plan(int mode, uint64_t n, RecArrays a, const uint32_t *aux_in, uint32_t param, uint32_t *out,
+                            cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    rec_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mode, n, a, aux_in, param, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_sig_extract(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, int16_t *sig,
+                               const uint64_t *sig_off, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    sig_extract_kernel<<<rk_grid(n), RK_WARPS * 32, 0, st>>>(rec, rec_off, a, n, sig, sig_off);
+    return cudaGetLastError();
+}
+cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint8_t *sig_src,
+                            const uint64_t *sig_src_off, const uint32_t *sig_src_len, int sig_src_is_samples,
+                            int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    rec_pack_kernel<<<rk_grid(n), RK_WARPS * 32, 0, st>>>(rec, rec_off, a, n, sig_src, sig_src_off, sig_src_len,
+                                                         sig_src_is_samples, sig_out_compressed, out, out_off);
+    return cudaGetLastError();
+}
+cudaError_t launch_image_gather(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n, uint8_t *img,
+                                const uint64_t *img_off, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    image_gather_kernel<<<rk_grid(n), RK_WARPS * 32, 0, st>>>(src, src_off, len, n, img, img_off);
+    return cudaGetLastError();
+}
+
+}  // namespace s5b

@@ -83,6 +83,7 @@ struct s5b_ctx {
     DevBuf d_scratch;
     PipeSlot slot[NSLOT];
     PinBuf h_stage_in, h_stage_out;  // pointer-array forms
+    DevBuf r_in, r_infl, r_sig, r_svb, r_packed, r_z, r_img, r_meta, r_scratch;  // s5b_blow5_recode_host
     uint64_t launches = 0;
     size_t chunk_bytes = 64u << 20;
     std::string last_cuda_error;
@@ -211,6 +212,9 @@ void s5b_ctx_destroy(s5b_ctx_t *ctx) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     ctx->d_scratch.release();
+    for (DevBuf *b : {&ctx->r_in, &ctx->r_infl, &ctx->r_sig, &ctx->r_svb, &ctx->r_packed, &ctx->r_z, &ctx->r_img, &ctx->r_meta,
+                      &ctx->r_scratch})
+        b->release();
     ctx->h_stage_in.release();
     ctx->h_stage_out.release();
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -886,6 +890,220 @@ int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, 
         }
         default: return S5B_ERR_ARG;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole-batch record transcoding, device resident between one H2D and one D2H
+// ---------------------------------------------------------------------------------------------
+void *s5b_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void s5b_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
+                          uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
+                          uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes) {
+    if (!ctx || !out_bytes) return S5B_ERR_ARG;
+    *out_bytes = 0;
+    if (n == 0) return S5B_OK;
+    if (!h_in || !rec_off || !rec_len || !h_out) return S5B_ERR_ARG;
+    auto rec_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_ZLIB; };
+    auto sig_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_SVB_ZD; };
+    if (!rec_ok(in_rec) || !rec_ok(out_rec) || !sig_ok(in_sig) || !sig_ok(out_sig)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->slot[0].stream;
+    unsigned long long *counter = ctx->slot[0].d_counter;
+    // ---- per-record arrays: 16 x u32[n] and 8 x u64[n+1]
+    const size_t n1 = n + 1;
+    CU(ctx->r_meta.reserve(16 * n * 4 + 8 * n1 * 8 + 256));
+    CU(ctx->r_scratch.reserve(compact_scratch_bytes(n)));
+    uint64_t *u64p = static_cast<uint64_t *>(ctx->r_meta.p);
+    uint64_t *d_rec_off = u64p, *d_infl_off = u64p + n1, *d_sig_off = u64p + 2 * n1, *d_svb_off = u64p + 3 * n1,
+             *d_packed_off = u64p + 4 * n1, *d_z_off = u64p + 5 * n1, *d_img_off = u64p + 6 * n1, *d_sigabs = u64p + 7 * n1;
+    uint32_t *u32p = reinterpret_cast<uint32_t *>(u64p + 8 * n1);
+    uint32_t *d_rec_len = u32p, *d_tmp = u32p + n, *d_infl_len = u32p + 2 * n, *d_svb_len = u32p + 3 * n,
+             *d_packed_len = u32p + 4 * n, *d_z_len = u32p + 5 * n, *d_split = u32p + 6 * n, *d_ns2 = u32p + 7 * n;
+    RecArrays ra{u32p + 8 * n, u32p + 9 * n, u32p + 10 * n, u32p + 11 * n, u32p + 12 * n,
+                 reinterpret_cast<int32_t *>(u32p + 13 * n)};
+    int32_t *d_st2 = reinterpret_cast<int32_t *>(u32p + 14 * n);
+    int32_t *d_st3 = reinterpret_cast<int32_t *>(u32p + 15 * n);
+    std::vector<int32_t> h_st(n);
+    int first_err = S5B_OK;
+    auto check_status = [&](const int32_t *d) -> int {
+        if (cudaMemcpyAsync(h_st.data(), d, n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            return S5B_ERR_DEVICE;
+        for (uint64_t i = 0; i < n; ++i)
+            if (h_st[i] != S5B_OK && first_err == S5B_OK) first_err = h_st[i];
+        return S5B_OK;
+    };
+    // exclusive scan of len[] (rounded to align) into off[0..n]; returns the total through *total
+    auto scan_total = [&](const uint32_t *len, uint32_t align, uint64_t *off, uint64_t *total) -> cudaError_t {
+        cudaError_t e = launch_scan(len, n, align, off, ctx->r_scratch.p, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(total, off + n, 8, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+        ctx->launches += 3;
+        return cudaStreamSynchronize(st);
+    };
+
+    // ---- input up
+    const uint64_t in_cap = round_up(in_bytes, 16);
+    CU(ctx->r_in.reserve(in_cap + 16));
+    CU(cudaMemcpyAsync(ctx->r_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rec_off, rec_off, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rec_len, rec_len, n * 4, cudaMemcpyHostToDevice, st));
+    const uint8_t *cur = static_cast<const uint8_t *>(ctx->r_in.p);
+    const uint64_t *cur_off = d_rec_off;
+    const uint32_t *cur_len = d_rec_len;
+    uint64_t cur_cap = in_cap;
+
+    // ---- record decompression (slow5.c:2586)
+    if (in_rec == S5B_COMPRESS_ZLIB) {
+        CU(launch_rec_plan(PLAN_INFLATE_GUESS, n, ra, d_rec_len, 4, d_tmp, st));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            uint64_t total = 0;
+            CU(scan_total(d_tmp, 16, d_infl_off, &total));
+            CU(ctx->r_infl.reserve(total + 16));
+            InflateArgs ia{cur, cur_off, cur_len, cur_cap, n, static_cast<uint8_t *>(ctx->r_infl.p), d_infl_off, d_infl_len,
+                           d_st2, counter};
+            CU(launch_inflate(ia, ctx->num_sms, ctx->inf_bps, st));
+            ctx->launches += 2;
+            CU(cudaMemcpyAsync(h_st.data(), d_st2, n * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            bool overflow = false;
+            for (uint64_t i = 0; i < n; ++i) overflow |= h_st[i] == S5B_ERR_NOSPACE;
+            if (!overflow || attempt == 1) {
+                for (uint64_t i = 0; i < n; ++i)
+                    if (h_st[i] != S5B_OK && first_err == S5B_OK) first_err = h_st[i];
+                cur_cap = round_up(total, 16);
+                break;
+            }
+            // some slots were too small: the first pass reported the sizes needed -> exact slots, run again
+            CU(cudaMemcpyAsync(d_tmp, d_infl_len, n * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        if (first_err != S5B_OK) return first_err;
+        cur = static_cast<const uint8_t *>(ctx->r_infl.p);
+        cur_off = d_infl_off;
+        cur_len = d_infl_len;
+    }
+    // ---- where is the signal (slow5.c:2811-2927)
+    CU(launch_rec_locate(cur, cur_off, cur_len, n, in_sig == S5B_COMPRESS_SVB_ZD, ra, st));
+    ctx->launches += 1;
+    {
+        int rc = check_status(ra.status);
+        if (rc != S5B_OK) return cuda_fail(ctx, cudaGetLastError());
+        if (first_err != S5B_OK) return first_err;
+    }
+    // ---- signal stage
+    const uint8_t *sig_src = nullptr;  // nullptr = pass the stored bytes through
+    const uint64_t *sig_src_off = nullptr;
+    const uint32_t *sig_src_len = ra.sig_bytes;
+    int sig_src_is_samples = 0;
+    if (in_sig != out_sig) {
+        uint64_t total = 0;
+        CU(launch_rec_plan(PLAN_SIG_SAMPLES, n, ra, nullptr, 0, d_tmp, st));
+        CU(scan_total(d_tmp, 8, d_sig_off, &total));
+        CU(ctx->r_sig.reserve(total * 2 + 32));
+        ctx->launches += 1;
+        if (in_sig == S5B_COMPRESS_SVB_ZD) {  // decode (slow5.c:2915)
+            CU(launch_rec_sig_abs(cur_off, ra, n, d_sigabs, st));
+            SvbDecodeArgs da{cur, d_sigabs, ra.sig_bytes, cur_cap, n, static_cast<int16_t *>(ctx->r_sig.p), d_sig_off, d_ns2,
+                             d_st2, counter};
+            CU(launch_svbzd_decode(da, ctx->num_sms, ctx->dec_bps, st));
+            ctx->launches += 2;
+            if (check_status(d_st2) != S5B_OK) return S5B_ERR_DEVICE;
+            if (first_err != S5B_OK) return first_err;
+            sig_src = static_cast<const uint8_t *>(ctx->r_sig.p);
+            sig_src_off = d_sig_off;
+            sig_src_is_samples = 1;
+        } else {  // encode (slow5.c:3973): raw samples to an aligned slab, then svb-zd into slots
+            CU(launch_sig_extract(cur, cur_off, ra, n, static_cast<int16_t *>(ctx->r_sig.p), d_sig_off, st));
+            CU(launch_rec_plan(PLAN_SVB_BOUND, n, ra, nullptr, 0, d_tmp, st));
+            CU(scan_total(d_tmp, 16, d_svb_off, &total));
+            CU(ctx->r_svb.reserve(total + 32));
+            SvbEncodeArgs ea{static_cast<const int16_t *>(ctx->r_sig.p), d_sig_off, ra.n_samples, n,
+                             static_cast<uint8_t *>(ctx->r_svb.p), d_svb_off, d_svb_len, d_st2, counter};
+            CU(launch_svbzd_encode(ea, ctx->num_sms, ctx->enc_bps, st));
+            ctx->launches += 3;
+            if (check_status(d_st2) != S5B_OK) return S5B_ERR_DEVICE;
+            if (first_err != S5B_OK) return first_err;
+            sig_src = static_cast<const uint8_t *>(ctx->r_svb.p);
+            sig_src_off = d_svb_off;
+            sig_src_len = d_svb_len;
+        }
+    }
+    // ---- pack (slow5.c:3928-4044)
+    const uint8_t *fin = cur;
+    const uint64_t *fin_off = cur_off;
+    const uint32_t *fin_len = cur_len;
+    uint64_t fin_cap = cur_cap;
+    if (in_sig != out_sig) {
+        uint64_t total = 0;
+        if (sig_src_is_samples) {  // raw signal goes into the record: 2 * n_samples bytes
+            CU(launch_rec_plan(PLAN_SIG_BYTES_RAW, n, ra, nullptr, 0, d_svb_len, st));
+            sig_src_len = d_svb_len;
+        }
+        CU(launch_rec_plan(PLAN_PACKED_LEN, n, ra, sig_src_len, 0, d_packed_len, st));
+        CU(scan_total(d_packed_len, 16, d_packed_off, &total));
+        CU(ctx->r_packed.reserve(total + 32));
+        CU(launch_rec_pack(cur, cur_off, ra, n, sig_src, sig_src_off, sig_src_len, sig_src_is_samples,
+                           out_sig != S5B_COMPRESS_NONE, static_cast<uint8_t *>(ctx->r_packed.p), d_packed_off, st));
+        ctx->launches += 3;
+        fin = static_cast<const uint8_t *>(ctx->r_packed.p);
+        fin_off = d_packed_off;
+        fin_len = d_packed_len;
+        fin_cap = round_up(total, 16);
+    }
+    // ---- record compression (slow5.c:4050)
+    if (out_rec == S5B_COMPRESS_ZLIB) {
+        if (in_rec == S5B_COMPRESS_ZLIB && in_sig == out_sig) {
+            // nothing changed inside the records: the stored compressed records are the answer
+            fin = static_cast<const uint8_t *>(ctx->r_in.p);
+            fin_off = d_rec_off;
+            fin_len = d_rec_len;
+        } else {
+            uint64_t total = 0;
+            CU(launch_rec_plan(PLAN_ZLIB_BOUND, n, ra, fin_len, 0, d_tmp, st));
+            CU(scan_total(d_tmp, 16, d_z_off, &total));
+            CU(ctx->r_z.reserve(total + 32));
+            const uint32_t *split = nullptr;
+            if (out_sig == S5B_COMPRESS_SVB_ZD) {
+                CU(launch_rec_plan(PLAN_SPLIT, n, ra, nullptr, 0, d_split, st));
+                split = d_split;
+            }
+            DeflateArgs za{fin, fin_off, fin_len, fin_cap, split, n, static_cast<uint8_t *>(ctx->r_z.p), d_z_off, d_z_len, d_st3,
+                           counter};
+            CU(launch_deflate(za, ctx->num_sms, ctx->def_bps, st));
+            ctx->launches += 3;
+            if (check_status(d_st3) != S5B_OK) return S5B_ERR_DEVICE;
+            if (first_err != S5B_OK) return first_err;
+            fin = static_cast<const uint8_t *>(ctx->r_z.p);
+            fin_off = d_z_off;
+            fin_len = d_z_len;
+        }
+    }
+    // ---- file image: [u64 size][record] ... (slow5.c:4055-4060), one D2H
+    {
+        uint64_t total = 0;
+        CU(launch_rec_plan(PLAN_IMAGE_LEN, n, ra, fin_len, 0, d_tmp, st));
+        CU(scan_total(d_tmp, 1, d_img_off, &total));
+        *out_bytes = total;
+        if (total > out_cap) return S5B_ERR_NOSPACE;
+        CU(ctx->r_img.reserve(total + 32));
+        CU(launch_image_gather(fin, fin_off, fin_len, n, static_cast<uint8_t *>(ctx->r_img.p), d_img_off, st));
+        ctx->launches += 2;
+        CU(cudaMemcpyAsync(h_out, ctx->r_img.p, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return first_err;
 }
 
 // ---------------------------------------------------------------------------------------------

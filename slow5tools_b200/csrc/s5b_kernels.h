@@ -71,6 +71,38 @@ cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_
 cudaError_t launch_svbzd_peek(const uint8_t *svb, const uint64_t *svb_off, const uint32_t *svb_len, uint64_t n_reads,
                               uint32_t *n_samples, cudaStream_t st);
 
+// exclusive scan of len[] rounded up to `align` units -> off[0..n] (n+1 entries); 3 launches
+cudaError_t launch_scan(const uint32_t *len, uint64_t n, uint32_t align, uint64_t *off, void *scratch, cudaStream_t st);
+
+// ---- record-level kernels (record_kernels.cu): locate the signal inside packed BLOW5 records, plan the
+// layouts of the following stages, pack records, build the file image
+struct RecArrays {           // per-record device arrays, n entries each (SoA)
+    uint32_t *head_len;      // bytes before the u64 len_raw_signal field (slow5.c:3928-3987)
+    uint32_t *n_samples;
+    uint32_t *sig_at;        // offset of the stored signal bytes inside the record
+    uint32_t *sig_bytes;     // stored signal bytes (input form)
+    uint32_t *aux_len;
+    int32_t *status;
+};
+cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
+                              int sig_is_svb, RecArrays a, cudaStream_t st);
+// elementwise size planning: mode selects which length is written to out[]
+enum RecPlan { PLAN_SIG_SAMPLES = 0, PLAN_SVB_BOUND = 1, PLAN_PACKED_LEN = 2, PLAN_ZLIB_BOUND = 3, PLAN_IMAGE_LEN = 4,
+               PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7 };
+cudaError_t launch_rec_plan(int mode, uint64_t n, RecArrays a, const uint32_t *aux_in /*mode dependent*/, uint32_t param,
+                            uint32_t *out, cudaStream_t st);
+// out[r] = rec_off[r] + sig_at[r] (absolute offset of the stored signal in the record slab)
+cudaError_t launch_rec_sig_abs(const uint64_t *rec_off, RecArrays a, uint64_t n, uint64_t *out, cudaStream_t st);
+cudaError_t launch_sig_extract(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, int16_t *sig,
+                               const uint64_t *sig_off, cudaStream_t st);
+// packed record r = head (from the input record) + u64 len field + signal bytes + aux (from the input record)
+cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint8_t *sig_src,
+                            const uint64_t *sig_src_off, const uint32_t *sig_src_len, int sig_src_is_samples,
+                            int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st);
+// file image: [u64 size][bytes] per record, back to back
+cudaError_t launch_image_gather(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n, uint8_t *img,
+                                const uint64_t *img_off, cudaStream_t st);
+
 // dense gather: scratch must hold >= compact_scratch_bytes(n_reads)
 size_t compact_scratch_bytes(uint64_t n_reads);
 cudaError_t launch_compact(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n_reads,

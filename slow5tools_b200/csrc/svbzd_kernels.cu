@@ -705,6 +705,16 @@ cudaError_t launch_svbzd_peek(const uint8_t *svb, const uint64_t *svb_off, const
 
 size_t compact_scratch_bytes(uint64_t n_reads) { return ((n_reads + SCAN_T - 1) / SCAN_T + 1) * sizeof(uint64_t); }
 
+cudaError_t launch_scan(const uint32_t *len, uint64_t n, uint32_t align, uint64_t *off, void *scratch, cudaStream_t st) {
+    if (n == 0) return cudaMemsetAsync(off, 0, sizeof(uint64_t), st);
+    uint64_t *block_sums = static_cast<uint64_t *>(scratch);
+    const uint64_t nblocks = (n + SCAN_T - 1) / SCAN_T;
+    scan_block_sums_kernel<<<(unsigned)nblocks, SCAN_T, 0, st>>>(len, n, align, block_sums);
+    scan_top_kernel<<<1, SCAN_T, 0, st>>>(block_sums, nblocks);
+    scan_write_kernel<<<(unsigned)nblocks, SCAN_T, 0, st>>>(len, n, align, block_sums, off);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_compact(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n_reads,
                            uint32_t align, uint8_t *dst, uint64_t *dst_off, void *scratch, cudaStream_t st,
                            int *n_launches) {
