@@ -263,15 +263,45 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
     int wret = 0;
     const int ofd = fileno(fout);
     fflush(fout);
+    const off_t wstart = lseek(ofd, 0, SEEK_CUR);
+    const bool seekable = wstart >= 0;
+    uint64_t wpos = seekable ? (uint64_t)wstart : 0;
     std::thread writer([&] {
         for (;;) {
             Chunk *c = done_q.pop();
             if (!c) break;
-            uint64_t done = 0;
-            while (!wret && done < c->out_bytes) {
-                const ssize_t w = write(ofd, c->out + done, c->out_bytes - done);
-                if (w <= 0) wret = 1;
-                else done += (uint64_t)w;
+            // a regular file takes the chunk as parallel pwrite()s (page-cache / tmpfs copies scale with threads);
+            // pipes and terminals get one sequential write
+            const uint64_t nb = c->out_bytes;
+            if (seekable && nb > (8u << 20)) {
+                const int parts = 4;
+                std::thread th[parts];
+                std::atomic<int> bad(0);
+                for (int k = 0; k < parts; ++k) {
+                    const uint64_t a0 = nb * k / parts, a1 = nb * (k + 1) / parts;
+                    th[k] = std::thread([&, a0, a1] {
+                        uint64_t done = a0;
+                        while (done < a1) {
+                            const ssize_t w = pwrite(ofd, c->out + done, a1 - done, (off_t)(wpos + done));
+                            if (w <= 0) {
+                                bad = 1;
+                                return;
+                            }
+                            done += (uint64_t)w;
+                        }
+                    });
+                }
+                for (int k = 0; k < parts; ++k) th[k].join();
+                if (bad) wret = 1;
+                wpos += nb;
+            } else {
+                uint64_t done = 0;
+                while (!wret && done < nb) {
+                    const ssize_t w = write(ofd, c->out + done, nb - done);
+                    if (w <= 0) wret = 1;
+                    else done += (uint64_t)w;
+                }
+                wpos += nb;
             }
             free_q.push(c);
         }
@@ -312,6 +342,7 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
     reader.join();
     done_q.push(nullptr);
     writer.join();
+    if (seekable && lseek(ofd, (off_t)wpos, SEEK_SET) < 0) wret = 1;  // the end-of-file marker goes after the last chunk
     if (wret) {
         ERROR("%s", "writing the output failed");
         ret = 1;
