@@ -112,6 +112,17 @@ int s5b_zlib_inflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_
                          uint64_t in_capacity, uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off,
                          uint32_t *d_out_len, int32_t *d_status, void *stream);
 
+/* Replaces ptr_depress_zstd (slow5_press.c:1205-1230: ZSTD_getFrameContentSize + ZSTD_decompress) for a batch of
+ * independent single-frame streams.  Same slab contract as s5b_zlib_inflate_dev.  Every frame must carry its
+ * content size (the reference refuses frames that do not, :1206-1211); s5b_zstd_content_size() reads it on the
+ * host so slots can be sized exactly.  S5B_ERR_PRESS for anything libzstd rejects; S5B_ERR_NOSPACE (d_out_len[r] =
+ * content size) when the slot is too small. */
+int s5b_zstd_decode_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                        uint64_t in_capacity, uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off,
+                        uint32_t *d_out_len, int32_t *d_status, void *stream);
+/* content size stored in a frame header; returns 0 and *size, or S5B_ERR_PRESS (not a zstd frame / no size) */
+int s5b_zstd_content_size(const void *frame, size_t len, uint64_t *size);
+
 /* Replaces ptr_compress_zlib / ptr_compress_zlib_solo (slow5_press.c:837-913: deflate at level 6 with
  * Z_FINISH) for a batch: record r = d_in[d_in_off[r] .. +d_in_len[r]) becomes one complete zlib stream
  * (78 9C .. Adler-32) in the slot [d_out_off[r], d_out_off[r+1]), which must hold s5b_zlib_bound(len).

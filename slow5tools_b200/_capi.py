@@ -94,3 +94,7 @@ lib.s5b_zlib_bound.restype = _u64
 lib.s5b_zlib_bound.argtypes = [_u64]
 lib.s5b_zlib_deflate_dev.restype = C.c_int
 lib.s5b_zlib_deflate_dev.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]
+lib.s5b_zstd_decode_dev.restype = C.c_int
+lib.s5b_zstd_decode_dev.argtypes = [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]
+lib.s5b_zstd_content_size.restype = C.c_int
+lib.s5b_zstd_content_size.argtypes = [_vp, _sz, _P(_u64)]

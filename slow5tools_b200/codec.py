@@ -101,6 +101,11 @@ class Codec:
                                              in_len.numel(), _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status),
                                              self._stream()), "s5b_zlib_inflate_dev")
 
+    def zstd_decode_dev(self, zin, in_off, in_len, out, out_off, out_len, status):
+        self._check(lib.s5b_zstd_decode_dev(self._h, _ptr(zin), _ptr(in_off), _ptr(in_len), zin.numel(),
+                                            in_len.numel(), _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status),
+                                            self._stream()), "s5b_zstd_decode_dev")
+
     def zlib_deflate_dev(self, din, in_off, in_len, out, out_off, out_len, status, split=None):
         self._check(lib.s5b_zlib_deflate_dev(self._h, _ptr(din), _ptr(in_off), _ptr(in_len), din.numel(), _ptr(split),
                                              in_len.numel(), _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status),

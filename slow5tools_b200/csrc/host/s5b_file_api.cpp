@@ -148,14 +148,15 @@ int s5b_decode_batch(s5b_file_t *f, char **mems, size_t *bytes, size_t n, s5b_re
     }
     std::vector<const void *> ptrs(n);
     std::vector<size_t> counts(n);
-    if (h.record_method == PRESS_ZLIB) {
+    if (h.record_method == PRESS_ZLIB || h.record_method == PRESS_ZSTD) {
         std::vector<void *> out(n, nullptr);
         std::vector<size_t> out_n(n, 0);
         for (size_t i = 0; i < n; ++i) {
             ptrs[i] = mems[i];
             counts[i] = bytes[i];
         }
-        const int rc = s5b_depress_batch_host(f->gpu, S5B_COMPRESS_ZLIB, ptrs.data(), counts.data(), n, out.data(), out_n.data());
+        const int rc = s5b_depress_batch_host(f->gpu, h.record_method == PRESS_ZLIB ? S5B_COMPRESS_ZLIB : S5B_COMPRESS_ZSTD,
+                                              ptrs.data(), counts.data(), n, out.data(), out_n.data());
         if (rc != S5B_OK) {
             for (void *p : out) free(p);
             return fail(rc == S5B_ERR_PRESS ? S5B_ERR_PRESS : rc);

@@ -446,9 +446,9 @@ int view_main(int argc, char **argv) {
         return 1;
     }
     const Header &hdr = rd.hdr;
-    if ((hdr.record_method != PRESS_NONE && hdr.record_method != PRESS_ZLIB) ||
+    if ((hdr.record_method != PRESS_NONE && hdr.record_method != PRESS_ZLIB && hdr.record_method != PRESS_ZSTD) ||
         (hdr.signal_method != PRESS_NONE && hdr.signal_method != PRESS_SVB_ZD)) {
-        ERROR("%s", "input uses a compression method this build does not support (zstd / ex-zd)");
+        ERROR("%s", "input uses a compression method this build does not support (ex-zd, or zlib/zstd as signal method)");
         return 1;
     }
     FILE *fout = stdout;
@@ -513,15 +513,15 @@ int view_main(int argc, char **argv) {
         // ---- record decompression
         std::vector<const uint8_t *> packed(n);
         std::vector<size_t> packed_n(n);
-        if (rd.fmt == FMT_BINARY && hdr.record_method == PRESS_ZLIB) {
+        if (rd.fmt == FMT_BINARY && (hdr.record_method == PRESS_ZLIB || hdr.record_method == PRESS_ZSTD)) {
             for (size_t i = 0; i < n; ++i) {
                 ptrs[i] = b.mem[i].data();
                 counts[i] = b.mem[i].size();
             }
             b.inflated.assign(n, nullptr);
             b.inflated_n.assign(n, 0);
-            const int rc = s5b_depress_batch_host(gpu, S5B_COMPRESS_ZLIB, ptrs.data(), counts.data(), n, b.inflated.data(),
-                                                  b.inflated_n.data());
+            const int rc = s5b_depress_batch_host(gpu, hdr.record_method == PRESS_ZLIB ? S5B_COMPRESS_ZLIB : S5B_COMPRESS_ZSTD,
+                                                  ptrs.data(), counts.data(), n, b.inflated.data(), b.inflated_n.data());
             if (rc != S5B_OK) {
                 ERROR("record decompression failed: %s", s5b_strerror(rc));
                 ret = 1;
