@@ -20,6 +20,14 @@
 #define ZHDN
 #endif
 
+// development aid: the host harness records where a frame was rejected
+#if defined(S5BZ_TRACE) && !defined(__CUDA_ARCH__)
+static int s5bz_fail_line = 0;
+#define ZF(code) (s5bz_fail_line = __LINE__, (code))
+#else
+#define ZF(code) (code)
+#endif
+
 namespace s5bz {
 
 enum { Z_OK = 0, Z_ERR_CORRUPT = -13 /* S5B_ERR_PRESS */, Z_ERR_NOSPACE = -40, Z_ERR_UNSUPPORTED = -13 };
@@ -109,9 +117,9 @@ struct BackBits {
 // Reads a normalised-count table description (forward bits) into t.norm; returns bytes consumed or < 0.
 ZHDN inline int fse_read_ncount(Tables &t, const uint8_t *src, uint32_t len, int max_al, int max_sym, int *al_out, int *nsym_out) {
     FwdBits fb{src, (uint64_t)len * 8, 0};
-    if (len < 1) return Z_ERR_CORRUPT;
+    if (len < 1) return ZF(Z_ERR_CORRUPT);
     const int al = 5 + (int)fb.read(4);
-    if (al > max_al) return Z_ERR_CORRUPT;
+    if (al > max_al) return ZF(Z_ERR_CORRUPT);
     int remaining = 1 << al;
     int sym = 0;
     while (remaining > 0 && sym <= max_sym) {
@@ -136,10 +144,10 @@ ZHDN inline int fse_read_ncount(Tables &t, const uint8_t *src, uint32_t len, int
                 else break;
             }
         }
-        if (fb.pos > fb.nbits_total + 16) return Z_ERR_CORRUPT;
+        if (fb.pos > fb.nbits_total + 16) return ZF(Z_ERR_CORRUPT);
     }
-    if (remaining != 0 || sym > max_sym + 1) return Z_ERR_CORRUPT;
-    if (fb.pos > fb.nbits_total) return Z_ERR_CORRUPT;
+    if (remaining != 0 || sym > max_sym + 1) return ZF(Z_ERR_CORRUPT);
+    if (fb.pos > fb.nbits_total) return ZF(Z_ERR_CORRUPT);
     *al_out = al;
     *nsym_out = sym;
     return (int)((fb.pos + 7) >> 3);
@@ -167,7 +175,7 @@ ZHDN inline int fse_build(Tables &t, FseEntry *tab, int al, int nsym) {
             } while (pos >= high);
         }
     }
-    if (pos != 0) return Z_ERR_CORRUPT;
+    if (pos != 0) return ZF(Z_ERR_CORRUPT);
     for (int i = 0; i < size; ++i) {
         const int s = tab[i].sym;
         const uint32_t nx = t.next[s]++;
@@ -189,15 +197,15 @@ ZHD void fse_rle(FseEntry *tab, uint8_t sym) {
 ZHDN inline int huf_build(Tables &t, int n) {
     uint32_t sum = 0;
     for (int i = 0; i < n; ++i) {
-        if (t.weights[i] > HUF_MAX_BITS) return Z_ERR_CORRUPT;
+        if (t.weights[i] > HUF_MAX_BITS) return ZF(Z_ERR_CORRUPT);
         sum += t.weights[i] ? 1u << (t.weights[i] - 1) : 0;
     }
-    if (sum == 0) return Z_ERR_CORRUPT;
+    if (sum == 0) return ZF(Z_ERR_CORRUPT);
     const int max_bits = highest_bit(sum) + 1;
-    if (max_bits > HUF_MAX_BITS) return Z_ERR_CORRUPT;
+    if (max_bits > HUF_MAX_BITS) return ZF(Z_ERR_CORRUPT);
     const uint32_t left = (1u << max_bits) - sum;
-    if (left & (left - 1)) return Z_ERR_CORRUPT;  // must be a power of two
-    if (n >= 256) return Z_ERR_CORRUPT;
+    if (left & (left - 1)) return ZF(Z_ERR_CORRUPT);  // must be a power of two
+    if (n >= 256) return ZF(Z_ERR_CORRUPT);
     t.weights[n] = (uint8_t)(highest_bit(left) + 1);
     const int nsym = n + 1;
     // code length = max_bits + 1 - weight; table filled from the longest codes (smallest weights) upwards
@@ -211,7 +219,7 @@ ZHDN inline int huf_build(Tables &t, int n) {
         start[w] = pos;
         pos += rank_count[w] << (w - 1);
     }
-    if (pos != (1u << max_bits)) return Z_ERR_CORRUPT;
+    if (pos != (1u << max_bits)) return ZF(Z_ERR_CORRUPT);
     for (int i = 0; i < nsym; ++i) {
         const int w = t.weights[i];
         if (!w) continue;
@@ -226,38 +234,38 @@ ZHDN inline int huf_build(Tables &t, int n) {
 
 // Huffman tree description: direct 4-bit weights or FSE-compressed weights.  Returns bytes consumed or < 0.
 ZHDN inline int huf_read_tree(Tables &t, const uint8_t *src, uint32_t len) {
-    if (len < 1) return Z_ERR_CORRUPT;
+    if (len < 1) return ZF(Z_ERR_CORRUPT);
     const uint32_t hb = src[0];
     int n = 0;
     uint32_t used;
     if (hb >= 128) {
         n = (int)hb - 127;
         const uint32_t bytes = (uint32_t)(n + 1) / 2;
-        if (1 + bytes > len) return Z_ERR_CORRUPT;
+        if (1 + bytes > len) return ZF(Z_ERR_CORRUPT);
         for (int i = 0; i < n; ++i) {
             const uint8_t b = src[1 + i / 2];
             t.weights[i] = (i & 1) ? (b & 15) : (b >> 4);
         }
         used = 1 + bytes;
     } else {
-        if (1 + hb > len || hb == 0) return Z_ERR_CORRUPT;
+        if (1 + hb > len || hb == 0) return ZF(Z_ERR_CORRUPT);
         int al, nsym;
         const int hdr = fse_read_ncount(t, src + 1, hb, WT_MAX_AL, 12, &al, &nsym);
         if (hdr < 0) return hdr;
-        if (fse_build(t, t.wt, al, nsym) != Z_OK) return Z_ERR_CORRUPT;
+        if (fse_build(t, t.wt, al, nsym) != Z_OK) return ZF(Z_ERR_CORRUPT);
         BackBits bb;
-        if ((uint32_t)hdr >= hb || !bb.init(src + 1 + hdr, hb - hdr)) return Z_ERR_CORRUPT;
+        if ((uint32_t)hdr >= hb || !bb.init(src + 1 + hdr, hb - hdr)) return ZF(Z_ERR_CORRUPT);
         uint32_t s1 = bb.read(al), s2 = bb.read(al);
-        if (bb.off < 0) return Z_ERR_CORRUPT;
+        if (bb.off < 0) return ZF(Z_ERR_CORRUPT);
         for (;;) {
-            if (n >= 254) return Z_ERR_CORRUPT;
+            if (n >= 254) return ZF(Z_ERR_CORRUPT);
             t.weights[n++] = t.wt[s1].sym;
             s1 = t.wt[s1].base + bb.read(t.wt[s1].nbits);
             if (bb.off < 0) {
                 t.weights[n++] = t.wt[s2].sym;
                 break;
             }
-            if (n >= 254) return Z_ERR_CORRUPT;
+            if (n >= 254) return ZF(Z_ERR_CORRUPT);
             t.weights[n++] = t.wt[s2].sym;
             s2 = t.wt[s2].base + bb.read(t.wt[s2].nbits);
             if (bb.off < 0) {
@@ -275,19 +283,19 @@ ZHDN inline int huf_read_tree(Tables &t, const uint8_t *src, uint32_t len) {
 // one Huffman stream -> exactly `regen` symbols
 ZHDN inline int huf_decode_stream(const Tables &t, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t regen) {
     BackBits bb;
-    if (!bb.init(src, len)) return Z_ERR_CORRUPT;
+    if (!bb.init(src, len)) return ZF(Z_ERR_CORRUPT);
     const int mb = t.huf_bits;
     const uint32_t mask = (1u << mb) - 1u;
     uint32_t state = bb.read(mb);
     uint32_t n = 0;
     while (bb.off > -(int64_t)mb) {
-        if (n >= regen) return Z_ERR_CORRUPT;
+        if (n >= regen) return ZF(Z_ERR_CORRUPT);
         const uint16_t e = t.huf[state];
         dst[n++] = (uint8_t)(e >> 4);
         const int nb = e & 15;
         state = ((state << nb) + bb.read(nb)) & mask;
     }
-    if (bb.off != -(int64_t)mb || n != regen) return Z_ERR_CORRUPT;
+    if (bb.off != -(int64_t)mb || n != regen) return ZF(Z_ERR_CORRUPT);
     return Z_OK;
 }
 
@@ -350,23 +358,23 @@ ZHDN inline int seq_table(Tables &t, int which, int mode, const uint8_t *src, ui
     switch (mode) {
         case 0:
             load_default_norm(t, which, &al, &nsym);
-            if (fse_build(t, tab, al, nsym) != Z_OK) return Z_ERR_CORRUPT;
+            if (fse_build(t, tab, al, nsym) != Z_OK) return ZF(Z_ERR_CORRUPT);
             *alp = al;
             return 0;
         case 1:
-            if (len < 1 || src[0] > max_sym) return Z_ERR_CORRUPT;
+            if (len < 1 || src[0] > max_sym) return ZF(Z_ERR_CORRUPT);
             fse_rle(tab, src[0]);
             *alp = 0;
             return 1;
         case 2: {
             const int used = fse_read_ncount(t, src, len, max_al, max_sym, &al, &nsym);
             if (used < 0) return used;
-            if (fse_build(t, tab, al, nsym) != Z_OK) return Z_ERR_CORRUPT;
+            if (fse_build(t, tab, al, nsym) != Z_OK) return ZF(Z_ERR_CORRUPT);
             *alp = al;
             return used;
         }
         default:  // repeat
-            if (*alp < 0) return Z_ERR_CORRUPT;
+            if (*alp < 0) return ZF(Z_ERR_CORRUPT);
             return 0;
     }
 }
@@ -381,16 +389,16 @@ struct FrameInfo {
 };
 
 ZHDN inline int parse_frame_header(const uint8_t *src, uint64_t len, FrameInfo &fi) {
-    if (len < 6) return Z_ERR_CORRUPT;
-    if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) return Z_ERR_CORRUPT;
+    if (len < 6) return ZF(Z_ERR_CORRUPT);
+    if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) return ZF(Z_ERR_CORRUPT);
     const uint32_t fhd = src[4];
     const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, dict_flag = fhd & 3;
-    if (fhd & 0x08) return Z_ERR_CORRUPT;  // reserved bit
+    if (fhd & 0x08) return ZF(Z_ERR_CORRUPT);  // reserved bit
     fi.checksum = (fhd >> 2) & 1;
     uint32_t pos = 5;
     fi.window = 0;
     if (!single) {
-        if (pos >= len) return Z_ERR_CORRUPT;
+        if (pos >= len) return ZF(Z_ERR_CORRUPT);
         const uint32_t wd = src[pos++];
         const uint32_t e = wd >> 3, m = wd & 7;
         const uint64_t base = 1ull << (10 + e);
@@ -400,7 +408,7 @@ ZHDN inline int parse_frame_header(const uint8_t *src, uint64_t len, FrameInfo &
     if (dict_bytes) {
         // a dictionary id of 0 means "none"; anything else cannot be honoured
         uint32_t id = 0;
-        if (pos + dict_bytes > len) return Z_ERR_CORRUPT;
+        if (pos + dict_bytes > len) return ZF(Z_ERR_CORRUPT);
         for (uint32_t i = 0; i < dict_bytes; ++i) id |= (uint32_t)src[pos + i] << (8 * i);
         pos += dict_bytes;
         if (id != 0) return Z_ERR_UNSUPPORTED;
@@ -408,7 +416,7 @@ ZHDN inline int parse_frame_header(const uint8_t *src, uint64_t len, FrameInfo &
     uint32_t fcs_bytes = fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
     fi.has_content_size = fcs_bytes != 0;
     fi.content_size = 0;
-    if (pos + fcs_bytes > len) return Z_ERR_CORRUPT;
+    if (pos + fcs_bytes > len) return ZF(Z_ERR_CORRUPT);
     for (uint32_t i = 0; i < fcs_bytes; ++i) fi.content_size |= (uint64_t)src[pos + i] << (8 * i);
     if (fcs_bytes == 2) fi.content_size += 256;
     pos += fcs_bytes;
@@ -476,7 +484,7 @@ ZHDN inline uint64_t xxh64(const uint8_t *p, uint64_t len) {
 ZHDN inline int decode_literals(Tables &t, const uint8_t *src, uint32_t len, uint8_t *lit, uint32_t lit_cap, const uint8_t **lit_ptr,
                                 uint32_t *lit_len, int lane_count = 1) {
     (void)lane_count;
-    if (len < 1) return Z_ERR_CORRUPT;
+    if (len < 1) return ZF(Z_ERR_CORRUPT);
     const uint32_t b0 = src[0];
     const uint32_t type = b0 & 3, sf = (b0 >> 2) & 3;
     uint32_t regen, comp = 0, hdr, streams = 1;
@@ -485,49 +493,49 @@ ZHDN inline int decode_literals(Tables &t, const uint8_t *src, uint32_t len, uin
             regen = b0 >> 3;
             hdr = 1;
         } else if (sf == 1) {
-            if (len < 2) return Z_ERR_CORRUPT;
+            if (len < 2) return ZF(Z_ERR_CORRUPT);
             regen = (b0 >> 4) | ((uint32_t)src[1] << 4);
             hdr = 2;
         } else {
-            if (len < 3) return Z_ERR_CORRUPT;
+            if (len < 3) return ZF(Z_ERR_CORRUPT);
             regen = (b0 >> 4) | ((uint32_t)src[1] << 4) | ((uint32_t)src[2] << 12);
             hdr = 3;
         }
         if (type == 0) {
-            if (hdr + regen > len) return Z_ERR_CORRUPT;
+            if (hdr + regen > len) return ZF(Z_ERR_CORRUPT);
             *lit_ptr = src + hdr;
             *lit_len = regen;
             return (int)(hdr + regen);
         }
-        if (hdr + 1 > len || regen > lit_cap) return Z_ERR_CORRUPT;
+        if (hdr + 1 > len || regen > lit_cap) return ZF(Z_ERR_CORRUPT);
         memset(lit, src[hdr], regen);
         *lit_ptr = lit;
         *lit_len = regen;
         return (int)(hdr + 1);
     }
     if (sf == 0 || sf == 1) {
-        if (len < 3) return Z_ERR_CORRUPT;
+        if (len < 3) return ZF(Z_ERR_CORRUPT);
         const uint32_t v = b0 | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
         regen = (v >> 4) & 0x3FF;
         comp = (v >> 14) & 0x3FF;
         hdr = 3;
         streams = sf == 0 ? 1 : 4;
     } else if (sf == 2) {
-        if (len < 4) return Z_ERR_CORRUPT;
+        if (len < 4) return ZF(Z_ERR_CORRUPT);
         const uint32_t v = rd32(src);
         regen = (v >> 4) & 0x3FFF;
         comp = v >> 18;
         hdr = 4;
         streams = 4;
     } else {
-        if (len < 5) return Z_ERR_CORRUPT;
+        if (len < 5) return ZF(Z_ERR_CORRUPT);
         const uint64_t v = (uint64_t)rd32(src) | ((uint64_t)src[4] << 32);
         regen = (uint32_t)(v >> 4) & 0x3FFFF;
         comp = (uint32_t)(v >> 22) & 0x3FFFF;
         hdr = 5;
         streams = 4;
     }
-    if (hdr + comp > len || regen > lit_cap) return Z_ERR_CORRUPT;
+    if (hdr + comp > len || regen > lit_cap) return ZF(Z_ERR_CORRUPT);
     const uint8_t *p = src + hdr;
     uint32_t left = comp;
     if (type == 2) {
@@ -536,18 +544,18 @@ ZHDN inline int decode_literals(Tables &t, const uint8_t *src, uint32_t len, uin
         p += used;
         left -= used;
     } else if (t.huf_bits == 0) {
-        return Z_ERR_CORRUPT;  // treeless block without a previous tree
+        return ZF(Z_ERR_CORRUPT);  // treeless block without a previous tree
     }
     if (streams == 1) {
         const int rc = huf_decode_stream(t, p, left, lit, regen);
         if (rc != Z_OK) return rc;
     } else {
-        if (left < 6) return Z_ERR_CORRUPT;
+        if (left < 6) return ZF(Z_ERR_CORRUPT);
         const uint32_t s1 = p[0] | (p[1] << 8), s2 = p[2] | (p[3] << 8), s3 = p[4] | (p[5] << 8);
-        if (6ull + s1 + s2 + s3 > left) return Z_ERR_CORRUPT;
+        if (6ull + s1 + s2 + s3 > left) return ZF(Z_ERR_CORRUPT);
         const uint32_t s4 = left - 6 - s1 - s2 - s3;
         const uint32_t q = (regen + 3) / 4;
-        if (3ull * q > regen) return Z_ERR_CORRUPT;
+        if (3ull * q > regen) return ZF(Z_ERR_CORRUPT);
         const uint8_t *b = p + 6;
         int rc = huf_decode_stream(t, b, s1, lit, q);
         if (rc == Z_OK) rc = huf_decode_stream(t, b + s1, s2, lit + q, q);
@@ -568,16 +576,16 @@ struct FrameState {
 // output, frames here are far smaller than any window).  Returns Z_OK or < 0.
 ZHDN inline int decode_sequences(Tables &t, FrameState &fs, const uint8_t *src, uint32_t len, const uint8_t *lit, uint32_t lit_len,
                                  uint8_t *dst, uint64_t dst_cap, uint64_t *dst_pos) {
-    if (len < 1) return Z_ERR_CORRUPT;
+    if (len < 1) return ZF(Z_ERR_CORRUPT);
     uint32_t pos = 0;
     uint32_t nseq = src[pos++];
     if (nseq >= 128) {
         if (nseq == 255) {
-            if (len < 3) return Z_ERR_CORRUPT;
+            if (len < 3) return ZF(Z_ERR_CORRUPT);
             nseq = src[1] + ((uint32_t)src[2] << 8) + 0x7F00;
             pos = 3;
         } else {
-            if (len < 2) return Z_ERR_CORRUPT;
+            if (len < 2) return ZF(Z_ERR_CORRUPT);
             nseq = ((nseq - 128) << 8) + src[1];
             pos = 2;
         }
@@ -585,9 +593,9 @@ ZHDN inline int decode_sequences(Tables &t, FrameState &fs, const uint8_t *src, 
     uint64_t out = *dst_pos;
     uint32_t lp = 0;
     if (nseq) {
-        if (pos >= len) return Z_ERR_CORRUPT;
+        if (pos >= len) return ZF(Z_ERR_CORRUPT);
         const uint32_t modes = src[pos++];
-        if (modes & 3) return Z_ERR_CORRUPT;
+        // (the two reserved bits of the modes byte are ignored, as libzstd does)
         int used = seq_table(t, 0, (modes >> 6) & 3, src + pos, len - pos);
         if (used < 0) return used;
         pos += used;
@@ -598,12 +606,12 @@ ZHDN inline int decode_sequences(Tables &t, FrameState &fs, const uint8_t *src, 
         if (used < 0) return used;
         pos += used;
         BackBits bb;
-        if (pos >= len || !bb.init(src + pos, len - pos)) return Z_ERR_CORRUPT;
+        if (pos >= len || !bb.init(src + pos, len - pos)) return ZF(Z_ERR_CORRUPT);
         uint32_t sl = bb.read(t.ll_al), so = bb.read(t.of_al), sm = bb.read(t.ml_al);
-        if (bb.off < 0) return Z_ERR_CORRUPT;
+        if (bb.off < 0) return ZF(Z_ERR_CORRUPT);
         for (uint32_t i = 0; i < nseq; ++i) {
             const int of_code = t.of[so].sym, ml_code = t.ml[sm].sym, ll_code = t.ll[sl].sym;
-            if (of_code > 31 || ml_code > 52 || ll_code > 35) return Z_ERR_CORRUPT;
+            if (of_code > 31 || ml_code > 52 || ll_code > 35) return ZF(Z_ERR_CORRUPT);
             const uint64_t ofv = (1ull << of_code) + bb.read(of_code);
             const uint32_t mlen = ml_base_of(ml_code) + bb.read(ml_bits_of(ml_code));
             const uint32_t llen = ll_base_of(ll_code) + bb.read(ll_bits_of(ll_code));
@@ -612,7 +620,7 @@ ZHDN inline int decode_sequences(Tables &t, FrameState &fs, const uint8_t *src, 
                 sm = t.ml[sm].base + bb.read(t.ml[sm].nbits);
                 so = t.of[so].base + bb.read(t.of[so].nbits);
             }
-            if (bb.off < 0) return Z_ERR_CORRUPT;
+            if (bb.off < 0) return ZF(Z_ERR_CORRUPT);
             uint64_t offset;
             if (ofv > 3) {
                 offset = ofv - 3;
@@ -635,13 +643,13 @@ ZHDN inline int decode_sequences(Tables &t, FrameState &fs, const uint8_t *src, 
             for (uint32_t k = 0; k < llen; ++k) dst[out + k] = lit[lp + k];
             out += llen;
             lp += llen;
-            if (offset == 0 || offset > out) return Z_ERR_CORRUPT;
+            if (offset == 0 || offset > out) return ZF(Z_ERR_CORRUPT);
             for (uint32_t k = 0; k < mlen; ++k) dst[out + k] = dst[out - offset + k];
             out += mlen;
         }
-        if (bb.off != 0) return Z_ERR_CORRUPT;
+        if (bb.off != 0) return ZF(Z_ERR_CORRUPT);
     } else if (pos != len) {
-        return Z_ERR_CORRUPT;
+        return ZF(Z_ERR_CORRUPT);
     }
     const uint32_t rest = lit_len - lp;
     if (out + rest > dst_cap) return Z_ERR_NOSPACE;
@@ -658,7 +666,7 @@ ZHDN inline int decode_frame(Tables &t, const uint8_t *src, uint64_t len, uint8_
     int rc = parse_frame_header(src, len, fi);
     if (rc != Z_OK) return rc;
     // the reference refuses frames without a content size (slow5_press.c:1206-1211)
-    if (!fi.has_content_size) return Z_ERR_CORRUPT;
+    if (!fi.has_content_size) return ZF(Z_ERR_CORRUPT);
     if (fi.content_size > dst_cap) {
         *out_len = fi.content_size;
         return Z_ERR_NOSPACE;
@@ -671,23 +679,23 @@ ZHDN inline int decode_frame(Tables &t, const uint8_t *src, uint64_t len, uint8_
     fs.rep[2] = 8;
     uint64_t pos = fi.header_bytes, out = 0;
     for (;;) {
-        if (pos + 3 > len) return Z_ERR_CORRUPT;
+        if (pos + 3 > len) return ZF(Z_ERR_CORRUPT);
         const uint32_t bh = src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16);
         pos += 3;
         const bool last = bh & 1;
         const uint32_t type = (bh >> 1) & 3, bsize = bh >> 3;
         if (type == 0) {
-            if (pos + bsize > len || out + bsize > fi.content_size) return Z_ERR_CORRUPT;
+            if (pos + bsize > len || out + bsize > fi.content_size) return ZF(Z_ERR_CORRUPT);
             for (uint32_t k = 0; k < bsize; ++k) dst[out + k] = src[pos + k];
             out += bsize;
             pos += bsize;
         } else if (type == 1) {
-            if (pos + 1 > len || out + bsize > fi.content_size) return Z_ERR_CORRUPT;
+            if (pos + 1 > len || out + bsize > fi.content_size) return ZF(Z_ERR_CORRUPT);
             for (uint32_t k = 0; k < bsize; ++k) dst[out + k] = src[pos];
             out += bsize;
             pos += 1;
         } else if (type == 2) {
-            if (pos + bsize > len || bsize > (128u << 10)) return Z_ERR_CORRUPT;
+            if (pos + bsize > len || bsize > (128u << 10)) return ZF(Z_ERR_CORRUPT);
             const uint8_t *lp;
             uint32_t ll;
             const int used = decode_literals(t, src + pos, bsize, lit, lit_cap, &lp, &ll);
@@ -696,19 +704,19 @@ ZHDN inline int decode_frame(Tables &t, const uint8_t *src, uint64_t len, uint8_
             if (rc != Z_OK) return rc == Z_ERR_NOSPACE ? Z_ERR_CORRUPT : rc;  // more output than the header promised
             pos += bsize;
         } else {
-            return Z_ERR_CORRUPT;
+            return ZF(Z_ERR_CORRUPT);
         }
         if (last) break;
     }
-    if (out != fi.content_size) return Z_ERR_CORRUPT;
+    if (out != fi.content_size) return ZF(Z_ERR_CORRUPT);
     if (fi.checksum) {
-        if (pos + 4 > len) return Z_ERR_CORRUPT;
-        if ((uint32_t)xxh64(dst, out) != rd32(src + pos)) return Z_ERR_CORRUPT;
+        if (pos + 4 > len) return ZF(Z_ERR_CORRUPT);
+        if ((uint32_t)xxh64(dst, out) != rd32(src + pos)) return ZF(Z_ERR_CORRUPT);
         pos += 4;
     }
     // ZSTD_decompress would go on to decode further frames into the same buffer; with the buffer sized for the
     // first frame (slow5_press.c:1214) anything but trailing nothing is an error there
-    if (pos != len) return Z_ERR_CORRUPT;
+    if (pos != len) return ZF(Z_ERR_CORRUPT);
     *out_len = out;
     return Z_OK;
 }

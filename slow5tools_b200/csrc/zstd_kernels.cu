@@ -162,7 +162,6 @@ __device__ int decode_sequences_warp(Tables &t, FrameState &fs, const uint8_t *s
                 rc = Z_ERR_CORRUPT;
             } else {
                 const uint32_t modes = src[pos++];
-                if (modes & 3) rc = Z_ERR_CORRUPT;
                 for (int w = 0; w < 3 && rc == Z_OK; ++w) {
                     const int used = seq_table(t, w, (modes >> (6 - 2 * w)) & 3, src + pos, len - pos);
                     if (used < 0) rc = used;
