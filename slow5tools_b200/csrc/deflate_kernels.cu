@@ -21,6 +21,7 @@
 //   * a block that would not shrink is emitted as stored blocks, like zlib does.
 #include "s5b_kernels.h"
 #include "s5b_ptx.cuh"
+#include "huff_common.cuh"
 #include "../../include/slow5b200.h"
 
 namespace s5b {
@@ -29,8 +30,8 @@ namespace {
 
 constexpr int DEF_WARPS = 4;
 constexpr int DEF_BLOCK = 6144;  // max input bytes per deflate block (multiple of 32)
-constexpr int DEF_OUT = 2048;    // output bit buffer bytes (multiple of 16)
-constexpr int DEF_OUT_SLACK = 96;
+constexpr int DEF_OUT = HC_OUT;
+constexpr int DEF_OUT_SLACK = HC_OUT_SLACK;
 constexpr uint32_t ADLER_MOD = 65521u;
 
 struct __align__(128) DefWarpSmem {
@@ -71,109 +72,6 @@ __device__ __forceinline__ void len_code(uint32_t m, uint32_t &sym, uint32_t &xb
     }
 }
 
-// ---- bitonic sort of n (power of two, <= 512) u32 keys in shared memory, ascending -------------
-__device__ void warp_sort(uint32_t *a, int n, int lane) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < n / 2; t += 32) {
-                // t-th compare-exchange pair of this stage
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const bool up = (i & k) == 0;
-                const uint32_t x = a[i], y = a[p];
-                if ((x > y) == up) {
-                    a[i] = y;
-                    a[p] = x;
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// ---- Huffman code lengths for `n` symbols with frequencies hist[] (0 = unused), limited to `limit` bits.
-// Writes len[0..n).  Guarantees at least two coded symbols (like zlib's build_tree) so the code is complete.
-// sortbuf: >= 512 entries (>= 32 for n <= 32), weight/parent: >= 2*n entries.  Whole warp calls it.
-__device__ void huffman_lengths(uint32_t *hist, int n, int limit, uint8_t *len, uint32_t *sortbuf, uint32_t *weight,
-                                uint16_t *parent, uint16_t *bl_count, int lane) {
-    const int npad = n <= 32 ? 32 : 512;
-    // zlib forces two codes of non-zero frequency; mimic that so a lone symbol still gets a 1-bit code
-    int used = 0;
-    for (int s = lane; s < n; s += 32) used += hist[s] != 0;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) used += __shfl_xor_sync(FULL, used, d);
-    if (used < 2 && lane == 0) {
-        for (int s = 0; s < n && used < 2; ++s)
-            if (hist[s] == 0) {
-                hist[s] = 1;
-                ++used;
-            }
-    }
-    used = max(used, 2);
-    __syncwarp();
-    for (int s = lane; s < npad; s += 32) {
-        const uint32_t f = s < n ? hist[s] : 0;
-        sortbuf[s] = f ? (min(f, 0x7fffffu) << 9) | (uint32_t)s : 0xffffffffu;
-        if (s < n) len[s] = 0;
-    }
-    __syncwarp();
-    warp_sort(sortbuf, npad, lane);
-    // leaves 0..used-1 in ascending weight; internal nodes used..2*used-2 are created in ascending weight too
-    for (int i = lane; i < used; i += 32) weight[i] = sortbuf[i] >> 9;
-    __syncwarp();
-    if (lane == 0) {
-        int li = 0, ii = used, next = used;
-        for (int j = 0; j < used - 1; ++j) {
-            int pick[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                if (li < used && (ii >= next || weight[li] <= weight[ii])) pick[t] = li++;
-                else pick[t] = ii++;
-            }
-            weight[next] = weight[pick[0]] + weight[pick[1]];
-            parent[pick[0]] = (uint16_t)next;
-            parent[pick[1]] = (uint16_t)next;
-            ++next;
-        }
-        // depths: a child always has a smaller index than its parent.  weight[] is reused for the depth.
-        const int root = next - 1;
-        weight[root] = 0;
-        for (int v = root - 1; v >= 0; --v) weight[v] = weight[parent[v]] + 1;
-        // length limiting: clamp the depths to `limit`, measure by how much the Kraft sum now exceeds 1 (in units
-        // of 2^-limit), and repair it one unit at a time the way zlib's gen_bitlen does: push a leaf from the
-        // deepest level above the limit one level down and hang one clamped leaf next to it.
-        for (int b = 0; b <= 15; ++b) bl_count[b] = 0;
-        bool clamped = false;
-        uint32_t kraft = 0;
-        for (int i = 0; i < used; ++i) {
-            int dpt = (int)weight[i];
-            if (dpt > limit) {
-                dpt = limit;
-                clamped = true;
-            }
-            bl_count[dpt]++;
-            kraft += 1u << (limit - dpt);
-        }
-        if (clamped) {
-            int excess = (int)kraft - (1 << limit);
-            while (excess > 0) {
-                int bits = limit - 1;
-                while (bl_count[bits] == 0) --bits;
-                bl_count[bits]--;
-                bl_count[bits + 1] += 2;
-                bl_count[limit]--;
-                --excess;
-            }
-            // hand the lengths out again: longest codes to the rarest symbols (leaves are sorted by weight)
-            int i = 0;
-            for (int bits = limit; bits >= 1; --bits)
-                for (int c = bl_count[bits]; c > 0; --c) weight[i++] = (uint32_t)bits;
-        }
-        for (int i = 0; i < used; ++i) len[sortbuf[i] & 511u] = (uint8_t)weight[i];
-    }
-    __syncwarp();
-}
-
 // canonical codes (RFC 1951 3.2.2), bit-reversed for LSB-first packing; lane 0 does the serial part
 __device__ void canonical_codes(const uint8_t *len, int n, uint16_t *code, uint16_t *bl_count, int lane) {
     if (lane == 0) {
@@ -201,56 +99,6 @@ __device__ void canonical_codes(const uint8_t *len, int n, uint16_t *code, uint1
     }
     __syncwarp();
 }
-
-// ---- output bit buffer (warp-uniform bookkeeping; lanes OR their bits in with shared-memory atomics) ----
-struct BitOut {
-    uint32_t *buf;    // smem words; bit 0 of buf[0] <-> bit 0 of the byte at gbase
-    uint8_t *gbase;   // 16-byte aligned global address of buf[0]
-    uint32_t bitpos;  // next free bit
-    uint32_t head;    // first valid byte of buf (stream start not 16-byte aligned), only before the first flush
-    uint64_t written; // bytes already stored (excluding head padding)
-
-    __device__ __forceinline__ void put(uint32_t pos, uint32_t bits, uint32_t nbits) const {
-        if (nbits == 0) return;
-        const uint32_t w = pos >> 5, sh = pos & 31u;
-        atomicOr(&buf[w], bits << sh);
-        if (sh + nbits > 32) atomicOr(&buf[w + 1], bits >> (32 - sh));
-    }
-    // store whole 16-byte segments, carry the rest (including the partly filled last byte) to the front
-    __device__ void flush(int lane, bool final) {
-        __syncwarp();
-        const uint32_t nbytes = final ? (bitpos + 7) >> 3 : bitpos >> 3;
-        const uint32_t wseg = final ? (nbytes + 15) >> 4 : nbytes >> 4;
-        const uint8_t *b8 = reinterpret_cast<const uint8_t *>(buf);
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(buf);
-        uint4 *g4 = reinterpret_cast<uint4 *>(gbase);
-        for (uint32_t seg = lane; seg < wseg; seg += 32) {
-            const uint32_t lo = seg * 16, hi = lo + 16;
-            if (lo >= head && hi <= nbytes) {
-                g4[seg] = s4[seg];
-            } else {
-                for (uint32_t i = max(lo, head); i < min(hi, nbytes); ++i) gbase[i] = b8[i];
-            }
-        }
-        if (wseg == 0) return;
-        const uint32_t full = final ? nbytes : wseg * 16;
-        written += full - head;
-        head = 0;
-        // carry: bytes [full, ceil(bitpos/8)) move to the front, everything else becomes zero
-        const uint32_t tail_bytes = final ? 0 : ((bitpos + 7) >> 3) - full;
-        uint32_t keep[1];
-        // tail < 16 bytes + slack: at most 4 words plus the slack words (one per lane is plenty)
-        const uint32_t tail_words = (tail_bytes + 3) >> 2;
-        keep[0] = lane < (int)tail_words ? buf[(full >> 2) + lane] : 0u;
-        __syncwarp();
-        for (uint32_t i = lane; i < (DEF_OUT + DEF_OUT_SLACK) / 4; i += 32) buf[i] = 0;
-        __syncwarp();
-        if (lane < (int)tail_words) buf[lane] = keep[0];
-        gbase += full;
-        bitpos -= full * 8;
-        __syncwarp();
-    }
-};
 
 // Adler-32 over n staged bytes (whole warp)
 __device__ __forceinline__ void adler_update(uint32_t &a, uint32_t &b, const uint8_t *p, uint32_t n, int lane) {
