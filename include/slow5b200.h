@@ -135,6 +135,16 @@ int s5b_zlib_deflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_
                          uint64_t in_capacity, const uint32_t *d_split, uint64_t n_reads, uint8_t *d_out,
                          const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream);
 
+/* Replaces ptr_compress_zstd (slow5_press.c:1183-1202: ZSTD_compress at level 1) for a batch: record r becomes one
+ * single-segment zstd frame with its content size in the header (what ptr_depress_zstd requires, :1206-1211) in
+ * the slot [d_out_off[r], d_out_off[r+1]), which must hold s5b_zstd_bound(len).  Same argument contract as
+ * s5b_zlib_deflate_dev, split hint included.  The bytes differ from libzstd's (Huffman-coded literals, no
+ * sequences); any zstd decoder regenerates the exact input. */
+uint64_t s5b_zstd_bound(uint64_t len);
+int s5b_zstd_encode_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                        uint64_t in_capacity, const uint32_t *d_split, uint64_t n_reads, uint8_t *d_out,
+                        const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream);
+
 /* Gathers slotted streams into a dense slab: d_dst_off[r] (n_reads+1 entries, exclusive scan of
  * len rounded up to `align`, align in {1,16}) and the copied bytes.  d_dst capacity is checked
  * against dst_capacity (S5B_ERR_NOSPACE is reported through the return of the host wrappers). */
@@ -165,18 +175,18 @@ int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs,
                             size_t n, void **out_ptrs, size_t *out_n);
 int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
                            size_t n, void **out_ptrs, size_t *out_n);
-/* zlib record compression (the slow5_ptr_compress(record_press) call of slow5_rec_to_mem, slow5.c:4050) for a
- * batch of packed records, with the per-record Huffman-block split hint of s5b_zlib_deflate_dev (splits may
- * be NULL). */
-int s5b_compress_records_host(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, const uint32_t *splits,
-                              size_t n, void **out_ptrs, size_t *out_n);
+/* Record compression (the slow5_ptr_compress(record_press) call of slow5_rec_to_mem, slow5.c:4050) for a batch of
+ * packed records, method S5B_COMPRESS_ZLIB or S5B_COMPRESS_ZSTD, with the per-record Huffman-block split hint of
+ * s5b_zlib_deflate_dev / s5b_zstd_encode_dev (splits may be NULL). */
+int s5b_compress_records_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
+                              const uint32_t *splits, size_t n, void **out_ptrs, size_t *out_n);
 
 /* Whole-batch BLOW5 record transcoding with everything between the two copies on the device: the body of
  * slow5_convert_parallel's batch loop (src/view.c:254-301: work_db over depress_parse_rec_to_mem) for
  * blow5 -> blow5 conversions.  h_in holds n packed records exactly as stored in the file (record i =
  * h_in[rec_off[i] .. +rec_len[i]), size prefixes excluded), compressed with (in_rec, in_sig); h_out receives the
  * output FILE IMAGE -- [u64 size][record bytes] per record, in order -- compressed with (out_rec, out_sig), ready
- * for one fwrite.  Methods: S5B_COMPRESS_NONE / ZLIB for records, NONE / SVB_ZD for signals.  Pinned h_in / h_out
+ * for one fwrite.  Methods: S5B_COMPRESS_NONE / ZLIB / ZSTD for records, NONE / SVB_ZD for signals.  Pinned h_in / h_out
  * (s5b_host_alloc) avoid staging copies.  Returns 0, the first per-record error, or S5B_ERR_NOSPACE with *out_bytes =
  * bytes needed when out_cap is too small. */
 int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,

@@ -98,3 +98,7 @@ lib.s5b_zstd_decode_dev.restype = C.c_int
 lib.s5b_zstd_decode_dev.argtypes = [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]
 lib.s5b_zstd_content_size.restype = C.c_int
 lib.s5b_zstd_content_size.argtypes = [_vp, _sz, _P(_u64)]
+lib.s5b_zstd_bound.restype = _u64
+lib.s5b_zstd_bound.argtypes = [_u64]
+lib.s5b_zstd_encode_dev.restype = C.c_int
+lib.s5b_zstd_encode_dev.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]

@@ -111,6 +111,11 @@ class Codec:
                                              in_len.numel(), _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status),
                                              self._stream()), "s5b_zlib_deflate_dev")
 
+    def zstd_encode_dev(self, din, in_off, in_len, out, out_off, out_len, status, split=None):
+        self._check(lib.s5b_zstd_encode_dev(self._h, _ptr(din), _ptr(in_off), _ptr(in_len), din.numel(), _ptr(split),
+                                            in_len.numel(), _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status),
+                                            self._stream()), "s5b_zstd_encode_dev")
+
     def compact_dev(self, src, src_off, length, dst, dst_off, align=16):
         self._check(lib.s5b_compact_dev(self._h, _ptr(src), _ptr(src_off), _ptr(length), length.numel(), align,
                                         _ptr(dst), _ptr(dst_off), self._stream()), "s5b_compact_dev")

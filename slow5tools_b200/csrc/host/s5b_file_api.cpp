@@ -86,8 +86,9 @@ int s5b_hdr_copy(s5b_file_t *dst, const s5b_file_t *src) {
 }
 int s5b_set_press(s5b_file_t *f, int rec_press, int sig_press) {
     if (!f || !f->writing || f->hdr_written) return fail(S5B_ERR_ARG);
-    if ((rec_press != PRESS_NONE && rec_press != PRESS_ZLIB) || (sig_press != PRESS_NONE && sig_press != PRESS_SVB_ZD))
-        return fail(S5B_ERR_ARG);  // zstd / ex-zd: not in this build (slow5_press.c:282-290 behaves alike without zstd)
+    if ((rec_press != PRESS_NONE && rec_press != PRESS_ZLIB && rec_press != PRESS_ZSTD) ||
+        (sig_press != PRESS_NONE && sig_press != PRESS_SVB_ZD))
+        return fail(S5B_ERR_ARG);  // ex-zd: not in this build
     f->rec_press = rec_press;
     f->sig_press = sig_press;
     return 0;
@@ -275,20 +276,22 @@ int s5b_encode_batch(s5b_file_t *f, s5b_rec_t **reads, size_t n, char **mems, si
     }
     std::vector<void *> z(n, nullptr);
     std::vector<size_t> z_n(n, 0);
-    if (f->rec_press == PRESS_ZLIB) {
+    const bool rec_packed = f->rec_press == PRESS_ZLIB || f->rec_press == PRESS_ZSTD;
+    if (rec_packed) {
         for (size_t i = 0; i < n; ++i) {
             ptrs[i] = packed[i].data();
             counts[i] = packed[i].size();
         }
-        const int rc = s5b_compress_records_host(f->gpu, ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
+        const int rc = s5b_compress_records_host(f->gpu, f->rec_press == PRESS_ZSTD ? S5B_COMPRESS_ZSTD : S5B_COMPRESS_ZLIB,
+                                                 ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
         if (rc != S5B_OK) {
             for (void *p : z) free(p);
             return fail(rc);
         }
     }
     for (size_t i = 0; i < n; ++i) {
-        const void *p = f->rec_press == PRESS_ZLIB ? z[i] : packed[i].data();
-        const uint64_t sz = f->rec_press == PRESS_ZLIB ? z_n[i] : packed[i].size();
+        const void *p = rec_packed ? z[i] : packed[i].data();
+        const uint64_t sz = rec_packed ? z_n[i] : packed[i].size();
         char *m = static_cast<char *>(malloc(8 + sz));
         if (!m) return fail(S5B_ERR_MEM);
         memcpy(m, &sz, 8);  // size prefix, slow5.c:4055-4060

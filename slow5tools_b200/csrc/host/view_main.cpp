@@ -75,7 +75,7 @@ void usage(FILE *f) {
             "    -K, --batchsize INT           number of records loaded to the memory at once [4096]\n"
             "    --from FORMAT                 specify input file format (slow5 or blow5)\n"
             "    -h, --help                    display this message and exit\n"
-            "REC_MTD: none, zlib      SIG_MTD: none, svb-zd      (zstd / ex-zd: not in this build)\n");
+            "REC_MTD: none, zlib, zstd      SIG_MTD: none, svb-zd      (ex-zd: not in this build)\n");
 }
 
 struct Batch {
@@ -356,9 +356,6 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
 
 }  // namespace
 
-extern "C" int s5b_compress_records_host(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts,
-                                         const uint32_t *splits, size_t n, void **out_ptrs, size_t *out_n);
-
 int view_main(int argc, char **argv) {
     static const struct option long_opts[] = {
         {"sig-compress", required_argument, nullptr, 's'}, {"compress", required_argument, nullptr, 'c'},
@@ -435,8 +432,9 @@ int view_main(int argc, char **argv) {
         return 1;
     }
     if (fmt_out == FMT_ASCII) rec_out = sig_out = PRESS_NONE;
-    if ((rec_out != PRESS_NONE && rec_out != PRESS_ZLIB) || (sig_out != PRESS_NONE && sig_out != PRESS_SVB_ZD)) {
-        ERROR("%s", "this build supports record compression none/zlib and signal compression none/svb-zd only");
+    if ((rec_out != PRESS_NONE && rec_out != PRESS_ZLIB && rec_out != PRESS_ZSTD) ||
+        (sig_out != PRESS_NONE && sig_out != PRESS_SVB_ZD)) {
+        ERROR("%s", "this build supports record compression none/zlib/zstd and signal compression none/svb-zd only");
         return 1;
     }
 
@@ -633,20 +631,22 @@ int view_main(int argc, char **argv) {
             for (void *p : svb) free(p);
             std::vector<void *> z(n, nullptr);
             std::vector<size_t> z_n(n, 0);
-            if (ret == 0 && rec_out == PRESS_ZLIB) {
+            const bool rec_packed = rec_out == PRESS_ZLIB || rec_out == PRESS_ZSTD;
+            if (ret == 0 && rec_packed) {
                 for (size_t i = 0; i < n; ++i) {
                     ptrs[i] = rec_mem[i].data();
                     counts[i] = rec_mem[i].size();
                 }
-                const int rc = s5b_compress_records_host(gpu, ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
+                const int rc = s5b_compress_records_host(gpu, rec_out == PRESS_ZSTD ? S5B_COMPRESS_ZSTD : S5B_COMPRESS_ZLIB,
+                                                         ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
                 if (rc != S5B_OK) {
                     ERROR("record compression failed: %s", s5b_strerror(rc));
                     ret = 1;
                 }
             }
             for (size_t i = 0; i < n && ret == 0; ++i) {
-                const void *p = rec_out == PRESS_ZLIB ? z[i] : rec_mem[i].data();
-                const uint64_t sz = rec_out == PRESS_ZLIB ? z_n[i] : rec_mem[i].size();
+                const void *p = rec_packed ? z[i] : rec_mem[i].data();
+                const uint64_t sz = rec_packed ? z_n[i] : rec_mem[i].size();
                 if (fwrite(&sz, 8, 1, fout) != 1 || (sz && fwrite(p, 1, sz, fout) != sz)) ret = 1;  // slow5.c:4055-4060
             }
             for (void *p : z) free(p);

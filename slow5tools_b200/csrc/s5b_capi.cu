@@ -78,7 +78,7 @@ struct PipeSlot {
 struct s5b_ctx {
     int device = 0;
     int num_sms = 0;
-    int enc_bps = 0, dec_bps = 0, inf_bps = 0, def_bps = 0, zd_bps = 0;
+    int enc_bps = 0, dec_bps = 0, inf_bps = 0, def_bps = 0, zd_bps = 0, ze_bps = 0;
     DevBuf zd_scratch;
     cudaStream_t stream = nullptr;  // default stream for *_dev calls
     unsigned long long *d_counter = nullptr;
@@ -174,7 +174,9 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
     ctx->inf_bps = inflate_blocks_per_sm();
     ctx->def_bps = deflate_blocks_per_sm();
     ctx->zd_bps = zstd_decode_blocks_per_sm();
-    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0 || ctx->inf_bps <= 0 || ctx->def_bps <= 0 || ctx->zd_bps <= 0) {  // no sm_100a image for this device
+    ctx->ze_bps = zstd_encode_blocks_per_sm();
+    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0 || ctx->inf_bps <= 0 || ctx->def_bps <= 0 || ctx->zd_bps <= 0 ||
+        ctx->ze_bps <= 0) {  // no sm_100a image for this device
         (void)cudaGetLastError();
         delete ctx;
         return S5B_ERR_DEVICE;
@@ -337,6 +339,24 @@ int s5b_zlib_deflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_
     DeflateArgs a{d_in, d_in_off, d_in_len, in_capacity, d_split, n_reads, d_out, d_out_off, d_out_len, d_status,
                   ctx->d_counter + 24};
     CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+uint64_t s5b_zstd_bound(uint64_t len) { return round_up(zstd_encode_bound(len), 16); }
+
+int s5b_zstd_encode_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                        uint64_t in_capacity, const uint32_t *d_split, uint64_t n_reads, uint8_t *d_out,
+                        const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_len || !d_status) return S5B_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (in_capacity & 15u)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    DeflateArgs a{d_in, d_in_off, d_in_len, in_capacity, d_split, n_reads, d_out, d_out_off, d_out_len, d_status,
+                  ctx->d_counter + 20};
+    CU(launch_zstd_encode(a, ctx->num_sms, ctx->ze_bps, st));
     ctx->launches += 1;
     return S5B_OK;
 }
@@ -805,8 +825,9 @@ static int zlib_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size
     return first;
 }
 
-static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, const uint32_t *splits,
-                              size_t n, void **out_ptrs, size_t *out_n) {
+// record / buffer entropy coding for the pointer-array forms: method is S5B_COMPRESS_ZLIB or S5B_COMPRESS_ZSTD
+static int entropy_compress_ptrs(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
+                                 const uint32_t *splits, size_t n, void **out_ptrs, size_t *out_n) {
     std::vector<uint64_t> in_off(n + 1), out_off(n + 1);
     std::vector<uint32_t> in_len(n), out_len(n);
     std::vector<int32_t> status(n);
@@ -820,7 +841,7 @@ static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const siz
         in_off[i] = tot;
         tot += round_up(in_len[i], 16);
         out_off[i] = otot;
-        otot += s5b_zlib_bound(in_len[i]);
+        otot += method == S5B_COMPRESS_ZSTD ? s5b_zstd_bound(in_len[i]) : s5b_zlib_bound(in_len[i]);
     }
     in_off[n] = tot;
     out_off[n] = otot;
@@ -846,7 +867,8 @@ static int zlib_compress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const siz
     CU(cudaMemcpyAsync(d_in_len, in_len.data(), n * 4, cudaMemcpyHostToDevice, st));
     DeflateArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), splits ? d_split : nullptr, n,
                   static_cast<uint8_t *>(s.d_b.p), d_out_off, d_out_len, d_status, s.d_counter};
-    CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
+    if (method == S5B_COMPRESS_ZSTD) CU(launch_zstd_encode(a, ctx->num_sms, ctx->ze_bps, st));
+    else CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
     ctx->launches += 1;
     CU(cudaMemcpyAsync(out_len.data(), d_out_len, n * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(status.data(), d_status, n * 4, cudaMemcpyDeviceToHost, st));
@@ -961,20 +983,22 @@ int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs,
     switch (method) {
         case S5B_COMPRESS_NONE: return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_SVB_ZD: return svbzd_compress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
-        case S5B_COMPRESS_ZLIB: {
+        case S5B_COMPRESS_ZLIB:
+        case S5B_COMPRESS_ZSTD: {
             DeviceGuard g(ctx->device);
-            return zlib_compress_ptrs(ctx, ptrs, counts, nullptr, n, out_ptrs, out_n);
+            return entropy_compress_ptrs(ctx, method, ptrs, counts, nullptr, n, out_ptrs, out_n);
         }
         default: return S5B_ERR_ARG;
     }
 }
 
-int s5b_compress_records_host(s5b_ctx_t *ctx, const void *const *ptrs, const size_t *counts, const uint32_t *splits,
-                              size_t n, void **out_ptrs, size_t *out_n) {
+int s5b_compress_records_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
+                              const uint32_t *splits, size_t n, void **out_ptrs, size_t *out_n) {
     if (!ctx || (n && (!ptrs || !counts || !out_ptrs || !out_n))) return S5B_ERR_ARG;
+    if (method != S5B_COMPRESS_ZLIB && method != S5B_COMPRESS_ZSTD) return S5B_ERR_ARG;
     if (n == 0) return S5B_OK;
     DeviceGuard g(ctx->device);
-    return zlib_compress_ptrs(ctx, ptrs, counts, splits, n, out_ptrs, out_n);
+    return entropy_compress_ptrs(ctx, method, ptrs, counts, splits, n, out_ptrs, out_n);
 }
 
 int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts, size_t n,
@@ -1018,10 +1042,9 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
     *out_bytes = 0;
     if (n == 0) return S5B_OK;
     if (!h_in || !rec_off || !rec_len || !h_out) return S5B_ERR_ARG;
-    auto rec_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_ZLIB; };
+    auto rec_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_ZLIB || m == S5B_COMPRESS_ZSTD; };
     auto sig_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_SVB_ZD; };
-    // zstd records can be read (the reference pins the decode direction only, test/test_view.sh:216-229), not written
-    if (!(rec_ok(in_rec) || in_rec == S5B_COMPRESS_ZSTD) || !rec_ok(out_rec) || !sig_ok(in_sig) || !sig_ok(out_sig))
+    if (!rec_ok(in_rec) || !rec_ok(out_rec) || !sig_ok(in_sig) || !sig_ok(out_sig))
         return S5B_ERR_ARG;
     DeviceGuard g(ctx->device);
     cudaStream_t st = ctx->slot[0].stream;
@@ -1194,8 +1217,8 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
         fin_cap = round_up(total, 16);
     }
     // ---- record compression (slow5.c:4050)
-    if (out_rec == S5B_COMPRESS_ZLIB) {
-        if (in_rec == S5B_COMPRESS_ZLIB && in_sig == out_sig) {
+    if (out_rec == S5B_COMPRESS_ZLIB || out_rec == S5B_COMPRESS_ZSTD) {
+        if (in_rec == out_rec && in_sig == out_sig) {
             // nothing changed inside the records: the stored compressed records are the answer
             fin = static_cast<const uint8_t *>(ctx->r_in.p);
             fin_off = d_rec_off;
@@ -1212,7 +1235,9 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
             }
             DeflateArgs za{fin, fin_off, fin_len, fin_cap, split, n, static_cast<uint8_t *>(ctx->r_z.p), d_z_off, d_z_len, d_st3,
                            counter};
-            CU(launch_deflate(za, ctx->num_sms, ctx->def_bps, st));
+            // PLAN_ZLIB_BOUND slots also cover zstd_encode_bound() (3 bytes of header per block instead of 6)
+            if (out_rec == S5B_COMPRESS_ZSTD) CU(launch_zstd_encode(za, ctx->num_sms, ctx->ze_bps, st));
+            else CU(launch_deflate(za, ctx->num_sms, ctx->def_bps, st));
             ctx->launches += 3;
             if (check_status(d_st3) != S5B_OK) return S5B_ERR_DEVICE;
             if (first_err != S5B_OK) return first_err;

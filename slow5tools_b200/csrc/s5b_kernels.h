@@ -60,6 +60,11 @@ int deflate_blocks_per_sm();
 uint64_t deflate_bound(uint64_t len);
 cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
 
+// zstd frame encoder: same argument block as deflate (split hint included)
+int zstd_encode_blocks_per_sm();
+uint64_t zstd_encode_bound(uint64_t len);
+cudaError_t launch_zstd_encode(const DeflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
+
 // zstd frames: same argument block as inflate (exact output slots: every frame carries its content size)
 int zstd_decode_blocks_per_sm();
 size_t zstd_decode_scratch_bytes(int num_sms, int blocks_per_sm);
