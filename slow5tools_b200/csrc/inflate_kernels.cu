@@ -7,12 +7,19 @@
 // early is NOT an error there (Z_BUF_ERROR / Z_OK fall through, :1001-1003) and yields the bytes decoded
 // so far -- mirrored here; bytes after the Adler-32 trailer are ignored.
 //
-// Every record is an independent complete zlib stream (slow5.c:4046, slow5_press.c:868-871), so the
-// parallelism is across records: one warp per stream.  Within a warp lane 0 runs the serial Huffman
-// decode out of shared memory (input staged by 1-D bulk async copies into a per-warp ring, 10-bit /
-// 8-bit first-level lookup tables built cooperatively per block); all lanes cooperate on table
-// construction, long LZ77 copies, the Adler-32 and the 128-bit coalesced stores of the output staging
-// buffer.  Latency/issue bound, far from the HBM roofline by nature -- see DESIGN.md.
+// Every record is an independent complete zlib stream (slow5.c:4046, slow5_press.c:868-871): one warp per
+// stream.  Inside a Huffman block the symbols are decoded by ALL 32 lanes at once ("window decode"): the
+// compressed bits ahead are cut into 32 chunks, every lane decodes its chunk speculatively from the chunk's
+// first bit, and because Huffman codes self-synchronise a wrongly started lane falls onto true symbol
+// boundaries within a few symbols; lanes then restart at their left neighbour's end position until all
+// boundaries agree (usually one extra round), a warp prefix scan over the per-lane output byte counts gives
+// the output offsets, and a last pass writes the literals while LZ77 matches are queued and resolved in stream
+// order by the whole warp.  Anything unusual (stored blocks, invalid codes, the last < 48 bits of a stream,
+// a too small output slot, windows that do not fit the staging buffer) is handed to the serial decoder --
+// lane 0 running out of shared memory (input ring filled by 1-D bulk async copies, 10-bit / 8-bit first-level
+// tables) -- which also owns every error / truncation verdict, so behaviour matches zlib's exactly.  All
+// lanes cooperate on table construction, LZ77 copies, the Adler-32 and the 128-bit stores of the staging
+// buffer.
 #include "s5b_kernels.h"
 #include "s5b_ptx.cuh"
 #include "../../include/slow5b200.h"
@@ -25,7 +32,14 @@ constexpr int INF_WARPS = 4;
 constexpr int INF_BLK = 1024;  // input ring block
 constexpr int INF_NB = 2;
 constexpr int INF_RING = INF_BLK * INF_NB;
-constexpr int INF_STAGE = 4096;  // output staging bytes (a multiple of 16)
+constexpr int INF_STAGE = 8192;  // output staging bytes (a multiple of 16)
+constexpr int PAR_CHUNK_MAX_BITS = 1024;  // window decode: at most this many compressed bits per lane and window
+constexpr int PAR_CHUNK_MIN_BITS = 64;
+constexpr int PAR_CHUNK_START_BITS = 128; // first window of a block (its end is unknown: bits past the end-of-block
+                                          // symbol are decoded for nothing), x4 for every further window
+constexpr int PAR_LIST = 256;             // queued matches per window
+constexpr int PAR_MAX_ROUNDS = 8;         // boundary rounds before only the agreed prefix of lanes is committed
+constexpr uint32_t PAR_SYM_BITS = 48;     // longest length/distance pair: 15 + 5 + 15 + 13
 constexpr int LIT_FAST_BITS = 10;
 constexpr int DIST_FAST_BITS = 8;
 constexpr uint32_t ADLER_MOD = 65521u;
@@ -47,6 +61,7 @@ struct __align__(128) InfWarpSmem {
     uint16_t dist_fcode[16], dist_fidx[16];
     uint16_t cl_fcode[16], cl_fidx[16];
     uint8_t lens[384];                        // code lengths: lit/len at 0, dist at 288; scratch from 32
+    uint2 list[PAR_LIST];                     // window decode: (stage position | length << 16, distance)
     unsigned long long bar[INF_NB];
 };
 
@@ -67,6 +82,10 @@ enum : int32_t { END_OK = 0, END_TRUNC = 1, END_ERR = 2 };
 // ---- input side (lane 0 only) ----------------------------------------------------------------
 struct BitReader {
     const uint8_t *ring;     // smem
+    const uint8_t *p0;       // first byte of the stream (global)
+    const uint8_t *slab_end; // end of the input slab (bulk copies never read past it)
+    uint32_t full_len;       // stream bytes
+    uint32_t base;           // stream byte the ring was (re)started at: ipos / in_len count from here
     const uint8_t *src16;    // 16-byte aligned global address of ring position 0
     uint64_t lim;            // bulk-copyable bytes from src16
     uint32_t bar0, ring0;    // smem addresses
@@ -136,7 +155,177 @@ struct BitReader {
             ++waited;
         }
     }
+    // (re)start the ring at stream byte `byte`
+    __device__ __forceinline__ void start_at(uint32_t byte) {
+        const uint8_t *p = p0 + byte;
+        base = byte;
+        skew = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+        src16 = p - skew;
+        in_len = full_len - byte;
+        lim = ((uint64_t)skew + in_len + 15) & ~15ull;
+        const uint64_t room = (uint64_t)(slab_end - src16);
+        if (lim > room) lim = room & ~15ull;
+        nblk = in_len ? (uint32_t)((lim + INF_BLK - 1) / INF_BLK) : 0;
+        issued = waited = 0;
+        ipos = 0;
+        bb = 0;
+        nb = 0;
+        recycle();
+    }
+    // stream bit position of the next unread bit
+    __device__ __forceinline__ uint32_t bitpos() const { return (base + ipos) * 8u - nb; }
+    // continue at an arbitrary stream bit (after a window decode ran ahead of the ring)
+    __device__ __forceinline__ void seek_bit(uint32_t bit) {
+        drain();
+        start_at(bit >> 3);
+        refill();
+        const uint32_t frac = bit & 7u;
+        if (nb >= frac) drop(frac);
+    }
 };
+
+// ---- window decode (all lanes) ------------------------------------------------------------------
+// how a lane's run over its chunk ended
+enum : uint32_t { PS_NONE = 0, PS_EOB = 1, PS_INVALID = 2, PS_TAIL = 3 };
+// what a window did
+enum : uint32_t { PAR_CONT = 0, PAR_EOB = 1, PAR_SERIAL = 2, PAR_FLUSH = 3, PAR_ERR = 4 };
+
+struct ParIn {               // warp-uniform view of the compressed stream
+    const uint32_t *w4;      // 4-byte aligned global address at or below the first stream byte
+    uint32_t bit0;           // position of stream bit 0 inside w4[0] (0, 8, 16 or 24)
+    uint32_t nwords;         // words that hold stream bytes
+    uint32_t end_bits;       // stream length in bits
+};
+
+struct LaneBits {
+    uint64_t bb;
+    uint32_t nb, wi;  // wi: index of the word held in `ahead`
+    uint32_t ahead;   // loaded one refill early, so its latency hides behind the symbols in between
+    __device__ __forceinline__ void seek(const ParIn &in, uint32_t p) {
+        const uint32_t q = p + in.bit0;
+        wi = q >> 5;
+        const uint32_t w = wi < in.nwords ? __ldg(in.w4 + wi) : 0u;
+        ++wi;
+        ahead = wi < in.nwords ? __ldg(in.w4 + wi) : 0u;
+        bb = w >> (q & 31u);
+        nb = 32u - (q & 31u);
+    }
+    __device__ __forceinline__ void refill(const ParIn &in) {
+        if (nb <= 32) {
+            bb |= (uint64_t)ahead << nb;
+            nb += 32;
+            ++wi;
+            ahead = wi < in.nwords ? __ldg(in.w4 + wi) : 0u;
+        }
+    }
+    __device__ __forceinline__ void drop(uint32_t n) {
+        bb >>= n;
+        nb -= n;
+    }
+};
+
+// canonical walk for codes longer than the first-level table, on a lane's own bit buffer (>= 15 valid bits)
+__device__ __forceinline__ int slow_walk(uint64_t bits, const uint16_t *count, const uint16_t *sorted, const uint16_t *fcode,
+                                         const uint16_t *fidx, const int fast_bits, uint32_t *used) {
+    uint32_t code = __brev((uint32_t)bits) >> (32 - fast_bits);
+    uint64_t b = bits >> fast_bits;
+    for (uint32_t len = fast_bits + 1; len <= 15; ++len) {
+        code = (code << 1) | (uint32_t)(b & 1u);
+        b >>= 1;
+        const uint32_t d = code - fcode[len];
+        if (d < count[len]) {
+            *used = len;
+            return sorted[fidx[len] + d];
+        }
+    }
+    return -1;
+}
+
+struct LenDistTabs {  // CTA-shared copies of the RFC 1951 base / extra-bit tables (divergent indices)
+    uint16_t len_base[32];
+    uint16_t dist_base[32];
+    uint8_t len_extra[32];
+    uint8_t dist_extra[32];
+};
+
+// One lane decodes the symbols that START in [start, limit).  WRITE = false: count output bytes and matches;
+// WRITE = true: literals go to out[], matches are queued as (stage position, length, distance).
+template <bool WRITE>
+__device__ __forceinline__ void par_run(const InfWarpSmem &ws, const LenDistTabs &ld, const ParIn &in, const uint32_t start,
+                                        const uint32_t limit, uint32_t &end, uint32_t &nbytes, uint32_t &nmatch,
+                                        uint32_t &stop, uint8_t *stage, uint32_t o, uint2 *list, uint32_t list_at) {
+    LaneBits b;
+    uint32_t p = start, nby = 0, nm = 0, st = PS_NONE;
+    // the last PAR_SYM_BITS of the stream belong to the serial decoder (it owns the truncation verdicts)
+    const uint32_t safe = in.end_bits - PAR_SYM_BITS;
+    const uint32_t lim2 = min(limit, safe + 1u);
+    if (p < lim2) b.seek(in, p);
+    if (p < limit && p > safe) st = PS_TAIL;
+    while (p < lim2) {
+        b.refill(in);
+        uint32_t e = ws.lit_fast[(uint32_t)b.bb & ((1u << LIT_FAST_BITS) - 1u)];
+        uint32_t l = e & 15u;
+        int sym = (int)(e >> 4);
+        if (l == 0) {
+            sym = slow_walk(b.bb, ws.lit_count, ws.lit_sorted, ws.lit_fcode, ws.lit_fidx, LIT_FAST_BITS, &l);
+            if (sym < 0) {
+                st = PS_INVALID;
+                break;
+            }
+        }
+        if (sym < 256) {
+            if (WRITE) stage[o] = (uint8_t)sym;
+            ++o;
+            ++nby;
+            b.drop(l);
+            p += l;
+            continue;
+        }
+        if (sym == 256) {
+            p += l;
+            st = PS_EOB;
+            break;
+        }
+        if (sym > 285) {
+            st = PS_INVALID;
+            break;
+        }
+        b.drop(l);
+        const uint32_t li = (uint32_t)sym - 257u;
+        const uint32_t lx = ld.len_extra[li];
+        const uint32_t mlen = ld.len_base[li] + ((uint32_t)b.bb & ((1u << lx) - 1u));
+        b.drop(lx);
+        b.refill(in);
+        const uint32_t de = ws.dist_fast[(uint32_t)b.bb & ((1u << DIST_FAST_BITS) - 1u)];
+        uint32_t dl = de & 15u;
+        int dsym = (int)(de >> 4);
+        if (dl == 0) {
+            dsym = slow_walk(b.bb, ws.dist_count, ws.dist_sorted, ws.dist_fcode, ws.dist_fidx, DIST_FAST_BITS, &dl);
+            if (dsym < 0) {
+                st = PS_INVALID;
+                break;
+            }
+        }
+        if (dsym > 29) {
+            st = PS_INVALID;
+            break;
+        }
+        b.drop(dl);
+        const uint32_t dx = ld.dist_extra[dsym];
+        const uint32_t dist = ld.dist_base[dsym] + ((uint32_t)b.bb & ((1u << dx) - 1u));
+        b.drop(dx);
+        p += l + lx + dl + dx;
+        if (WRITE) list[list_at + nm] = make_uint2(o | (mlen << 16), dist);
+        o += mlen;
+        nby += mlen;
+        ++nm;
+    }
+    if (st == PS_NONE && p < limit) st = PS_TAIL;
+    end = p;
+    nbytes = nby;
+    nmatch = nm;
+    stop = st;
+}
 
 // canonical decode for codes longer than the first-level table: the first `fast_bits` bits are already known
 // not to form a code, so the walk starts at length fast_bits + 1 with the per-length first code / first index
@@ -266,6 +455,14 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
     InfWarpSmem &ws = reinterpret_cast<InfWarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(&ws.bar[0]);
+    __shared__ LenDistTabs ld;
+    if (threadIdx.x < 32) {
+        ld.len_base[threadIdx.x] = threadIdx.x < 29 ? c_len_base[threadIdx.x] : 0;
+        ld.len_extra[threadIdx.x] = threadIdx.x < 29 ? c_len_extra[threadIdx.x] : 0;
+        ld.dist_base[threadIdx.x] = threadIdx.x < 30 ? c_dist_base[threadIdx.x] : 0;
+        ld.dist_extra[threadIdx.x] = threadIdx.x < 30 ? c_dist_extra[threadIdx.x] : 0;
+    }
+    __syncthreads();
     if (lane == 0) {
         for (int s = 0; s < INF_NB; ++s) mbar_init(bar0 + 8 * s, 1);
         mbar_fence_init();
@@ -293,25 +490,29 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
 
         // ---- input side: only lane 0 ever advances it
         BitReader br;
+        ParIn pin;
         {
             const uint8_t *p = a.in + ioff;
             br.ring = ws.ring;
-            br.skew = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
-            br.src16 = p - br.skew;
-            br.lim = ((uint64_t)br.skew + ilen + 15) & ~15ull;
-            const uint64_t room = a.in_capacity - (uint64_t)(br.src16 - a.in);
-            if (br.lim > room) br.lim = room & ~15ull;
+            br.p0 = p;
+            br.slab_end = a.in + a.in_capacity;
+            br.full_len = ilen;
             br.bar0 = bar0;
             br.ring0 = smem_u32(&ws.ring[0]);
-            br.nblk = ilen ? (uint32_t)((br.lim + INF_BLK - 1) / INF_BLK) : 0;
-            br.issued = br.waited = 0;
             br.phase_bits = phase_bits;
-            br.in_len = ilen;
-            br.ipos = 0;
-            br.bb = 0;
-            br.nb = 0;
-            if (lane == 0) br.recycle();
+            br.issued = br.waited = 0;
+            if (lane == 0) br.start_at(0);
+            const uint32_t sk4 = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+            pin.w4 = reinterpret_cast<const uint32_t *>(p - sk4);
+            pin.bit0 = sk4 * 8u;
+            pin.nwords = (sk4 + ilen + 3u) >> 2;
+            pin.end_bits = ilen * 8u;
         }
+        // window decode is attempted once per Huffman block, right after its tables are built (warp-uniform)
+        bool try_par = false;
+        uint32_t par_pos = 0;  // stream bit the next window starts at while try_par is set
+        uint32_t par_chunk = PAR_CHUNK_START_BITS;
+        const bool par_allowed = ilen < (1u << 28);
         // ---- output staging (warp-uniform): stage[i] <-> global gbase[i], gbase 16-byte aligned.
         //   [vstart, spos) valid bytes not yet stored, [astart, spos) not yet counted in total / Adler-32.
         //   absolute output position of stage[i] = total - astart + i.
@@ -343,6 +544,111 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
 
         while (!stream_done) {
             uint32_t ev = 0, ev_a = 0, ev_b = 0;
+            if (try_par) {
+                // ---- window decode: all lanes, see the header comment
+                uint32_t result = PAR_SERIAL;
+                const uint32_t P0 = par_pos;
+                const uint32_t rem = pin.end_bits - P0;
+                if (rem >= 2u * PAR_SYM_BITS) {
+                    const uint32_t W = min(rem, 32u * par_chunk);
+                    par_chunk = min(par_chunk * 4u, (uint32_t)PAR_CHUNK_MAX_BITS);
+                    const uint32_t C = max((uint32_t)PAR_CHUNK_MIN_BITS, (W + 31u) >> 5);
+                    const uint32_t We = P0 + W;
+                    uint32_t start = min(P0 + (uint32_t)lane * C, We);
+                    const uint32_t limit = min(P0 + ((uint32_t)lane + 1u) * C, We);
+                    uint32_t end, nby, nm, stop;
+                    par_run<false>(ws, ld, pin, start, limit, end, nby, nm, stop, nullptr, 0, nullptr, 0);
+                    // boundary rounds: a lane whose left neighbour ended somewhere else than it started decodes again
+                    uint32_t agreed = 32;
+                    for (int round = 1;; ++round) {
+                        const uint32_t pe = __shfl_up_sync(FULL, end, 1);
+                        const uint32_t ps = __shfl_up_sync(FULL, stop, 1);
+                        const bool need = lane > 0 && ps == PS_NONE && pe != start;
+                        const uint32_t needmask = __ballot_sync(FULL, need);
+                        if (!needmask) break;
+                        if (round > PAR_MAX_ROUNDS) {
+                            agreed = (uint32_t)__ffs(needmask) - 1u;  // lanes below the first disagreement are exact
+                            break;
+                        }
+                        if (need) {
+                            start = pe;
+                            par_run<false>(ws, ld, pin, start, limit, end, nby, nm, stop, nullptr, 0, nullptr, 0);
+                        }
+                    }
+                    // lanes [0, nvalid) hold the true decode; the last of them may have stopped (EOB / invalid / tail)
+                    const uint32_t stopmask = __ballot_sync(FULL, stop != PS_NONE) & (agreed < 32 ? (1u << agreed) - 1u : FULL);
+                    const uint32_t nvalid = stopmask ? (uint32_t)__ffs(stopmask) : agreed;
+                    const uint32_t cb = (uint32_t)lane < nvalid ? nby : 0u, cm = (uint32_t)lane < nvalid ? nm : 0u;
+                    uint32_t ib = cb, im = cm;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t tb = __shfl_up_sync(FULL, ib, d), tm = __shfl_up_sync(FULL, im, d);
+                        if (lane >= d) {
+                            ib += tb;
+                            im += tm;
+                        }
+                    }
+                    const uint32_t win_bytes = __shfl_sync(FULL, ib, 31);
+                    if (total + (spos - astart) + win_bytes <= ocap) {  // else: the serial decoder owns slot overflow
+                        const uint32_t room = (uint32_t)INF_STAGE - spos;
+                        const bool fits = (uint32_t)lane < nvalid && ib <= room && im <= (uint32_t)PAR_LIST;
+                        const uint32_t fitmask = __ballot_sync(FULL, fits);
+                        const uint32_t m = fitmask == FULL ? 32u : (uint32_t)__ffs(~fitmask) - 1u;  // leading lanes that fit
+                        if (m == 0) {
+                            result = spos > 64 ? PAR_FLUSH : PAR_SERIAL;
+                        } else {
+                            if ((uint32_t)lane < m) {
+                                uint32_t e2, b2, m2, s2;
+                                par_run<true>(ws, ld, pin, start, limit, e2, b2, m2, s2, ws.stage, spos + ib - cb, ws.list, im - cm);
+                            }
+                            __syncwarp();
+                            const uint32_t tot_b = __shfl_sync(FULL, ib, m - 1), tot_m = __shfl_sync(FULL, im, m - 1);
+                            // queued matches, in stream order; sources that left the stage are read back through L2
+                            const int64_t stage0 = (int64_t)total - (int64_t)astart;  // absolute position of stage[0]
+                            bool bad = false;
+                            for (uint32_t k = 0; k < tot_m; ++k) {
+                                const uint2 mt = ws.list[k];
+                                const uint32_t o = mt.x & 0xffffu, mlen = mt.x >> 16, dist = mt.y;
+                                const int64_t pos = stage0 + o;
+                                if ((int64_t)dist > pos) {  // "invalid distance too far back"
+                                    bad = true;
+                                    break;
+                                }
+                                for (uint32_t kk = lane; kk < mlen; kk += 32) {
+                                    const int64_t sp = pos - dist + (kk % dist);
+                                    const int64_t si = sp - stage0;
+                                    ws.stage[o + kk] = si >= (int64_t)vstart ? ws.stage[si] : __ldcg(dst + sp);
+                                }
+                                __syncwarp();
+                            }
+                            if (bad) {
+                                result = PAR_ERR;
+                            } else {
+                                spos += tot_b;
+                                par_pos = __shfl_sync(FULL, end, m - 1);
+                                const uint32_t last_stop = __shfl_sync(FULL, stop, m - 1);
+                                result = last_stop == PS_NONE ? PAR_CONT : last_stop == PS_EOB ? PAR_EOB : PAR_SERIAL;
+                            }
+                        }
+                    }
+                }
+                if (result == PAR_ERR) {
+                    ev = EV_END;
+                    ev_a = END_ERR;
+                } else if (result == PAR_FLUSH) {
+                    ev = EV_FLUSH;
+                } else {
+                    if (result != PAR_CONT) {  // leaving the block (EOB) or handing the rest of it to lane 0
+                        try_par = false;
+                        if (lane == 0) {
+                            if (br.bitpos() != par_pos) br.seek_bit(par_pos);
+                            if (result == PAR_EOB) in_block = false;
+                        }
+                    }
+                    if (spos > (uint32_t)INF_STAGE / 2) ev = EV_FLUSH;
+                }
+                __syncwarp();
+            } else {
             if (lane == 0) {
                 // ---- decode until something needs the whole warp
                 for (;;) {
@@ -586,6 +892,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
             ev_a = __shfl_sync(FULL, ev_a, 0);
             ev_b = __shfl_sync(FULL, ev_b, 0);
             spos = __shfl_sync(FULL, spos, 0);
+            }
 
             if (ev == EV_TABLES) {
                 // ---- fixed (btype 1) or dynamic (btype 2) code tables
@@ -713,6 +1020,11 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                     ev_a = bad == 3 ? END_TRUNC : END_ERR;
                 } else {
                     in_block = true;
+                    if (par_allowed && store) {
+                        try_par = true;
+                        par_pos = __shfl_sync(FULL, br.bitpos(), 0);
+                        par_chunk = PAR_CHUNK_START_BITS;
+                    }
                 }
             }
 
