@@ -404,22 +404,28 @@ __device__ int build_table(const uint8_t *lens, int n, uint16_t *count, uint16_t
         const int s = s0 + lane;
         const uint32_t l = s < n ? lens[s] : 0;
         const unsigned same = __match_any_sync(FULL, l);
+        uint32_t rev = 0, e = 0;
+        bool fill = false;
         if (l) {
             const uint32_t rank = base[l] + __popc(same & ((1u << lane) - 1u));
             sorted[rank] = (uint16_t)s;
             if ((int)l <= fast_bits) {
-                uint32_t fc = 0, fi = 0;
-#pragma unroll
-                for (int k = 1; k <= 15; ++k)
-                    if (k == (int)l) {
-                        fc = first_code[k];
-                        fi = first_idx[k];
-                    }
-                const uint32_t cw = fc + (rank - fi);           // canonical code, MSB first
-                const uint32_t rev = __brev(cw) >> (32 - l);    // as it appears in the LSB-first bit stream
-                const uint16_t e = (uint16_t)((s << 4) | l);
-                for (uint32_t i = rev; i < (1u << fast_bits); i += (1u << l)) fast[i] = e;
+                const uint32_t cw = fcode[l] + (rank - fidx[l]);  // canonical code, MSB first
+                rev = __brev(cw) >> (32 - l);                      // as it appears in the LSB-first bit stream
+                e = ((uint32_t)s << 4) | l;
+                fill = true;
             }
+        }
+        // codes that own >= 32 table entries are filled by the whole warp, the others by their lane
+        const int wide = fast_bits - 5;
+        unsigned widemask = __ballot_sync(FULL, fill && (int)l <= wide);
+        if (fill && (int)l > wide)
+            for (uint32_t i = rev; i < (1u << fast_bits); i += (1u << l)) fast[i] = (uint16_t)e;
+        while (widemask) {
+            const int src = __ffs(widemask) - 1;
+            widemask &= widemask - 1;
+            const uint32_t r2 = __shfl_sync(FULL, rev, src), l2 = __shfl_sync(FULL, l, src), e2 = __shfl_sync(FULL, e, src);
+            for (uint32_t i = r2 + ((uint32_t)lane << l2); i < (1u << fast_bits); i += (32u << l2)) fast[i] = (uint16_t)e2;
         }
         __syncwarp();
         if (l && __ffs(same) - 1 == lane) base[l] += (uint16_t)__popc(same);  // one leader per length class
@@ -614,10 +620,19 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                                     bad = true;
                                     break;
                                 }
-                                for (uint32_t kk = lane; kk < mlen; kk += 32) {
-                                    const int64_t sp = pos - dist + (kk % dist);
-                                    const int64_t si = sp - stage0;
-                                    ws.stage[o + kk] = si >= (int64_t)vstart ? ws.stage[si] : __ldcg(dst + sp);
+                                if (dist <= o - vstart) {  // the usual case: source inside the stage
+                                    const uint8_t *srcb = ws.stage + (o - dist);
+                                    if (dist >= mlen) {
+                                        for (uint32_t kk = lane; kk < mlen; kk += 32) ws.stage[o + kk] = srcb[kk];
+                                    } else {
+                                        for (uint32_t kk = lane; kk < mlen; kk += 32) ws.stage[o + kk] = srcb[kk % dist];
+                                    }
+                                } else {
+                                    for (uint32_t kk = lane; kk < mlen; kk += 32) {
+                                        const int64_t sp = pos - dist + (kk % dist);
+                                        const int64_t si = sp - stage0;
+                                        ws.stage[o + kk] = si >= (int64_t)vstart ? ws.stage[si] : __ldcg(dst + sp);
+                                    }
                                 }
                                 __syncwarp();
                             }
