@@ -49,7 +49,7 @@ struct __align__(128) DefWarpSmem {
     uint32_t clhist[32];
     uint16_t clcode[20];
     uint8_t cllen[20];
-    uint16_t bl_count[16];
+    alignas(4) uint16_t bl_count[16];
     unsigned long long bar;
 };
 
@@ -70,34 +70,6 @@ __device__ __forceinline__ void len_code(uint32_t m, uint32_t &sym, uint32_t &xb
         xbits = 2;
         xval = (m - 19) & 3u;
     }
-}
-
-// canonical codes (RFC 1951 3.2.2), bit-reversed for LSB-first packing; lane 0 does the serial part
-__device__ void canonical_codes(const uint8_t *len, int n, uint16_t *code, uint16_t *bl_count, int lane) {
-    if (lane == 0) {
-        for (int b = 0; b <= 15; ++b) bl_count[b] = 0;
-        for (int s = 0; s < n; ++s) bl_count[len[s]]++;
-        bl_count[0] = 0;
-        uint32_t next[16];
-        uint32_t c = 0;
-        next[0] = 0;
-        for (int b = 1; b <= 15; ++b) {
-            c = (c + bl_count[b - 1]) << 1;
-            next[b] = c;
-        }
-        for (int s = 0; s < n; ++s) {
-            const uint32_t l = len[s];
-            uint32_t cw = 0;
-            if (l) {
-#pragma unroll
-                for (int b = 1; b <= 15; ++b)
-                    if (b == (int)l) cw = next[b]++;
-                cw = __brev(cw) >> (32 - l);
-            }
-            code[s] = (uint16_t)cw;
-        }
-    }
-    __syncwarp();
 }
 
 // Adler-32 over n staged bytes (whole warp)
@@ -203,7 +175,6 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
         uint32_t ad_a = 1, ad_b = 0;
 
         uint32_t b0 = 0;
-        bool first = true;
         do {  // at least one block, so an empty record still gets a (final) block
             uint32_t b1 = ilen;
             if (split > b0) b1 = split;
@@ -262,47 +233,109 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
             int ncl = 0;
             if (lane < 19) ws.clhist[lane] = 0;
             __syncwarp();
-            if (lane == 0) {
+            {
+                // run-length coding of the hlit + hdist code lengths (RFC 1951 3.2.7), whole warp: find the runs of
+                // equal lengths, turn every run into its symbols (16: repeat previous 3-6, 17: zeros 3-10,
+                // 18: zeros 11-138, greedy like zlib's send_tree), place them with a prefix scan over the runs
                 const int total = hlit + hdist;
-                int i = 0;
                 auto length_at = [&](int k) -> uint32_t { return k < hlit ? ws.len[k] : dist_len; };
-                while (i < total) {
-                    const uint32_t v = length_at(i);
-                    int run = 1;
-                    while (i + run < total && length_at(i + run) == v) ++run;
-                    int left = run;
-                    if (v == 0) {
-                        while (left >= 11) {
-                            const int n = min(left, 138);
-                            ws.clsym[ncl] = 18;
-                            ws.clext[ncl++] = (uint8_t)(n - 11);
-                            left -= n;
-                        }
-                        if (left >= 3) {
-                            ws.clsym[ncl] = 17;
-                            ws.clext[ncl++] = (uint8_t)(left - 3);
-                            left = 0;
-                        }
-                    } else {
-                        ws.clsym[ncl] = (uint8_t)v;  // the value itself first, repeats refer back to it
-                        ws.clext[ncl++] = 0;
-                        --left;
-                        while (left >= 3) {
-                            const int n = min(left, 6);
-                            ws.clsym[ncl] = 16;
-                            ws.clext[ncl++] = (uint8_t)(n - 3);
-                            left -= n;
-                        }
-                    }
-                    while (left-- > 0) {
-                        ws.clsym[ncl] = (uint8_t)v;
-                        ws.clext[ncl++] = 0;
-                    }
-                    i += run;
+                uint16_t *run_start = ws.parent;  // scratch: free once the code lengths exist
+                int nruns = 0;
+                for (int k0 = 0; k0 < total; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool st = k < total && (k == 0 || length_at(k) != length_at(k - 1));
+                    const uint32_t m = __ballot_sync(FULL, st);
+                    if (st) run_start[nruns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+                    nruns += __popc(m);
                 }
-                for (int k = 0; k < ncl; ++k) ws.clhist[ws.clsym[k]]++;
+                __syncwarp();
+                for (int r0 = 0; r0 < nruns; r0 += 32) {
+                    const int r = r0 + lane;
+                    uint32_t v = 0, n18 = 0, n17 = 0, n16 = 0, nlit = 0, tail = 0;
+                    // n18 / n16: full-size repeat symbols; tail: size of one more, smaller repeat symbol (0 = none)
+                    if (r < nruns) {
+                        const int s0 = run_start[r];
+                        const int s1 = r + 1 < nruns ? run_start[r + 1] : total;
+                        uint32_t left = (uint32_t)(s1 - s0);
+                        v = length_at(s0);
+                        if (v == 0) {
+                            n18 = left / 138u;
+                            left -= n18 * 138u;
+                            if (left >= 11) {
+                                tail = left;
+                                ++n18;
+                                left = 0;
+                            } else if (left >= 3) {
+                                tail = left;
+                                n17 = 1;
+                                left = 0;
+                            }
+                            nlit = left;
+                        } else {
+                            nlit = 1;  // the value itself first, repeats refer back to it
+                            --left;
+                            n16 = left / 6u;
+                            left -= n16 * 6u;
+                            if (left >= 3) {
+                                tail = left;
+                                ++n16;
+                                left = 0;
+                            }
+                            nlit += left;
+                        }
+                    }
+                    const uint32_t cnt = n18 + n17 + n16 + nlit;
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    int at = ncl + (int)(incl - cnt);
+                    if (r < nruns) {
+                        if (v == 0) {
+                            const uint32_t full18 = tail >= 11 ? n18 - 1 : n18;
+                            for (uint32_t i = 0; i < full18; ++i) {
+                                ws.clsym[at] = 18;
+                                ws.clext[at++] = 138 - 11;
+                            }
+                            if (tail >= 11) {
+                                ws.clsym[at] = 18;
+                                ws.clext[at++] = (uint8_t)(tail - 11);
+                            } else if (tail >= 3) {
+                                ws.clsym[at] = 17;
+                                ws.clext[at++] = (uint8_t)(tail - 3);
+                            }
+                            if (n18) atomicAdd(&ws.clhist[18], n18);
+                            if (n17) atomicAdd(&ws.clhist[17], n17);
+                            for (uint32_t i = 0; i < nlit; ++i) {
+                                ws.clsym[at] = 0;
+                                ws.clext[at++] = 0;
+                            }
+                            if (nlit) atomicAdd(&ws.clhist[0], nlit);
+                        } else {
+                            ws.clsym[at] = (uint8_t)v;
+                            ws.clext[at++] = 0;
+                            const uint32_t full16 = tail ? n16 - 1 : n16;
+                            for (uint32_t i = 0; i < full16; ++i) {
+                                ws.clsym[at] = 16;
+                                ws.clext[at++] = 6 - 3;
+                            }
+                            if (tail) {
+                                ws.clsym[at] = 16;
+                                ws.clext[at++] = (uint8_t)(tail - 3);
+                            }
+                            if (n16) atomicAdd(&ws.clhist[16], n16);
+                            for (uint32_t i = 1; i < nlit; ++i) {
+                                ws.clsym[at] = (uint8_t)v;
+                                ws.clext[at++] = 0;
+                            }
+                            atomicAdd(&ws.clhist[v], nlit);
+                        }
+                    }
+                    ncl += (int)__shfl_sync(FULL, incl, 31);
+                }
             }
-            ncl = __shfl_sync(FULL, ncl, 0);
             __syncwarp();
             huffman_lengths(ws.clhist, 19, 7, ws.cllen, ws.sortbuf, ws.weight, ws.parent, ws.bl_count, lane);
             canonical_codes(ws.cllen, 19, ws.clcode, ws.bl_count, lane);
@@ -417,10 +450,8 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
                 bo.bitpos += ws.len[256];
             }
             b0 = b1;
-            first = false;
             __syncwarp();
         } while (b0 < ilen);
-        (void)first;
         // ---- Adler-32 trailer, big endian, byte aligned
         bo.bitpos = (bo.bitpos + 7) & ~7u;
         if ((bo.bitpos >> 3) + 8 > DEF_OUT) bo.flush(lane, false);

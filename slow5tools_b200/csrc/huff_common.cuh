@@ -32,9 +32,11 @@ __device__ inline void warp_sort(uint32_t *a, int n, int lane) {
 // ---- Huffman code lengths for `n` symbols with frequencies hist[] (0 = unused), limited to `limit` bits.
 // Writes len[0..n).  Guarantees at least two coded symbols (like zlib's build_tree) so the code is complete.
 // sortbuf: >= 512 entries (>= 32 for n <= 32), weight/parent: >= 2*n entries.  Whole warp calls it.
+// Parallel parts: compaction of the used symbols, bitonic sort of just those, leaf depths (every lane walks its
+// leaves up to the root), Kraft sum, length hand-out; lane 0 runs the two-queue merge and, only when a depth
+// exceeds the limit, the repair loop.
 __device__ inline void huffman_lengths(uint32_t *hist, int n, int limit, uint8_t *len, uint32_t *sortbuf, uint32_t *weight,
                                 uint16_t *parent, uint16_t *bl_count, int lane) {
-    const int npad = n <= 32 ? 32 : 512;
     // zlib forces two codes of non-zero frequency; mimic that so a lone symbol still gets a 1-bit code
     int used = 0;
     for (int s = lane; s < n; s += 32) used += hist[s] != 0;
@@ -49,10 +51,20 @@ __device__ inline void huffman_lengths(uint32_t *hist, int n, int limit, uint8_t
     }
     used = max(used, 2);
     __syncwarp();
-    for (int s = lane; s < npad; s += 32) {
-        const uint32_t f = s < n ? hist[s] : 0;
-        sortbuf[s] = f ? (min(f, 0x7fffffu) << 9) | (uint32_t)s : 0xffffffffu;
-        if (s < n) len[s] = 0;
+    // compact (frequency, symbol) keys of the used symbols, pad to a power of two, sort ascending
+    int npad = 32;
+    while (npad < used) npad <<= 1;
+    {
+        int base = 0;
+        for (int s0 = 0; s0 < n; s0 += 32) {
+            const int s = s0 + lane;
+            const uint32_t f = s < n ? hist[s] : 0;
+            if (s < n) len[s] = 0;
+            const uint32_t m = __ballot_sync(FULL, f != 0);
+            if (f) sortbuf[base + __popc(m & ((1u << lane) - 1u))] = (min(f, 0x7fffffu) << 9) | (uint32_t)s;
+            base += __popc(m);
+        }
+        for (int i = used + lane; i < npad; i += 32) sortbuf[i] = 0xffffffffu;
     }
     __syncwarp();
     warp_sort(sortbuf, npad, lane);
@@ -73,26 +85,37 @@ __device__ inline void huffman_lengths(uint32_t *hist, int n, int limit, uint8_t
             parent[pick[1]] = (uint16_t)next;
             ++next;
         }
-        // depths: a child always has a smaller index than its parent.  weight[] is reused for the depth.
-        const int root = next - 1;
-        weight[root] = 0;
-        for (int v = root - 1; v >= 0; --v) weight[v] = weight[parent[v]] + 1;
-        // length limiting: clamp the depths to `limit`, measure by how much the Kraft sum now exceeds 1 (in units
-        // of 2^-limit), and repair it one unit at a time the way zlib's gen_bitlen does: push a leaf from the
-        // deepest level above the limit one level down and hang one clamped leaf next to it.
-        for (int b = 0; b <= 15; ++b) bl_count[b] = 0;
-        bool clamped = false;
-        uint32_t kraft = 0;
-        for (int i = 0; i < used; ++i) {
-            int dpt = (int)weight[i];
-            if (dpt > limit) {
-                dpt = limit;
-                clamped = true;
-            }
-            bl_count[dpt]++;
-            kraft += 1u << (limit - dpt);
+    }
+    __syncwarp();
+    // leaf depths: walk up to the root (node 2*used-2); clamp to the limit and sum the Kraft terms in 2^-limit units
+    const int root = 2 * used - 2;
+    if (lane < 16) bl_count[lane] = 0;
+    __syncwarp();
+    uint32_t kraft = 0;
+    int over = 0;
+    for (int i = lane; i < used; i += 32) {
+        int d = 0;
+        for (int v = i; v != root; v = parent[v]) ++d;
+        if (d > limit) {
+            d = limit;
+            over = 1;
         }
-        if (clamped) {
+        kraft += 1u << (limit - d);
+        weight[i] = (uint32_t)d;  // (the leaf weights are no longer needed)
+        atomicAdd(reinterpret_cast<unsigned int *>(bl_count) + (d >> 1), (d & 1) ? 0x10000u : 1u);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        kraft += __shfl_xor_sync(FULL, kraft, d);
+        over |= __shfl_xor_sync(FULL, over, d);
+    }
+    __syncwarp();
+    if (over) {
+        // length limiting: the clamped depths over-subscribe the code by `excess` units of 2^-limit; repair it one
+        // unit at a time the way zlib's gen_bitlen does (push a leaf from the deepest level above the limit one
+        // level down and hang one clamped leaf next to it), then hand the lengths out again: longest codes to the
+        // rarest symbols (leaves are sorted by weight)
+        if (lane == 0) {
             int excess = (int)kraft - (1 << limit);
             while (excess > 0) {
                 int bits = limit - 1;
@@ -102,12 +125,58 @@ __device__ inline void huffman_lengths(uint32_t *hist, int n, int limit, uint8_t
                 bl_count[limit]--;
                 --excess;
             }
-            // hand the lengths out again: longest codes to the rarest symbols (leaves are sorted by weight)
             int i = 0;
             for (int bits = limit; bits >= 1; --bits)
                 for (int c = bl_count[bits]; c > 0; --c) weight[i++] = (uint32_t)bits;
         }
-        for (int i = 0; i < used; ++i) len[sortbuf[i] & 511u] = (uint8_t)weight[i];
+        __syncwarp();
+    }
+    for (int i = lane; i < used; i += 32) len[sortbuf[i] & 511u] = (uint8_t)weight[i];
+    __syncwarp();
+}
+
+// canonical codes (RFC 1951 3.2.2) for len[0..n), n <= 288, lengths <= 15; bit-reversed for LSB-first packing when
+// `reversed`.  bl_count is a 16-entry scratch.  Whole warp: per-length counts by shared-memory atomics, the
+// first code of every length in registers, then 32 symbols per round ranked inside their length class with
+// __match_any_sync (symbols of one length get consecutive codes in symbol order).
+__device__ inline void canonical_codes(const uint8_t *len, int n, uint16_t *code, uint16_t *bl_count, int lane,
+                                       bool reversed = true) {
+    if (lane < 16) bl_count[lane] = 0;
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) {
+        const uint32_t l = len[s];
+        if (l) atomicAdd(reinterpret_cast<unsigned int *>(bl_count) + (l >> 1), (l & 1) ? 0x10000u : 1u);
+    }
+    __syncwarp();
+    // lane b (1..15) keeps the next code of length b
+    uint32_t next = 0;
+    {
+        uint32_t c = 0;
+#pragma unroll
+        for (int b = 1; b <= 15; ++b) {
+            c = (c + (b > 1 ? bl_count[b - 1] : 0)) << 1;
+            if (lane == b) next = c;
+        }
+    }
+    for (int s0 = 0; s0 < n; s0 += 32) {
+        const int s = s0 + lane;
+        const uint32_t l = s < n ? len[s] : 0;
+        const unsigned same = __match_any_sync(FULL, l);
+        const uint32_t base = __shfl_sync(FULL, next, (int)l & 15);  // l == 0 reads lane 0's unused value
+        if (s < n) {
+            uint32_t cw = 0;
+            if (l) {
+                cw = base + __popc(same & ((1u << lane) - 1u));
+                if (reversed) cw = __brev(cw) >> (32 - l);
+            }
+            code[s] = (uint16_t)cw;
+        }
+        // the lane that owns length b advances its counter by the number of symbols of that length in this round
+#pragma unroll
+        for (int b = 1; b <= 15; ++b) {
+            const unsigned mb = __ballot_sync(FULL, l == (uint32_t)b);
+            if (lane == b) next += __popc(mb);
+        }
     }
     __syncwarp();
 }

@@ -46,7 +46,7 @@ struct __align__(128) ZeWarpSmem {
     uint8_t prev_len[256];
     uint8_t weights[256];
     uint8_t tree[HUF_TREE_MAX_BYTES];
-    uint16_t bl_count[16];
+    alignas(4) uint16_t bl_count[16];
     WeightEnc we;
     unsigned long long bar;
 };
