@@ -34,13 +34,21 @@ constexpr int DEF_OUT = HC_OUT;
 constexpr int DEF_OUT_SLACK = HC_OUT_SLACK;
 constexpr uint32_t ADLER_MOD = 65521u;
 
-struct __align__(128) DefWarpSmem {
-    uint8_t in[16 + DEF_BLOCK + 16];  // block staged from the 16-byte granule below its first byte
-    uint32_t out[(DEF_OUT + DEF_OUT_SLACK) / 4];
-    uint32_t hist[288];
+struct DefTreeScratch {  // live only while a block's codes are being constructed
     uint32_t sortbuf[512];
     uint32_t weight[576];
     uint16_t parent[576];
+};
+struct __align__(128) DefWarpSmem {
+    // The staged block and the code-construction scratch share their bytes: the block is staged, counted,
+    // overwritten by the scratch, and staged again (from L2 this time) for the emit pass.  Halves the shared
+    // memory per warp, i.e. doubles the resident warps of this latency-bound kernel.
+    union {
+        uint8_t in[16 + DEF_BLOCK + 16];  // block staged from the 16-byte granule below its first byte
+        DefTreeScratch k;
+    };
+    uint32_t out[(DEF_OUT + DEF_OUT_SLACK) / 4];
+    uint32_t hist[288];
     uint16_t code[288];  // bit-reversed canonical codes (LSB-first ready)
     uint8_t len[288];
     uint8_t dlen[32];
@@ -188,14 +196,18 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
             uint64_t bytes = ((uint64_t)skew + blen + (b0 ? 1 : 0) + 15) & ~15ull;
             const uint64_t room = a.in_capacity - (uint64_t)(g16 - a.in);
             if (bytes > room) bytes = room & ~15ull;
-            if (bytes) {
+            auto stage_block = [&]() {
+                if (!bytes) return;
+                fence_proxy_async_smem();  // every lane's earlier generic accesses to these bytes come first
+                __syncwarp();
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, (uint32_t)bytes);
                     bulk_g2s(smem_u32(ws.in), g16, (uint32_t)bytes, bar);
                 }
                 mbar_wait(bar, phase);
                 phase ^= 1u;
-            }
+            };
+            stage_block();
             const uint8_t *blk = ws.in + skew + (b0 ? 1 : 0);  // blk[0] = first byte of the block, blk[-1] valid if b0 > 0
             const bool have_prev = b0 > 0;
             adler_update(ad_a, ad_b, blk, blen, lane);
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
             __syncwarp();
 
             // ---- code construction
-            huffman_lengths(ws.hist, 286, 15, ws.len, ws.sortbuf, ws.weight, ws.parent, ws.bl_count, lane);
+            huffman_lengths(ws.hist, 286, 15, ws.len, ws.k.sortbuf, ws.k.weight, ws.k.parent, ws.bl_count, lane);
             canonical_codes(ws.len, 286, ws.code, ws.bl_count, lane);
             // distance alphabet: only distance 1 (code 0) is ever used.  One code of one bit when there are
             // matches, one code of zero bits when the block is all literals (RFC 1951 3.2.7).
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
                 // 18: zeros 11-138, greedy like zlib's send_tree), place them with a prefix scan over the runs
                 const int total = hlit + hdist;
                 auto length_at = [&](int k) -> uint32_t { return k < hlit ? ws.len[k] : dist_len; };
-                uint16_t *run_start = ws.parent;  // scratch: free once the code lengths exist
+                uint16_t *run_start = ws.k.parent;  // scratch: free once the code lengths exist
                 int nruns = 0;
                 for (int k0 = 0; k0 < total; k0 += 32) {
                     const int k = k0 + lane;
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
                 }
             }
             __syncwarp();
-            huffman_lengths(ws.clhist, 19, 7, ws.cllen, ws.sortbuf, ws.weight, ws.parent, ws.bl_count, lane);
+            huffman_lengths(ws.clhist, 19, 7, ws.cllen, ws.k.sortbuf, ws.k.weight, ws.k.parent, ws.bl_count, lane);
             canonical_codes(ws.cllen, 19, ws.clcode, ws.bl_count, lane);
             const uint8_t *order = c_def_cl_order;
             int hclen = 19;
@@ -362,6 +374,7 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
             for (int d = 16; d; d >>= 1) dyn_bits += __shfl_xor_sync(FULL, dyn_bits, d);
             dyn_bits += 3 + 5 + 5 + 4 + 3 * hclen;
             const uint32_t stored_bits = 8u * blen + 40u;
+            stage_block();  // the construction scratch overwrote the block
 
             if (dyn_bits >= stored_bits + 7u) {
                 // ---- stored block: pad to a byte boundary, LEN, NLEN, raw bytes

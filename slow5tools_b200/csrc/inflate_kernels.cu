@@ -29,15 +29,16 @@ namespace s5b {
 namespace {
 
 constexpr int INF_WARPS = 4;
-constexpr int INF_BLK = 1024;  // input ring block
+constexpr int INF_BLK = 512;   // input ring block (the ring only feeds the serial decoder: headers and tails)
 constexpr int INF_NB = 2;
 constexpr int INF_RING = INF_BLK * INF_NB;
-constexpr int INF_STAGE = 8192;  // output staging bytes (a multiple of 16)
-constexpr int PAR_CHUNK_MAX_BITS = 1024;  // window decode: at most this many compressed bits per lane and window
+constexpr int INF_STAGE = 4096;  // output staging bytes (a multiple of 16)
+constexpr int PAR_CHUNK_MAX_BITS = 384;   // window decode: at most this many compressed bits per lane and window
+                                          // (1.5 KiB of input, whose output should fit the free part of the stage)
 constexpr int PAR_CHUNK_MIN_BITS = 64;
 constexpr int PAR_CHUNK_START_BITS = 128; // first window of a block (its end is unknown: bits past the end-of-block
-                                          // symbol are decoded for nothing), x4 for every further window
-constexpr int PAR_LIST = 256;             // queued matches per window
+                                          // symbol are decoded for nothing), x3 for every further window
+constexpr int PAR_LIST = 128;             // queued matches per window
 constexpr int PAR_MAX_ROUNDS = 8;         // boundary rounds before only the agreed prefix of lanes is committed
 constexpr uint32_t PAR_SYM_BITS = 48;     // longest length/distance pair: 15 + 5 + 15 + 13
 constexpr int LIT_FAST_BITS = 10;
@@ -58,6 +59,7 @@ struct __align__(128) InfWarpSmem {
     uint16_t cl_count[16];
     uint16_t tmp_base[16];
     uint16_t lit_fcode[16], lit_fidx[16];    // canonical first code / first sorted index per length
+    uint16_t lit_lim[16];                     // end of the codes of each length, left-aligned to 15 bits (saturated)
     uint16_t dist_fcode[16], dist_fidx[16];
     uint16_t cl_fcode[16], cl_fidx[16];
     uint8_t lens[384];                        // code lengths: lit/len at 0, dist at 288; scratch from 32
@@ -257,6 +259,9 @@ __device__ __forceinline__ void par_run(const InfWarpSmem &ws, const LenDistTabs
     LaneBits b;
     uint32_t p = start, nby = 0, nm = 0, st = PS_NONE;
     // the last PAR_SYM_BITS of the stream belong to the serial decoder (it owns the truncation verdicts)
+    static_assert(LIT_FAST_BITS == 10, "the long-code path below compares against the limits of lengths 11..15");
+    const uint32_t lim11 = ws.lit_lim[11], lim12 = ws.lit_lim[12], lim13 = ws.lit_lim[13], lim14 = ws.lit_lim[14],
+                   lim15 = ws.lit_lim[15];
     const uint32_t safe = in.end_bits - PAR_SYM_BITS;
     const uint32_t lim2 = min(limit, safe + 1u);
     if (p < lim2) b.seek(in, p);
@@ -267,11 +272,15 @@ __device__ __forceinline__ void par_run(const InfWarpSmem &ws, const LenDistTabs
         uint32_t l = e & 15u;
         int sym = (int)(e >> 4);
         if (l == 0) {
-            sym = slow_walk(b.bb, ws.lit_count, ws.lit_sorted, ws.lit_fcode, ws.lit_fidx, LIT_FAST_BITS, &l);
-            if (sym < 0) {
+            // code longer than the first-level table: canonical codes, left-aligned to 15 bits, ascend with their
+            // length, so four compares against the per-length limits give the length
+            const uint32_t c15 = __brev((uint32_t)b.bb) >> 17;
+            if (c15 >= lim15) {
                 st = PS_INVALID;
                 break;
             }
+            l = 11u + (c15 >= lim11) + (c15 >= lim12) + (c15 >= lim13) + (c15 >= lim14);
+            sym = ws.lit_sorted[ws.lit_fidx[l] + ((c15 >> (15u - l)) - ws.lit_fcode[l])];
         }
         if (sym < 256) {
             if (WRITE) stage[o] = (uint8_t)sym;
@@ -354,7 +363,7 @@ __device__ __forceinline__ int slow_decode(const BitReader &br, const uint16_t *
 // zlib's inflate_table rules: inftrees.c).
 __device__ int build_table(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *fast,
                            int fast_bits, uint16_t *base /*[16] scratch*/, uint16_t *fcode, uint16_t *fidx, int lane,
-                           int *max_len_out) {
+                           int *max_len_out, uint16_t *lim = nullptr) {
     if (lane < 16) count[lane] = 0;
     __syncwarp();
     for (int s = lane; s < n; s += 32) {
@@ -396,6 +405,7 @@ __device__ int build_table(const uint8_t *lens, int n, uint16_t *count, uint16_t
         base[lane] = (uint16_t)v;
         fidx[lane] = (uint16_t)v;
         fcode[lane] = (uint16_t)fc;
+        if (lim) lim[lane] = lane ? (uint16_t)min(0xffffu, (fc + count[lane]) << (15 - lane)) : (uint16_t)0;
     }
     for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
     __syncwarp();
@@ -557,7 +567,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                 const uint32_t rem = pin.end_bits - P0;
                 if (rem >= 2u * PAR_SYM_BITS) {
                     const uint32_t W = min(rem, 32u * par_chunk);
-                    par_chunk = min(par_chunk * 4u, (uint32_t)PAR_CHUNK_MAX_BITS);
+                    par_chunk = min(par_chunk * 3u, (uint32_t)PAR_CHUNK_MAX_BITS);
                     const uint32_t C = max((uint32_t)PAR_CHUNK_MIN_BITS, (W + 31u) >> 5);
                     const uint32_t We = P0 + W;
                     uint32_t start = min(P0 + (uint32_t)lane * C, We);
@@ -660,7 +670,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                             if (result == PAR_EOB) in_block = false;
                         }
                     }
-                    if (spos > (uint32_t)INF_STAGE / 2) ev = EV_FLUSH;
+                    if (spos > (uint32_t)INF_STAGE / 4) ev = EV_FLUSH;  // keep room for the next window's output
                 }
                 __syncwarp();
             } else {
@@ -1020,7 +1030,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
                 }
                 if (!bad) {
                     int maxl = 0;
-                    int st = build_table(ws.lens, hlit, ws.lit_count, ws.lit_sorted, ws.lit_fast, LIT_FAST_BITS, ws.tmp_base, ws.lit_fcode, ws.lit_fidx, lane, &maxl);
+                    int st = build_table(ws.lens, hlit, ws.lit_count, ws.lit_sorted, ws.lit_fast, LIT_FAST_BITS, ws.tmp_base, ws.lit_fcode, ws.lit_fidx, lane, &maxl, ws.lit_lim);
                     // inftrees.c: over-subscribed never; incomplete only for a single 1-bit code
                     if (st == 1 || (st == 2 && maxl != 1)) bad = 2;  // "invalid literal/lengths set"
                     __syncwarp();
