@@ -280,6 +280,32 @@ def run_ours(args):
               "full_decode_reads_per_s": R / ((dec_ms_max + inf_ms) * 1e-3),
               "note": "zlib stage run on the svb-zd streams of the same batch (a BLOW5 record minus ~70 B of fixed fields); "
                       "latency/issue bound kernels, HBM fraction reported for completeness"}
+        # the same stage with the zstd record codec (BASELINE config[4]'s inner codec): frame encode of every svb-zd
+        # stream, frame decode of the result, svb-zd decode must give back the signal
+        cdc.zstd_encode_dev(svb, ooff, svb_len, zbuf, zoff, zlen, zst, split=split)
+        cdc.zstd_decode_dev(zbuf, zoff, zlen, svb2, ooff, svb2_len, ist)
+        barrier()
+        sev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KZ)]
+        for k in range(KZ):
+            sev[k][0].record()
+            cdc.zstd_encode_dev(svb, ooff, svb_len, zbuf, zoff, zlen, zst, split=split)
+            sev[k][1].record()
+            cdc.zstd_decode_dev(zbuf, zoff, zlen, svb2, ooff, svb2_len, ist)
+            sev[k][2].record()
+        barrier()
+        zse_ms = sum(e[0].elapsed_time(e[1]) for e in sev) / KZ
+        zsd_ms = sum(e[1].elapsed_time(e[2]) for e in sev) / KZ
+        assert int(zst.abs().sum()) == 0 and int(ist.abs().sum()) == 0 and torch.equal(svb2_len, svb_len), "zstd stage failed"
+        cdc.svbzd_decode_dev(svb2, ooff, svb2_len, back, soff, n2, st_d)
+        torch.cuda.synchronize()
+        assert int(st_d.abs().sum()) == 0 and torch.equal(back, sig), "zstd round trip failed"
+        zsbytes = int(zlen.sum())
+        zse_ms, zsd_ms = max_over_ranks([zse_ms, zsd_ms])
+        zx["zstd"] = {"encode_ms": zse_ms, "decode_ms": zsd_ms, "zstd_bytes_per_read": zsbytes / R,
+                      "zstd_ratio_on_svb_stream": zsbytes / svb_bytes,
+                      "encode_reads_per_s": R / (zse_ms * 1e-3), "decode_reads_per_s": R / (zsd_ms * 1e-3),
+                      "full_encode_reads_per_s": R / ((enc_ms_max + zse_ms) * 1e-3),
+                      "full_decode_reads_per_s": R / ((dec_ms_max + zsd_ms) * 1e-3)}
         del zbuf, svb2
 
     if args.profile:

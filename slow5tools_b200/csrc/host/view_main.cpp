@@ -36,12 +36,7 @@ using namespace s5b;
 
 namespace {
 
-int g_verbose = 3;
 #define ERROR(fmt, ...) fprintf(stderr, "[%s::ERROR]\033[1;31m " fmt "\033[0m\n", __func__, __VA_ARGS__)
-#define INFO(fmt, ...)                                                         \
-    do {                                                                       \
-        if (g_verbose >= 3) fprintf(stderr, "[%s::INFO] " fmt "\n", __func__, __VA_ARGS__); \
-    } while (0)
 
 void parallel_for(size_t n, int threads, const std::function<void(size_t)> &fn) {
     if (threads <= 1 || n < 64) {

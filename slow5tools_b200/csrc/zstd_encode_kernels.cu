@@ -33,13 +33,20 @@ using namespace s5bz;
 constexpr int ZE_WARPS = 4;
 constexpr int ZE_BLOCK = 6144;  // max input bytes per block (multiple of 32)
 
-struct __align__(128) ZeWarpSmem {
-    uint8_t in[16 + ZE_BLOCK + 16];
-    uint32_t out[(HC_OUT + HC_OUT_SLACK) / 4];
-    uint32_t hist[256];
+struct ZeTreeScratch {  // live only while a block's code is being constructed
     uint32_t sortbuf[512];
     uint32_t weight[512];
     uint16_t parent[512];
+};
+struct __align__(128) ZeWarpSmem {
+    // the staged block and the construction scratch share their bytes (the block is staged again, from L2, once
+    // the code exists): fewer bytes per warp, more resident warps
+    union {
+        uint8_t in[16 + ZE_BLOCK + 16];
+        ZeTreeScratch k;
+    };
+    uint32_t out[(HC_OUT + HC_OUT_SLACK) / 4];
+    uint32_t hist[256];
     uint16_t code[256];
     uint16_t prev_code[256];
     uint8_t len[256];
@@ -142,14 +149,18 @@ __global__ void __launch_bounds__(ZE_WARPS * 32) zstd_encode_kernel(const Deflat
             uint64_t bytes = ((uint64_t)skew + n + 15) & ~15ull;
             const uint64_t room = a.in_capacity - (uint64_t)(g16 - a.in);
             if (bytes > room) bytes = room & ~15ull;
-            if (bytes && n) {
+            auto stage_block = [&]() {
+                if (!bytes || !n) return;
+                fence_proxy_async_smem();  // every lane's earlier generic accesses to these bytes come first
+                __syncwarp();
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, (uint32_t)bytes);
                     bulk_g2s(smem_u32(ws.in), g16, (uint32_t)bytes, bar);
                 }
                 mbar_wait(bar, phase);
                 phase ^= 1u;
-            }
+            };
+            stage_block();
             const uint8_t *blk = ws.in + skew;
 
             // ---- pass 1: byte histogram (one atomic per distinct value in a strip)
@@ -189,7 +200,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32) zstd_encode_kernel(const Deflat
                     miss = warp_sum(miss);
                     if (!miss) cost_prev = c;
                 }
-                huffman_lengths(ws.hist, 256, HUF_MAX_BITS, ws.len, ws.sortbuf, ws.weight, ws.parent, ws.bl_count, lane);
+                huffman_lengths(ws.hist, 256, HUF_MAX_BITS, ws.len, ws.k.sortbuf, ws.k.weight, ws.k.parent, ws.bl_count, lane);
                 int tb = 0;
                 if (lane == 0) {
                     int nsym = 0;
@@ -197,7 +208,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32) zstd_encode_kernel(const Deflat
                     if (mb) tb = huf_write_tree(ws.we, ws.weights, nsym, ws.tree);
                 }
                 tb = __shfl_sync(FULL, tb, 0);
-                __syncwarp();
+                stage_block();  // the construction scratch overwrote the block
                 uint32_t cost_new = 0;
                 for (int s = lane; s < 256; s += 32) cost_new += ws.hist[s] * ws.len[s];
                 cost_new = warp_sum(cost_new);

@@ -39,7 +39,123 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, uint64_t offset, u
     }
 }
 
-// warp version of s5bz::decode_literals: tree by lane 0, the four streams by lanes 0..3
+// ---- window decode of the four Huffman literal streams (all 32 lanes, 8 per stream) ------------------------
+// A zstd Huffman stream is read from its last bit towards its first: with x = number of unread bits, the next
+// symbol is huf[bits [x - mb, x)] (bits below the stream start read as zero) and x drops by that symbol's length;
+// a valid stream ends at exactly x == 0 after `regen` symbols (huf_decode_stream in zstd_core.h).  Each stream is
+// cut into 8 chunks of x; a lane decodes the symbols that start inside its chunk, first speculatively from the
+// chunk's top bit -- Huffman codes self-synchronise, so the run soon falls onto true symbol boundaries -- and again
+// from its upper neighbour's end position until all boundaries agree (usually one extra round); an 8-lane prefix
+// scan over the symbol counts then places every lane's output and a last pass writes it.
+struct HufLane {
+    const uint32_t *w4;  // 4-byte aligned address at or below the stream's first byte (shared or global memory)
+    uint32_t delta;      // grid bit position of stream bit 0 (0, 8, 16 or 24)
+    uint64_t acc;        // unread bits, left-aligned
+    int cnt;             // valid bits in acc
+    int j;               // next (lower) grid word to load
+    __device__ __forceinline__ uint32_t word(int k) const {
+        if (k < 0) return 0u;
+        uint32_t w = w4[k];
+        if (k == 0) w &= ~((1u << delta) - 1u);  // bytes below the stream start are not part of it
+        return w;
+    }
+    // position the reader so that stream bit x - 1 is the next bit (x >= 1)
+    __device__ __forceinline__ void seek(int x) {
+        const int g = x + (int)delta;
+        j = (g - 1) >> 5;
+        const int c0 = g - 32 * j;  // 1..32 bits of word j lie below g
+        acc = (uint64_t)word(j) << (64 - c0);
+        cnt = c0;
+        --j;
+        refill();
+    }
+    __device__ __forceinline__ void refill() {
+        if (cnt <= 32) {
+            acc |= (uint64_t)word(j) << (32 - cnt);
+            cnt += 32;
+            --j;
+        }
+    }
+};
+
+// Symbols that start at x in (limit, start]; returns the end position (<= limit, may be negative for a damaged
+// stream) and the symbol count.  WRITE: symbols go to out[0 ..).
+template <bool WRITE>
+__device__ __forceinline__ void huf_run(const uint16_t *huf, const int mb, HufLane &b, const int start, const int limit,
+                                        int &end, uint32_t &count, uint8_t *out) {
+    int x = start;
+    uint32_t n = 0;
+    if (x > limit) b.seek(x);
+    while (x > limit) {
+        b.refill();
+        const uint32_t e = huf[(uint32_t)(b.acc >> (64 - mb))];
+        const int nb = (int)(e & 15u);
+        if (WRITE) out[n] = (uint8_t)(e >> 4);
+        ++n;
+        b.acc <<= nb;
+        b.cnt -= nb;
+        x -= nb;
+    }
+    end = x;
+    count = n;
+}
+
+// Returns Z_OK, or Z_ERR_CORRUPT when the streams do not end exactly at their first bit after exactly the
+// regenerated sizes (the caller then lets the serial decoders give the verdict).
+__device__ int huf_decode_4x_window(const Tables &t, const uint8_t *const sp[4], const uint32_t sl[4], uint8_t *lit,
+                                    const uint32_t q, const uint32_t regen, const int lane) {
+    const int g = lane >> 3, k = lane & 7;  // stream, chunk
+    const uint8_t *src = sp[0];
+    uint32_t len = sl[0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (g == i) {
+            src = sp[i];
+            len = sl[i];
+        }
+    const uint32_t want = g < 3 ? q : regen - 3 * q;
+    bool ok = len != 0 && len < (1u << 24);
+    const uint32_t lastb = ok ? src[len - 1] : 1u;
+    ok = ok && lastb != 0;
+    const int T = ok ? (int)(len * 8 - (8 - (uint32_t)highest_bit(lastb))) : 0;  // data bits below the end mark
+    HufLane b;
+    const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    b.w4 = reinterpret_cast<const uint32_t *>(src - sk);
+    b.delta = sk * 8u;
+    const int mb = t.huf_bits;
+    const int C = max(32, (T + 7) >> 3);
+    int start = max(T - k * C, 0);
+    const int limit = k == 7 ? 0 : max(T - (k + 1) * C, 0);
+    int end;
+    uint32_t cnt;
+    huf_run<false>(t.huf, mb, b, start, limit, end, cnt, nullptr);
+    for (int round = 1; round <= 8; ++round) {
+        const int pe = __shfl_up_sync(FULL, end, 1, 8);
+        const bool need = k > 0 && pe != start;
+        if (!__any_sync(FULL, need)) break;
+        if (need) {
+            start = pe;
+            huf_run<false>(t.huf, mb, b, start, limit, end, cnt, nullptr);
+        }
+    }
+    // agreement, exact end, exact symbol count -- per stream, then for the whole warp
+    const int pe = __shfl_up_sync(FULL, end, 1, 8);
+    bool good = ok && (k == 0 || pe == start) && (k < 7 || end == 0);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, d, 8);
+        if (k >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 7, 8);
+    good = good && total == want;
+    if (!__all_sync(FULL, good)) return Z_ERR_CORRUPT;
+    huf_run<true>(t.huf, mb, b, start, limit, end, cnt, lit + (uint32_t)g * q + (incl - cnt));
+    __syncwarp();
+    return Z_OK;
+}
+
+// warp version of s5bz::decode_literals: tree by lane 0, the four streams by the window decoder
 __device__ int decode_literals_warp(Tables &t, const uint8_t *src, uint32_t len, uint8_t *lit, uint32_t lit_cap,
                                     const uint8_t **lit_ptr, uint32_t *lit_len, int lane) {
     if (len < 1) return Z_ERR_CORRUPT;
@@ -120,10 +236,15 @@ __device__ int decode_literals_warp(Tables &t, const uint8_t *src, uint32_t len,
         const uint32_t q = (regen + 3) / 4;
         if (3ull * q > regen) return Z_ERR_CORRUPT;
         const uint8_t *b = p + 6;
-        if (lane == 0) rc = huf_decode_stream(t, b, s1, lit, q);
-        else if (lane == 1) rc = huf_decode_stream(t, b + s1, s2, lit + q, q);
-        else if (lane == 2) rc = huf_decode_stream(t, b + s1 + s2, s3, lit + 2 * q, q);
-        else if (lane == 3) rc = huf_decode_stream(t, b + s1 + s2 + s3, s4, lit + 3 * q, regen - 3 * q);
+        const uint8_t *const sp[4] = {b, b + s1, b + s1 + s2, b + s1 + s2 + s3};
+        const uint32_t sl[4] = {s1, s2, s3, s4};
+        if (huf_decode_4x_window(t, sp, sl, lit, q, regen, lane) != Z_OK) {
+            // damaged (or pathological) streams: the serial decoders own the verdict
+            if (lane == 0) rc = huf_decode_stream(t, b, s1, lit, q);
+            else if (lane == 1) rc = huf_decode_stream(t, b + s1, s2, lit + q, q);
+            else if (lane == 2) rc = huf_decode_stream(t, b + s1 + s2, s3, lit + 2 * q, q);
+            else if (lane == 3) rc = huf_decode_stream(t, b + s1 + s2 + s3, s4, lit + 3 * q, regen - 3 * q);
+        }
     }
     // any lane's failure fails the block
     rc = __any_sync(FULL, rc != Z_OK) ? Z_ERR_CORRUPT : Z_OK;
