@@ -18,6 +18,7 @@
 //   * decode: the variable-length data stream is staged by bulk async copies into a 4 x 1 KiB
 //     per-warp ring; a warp prefix scan over the control-byte lengths resolves the per-lane data
 //     offsets, a second scan rebuilds the running sum; samples leave as 128-bit coalesced stores.
+#include <cstdlib>
 #include "s5b_kernels.h"
 #include "s5b_ptx.cuh"
 #include "../../include/slow5b200.h"
@@ -60,133 +61,192 @@ __device__ __forceinline__ uint64_t next_work(unsigned long long *counter, int l
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
+// Lane mapping of one 256-sample iteration: lane owns values 4*lane .. 4*lane+3 ("quad A") and
+// 128+4*lane .. 128+4*lane+3 ("quad B").  Neighbouring lanes of one byte-store instruction are then
+// ~4.1 bytes apart (a warp's 32 addresses span ~33 words: no shared-memory bank conflicts), where
+// 8 consecutive values per lane put them ~8.3 bytes apart (66 words, 2 wavefronts per store).
 constexpr int ENC_WARPS = 8;
 constexpr int ENC_CH_SAMPLES = 1024;  // samples per bulk-copy chunk (4 iterations of 256)
 constexpr int ENC_CH_BYTES = ENC_CH_SAMPLES * 2;
 constexpr int ENC_STAGES = 2;
-constexpr int ENC_DBUF = 16 + 3 * ENC_CH_SAMPLES + 16;  // data bytes of one chunk (+ carried partial segment)
+// Data bytes of one chunk between two drains.  Iteration i of a chunk starts with at most 15 + 512*i
+// bytes buffered (an iteration without 3-byte codes appends <= 512; one with them drains right away),
+// and appends at most 768: 15 + 3*512 + 768 = 2319.
+constexpr int ENC_DB = 2320;
 
 struct __align__(128) EncWarpSmem {
     uint8_t in[ENC_STAGES][ENC_CH_BYTES];  // staged signal
-    uint8_t dbuf[ENC_DBUF];                // dbuf[0] <-> 16-byte aligned global address
+    uint8_t dbuf[2][ENC_DB];               // data-stream double buffer; dbuf[x][0] <-> 16-byte aligned global address
     uint8_t kbuf[ENC_CH_SAMPLES / 4];      // key bytes of one chunk, natural index
     unsigned long long bar[ENC_STAGES];
 };
+static_assert(ENC_DB % 16 == 0, "both halves of the double buffer must stay 16-byte aligned");
 
-// Per-warp output state of the data stream (all members warp-uniform).  Data bytes of a chunk are
-// appended linearly to dbuf; complete 16-byte segments leave after every iteration as 128-bit stores;
-// at the end of a chunk the (< 16 byte) remainder moves to the front.
+// Per-warp output state of the data stream (all members warp-uniform).  Data bytes are appended linearly
+// to the current half of the double buffer; a drain sends its complete 16-byte segments to global memory
+// with one bulk shared->global copy (async proxy, no LDS/STG by the lanes) and moves the (< 16 byte)
+// remainder to the front of the other half, which becomes current.
 struct EncData {
-    uint8_t *gbase;  // 16-byte aligned global address of dbuf[0]
-    uint32_t pos;    // bytes appended (index into dbuf)
-    uint32_t fseg;   // 16-byte segments of dbuf already stored
+    uint8_t *gbase;  // 16-byte aligned global address of buf[0]
+    uint8_t *buf;    // current half
+    uint8_t *oth;    // other half
+    uint32_t pos;    // bytes appended (index into buf)
     uint32_t head;   // first valid byte of segment 0 (stream start not 16-byte aligned), else 0
 };
 
-__device__ __forceinline__ void enc_flush_segments(EncData &d, const uint8_t *dbuf, const int lane) {
-    // an iteration appends at most 768 bytes -> at most 49 new complete segments -> two store rounds
-    const uint32_t wseg = d.pos >> 4;
-    if (wseg > d.fseg) {
-        uint32_t seg = d.fseg + lane;
-        if (d.head) {  // ragged stream start: segment 0 leaves as byte stores
-            if (lane >= (int)d.head && lane < 16) d.gbase[lane] = dbuf[lane];
-            d.head = 0;
-            seg += 1;
-        }
-        const uint4 *s = reinterpret_cast<const uint4 *>(dbuf);
-        uint4 *g = reinterpret_cast<uint4 *>(d.gbase);
-        if (seg < wseg) g[seg] = s[seg];
-        if (seg + 32 < wseg) g[seg + 32] = s[seg + 32];
-        d.fseg = wseg;
+__device__ __forceinline__ void enc_drain(EncData &d, const int lane) {
+    const uint32_t nseg = d.pos >> 4;
+    uint32_t first = 0;
+    if (d.head && nseg) {  // ragged stream start: segment 0 leaves as byte stores, never touching the bytes before it
+        if (lane >= (int)d.head && lane < 16) d.gbase[lane] = d.buf[lane];
+        d.head = 0;
+        first = 1;
     }
+    fence_proxy_async_smem();  // every lane's byte stores become visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+        if (nseg > first) bulk_s2g(d.gbase + first * 16, smem_u32(d.buf) + first * 16, (nseg - first) * 16);
+        bulk_commit();       // (possibly empty) group, so "all but the newest" below always covers the other half
+        bulk_wait_read<1>();  // the previous drain has finished reading the other half
+    }
+    __syncwarp();
+    const uint32_t rem = d.pos & 15u;
+    if (lane < (int)rem) d.oth[lane] = d.buf[nseg * 16 + lane];
+    d.gbase += nseg * 16;
+    d.pos = rem;
+    uint8_t *t = d.buf;
+    d.buf = d.oth;
+    d.oth = t;
 }
+
+// min(t, 1) kept opaque so the 1-bit code stays an integer (the compiler otherwise turns it into a predicate and
+// every later use into a compare/select pair)
+__device__ __forceinline__ uint32_t min1(uint32_t t) {
+    uint32_t c;
+    asm("min.u32 %0, %1, 1;" : "=r"(c) : "r"(t));
+    return c;
+}
+
+// zigzag, streamvbyte_zigzag.c:4-6
+__device__ __forceinline__ uint32_t zz_enc(int dd) { return ((uint32_t)dd << 1) ^ (uint32_t)(dd >> 31); }
 
 // Second half of an iteration: codes, keys, prefix scan, byte assembly.  WIDE (3-byte codes present in
 // the warp, |delta| >= 32768) is a separate instantiation so the common path carries 1-bit codes only.
 template <bool PARTIAL, bool WIDE>
-__device__ __forceinline__ void enc_emit(const uint32_t (&z)[8], const int lane, const int nvalid, EncData &d,
-                                         uint8_t *dbuf, uint16_t *kslot) {
+__device__ __forceinline__ void enc_emit(const uint32_t (&za)[4], const uint32_t (&zb)[4], const int lane,
+                                         const int nvalid, EncData &d, uint8_t *kslot) {
     // svb code = bytes - 1 (streamvbyte_encode.c:31-54; code 3 is unreachable from int16 input: z < 2^17)
-    uint32_t t[8], c[8];
-    uint32_t key = 0, csum = 0;
+    uint32_t ta[4], tb[4], ca[4], cb[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        t[j] = z[j] >> 8;
-        c[j] = WIDE ? (z[j] > 0xFFu) + (z[j] > 0xFFFFu) : (z[j] + 0xFF00u) >> 16;
-        csum += c[j];
-        key |= c[j] << (2 * j);  // 2 bits per value, value i -> byte i/4, shift 2*(i%4) (streamvbyte_encode.c:56-79)
+    for (int j = 0; j < 4; ++j) {
+        ta[j] = za[j] >> 8;
+        tb[j] = zb[j] >> 8;
+        ca[j] = WIDE ? (za[j] > 0xFFu) + (za[j] > 0xFFFFu) : min1(ta[j]);
+        cb[j] = WIDE ? (zb[j] > 0xFFu) + (zb[j] > 0xFFFFu) : min1(tb[j]);
     }
-    uint32_t lane_len = 8 + csum;
-    if (PARTIAL) lane_len = min(max(nvalid - lane * 8, 0), 8) + csum;  // invalid samples: z = 0, c = 0, no byte
-    const uint32_t incl = warp_incl_scan(lane_len);  // prefix scan over per-lane byte counts -> data offsets
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    uint8_t *p = dbuf + d.pos + (incl - lane_len);
+    // 2 bits per value, value i -> key byte i/4, shift 2*(i%4) (streamvbyte_encode.c:56-79)
+    const uint32_t key_a = ((ca[3] * 4 + ca[2]) * 4 + ca[1]) * 4 + ca[0];
+    const uint32_t key_b = ((cb[3] * 4 + cb[2]) * 4 + cb[1]) * 4 + cb[0];
+    uint32_t len_a = 4 + ca[0] + ca[1] + ca[2] + ca[3];
+    uint32_t len_b = 4 + cb[0] + cb[1] + cb[2] + cb[3];
+    if (PARTIAL) {  // invalid samples: z = 0, c = 0, no byte
+        len_a += (uint32_t)min(max(nvalid - lane * 4, 0), 4) - 4;
+        len_b += (uint32_t)min(max(nvalid - 128 - lane * 4, 0), 4) - 4;
+    }
+    // one prefix scan over both quads' byte counts (16 bits each; a warp appends <= 32*12 per quad row)
+    const uint32_t lens = len_a | (len_b << 16);
+    const uint32_t incl = warp_incl_scan(lens);
+    const uint32_t tot = __shfl_sync(FULL, incl, 31);
+    const uint32_t excl = incl - lens;
+    const uint32_t tot_a = tot & 0xFFFFu;
+    uint8_t *pa = d.buf + d.pos + (excl & 0xFFFFu);
+    uint8_t *pb = d.buf + d.pos + tot_a + (excl >> 16);
     if (!PARTIAL) {
-        // Both bytes are stored unconditionally except for the lane's last value: a spurious high byte
+        // Both bytes are stored unconditionally except for the quad's last value: a spurious high byte
         // lands where the same lane's next value puts its low byte afterwards (program order), so it
         // never survives.  The last value must not spill into the next lane's first byte.
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            p[0] = (uint8_t)z[j];
-            if (j < 7 || c[j]) p[1] = (uint8_t)t[j];
-            if (WIDE && c[j] == 2) p[2] = (uint8_t)(z[j] >> 16);
-            p += 1 + c[j];
+        for (int j = 0; j < 4; ++j) {
+            pa[0] = (uint8_t)za[j];
+            if (j < 3 || ca[j]) pa[1] = (uint8_t)ta[j];
+            if (WIDE && ca[j] == 2) pa[2] = (uint8_t)(za[j] >> 16);
+            pa += 1 + ca[j];
+            pb[0] = (uint8_t)zb[j];
+            if (j < 3 || cb[j]) pb[1] = (uint8_t)tb[j];
+            if (WIDE && cb[j] == 2) pb[2] = (uint8_t)(zb[j] >> 16);
+            pb += 1 + cb[j];
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (lane * 8 + j < nvalid) {
-                p[0] = (uint8_t)z[j];
-                if (c[j]) p[1] = (uint8_t)t[j];
-                if (WIDE && c[j] == 2) p[2] = (uint8_t)(z[j] >> 16);
-                p += 1 + c[j];
+        for (int j = 0; j < 4; ++j) {
+            if (lane * 4 + j < nvalid) {
+                pa[0] = (uint8_t)za[j];
+                if (ca[j]) pa[1] = (uint8_t)ta[j];
+                if (WIDE && ca[j] == 2) pa[2] = (uint8_t)(za[j] >> 16);
+                pa += 1 + ca[j];
+            }
+            if (128 + lane * 4 + j < nvalid) {
+                pb[0] = (uint8_t)zb[j];
+                if (cb[j]) pb[1] = (uint8_t)tb[j];
+                if (WIDE && cb[j] == 2) pb[2] = (uint8_t)(zb[j] >> 16);
+                pb += 1 + cb[j];
             }
         }
     }
-    kslot[lane] = (uint16_t)key;  // invalid samples carry code 0, so padding bits are zero
-    d.pos += total;
+    kslot[lane] = (uint8_t)key_a;  // invalid samples carry code 0, so padding bits are zero
+    kslot[32 + lane] = (uint8_t)key_b;
+    d.pos += tot_a + (tot >> 16);
 }
 
-// One 256-sample iteration: lane owns samples 8*lane .. 8*lane+7 of the iteration.
+// One 256-sample iteration.  wa / wb: the lane's quads (4 packed int16 each); carry (meaningful in lane 0):
+// the sample before this iteration's first one; rot_src = (lane + 31) & 31.
 template <bool PARTIAL>
-__device__ __forceinline__ void enc_iteration(const uint4 w, int &carry, const int lane, const int nvalid,
-                                              EncData &d, uint8_t *dbuf, uint16_t *kslot) {
+__device__ __forceinline__ void enc_iteration(const uint2 wa, const uint2 wb, int &carry, const int lane,
+                                              const int rot_src, const int nvalid, EncData &d, uint8_t *kslot) {
     // widen (slow5_press.c:1095-1097): one PRMT (sign-replicating) / one arithmetic shift per sample
-    int x[8];
-    x[0] = sext_lo16(w.x);
-    x[1] = (int)w.x >> 16;
-    x[2] = sext_lo16(w.y);
-    x[3] = (int)w.y >> 16;
-    x[4] = sext_lo16(w.z);
-    x[5] = (int)w.z >> 16;
-    x[6] = sext_lo16(w.w);
-    x[7] = (int)w.w >> 16;
-    const int up = __shfl_up_sync(FULL, (int)w.w, 1);
-    int prev = lane ? (up >> 16) : carry;
-    carry = __shfl_sync(FULL, (int)w.w, 31) >> 16;
+    int xa[4], xb[4];
+    xa[0] = sext_lo16(wa.x);
+    xa[1] = (int)wa.x >> 16;
+    xa[2] = sext_lo16(wa.y);
+    xa[3] = (int)wa.y >> 16;
+    xb[0] = sext_lo16(wb.x);
+    xb[1] = (int)wb.x >> 16;
+    xb[2] = sext_lo16(wb.y);
+    xb[3] = (int)wb.y >> 16;
+    // previous samples: one rotate-by-one shuffle of (last of quad A, last of quad B).  Lane 0 receives lane
+    // 31's pair: its quad-A last sample precedes lane 0's quad B, its quad-B last sample is the next carry.
+    const uint32_t lasts = __byte_perm(wa.y, wb.y, 0x7632);
+    const uint32_t rot = __shfl_sync(FULL, lasts, rot_src);
+    const int r_lo = sext_lo16(rot), r_hi = (int)rot >> 16;
+    int pa = lane ? r_lo : carry;
+    int pb = lane ? r_hi : r_lo;
+    carry = r_hi;
 
-    uint32_t z[8], zor = 0;
+    uint32_t za[4], zb[4], zor = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int dd = x[j] - prev;  // zigzag-delta, streamvbyte_zigzag.c:4-6,15-20
-        prev = x[j];
-        z[j] = ((uint32_t)dd << 1) ^ (uint32_t)(dd >> 31);
-        if (PARTIAL && lane * 8 + j >= nvalid) z[j] = 0;
-        zor |= z[j];
+    for (int j = 0; j < 4; ++j) {  // zigzag-delta, streamvbyte_zigzag.c:15-20
+        za[j] = zz_enc(xa[j] - pa);
+        pa = xa[j];
+        zb[j] = zz_enc(xb[j] - pb);
+        pb = xb[j];
+        if (PARTIAL && lane * 4 + j >= nvalid) za[j] = 0;
+        if (PARTIAL && 128 + lane * 4 + j >= nvalid) zb[j] = 0;
+        zor |= za[j] | zb[j];
     }
     if (__any_sync(FULL, zor > 0xFFFFu)) {
-        enc_emit<PARTIAL, true>(z, lane, nvalid, d, dbuf, kslot);
+        enc_emit<PARTIAL, true>(za, zb, lane, nvalid, d, kslot);
+        __syncwarp();
+        enc_drain(d, lane);  // keeps the buffered bytes inside the ENC_DB envelope (rare path)
     } else {
-        enc_emit<PARTIAL, false>(z, lane, nvalid, d, dbuf, kslot);
+        enc_emit<PARTIAL, false>(za, zb, lane, nvalid, d, kslot);
     }
-    __syncwarp();
-    enc_flush_segments(d, dbuf, lane);
 }
 
-__global__ void __launch_bounds__(ENC_WARPS * 32) svbzd_encode_kernel(const SvbEncodeArgs a) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, 3) svbzd_encode_kernel(const SvbEncodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncWarpSmem *smem = reinterpret_cast<EncWarpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31;
+    const int rot_src = (lane + 31) & 31;
     EncWarpSmem &ws = smem[threadIdx.x >> 5];
     const uint32_t bar0 = smem_u32(&ws.bar[0]);
     const uint32_t in0 = smem_u32(&ws.in[0][0]);
@@ -196,6 +256,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) svbzd_encode_kernel(const SvbE
     }
     __syncwarp();
     uint32_t q = 0;  // chunks consumed by this warp so far (stage = q & 1, parity = (q >> 1) & 1)
+    EncData d;
+    d.buf = ws.dbuf[0];
+    d.oth = ws.dbuf[1];
 
     for (;;) {
         const uint64_t r = next_work(a.work_counter, lane);
@@ -226,10 +289,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) svbzd_encode_kernel(const SvbE
         if (lane < 4) dst[lane] = (uint8_t)(n >> (8 * lane));  // u32 LE header, slow5_press.c:1074
         uint8_t *kdst = dst + 4;
         uint8_t *ddst = kdst + nkeys;
-        EncData d;
         d.head = d.pos = (uint32_t)(reinterpret_cast<uintptr_t>(ddst) & 15u);
         d.gbase = ddst - d.head;
-        d.fseg = 0;
 
         const uint32_t nchunks = (n + ENC_CH_SAMPLES - 1) / ENC_CH_SAMPLES;
         auto issue = [&](uint32_t k, uint32_t qq) {
@@ -267,14 +328,17 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) svbzd_encode_kernel(const SvbE
                 for (uint32_t i = bytes_cur / 2 + lane; i < chunk_samples; i += 32) s[i] = g[i];
                 __syncwarp();
             }
-            const uint4 *in4 = reinterpret_cast<const uint4 *>(ws.in[stage]);
-            uint16_t *k16 = reinterpret_cast<uint16_t *>(ws.kbuf);
+            const uint2 *in2 = reinterpret_cast<const uint2 *>(ws.in[stage]);
             const uint32_t full_iters = chunk_samples >> 8;
             for (uint32_t it = 0; it < full_iters; ++it)
-                enc_iteration<false>(in4[it * 32 + lane], carry, lane, 256, d, ws.dbuf, k16 + it * 32);
+                enc_iteration<false>(in2[it * 64 + lane], in2[it * 64 + 32 + lane], carry, lane, rot_src, 256, d,
+                                     ws.kbuf + it * 64);
             const int tail = chunk_samples & 255;
-            if (tail) enc_iteration<true>(in4[full_iters * 32 + lane], carry, lane, tail, d, ws.dbuf, k16 + full_iters * 32);
-            // ---- end of chunk: key bytes out, carry the partial data segment to the front
+            if (tail)
+                enc_iteration<true>(in2[full_iters * 64 + lane], in2[full_iters * 64 + 32 + lane], carry, lane, rot_src,
+                                    tail, d, ws.kbuf + full_iters * 64);
+            __syncwarp();
+            // ---- end of chunk: key bytes out, data segments out
             {
                 const uint32_t nk = (chunk_samples + 3) >> 2;
                 uint8_t *kg = kdst + (uint64_t)k * (ENC_CH_SAMPLES / 4);
@@ -289,22 +353,13 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) svbzd_encode_kernel(const SvbE
                     for (uint32_t i = lane; i < nk; i += 32) kg[i] = ws.kbuf[i];
                 }
             }
-            if (d.fseg) {
-                const uint32_t rem = d.pos & 15u;
-                uint8_t t = 0;
-                if (lane < (int)rem) t = ws.dbuf[d.fseg * 16 + lane];
-                __syncwarp();
-                if (lane < (int)rem) ws.dbuf[lane] = t;
-                d.gbase += d.fseg * 16;
-                d.pos = rem;
-                d.fseg = 0;
-            }
+            enc_drain(d, lane);
             ++q;
             bytes_cur = bytes_next;
-            __syncwarp();  // stage, kbuf and dbuf front are free / visible before the next chunk touches them
+            __syncwarp();  // stage, kbuf and the buffer fronts are free / visible before the next chunk touches them
         }
         // remaining (< 16) data bytes of the stream leave as byte stores
-        if (lane >= (int)d.head && lane < (int)d.pos) d.gbase[lane] = ws.dbuf[lane];
+        if (lane >= (int)d.head && lane < (int)d.pos) d.gbase[lane] = d.buf[lane];
         const uint64_t data_bytes = (uint64_t)((d.gbase + d.pos) - ddst);
         if (lane == 0) {
             a.svb_len[r] = (uint32_t)(4 + nkeys + data_bytes);
@@ -312,6 +367,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) svbzd_encode_kernel(const SvbE
         }
         __syncwarp();
     }
+    if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk copy's reads
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -321,15 +377,15 @@ constexpr int DEC_WARPS = 8;
 constexpr int DEC_BLK = 1024;  // bytes per bulk copy
 constexpr int DEC_NB = 4;      // ring blocks per warp
 constexpr int DEC_RING = DEC_BLK * DEC_NB;
+constexpr int DEC_MIRROR = 32;  // the ring's first bytes repeated behind its end: word loads never wrap
 
 struct __align__(128) DecWarpSmem {
-    uint8_t ring[DEC_RING];
+    uint8_t ring[DEC_RING + DEC_MIRROR];
     unsigned long long bar[DEC_NB];
 };
 
-// zigzag decode (streamvbyte_zigzag.c:23-25): (v >> 1) ^ -(v & 1) == (v >> 1) - (v & 1) * v, which is one
-// instruction shorter (LOP, SHF, IMAD)
-__device__ __forceinline__ uint32_t zz_dec(uint32_t v) { return (v >> 1) - (v & 1u) * v; }
+// zigzag decode (streamvbyte_zigzag.c:23-25)
+__device__ __forceinline__ uint32_t zz_dec(uint32_t v) { return (v >> 1) ^ (0u - (v & 1u)); }
 
 // Per-read decode state (warp-uniform unless noted).
 struct DecState {
@@ -342,7 +398,8 @@ struct DecState {
     uint32_t pos;           // data bytes consumed
     uint32_t acc;           // running sum, prev = 0 (slow5_press.c:1162)
     uint32_t nkeys;
-    uint32_t kk;            // per lane: the two control bytes of the coming iteration
+    uint32_t k0, k1;        // per lane: the two control bytes of the coming iteration (combined at use, so
+                            // the loads have a whole iteration to land)
 };
 
 __device__ __forceinline__ void dec_issue_block(DecState &s, uint32_t bar0, uint32_t ring0, const int lane) {
@@ -357,59 +414,121 @@ __device__ __forceinline__ void dec_issue_block(DecState &s, uint32_t bar0, uint
     ++s.issued;
 }
 
-// One 256-sample iteration; lane owns values 8*lane .. 8*lane+7.  Returns false when the control bytes
-// claim more data than the stream holds.
-template <bool PARTIAL>
-__device__ __forceinline__ bool dec_iteration(DecState &s, const uint8_t *ring, const uint8_t *knext, const bool guard,
-                                              const uint32_t next_ki, int16_t *o, const int nvalid, const int lane,
-                                              uint32_t &phase_bits, const uint32_t bar0, const uint32_t ring0) {
-    const uint32_t k_now = s.kk;
-    if (!PARTIAL) {  // prefetch the next iteration's control bytes (the last iteration has no successor)
-        if (!guard) {
-            s.kk = (uint32_t)__ldg(knext) | ((uint32_t)__ldg(knext + 1) << 8);
-        } else {
-            s.kk = 0;
-            if (next_ki < s.nkeys) s.kk = __ldg(knext);
-            if (next_ki + 1 < s.nkeys) s.kk |= (uint32_t)__ldg(knext + 1) << 8;
-        }
-    }
-    uint32_t c[8];
-    uint32_t csum = 0, cor = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        c[j] = (k_now >> (2 * j)) & 3u;
-        if (PARTIAL && lane * 8 + j >= nvalid) c[j] = 0;
-        csum += c[j];
-        cor |= c[j];
-    }
-    uint32_t lane_len = 8 + csum;
-    if (PARTIAL) lane_len = min(max(nvalid - lane * 8, 0), 8) + csum;
-    // prefix scan over the control-byte lengths -> per-lane data offsets
-    const uint32_t incl = warp_incl_scan(lane_len);
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    if (s.pos + total > s.D) return false;  // stream claims more data than it holds: never gather past it
-    const uint32_t need = (s.skew + s.pos + total + DEC_BLK - 1) / DEC_BLK;
+// wait until ring blocks [waited, need) have landed; a block landing in slot 0 refreshes the mirror
+__device__ __forceinline__ void dec_wait_blocks(DecState &s, const uint32_t need, uint8_t *ring, uint32_t &phase_bits,
+                                                const uint32_t bar0, const int lane) {
     while (s.waited < need) {
         const uint32_t slot = s.waited % DEC_NB;
         mbar_wait(bar0 + 8 * slot, (phase_bits >> slot) & 1u);
         phase_bits ^= 1u << slot;
         ++s.waited;
+        if (slot == 0) {
+            uint32_t *r32 = reinterpret_cast<uint32_t *>(ring);
+            if (lane < DEC_MIRROR / 4) r32[DEC_RING / 4 + lane] = r32[lane];
+            __syncwarp();
+        }
     }
-    const uint32_t ri = (s.skew + s.pos + incl - lane_len) & (DEC_RING - 1);
-    const bool wrap = __any_sync(FULL, ri + lane_len > DEC_RING);
-    const bool wide = __any_sync(FULL, (cor & 2u) != 0);
-    uint32_t v[8];
-    if (!PARTIAL && !wrap && !wide) {
-        // common path: 1- and 2-byte values, no ring wrap inside any lane's run
-        const uint8_t *q = ring + ri;
+}
+
+// selector of the PRMT that widens two adjacent stream values (1 or 2 bytes each) out of a 4-byte window into
+// one packed pair (value a in the low half, value b in the high half); q = (a is 2 bytes) + 4 * (b is 2 bytes).
+// Result bytes: [w0, a2 ? w1 : 0, w[1+a2], b2 ? w[2+a2] : 0]; selector nibbles 4..7 address the zero operand.
+//   q=0: 0x6150   q=1: 0x7210   q=4: 0x2150   q=5: 0x3210      (looked up bytewise by a PRMT over the 8-byte table)
+// (raw prmt: the __byte_perm intrinsic would spend an extra AND on masking every run-time selector)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ uint32_t pair_selector(uint32_t q) {
+    return prmt(0x72611050u, 0x32211050u, q * 0x11u + 0x20u);
+}
+// packed zigzag decode of two 16-bit values (exact mod 2^16, which is all the truncating int16 store keeps)
+__device__ __forceinline__ uint32_t zz_dec2(uint32_t p) {
+    const uint32_t m = (p & 0x00010001u) * 0xFFFFu;  // 0xFFFF in every half whose value is odd
+    return ((p >> 1) & 0x7FFF7FFFu) ^ m;
+}
+
+// One 256-sample iteration; lane owns values 8*lane .. 8*lane+7.  Returns false when the control bytes
+// claim more data than the stream holds.
+template <bool PARTIAL>
+__device__ __forceinline__ bool dec_iteration(DecState &s, uint8_t *ring, const uint8_t *knext, const bool guard,
+                                              const uint32_t next_ki, int16_t *o, const int nvalid, const int lane,
+                                              uint32_t &phase_bits, const uint32_t bar0, const uint32_t ring0) {
+    const uint32_t k_now = s.k0 | (s.k1 << 8);
+    if (!PARTIAL) {  // prefetch the next iteration's control bytes (the last iteration has no successor)
+        if (!guard) {
+            s.k0 = __ldg(knext);
+            s.k1 = __ldg(knext + 1);
+        } else {
+            s.k0 = s.k1 = 0;
+            if (next_ki < s.nkeys) s.k0 = __ldg(knext);
+            if (next_ki + 1 < s.nkeys) s.k1 = __ldg(knext + 1);
+        }
+    }
+    const bool wide = __any_sync(FULL, (k_now & 0xAAAAu) != 0);
+    if (!PARTIAL && !wide) {
+        // ---- common path: every value of the iteration is 1 or 2 bytes; k_now holds one flag per value at bit 2j
+        const uint32_t lane_len = 8 + __popc(k_now);
+        const uint32_t incl = warp_incl_scan(lane_len);  // prefix scan over the control-byte lengths -> data offsets
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (s.pos + total > s.D) return false;  // stream claims more data than it holds: never gather past it
+        dec_wait_blocks(s, (s.skew + s.pos + total + DEC_BLK - 1) / DEC_BLK, ring, phase_bits, bar0, lane);
+        const uint32_t ri = (s.skew + s.pos + incl - lane_len) & (DEC_RING - 1);
+        // the lane's 8..16 bytes, realigned into four registers (five aligned word loads + funnel shifts)
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(ring) + (ri >> 2);
+        const uint32_t sh = (ri & 3u) * 8;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
+        const uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
+        const uint32_t kf = k_now;  // flags at bits 0,2,..,14
+        // values 0..3 sit in bytes [0, 8) = (a0, a1); values 4..7 start at byte 4 + (2-byte values among 0..3)
+        const uint32_t o2 = 2 + (kf & 1u) + ((kf >> 2) & 1u);  // byte offset of value 2
+        const uint32_t o4 = __popc(kf & 0x55u);                // byte offset of value 4, minus 4
+        const uint32_t c0 = __funnelshift_rc(a1, a2, o4 * 8), c1 = __funnelshift_rc(a2, a3, o4 * 8);
+        const uint32_t o6 = 2 + ((kf >> 8) & 1u) + ((kf >> 10) & 1u);  // value 6 relative to value 4
+        const uint32_t t1 = __funnelshift_rc(a0, a1, o2 * 8);
+        const uint32_t t3 = __funnelshift_rc(c0, c1, o6 * 8);
+        const uint32_t p0 = prmt(a0, 0u, pair_selector(kf & 5u));
+        const uint32_t p1 = prmt(t1, 0u, pair_selector((kf >> 4) & 5u));
+        const uint32_t p2 = prmt(c0, 0u, pair_selector((kf >> 8) & 5u));
+        const uint32_t p3 = prmt(t3, 0u, pair_selector((kf >> 12) & 5u));
+        // zigzag decode + running sum, two 16-bit lanes per register (streamvbyte_zigzag.c:23-25,34-40)
+        // x * 0x10001 = (lo, lo + hi): the pair's own prefix; the carry-in from the left is added per half
+        // (a plain 32-bit add would leak the low half's carry into the high half)
+        const uint32_t s0 = zz_dec2(p0) * 0x10001u;  // (d0, d0 + d1)
+        const uint32_t s1 = __vadd2(zz_dec2(p1) * 0x10001u, __byte_perm(s0, 0u, 0x3232));
+        const uint32_t s2 = __vadd2(zz_dec2(p2) * 0x10001u, __byte_perm(s1, 0u, 0x3232));
+        const uint32_t s3 = __vadd2(zz_dec2(p3) * 0x10001u, __byte_perm(s2, 0u, 0x3232));
+        const uint32_t run = s3 >> 16;  // the lane's total (mod 2^16)
+        const uint32_t incl_sum = warp_incl_scan(run);
+        const uint32_t base = (s.acc + incl_sum - run) & 0xFFFFu;
+        s.acc += __shfl_sync(FULL, incl_sum, 31);
+        const uint32_t base2 = base * 0x10001u;
+        uint4 wv;
+        wv.x = __vadd2(s0, base2);
+        wv.y = __vadd2(s1, base2);
+        wv.z = __vadd2(s2, base2);
+        wv.w = __vadd2(s3, base2);
+        *reinterpret_cast<uint4 *>(o) = wv;
+        s.pos += total;
+    } else {
+        uint32_t c[8];
+        uint32_t csum = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            v[j] = q[0];
-            if (c[j]) v[j] |= (uint32_t)q[1] << 8;
-            q += 1 + c[j];
+            c[j] = (k_now >> (2 * j)) & 3u;
+            if (PARTIAL && lane * 8 + j >= nvalid) c[j] = 0;
+            csum += c[j];
         }
-    } else {
-        uint32_t p = ri;
+        uint32_t lane_len = 8 + csum;
+        if (PARTIAL) lane_len = min(max(nvalid - lane * 8, 0), 8) + csum;
+        const uint32_t incl = warp_incl_scan(lane_len);
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (s.pos + total > s.D) return false;
+        dec_wait_blocks(s, (s.skew + s.pos + total + DEC_BLK - 1) / DEC_BLK, ring, phase_bits, bar0, lane);
+        uint32_t p = (s.skew + s.pos + incl - lane_len) & (DEC_RING - 1);
+        uint32_t v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             v[j] = 0;
@@ -421,39 +540,39 @@ __device__ __forceinline__ bool dec_iteration(DecState &s, const uint8_t *ring, 
                 p += 1 + c[j];
             }
         }
-    }
-    // zigzag decode + running sum (streamvbyte_zigzag.c:23-25,34-40); mod 2^32 arithmetic, the truncating
-    // int16 store keeps the low 16 bits
-    uint32_t sum[8];
-    uint32_t run = 0;
+        // zigzag decode + running sum (streamvbyte_zigzag.c:23-25,34-40); mod 2^32 arithmetic, the truncating
+        // int16 store keeps the low 16 bits
+        uint32_t sum[8];
+        uint32_t run = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        run += zz_dec(v[j]);
-        sum[j] = run;
-    }
-    const uint32_t incl_sum = warp_incl_scan(run);
-    const uint32_t base = s.acc + incl_sum - run;
-    s.acc += __shfl_sync(FULL, incl_sum, 31);
-    if (!PARTIAL) {
-        uint4 w;
-        w.x = __byte_perm(sum[0] + base, sum[1] + base, 0x5410);
-        w.y = __byte_perm(sum[2] + base, sum[3] + base, 0x5410);
-        w.z = __byte_perm(sum[4] + base, sum[5] + base, 0x5410);
-        w.w = __byte_perm(sum[6] + base, sum[7] + base, 0x5410);
-        *reinterpret_cast<uint4 *>(o) = w;
-    } else {
+        for (int j = 0; j < 8; ++j) {
+            run += zz_dec(v[j]);
+            sum[j] = run;
+        }
+        const uint32_t incl_sum = warp_incl_scan(run);
+        const uint32_t base = s.acc + incl_sum - run;
+        s.acc += __shfl_sync(FULL, incl_sum, 31);
+        if (!PARTIAL) {
+            uint4 wv;
+            wv.x = __byte_perm(sum[0] + base, sum[1] + base, 0x5410);
+            wv.y = __byte_perm(sum[2] + base, sum[3] + base, 0x5410);
+            wv.z = __byte_perm(sum[4] + base, sum[5] + base, 0x5410);
+            wv.w = __byte_perm(sum[6] + base, sum[7] + base, 0x5410);
+            *reinterpret_cast<uint4 *>(o) = wv;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (lane * 8 + j < nvalid) o[j] = (int16_t)(uint16_t)(sum[j] + base);
+            for (int j = 0; j < 8; ++j)
+                if (lane * 8 + j < nvalid) o[j] = (int16_t)(uint16_t)(sum[j] + base);
+        }
+        s.pos += total;
     }
-    s.pos += total;
     __syncwarp();  // all lanes have finished reading the ring before blocks are recycled
     const uint32_t done_blocks = (s.skew + s.pos) / DEC_BLK;
     while (s.issued < s.nblk && s.issued < done_blocks + DEC_NB) dec_issue_block(s, bar0, ring0, lane);
     return true;
 }
 
-__global__ void __launch_bounds__(DEC_WARPS * 32, 5) svbzd_decode_kernel(const SvbDecodeArgs a) {
+__global__ void __launch_bounds__(DEC_WARPS * 32, 4) svbzd_decode_kernel(const SvbDecodeArgs a) {
     __shared__ DecWarpSmem smem[DEC_WARPS];
     const int lane = threadIdx.x & 31;
     DecWarpSmem &ws = smem[threadIdx.x >> 5];
@@ -516,11 +635,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 5) svbzd_decode_kernel(const S
 
         int16_t *out = a.sig + soff + lane * 8;
         // control bytes of the first iteration
-        s.kk = 0;
+        s.k0 = s.k1 = 0;
         {
             const uint32_t ki = 2 * lane;
-            if (ki < nkeys) s.kk = __ldg(keys + ki);
-            if (ki + 1 < nkeys) s.kk |= (uint32_t)__ldg(keys + ki + 1) << 8;
+            if (ki < nkeys) s.k0 = __ldg(keys + ki);
+            if (ki + 1 < nkeys) s.k1 = __ldg(keys + ki + 1);
         }
         const uint32_t full_iters = n >> 8;
         const int tail = (int)(n & 255u);
@@ -659,7 +778,25 @@ __global__ void __launch_bounds__(COPY_WARPS * 32) gather_copy_kernel(const uint
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// S5B_SVBZD_LEGACY=1 (read once) routes both launchers to the round-1 "v3" kernels for A/B timing
+namespace v3 {
+int svbzd_encode_blocks_per_sm();
+int svbzd_decode_blocks_per_sm();
+cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, unsigned grid, cudaStream_t st);
+cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, unsigned grid, cudaStream_t st);
+int enc_warps();
+int dec_warps();
+}  // namespace v3
+static bool use_legacy() {
+    static const bool v = [] {
+        const char *e = getenv("S5B_SVBZD_LEGACY");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
 int svbzd_encode_blocks_per_sm() {
+    if (use_legacy()) return v3::svbzd_encode_blocks_per_sm();
     int n = 0;
     if (cudaFuncSetAttribute(svbzd_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(sizeof(EncWarpSmem) * ENC_WARPS)) != cudaSuccess)
@@ -670,6 +807,7 @@ int svbzd_encode_blocks_per_sm() {
     return n;
 }
 int svbzd_decode_blocks_per_sm() {
+    if (use_legacy()) return v3::svbzd_decode_blocks_per_sm();
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, svbzd_decode_kernel, DEC_WARPS * 32, 0) != cudaSuccess)
         return 0;
@@ -686,6 +824,8 @@ static unsigned persistent_grid(uint64_t n_reads, int warps, int num_sms, int bl
 cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
+    if (use_legacy())
+        return v3::launch_svbzd_encode(a, persistent_grid(a.n_reads, v3::enc_warps(), num_sms, blocks_per_sm), st);
     svbzd_encode_kernel<<<persistent_grid(a.n_reads, ENC_WARPS, num_sms, blocks_per_sm), ENC_WARPS * 32,
                           sizeof(EncWarpSmem) * ENC_WARPS, st>>>(a);
     return cudaGetLastError();
@@ -693,6 +833,8 @@ cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_
 cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
+    if (use_legacy())
+        return v3::launch_svbzd_decode(a, persistent_grid(a.n_reads, v3::dec_warps(), num_sms, blocks_per_sm), st);
     svbzd_decode_kernel<<<persistent_grid(a.n_reads, DEC_WARPS, num_sms, blocks_per_sm), DEC_WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
