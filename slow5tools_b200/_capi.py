@@ -6,7 +6,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path():
-    return os.path.join(_HERE, "libslow5b200.so")
+    # S5B_LIBRARY: development override used for A/B runs of kernel variants (csrc/Makefile `variant`)
+    return os.environ.get("S5B_LIBRARY") or os.path.join(_HERE, "libslow5b200.so")
 
 
 class S5BError(RuntimeError):

@@ -65,6 +65,15 @@ __device__ __forceinline__ uint64_t next_work(unsigned long long *counter, int l
 // 128+4*lane .. 128+4*lane+3 ("quad B").  Neighbouring lanes of one byte-store instruction are then
 // ~4.1 bytes apart (a warp's 32 addresses span ~33 words: no shared-memory bank conflicts), where
 // 8 consecutive values per lane put them ~8.3 bytes apart (66 words, 2 wavefronts per store).
+#ifndef S5B_ENC_MIN_CTAS
+#define S5B_ENC_MIN_CTAS 4
+#endif
+#ifndef S5B_DEC_MIN_CTAS
+#define S5B_DEC_MIN_CTAS 5
+#endif
+#ifndef S5B_ENC_NDBUF
+#define S5B_ENC_NDBUF 1  // 1: single data buffer, every drain waits for its own bulk copy (smaller footprint, more CTAs)
+#endif
 constexpr int ENC_WARPS = 8;
 constexpr int ENC_CH_SAMPLES = 1024;  // samples per bulk-copy chunk (4 iterations of 256)
 constexpr int ENC_CH_BYTES = ENC_CH_SAMPLES * 2;
@@ -76,7 +85,7 @@ constexpr int ENC_DB = 2320;
 
 struct __align__(128) EncWarpSmem {
     uint8_t in[ENC_STAGES][ENC_CH_BYTES];  // staged signal
-    uint8_t dbuf[2][ENC_DB];               // data-stream double buffer; dbuf[x][0] <-> 16-byte aligned global address
+    uint8_t dbuf[S5B_ENC_NDBUF][ENC_DB];   // data-stream double buffer; dbuf[x][0] <-> 16-byte aligned global address
     uint8_t kbuf[ENC_CH_SAMPLES / 4];      // key bytes of one chunk, natural index
     unsigned long long bar[ENC_STAGES];
 };
@@ -107,16 +116,23 @@ __device__ __forceinline__ void enc_drain(EncData &d, const int lane) {
     if (lane == 0) {
         if (nseg > first) bulk_s2g(d.gbase + first * 16, smem_u32(d.buf) + first * 16, (nseg - first) * 16);
         bulk_commit();       // (possibly empty) group, so "all but the newest" below always covers the other half
-        bulk_wait_read<1>();  // the previous drain has finished reading the other half
+        bulk_wait_read<S5B_ENC_NDBUF - 1>();  // the previous drain has finished reading the other half
     }
     __syncwarp();
     const uint32_t rem = d.pos & 15u;
+#if S5B_ENC_NDBUF == 2
     if (lane < (int)rem) d.oth[lane] = d.buf[nseg * 16 + lane];
-    d.gbase += nseg * 16;
-    d.pos = rem;
     uint8_t *t = d.buf;
     d.buf = d.oth;
     d.oth = t;
+#else
+    uint8_t t = 0;
+    if (lane < (int)rem) t = d.buf[nseg * 16 + lane];
+    __syncwarp();
+    if (lane < (int)rem) d.buf[lane] = t;
+#endif
+    d.gbase += nseg * 16;
+    d.pos = rem;
 }
 
 // min(t, 1) kept opaque so the 1-bit code stays an integer (the compiler otherwise turns it into a predicate and
@@ -242,7 +258,7 @@ __device__ __forceinline__ void enc_iteration(const uint2 wa, const uint2 wb, in
     }
 }
 
-__global__ void __launch_bounds__(ENC_WARPS * 32, 3) svbzd_encode_kernel(const SvbEncodeArgs a) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode_kernel(const SvbEncodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncWarpSmem *smem = reinterpret_cast<EncWarpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) svbzd_encode_kernel(const S
     uint32_t q = 0;  // chunks consumed by this warp so far (stage = q & 1, parity = (q >> 1) & 1)
     EncData d;
     d.buf = ws.dbuf[0];
-    d.oth = ws.dbuf[1];
+    d.oth = ws.dbuf[S5B_ENC_NDBUF - 1];
 
     for (;;) {
         const uint64_t r = next_work(a.work_counter, lane);
@@ -293,19 +309,19 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) svbzd_encode_kernel(const S
         d.gbase = ddst - d.head;
 
         const uint32_t nchunks = (n + ENC_CH_SAMPLES - 1) / ENC_CH_SAMPLES;
+        // bulk-copyable bytes of the read, split into whole chunks and one last piece (32-bit from here on)
+        uint64_t copyable = (n_bytes + 15) & ~15ull;
+        if (copyable > slot_bytes16) copyable = slot_bytes16;
+        const uint32_t copy_full = (uint32_t)(copyable / ENC_CH_BYTES);
+        const uint32_t copy_last = (uint32_t)(copyable % ENC_CH_BYTES);
         auto issue = [&](uint32_t k, uint32_t qq) {
             // chunk k of this read -> stage qq & 1
-            const uint64_t b0 = (uint64_t)k * ENC_CH_BYTES;
-            uint64_t want = n_bytes - b0;
-            if (want > ENC_CH_BYTES) want = ENC_CH_BYTES;
-            want = (want + 15) & ~15ull;
-            uint64_t can = slot_bytes16 > b0 ? slot_bytes16 - b0 : 0;
-            const uint32_t bytes = (uint32_t)(want < can ? want : can);
+            const uint32_t bytes = k < copy_full ? (uint32_t)ENC_CH_BYTES : (k == copy_full ? copy_last : 0u);
             const uint32_t stage = qq & 1;
             if (lane == 0) {
                 if (bytes) {
                     mbar_arrive_expect_tx(bar0 + 8 * stage, bytes);
-                    bulk_g2s(in0 + stage * ENC_CH_BYTES, src + b0, bytes, bar0 + 8 * stage);
+                    bulk_g2s(in0 + stage * ENC_CH_BYTES, src + (size_t)k * ENC_CH_BYTES, bytes, bar0 + 8 * stage);
                 } else {
                     // nothing bulk-copyable (a < 8-sample tail in the last slot): complete the phase by hand
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * stage) : "memory");
@@ -341,15 +357,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) svbzd_encode_kernel(const S
             // ---- end of chunk: key bytes out, data segments out
             {
                 const uint32_t nk = (chunk_samples + 3) >> 2;
-                uint8_t *kg = kdst + (uint64_t)k * (ENC_CH_SAMPLES / 4);
-                if ((reinterpret_cast<uintptr_t>(kg) & 3u) == 0) {
-                    const uint32_t nw = nk >> 2;
-                    const uint32_t *ks = reinterpret_cast<const uint32_t *>(ws.kbuf);
-                    uint32_t *kg32 = reinterpret_cast<uint32_t *>(kg);
-                    for (uint32_t i = lane; i < nw; i += 32) kg32[i] = ks[i];
-                    const uint32_t i = (nw << 2) + lane;
-                    if (i < nk) kg[i] = ws.kbuf[i];
+                uint8_t *kg = kdst + (size_t)k * (ENC_CH_SAMPLES / 4);
+                const uint32_t *ks = reinterpret_cast<const uint32_t *>(ws.kbuf);
+                if (nk == ENC_CH_SAMPLES / 4 && (reinterpret_cast<uintptr_t>(kg) & 3u) == 0) {
+                    uint32_t *kg32 = reinterpret_cast<uint32_t *>(kg);  // whole chunk, word aligned: two words per lane
+                    kg32[lane] = ks[lane];
+                    kg32[lane + 32] = ks[lane + 32];
                 } else {
+#pragma unroll 1
                     for (uint32_t i = lane; i < nk; i += 32) kg[i] = ws.kbuf[i];
                 }
             }
@@ -572,7 +587,7 @@ __device__ __forceinline__ bool dec_iteration(DecState &s, uint8_t *ring, const 
     return true;
 }
 
-__global__ void __launch_bounds__(DEC_WARPS * 32, 4) svbzd_decode_kernel(const SvbDecodeArgs a) {
+__global__ void __launch_bounds__(DEC_WARPS * 32, S5B_DEC_MIN_CTAS) svbzd_decode_kernel(const SvbDecodeArgs a) {
     __shared__ DecWarpSmem smem[DEC_WARPS];
     const int lane = threadIdx.x & 31;
     DecWarpSmem &ws = smem[threadIdx.x >> 5];
