@@ -57,6 +57,14 @@ int  orc_svbzd_depress_batch(const uint8_t *in, const uint64_t *in_off, const ui
 /* size only (no output written) */
 size_t orc_svbzd_size(const int16_t *in, uint32_t n_samples);
 
+/* ---- ex-zd signal codec (oracle/exzd_oracle.c), slow5_press.c:1236-1848 ------------------------------------
+ * Pinned by tests/test_oracle_exzd.py against the compiled reference and the reference's ex-zd BLOW5 golden. */
+size_t orc_exzd_bound(uint64_t n_samples);
+/* ptr_compress_ex_zd (:1778 -> _v0 :1721-1776); returns bytes written, 0 for an empty input (undefined in the reference) */
+size_t orc_exzd_compress(const int16_t *in, size_t count_bytes, uint8_t *out);
+/* ptr_depress_ex_zd (:1824 -> _v0 :1787-1822); 0 / -13 (SLOW5_ERR_PRESS) / -2 */
+int orc_exzd_depress(const uint8_t *in, size_t count, int16_t *out, size_t out_cap_samples, uint64_t *n_samples);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,13 @@ cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_
 cudaError_t launch_svbzd_peek(const uint8_t *svb, const uint64_t *svb_off, const uint32_t *svb_len, uint64_t n_reads,
                               uint32_t *n_samples, cudaStream_t st);
 
+// ex-zd signal codec (exzd_kernels.cu): same argument blocks as svb-zd (svb = the ex-zd byte slab)
+int exzd_encode_blocks_per_sm();
+int exzd_decode_blocks_per_sm();
+uint64_t exzd_bound(uint32_t n_samples);
+cudaError_t launch_exzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
+cudaError_t launch_exzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
+
 // exclusive scan of len[] rounded up to `align` units -> off[0..n] (n+1 entries); 3 launches
 cudaError_t launch_scan(const uint32_t *len, uint64_t n, uint32_t align, uint64_t *off, void *scratch, cudaStream_t st);
 

@@ -34,6 +34,28 @@ class Oracle:
         L.orc_svbzd_depress_batch.restype = C.c_int
         L.orc_svbzd_depress_batch.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
 
+        L.orc_exzd_bound.restype = sz
+        L.orc_exzd_bound.argtypes = [u64]
+        L.orc_exzd_compress.restype = sz
+        L.orc_exzd_compress.argtypes = [vp, sz, vp]
+        L.orc_exzd_depress.restype = C.c_int
+        L.orc_exzd_depress.argtypes = [vp, sz, vp, sz, C.POINTER(u64)]
+
+    def exzd_compress(self, x):
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        out = np.empty(int(self.lib.orc_exzd_bound(x.size)) + 16, np.uint8)
+        k = self.lib.orc_exzd_compress(x.ctypes.data, x.nbytes, out.ctypes.data)
+        return out[:k].tobytes()
+
+    def exzd_depress(self, b, cap=None):
+        buf = np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, np.uint8)
+        n = int.from_bytes(b[1:9], "little") if len(b) >= 9 else 0
+        cap = min(n, 1 << 28) if cap is None else cap
+        out = np.zeros(max(cap, 1), np.int16)
+        nn = C.c_uint64()
+        rc = self.lib.orc_exzd_depress(buf.ctypes.data, len(b), out.ctypes.data, cap, C.byref(nn))
+        return rc, out[:nn.value].copy() if rc == 0 else None
+
     def compress(self, x):
         x = np.ascontiguousarray(x, dtype=np.int16)
         out = np.empty(int(self.lib.orc_svbzd_bound(x.size)) + 16, np.uint8)
