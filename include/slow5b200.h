@@ -102,6 +102,22 @@ int s5b_svbzd_decode_dev(s5b_ctx_t *ctx,
 int s5b_svbzd_peek_dev(s5b_ctx_t *ctx, const uint8_t *d_svb, const uint64_t *d_svb_off,
                        const uint32_t *d_svb_len, uint64_t n_reads, uint32_t *d_n_samples, void *stream);
 
+/* ex-zd signal codec (slow5_press.c:1236-1848): QTS shift + 16-bit zigzag-delta + one byte per value with an exception
+ * list.  Same slab contract as the svb-zd pair; d_out slots must hold s5b_exzd_bound(n) = 2n + 1024 bytes, the size of
+ * the reference's own working buffer (:1728) -- a read whose stream would not fit makes the reference abort
+ * (SLOW5_ASSERT) and gets S5B_ERR_PRESS here; an empty read (undefined in the reference) gets S5B_ERR_ARG.
+ * Replaces ptr_compress_ex_zd (:1778) / ptr_depress_ex_zd (:1824); bytes identical to the reference's. */
+uint64_t s5b_exzd_bound(uint32_t n_samples);
+uint64_t s5b_exzd_slot(uint32_t n_samples);
+int s5b_exzd_encode_dev(s5b_ctx_t *ctx, const int16_t *d_sig, const uint64_t *d_sig_off, const uint32_t *d_n_samples,
+                        uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off, uint32_t *d_out_len,
+                        int32_t *d_status, void *stream);
+/* d_n_samples[r] receives the header's sample count; S5B_ERR_PRESS for an unsupported version, sections that overrun
+ * the stream or do not consume their stated length (:1492-1500), exception positions outside the read. */
+int s5b_exzd_decode_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                        uint64_t in_capacity, uint64_t n_reads, int16_t *d_sig, const uint64_t *d_sig_off,
+                        uint32_t *d_n_samples, int32_t *d_status, void *stream);
+
 /* Replaces ptr_depress_zlib_solo (slow5_press.c:973-1010: inflateInit2(15) + inflate loop) for a batch of
  * independent zlib streams (one per record, slow5.c:4046).  Stream r = d_in[d_in_off[r] .. +d_in_len[r])
  * (any alignment; d_in base 16-byte aligned, in_capacity a multiple of 16); its output goes to the slot
@@ -170,7 +186,7 @@ int s5b_svbzd_decode_host(s5b_ctx_t *ctx,
 
 /* Pointer-array form, the exact shape of db_t / slow5_batch_t: n buffers in, n malloc()'d buffers
  * out (caller free()s each), NULL + out_n[i]=0 for a failed record.  `method` is a
- * S5B_COMPRESS_* value; SVB_ZD and ZLIB are accelerated, NONE is a copy. */
+ * S5B_COMPRESS_* value (NONE is a copy; ZLIB, SVB_ZD, ZSTD and EX_ZD run on the GPU). */
 int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
                             size_t n, void **out_ptrs, size_t *out_n);
 int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,

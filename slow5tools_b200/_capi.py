@@ -63,6 +63,10 @@ _SIGS = {
     "s5b_svbzd_encode_dev": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "s5b_svbzd_decode_dev": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "s5b_svbzd_peek_dev": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "s5b_exzd_bound": (_u64, [_u32]),
+    "s5b_exzd_slot": (_u64, [_u32]),
+    "s5b_exzd_encode_dev": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "s5b_exzd_decode_dev": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "s5b_compact_dev": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp]),
     "s5b_svbzd_encode_host": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "s5b_svbzd_decode_host": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),

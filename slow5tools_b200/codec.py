@@ -96,6 +96,17 @@ class Codec:
         self._check(lib.s5b_svbzd_peek_dev(self._h, _ptr(svb), _ptr(svb_off), _ptr(svb_len), svb_len.numel(),
                                            _ptr(n_samples), self._stream()), "s5b_svbzd_peek_dev")
 
+    def exzd_encode_dev(self, sig, sig_off, n_samples, out, out_off, out_len, status):
+        self._check(lib.s5b_exzd_encode_dev(self._h, _ptr(sig), _ptr(sig_off), _ptr(n_samples), n_samples.numel(),
+                                            _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status), self._stream()),
+                    "s5b_exzd_encode_dev")
+
+    def exzd_decode_dev(self, din, in_off, in_len, sig, sig_off, n_samples, status):
+        self._check(lib.s5b_exzd_decode_dev(self._h, _ptr(din), _ptr(in_off), _ptr(in_len), din.numel(),
+                                            in_len.numel(), _ptr(sig), _ptr(sig_off), _ptr(n_samples), _ptr(status),
+                                            self._stream()),
+                    "s5b_exzd_decode_dev")
+
     def zlib_inflate_dev(self, zin, in_off, in_len, out, out_off, out_len, status):
         self._check(lib.s5b_zlib_inflate_dev(self._h, _ptr(zin), _ptr(in_off), _ptr(in_len), zin.numel(),
                                              in_len.numel(), _ptr(out), _ptr(out_off), _ptr(out_len), _ptr(status),

@@ -78,7 +78,7 @@ struct PipeSlot {
 struct s5b_ctx {
     int device = 0;
     int num_sms = 0;
-    int enc_bps = 0, dec_bps = 0, inf_bps = 0, def_bps = 0, zd_bps = 0, ze_bps = 0;
+    int enc_bps = 0, dec_bps = 0, inf_bps = 0, def_bps = 0, zd_bps = 0, ze_bps = 0, xe_bps = 0, xd_bps = 0;
     DevBuf zd_scratch;
     cudaStream_t stream = nullptr;  // default stream for *_dev calls
     unsigned long long *d_counter = nullptr;
@@ -175,7 +175,9 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
     ctx->def_bps = deflate_blocks_per_sm();
     ctx->zd_bps = zstd_decode_blocks_per_sm();
     ctx->ze_bps = zstd_encode_blocks_per_sm();
-    if (ctx->enc_bps <= 0 || ctx->dec_bps <= 0 || ctx->inf_bps <= 0 || ctx->def_bps <= 0 || ctx->zd_bps <= 0 ||
+    ctx->xe_bps = exzd_encode_blocks_per_sm();
+    ctx->xd_bps = exzd_decode_blocks_per_sm();
+    if (ctx->xe_bps <= 0 || ctx->xd_bps <= 0 || ctx->enc_bps <= 0 || ctx->dec_bps <= 0 || ctx->inf_bps <= 0 || ctx->def_bps <= 0 || ctx->zd_bps <= 0 ||
         ctx->ze_bps <= 0) {  // no sm_100a image for this device
         (void)cudaGetLastError();
         delete ctx;
@@ -276,6 +278,40 @@ int s5b_svbzd_peek_dev(s5b_ctx_t *ctx, const uint8_t *d_svb, const uint64_t *d_s
     DeviceGuard g(ctx->device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     CU(launch_svbzd_peek(d_svb, d_svb_off, d_svb_len, n_reads, d_n_samples, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+uint64_t s5b_exzd_bound(uint32_t n) { return exzd_bound(n); }
+uint64_t s5b_exzd_slot(uint32_t n) { return round_up(exzd_bound(n), 16); }
+
+int s5b_exzd_encode_dev(s5b_ctx_t *ctx, const int16_t *d_sig, const uint64_t *d_sig_off, const uint32_t *d_n_samples,
+                        uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off, uint32_t *d_out_len,
+                        int32_t *d_status, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_sig || !d_sig_off || !d_n_samples || !d_out || !d_out_off || !d_out_len || !d_status) return S5B_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_sig) & 15u) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    SvbEncodeArgs a{d_sig, d_sig_off, d_n_samples, n_reads, d_out, d_out_off, d_out_len, d_status, ctx->d_counter + 24};
+    CU(launch_exzd_encode(a, ctx->num_sms, ctx->xe_bps, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
+int s5b_exzd_decode_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                        uint64_t in_capacity, uint64_t n_reads, int16_t *d_sig, const uint64_t *d_sig_off,
+                        uint32_t *d_n_samples, int32_t *d_status, void *stream) {
+    if (!ctx) return S5B_ERR_ARG;
+    if (n_reads == 0) return S5B_OK;
+    if (!d_in || !d_in_off || !d_in_len || !d_sig || !d_sig_off || !d_n_samples || !d_status) return S5B_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(d_sig) & 15u) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    SvbDecodeArgs a{d_in, d_in_off, d_in_len, in_capacity, n_reads, d_sig, d_sig_off, d_n_samples, d_status,
+                    ctx->d_counter + 28};
+    CU(launch_exzd_decode(a, ctx->num_sms, ctx->xd_bps, st));
     ctx->launches += 1;
     return S5B_OK;
 }
@@ -705,6 +741,94 @@ static int svbzd_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const siz
     return first;
 }
 
+// ex-zd: one shot (H2D, kernel, D2H) on slot 0's stream; the stream header carries the sample count (:1790-1793)
+static int exzd_ptrs(s5b_ctx_t *ctx, bool compress, const void *const *ptrs, const size_t *counts, size_t n,
+                     void **out_ptrs, size_t *out_n) {
+    std::vector<uint64_t> in_off(n + 1), out_off(n + 1);
+    std::vector<uint32_t> in_len(n);
+    uint64_t in_tot = 0, out_tot = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (!ptrs[i] && counts[i]) return S5B_ERR_ARG;
+        in_off[i] = in_tot;
+        out_off[i] = out_tot;
+        if (compress) {
+            if (counts[i] / 2 > 0xffffffffull) return S5B_ERR_ARG;
+            in_len[i] = (uint32_t)(counts[i] / 2);  // samples; count is BYTES (:1723)
+            in_tot += round_up(in_len[i], 8) * 2;
+            out_tot += s5b_exzd_slot(in_len[i]);
+        } else {
+            if (counts[i] > 0xffffffffull) return S5B_ERR_ARG;
+            in_len[i] = (uint32_t)counts[i];
+            in_tot += round_up(in_len[i], 16);
+            uint64_t nin = 0;
+            if (counts[i] >= 9) memcpy(&nin, static_cast<const uint8_t *>(ptrs[i]) + 1, 8);
+            if (nin > 0xffffffffull) nin = 0;  // the kernel reports the bad header
+            out_tot += round_up(nin, 8) * 2;
+        }
+    }
+    in_off[n] = in_tot;
+    out_off[n] = out_tot;
+    DeviceGuard g(ctx->device);
+    PipeSlot &s = ctx->slot[0];
+    CU(ctx->h_stage_in.reserve(in_tot + 16));
+    CU(ctx->h_stage_out.reserve(out_tot + 16));
+    uint8_t *hin = static_cast<uint8_t *>(ctx->h_stage_in.p);
+    for (size_t i = 0; i < n; ++i) memcpy(hin + in_off[i], ptrs[i], counts[i]);
+    // device meta: [in_off (n+1) u64][out_off (n+1) u64][in_len n u32][out_len n u32][status n i32]
+    const size_t meta_bytes = 2 * (n + 1) * 8 + 3 * n * 4;
+    CU(s.h_meta.reserve(meta_bytes));
+    CU(s.d_meta.reserve(meta_bytes));
+    CU(s.d_a.reserve(in_tot + 16));
+    CU(s.d_b.reserve(out_tot + 16));
+    uint64_t *m_in_off = static_cast<uint64_t *>(s.h_meta.p), *m_out_off = m_in_off + (n + 1);
+    uint32_t *m_in_len = reinterpret_cast<uint32_t *>(m_out_off + (n + 1)), *m_out_len = m_in_len + n;
+    int32_t *m_status = reinterpret_cast<int32_t *>(m_out_len + n);
+    for (size_t i = 0; i <= n; ++i) {
+        m_in_off[i] = compress ? in_off[i] / 2 : in_off[i];     // samples on the signal side
+        m_out_off[i] = compress ? out_off[i] : out_off[i] / 2;
+    }
+    for (size_t i = 0; i < n; ++i) m_in_len[i] = in_len[i];
+    uint8_t *dm = static_cast<uint8_t *>(s.d_meta.p);
+    uint64_t *d_in_off = reinterpret_cast<uint64_t *>(dm), *d_out_off = d_in_off + (n + 1);
+    uint32_t *d_in_len = reinterpret_cast<uint32_t *>(d_out_off + (n + 1)), *d_out_len = d_in_len + n;
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_out_len + n);
+    CU(cudaMemcpyAsync(dm, s.h_meta.p, 2 * (n + 1) * 8 + n * 4, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.d_a.p, hin, in_tot, cudaMemcpyHostToDevice, s.stream));
+    if (compress) {
+        SvbEncodeArgs a{static_cast<const int16_t *>(s.d_a.p), d_in_off, d_in_len, n, static_cast<uint8_t *>(s.d_b.p),
+                        d_out_off, d_out_len, d_status, s.d_counter};
+        CU(launch_exzd_encode(a, ctx->num_sms, ctx->xe_bps, s.stream));
+    } else {
+        SvbDecodeArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(in_tot, 16), n,
+                        static_cast<int16_t *>(s.d_b.p), d_out_off, d_out_len, d_status, s.d_counter};
+        CU(launch_exzd_decode(a, ctx->num_sms, ctx->xd_bps, s.stream));
+    }
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(ctx->h_stage_out.p, s.d_b.p, out_tot, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(m_out_len, d_out_len, 2 * n * 4, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    const uint8_t *hout = static_cast<const uint8_t *>(ctx->h_stage_out.p);
+    int first = S5B_OK;
+    for (size_t i = 0; i < n; ++i) {
+        out_ptrs[i] = nullptr;
+        out_n[i] = 0;
+        if (m_status[i] != S5B_OK) {
+            if (first == S5B_OK) first = m_status[i];
+            continue;
+        }
+        const size_t bytes = compress ? (size_t)m_out_len[i] : (size_t)m_out_len[i] * 2;  // decode reports samples
+        void *m = malloc(bytes ? bytes : 1);
+        if (!m) {
+            if (first == S5B_OK) first = S5B_ERR_MEM;
+            continue;
+        }
+        memcpy(m, hout + out_off[i], bytes);
+        out_ptrs[i] = m;
+        out_n[i] = bytes;
+    }
+    return first;
+}
+
 // zlib streams: the inflated size is not stored anywhere (slow5_press.c:985-1003 grows its buffer in 256 KiB
 // steps), so slots are sized from a guess and the (rare) streams that overflow are run again with the exact
 // size the first pass reported.
@@ -983,6 +1107,7 @@ int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs,
     switch (method) {
         case S5B_COMPRESS_NONE: return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_SVB_ZD: return svbzd_compress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        case S5B_COMPRESS_EX_ZD: return exzd_ptrs(ctx, true, ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_ZLIB:
         case S5B_COMPRESS_ZSTD: {
             DeviceGuard g(ctx->device);
@@ -1008,6 +1133,7 @@ int s5b_depress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, 
     switch (method) {
         case S5B_COMPRESS_NONE: return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_SVB_ZD: return svbzd_depress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
+        case S5B_COMPRESS_EX_ZD: return exzd_ptrs(ctx, false, ptrs, counts, n, out_ptrs, out_n);
         case S5B_COMPRESS_ZLIB: {
             DeviceGuard g(ctx->device);
             return zlib_depress_ptrs(ctx, ptrs, counts, n, out_ptrs, out_n);
