@@ -308,6 +308,41 @@ def run_ours(args):
                       "full_decode_reads_per_s": R / ((dec_ms_max + zsd_ms) * 1e-3)}
         del zbuf, svb2
 
+    # ---- extras: the ex-zd signal codec (slow5_press.c:1236-1848) on the same batch: encode, decode, round trip
+    xz = None
+    if not args.no_zlib:
+        xslot = int(s5.lib.s5b_exzd_slot(N))
+        xoff = torch.arange(R + 1, dtype=torch.int64, device="cuda") * xslot
+        xbuf = torch.zeros(R * xslot + 16, dtype=torch.uint8, device="cuda")
+        xlen = torch.zeros(R, dtype=torch.int32, device="cuda")
+        xst = torch.ones(R, dtype=torch.int32, device="cuda")
+        KX = max(2, min(K, 20))
+        for _ in range(2):
+            cdc.exzd_encode_dev(sig, soff, n, xbuf, xoff, xlen, xst)
+            cdc.exzd_decode_dev(xbuf, xoff, xlen, back, soff, n2, st_d)
+        barrier()
+        xev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KX)]
+        for k in range(KX):
+            xev[k][0].record()
+            cdc.exzd_encode_dev(sig, soff, n, xbuf, xoff, xlen, xst)
+            xev[k][1].record()
+            cdc.exzd_decode_dev(xbuf, xoff, xlen, back, soff, n2, st_d)
+            xev[k][2].record()
+        barrier()
+        xe_ms = sum(e[0].elapsed_time(e[1]) for e in xev) / KX
+        xd_ms = sum(e[1].elapsed_time(e[2]) for e in xev) / KX
+        assert int(xst.abs().sum()) == 0 and int(st_d.abs().sum()) == 0 and torch.equal(back, sig), "ex-zd round trip failed"
+        xbytes = int(xlen.sum())
+        xe_ms, xd_ms = max_over_ranks([xe_ms, xd_ms])
+        peak_x, _ = load_peaks()
+        xz = {"encode_ms": xe_ms, "decode_ms": xd_ms, "exzd_bytes_per_sample": xbytes / (R * N),
+              "encode_reads_per_s": R / (xe_ms * 1e-3), "decode_reads_per_s": R / (xd_ms * 1e-3),
+              "algorithmic_bytes_per_launch": R * N * 2 + xbytes,
+              "encode_frac_of_hbm_peak": (R * N * 2 + xbytes) / (xe_ms * 1e-3) / 1e9 / peak_x,
+              "decode_frac_of_hbm_peak": (R * N * 2 + xbytes) / (xd_ms * 1e-3) / 1e9 / peak_x,
+              "note": "encode reads the signal three times (q, sizes, emit); passes two and three come out of L2"}
+        del xbuf
+
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_only": True, "encode_ms": enc_ms_max, "decode_ms": dec_ms_max,
@@ -379,6 +414,7 @@ def run_ours(args):
                     "steps": KE, "api": "s5b_svbzd_encode_host + s5b_svbzd_decode_host (pinned host slabs)"},
             "gpu_launches": int(launches),
             "zlib_stage": zx,
+            "exzd_stage": xz,
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)

@@ -87,8 +87,8 @@ int s5b_hdr_copy(s5b_file_t *dst, const s5b_file_t *src) {
 int s5b_set_press(s5b_file_t *f, int rec_press, int sig_press) {
     if (!f || !f->writing || f->hdr_written) return fail(S5B_ERR_ARG);
     if ((rec_press != PRESS_NONE && rec_press != PRESS_ZLIB && rec_press != PRESS_ZSTD) ||
-        (sig_press != PRESS_NONE && sig_press != PRESS_SVB_ZD))
-        return fail(S5B_ERR_ARG);  // ex-zd: not in this build
+        (sig_press != PRESS_NONE && sig_press != PRESS_SVB_ZD && sig_press != PRESS_EX_ZD))
+        return fail(S5B_ERR_ARG);
     f->rec_press = rec_press;
     f->sig_press = sig_press;
     return 0;
@@ -177,12 +177,12 @@ int s5b_decode_batch(s5b_file_t *f, char **mems, size_t *bytes, size_t n, s5b_re
             return fail(S5B_ERR_RECPARSE);
     std::vector<void *> sig(n, nullptr);
     std::vector<size_t> sig_n(n, 0);
-    if (h.signal_method == PRESS_SVB_ZD) {
+    if (h.signal_method == PRESS_SVB_ZD || h.signal_method == PRESS_EX_ZD) {  // PRESS_* == S5B_COMPRESS_*
         for (size_t i = 0; i < n; ++i) {
             ptrs[i] = rec[i].sig_bytes;
             counts[i] = rec[i].sig_nbytes;
         }
-        const int rc = s5b_depress_batch_host(f->gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, sig.data(), sig_n.data());
+        const int rc = s5b_depress_batch_host(f->gpu, h.signal_method, ptrs.data(), counts.data(), n, sig.data(), sig_n.data());
         if (rc != S5B_OK) {
             for (void *p : sig) free(p);
             return fail(rc);
@@ -238,12 +238,12 @@ int s5b_encode_batch(s5b_file_t *f, s5b_rec_t **reads, size_t n, char **mems, si
     std::vector<size_t> counts(n);
     std::vector<void *> svb(n, nullptr);
     std::vector<size_t> svb_n(n, 0);
-    if (f->sig_press == PRESS_SVB_ZD) {
+    if (f->sig_press != PRESS_NONE) {
         for (size_t i = 0; i < n; ++i) {
             ptrs[i] = reads[i]->raw_signal;
             counts[i] = reads[i]->len_raw_signal * 2;
         }
-        const int rc = s5b_compress_batch_host(f->gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
+        const int rc = s5b_compress_batch_host(f->gpu, f->sig_press, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
         if (rc != S5B_OK) {
             for (void *p : svb) free(p);
             return fail(rc);
@@ -263,9 +263,9 @@ int s5b_encode_batch(s5b_file_t *f, s5b_rec_t **reads, size_t n, char **mems, si
         rec.aux_bytes = r->aux;
         rec.aux_nbytes = r->aux_len;
         uint64_t at = 0;
-        if (f->sig_press == PRESS_SVB_ZD) {
+        if (f->sig_press != PRESS_NONE) {
             record_to_binary(rec, static_cast<const uint8_t *>(svb[i]), svb_n[i], true, packed[i], &at);
-            splits[i] = (uint32_t)(at + 4 + (r->len_raw_signal + 3) / 4);
+            if (f->sig_press == PRESS_SVB_ZD) splits[i] = (uint32_t)(at + 4 + (r->len_raw_signal + 3) / 4);
             // destructive like the reference: the record now owns the compressed signal (slow5.c:3982-3984)
             free(r->raw_signal);
             r->raw_signal = static_cast<int16_t *>(svb[i]);

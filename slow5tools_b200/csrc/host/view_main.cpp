@@ -70,7 +70,7 @@ void usage(FILE *f) {
             "    -K, --batchsize INT           number of records loaded to the memory at once [4096]\n"
             "    --from FORMAT                 specify input file format (slow5 or blow5)\n"
             "    -h, --help                    display this message and exit\n"
-            "REC_MTD: none, zlib, zstd      SIG_MTD: none, svb-zd      (ex-zd: not in this build)\n");
+            "REC_MTD: none, zlib, zstd      SIG_MTD: none, svb-zd, ex-zd\n");
 }
 
 struct Batch {
@@ -428,8 +428,8 @@ int view_main(int argc, char **argv) {
     }
     if (fmt_out == FMT_ASCII) rec_out = sig_out = PRESS_NONE;
     if ((rec_out != PRESS_NONE && rec_out != PRESS_ZLIB && rec_out != PRESS_ZSTD) ||
-        (sig_out != PRESS_NONE && sig_out != PRESS_SVB_ZD)) {
-        ERROR("%s", "this build supports record compression none/zlib/zstd and signal compression none/svb-zd only");
+        (sig_out != PRESS_NONE && sig_out != PRESS_SVB_ZD && sig_out != PRESS_EX_ZD)) {
+        ERROR("%s", "this build supports record compression none/zlib/zstd and signal compression none/svb-zd/ex-zd only");
         return 1;
     }
 
@@ -440,8 +440,8 @@ int view_main(int argc, char **argv) {
     }
     const Header &hdr = rd.hdr;
     if ((hdr.record_method != PRESS_NONE && hdr.record_method != PRESS_ZLIB && hdr.record_method != PRESS_ZSTD) ||
-        (hdr.signal_method != PRESS_NONE && hdr.signal_method != PRESS_SVB_ZD)) {
-        ERROR("%s", "input uses a compression method this build does not support (ex-zd, or zlib/zstd as signal method)");
+        (hdr.signal_method != PRESS_NONE && hdr.signal_method != PRESS_SVB_ZD && hdr.signal_method != PRESS_EX_ZD)) {
+        ERROR("%s", "input uses a compression method this build does not support (zlib/zstd as signal method)");
         return 1;
     }
     FILE *fout = stdout;
@@ -475,7 +475,9 @@ int view_main(int argc, char **argv) {
     Batch b;
     std::string err;
     bool eof = false;
-    if (rd.fmt == FMT_BINARY && fmt_out == FMT_BINARY && need_gpu && !getenv("S5B_VIEW_SLOW_PATH")) {
+    // (ex-zd signals go through the general path: host parse / pack around the batched GPU codec calls)
+    const bool exzd_involved = hdr.signal_method == PRESS_EX_ZD || sig_out == PRESS_EX_ZD;
+    if (rd.fmt == FMT_BINARY && fmt_out == FMT_BINARY && need_gpu && !exzd_involved && !getenv("S5B_VIEW_SLOW_PATH")) {
         // blow5 -> blow5: whole batches stay on the device (pinned chunk pipeline)
         ret = view_fast_binary(rd, fout, gpu, rec_out, sig_out, batch);
         eof = true;
@@ -550,14 +552,14 @@ int view_main(int argc, char **argv) {
         }
         // ---- signal decompression
         std::vector<const int16_t *> sig(n);
-        if (rd.fmt == FMT_BINARY && hdr.signal_method == PRESS_SVB_ZD) {
+        if (rd.fmt == FMT_BINARY && hdr.signal_method != PRESS_NONE) {  // PRESS_* == S5B_COMPRESS_* (slow5_press.h:61-67)
             for (size_t i = 0; i < n; ++i) {
                 ptrs[i] = b.rec[i].sig_bytes;
                 counts[i] = b.rec[i].sig_nbytes;
             }
             b.sig.assign(n, nullptr);
             b.sig_n.assign(n, 0);
-            const int rc = s5b_depress_batch_host(gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, b.sig.data(),
+            const int rc = s5b_depress_batch_host(gpu, hdr.signal_method, ptrs.data(), counts.data(), n, b.sig.data(),
                                                   b.sig_n.data());
             if (rc != S5B_OK) {
                 ERROR("signal decompression failed: %s", s5b_strerror(rc));
@@ -593,12 +595,12 @@ int view_main(int argc, char **argv) {
             std::vector<size_t> svb_n(n, 0);
             std::vector<const uint8_t *> store(n);
             std::vector<size_t> store_n(n);
-            if (sig_out == PRESS_SVB_ZD) {
+            if (sig_out != PRESS_NONE) {
                 for (size_t i = 0; i < n; ++i) {
                     ptrs[i] = sig[i];
                     counts[i] = b.rec[i].len_raw_signal * 2;
                 }
-                const int rc = s5b_compress_batch_host(gpu, S5B_COMPRESS_SVB_ZD, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
+                const int rc = s5b_compress_batch_host(gpu, sig_out, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
                 if (rc != S5B_OK) {
                     ERROR("signal compression failed: %s", s5b_strerror(rc));
                     ret = 1;

@@ -124,3 +124,36 @@ def test_low_level_file_api_roundtrip(tmp_path):
     back = tmp_path / "api.slow5"
     ours(str(out), "-o", str(back))
     assert filecmp.cmp(back, os.path.join(FIX, "zlib_svb-zd_multi_rg_v0.2.0.expected.slow5"), shallow=False)
+
+
+# ---- ex-zd signal compression (test/test_view.sh:102-163)
+def test_exzd_golden_to_slow5_matches_reference_golden(tmp_path):
+    out = tmp_path / "a.slow5"
+    ours(os.path.join(FIX, "exp_1_lossless_zlib_ex_zd.blow5"), "-o", str(out))        # test_view.sh:158-160
+    assert filecmp.cmp(out, os.path.join(FIX, "exp_1_lossless_v0.2.0.slow5"), shallow=False)
+
+
+@have_ref
+def test_exzd_files_byte_identical_without_zlib_and_read_by_the_reference(tmp_path):
+    src = os.path.join(FIX, "exp_1_lossless_zlib_svb_v0.2.0.blow5")
+    # ex-zd is deterministic: with uncompressed records our file must equal the reference's byte for byte
+    a, b = tmp_path / "ours.blow5", tmp_path / "ref.blow5"
+    ours(src, "-o", str(a), "-c", "none", "-s", "ex-zd")
+    ref(src, "-o", str(b), "-c", "none", "-s", "ex-zd")
+    assert filecmp.cmp(a, b, shallow=False)
+    # zlib records around ex-zd signals: the reference reads ours back to the golden text, and we read the reference's
+    mine = tmp_path / "mine.blow5"
+    ours(os.path.join(FIX, "exp_1_lossless.slow5"), "-o", str(mine), "-s", "ex-zd")   # test_view.sh:102-104 (bytes: zlib's)
+    t1, t2 = tmp_path / "t1.slow5", tmp_path / "t2.slow5"
+    ref(str(mine), "-o", str(t1))
+    assert filecmp.cmp(t1, os.path.join(FIX, "exp_1_lossless_v0.2.0.slow5"), shallow=False)
+    ours(str(b), "-o", str(t2))
+    assert filecmp.cmp(t2, os.path.join(FIX, "exp_1_lossless_v0.2.0.slow5"), shallow=False)
+    # ex-zd -> ex-zd and ex-zd -> svb-zd re-encodes (test_view.sh:161-163)
+    c = tmp_path / "c.blow5"
+    ours(os.path.join(FIX, "exp_1_lossless_zlib_ex_zd.blow5"), "-o", str(c), "-c", "none", "-s", "ex-zd")
+    assert filecmp.cmp(c, b, shallow=False)
+    d, e = tmp_path / "d.blow5", tmp_path / "e.blow5"
+    ours(os.path.join(FIX, "exp_1_lossless_zlib_ex_zd.blow5"), "-o", str(d), "-c", "none", "-s", "svb-zd")
+    ref(os.path.join(FIX, "exp_1_lossless_zlib_ex_zd.blow5"), "-o", str(e), "-c", "none", "-s", "svb-zd")
+    assert filecmp.cmp(d, e, shallow=False)
