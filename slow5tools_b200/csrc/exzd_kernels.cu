@@ -61,6 +61,7 @@ constexpr int XE_KWIN = 128;              // key-window bytes per svb section (5
 struct __align__(128) XeWarpSmem {
     uint8_t dbuf[XE_DB];
     uint32_t kwin[2][XE_KWIN / 4];  // [0] positions, [1] values
+    uint32_t list[256];             // this iteration's exceptions, in order: (value index << 16) | zd
 };
 
 // the lane's 8 samples of iteration `base` (values i = base + 8*lane + k), shifted right by q, plus the sample before them
@@ -197,7 +198,9 @@ __global__ void __launch_bounds__(XE_WARPS * 32) exzd_encode_kernel(const SvbEnc
         orv = __reduce_or_sync(FULL, orv);
         const uint32_t q = (orv & 31u) ? (uint32_t)(__ffs((int)(orv & 31u)) - 1) : 5u;
 
-        // ---- pass B: exception count, data bytes of the position / value sections
+        // ---- pass B: exception count, data bytes of the position / value sections.  Loop-free per lane: only a lane's
+        // first exception can be more than 255 values after its predecessor, and a value section entry takes two bytes
+        // exactly when zd > 511
         uint32_t cnt = 0, pd = 0, ed = 0;
         uint32_t zd0 = 0;
         {
@@ -207,16 +210,19 @@ __global__ void __launch_bounds__(XE_WARPS * 32) exzd_encode_kernel(const SvbEnc
                 const uint32_t base = it * 256;
                 const Samples s = load_samples(sig, base, n, q, lane, carry);
                 int prev = s.prev;
-                uint32_t f = 0;
-                uint32_t z[8];
+                uint32_t f = 0, g = 0;
+                uint32_t z0 = 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    z[k] = zz16(s.x[k] - prev);
+                    const uint32_t z = zz16(s.x[k] - prev);
                     prev = s.x[k];
+                    if (k == 0) z0 = z;
                     const uint32_t i = base + 8 * lane + k;
-                    if (i >= 1 && i < n && z[k] > 255u) f |= 1u << k;
+                    const bool valid = i >= 1 && i < n;
+                    if (valid && z > 255u) f |= 1u << k;
+                    if (valid && z > 511u) g |= 1u << k;
                 }
-                if (it == 0) zd0 = __shfl_sync(FULL, z[0], 0);
+                if (it == 0) zd0 = __shfl_sync(FULL, z0, 0);
                 const uint32_t B = __ballot_sync(FULL, f != 0);
                 if (B) {
                     const int p0 = (int)(base + 8 * lane) - 1;  // position of the lane's value k is p0 + k
@@ -224,15 +230,14 @@ __global__ void __launch_bounds__(XE_WARPS * 32) exzd_encode_kernel(const SvbEnc
                     const uint32_t lower = B & lt;
                     const int src = lower ? 31 - __clz((int)lower) : 0;
                     const int got = __shfl_sync(FULL, own_last, src);
-                    int pp = lower ? got : lastpos;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (f & (1u << k)) {
-                            ++cnt;
-                            pd += svb_bytes((uint32_t)(p0 + k - pp - 1));
-                            ed += svb_bytes(z[k] - 256u);
-                            pp = p0 + k;
-                        }
+                    const int pp = lower ? got : lastpos;
+                    if (f) {
+                        const uint32_t c = __popc(f);
+                        const int first = p0 + (__ffs((int)f) - 1);
+                        cnt += c;
+                        pd += c - 1 + svb_bytes((uint32_t)(first - pp - 1));
+                        ed += c + __popc(g);
+                    }
                     lastpos = __shfl_sync(FULL, own_last, 31 - __clz((int)B));
                 }
             }
@@ -309,63 +314,62 @@ __global__ void __launch_bounds__(XE_WARPS * 32) exzd_encode_kernel(const SvbEnc
                 const uint32_t B = __ballot_sync(FULL, f != 0);
                 uint32_t excl_cnt = 0, it_cnt = 0;
                 if (B) {
-                    const int p0 = (int)(base + 8 * lane) - 1;
-                    const int own_last = p0 + (31 - __clz((int)(f | 1u)));
-                    const uint32_t lower = B & lt;
-                    const int src = lower ? 31 - __clz((int)lower) : 0;
-                    const int got = __shfl_sync(FULL, own_last, src);
-                    int pp = lower ? got : lastpos;
-                    // per-lane sizes, then one packed exclusive scan: count (9 bits) | position bytes (11) | value bytes (10)
-                    uint32_t c = 0, lp = 0, le = 0;
+                    // compact the iteration's exceptions, in order, into a shared list: (value index << 16) | zd
+                    const uint32_t c = __popc(f);
+                    const uint32_t incl = scan_incl(c);
+                    excl_cnt = incl - c;
+                    it_cnt = __shfl_sync(FULL, incl, 31);
                     {
-                        int p2 = pp;
+                        uint32_t rk = excl_cnt;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (f & (1u << k)) {
-                                ++c;
-                                lp += svb_bytes((uint32_t)(p0 + k - p2 - 1));
-                                le += svb_bytes(z[k] - 256u);
-                                p2 = p0 + k;
-                            }
+                        for (int k = 0; k < 8; ++k) {
+                            if (f & (1u << k)) ws.list[rk] = ((8u * lane + k) << 16) | z[k];
+                            rk += (f >> k) & 1u;
+                        }
                     }
-                    const uint32_t packed = c | (lp << 9) | (le << 20);
-                    const uint32_t incl = scan_incl(packed);
-                    const uint32_t tot = __shfl_sync(FULL, incl, 31);
-                    const uint32_t excl = incl - packed;
-                    excl_cnt = excl & 0x1FFu;
                     // make room in the key windows for this iteration's (at most 256) exceptions
                     if (nex > 1 && R - wbase > 256u) keys_flush(ws, dst + o_keysP, dst + o_keysE, wbase, R, false, lane);
-                    uint32_t rk = R + excl_cnt;
-                    uint32_t op = PD + ((excl >> 9) & 0x7FFu);
-                    uint32_t oe = ED + (excl >> 20);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (f & (1u << k)) {
-                            const uint32_t dv = (uint32_t)(p0 + k - pp - 1);
-                            const uint32_t ev = z[k] - 256u;
-                            pp = p0 + k;
+                    __syncwarp();
+                    // one exception per lane: delta to the previous position, svb sizes, offsets by a packed scan
+                    for (uint32_t j0 = 0; j0 < it_cnt; j0 += 32) {
+                        const uint32_t j = j0 + lane;
+                        const bool act = j < it_cnt;
+                        const uint32_t e = act ? ws.list[j] : 0u;
+                        const int pos = (int)(base + (e >> 16)) - 1;
+                        int pp = lastpos;
+                        if (act && j) pp = (int)(base + (ws.list[j - 1] >> 16)) - 1;
+                        const uint32_t dv = (uint32_t)(pos - pp - 1);
+                        const uint32_t ev = (e & 0xFFFFu) - 256u;
+                        const uint32_t bd = act ? svb_bytes(dv) : 0u, be = act ? 1u + (ev > 0xFFu) : 0u;
+                        const uint32_t packed = bd | (be << 16);
+                        const uint32_t inc2 = scan_incl(packed);
+                        const uint32_t tot = __shfl_sync(FULL, inc2, 31);
+                        if (act) {
                             if (nex > 1) {
-                                const uint32_t bd = svb_bytes(dv), be = svb_bytes(ev);
-                                for (uint32_t b = 0; b < bd; ++b) dst[o_dataP + op + b] = (uint8_t)(dv >> (8 * b));
-                                for (uint32_t b = 0; b < be; ++b) dst[o_dataE + oe + b] = (uint8_t)(ev >> (8 * b));
-                                op += bd;
-                                oe += be;
-                                const uint32_t slot = rk - wbase;  // 2-bit slot inside the windows
+                                uint8_t *gp = dst + o_dataP + PD + ((inc2 - packed) & 0xFFFFu);
+                                uint8_t *ge = dst + o_dataE + ED + ((inc2 - packed) >> 16);
+                                gp[0] = (uint8_t)dv;
+                                if (bd > 1) gp[1] = (uint8_t)(dv >> 8);
+                                if (bd > 2) gp[2] = (uint8_t)(dv >> 16);
+                                if (bd > 3) gp[3] = (uint8_t)(dv >> 24);
+                                ge[0] = (uint8_t)ev;
+                                if (be > 1) ge[1] = (uint8_t)(ev >> 8);
+                                const uint32_t slot = R + j - wbase;  // 2-bit slot inside the windows
                                 atomicOr(&ws.kwin[0][slot >> 4], (bd - 1) << (2 * (slot & 15u)));
                                 atomicOr(&ws.kwin[1][slot >> 4], (be - 1) << (2 * (slot & 15u)));
                             } else {  // a single exception is stored raw (:1405-1411)
-                                for (int b = 0; b < 4; ++b) {
-                                    dst[16 + b] = (uint8_t)(dv >> (8 * b));
-                                    dst[20 + b] = (uint8_t)(ev >> (8 * b));
+                                for (int b2 = 0; b2 < 4; ++b2) {
+                                    dst[16 + b2] = (uint8_t)(dv >> (8 * b2));
+                                    dst[20 + b2] = (uint8_t)(ev >> (8 * b2));
                                 }
                             }
-                            ++rk;
                         }
-                    it_cnt = tot & 0x1FFu;
+                        PD += tot & 0xFFFFu;
+                        ED += tot >> 16;
+                    }
+                    lastpos = (int)(base + (ws.list[it_cnt - 1] >> 16)) - 1;
                     R += it_cnt;
-                    PD += (tot >> 9) & 0x7FFu;
-                    ED += tot >> 20;
-                    lastpos = __shfl_sync(FULL, own_last, 31 - __clz((int)B));
+                    __syncwarp();
                 }
                 // byte stream: the lane's non-exception values, in order
                 {
