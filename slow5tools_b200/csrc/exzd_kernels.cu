@@ -27,11 +27,16 @@
 namespace s5b {
 namespace {
 
+// inclusive warp scan; shfl.up's predicate says whether the source lane exists, so each step is SHFL + one predicated add
 __device__ __forceinline__ uint32_t scan_incl(uint32_t v) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, v, d);
-        if ((int)(threadIdx.x & 31) >= d) v += t;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t"
+            "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+            "@p add.u32 %0, %0, t;\n\t}"
+            : "+r"(v)
+            : "r"(d));
     }
     return v;
 }
@@ -69,12 +74,14 @@ struct Samples {
     int x[8];
     int prev;
 };
-__device__ __forceinline__ Samples load_samples(const int16_t *sig, uint32_t base, uint32_t n, uint32_t q, int lane,
-                                                int &carry) {
-    Samples s;
-    const uint32_t i0 = base + 8 * lane;
+__device__ __forceinline__ uint4 load_raw(const int16_t *sig, uint32_t it, uint32_t n, int lane) {
+    const uint32_t i0 = it * 256 + 8 * lane;
     uint4 w = make_uint4(0, 0, 0, 0);
     if (i0 < n) w = __ldg(reinterpret_cast<const uint4 *>(sig + i0));  // slots are padded to 8 samples
+    return w;
+}
+__device__ __forceinline__ Samples shift_samples(const uint4 w, uint32_t q, int lane, int &carry) {
+    Samples s;
     const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -85,6 +92,72 @@ __device__ __forceinline__ Samples load_samples(const int16_t *sig, uint32_t bas
     s.prev = lane ? up : carry;
     carry = __shfl_sync(FULL, s.x[7], 31);
     return s;
+}
+
+// Size pass of the encoder: exception count and the data bytes of the position / value sections for a given q, plus
+// zd[0] and the OR of all samples.  Loop-free per lane: only a lane's first exception can be more than 255 values after
+// its predecessor, and a value-section entry takes two bytes exactly when zd > 511.
+struct Sizes {
+    uint32_t nex, pdt, edt, zd0, orv;
+};
+__device__ __forceinline__ Sizes size_pass(const int16_t *sig, const uint32_t n, const uint32_t iters, const uint32_t q,
+                                           const int lane, const uint32_t lt) {
+    uint32_t cnt = 0, pd = 0, ed = 0, zd0 = 0, orv = 0;
+    int carry = 0;
+    int lastpos = -1;  // warp-uniform: position (index into zd[1..]) of the last exception so far
+    uint4 w = load_raw(sig, 0, n, lane);
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint4 wn = it + 1 < iters ? load_raw(sig, it + 1, n, lane) : make_uint4(0, 0, 0, 0);
+        const uint32_t base = it * 256;
+        const uint32_t i0 = base + 8 * lane;
+        if (i0 + 8 <= n) {
+            orv |= w.x | w.y | w.z | w.w;
+        } else {
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (i0 + k < n) orv |= (ww[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+        }
+        const Samples s = shift_samples(w, q, lane, carry);
+        w = wn;
+        int prev = s.prev;
+        uint32_t f = 0, g = 0, z0 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t z = zz16(s.x[k] - prev);
+            prev = s.x[k];
+            if (k == 0) z0 = z;
+            const uint32_t i = i0 + k;
+            const bool valid = i >= 1 && i < n;
+            if (valid && z > 255u) f |= 1u << k;
+            if (valid && z > 511u) g |= 1u << k;
+        }
+        if (it == 0) zd0 = __shfl_sync(FULL, z0, 0);
+        const uint32_t B = __ballot_sync(FULL, f != 0);
+        if (B) {
+            const int p0 = (int)i0 - 1;  // position of the lane's value k is p0 + k
+            const int own_last = p0 + (31 - __clz((int)(f | 1u)));
+            const uint32_t lower = B & lt;
+            const int src = lower ? 31 - __clz((int)lower) : 0;
+            const int got = __shfl_sync(FULL, own_last, src);
+            const int pp = lower ? got : lastpos;
+            if (f) {
+                const uint32_t c = __popc(f);
+                const int first = p0 + (__ffs((int)f) - 1);
+                cnt += c;
+                pd += c - 1 + svb_bytes((uint32_t)(first - pp - 1));
+                ed += c + __popc(g);
+            }
+            lastpos = __shfl_sync(FULL, own_last, 31 - __clz((int)B));
+        }
+    }
+    Sizes r;
+    r.nex = __reduce_add_sync(FULL, cnt);
+    r.pdt = __reduce_add_sync(FULL, pd);
+    r.edt = __reduce_add_sync(FULL, ed);
+    r.zd0 = zd0;
+    r.orv = __reduce_or_sync(FULL, (orv | (orv >> 16)) & 0xFFFFu);
+    return r;
 }
 
 // ---- byte-stream output through shared memory (same scheme as the svb-zd encoder's data stream)
@@ -155,7 +228,7 @@ __device__ __forceinline__ void keys_flush(XeWarpSmem &ws, uint8_t *keys_p, uint
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(XE_WARPS * 32) exzd_encode_kernel(const SvbEncodeArgs a) {
+__global__ void __launch_bounds__(XE_WARPS * 32, 4) exzd_encode_kernel(const SvbEncodeArgs a) {
     __shared__ XeWarpSmem smem[XE_WARPS];
     const int lane = threadIdx.x & 31;
     XeWarpSmem &ws = smem[threadIdx.x >> 5];
@@ -183,68 +256,13 @@ __global__ void __launch_bounds__(XE_WARPS * 32) exzd_encode_kernel(const SvbEnc
         uint8_t *dst = a.svb + ooff;
         const uint32_t iters = (n + 255) >> 8;
 
-        // ---- pass A: q = shared low zero bits, at most 5 (find_qts, :1675-1698)
-        uint32_t orv = 0;
-        for (uint32_t it = 0; it < iters; ++it) {
-            const uint32_t i0 = it * 256 + 8 * lane;
-            if (i0 < n) {
-                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(sig + i0));
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (i0 + k < n) orv |= (ww[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            }
-        }
-        orv = __reduce_or_sync(FULL, orv);
-        const uint32_t q = (orv & 31u) ? (uint32_t)(__ffs((int)(orv & 31u)) - 1) : 5u;
-
-        // ---- pass B: exception count, data bytes of the position / value sections.  Loop-free per lane: only a lane's
-        // first exception can be more than 255 values after its predecessor, and a value section entry takes two bytes
-        // exactly when zd > 511
-        uint32_t cnt = 0, pd = 0, ed = 0;
-        uint32_t zd0 = 0;
-        {
-            int carry = 0;
-            int lastpos = -1;  // warp-uniform: position (index into zd[1..]) of the last exception so far
-            for (uint32_t it = 0; it < iters; ++it) {
-                const uint32_t base = it * 256;
-                const Samples s = load_samples(sig, base, n, q, lane, carry);
-                int prev = s.prev;
-                uint32_t f = 0, g = 0;
-                uint32_t z0 = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t z = zz16(s.x[k] - prev);
-                    prev = s.x[k];
-                    if (k == 0) z0 = z;
-                    const uint32_t i = base + 8 * lane + k;
-                    const bool valid = i >= 1 && i < n;
-                    if (valid && z > 255u) f |= 1u << k;
-                    if (valid && z > 511u) g |= 1u << k;
-                }
-                if (it == 0) zd0 = __shfl_sync(FULL, z0, 0);
-                const uint32_t B = __ballot_sync(FULL, f != 0);
-                if (B) {
-                    const int p0 = (int)(base + 8 * lane) - 1;  // position of the lane's value k is p0 + k
-                    const int own_last = p0 + (31 - __clz((int)(f | 1u)));
-                    const uint32_t lower = B & lt;
-                    const int src = lower ? 31 - __clz((int)lower) : 0;
-                    const int got = __shfl_sync(FULL, own_last, src);
-                    const int pp = lower ? got : lastpos;
-                    if (f) {
-                        const uint32_t c = __popc(f);
-                        const int first = p0 + (__ffs((int)f) - 1);
-                        cnt += c;
-                        pd += c - 1 + svb_bytes((uint32_t)(first - pp - 1));
-                        ed += c + __popc(g);
-                    }
-                    lastpos = __shfl_sync(FULL, own_last, 31 - __clz((int)B));
-                }
-            }
-        }
-        const uint32_t nex = __reduce_add_sync(FULL, cnt);
-        const uint32_t pdt = __reduce_add_sync(FULL, pd);
-        const uint32_t edt = __reduce_add_sync(FULL, ed);
+        // ---- passes A + B: q = shared low zero bits, at most 5 (find_qts, :1675-1698), and the section sizes.  The size
+        // pass runs speculatively with q = 0 (one odd sample makes it so) while OR-ing the samples; only reads whose
+        // samples share low zero bits -- lossy "degrade"d data -- pay a second size pass with their real q
+        Sizes sz = size_pass(sig, n, iters, 0, lane, lt);
+        const uint32_t q = (sz.orv & 31u) ? (uint32_t)(__ffs((int)(sz.orv & 31u)) - 1) : 5u;
+        if (q) sz = size_pass(sig, n, iters, q, lane, lt);
+        const uint32_t nex = sz.nex, pdt = sz.pdt, edt = sz.edt, zd0 = sz.zd0;
         const uint32_t nkeys = (nex + 3) >> 2;
         // section offsets
         uint64_t o_keysP = 16, o_dataP = 16, o_keysE = 16, o_dataE = 16, o_bytes = 16;
@@ -297,7 +315,7 @@ __global__ void __launch_bounds__(XE_WARPS * 32) exzd_encode_kernel(const SvbEnc
             uint32_t wbase = 0;              // first rank covered by the key windows
             for (uint32_t it = 0; it < iters; ++it) {
                 const uint32_t base = it * 256;
-                const Samples s = load_samples(sig, base, n, q, lane, carry);
+                const Samples s = shift_samples(load_raw(sig, it, n, lane), q, lane, carry);
                 int prev = s.prev;
                 uint32_t f = 0, vmask = 0;
                 uint32_t z[8];
@@ -591,6 +609,21 @@ __global__ void __launch_bounds__(XD_WARPS * 32) exzd_decode_kernel(const SvbDec
             const uint32_t hi = min(base + 256u, n);
             const uint32_t i0 = min(max(base + 8u * lane, lo), hi);
             const uint8_t *bp = bytes + bytes_done + (i0 - lo) - excl_cnt;
+            // the lane's (at most 8) stream bytes: three aligned word loads realigned into a 64-bit window; the last
+            // lanes of a slab, where the words would run past it, read byte by byte
+            uint64_t win = 0;
+            {
+                const uint8_t *wa = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(bp) & ~uintptr_t(3));
+                if (wa + 12 <= a.svb + a.svb_capacity) {
+                    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(wa);
+                    const uint32_t w0 = __ldg(w32), w1 = __ldg(w32 + 1), w2 = __ldg(w32 + 2);
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(bp) & 3u) * 8;
+                    win = (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+                } else {
+                    const uint32_t need = __popc(~f & 0xFFu);
+                    for (uint32_t t = 0; t < need && bp + t < p + ilen; ++t) win |= (uint64_t)bp[t] << (8 * t);
+                }
+            }
             // ---- values, zigzag decode, running sum (unzigdelta_u16_16 :1635-1645), QTS shift back (:1713-1718)
             uint32_t sum[8];
             uint32_t run = 0;
@@ -601,7 +634,10 @@ __global__ void __launch_bounds__(XD_WARPS * 32) exzd_decode_kernel(const SvbDec
                 if (i < n) {
                     if (i == 0) z = zd0;
                     else if (f & (1u << k)) z = ws.ztmp[8 * lane + k];
-                    else z = __ldg(bp++);
+                    else {
+                        z = (uint32_t)win & 0xFFu;
+                        win >>= 8;
+                    }
                 }
                 run += (uint32_t)unzz16(z);
                 sum[k] = run;
@@ -626,6 +662,11 @@ __global__ void __launch_bounds__(XD_WARPS * 32) exzd_decode_kernel(const SvbDec
                     if (i8 + k < n) out[i8 + k] = (int16_t)(uint16_t)(((sum[k] + basev) << q) & 0xFFFFu);
             }
             bytes_done += (hi > lo ? hi - lo : 0u) - it_cnt;
+            {   // the byte stream is consumed front to back, at most 256 bytes per iteration: pull the lines two iterations
+                // ahead towards the SM so the dependent loads above do not wait on DRAM
+                const uint8_t *pf = bytes + bytes_done + 256 + 16 * lane;
+                if (pf < p + ilen) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+            }
             __syncwarp();
         }
         // every exception used, both svb sections consumed exactly (the reference compares the decoder's byte count with
