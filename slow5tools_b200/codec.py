@@ -169,6 +169,28 @@ class Codec:
                 res.append(None)
         return rc, res
 
+    def blow5_recode(self, in_rec, in_sig, out_rec, out_sig, records):
+        """s5b_blow5_recode_host on a list of packed records (bytes, as stored in the file without their size prefix).
+        Returns (rc, file image bytes: [u64 size][record] per record)."""
+        n = len(records)
+        rec_len = np.array([len(r) for r in records], np.uint32)
+        rec_off = np.zeros(n + 1, np.uint64)
+        np.cumsum((rec_len.astype(np.uint64) + np.uint64(15)) // np.uint64(16) * np.uint64(16), out=rec_off[1:])
+        h_in = np.zeros(int(rec_off[-1]) + 16, np.uint8)
+        for r, o in zip(records, rec_off):
+            h_in[int(o):int(o) + len(r)] = np.frombuffer(r, np.uint8)
+        cap = int(rec_len.sum()) * 4 + 64 * n + 4096
+        for _ in range(2):
+            h_out = np.zeros(cap, np.uint8)
+            nb = C.c_uint64()
+            rc = lib.s5b_blow5_recode_host(self._h, in_rec, in_sig, out_rec, out_sig, h_in.ctypes.data, h_in.size,
+                                           rec_off.ctypes.data, rec_len.ctypes.data, n, h_out.ctypes.data, cap, C.byref(nb))
+            if rc == _capi.ERR.NOSPACE and nb.value > cap:
+                cap = int(nb.value) + 16
+                continue
+            break
+        return rc, h_out[:nb.value].tobytes() if rc == 0 else None
+
     def compress_batch(self, method, bufs):
         return self._batch(lib.s5b_compress_batch_host, method, bufs)
 

@@ -87,7 +87,7 @@ struct s5b_ctx {
     PinBuf h_stage_in, h_stage_out;  // pointer-array forms
     DevBuf r_in, r_infl, r_sig, r_svb, r_packed, r_z, r_img, r_meta, r_scratch;  // s5b_blow5_recode_host
     uint64_t launches = 0;
-    size_t chunk_bytes = 64u << 20;
+    size_t chunk_bytes = 32u << 20;  // e2e is flat between 16 and 128 MiB (PCIe bound), 32 MiB marginally best
     std::string last_cuda_error;
 };
 
