@@ -176,7 +176,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # rank 0 prints exactly one JSON line on stdout: NCCL's version banner / debug lines go to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "WARN", "VERSION"):
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
