@@ -82,6 +82,49 @@ enum : uint32_t { EV_FLUSH = 1, EV_MATCH = 2, EV_TABLES = 3, EV_END = 4 };
 enum : int32_t { END_OK = 0, END_TRUNC = 1, END_ERR = 2 };
 
 // ---- input side (lane 0 only) ----------------------------------------------------------------
+struct RingState {
+    uint32_t issued, waited, phase_bits;
+};
+// issue bulk copies for every ring block that is free: blocks [issued, min(nblk, done + INF_NB))
+__device__ __noinline__ uint32_t ring_issue(uint32_t bar0, uint32_t ring0, const uint8_t *src16, uint64_t lim, uint32_t nblk,
+                                            uint32_t done, uint32_t issued) {
+    while (issued < nblk && issued < done + INF_NB) {
+        const uint32_t slot = issued % INF_NB;
+        const uint64_t b0 = (uint64_t)issued * INF_BLK;
+        uint64_t bytes = lim - b0;
+        if (bytes > INF_BLK) bytes = INF_BLK;
+        mbar_arrive_expect_tx(bar0 + 8 * slot, (uint32_t)bytes);
+        bulk_g2s(ring0 + slot * INF_BLK, src16 + b0, (uint32_t)bytes, bar0 + 8 * slot);
+        ++issued;
+    }
+    return issued;
+}
+// wait until `need` blocks have landed (issuing into free blocks first, as the waits advance)
+__device__ __noinline__ RingState ring_wait(uint32_t bar0, uint32_t ring0, const uint8_t *src16, uint64_t lim, uint32_t nblk,
+                                            uint32_t done, uint32_t issued, uint32_t waited, uint32_t phase_bits,
+                                            uint32_t need) {
+    while (waited < need) {
+        while (issued < nblk && issued < done + INF_NB) {
+            const uint32_t slot = issued % INF_NB;
+            const uint64_t b0 = (uint64_t)issued * INF_BLK;
+            uint64_t bytes = lim - b0;
+            if (bytes > INF_BLK) bytes = INF_BLK;
+            mbar_arrive_expect_tx(bar0 + 8 * slot, (uint32_t)bytes);
+            bulk_g2s(ring0 + slot * INF_BLK, src16 + b0, (uint32_t)bytes, bar0 + 8 * slot);
+            ++issued;
+        }
+        const uint32_t slot = waited % INF_NB;
+        mbar_wait(bar0 + 8 * slot, (phase_bits >> slot) & 1u);
+        phase_bits ^= 1u << slot;
+        ++waited;
+    }
+    RingState r;
+    r.issued = issued;
+    r.waited = waited;
+    r.phase_bits = phase_bits;
+    return r;
+}
+
 struct BitReader {
     const uint8_t *ring;     // smem
     const uint8_t *p0;       // first byte of the stream (global)
@@ -98,29 +141,23 @@ struct BitReader {
     uint64_t bb;
     uint32_t nb;
 
-    __device__ __forceinline__ void issue_block() {
-        const uint32_t slot = issued % INF_NB;
-        const uint64_t b0 = (uint64_t)issued * INF_BLK;
-        uint64_t bytes = lim - b0;
-        if (bytes > INF_BLK) bytes = INF_BLK;
-        mbar_arrive_expect_tx(bar0 + 8 * slot, (uint32_t)bytes);
-        bulk_g2s(ring0 + slot * INF_BLK, src16 + b0, (uint32_t)bytes, bar0 + 8 * slot);
-        ++issued;
-    }
+    // The ring maintenance (issue bulk copies into free blocks, wait for a block) lives in two out-of-line functions:
+    // refill() is inlined at every symbol-decoding site, and carrying the TMA issue sequence along made the kernel
+    // ~200 KB of code (instruction-fetch stalls were the largest stall reason).  State goes in and out by value so
+    // the reader itself stays in registers.
     // a ring block may only be overwritten once every byte of it has been moved into bb
     __device__ __forceinline__ void recycle() {
         const uint32_t done = (skew + ipos) / INF_BLK;
-        while (issued < nblk && issued < done + INF_NB) issue_block();
+        if (issued < nblk && issued < done + INF_NB) issued = ring_issue(bar0, ring0, src16, lim, nblk, done, issued);
     }
     // make ring position rp readable
     __device__ __forceinline__ void ensure(uint32_t rp) {
         const uint32_t need = rp / INF_BLK + 1;
-        while (waited < need) {
-            recycle();
-            const uint32_t slot = waited % INF_NB;
-            mbar_wait(bar0 + 8 * slot, (phase_bits >> slot) & 1u);
-            phase_bits ^= 1u << slot;
-            ++waited;
+        if (waited < need) {
+            const RingState r = ring_wait(bar0, ring0, src16, lim, nblk, (skew + ipos) / INF_BLK, issued, waited, phase_bits, need);
+            issued = r.issued;
+            waited = r.waited;
+            phase_bits = r.phase_bits;
         }
     }
     __device__ __forceinline__ void refill() {
