@@ -202,7 +202,7 @@ int s5b_compress_records_host(s5b_ctx_t *ctx, int method, const void *const *ptr
  * blow5 -> blow5 conversions.  h_in holds n packed records exactly as stored in the file (record i =
  * h_in[rec_off[i] .. +rec_len[i]), size prefixes excluded), compressed with (in_rec, in_sig); h_out receives the
  * output FILE IMAGE -- [u64 size][record bytes] per record, in order -- compressed with (out_rec, out_sig), ready
- * for one fwrite.  Methods: S5B_COMPRESS_NONE / ZLIB / ZSTD for records, NONE / SVB_ZD for signals.  Pinned h_in / h_out
+ * for one fwrite.  Methods: S5B_COMPRESS_NONE / ZLIB / ZSTD for records, NONE / SVB_ZD / EX_ZD for signals.  Pinned h_in / h_out
  * (s5b_host_alloc) avoid staging copies.  Returns 0, the first per-record error, or S5B_ERR_NOSPACE with *out_bytes =
  * bytes needed when out_cap is too small. */
 int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,

@@ -475,9 +475,7 @@ int view_main(int argc, char **argv) {
     Batch b;
     std::string err;
     bool eof = false;
-    // (ex-zd signals go through the general path: host parse / pack around the batched GPU codec calls)
-    const bool exzd_involved = hdr.signal_method == PRESS_EX_ZD || sig_out == PRESS_EX_ZD;
-    if (rd.fmt == FMT_BINARY && fmt_out == FMT_BINARY && need_gpu && !exzd_involved && !getenv("S5B_VIEW_SLOW_PATH")) {
+    if (rd.fmt == FMT_BINARY && fmt_out == FMT_BINARY && need_gpu && !getenv("S5B_VIEW_SLOW_PATH")) {
         // blow5 -> blow5: whole batches stay on the device (pinned chunk pipeline)
         ret = view_fast_binary(rd, fout, gpu, rec_out, sig_out, batch);
         eof = true;

@@ -65,14 +65,19 @@ __global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, c
             const uint64_t lrs = ld_u64_unaligned(p + head);
             sig_at = head + 8;
             // the field counts samples for a raw signal and bytes for a compressed one (slow5.c:3983-3987)
+            // sig_is_svb: 0 raw int16, 1 svb-zd stream (u32 sample count first), 2 ex-zd stream (u64 count at byte 1)
             const uint64_t sb = sig_is_svb ? lrs : lrs * 2;
-            if (sb > len - sig_at || (sig_is_svb && sb < 4)) {
+            if (sb > len - sig_at || (sig_is_svb == 1 && sb < 4) || (sig_is_svb == 2 && sb < 16)) {
                 st = S5B_ERR_PRESS;
             } else {
                 sig_bytes = (uint32_t)sb;
-                if (sig_is_svb) {
+                if (sig_is_svb == 1) {
                     const uint8_t *q = p + sig_at;
                     ns = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+                } else if (sig_is_svb == 2) {
+                    const uint64_t nin = ld_u64_unaligned(p + sig_at + 1);  // slow5_press.c:1790-1793
+                    if (nin > 0xFFFFFFFFull) st = S5B_ERR_PRESS;
+                    ns = (uint32_t)nin;
                 } else {
                     ns = (uint32_t)lrs;
                 }
@@ -96,6 +101,7 @@ __global__ void rec_plan_kernel(int mode, uint64_t n, RecArrays a, const uint32_
     switch (mode) {
         case PLAN_SIG_SAMPLES: v = ns; break;                                       // scanned with align 8 (samples)
         case PLAN_SVB_BOUND: v = 4u + (ns + 3u) / 4u + 3u * ns; break;              // s5b_svbzd_bound
+        case PLAN_EXZD_BOUND: v = 2u * ns + 1024u; break;                           // s5b_exzd_bound
         case PLAN_PACKED_LEN: v = a.head_len[r] + 8u + aux_in[r] + a.aux_len[r]; break;  // aux_in = signal bytes to store
         case PLAN_ZLIB_BOUND: v = aux_in[r] + 6u * (aux_in[r] / 6144u + 2u) + 8u; break; // == deflate_bound() (DEF_BLOCK 6144)
         case PLAN_IMAGE_LEN: v = aux_in[r] + 8u; break;

@@ -1169,7 +1169,7 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
     if (n == 0) return S5B_OK;
     if (!h_in || !rec_off || !rec_len || !h_out) return S5B_ERR_ARG;
     auto rec_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_ZLIB || m == S5B_COMPRESS_ZSTD; };
-    auto sig_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_SVB_ZD; };
+    auto sig_ok = [](int m) { return m == S5B_COMPRESS_NONE || m == S5B_COMPRESS_SVB_ZD || m == S5B_COMPRESS_EX_ZD; };
     if (!rec_ok(in_rec) || !rec_ok(out_rec) || !sig_ok(in_sig) || !sig_ok(out_sig))
         return S5B_ERR_ARG;
     DeviceGuard g(ctx->device);
@@ -1275,7 +1275,8 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
         cur_cap = round_up(total, 16);
     }
     // ---- where is the signal (slow5.c:2811-2927)
-    CU(launch_rec_locate(cur, cur_off, cur_len, n, in_sig == S5B_COMPRESS_SVB_ZD, ra, st));
+    CU(launch_rec_locate(cur, cur_off, cur_len, n, in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra,
+                         st));
     ctx->launches += 1;
     {
         int rc = check_status(ra.status);
@@ -1293,26 +1294,34 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
         CU(scan_total(d_tmp, 8, d_sig_off, &total));
         CU(ctx->r_sig.reserve(total * 2 + 32));
         ctx->launches += 1;
-        if (in_sig == S5B_COMPRESS_SVB_ZD) {  // decode (slow5.c:2915)
+        // the raw samples of every read, in an aligned slab: decoded from the stored stream (slow5.c:2915) or copied out
+        if (in_sig != S5B_COMPRESS_NONE) {
             CU(launch_rec_sig_abs(cur_off, ra, n, d_sigabs, st));
             SvbDecodeArgs da{cur, d_sigabs, ra.sig_bytes, cur_cap, n, static_cast<int16_t *>(ctx->r_sig.p), d_sig_off, d_ns2,
                              d_st2, counter};
-            CU(launch_svbzd_decode(da, ctx->num_sms, ctx->dec_bps, st));
+            if (in_sig == S5B_COMPRESS_SVB_ZD) CU(launch_svbzd_decode(da, ctx->num_sms, ctx->dec_bps, st));
+            else CU(launch_exzd_decode(da, ctx->num_sms, ctx->xd_bps, st));
             ctx->launches += 2;
             if (check_status(d_st2) != S5B_OK) return S5B_ERR_DEVICE;
             if (first_err != S5B_OK) return first_err;
+        } else {
+            CU(launch_sig_extract(cur, cur_off, ra, n, static_cast<int16_t *>(ctx->r_sig.p), d_sig_off, st));
+            ctx->launches += 1;
+        }
+        if (out_sig == S5B_COMPRESS_NONE) {
             sig_src = static_cast<const uint8_t *>(ctx->r_sig.p);
             sig_src_off = d_sig_off;
             sig_src_is_samples = 1;
-        } else {  // encode (slow5.c:3973): raw samples to an aligned slab, then svb-zd into slots
-            CU(launch_sig_extract(cur, cur_off, ra, n, static_cast<int16_t *>(ctx->r_sig.p), d_sig_off, st));
-            CU(launch_rec_plan(PLAN_SVB_BOUND, n, ra, nullptr, 0, d_tmp, st));
+        } else {  // encode (slow5.c:3973) into worst-case slots
+            const bool svb = out_sig == S5B_COMPRESS_SVB_ZD;
+            CU(launch_rec_plan(svb ? PLAN_SVB_BOUND : PLAN_EXZD_BOUND, n, ra, nullptr, 0, d_tmp, st));
             CU(scan_total(d_tmp, 16, d_svb_off, &total));
             CU(ctx->r_svb.reserve(total + 32));
             SvbEncodeArgs ea{static_cast<const int16_t *>(ctx->r_sig.p), d_sig_off, ra.n_samples, n,
                              static_cast<uint8_t *>(ctx->r_svb.p), d_svb_off, d_svb_len, d_st2, counter};
-            CU(launch_svbzd_encode(ea, ctx->num_sms, ctx->enc_bps, st));
-            ctx->launches += 3;
+            if (svb) CU(launch_svbzd_encode(ea, ctx->num_sms, ctx->enc_bps, st));
+            else CU(launch_exzd_encode(ea, ctx->num_sms, ctx->xe_bps, st));
+            ctx->launches += 2;
             if (check_status(d_st2) != S5B_OK) return S5B_ERR_DEVICE;
             if (first_err != S5B_OK) return first_err;
             sig_src = static_cast<const uint8_t *>(ctx->r_svb.p);

@@ -105,7 +105,7 @@ cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const
                               int sig_is_svb, RecArrays a, cudaStream_t st);
 // elementwise size planning: mode selects which length is written to out[]
 enum RecPlan { PLAN_SIG_SAMPLES = 0, PLAN_SVB_BOUND = 1, PLAN_PACKED_LEN = 2, PLAN_ZLIB_BOUND = 3, PLAN_IMAGE_LEN = 4,
-               PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7 };
+               PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7, PLAN_EXZD_BOUND = 8 };
 cudaError_t launch_rec_plan(int mode, uint64_t n, RecArrays a, const uint32_t *aux_in /*mode dependent*/, uint32_t param,
                             uint32_t *out, cudaStream_t st);
 // out[r] = rec_off[r] + sig_at[r] (absolute offset of the stored signal in the record slab)

@@ -16,8 +16,9 @@ REF = os.path.join(ROOT, "oracle", "_ref", "slow5tools_ref")
 have_ref = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/slow5tools_ref not present")
 
 
-def ours(*args):
-    r = subprocess.run([CLI, "view"] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+def ours(*args, env=None):
+    r = subprocess.run([CLI, "view"] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       env=dict(os.environ, **env) if env else None)
     assert r.returncode == 0, r.stderr.decode()
     return r
 
@@ -157,3 +158,19 @@ def test_exzd_files_byte_identical_without_zlib_and_read_by_the_reference(tmp_pa
     ours(os.path.join(FIX, "exp_1_lossless_zlib_ex_zd.blow5"), "-o", str(d), "-c", "none", "-s", "svb-zd")
     ref(os.path.join(FIX, "exp_1_lossless_zlib_ex_zd.blow5"), "-o", str(e), "-c", "none", "-s", "svb-zd")
     assert filecmp.cmp(d, e, shallow=False)
+
+
+@have_ref
+def test_exzd_fast_and_general_paths_agree(tmp_path):
+    """blow5 -> blow5 with ex-zd on either side: the device-resident path and the host parse/pack path write the same file."""
+    src = os.path.join(FIX, "exp_1_lossless_zlib_svb_v0.2.0.blow5")
+    exz = os.path.join(FIX, "exp_1_lossless_zlib_ex_zd.blow5")
+    for inp, flags in ((src, ["-c", "none", "-s", "ex-zd"]), (exz, ["-c", "none", "-s", "svb-zd"]),
+                       (exz, ["-c", "none", "-s", "none"]), (src, ["-c", "zstd", "-s", "ex-zd"]), (exz, ["-c", "zstd", "-s", "svb-zd"])):
+        a, b = tmp_path / "fast.blow5", tmp_path / "slow.blow5"
+        ours(inp, "-o", str(a), *flags)
+        ours(inp, "-o", str(b), *flags, env={"S5B_VIEW_SLOW_PATH": "1"})
+        assert filecmp.cmp(a, b, shallow=False), flags
+        t = tmp_path / "t.slow5"
+        ref(str(a), "-o", str(t))
+        assert filecmp.cmp(t, os.path.join(FIX, "exp_1_lossless_v0.2.0.slow5"), shallow=False), flags

@@ -13,10 +13,10 @@ fi
 timeout 600 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
 echo "bench exit $?"; tail -c 600 gpurun_out/${TAG}_bench_n1.json
 timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
-KR='regex:svbzd_|inflate|deflate|zstd'
+KR='regex:svbzd_|inflate|deflate|zstd|exzd'
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 200 --csv \
    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --profile > gpurun_out/${TAG}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k "$KR" -s 8 -c 14 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "$KR" -s 8 -c 12 \
    -o gpurun_out/${TAG}_full -f python bench.py --steps 2 --warmup 3 --profile > gpurun_out/${TAG}_ncu_full.log 2>&1
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page source --csv -k regex:svbzd_ 2>/dev/null | gzip > gpurun_out/${TAG}_svbzd_source.csv.gz
