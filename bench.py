@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "BLOW5 svb-zd reads/sec (encode+decode)"
 UNIT = "reads/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the default
+# workload (100k reads x 4096; profiles/r1_v4_ncu_full.md): bench.py cannot run under a profiler, so the figure is carried
+NCU_TRAFFIC = {"svbzd_encode_kernel": 828.7e6 + 495.1e6, "svbzd_decode_kernel": 536.7e6 + 767.5e6}
 
 
 def load_peaks():
@@ -408,7 +411,9 @@ def run_ours(args):
             "encode_ms": enc_ms_max, "decode_ms": dec_ms_max,
             "encode_reads_per_s": R / (enc_ms_max * 1e-3), "decode_reads_per_s": R / (dec_ms_max * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "svbzd_%s_kernel" % dom, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC.get("svbzd_%s_kernel" % dom) if (R, N) == (100000, 4096) else None,
+                         "traffic_source": "profiles/r1_v4_ncu_full.md (ncu --set full, same workload)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg,
                          "encode_frac": alg / (enc_ms_max * 1e-3) / 1e9 / peak,
                          "decode_frac": alg / (dec_ms_max * 1e-3) / 1e9 / peak},
