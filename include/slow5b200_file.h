@@ -73,7 +73,44 @@ void s5b_rec_free(s5b_rec_t *read);
 int s5b_decode_batch(s5b_file_t *fp, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads);
 int s5b_encode_batch(s5b_file_t *fp, s5b_rec_t **reads, size_t n, char **mems, size_t *bytes);
 
+/* ---- the "easy multi-thread" batch API (slow5lib/include/slow5/slow5_mt.h:23-65, slow5lib/src/slow5_mt.c:202-400), the
+ * interface pyslow5 uses.  Same structs, field order and call shapes; `num_thread` keeps its place in the signature but
+ * the codec stage of a batch is one pass over the GPU (s5b_decode_batch / s5b_encode_batch), not a fork-join pool.
+ *   s5b_get_next_batch : up to num_reads records fetched (serial, like slow5_mt.c:84-107) and decoded into
+ *                        batch->slow5_rec[]; returns the number of records, < num_reads at the end of the file
+ *   s5b_encode_batch_mt: batch->slow5_rec[] -> batch->mem_records[] / mem_bytes[] (slow5_encode_batch, :353)
+ *   s5b_write_batch    : encode + write, returns the number of records written (slow5_write_batch, :359)
+ * Errors: a negative S5B_ERR_* return (the reference exits the process instead, slow5_mt.c:131-137). */
+typedef struct {
+    int32_t n_rec;
+    int32_t capacity_rec;
+    char **mem_records;
+    size_t *mem_bytes;
+    s5b_rec_t **slow5_rec;
+    char **rid; /* get() by read id needs the index: not provided */
+} s5b_batch_t;
+typedef struct {
+    s5b_file_t *sf;
+    int num_thread;
+} s5b_mt_t;
+s5b_mt_t *s5b_init_mt(int num_thread, s5b_file_t *fp);
+s5b_batch_t *s5b_init_batch(int batch_capacity);
+int s5b_get_next_batch(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
+int s5b_encode_batch_mt(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
+int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
+void s5b_free_batch(s5b_batch_t *batch);
+void s5b_free_mt(s5b_mt_t *mt);
+
 #ifdef S5B_SLOW5_COMPAT
+#define slow5_batch_t s5b_batch_t
+#define slow5_mt_t s5b_mt_t
+#define slow5_init_mt s5b_init_mt
+#define slow5_init_batch s5b_init_batch
+#define slow5_get_next_batch s5b_get_next_batch
+#define slow5_encode_batch s5b_encode_batch_mt
+#define slow5_write_batch s5b_write_batch
+#define slow5_free_batch s5b_free_batch
+#define slow5_free_mt s5b_free_mt
 #define slow5_file_t s5b_file_t
 #define slow5_rec_t s5b_rec_t
 #define slow5_open s5b_open

@@ -315,3 +315,87 @@ int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *f) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// slow5_mt.h twins (slow5lib/src/slow5_mt.c:202-400)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+s5b_mt_t *s5b_init_mt(int num_thread, s5b_file_t *fp) {  // slow5_mt.c:257-268
+    if (!fp) return nullptr;
+    s5b_mt_t *mt = static_cast<s5b_mt_t *>(calloc(1, sizeof(s5b_mt_t)));
+    if (!mt) return nullptr;
+    mt->sf = fp;
+    mt->num_thread = num_thread;
+    return mt;
+}
+void s5b_free_mt(s5b_mt_t *mt) { free(mt); }
+
+s5b_batch_t *s5b_init_batch(int cap) {  // slow5_mt.c:270-291
+    if (cap <= 0) return nullptr;
+    s5b_batch_t *b = static_cast<s5b_batch_t *>(calloc(1, sizeof(s5b_batch_t)));
+    if (!b) return nullptr;
+    b->capacity_rec = cap;
+    b->mem_records = static_cast<char **>(calloc(cap, sizeof(char *)));
+    b->mem_bytes = static_cast<size_t *>(calloc(cap, sizeof(size_t)));
+    b->slow5_rec = static_cast<s5b_rec_t **>(calloc(cap, sizeof(s5b_rec_t *)));
+    if (!b->mem_records || !b->mem_bytes || !b->slow5_rec) {
+        s5b_free_batch(b);
+        return nullptr;
+    }
+    return b;
+}
+static void batch_drop_mem(s5b_batch_t *b) {
+    for (int i = 0; i < b->capacity_rec; ++i) {
+        free(b->mem_records[i]);
+        b->mem_records[i] = nullptr;
+        b->mem_bytes[i] = 0;
+    }
+}
+void s5b_free_batch(s5b_batch_t *b) {  // slow5_mt.c:293-316
+    if (!b) return;
+    if (b->mem_records && b->mem_bytes) batch_drop_mem(b);
+    if (b->slow5_rec)
+        for (int i = 0; i < b->capacity_rec; ++i) s5b_rec_free(b->slow5_rec[i]);
+    free(b->mem_records);
+    free(b->mem_bytes);
+    free(b->slow5_rec);
+    free(b);
+}
+
+int s5b_get_next_batch(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5_mt.c:336-351 (+ :84-107)
+    if (!mt || !mt->sf || !b || num_reads < 0 || num_reads > b->capacity_rec) return fail(S5B_ERR_ARG);
+    batch_drop_mem(b);
+    int n = 0;
+    while (n < num_reads) {
+        if (s5b_get_next_bytes(&b->mem_records[n], &b->mem_bytes[n], mt->sf) < 0) {
+            if (s5b_errno_value() != S5B_ERR_EOF) return s5b_errno_value();
+            break;
+        }
+        ++n;
+    }
+    b->n_rec = n;
+    if (n == 0) return 0;
+    const int rc = s5b_decode_batch(mt->sf, b->mem_records, b->mem_bytes, (size_t)n, b->slow5_rec);
+    if (rc < 0) return rc;
+    return n;
+}
+
+int s5b_encode_batch_mt(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5_mt.c:353-357
+    if (!mt || !mt->sf || !b || num_reads < 0 || num_reads > b->capacity_rec) return fail(S5B_ERR_ARG);
+    batch_drop_mem(b);
+    b->n_rec = num_reads;
+    if (num_reads == 0) return 0;
+    const int rc = s5b_encode_batch(mt->sf, b->slow5_rec, (size_t)num_reads, b->mem_records, b->mem_bytes);
+    return rc < 0 ? rc : num_reads;
+}
+
+int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5_mt.c:359-378
+    const int rc = s5b_encode_batch_mt(mt, b, num_reads);
+    if (rc < 0) return rc;
+    for (int i = 0; i < num_reads; ++i)
+        if (s5b_write_bytes(b->mem_records[i], b->mem_bytes[i], mt->sf) < 0) return s5b_errno_value();
+    return num_reads;
+}
+
+}  // extern "C"

@@ -174,3 +174,59 @@ def test_exzd_fast_and_general_paths_agree(tmp_path):
         t = tmp_path / "t.slow5"
         ref(str(a), "-o", str(t))
         assert filecmp.cmp(t, os.path.join(FIX, "exp_1_lossless_v0.2.0.slow5"), shallow=False), flags
+
+
+def test_mt_batch_api_roundtrip(tmp_path):
+    """slow5_mt.h twins: slow5_init_mt / slow5_init_batch / slow5_get_next_batch / slow5_write_batch (pyslow5's path)."""
+    L = C.CDLL(os.path.join(ROOT, "slow5tools_b200", "libslow5b200.so"))
+    vp = C.c_void_p
+
+    class Batch(C.Structure):  # slow5_batch_t, slow5_mt.h:23-33
+        _fields_ = [("n_rec", C.c_int32), ("capacity_rec", C.c_int32), ("mem_records", C.POINTER(vp)),
+                    ("mem_bytes", C.POINTER(C.c_size_t)), ("slow5_rec", C.POINTER(vp)), ("rid", C.POINTER(vp))]
+
+    L.s5b_open.restype = vp
+    L.s5b_open.argtypes = [C.c_char_p, C.c_char_p]
+    L.s5b_init_mt.restype = vp
+    L.s5b_init_mt.argtypes = [C.c_int, vp]
+    L.s5b_init_batch.restype = C.POINTER(Batch)
+    L.s5b_init_batch.argtypes = [C.c_int]
+    for f in (L.s5b_get_next_batch, L.s5b_write_batch):
+        f.argtypes = [vp, C.POINTER(Batch), C.c_int]
+    L.s5b_free_batch.argtypes = [C.POINTER(Batch)]
+    for f in (L.s5b_close, L.s5b_hdr_write, L.s5b_free_mt):
+        f.argtypes = [vp]
+    L.s5b_hdr_copy.argtypes = [vp, vp]
+    L.s5b_set_press.argtypes = [vp, C.c_int, C.c_int]
+    src = os.path.join(FIX, "zlib_svb-zd_multi_rg_v0.2.0.blow5")
+    for rec_press, sig_press in ((1, 2), (3, 4), (0, 0)):      # zlib+svb-zd, zstd+ex-zd, none/none
+        out = tmp_path / ("mt_%d_%d.blow5" % (rec_press, sig_press))
+        fin, fout = L.s5b_open(src.encode(), b"r"), L.s5b_open(str(out).encode(), b"w")
+        assert fin and fout
+        assert L.s5b_hdr_copy(fout, fin) == 0 and L.s5b_set_press(fout, rec_press, sig_press) == 0 and L.s5b_hdr_write(fout) > 0
+        mt_in, mt_out = L.s5b_init_mt(4, fin), L.s5b_init_mt(4, fout)
+        batch = L.s5b_init_batch(3)
+        total, sizes = 0, []
+        while True:
+            n = L.s5b_get_next_batch(mt_in, batch, 3)
+            assert n >= 0
+            if n == 0:
+                break
+            assert batch.contents.n_rec == n
+            assert L.s5b_write_batch(mt_out, batch, n) == n
+            total += n
+            sizes.append(n)
+            if n < 3:
+                break
+        assert total == 7 and sizes == [3, 3, 1]
+        L.s5b_free_batch(batch)
+        L.s5b_free_mt(mt_in)
+        L.s5b_free_mt(mt_out)
+        assert L.s5b_close(fin) == 0 and L.s5b_close(fout) == 0
+        back = tmp_path / "mt.slow5"
+        ours(str(out), "-o", str(back))
+        assert filecmp.cmp(back, os.path.join(FIX, "zlib_svb-zd_multi_rg_v0.2.0.expected.slow5"), shallow=False)
+        if os.path.exists(REF):
+            back2 = tmp_path / "mt_ref.slow5"
+            ref(str(out), "-o", str(back2))
+            assert filecmp.cmp(back2, os.path.join(FIX, "zlib_svb-zd_multi_rg_v0.2.0.expected.slow5"), shallow=False)
