@@ -346,7 +346,7 @@ def run_ours(args):
               "algorithmic_bytes_per_launch": R * N * 2 + xbytes,
               "encode_frac_of_hbm_peak": (R * N * 2 + xbytes) / (xe_ms * 1e-3) / 1e9 / peak_x,
               "decode_frac_of_hbm_peak": (R * N * 2 + xbytes) / (xd_ms * 1e-3) / 1e9 / peak_x,
-              "note": "encode reads the signal three times (q, sizes, emit); passes two and three come out of L2"}
+              "note": "encode reads the signal twice (size pass, emitting pass; the second comes out of L2), three times when q > 0"}
         del xbuf
 
     if args.profile:
