@@ -290,9 +290,13 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
                 if (bad) wret = 1;
                 wpos += nb;
             } else {
+                // small chunk (or a pipe): one sequential write.  On a seekable file it must be a pwrite at wpos as well:
+                // the pwrite()s above never move the descriptor's own offset, so a plain write() here would land at
+                // the start of the record area and overwrite the first records of the file
                 uint64_t done = 0;
                 while (!wret && done < nb) {
-                    const ssize_t w = write(ofd, c->out + done, nb - done);
+                    const ssize_t w = seekable ? pwrite(ofd, c->out + done, nb - done, (off_t)(wpos + done))
+                                               : write(ofd, c->out + done, nb - done);
                     if (w <= 0) wret = 1;
                     else done += (uint64_t)w;
                 }

@@ -230,3 +230,23 @@ def test_mt_batch_api_roundtrip(tmp_path):
             back2 = tmp_path / "mt_ref.slow5"
             ref(str(out), "-o", str(back2))
             assert filecmp.cmp(back2, os.path.join(FIX, "zlib_svb-zd_multi_rg_v0.2.0.expected.slow5"), shallow=False)
+
+
+def test_fast_path_small_last_chunk_lands_after_the_big_ones(tmp_path):
+    """Regression: the chunk writer mixes parallel pwrite()s (chunks > 8 MiB) with a sequential write for small chunks;
+    a small LAST chunk used to be written at the descriptor's stale offset, over the first records of the file."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_view
+    from slow5tools_b200 import synth
+    R, N = 5600, 4096            # 46 MB of records: one 40 MB input chunk (18 MB out) + a 4 MB tail (1.8 MB out)
+    raw = tmp_path / "raw.blow5"
+    bench_view.write_blow5(str(raw), synth.nanopore_signal(R * N, seed=5).numpy(), R, N)
+    for flags in (["-c", "zlib", "-s", "svb-zd"], ["-c", "zstd", "-s", "ex-zd"]):
+        z, back = tmp_path / "z.blow5", tmp_path / "back.blow5"
+        ours(str(raw), "-o", str(z), *flags)
+        ours(str(z), "-o", str(back), "-c", "none", "-s", "none")
+        assert filecmp.cmp(raw, back, shallow=False), flags
+        slow = tmp_path / "slow.blow5"
+        ours(str(raw), "-o", str(slow), *flags, env={"S5B_VIEW_SLOW_PATH": "1"})
+        assert filecmp.cmp(z, slow, shallow=False), flags

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """CLI-level comparison on one host: `slow5tools-b200 view` (GPU codec) next to the unmodified reference
 `slow5tools view -t <ncores>` (oracle/_ref/slow5tools_ref) on the same synthetic BLOW5 file -- the comparison
-BASELINE.json's north_star asks for.  Encode = none/none -> zlib+svb-zd, decode = zlib+svb-zd -> none/none.
+BASELINE.json's north_star asks for.  Encode = none/none -> REC+SIG (default zlib+svb-zd), decode = REC+SIG -> none/none.
 
     python tools/bench_view.py [--reads 100000] [--samples 4096] [--dir /dev/shm]
 """
@@ -60,32 +60,38 @@ def main():
     ap.add_argument("--samples", type=int, default=4096)
     ap.add_argument("--dir", default="/dev/shm")
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--methods", default="zlib:svb-zd", help="comma separated REC:SIG output methods to time")
     a = ap.parse_args()
     from slow5tools_b200 import synth
     cores = os.cpu_count() or 1
     raw = os.path.join(a.dir, "s5b_raw.blow5")
     sig = synth.nanopore_signal(a.reads * a.samples, seed=42).numpy()
     write_blow5(raw, sig, a.reads, a.samples)
-    out = {"reads": a.reads, "samples": a.samples, "cores": cores, "raw_bytes": os.path.getsize(raw)}
+    out = {"reads": a.reads, "samples": a.samples, "cores": cores, "raw_bytes": os.path.getsize(raw), "methods": {}}
     z_ref, z_ours = os.path.join(a.dir, "s5b_ref.blow5"), os.path.join(a.dir, "s5b_ours.blow5")
     back = os.path.join(a.dir, "s5b_back.blow5")
-    for name, exe, z in (("reference", REF, z_ref), ("ours", CLI, z_ours)):
-        if not os.path.exists(exe):
-            continue
-        enc = min(timed([exe, "view", "-t", str(cores), "-K", "4096" if name == "reference" else "20000", raw, "-o", z])
-                  for _ in range(a.repeat))
-        dec = min(timed([exe, "view", "-t", str(cores), "-K", "4096" if name == "reference" else "20000", z, "-c", "none", "-s", "none", "-o", back])
-                  for _ in range(a.repeat))
-        same = open(back, "rb").read() == open(raw, "rb").read()
-        out[name] = {"encode_s": enc, "decode_s": dec, "encode_reads_per_s": a.reads / enc, "decode_reads_per_s": a.reads / dec,
-                     "compressed_bytes": os.path.getsize(z), "roundtrip_identical": same}
-    if "reference" in out and "ours" in out:
-        # cross-check: the reference decodes OUR file to the original bytes
-        subprocess.check_call([REF, "view", "-t", str(cores), z_ours, "-c", "none", "-s", "none", "-o", back], stderr=subprocess.DEVNULL)
-        out["reference_reads_our_file"] = open(back, "rb").read() == open(raw, "rb").read()
-        out["size_vs_reference"] = out["ours"]["compressed_bytes"] / out["reference"]["compressed_bytes"]
-        out["encode_speedup"] = out["reference"]["encode_s"] / out["ours"]["encode_s"]
-        out["decode_speedup"] = out["reference"]["decode_s"] / out["ours"]["decode_s"]
+    raw_bytes = open(raw, "rb").read()
+    for combo in a.methods.split(","):
+        rec_m, sig_m = combo.split(":")
+        res = {}
+        for name, exe, z in (("reference", REF, z_ref), ("ours", CLI, z_ours)):
+            if not os.path.exists(exe):
+                continue
+            k = "4096" if name == "reference" else "20000"
+            enc = min(timed([exe, "view", "-t", str(cores), "-K", k, raw, "-c", rec_m, "-s", sig_m, "-o", z]) for _ in range(a.repeat))
+            dec = min(timed([exe, "view", "-t", str(cores), "-K", k, z, "-c", "none", "-s", "none", "-o", back])
+                      for _ in range(a.repeat))
+            same = open(back, "rb").read() == raw_bytes
+            res[name] = {"encode_s": enc, "decode_s": dec, "encode_reads_per_s": a.reads / enc, "decode_reads_per_s": a.reads / dec,
+                         "compressed_bytes": os.path.getsize(z), "roundtrip_identical": same}
+        if "reference" in res and "ours" in res:
+            # cross-check: the reference decodes OUR file to the original bytes
+            subprocess.check_call([REF, "view", "-t", str(cores), z_ours, "-c", "none", "-s", "none", "-o", back], stderr=subprocess.DEVNULL)
+            res["reference_reads_our_file"] = open(back, "rb").read() == raw_bytes
+            res["size_vs_reference"] = res["ours"]["compressed_bytes"] / res["reference"]["compressed_bytes"]
+            res["encode_speedup"] = res["reference"]["encode_s"] / res["ours"]["encode_s"]
+            res["decode_speedup"] = res["reference"]["decode_s"] / res["ours"]["decode_s"]
+        out["methods"][combo] = res
     for p in (raw, z_ref, z_ours, back):
         if os.path.exists(p):
             os.remove(p)
