@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -153,8 +154,19 @@ uint64_t s5b_svbzd_slot(uint32_t n) { return round_up(s5b_svbzd_bound(n), 16); }
 int s5b_ctx_create(int device, s5b_ctx_t **out) {
     if (!out) return S5B_ERR_ARG;
     *out = nullptr;
+    const bool timing = getenv("S5B_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    auto lap = [&](const char *what) {
+        if (timing) {
+            const double t1 = now();
+            fprintf(stderr, "[timing]   ctx: %-28s %.3f s\n", what, t1 - t0);
+            t0 = t1;
+        }
+    };
     int ndev = s5b_device_count();
     if (ndev <= 0) return S5B_ERR_DEVICE;
+    lap("driver init / device count");
     if (device < 0) {
         if (cudaGetDevice(&device) != cudaSuccess) return S5B_ERR_DEVICE;
     }
@@ -169,6 +181,7 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
         return S5B_ERR_DEVICE;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    lap("set device / properties");
     ctx->enc_bps = svbzd_encode_blocks_per_sm();
     ctx->dec_bps = svbzd_decode_blocks_per_sm();
     ctx->inf_bps = inflate_blocks_per_sm();
@@ -183,6 +196,7 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
         delete ctx;
         return S5B_ERR_DEVICE;
     }
+    lap("kernel occupancy queries");
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counter, 256) == cudaSuccess;
     for (int i = 0; ok && i < NSLOT; ++i) {
@@ -190,6 +204,7 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
         ok = ok && cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&ctx->slot[i].d_counter, 256) == cudaSuccess;
     }
+    lap("streams, events, counters");
     if (const char *e = getenv("S5B_CHUNK_MB")) {
         long v = atol(e);
         if (v > 0) ctx->chunk_bytes = (size_t)v << 20;
