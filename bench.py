@@ -164,6 +164,27 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pins this rank (and so its pinned-buffer allocations and copy submissions) to the CPUs next to its GPU.  With one
+    rank per GPU the host side of the e2e path is memory-bandwidth bound; crossing sockets costs PCIe throughput."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -177,6 +198,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # rank 0 prints exactly one JSON line on stdout: NCCL's version banner / debug lines go to stderr
@@ -406,7 +428,8 @@ def run_ours(args):
                        "reads_per_gpu": R, "samples_per_read": N, "signal_model": "SURVEY 8d nanopore-like, seed 42+rank",
                        "svb_bytes_per_sample": svb_bytes / (R * N),
                        "l2": "inputs (%.0f MB per kernel) exceed the 126 MB L2; no flush needed" % (alg / 1e6),
-                       "sharding": "reads split across ranks, no collective on the data path"},
+                       "sharding": "reads split across ranks, no collective on the data path",
+                       "rank0_numa_binding": numa},
             "raw_signal_GBps": raw_bytes * world * K / (ms_total * 1e-3) / 1e9,
             "encode_ms": enc_ms_max, "decode_ms": dec_ms_max,
             "encode_reads_per_s": R / (enc_ms_max * 1e-3), "decode_reads_per_s": R / (dec_ms_max * 1e-3),
