@@ -208,6 +208,13 @@ int s5b_compress_records_host(s5b_ctx_t *ctx, int method, const void *const *ptr
 int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
                           uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
                           uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes);
+/* The per-record work of index building (slow5_idx_build, slow5lib/src/slow5_idx.c:283-334) for a batch: the read_id of
+ * every stored record.  Records compressed with in_rec (S5B_COMPRESS_NONE / ZLIB / ZSTD) are decompressed on the device --
+ * for zlib only their first 256 bytes, like the reference's partial decompression (:290-310), with a full pass for the
+ * records whose id does not fit in that prefix (:312-320) -- and only the id bytes come back: record i's id is
+ * h_ids[id_off[i] .. id_off[i+1]) (no terminator).  ctx may be NULL for S5B_COMPRESS_NONE. */
+int s5b_blow5_read_ids_host(s5b_ctx_t *ctx, int in_rec, const uint8_t *h_in, uint64_t in_bytes, const uint64_t *rec_off,
+                            const uint32_t *rec_len, uint64_t n, uint8_t *h_ids, uint64_t ids_cap, uint64_t *id_off);
 /* page-locked host memory for the slab entry points (cudaHostAlloc / cudaFreeHost) */
 void *s5b_host_alloc(size_t bytes);
 void s5b_host_free(void *p);

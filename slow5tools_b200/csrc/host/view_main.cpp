@@ -667,14 +667,24 @@ int view_main(int argc, char **argv) {
     return ret;
 }
 
+int index_main(int argc, char **argv);  // index_main.cpp
+
 int main(int argc, char **argv) {
     if (argc >= 2 && (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V"))) {
         printf("slow5tools-b200 %s\n", s5b_version());
         return 0;
     }
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
-        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n");
+        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n    index   create a SLOW5/BLOW5 index file\n");
         return argc < 2 ? 1 : 0;
+    }
+    if (!strcmp(argv[1], "index")) {
+        const int rc = index_main(argc - 1, argv + 1);
+        if (rc != 0) {
+            fprintf(stderr, "[main::ERROR] index failed\n");
+            return EXIT_FAILURE;
+        }
+        return 0;
     }
     if (!strcmp(argv[1], "view")) {
         const int rc = view_main(argc - 1, argv + 1);
@@ -684,6 +694,6 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
-    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view)\n", argv[1]);
+    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view, index)\n", argv[1]);
     return EXIT_FAILURE;
 }

@@ -166,6 +166,22 @@ __global__ void rec_sig_abs_kernel(const uint64_t *rec_off, RecArrays a, uint64_
     if (r == n) out[n] = 0;
 }
 
+// read_id of every (decompressed prefix of a) record: len[r] = id bytes when the prefix holds the whole id, 0xFFFFFFFF when it
+// does not (the caller decompresses that record in full), src[r] = where the id bytes start (slow5_idx.c:322-334)
+__global__ void rec_ids_kernel(const uint64_t *rec_off, const uint32_t *have, const int32_t *status, uint64_t n, uint32_t *len,
+                               uint64_t *src, const uint8_t *rec) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t l = 0xFFFFFFFFu;
+    const uint64_t at = rec_off[r];
+    if (status[r] == S5B_OK && have[r] >= 2) {
+        const uint32_t rid = (uint32_t)rec[at] | ((uint32_t)rec[at + 1] << 8);
+        if (have[r] >= 2 + rid) l = rid;
+    }
+    len[r] = l;
+    src[r] = at + 2;
+}
+
 unsigned rk_grid(uint64_t n) {
     uint64_t g = (n + RK_WARPS - 1) / RK_WARPS;
     if (g > 148ull * 8) g = 148ull * 8;
@@ -182,6 +198,12 @@ cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const
 }
 cudaError_t launch_rec_sig_abs(const uint64_t *rec_off, RecArrays a, uint64_t n, uint64_t *out, cudaStream_t st) {
     rec_sig_abs_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(rec_off, a, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_rec_ids(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *have, const int32_t *status, uint64_t n,
+                           uint32_t *len, uint64_t *src, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    rec_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec_off, have, status, n, len, src, rec);
     return cudaGetLastError();
 }
 cudaError_t launch_rec_plan(int mode, uint64_t n, RecArrays a, const uint32_t *aux_in, uint32_t param, uint32_t *out,

@@ -1413,6 +1413,179 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// read ids of a batch of stored records: the per-record work of slow5_idx_build (slow5_idx.c:283-334)
+// ---------------------------------------------------------------------------------------------
+int s5b_blow5_read_ids_host(s5b_ctx_t *ctx, int in_rec, const uint8_t *h_in, uint64_t in_bytes, const uint64_t *rec_off,
+                            const uint32_t *rec_len, uint64_t n, uint8_t *h_ids, uint64_t ids_cap, uint64_t *id_off) {
+    if (!id_off) return S5B_ERR_ARG;
+    id_off[0] = 0;
+    if (n == 0) return S5B_OK;
+    if (!h_in || !rec_off || !rec_len || !h_ids) return S5B_ERR_ARG;
+    for (uint64_t i = 0; i < n; ++i)
+        if (rec_off[i] + rec_len[i] > in_bytes) return S5B_ERR_ARG;
+    if (in_rec == S5B_COMPRESS_NONE) {  // the id is right there
+        uint64_t tot = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            if (rec_len[i] < 2) return S5B_ERR_PRESS;
+            uint16_t rid;
+            memcpy(&rid, h_in + rec_off[i], 2);
+            if (2u + rid > rec_len[i]) return S5B_ERR_PRESS;
+            if (tot + rid > ids_cap) return S5B_ERR_NOSPACE;
+            memcpy(h_ids + tot, h_in + rec_off[i] + 2, rid);
+            tot += rid;
+            id_off[i + 1] = tot;
+        }
+        return S5B_OK;
+    }
+    if (!ctx || (in_rec != S5B_COMPRESS_ZLIB && in_rec != S5B_COMPRESS_ZSTD)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->slot[0].stream;
+    unsigned long long *counter = ctx->slot[0].d_counter;
+    // zlib: like the reference (slow5_idx.c:290-310) only the first 256 bytes of every record are decompressed -- a cut
+    // stream is not an error for inflate, it yields the bytes decoded so far; zstd frames are decoded in full (:289)
+    const bool zl = in_rec == S5B_COMPRESS_ZLIB;
+    const uint32_t PFX = 256, SLOT = 4096;
+    std::vector<uint32_t> idlen(n);
+    uint64_t tot = 0;
+    std::vector<uint64_t> redo;  // records whose prefix did not reach the end of the id
+    const uint64_t SUB = 200000;
+    for (uint64_t b0 = 0; b0 < n; b0 += SUB) {
+        const uint64_t m = (n - b0 < SUB) ? n - b0 : SUB;
+        // ---- pinned input slab + offsets
+        std::vector<uint64_t> ioff(m + 1), ooff(m + 1);
+        std::vector<uint32_t> ilen(m);
+        uint64_t itot = 0, otot = 0;
+        for (uint64_t i = 0; i < m; ++i) {
+            const uint32_t l = zl ? (rec_len[b0 + i] < PFX ? rec_len[b0 + i] : PFX) : rec_len[b0 + i];
+            ioff[i] = itot;
+            ilen[i] = l;
+            itot += round_up(l, 16);
+            ooff[i] = otot;
+            if (zl) {
+                otot += SLOT;
+            } else {
+                uint64_t sz = 0;
+                if (s5b_zstd_content_size(h_in + rec_off[b0 + i], rec_len[b0 + i], &sz) != S5B_OK || sz > 0xfffffff0ull)
+                    return S5B_ERR_PRESS;
+                otot += round_up(sz, 16);
+            }
+        }
+        ioff[m] = itot;
+        ooff[m] = otot;
+        CU(ctx->h_stage_in.reserve(itot + 16));
+        uint8_t *hin = static_cast<uint8_t *>(ctx->h_stage_in.p);
+        for (uint64_t i = 0; i < m; ++i) memcpy(hin + ioff[i], h_in + rec_off[b0 + i], ilen[i]);
+        // ---- device buffers: [ioff][ooff][src] u64 (m+1 each) | [ilen][olen][idlen] u32 | [status] i32
+        const size_t meta = 4 * (m + 1) * 8 + 4 * m * 4;
+        CU(ctx->r_meta.reserve(meta + 64));
+        CU(ctx->r_in.reserve(itot + 16));
+        CU(ctx->r_infl.reserve(otot + 16));
+        CU(ctx->r_scratch.reserve(compact_scratch_bytes(m)));
+        uint64_t *d_ioff = static_cast<uint64_t *>(ctx->r_meta.p), *d_ooff = d_ioff + (m + 1), *d_src = d_ooff + (m + 1),
+                 *d_dense = d_src + (m + 1);
+        uint32_t *d_ilen = reinterpret_cast<uint32_t *>(d_dense + (m + 1)), *d_olen = d_ilen + m, *d_idlen = d_olen + m;
+        int32_t *d_st = reinterpret_cast<int32_t *>(d_idlen + m);
+        CU(cudaMemcpyAsync(d_ioff, ioff.data(), (m + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_ooff, ooff.data(), (m + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_ilen, ilen.data(), m * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->r_in.p, hin, itot, cudaMemcpyHostToDevice, st));
+        InflateArgs ia{static_cast<const uint8_t *>(ctx->r_in.p), d_ioff, d_ilen, round_up(itot, 16), m,
+                       static_cast<uint8_t *>(ctx->r_infl.p), d_ooff, d_olen, d_st, counter};
+        if (zl) {
+            CU(launch_inflate(ia, ctx->num_sms, ctx->inf_bps, st));
+            ctx->launches += 1;
+        } else {
+            const int rc = zstd_launch(ctx, ia, st);
+            if (rc != S5B_OK) return rc;
+        }
+        CU(launch_rec_ids(static_cast<const uint8_t *>(ctx->r_infl.p), d_ooff, d_olen, d_st, m, d_idlen, d_src, st));
+        CU(cudaMemcpyAsync(idlen.data() + b0, d_idlen, m * 4, cudaMemcpyDeviceToHost, st));
+        std::vector<int32_t> h_st(m);
+        CU(cudaMemcpyAsync(h_st.data(), d_st, m * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // records to redo get length 0 in the gather; data errors are errors (a zstd frame that fails, a zlib prefix that is
+        // not a zlib stream); NOSPACE on a prefix just means the slot was too small to hold what 256 bytes inflate to
+        std::vector<uint32_t> glen(m);
+        for (uint64_t i = 0; i < m; ++i) {
+            if (h_st[i] == S5B_ERR_PRESS) return S5B_ERR_PRESS;
+            if (idlen[b0 + i] == 0xFFFFFFFFu) {
+                if (!zl) return S5B_ERR_PRESS;
+                redo.push_back(b0 + i);
+                glen[i] = 0;
+            } else {
+                glen[i] = idlen[b0 + i];
+            }
+        }
+        CU(cudaMemcpyAsync(d_idlen, glen.data(), m * 4, cudaMemcpyHostToDevice, st));
+        int nl = 0;
+        // dense gather of the id bytes, then one small D2H
+        uint64_t sub_tot = 0;
+        for (uint64_t i = 0; i < m; ++i) sub_tot += glen[i];
+        CU(ctx->r_packed.reserve(sub_tot + 64));
+        CU(launch_compact(static_cast<const uint8_t *>(ctx->r_infl.p), d_src, d_idlen, m, 1,
+                          static_cast<uint8_t *>(ctx->r_packed.p), d_dense, ctx->r_scratch.p, st, &nl));
+        ctx->launches += 1 + nl;
+        if (tot + sub_tot > ids_cap) return S5B_ERR_NOSPACE;
+        CU(cudaMemcpyAsync(h_ids + tot, ctx->r_packed.p, sub_tot, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (uint64_t i = 0; i < m; ++i) {
+            tot += glen[i];
+            id_off[b0 + i + 1] = tot;
+        }
+    }
+    if (!redo.empty()) {
+        // ids longer than what the prefix gave: decompress those records in full (slow5_idx.c:312-320), then rebuild the slab
+        std::vector<const void *> ptrs(redo.size());
+        std::vector<size_t> counts(redo.size()), out_n(redo.size());
+        std::vector<void *> outs(redo.size(), nullptr);
+        for (size_t k = 0; k < redo.size(); ++k) {
+            ptrs[k] = h_in + rec_off[redo[k]];
+            counts[k] = rec_len[redo[k]];
+        }
+        const int rc = s5b_depress_batch_host(ctx, S5B_COMPRESS_ZLIB, ptrs.data(), counts.data(), redo.size(), outs.data(),
+                                              out_n.data());
+        std::vector<std::string> ids(redo.size());
+        int bad = rc;
+        for (size_t k = 0; k < redo.size(); ++k) {
+            if (outs[k] && out_n[k] >= 2) {
+                uint16_t rid;
+                memcpy(&rid, outs[k], 2);
+                if (2u + rid <= out_n[k]) ids[k].assign(static_cast<const char *>(outs[k]) + 2, rid);
+                else bad = S5B_ERR_PRESS;
+            } else if (bad == S5B_OK) {
+                bad = S5B_ERR_PRESS;
+            }
+            free(outs[k]);
+        }
+        if (bad != S5B_OK) return bad;
+        // splice: walk backwards so the dense slab can be expanded in place
+        uint64_t extra = 0;
+        for (const auto &sid : ids) extra += sid.size();
+        if (tot + extra > ids_cap) return S5B_ERR_NOSPACE;
+        std::vector<uint64_t> new_off(n + 1);
+        uint64_t acc = 0;
+        size_t k = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            new_off[i] = acc;
+            if (k < redo.size() && redo[k] == i) acc += ids[k++].size();
+            else acc += id_off[i + 1] - id_off[i];
+        }
+        new_off[n] = acc;
+        k = redo.size();
+        for (uint64_t i = n; i-- > 0;) {
+            if (k > 0 && redo[k - 1] == i) {
+                --k;
+                memcpy(h_ids + new_off[i], ids[k].data(), ids[k].size());
+            } else {
+                memmove(h_ids + new_off[i], h_ids + id_off[i], id_off[i + 1] - id_off[i]);
+            }
+        }
+        for (uint64_t i = 0; i <= n; ++i) id_off[i] = new_off[i];
+    }
+    return S5B_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // single buffers
 // ---------------------------------------------------------------------------------------------
 namespace {

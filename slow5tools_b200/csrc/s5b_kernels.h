@@ -108,6 +108,9 @@ enum RecPlan { PLAN_SIG_SAMPLES = 0, PLAN_SVB_BOUND = 1, PLAN_PACKED_LEN = 2, PL
                PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7, PLAN_EXZD_BOUND = 8 };
 cudaError_t launch_rec_plan(int mode, uint64_t n, RecArrays a, const uint32_t *aux_in /*mode dependent*/, uint32_t param,
                             uint32_t *out, cudaStream_t st);
+// read ids out of (prefixes of) decompressed records: len[r] = id bytes or 0xFFFFFFFF (prefix too short), src[r] = id start
+cudaError_t launch_rec_ids(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *have, const int32_t *status, uint64_t n,
+                           uint32_t *len, uint64_t *src, cudaStream_t st);
 // out[r] = rec_off[r] + sig_at[r] (absolute offset of the stored signal in the record slab)
 cudaError_t launch_rec_sig_abs(const uint64_t *rec_off, RecArrays a, uint64_t n, uint64_t *out, cudaStream_t st);
 cudaError_t launch_sig_extract(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, int16_t *sig,
