@@ -355,6 +355,185 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
 
 }  // namespace
 
+// The general conversion loop (the body of slow5_convert_parallel, src/view.c:254-301, and of `get`'s per-batch work,
+// src/get.c:37-66): records come from `next` -- 1 = one stored record (binary: without its size prefix; text: one line
+// without the newline) placed in the buffer, 0 = no more, -1 = error already reported -- are decompressed, parsed,
+// re-encoded for (fmt_out, rec_out, sig_out) with the codec calls batched on the GPU, and written to fout in order.
+int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::vector<uint8_t> &)> &next, FILE *fout,
+                    s5b_ctx_t *gpu, Fmt fmt_out, int rec_out, int sig_out, long batch, int threads) {
+    int ret = 0;
+    Batch b;
+    bool eof = false;
+    while (!eof && ret == 0) {
+        // ---- load (serial)
+        b.mem.clear();
+        while ((long)b.mem.size() < batch) {
+            b.mem.emplace_back();
+            const int rc = next(b.mem.back());
+            if (rc <= 0) {
+                b.mem.pop_back();
+                if (rc < 0) ret = 1;  // the source has reported what went wrong
+                eof = true;
+                break;
+            }
+        }
+        const size_t n = b.mem.size();
+        if (n == 0 || ret) break;
+        b.rec.assign(n, Record());
+        b.aux_store.assign(n, std::vector<uint8_t>());
+        std::vector<const void *> ptrs(n);
+        std::vector<size_t> counts(n);
+
+        // ---- record decompression
+        std::vector<const uint8_t *> packed(n);
+        std::vector<size_t> packed_n(n);
+        if (fmt_in == FMT_BINARY && (hdr.record_method == PRESS_ZLIB || hdr.record_method == PRESS_ZSTD)) {
+            for (size_t i = 0; i < n; ++i) {
+                ptrs[i] = b.mem[i].data();
+                counts[i] = b.mem[i].size();
+            }
+            b.inflated.assign(n, nullptr);
+            b.inflated_n.assign(n, 0);
+            const int rc = s5b_depress_batch_host(gpu, hdr.record_method == PRESS_ZLIB ? S5B_COMPRESS_ZLIB : S5B_COMPRESS_ZSTD,
+                                                  ptrs.data(), counts.data(), n, b.inflated.data(), b.inflated_n.data());
+            if (rc != S5B_OK) {
+                ERROR("record decompression failed: %s", s5b_strerror(rc));
+                ret = 1;
+                break;
+            }
+            for (size_t i = 0; i < n; ++i) {
+                packed[i] = static_cast<const uint8_t *>(b.inflated[i]);
+                packed_n[i] = b.inflated_n[i];
+            }
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                packed[i] = b.mem[i].data();
+                packed_n[i] = b.mem[i].size();
+            }
+        }
+        // ---- parse
+        std::atomic<int> bad(0);
+        if (fmt_in == FMT_BINARY) {
+            parallel_for(n, threads, [&](size_t i) {
+                std::string e;
+                if (!record_parse_binary(packed[i], packed_n[i], hdr, hdr.signal_method, b.rec[i], e)) bad = 1;
+            });
+        } else {
+            parallel_for(n, threads, [&](size_t i) {
+                std::string e;
+                if (!record_parse_ascii(reinterpret_cast<const char *>(packed[i]), packed_n[i], hdr, b.rec[i], b.aux_store[i], e)) bad = 1;
+            });
+        }
+        if (bad) {
+            ERROR("%s", "a record could not be parsed");
+            ret = 1;
+            break;
+        }
+        // ---- signal decompression
+        std::vector<const int16_t *> sig(n);
+        if (fmt_in == FMT_BINARY && hdr.signal_method != PRESS_NONE) {  // PRESS_* == S5B_COMPRESS_* (slow5_press.h:61-67)
+            for (size_t i = 0; i < n; ++i) {
+                ptrs[i] = b.rec[i].sig_bytes;
+                counts[i] = b.rec[i].sig_nbytes;
+            }
+            b.sig.assign(n, nullptr);
+            b.sig_n.assign(n, 0);
+            const int rc = s5b_depress_batch_host(gpu, hdr.signal_method, ptrs.data(), counts.data(), n, b.sig.data(),
+                                                  b.sig_n.data());
+            if (rc != S5B_OK) {
+                ERROR("signal decompression failed: %s", s5b_strerror(rc));
+                ret = 1;
+                break;
+            }
+            for (size_t i = 0; i < n; ++i) {
+                sig[i] = static_cast<const int16_t *>(b.sig[i]);
+                b.rec[i].len_raw_signal = b.sig_n[i] / 2;
+            }
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                sig[i] = reinterpret_cast<const int16_t *>(b.rec[i].sig_bytes);  // memcpy'd below where alignment matters
+                b.rec[i].len_raw_signal = b.rec[i].sig_nbytes / 2;
+            }
+        }
+
+        // ---- output
+        if (fmt_out == FMT_ASCII) {
+            std::vector<std::string> lines(n);
+            parallel_for(n, threads, [&](size_t i) {
+                Record &r = b.rec[i];
+                r.raw_signal.resize(r.len_raw_signal);
+                if (r.len_raw_signal) memcpy(r.raw_signal.data(), sig[i], r.len_raw_signal * 2);
+                record_to_ascii(r, hdr, lines[i]);
+                std::vector<int16_t>().swap(r.raw_signal);
+            });
+            for (size_t i = 0; i < n && ret == 0; ++i)
+                if (fwrite(lines[i].data(), 1, lines[i].size(), fout) != lines[i].size()) ret = 1;
+        } else {
+            // signal compression
+            std::vector<void *> svb(n, nullptr);
+            std::vector<size_t> svb_n(n, 0);
+            std::vector<const uint8_t *> store(n);
+            std::vector<size_t> store_n(n);
+            if (sig_out != PRESS_NONE) {
+                for (size_t i = 0; i < n; ++i) {
+                    ptrs[i] = sig[i];
+                    counts[i] = b.rec[i].len_raw_signal * 2;
+                }
+                const int rc = s5b_compress_batch_host(gpu, sig_out, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
+                if (rc != S5B_OK) {
+                    ERROR("signal compression failed: %s", s5b_strerror(rc));
+                    ret = 1;
+                }
+                for (size_t i = 0; i < n; ++i) {
+                    store[i] = static_cast<const uint8_t *>(svb[i]);
+                    store_n[i] = svb_n[i];
+                }
+            } else {
+                for (size_t i = 0; i < n; ++i) {
+                    store[i] = reinterpret_cast<const uint8_t *>(sig[i]);
+                    store_n[i] = b.rec[i].len_raw_signal * 2;
+                }
+            }
+            std::vector<std::vector<uint8_t>> rec_mem(n);
+            std::vector<uint32_t> splits(n, 0);
+            if (ret == 0) {
+                parallel_for(n, threads, [&](size_t i) {
+                    uint64_t at = 0;
+                    record_to_binary(b.rec[i], store[i], store_n[i], sig_out != PRESS_NONE, rec_mem[i], &at);
+                    // Huffman block split for the zlib encoder: where the svb-zd data bytes start
+                    if (sig_out == PRESS_SVB_ZD) splits[i] = (uint32_t)(at + 4 + (b.rec[i].len_raw_signal + 3) / 4);
+                });
+            }
+            for (void *p : svb) free(p);
+            std::vector<void *> z(n, nullptr);
+            std::vector<size_t> z_n(n, 0);
+            const bool rec_packed = rec_out == PRESS_ZLIB || rec_out == PRESS_ZSTD;
+            if (ret == 0 && rec_packed) {
+                for (size_t i = 0; i < n; ++i) {
+                    ptrs[i] = rec_mem[i].data();
+                    counts[i] = rec_mem[i].size();
+                }
+                const int rc = s5b_compress_records_host(gpu, rec_out == PRESS_ZSTD ? S5B_COMPRESS_ZSTD : S5B_COMPRESS_ZLIB,
+                                                         ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
+                if (rc != S5B_OK) {
+                    ERROR("record compression failed: %s", s5b_strerror(rc));
+                    ret = 1;
+                }
+            }
+            for (size_t i = 0; i < n && ret == 0; ++i) {
+                const void *p = rec_packed ? z[i] : rec_mem[i].data();
+                const uint64_t sz = rec_packed ? z_n[i] : rec_mem[i].size();
+                if (fwrite(&sz, 8, 1, fout) != 1 || (sz && fwrite(p, 1, sz, fout) != sz)) ret = 1;  // slow5.c:4055-4060
+            }
+            for (void *p : z) free(p);
+        }
+        if (ret) ERROR("%s", "writing the output failed");
+        b.free_all();
+    }
+    b.free_all();
+    return ret;
+}
+
 int view_main(int argc, char **argv) {
     static const struct option long_opts[] = {
         {"sig-compress", required_argument, nullptr, 's'}, {"compress", required_argument, nullptr, 'c'},
@@ -476,184 +655,18 @@ int view_main(int argc, char **argv) {
     }
 
     int ret = 0;
-    Batch b;
-    std::string err;
     bool eof = false;
     if (rd.fmt == FMT_BINARY && fmt_out == FMT_BINARY && need_gpu && !getenv("S5B_VIEW_SLOW_PATH")) {
         // blow5 -> blow5: whole batches stay on the device (pinned chunk pipeline)
         ret = view_fast_binary(rd, fout, gpu, rec_out, sig_out, batch);
         eof = true;
     }
-    while (!eof && ret == 0) {
-        // ---- load (serial)
-        b.mem.clear();
-        while ((long)b.mem.size() < batch) {
-            b.mem.emplace_back();
-            const int rc = reader_next_mem(rd, b.mem.back());
-            if (rc <= 0) {
-                b.mem.pop_back();
-                if (rc < 0) {
-                    ERROR("%s", rd.err.c_str());
-                    ret = 1;
-                }
-                eof = true;
-                break;
-            }
-        }
-        const size_t n = b.mem.size();
-        if (n == 0 || ret) break;
-        b.rec.assign(n, Record());
-        b.aux_store.assign(n, std::vector<uint8_t>());
-        std::vector<const void *> ptrs(n);
-        std::vector<size_t> counts(n);
-
-        // ---- record decompression
-        std::vector<const uint8_t *> packed(n);
-        std::vector<size_t> packed_n(n);
-        if (rd.fmt == FMT_BINARY && (hdr.record_method == PRESS_ZLIB || hdr.record_method == PRESS_ZSTD)) {
-            for (size_t i = 0; i < n; ++i) {
-                ptrs[i] = b.mem[i].data();
-                counts[i] = b.mem[i].size();
-            }
-            b.inflated.assign(n, nullptr);
-            b.inflated_n.assign(n, 0);
-            const int rc = s5b_depress_batch_host(gpu, hdr.record_method == PRESS_ZLIB ? S5B_COMPRESS_ZLIB : S5B_COMPRESS_ZSTD,
-                                                  ptrs.data(), counts.data(), n, b.inflated.data(), b.inflated_n.data());
-            if (rc != S5B_OK) {
-                ERROR("record decompression failed: %s", s5b_strerror(rc));
-                ret = 1;
-                break;
-            }
-            for (size_t i = 0; i < n; ++i) {
-                packed[i] = static_cast<const uint8_t *>(b.inflated[i]);
-                packed_n[i] = b.inflated_n[i];
-            }
-        } else {
-            for (size_t i = 0; i < n; ++i) {
-                packed[i] = b.mem[i].data();
-                packed_n[i] = b.mem[i].size();
-            }
-        }
-        // ---- parse
-        std::atomic<int> bad(0);
-        if (rd.fmt == FMT_BINARY) {
-            parallel_for(n, threads, [&](size_t i) {
-                std::string e;
-                if (!record_parse_binary(packed[i], packed_n[i], hdr, hdr.signal_method, b.rec[i], e)) bad = 1;
-            });
-        } else {
-            parallel_for(n, threads, [&](size_t i) {
-                std::string e;
-                if (!record_parse_ascii(reinterpret_cast<const char *>(packed[i]), packed_n[i], hdr, b.rec[i], b.aux_store[i], e)) bad = 1;
-            });
-        }
-        if (bad) {
-            ERROR("%s", "a record could not be parsed");
-            ret = 1;
-            break;
-        }
-        // ---- signal decompression
-        std::vector<const int16_t *> sig(n);
-        if (rd.fmt == FMT_BINARY && hdr.signal_method != PRESS_NONE) {  // PRESS_* == S5B_COMPRESS_* (slow5_press.h:61-67)
-            for (size_t i = 0; i < n; ++i) {
-                ptrs[i] = b.rec[i].sig_bytes;
-                counts[i] = b.rec[i].sig_nbytes;
-            }
-            b.sig.assign(n, nullptr);
-            b.sig_n.assign(n, 0);
-            const int rc = s5b_depress_batch_host(gpu, hdr.signal_method, ptrs.data(), counts.data(), n, b.sig.data(),
-                                                  b.sig_n.data());
-            if (rc != S5B_OK) {
-                ERROR("signal decompression failed: %s", s5b_strerror(rc));
-                ret = 1;
-                break;
-            }
-            for (size_t i = 0; i < n; ++i) {
-                sig[i] = static_cast<const int16_t *>(b.sig[i]);
-                b.rec[i].len_raw_signal = b.sig_n[i] / 2;
-            }
-        } else {
-            for (size_t i = 0; i < n; ++i) {
-                sig[i] = reinterpret_cast<const int16_t *>(b.rec[i].sig_bytes);  // memcpy'd below where alignment matters
-                b.rec[i].len_raw_signal = b.rec[i].sig_nbytes / 2;
-            }
-        }
-
-        // ---- output
-        if (fmt_out == FMT_ASCII) {
-            std::vector<std::string> lines(n);
-            parallel_for(n, threads, [&](size_t i) {
-                Record &r = b.rec[i];
-                r.raw_signal.resize(r.len_raw_signal);
-                if (r.len_raw_signal) memcpy(r.raw_signal.data(), sig[i], r.len_raw_signal * 2);
-                record_to_ascii(r, hdr, lines[i]);
-                std::vector<int16_t>().swap(r.raw_signal);
-            });
-            for (size_t i = 0; i < n && ret == 0; ++i)
-                if (fwrite(lines[i].data(), 1, lines[i].size(), fout) != lines[i].size()) ret = 1;
-        } else {
-            // signal compression
-            std::vector<void *> svb(n, nullptr);
-            std::vector<size_t> svb_n(n, 0);
-            std::vector<const uint8_t *> store(n);
-            std::vector<size_t> store_n(n);
-            if (sig_out != PRESS_NONE) {
-                for (size_t i = 0; i < n; ++i) {
-                    ptrs[i] = sig[i];
-                    counts[i] = b.rec[i].len_raw_signal * 2;
-                }
-                const int rc = s5b_compress_batch_host(gpu, sig_out, ptrs.data(), counts.data(), n, svb.data(), svb_n.data());
-                if (rc != S5B_OK) {
-                    ERROR("signal compression failed: %s", s5b_strerror(rc));
-                    ret = 1;
-                }
-                for (size_t i = 0; i < n; ++i) {
-                    store[i] = static_cast<const uint8_t *>(svb[i]);
-                    store_n[i] = svb_n[i];
-                }
-            } else {
-                for (size_t i = 0; i < n; ++i) {
-                    store[i] = reinterpret_cast<const uint8_t *>(sig[i]);
-                    store_n[i] = b.rec[i].len_raw_signal * 2;
-                }
-            }
-            std::vector<std::vector<uint8_t>> rec_mem(n);
-            std::vector<uint32_t> splits(n, 0);
-            if (ret == 0) {
-                parallel_for(n, threads, [&](size_t i) {
-                    uint64_t at = 0;
-                    record_to_binary(b.rec[i], store[i], store_n[i], sig_out != PRESS_NONE, rec_mem[i], &at);
-                    // Huffman block split for the zlib encoder: where the svb-zd data bytes start
-                    if (sig_out == PRESS_SVB_ZD) splits[i] = (uint32_t)(at + 4 + (b.rec[i].len_raw_signal + 3) / 4);
-                });
-            }
-            for (void *p : svb) free(p);
-            std::vector<void *> z(n, nullptr);
-            std::vector<size_t> z_n(n, 0);
-            const bool rec_packed = rec_out == PRESS_ZLIB || rec_out == PRESS_ZSTD;
-            if (ret == 0 && rec_packed) {
-                for (size_t i = 0; i < n; ++i) {
-                    ptrs[i] = rec_mem[i].data();
-                    counts[i] = rec_mem[i].size();
-                }
-                const int rc = s5b_compress_records_host(gpu, rec_out == PRESS_ZSTD ? S5B_COMPRESS_ZSTD : S5B_COMPRESS_ZLIB,
-                                                         ptrs.data(), counts.data(), splits.data(), n, z.data(), z_n.data());
-                if (rc != S5B_OK) {
-                    ERROR("record compression failed: %s", s5b_strerror(rc));
-                    ret = 1;
-                }
-            }
-            for (size_t i = 0; i < n && ret == 0; ++i) {
-                const void *p = rec_packed ? z[i] : rec_mem[i].data();
-                const uint64_t sz = rec_packed ? z_n[i] : rec_mem[i].size();
-                if (fwrite(&sz, 8, 1, fout) != 1 || (sz && fwrite(p, 1, sz, fout) != sz)) ret = 1;  // slow5.c:4055-4060
-            }
-            for (void *p : z) free(p);
-        }
-        if (ret) ERROR("%s", "writing the output failed");
-        b.free_all();
-    }
-    b.free_all();
+    if (!eof && ret == 0)
+        ret = convert_records(hdr, rd.fmt, [&](std::vector<uint8_t> &mem) {
+            const int rc = reader_next_mem(rd, mem);
+            if (rc < 0) ERROR("%s", rd.err.c_str());
+            return rc;
+        }, fout, gpu, fmt_out, rec_out, sig_out, batch, threads);
     fflush(fout);
     if (ret == 0 && fmt_out == FMT_BINARY && write(fileno(fout), "5WOLB", 5) != 5) ret = 1;  // view.c:313
     if (fout != stdout) {
@@ -668,6 +681,7 @@ int view_main(int argc, char **argv) {
 }
 
 int index_main(int argc, char **argv);  // index_main.cpp
+int get_main(int argc, char **argv);    // get_main.cpp
 
 int main(int argc, char **argv) {
     if (argc >= 2 && (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V"))) {
@@ -675,8 +689,16 @@ int main(int argc, char **argv) {
         return 0;
     }
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
-        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n    index   create a SLOW5/BLOW5 index file\n");
+        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n    index   create a SLOW5/BLOW5 index file\n    get     display the read entry for each specified read id\n");
         return argc < 2 ? 1 : 0;
+    }
+    if (!strcmp(argv[1], "get")) {
+        const int rc = get_main(argc - 1, argv + 1);
+        if (rc != 0) {
+            fprintf(stderr, "[main::ERROR] get failed\n");
+            return EXIT_FAILURE;
+        }
+        return 0;
     }
     if (!strcmp(argv[1], "index")) {
         const int rc = index_main(argc - 1, argv + 1);
@@ -694,6 +716,6 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
-    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view, index)\n", argv[1]);
+    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view, index, get)\n", argv[1]);
     return EXIT_FAILURE;
 }
