@@ -321,7 +321,8 @@ int s5b_exzd_decode_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_i
     if (!ctx) return S5B_ERR_ARG;
     if (n_reads == 0) return S5B_OK;
     if (!d_in || !d_in_off || !d_in_len || !d_sig || !d_sig_off || !d_n_samples || !d_status) return S5B_ERR_ARG;
-    if ((reinterpret_cast<uintptr_t>(d_sig) & 15u) || (reinterpret_cast<uintptr_t>(d_in) & 15u)) return S5B_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_sig) & 15u) || (reinterpret_cast<uintptr_t>(d_in) & 15u) || (in_capacity & 15u))
+        return S5B_ERR_ARG;
     DeviceGuard g(ctx->device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     SvbDecodeArgs a{d_in, d_in_off, d_in_len, in_capacity, n_reads, d_sig, d_sig_off, d_n_samples, d_status,
