@@ -1,7 +1,7 @@
 #!/bin/bash
 TAG=${1:-exzd}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_exzd_gpu.py tests/test_view_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+timeout 300 python -m pytest tests/test_exzd_gpu.py tests/test_view_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log; tail -30 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --steps 50 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 python - <<PY

@@ -2,7 +2,7 @@
 # svb-zd kernel iteration on the GPU box: parity tests, A/B bench against the legacy kernels, ncu capture.
 TAG=${1:-svb}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_svbzd_gpu.py tests/test_view_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+timeout 240 python -m pytest tests/test_svbzd_gpu.py tests/test_view_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log; tail -5 gpurun_out/${TAG}_pytest.log
 timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_svbzd_gpu.py -x -q -k "kat or ragged or adversarial" > gpurun_out/${TAG}_sanitizer.log 2>&1
 tail -3 gpurun_out/${TAG}_sanitizer.log

@@ -3,7 +3,7 @@
 # usage: bash tools/gpu_variants.sh <tag> <name> [<name> ...]   ("base" = the product library)
 TAG=$1; shift
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_svbzd_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+timeout 240 python -m pytest tests/test_svbzd_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log; tail -3 gpurun_out/${TAG}_pytest.log
 for v in "$@"; do
   if [ "$v" = base ]; then unset S5B_LIBRARY; else export S5B_LIBRARY=$PWD/slow5tools_b200/libslow5b200_$v.so; fi

@@ -2,7 +2,7 @@
 # entropy-kernel iteration: parity tests + the bench's zlib/zstd stage timings
 TAG=${1:-zl}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_inflate_gpu.py tests/test_deflate_gpu.py tests/test_zstd_gpu.py tests/test_zstd_encode_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+timeout 300 python -m pytest tests/test_inflate_gpu.py tests/test_deflate_gpu.py tests/test_zstd_gpu.py tests/test_zstd_encode_gpu.py -x -q > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log; tail -4 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --steps 20 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 python - <<PY
