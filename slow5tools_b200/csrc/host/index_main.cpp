@@ -8,6 +8,8 @@
 // The reference walks the file with one fread per record and, for zlib records, inflates the first 256 bytes of each to
 // reach the read_id (:283-334).  Here the file is read in large chunks, the size chain is walked in place, and the
 // decompression of every record's head happens in one GPU batch per chunk (s5b_blow5_read_ids_host).
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <cerrno>
@@ -115,6 +117,91 @@ int index_main(int argc, char **argv) {
             }
         }
         const int fd = fileno(rd.fp);
+        // ---- mapped walk: the size chain and the record heads are read straight out of the page cache, so an
+        // uncompressed or zlib file costs one page touch per record instead of a copy of the whole file (only the
+        // first 256 bytes of a zlib record are ever looked at); zstd frames are decoded in full and read sequentially
+        struct stat sb;
+        const uint8_t *map = nullptr;
+        if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                map = static_cast<const uint8_t *>(m);
+                madvise(m, (size_t)sb.st_size, hdr.record_method == PRESS_ZSTD ? MADV_SEQUENTIAL : MADV_RANDOM);
+            }
+        }
+        if (map) {
+            const uint64_t fsize = (uint64_t)sb.st_size;
+            uint64_t pos = (uint64_t)start;
+            std::vector<uint8_t> ids;
+            std::vector<uint64_t> id_off, rec_off, offs, sizes;
+            std::vector<uint32_t> rec_len;
+            bool eof = false;
+            const size_t BATCH = 200000;
+            const uint64_t BATCH_BYTES = hdr.record_method == PRESS_ZSTD ? (256ull << 20) : ~0ull;  // full records go up
+            auto flush = [&]() -> bool {
+                if (rec_off.empty()) return true;
+                uint64_t guess = 0;
+                for (uint32_t l : rec_len) guess += l < 128u ? l : 128u;
+                ids.resize(guess + 4096);
+                id_off.resize(rec_off.size() + 1);
+                int rc = S5B_ERR_NOSPACE;
+                while (rc == S5B_ERR_NOSPACE) {
+                    rc = s5b_blow5_read_ids_host(gpu, hdr.record_method, map, fsize, rec_off.data(), rec_len.data(),
+                                                 rec_off.size(), ids.data(), ids.size(), id_off.data());
+                    if (rc == S5B_ERR_NOSPACE) {
+                        if (ids.size() > rec_off.size() * 65536ull + 4096) break;
+                        ids.resize(ids.size() * 2 + 65536);
+                    }
+                }
+                if (rc != S5B_OK) {
+                    IDX_ERROR("could not read the record ids: %s", s5b_strerror(rc));
+                    return false;
+                }
+                const bool ok = add_ids(ids.data(), id_off.data(), offs, sizes, slab, entries, seen);
+                rec_off.clear();
+                rec_len.clear();
+                offs.clear();
+                sizes.clear();
+                return ok;
+            };
+            uint64_t batch_bytes = 0;
+            while (!eof && ret == 0) {
+                const uint64_t left = fsize - pos;
+                if (left == 5 && memcmp(map + pos, "5WOLB", 5) == 0) {  // end-of-file marker (slow5_idx.c:252-262)
+                    eof = true;
+                    break;
+                }
+                if (left < 8) {
+                    IDX_ERROR("Malformed blow5 record. Failed to read the record size.%s",
+                              left == 0 ? " Missing blow5 end of file marker." : "");
+                    ret = 1;
+                    break;
+                }
+                uint64_t size;
+                memcpy(&size, map + pos, 8);
+                if (size > (1ull << 32) - 64 || left < 8 + size) {
+                    IDX_ERROR("%s", size > (1ull << 32) - 64 ? "implausible record size (corrupt file?)" : "blow5 record is truncated");
+                    ret = 1;
+                    break;
+                }
+                rec_off.push_back(pos + 8);
+                rec_len.push_back((uint32_t)size);
+                offs.push_back(pos);
+                sizes.push_back(8 + size);
+                pos += 8 + size;
+                batch_bytes += size;
+                if (rec_off.size() >= BATCH || batch_bytes >= BATCH_BYTES) {
+                    if (!flush()) ret = 1;
+                    batch_bytes = 0;
+                }
+            }
+            if (ret == 0 && !flush()) ret = 1;
+            munmap(const_cast<uint8_t *>(map), (size_t)fsize);
+            if (gpu) s5b_ctx_destroy(gpu);
+            reader_close(rd);
+            if (ret) return ret;
+            goto write_index;
+        }
         if (lseek(fd, start, SEEK_SET) < 0) {
             IDX_ERROR("%s", "cannot seek in the input file");
             return 1;
@@ -230,6 +317,7 @@ int index_main(int argc, char **argv) {
     reader_close(rd);
     if (ret) return ret;
 
+write_index:
     // ---- slow5_idx_write (slow5_idx.c:360-412)
     const std::string out_path = std::string(path) + ".idx";
     FILE *fo = fopen(out_path.c_str(), "wb");
