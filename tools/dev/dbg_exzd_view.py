@@ -1,7 +1,7 @@
 """dev: find records that do not survive raw -> zlib+ex-zd -> raw through the CLI"""
 import os, struct, subprocess, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 from slow5tools_b200 import synth
 import bench_view

@@ -1,7 +1,7 @@
 """dev: where does s5b_blow5_recode_host spend its time for zstd vs zlib input"""
 import os, struct, subprocess, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import slow5tools_b200 as s5
 from slow5tools_b200 import synth
