@@ -84,3 +84,23 @@ def test_compressed_inputs_match_the_reference(tmp_path, name):
     # default output of get is blow5 zlib+svb-zd on stdout
     d = run(CLI, [a] + pick)
     assert d.returncode == 0 and d.stdout[:6] == b"BLOW5\x01" and d.stdout[-5:] == b"5WOLB"
+
+
+@have_ref
+def test_custom_and_malformed_index(tmp_path):
+    a, b = copies(tmp_path, "exp_1_lossless.blow5")
+    ids = ids_of(a)
+    subprocess.check_call([CLI, "index", a], stderr=subprocess.DEVNULL)
+    moved = tmp_path / "elsewhere.idx"
+    shutil.move(a + ".idx", moved)
+    r = run(CLI, [a, "--index", str(moved), "--to", "slow5", ids[0]])
+    t = run(REF, [b, "--to", "slow5", ids[0]])
+    assert r.returncode == 0 and r.stdout == t.stdout and not os.path.exists(a + ".idx")
+    bad = tmp_path / "bad.idx"
+    raw = open(moved, "rb").read()
+    bad.write_bytes(b"X" + raw[1:])                                  # wrong magic number
+    assert run(CLI, [a, "--index", str(bad), "--to", "slow5", ids[0]]).returncode != 0
+    bad.write_bytes(raw[:-8])                                        # end marker missing
+    assert run(CLI, [a, "--index", str(bad), "--to", "slow5", ids[0]]).returncode != 0
+    bad.write_bytes(raw[:80] + raw[-8:])                             # entry cut short
+    assert run(CLI, [a, "--index", str(bad), "--to", "slow5", ids[0]]).returncode != 0
