@@ -8,16 +8,19 @@
 //   __slow5_streamvbyte_encode / _decode        thirdparty/streamvbyte/src/streamvbyte_{en,de}code.c
 // Output bytes are identical to the reference's (tests/test_svbzd_gpu.py checks against the oracle).
 //
-// Data movement (both kernels are HBM-streaming, integer-only, no tensor cores):
-//   * each warp owns one read at a time (dynamic work counter), loops over 256-sample iterations
-//     (8 samples / lane, one 128-bit shared-memory load per lane);
-//   * encode: the int16 signal is staged HBM->smem by 1-D bulk async copies (TMA engine, UBLKCP)
-//     into a 2-stage per-warp pipeline guarded by mbarriers; a warp prefix scan over the per-lane
-//     byte counts gives every lane its data offset; key and data bytes are assembled in smem and
-//     leave as 128-bit coalesced stores;
+// Data movement (both kernels are HBM-streaming, integer-only, no tensor cores; "v4"):
+//   * each warp owns one read at a time (dynamic work counter) and loops over 256-sample iterations;
+//   * encode: the int16 signal is staged HBM->smem by 1-D bulk async copies (TMA engine, UBLKCP.S.G)
+//     into a 2-stage per-warp pipeline guarded by mbarriers; a lane owns two quads of values
+//     (4*lane.. and 128+4*lane..) so that the byte scatter into shared memory is nearly free of bank
+//     conflicts; one warp prefix scan over both quads' byte counts gives every lane its data offsets;
+//     the data stream leaves once per 1024-sample chunk as one bulk shared->global copy (UBLKCP.G.S),
+//     the key bytes as two word stores per lane;
 //   * decode: the variable-length data stream is staged by bulk async copies into a 4 x 1 KiB
-//     per-warp ring; a warp prefix scan over the control-byte lengths resolves the per-lane data
-//     offsets, a second scan rebuilds the running sum; samples leave as 128-bit coalesced stores.
+//     per-warp ring (mirrored at its end so word loads never wrap); a warp prefix scan over the
+//     control-byte lengths resolves the per-lane data offsets; values are widened pairwise with PRMT,
+//     zigzag-decoded and prefix-summed two 16-bit lanes per register; a second scan carries the running
+//     sum across lanes; samples leave as 128-bit coalesced stores.
 #include <cstdlib>
 #include "s5b_kernels.h"
 #include "s5b_ptx.cuh"
