@@ -208,6 +208,36 @@ int s5b_compress_records_host(s5b_ctx_t *ctx, int method, const void *const *ptr
 int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
                           uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
                           uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes);
+/* The same transcoding for batches of any size, as a 3-lane CUDA-stream pipeline (the replacement of the work_db pool of
+ * src/thread.c:114 around src/view.c:35-57): the batch is cut into chunks of <= 64 Ki records / 256 MiB, and the H2D copy
+ * of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 run concurrently; between its two copies a chunk never
+ * synchronises with the host.  s5b_blow5_recode_host is this call with out_img_off = NULL.  out_img_off (optional,
+ * n+1 entries) receives the offset of every record's u64 size prefix inside h_out (entry n = *out_bytes): record i of the
+ * output is h_out[out_img_off[i] + 8 .. out_img_off[i+1]).  The record table must be ascending for the batch to be
+ * chunked (a table in any other order is processed as one chunk). */
+int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
+                                uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
+                                uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes, uint64_t *out_img_off);
+/* Device-resident form: payload d_in and image d_out live in HBM (d_in's allocation must extend to in_bytes rounded up to
+ * 16), the record table rec_off / rec_len is HOST memory (metadata the caller produced when it laid the batch out).  The
+ * call only enqueues work on the context's transcoding stream (s5b_ctx_recode_stream) and returns; after s5b_ctx_sync
+ * d_result[0] = image bytes written, d_result[1] = first error as a sign-extended S5B_ERR_* (0 = none; S5B_ERR_NOSPACE also
+ * when a record inflates to more than 4x + 1 KiB of its stored size -- the host form retries those, this form cannot --
+ * or the image outgrows out_cap).  d_img_off: optional device array of n+1 image offsets as above. */
+int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *d_in,
+                         uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n, uint8_t *d_out,
+                         uint64_t out_cap, uint64_t *d_result, uint64_t *d_img_off);
+/* waits for everything the context has enqueued */
+int s5b_ctx_sync(s5b_ctx_t *ctx);
+/* the cudaStream_t the device-resident transcoder enqueues on (for callers that order their own work against it) */
+void *s5b_ctx_recode_stream(s5b_ctx_t *ctx);
+/* Per-stage device timing of the transcoder: when enabled every stage of every chunk is bracketed by CUDA events on its
+ * stream; s5b_ctx_stage_report waits for them and returns accumulated milliseconds and launch-group counts per stage
+ * (arrays of s5b_stage_count() entries, named by s5b_stage_name), optionally resetting the totals. */
+int s5b_ctx_stage_timing(s5b_ctx_t *ctx, int enable);
+int s5b_ctx_stage_report(s5b_ctx_t *ctx, double *ms, uint64_t *count, int reset);
+int s5b_stage_count(void);
+const char *s5b_stage_name(int stage);
 /* The per-record work of index building (slow5_idx_build, slow5lib/src/slow5_idx.c:283-334) for a batch: the read_id of
  * every stored record.  Records compressed with in_rec (S5B_COMPRESS_NONE / ZLIB / ZSTD) are decompressed on the device --
  * for zlib only their first 256 bytes, like the reference's partial decompression (:290-310), with a full pass for the

@@ -65,6 +65,12 @@ size_t orc_exzd_compress(const int16_t *in, size_t count_bytes, uint8_t *out);
 /* ptr_depress_ex_zd (:1824 -> _v0 :1787-1822); 0 / -13 (SLOW5_ERR_PRESS) / -2 */
 int orc_exzd_depress(const uint8_t *in, size_t count, int16_t *out, size_t out_cap_samples, uint64_t *n_samples);
 
+/* ---- the per-record transcoding step of `slow5tools view` (oracle/blow5_oracle.c), slow5.c:2580-2950, :3928-4074 ----
+ * one stored record in (no size prefix), one output record out INCLUDING its u64 size prefix (malloc'd).  Methods are
+ * enum slow5_press_method values; records none / zlib, signals none / svb-zd / ex-zd. */
+int orc_blow5_recode_record(int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *in, size_t in_len,
+                            uint8_t **out, size_t *out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,9 +12,11 @@
 #include "oracle.h"
 #include <dlfcn.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 typedef void *(*solo_fn)(int method, const void *ptr, size_t count, size_t *n);
 
@@ -121,5 +123,147 @@ int refdrv_svbzd_roundtrip(const char *ref_lib_path, const int16_t *sig, const u
     for (uint64_t r = 0; r < n_reads; ++r) { free(enc[r]); free(dec[r]); }
     free(off); free(len); free(enc); free(dec); free(enc_n); free(dec_n); free(zoff); free(zlen);
     if (h) dlclose(h);
+    return rc;
+}
+
+/* ---- the full record path: what `slow5tools view` does to every record (src/view.c:35-57 depress_parse_rec_to_mem) ----
+ * Per record, in the pool's worker threads:
+ *     mem = malloc + copy of the stored record          (slow5_get_next_mem, slow5.c:3233-3281, minus the fread)
+ *     slow5_decode(&mem, &bytes, &rec, from)            (slow5.h:658 -> slow5_rec_depress_parse, slow5.c:2580)
+ *     slow5_encode(&out, &out_bytes, rec, to)           (slow5.h:660 -> slow5_press_init + slow5_rec_to_mem, slow5.c:4083)
+ *     slow5_rec_free(rec); free(mem)
+ * `from` / `to` are slow5_file_t handles opened by the reference itself ("w" mode files in tmpdir with
+ * slow5_set_press(in/out methods)), so every byte of the work is the reference's own public API.  With ref_lib_path
+ * NULL the oracle's restatement (blow5_oracle.c) stands in ("port").  The outputs are concatenated into `out` (the
+ * file image, [u64 size][record] per record) after the clock stops; out may be NULL to time only.
+ * Returns 0, -1 (dlopen / dlsym / open failed), -2 (a record failed), -4 (out too small; *out_bytes = bytes needed). */
+typedef struct {
+    int use_ref;
+    int in_rec, in_sig, out_rec, out_sig;
+    void *from, *to;
+    int (*decode)(char **, size_t *, void **, void *);
+    int (*encode)(char **, size_t *, void *, void *);
+    void (*rec_free)(void *);
+    const uint8_t *in;
+    const uint64_t *rec_off;
+    const uint32_t *rec_len;
+    uint8_t **out;
+    size_t *out_n;
+    uint64_t n, next, grain;
+    int failed;
+} rjob_t;
+
+static void *rworker(void *arg) {
+    rjob_t *j = (rjob_t *) arg;
+    for (;;) {
+        uint64_t r0 = __sync_fetch_and_add(&j->next, j->grain);
+        if (r0 >= j->n) break;
+        uint64_t r1 = r0 + j->grain < j->n ? r0 + j->grain : j->n;
+        for (uint64_t r = r0; r < r1; ++r) {
+            j->out[r] = NULL;
+            j->out_n[r] = 0;
+            if (j->use_ref) {
+                size_t bytes = j->rec_len[r];
+                char *mem = (char *) malloc(bytes ? bytes : 1);
+                if (!mem) { j->failed = 1; continue; }
+                memcpy(mem, j->in + j->rec_off[r], bytes);
+                void *rec = NULL;
+                if (j->decode(&mem, &bytes, &rec, j->from) != 0) { free(mem); j->failed = 1; continue; }
+                free(mem);
+                char *o = NULL;
+                size_t on = 0;
+                if (j->encode(&o, &on, rec, j->to) != 0) { j->rec_free(rec); j->failed = 1; continue; }
+                j->rec_free(rec);
+                j->out[r] = (uint8_t *) o;
+                j->out_n[r] = on;
+            } else {
+                if (orc_blow5_recode_record(j->in_rec, j->in_sig, j->out_rec, j->out_sig, j->in + j->rec_off[r], j->rec_len[r],
+                                            &j->out[r], &j->out_n[r]) != 0)
+                    j->failed = 1;
+            }
+        }
+    }
+    return NULL;
+}
+
+int refdrv_record_pass(const char *ref_lib_path, const char *tmpdir, int in_rec, int in_sig, int out_rec, int out_sig,
+                       const uint8_t *in, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n, int threads,
+                       uint8_t *out, uint64_t out_cap, uint64_t *out_bytes, uint64_t *out_off, double *seconds) {
+    rjob_t j;
+    memset(&j, 0, sizeof j);
+    void *h = NULL;
+    int (*closef)(void *) = NULL;
+    char pa[4096], pb[4096];
+    if (ref_lib_path) {
+        h = dlopen(ref_lib_path, RTLD_NOW | RTLD_LOCAL);
+        if (!h) return -1;
+        void *(*openf)(const char *, const char *) = (void *(*)(const char *, const char *)) dlsym(h, "slow5_open");
+        int (*setp)(void *, int, int) = (int (*)(void *, int, int)) dlsym(h, "slow5_set_press");
+        void (*loglvl)(int) = (void (*)(int)) dlsym(h, "slow5_set_log_level");
+        closef = (int (*)(void *)) dlsym(h, "slow5_close");
+        j.decode = (int (*)(char **, size_t *, void **, void *)) dlsym(h, "slow5_decode");
+        j.encode = (int (*)(char **, size_t *, void *, void *)) dlsym(h, "slow5_encode");
+        j.rec_free = (void (*)(void *)) dlsym(h, "slow5_rec_free");
+        if (!openf || !setp || !closef || !j.decode || !j.encode || !j.rec_free) { dlclose(h); return -1; }
+        if (loglvl) loglvl(1 /* SLOW5_LOG_ERR */);
+        snprintf(pa, sizeof pa, "%s/refdrv_from_%d.blow5", tmpdir, (int) getpid());
+        snprintf(pb, sizeof pb, "%s/refdrv_to_%d.blow5", tmpdir, (int) getpid());
+        /* `from` must look like a file that was READ (header->aux_meta == NULL without aux columns, methods taken from
+         * the header): let the reference write an empty file with the input methods, then open that for reading */
+        int (*hdrw)(void *) = (int (*)(void *)) dlsym(h, "slow5_hdr_write");
+        void *tmp = openf(pa, "w");
+        if (!hdrw || !tmp || setp(tmp, in_rec, in_sig) != 0 || hdrw(tmp) < 0) {
+            if (tmp) closef(tmp);
+            dlclose(h);
+            return -1;
+        }
+        closef(tmp);
+        j.from = openf(pa, "r");
+        j.to = openf(pb, "w");
+        if (!j.from || !j.to || setp(j.to, out_rec, out_sig) != 0) {
+            if (j.from) closef(j.from);
+            if (j.to) closef(j.to);
+            dlclose(h);
+            return -1;
+        }
+        j.use_ref = 1;
+    }
+    if (threads < 1) threads = 1;
+    j.in_rec = in_rec; j.in_sig = in_sig; j.out_rec = out_rec; j.out_sig = out_sig;
+    j.in = in; j.rec_off = rec_off; j.rec_len = rec_len;
+    j.n = n; j.next = 0; j.grain = 16;
+    j.out = (uint8_t **) calloc(n ? n : 1, sizeof(uint8_t *));
+    j.out_n = (size_t *) calloc(n ? n : 1, sizeof(size_t));
+    pthread_t *t = (pthread_t *) malloc(sizeof(pthread_t) * (size_t) threads);
+    double t0 = now_s();
+    for (int i = 0; i < threads; ++i) pthread_create(&t[i], NULL, rworker, &j);
+    for (int i = 0; i < threads; ++i) pthread_join(t[i], NULL);
+    *seconds = now_s() - t0;
+    free(t);
+    int rc = j.failed ? -2 : 0;
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < n; ++r) total += j.out_n[r];
+    *out_bytes = total;
+    if (rc == 0 && out) {
+        if (total > out_cap) rc = -4;
+        else {
+            uint64_t at = 0;
+            for (uint64_t r = 0; r < n; ++r) {
+                if (out_off) out_off[r] = at;
+                memcpy(out + at, j.out[r], j.out_n[r]);
+                at += j.out_n[r];
+            }
+            if (out_off) out_off[n] = at;
+        }
+    }
+    for (uint64_t r = 0; r < n; ++r) free(j.out[r]);
+    free(j.out); free(j.out_n);
+    if (j.use_ref) {
+        closef(j.from);
+        closef(j.to);
+        remove(pa);
+        remove(pb);
+        dlclose(h);
+    }
     return rc;
 }

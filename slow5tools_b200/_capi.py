@@ -74,6 +74,15 @@ _SIGS = {
     "s5b_depress_batch_host": (C.c_int, [_vp, C.c_int, _P(_vp), _P(_sz), _sz, _P(_vp), _P(_sz)]),
     "s5b_blow5_recode_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _u64, _vp, _vp, _u64, _vp, _u64,
                                         _P(_u64)]),
+    "s5b_blow5_recode_batch_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _u64, _vp, _vp, _u64, _vp, _u64,
+                                              _P(_u64), _vp]),
+    "s5b_blow5_recode_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "s5b_ctx_sync": (C.c_int, [_vp]),
+    "s5b_ctx_recode_stream": (_vp, [_vp]),
+    "s5b_ctx_stage_timing": (C.c_int, [_vp, C.c_int]),
+    "s5b_ctx_stage_report": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "s5b_stage_count": (C.c_int, []),
+    "s5b_stage_name": (C.c_char_p, [C.c_int]),
     "s5b_ptr_compress_solo": (_vp, [C.c_int, _vp, _sz, _P(_sz)]),
     "s5b_ptr_depress_solo": (_vp, [C.c_int, _vp, _sz, _P(_sz)]),
     "s5b_last_error": (C.c_int, []),

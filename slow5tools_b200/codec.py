@@ -191,6 +191,49 @@ class Codec:
             break
         return rc, h_out[:nb.value].tobytes() if rc == 0 else None
 
+    # ---- whole-batch record transcoding (the `view` worker for a batch; src/view.c:254-301) ----------------
+    def blow5_recode_batch_host(self, in_rec, in_sig, out_rec, out_sig, h_in, in_bytes, rec_off, rec_len, h_out,
+                                img_off=None, check=True):
+        """s5b_blow5_recode_batch_host: h_in / h_out host tensors or arrays (pinned for speed), rec_off / rec_len numpy
+        (uint64 / uint32).  Returns (rc, image bytes); img_off (uint64[n+1]) receives the image offsets."""
+        n = len(rec_len)
+        nb = C.c_uint64()
+        cap = h_out.numel() if isinstance(h_out, torch.Tensor) else h_out.size
+        rc = lib.s5b_blow5_recode_batch_host(self._h, in_rec, in_sig, out_rec, out_sig, _ptr(h_in), int(in_bytes),
+                                             _ptr(rec_off), _ptr(rec_len), n, _ptr(h_out), cap, C.byref(nb), _ptr(img_off))
+        if check:
+            self._check(rc, "s5b_blow5_recode_batch_host")
+        return rc, int(nb.value)
+
+    def blow5_recode_dev(self, in_rec, in_sig, out_rec, out_sig, d_in, in_bytes, rec_off, rec_len, d_out, d_result,
+                         d_img_off=None):
+        """s5b_blow5_recode_dev: payload / image in HBM (torch uint8), record table numpy on the host; asynchronous --
+        call sync() before reading d_result (uint64[2]: image bytes, first error)."""
+        self._check(lib.s5b_blow5_recode_dev(self._h, in_rec, in_sig, out_rec, out_sig, _ptr(d_in), int(in_bytes),
+                                             _ptr(rec_off), _ptr(rec_len), len(rec_len), _ptr(d_out), d_out.numel(),
+                                             _ptr(d_result), _ptr(d_img_off)), "s5b_blow5_recode_dev")
+
+    def sync(self):
+        self._check(lib.s5b_ctx_sync(self._h), "s5b_ctx_sync")
+
+    def recode_stream(self):
+        """torch view of the stream the device-resident transcoder enqueues on (for CUDA-event timing)."""
+        h = lib.s5b_ctx_recode_stream(self._h)
+        if not h:
+            raise S5BError(_capi.ERR.DEVICE, "s5b_ctx_recode_stream")
+        return torch.cuda.ExternalStream(h, device=torch.device("cuda", self.device))
+
+    def stage_timing(self, enable=True):
+        self._check(lib.s5b_ctx_stage_timing(self._h, 1 if enable else 0), "s5b_ctx_stage_timing")
+
+    def stage_report(self, reset=True):
+        """{stage name: (milliseconds, launch groups)} accumulated since the last reset."""
+        k = lib.s5b_stage_count()
+        ms = (C.c_double * k)()
+        cnt = (C.c_uint64 * k)()
+        self._check(lib.s5b_ctx_stage_report(self._h, ms, cnt, 1 if reset else 0), "s5b_ctx_stage_report")
+        return {lib.s5b_stage_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k)}
+
     def compress_batch(self, method, bufs):
         return self._batch(lib.s5b_compress_batch_host, method, bufs)
 

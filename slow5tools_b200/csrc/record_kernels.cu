@@ -47,14 +47,15 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
 constexpr int RK_WARPS = 8;
 
 __global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
-                                  int sig_is_svb, RecArrays a) {
+                                  int sig_is_svb, RecArrays a, const int32_t *in_status) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint8_t *p = rec + rec_off[r];
     const uint64_t len = rec_len[r];
-    int32_t st = S5B_OK;
+    int32_t st = in_status ? in_status[r] : S5B_OK;  // a record whose decompression failed is not looked at
     uint32_t head = 0, ns = 0, sig_at = 0, sig_bytes = 0, aux = 0;
-    if (len < 2) {
+    if (st != S5B_OK) {
+    } else if (len < 2) {
         st = S5B_ERR_PRESS;
     } else {
         const uint32_t rid = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
@@ -81,6 +82,9 @@ __global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, c
                 } else {
                     ns = (uint32_t)lrs;
                 }
+                // every sample of a compressed signal takes at least one stream byte (slow5_press.c:1062-1079, :1721-1776):
+                // a count beyond that cannot decode, and the stages downstream size their slabs from it
+                if (sig_is_svb && ns > sb) st = S5B_ERR_PRESS;
                 aux = (uint32_t)(len - sig_at - sb);
             }
         }
@@ -149,15 +153,76 @@ __global__ void __launch_bounds__(RK_WARPS * 32) rec_pack_kernel(const uint8_t *
 
 __global__ void __launch_bounds__(RK_WARPS * 32) image_gather_kernel(const uint8_t *src, const uint64_t *src_off,
                                                                      const uint32_t *len, uint64_t n, uint8_t *img,
-                                                                     const uint64_t *img_off) {
+                                                                     const uint64_t *img_off, const uint64_t *base_ptr,
+                                                                     const uint64_t *res, uint64_t *abs_off) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * RK_WARPS + (threadIdx.x >> 5), nw = (uint64_t)gridDim.x * RK_WARPS;
+    if (res && (int32_t)res[1] == S5B_ERR_NOSPACE && res[2] == ~0ull) return;  // the image does not fit: nothing is written
+    const uint64_t base = base_ptr ? *base_ptr : 0;
     for (uint64_t r = warp; r < n; r += nw) {
-        uint8_t *o = img + img_off[r];
+        uint8_t *o = img + base + img_off[r];
+        if (abs_off && lane == 0) {
+            abs_off[r] = base + img_off[r];
+            if (r == n - 1) abs_off[n] = base + img_off[n];
+        }
         const uint64_t sz = len[r];
         if (lane < 8) o[lane] = (uint8_t)(sz >> (8 * lane));  // record size prefix, slow5.c:4055-4060
         warp_copy(o + 8, src + src_off[r], len[r], lane);
     }
+}
+
+// End of a transcoding pass over one chunk: the first failed record over up to four per-record status arrays (lowest
+// record index wins, like a serial loop over the batch would report), the chunk's image size, the capacity check.
+// res[0] = image bytes, res[1] = error code (int32), res[2] = its record index (~0 for a call-level error).
+__global__ void recode_finish_kernel(uint64_t n, const uint64_t *img_off, const uint64_t *base_ptr, uint64_t cap,
+                                     const int32_t *s0, const int32_t *s1, const int32_t *s2, const int32_t *s3, uint64_t *res) {
+    __shared__ unsigned long long best;
+    if (threadIdx.x == 0) best = ~0ull;
+    __syncthreads();
+    unsigned long long mine = ~0ull;
+    for (uint64_t r = threadIdx.x; r < n; r += blockDim.x) {
+        int32_t e = S5B_OK;
+        if (s0 && s0[r] != S5B_OK) e = s0[r];
+        else if (s1 && s1[r] != S5B_OK) e = s1[r];
+        else if (s2 && s2[r] != S5B_OK) e = s2[r];
+        else if (s3 && s3[r] != S5B_OK) e = s3[r];
+        if (e != S5B_OK) {
+            mine = (r << 8) | (uint32_t)(-e & 0xff);
+            break;  // this thread's later records have higher indices
+        }
+    }
+    if (mine != ~0ull) atomicMin(&best, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t total = img_off[n];
+        const uint64_t base = base_ptr ? *base_ptr : 0;
+        res[0] = total;
+        if (best != ~0ull) {
+            res[1] = (uint64_t)(uint32_t)(-(int32_t)(best & 0xff));
+            res[2] = best >> 8;
+        } else if (cap && base + total > cap) {
+            res[1] = (uint64_t)(uint32_t)S5B_ERR_NOSPACE;
+            res[2] = ~0ull;
+        } else {
+            res[1] = 0;
+            res[2] = 0;
+        }
+    }
+}
+// base += the chunk's image bytes, unless the chunk failed (a failed chunk is redone by the careful path or ends the call);
+// acc (optional) accumulates: acc[0] = total image bytes so far, acc[1] = first error of the whole call
+__global__ void recode_advance_kernel(uint64_t *base_ptr, const uint64_t *res, uint64_t *acc) {
+    const int32_t e = (int32_t)res[1];
+    if (e == S5B_OK) {
+        if (base_ptr) *base_ptr += res[0];
+        if (acc) acc[0] += res[0];
+    } else if (acc && (int32_t)acc[1] == S5B_OK) {
+        acc[1] = (uint64_t)(uint32_t)e;
+    }
+}
+__global__ void rebase_off_kernel(uint64_t *dst, const uint64_t *src, uint64_t n, uint64_t sub) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) dst[r] = src[r] - sub;
 }
 
 __global__ void rec_sig_abs_kernel(const uint64_t *rec_off, RecArrays a, uint64_t n, uint64_t *out) {
@@ -191,9 +256,23 @@ unsigned rk_grid(uint64_t n) {
 }  // namespace
 
 cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
-                              int sig_is_svb, RecArrays a, cudaStream_t st) {
+                              int sig_is_svb, RecArrays a, cudaStream_t st, const int32_t *in_status) {
     if (!n) return cudaSuccess;
-    rec_locate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, rec_off, rec_len, n, sig_is_svb, a);
+    rec_locate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, rec_off, rec_len, n, sig_is_svb, a, in_status);
+    return cudaGetLastError();
+}
+cudaError_t launch_recode_finish(uint64_t n, const uint64_t *img_off, const uint64_t *base_ptr, uint64_t cap, const int32_t *s0,
+                                 const int32_t *s1, const int32_t *s2, const int32_t *s3, uint64_t *res, cudaStream_t st) {
+    recode_finish_kernel<<<1, 1024, 0, st>>>(n, img_off, base_ptr, cap, s0, s1, s2, s3, res);
+    return cudaGetLastError();
+}
+cudaError_t launch_recode_advance(uint64_t *base_ptr, const uint64_t *res, uint64_t *acc, cudaStream_t st) {
+    recode_advance_kernel<<<1, 1, 0, st>>>(base_ptr, res, acc);
+    return cudaGetLastError();
+}
+cudaError_t launch_rebase_off(uint64_t *dst, const uint64_t *src, uint64_t n, uint64_t sub, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    rebase_off_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, src, n, sub);
     return cudaGetLastError();
 }
 cudaError_t launch_rec_sig_abs(const uint64_t *rec_off, RecArrays a, uint64_t n, uint64_t *out, cudaStream_t st) {
@@ -227,9 +306,10 @@ cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArra
     return cudaGetLastError();
 }
 cudaError_t launch_image_gather(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n, uint8_t *img,
-                                const uint64_t *img_off, cudaStream_t st) {
+                                const uint64_t *img_off, cudaStream_t st, const uint64_t *base_ptr, const uint64_t *res,
+                                uint64_t *abs_off) {
     if (!n) return cudaSuccess;
-    image_gather_kernel<<<rk_grid(n), RK_WARPS * 32, 0, st>>>(src, src_off, len, n, img, img_off);
+    image_gather_kernel<<<rk_grid(n), RK_WARPS * 32, 0, st>>>(src, src_off, len, n, img, img_off, base_ptr, res, abs_off);
     return cudaGetLastError();
 }
 

@@ -16,111 +16,13 @@
 
 #include "../../include/slow5b200.h"
 #include "s5b_kernels.h"
+#include "s5b_ctx.h"
 #include "zstd_core.h"
 
 using namespace s5b;
 
 namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        want = (want + 255) & ~size_t(255);
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-struct PinBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-constexpr int NSLOT = 2;
-
-struct PipeSlot {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
-    DevBuf d_a, d_b, d_c;       // payload in / slotted out / dense out
-    DevBuf d_meta;              // offsets, lengths, statuses
-    DevBuf d_scratch;           // scan scratch
-    PinBuf h_meta;              // pinned mirror of d_meta (both directions)
-    unsigned long long *d_counter = nullptr;
-};
-
-}  // namespace
-
-struct s5b_ctx {
-    int device = 0;
-    int num_sms = 0;
-    int enc_bps = 0, dec_bps = 0, inf_bps = 0, def_bps = 0, zd_bps = 0, ze_bps = 0, xe_bps = 0, xd_bps = 0;
-    DevBuf zd_scratch;
-    cudaStream_t stream = nullptr;  // default stream for *_dev calls
-    unsigned long long *d_counter = nullptr;
-    DevBuf d_scratch;
-    PipeSlot slot[NSLOT];
-    PinBuf h_stage_in, h_stage_out;  // pointer-array forms
-    DevBuf r_in, r_infl, r_sig, r_svb, r_packed, r_z, r_img, r_meta, r_scratch;  // s5b_blow5_recode_host
-    uint64_t launches = 0;
-    size_t chunk_bytes = 32u << 20;  // e2e is flat between 16 and 128 MiB (PCIe bound), 32 MiB marginally best
-    std::string last_cuda_error;
-};
-
-namespace {
-
 thread_local int tl_last_error = 0;
-
-int cuda_fail(s5b_ctx *c, cudaError_t e) {
-    if (c) c->last_cuda_error = cudaGetErrorString(e);
-    (void)cudaGetLastError();
-    return e == cudaErrorMemoryAllocation ? S5B_ERR_MEM : S5B_ERR_DEVICE;
-}
-#define CU(call)                                  \
-    do {                                          \
-        cudaError_t e__ = (call);                 \
-        if (e__ != cudaSuccess) return cuda_fail(ctx, e__); \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
-
 }  // namespace
 
 extern "C" {
@@ -209,6 +111,14 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
         long v = atol(e);
         if (v > 0) ctx->chunk_bytes = (size_t)v << 20;
     }
+    if (const char *e = getenv("S5B_RECODE_CHUNK")) {
+        long v = atol(e);
+        if (v > 0) ctx->recode_chunk_records = (size_t)v;
+    }
+    if (const char *e = getenv("S5B_RECODE_CHUNK_MB")) {
+        long v = atol(e);
+        if (v > 0) ctx->recode_chunk_bytes = (size_t)v << 20;
+    }
     if (!ok) {
         s5b_ctx_destroy(ctx);
         return S5B_ERR_DEVICE;
@@ -238,6 +148,7 @@ void s5b_ctx_destroy(s5b_ctx_t *ctx) {
     for (DevBuf *b : {&ctx->r_in, &ctx->r_infl, &ctx->r_sig, &ctx->r_svb, &ctx->r_packed, &ctx->r_z, &ctx->r_img, &ctx->r_meta,
                       &ctx->r_scratch})
         b->release();
+    recode_lanes_release(ctx);
     ctx->h_stage_in.release();
     ctx->h_stage_out.release();
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -357,12 +268,14 @@ int s5b_zstd_content_size(const void *frame, size_t len, uint64_t *size) {
     return S5B_OK;
 }
 
-static int zstd_launch(s5b_ctx_t *ctx, const InflateArgs &a, cudaStream_t st) {
+}  // extern "C"
+int s5b::zstd_launch(s5b_ctx *ctx, const InflateArgs &a, cudaStream_t st) {
     CU(ctx->zd_scratch.reserve(zstd_decode_scratch_bytes(ctx->num_sms, ctx->zd_bps)));
     CU(launch_zstd_decode(a, ctx->num_sms, ctx->zd_bps, ctx->zd_scratch.p, st));
     ctx->launches += 1;
     return S5B_OK;
 }
+extern "C" {
 
 int s5b_zstd_decode_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
                         uint64_t in_capacity, uint64_t n_reads, uint8_t *d_out, const uint64_t *d_out_off,
@@ -1177,9 +1090,10 @@ void s5b_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
-int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
-                          uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
-                          uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes) {
+}  // extern "C"
+int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
+                           uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
+                           uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes) {
     if (!ctx || !out_bytes) return S5B_ERR_ARG;
     *out_bytes = 0;
     if (n == 0) return S5B_OK;
@@ -1413,6 +1327,7 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
     return first_err;
 }
 
+extern "C" {
 // ---------------------------------------------------------------------------------------------
 // read ids of a batch of stored records: the per-record work of slow5_idx_build (slow5_idx.c:283-334)
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,152 @@
+// s5b_ctx.h -- internal: the codec context shared by the C-ABI translation units (s5b_capi.cu, recode_engine.cu).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/slow5b200.h"
+#include "s5b_kernels.h"
+
+namespace s5b {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t slack = bytes / 4;
+        if (slack > (64u << 20)) slack = 64u << 20;
+        size_t want = bytes + slack + 256;
+        want = (want + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int NSLOT = 2;
+
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf d_a, d_b, d_c;       // payload in / slotted out / dense out
+    DevBuf d_meta;              // offsets, lengths, statuses
+    DevBuf d_scratch;           // scan scratch
+    PinBuf h_meta;              // pinned mirror of d_meta (both directions)
+    unsigned long long *d_counter = nullptr;
+};
+
+// ---- the record transcoder's pipeline lanes (recode_engine.cu) --------------------------------
+constexpr int NLANE = 3;
+// stages of a transcoding pass, for the optional per-stage CUDA-event timing (s5b_ctx_stage_timing)
+enum Stage { ST_H2D = 0, ST_REC_DEPRESS, ST_GLUE, ST_SIG_DEPRESS, ST_SIG_PRESS, ST_PACK, ST_REC_PRESS, ST_IMAGE, ST_D2H,
+             ST_COUNT };
+
+struct RecodeLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t front = nullptr;     // everything up to the (size, status) read-back of the chunk in flight
+    DevBuf in, infl, sig, svb, packed, z, img, meta, scratch, zd_scratch, tab;
+    PinBuf h_tab;                    // pinned staging of the chunk's record table (up) and image offsets (down)
+    unsigned long long *d_counter = nullptr;
+    uint64_t *d_res = nullptr;       // [0] image bytes of the chunk, [1] first error (int32 in the low half), [2] its record
+    uint64_t *h_res = nullptr;       // pinned mirror
+    void release();
+};
+
+struct StageTimer {
+    bool enabled = false;
+    struct Mark { cudaEvent_t a, b; int stage; };
+    std::vector<Mark> marks;         // recorded, not yet read
+    std::vector<cudaEvent_t> pool;   // free events
+    double ms[ST_COUNT] = {0};
+    uint64_t count[ST_COUNT] = {0};
+};
+
+}  // namespace s5b
+
+struct s5b_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int enc_bps = 0, dec_bps = 0, inf_bps = 0, def_bps = 0, zd_bps = 0, ze_bps = 0, xe_bps = 0, xd_bps = 0;
+    s5b::DevBuf zd_scratch;
+    cudaStream_t stream = nullptr;  // default stream for *_dev calls
+    unsigned long long *d_counter = nullptr;
+    s5b::DevBuf d_scratch;
+    s5b::PipeSlot slot[s5b::NSLOT];
+    s5b::PinBuf h_stage_in, h_stage_out;  // pointer-array forms
+    s5b::DevBuf r_in, r_infl, r_sig, r_svb, r_packed, r_z, r_img, r_meta, r_scratch;  // the careful (synchronous) transcoder
+    s5b::RecodeLane lane[s5b::NLANE];     // the pipelined transcoder (lazily created)
+    bool lanes_ready = false;
+    uint64_t *d_img_base = nullptr;       // running output offset of a device-resident transcoding pass
+    s5b::StageTimer timer;
+    uint64_t launches = 0;
+    size_t chunk_bytes = 32u << 20;  // e2e is flat between 16 and 128 MiB (PCIe bound), 32 MiB marginally best
+    size_t recode_chunk_records = 65536;  // records per pipeline chunk of the transcoder (S5B_RECODE_CHUNK)
+    size_t recode_chunk_bytes = 256u << 20;
+    std::string last_cuda_error;
+};
+
+namespace s5b {
+
+inline int cuda_fail(s5b_ctx *c, cudaError_t e) {
+    if (c) c->last_cuda_error = cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? S5B_ERR_MEM : S5B_ERR_DEVICE;
+}
+#define CU(call)                                  \
+    do {                                          \
+        cudaError_t e__ = (call);                 \
+        if (e__ != cudaSuccess) return s5b::cuda_fail(ctx, e__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// the careful transcoder of one chunk (host syncs between stages, inflate-slot retry, exact error reporting); lives in
+// s5b_capi.cu and is the fallback of the pipelined engine
+int recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in, uint64_t in_bytes,
+                      const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n, uint8_t *h_out, uint64_t out_cap,
+                      uint64_t *out_bytes);
+int zstd_launch(s5b_ctx *ctx, const InflateArgs &a, cudaStream_t st);
+void recode_lanes_release(s5b_ctx *ctx);
+
+}  // namespace s5b

@@ -101,8 +101,9 @@ struct RecArrays {           // per-record device arrays, n entries each (SoA)
     uint32_t *aux_len;
     int32_t *status;
 };
+// in_status (optional): the status the record decompression left; a failed record is marked and skipped
 cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
-                              int sig_is_svb, RecArrays a, cudaStream_t st);
+                              int sig_is_svb, RecArrays a, cudaStream_t st, const int32_t *in_status = nullptr);
 // elementwise size planning: mode selects which length is written to out[]
 enum RecPlan { PLAN_SIG_SAMPLES = 0, PLAN_SVB_BOUND = 1, PLAN_PACKED_LEN = 2, PLAN_ZLIB_BOUND = 3, PLAN_IMAGE_LEN = 4,
                PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7, PLAN_EXZD_BOUND = 8 };
@@ -120,8 +121,20 @@ cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArra
                             const uint64_t *sig_src_off, const uint32_t *sig_src_len, int sig_src_is_samples,
                             int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st);
 // file image: [u64 size][bytes] per record, back to back
+// base_ptr (optional, device): added to every image offset; res (optional): the finish kernel's verdict -- an image that
+// does not fit is not written; abs_off (optional, n+1 entries): absolute image offset of every record's size prefix
 cudaError_t launch_image_gather(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n, uint8_t *img,
-                                const uint64_t *img_off, cudaStream_t st);
+                                const uint64_t *img_off, cudaStream_t st, const uint64_t *base_ptr = nullptr,
+                                const uint64_t *res = nullptr, uint64_t *abs_off = nullptr);
+// the sync-free end of a transcoding pass over one chunk (record_kernels.cu)
+cudaError_t launch_recode_finish(uint64_t n, const uint64_t *img_off, const uint64_t *base_ptr, uint64_t cap, const int32_t *s0,
+                                 const int32_t *s1, const int32_t *s2, const int32_t *s3, uint64_t *res, cudaStream_t st);
+cudaError_t launch_recode_advance(uint64_t *base_ptr, const uint64_t *res, uint64_t *acc, cudaStream_t st);
+cudaError_t launch_rebase_off(uint64_t *dst, const uint64_t *src, uint64_t n, uint64_t sub, cudaStream_t st);
+// content sizes of a batch of zstd frames (slow5_press.c:1206-1211): size[r], or status[r] = S5B_ERR_PRESS when the frame
+// carries none; sizes above len * mul + add get S5B_ERR_NOSPACE and size 0 (the careful path sizes those exactly)
+cudaError_t launch_zstd_sizes(const uint8_t *in, const uint64_t *off, const uint32_t *len, uint64_t n, uint32_t mul,
+                              uint32_t add, uint32_t *size, int32_t *status, cudaStream_t st);
 
 // dense gather: scratch must hold >= compact_scratch_bytes(n_reads)
 size_t compact_scratch_bytes(uint64_t n_reads);

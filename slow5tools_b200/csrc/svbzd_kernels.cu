@@ -796,25 +796,7 @@ __global__ void __launch_bounds__(COPY_WARPS * 32) gather_copy_kernel(const uint
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-// S5B_SVBZD_LEGACY=1 (read once) routes both launchers to the round-1 "v3" kernels for A/B timing
-namespace v3 {
-int svbzd_encode_blocks_per_sm();
-int svbzd_decode_blocks_per_sm();
-cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, unsigned grid, cudaStream_t st);
-cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, unsigned grid, cudaStream_t st);
-int enc_warps();
-int dec_warps();
-}  // namespace v3
-static bool use_legacy() {
-    static const bool v = [] {
-        const char *e = getenv("S5B_SVBZD_LEGACY");
-        return e && e[0] == '1';
-    }();
-    return v;
-}
-
 int svbzd_encode_blocks_per_sm() {
-    if (use_legacy()) return v3::svbzd_encode_blocks_per_sm();
     int n = 0;
     if (cudaFuncSetAttribute(svbzd_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(sizeof(EncWarpSmem) * ENC_WARPS)) != cudaSuccess)
@@ -825,7 +807,6 @@ int svbzd_encode_blocks_per_sm() {
     return n;
 }
 int svbzd_decode_blocks_per_sm() {
-    if (use_legacy()) return v3::svbzd_decode_blocks_per_sm();
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, svbzd_decode_kernel, DEC_WARPS * 32, 0) != cudaSuccess)
         return 0;
@@ -842,8 +823,6 @@ static unsigned persistent_grid(uint64_t n_reads, int warps, int num_sms, int bl
 cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    if (use_legacy())
-        return v3::launch_svbzd_encode(a, persistent_grid(a.n_reads, v3::enc_warps(), num_sms, blocks_per_sm), st);
     svbzd_encode_kernel<<<persistent_grid(a.n_reads, ENC_WARPS, num_sms, blocks_per_sm), ENC_WARPS * 32,
                           sizeof(EncWarpSmem) * ENC_WARPS, st>>>(a);
     return cudaGetLastError();
@@ -851,8 +830,6 @@ cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_
 cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    if (use_legacy())
-        return v3::launch_svbzd_decode(a, persistent_grid(a.n_reads, v3::dec_warps(), num_sms, blocks_per_sm), st);
     svbzd_decode_kernel<<<persistent_grid(a.n_reads, DEC_WARPS, num_sms, blocks_per_sm), DEC_WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -503,6 +503,32 @@ int zstd_decode_blocks_per_sm() {
     return n;
 }
 
+// content size of every frame, read from its header on the device (the pipelined transcoder sizes its slots from these
+// without a trip to the host)
+__global__ void zstd_sizes_kernel(const uint8_t *in, const uint64_t *off, const uint32_t *len, uint64_t n, uint32_t mul,
+                                  uint32_t add, uint32_t *size, int32_t *status) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    s5bz::FrameInfo fi;
+    int32_t st = S5B_OK;
+    uint32_t sz = 0;
+    if (s5bz::parse_frame_header(in + off[r], len[r], fi) != s5bz::Z_OK || !fi.has_content_size) {
+        st = S5B_ERR_PRESS;
+    } else if (fi.content_size > (uint64_t)len[r] * mul + add) {
+        st = S5B_ERR_NOSPACE;
+    } else {
+        sz = (uint32_t)fi.content_size;
+    }
+    size[r] = sz;
+    status[r] = st;
+}
+cudaError_t launch_zstd_sizes(const uint8_t *in, const uint64_t *off, const uint32_t *len, uint64_t n, uint32_t mul,
+                              uint32_t add, uint32_t *size, int32_t *status, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    zstd_sizes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, off, len, n, mul, add, size, status);
+    return cudaGetLastError();
+}
+
 size_t zstd_decode_scratch_bytes(int num_sms, int blocks_per_sm) {
     return (size_t)num_sms * (blocks_per_sm > 0 ? blocks_per_sm : 1) * ZD_WARPS * (128u << 10);
 }

@@ -51,3 +51,38 @@ def adversarial(kind, n, seed=1):
         d = rng.choice(np.array([-129, -128, -127, 126, 127, 128, 0, 1, -1]), n)
         return np.cumsum(d).astype(np.int16)
     raise ValueError(kind)
+
+
+# ---- packed BLOW5 records around the signal (per-record metadata of the real fixture, no aux fields) --------
+REC_ID_LEN = 36
+REC_HEAD = 2 + REC_ID_LEN + 4 + 32 + 8   # bytes before the signal: u16 id_len, id, u32 read_group, 4 x f64, u64 len_raw_signal
+
+
+def record_bytes(n_samples):
+    """stored size of one uncompressed record (slow5_rec_to_mem binary layout, slow5.c:3928-3990) without its size prefix"""
+    return REC_HEAD + 2 * int(n_samples)
+
+
+def blow5_records(sig, n_reads, n_samples, seed=42):
+    """uint8 tensor [n_reads, record_bytes(n_samples)] on sig's device: uncompressed (none/none) BLOW5 records, one per
+    read of `n_samples` consecutive samples of `sig`: read_id = 36-char UUID-shaped string from the RNG, read_group 0,
+    digitisation 8192, offset 9, range 1444.86, sampling_rate 4000 (the real fixture's values), no aux fields."""
+    dev = sig.device
+    R, N = int(n_reads), int(n_samples)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed) + 7919)
+    rec = torch.empty((R, REC_HEAD + 2 * N), dtype=torch.uint8, device=dev)
+    head = np.zeros(REC_HEAD, np.uint8)
+    head[0:2] = np.frombuffer(np.uint16(REC_ID_LEN).tobytes(), np.uint8)
+    at = 2 + REC_ID_LEN
+    head[at:at + 4] = 0
+    head[at + 4:at + 36] = np.frombuffer(np.array([8192.0, 9.0, 1444.86, 4000.0], "<f8").tobytes(), np.uint8)
+    head[at + 36:at + 44] = np.frombuffer(np.uint64(N).tobytes(), np.uint8)
+    rec[:, :REC_HEAD] = torch.from_numpy(head).to(dev)
+    hexchars = torch.tensor(list(b"0123456789abcdef"), dtype=torch.uint8, device=dev)
+    ids = hexchars[torch.randint(0, 16, (R, REC_ID_LEN), generator=g, device=dev)]
+    for dash in (8, 13, 18, 23):
+        ids[:, dash] = ord("-")
+    rec[:, 2:2 + REC_ID_LEN] = ids
+    rec[:, REC_HEAD:] = sig[:R * N].view(R, N).contiguous().view(torch.uint8).view(R, 2 * N)
+    return rec
