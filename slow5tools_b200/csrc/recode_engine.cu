@@ -153,6 +153,7 @@ Bounds chunk_bounds(const Job &j, uint64_t span, uint64_t n) {
         b.z = P + 6 * (P / 6144 + 2 * n) + 48 * n + 64;
     const uint64_t F = b.z ? b.z : (j.in_rec == j.out_rec && j.in_sig == j.out_sig ? span : P);
     b.img = F + 8 * n + 64;
+    if (j.in_sig != j.out_sig && j.out_rec == S5B_COMPRESS_NONE) b.img = b.packed + 8 * n + 64;
     return b;
 }
 
@@ -309,7 +310,18 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     const uint64_t *fin_off = cur_off;
     const uint32_t *fin_len = cur_len;
     uint64_t fin_cap = cur_cap;
-    if (j.in_sig != j.out_sig) {
+    // when the packed records are the output (no record compression), they are written straight into the file image
+    const bool direct_image = j.in_sig != j.out_sig && j.out_rec == S5B_COMPRESS_NONE;
+    const uint32_t *direct_sig_len = nullptr;
+    if (j.in_sig != j.out_sig && direct_image) {
+        if (sig_src_is_samples) {
+            StageScope ts(ctx, st, ST_PACK);
+            CU(launch_rec_plan(PLAN_SIG_BYTES_RAW, n, ra, nullptr, 0, d_svb_len, st));
+            sig_src_len = d_svb_len;
+            ctx->launches += 1;
+        }
+        direct_sig_len = sig_src_len;
+    } else if (j.in_sig != j.out_sig) {
         StageScope ts(ctx, st, ST_PACK);
         CU(L.packed.reserve(B.packed + 32));
         if (sig_src_is_samples) {  // raw signal goes into the record: 2 * n_samples bytes
@@ -359,8 +371,9 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     }
     // ---- file image: [u64 size][record] ... (slow5.c:4055-4060) and the chunk's verdict
     {
-        StageScope ts(ctx, st, ST_IMAGE);
-        CU(launch_rec_plan(PLAN_IMAGE_LEN, n, ra, fin_len, 0, d_tmp, st));
+        StageScope ts(ctx, st, direct_image ? ST_PACK : ST_IMAGE);
+        if (direct_image) CU(launch_rec_plan(PLAN_PACKED_IMAGE_LEN, n, ra, direct_sig_len, 0, d_tmp, st));
+        else CU(launch_rec_plan(PLAN_IMAGE_LEN, n, ra, fin_len, 0, d_tmp, st));
         CU(scan(d_tmp, 1, d_img_off));
         uint8_t *img;
         const uint64_t *base_ptr = nullptr;
@@ -377,7 +390,12 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
         }
         // statuses: locate (covers the record decompression it was handed), signal decode / encode, record compression
         CU(launch_recode_finish(n, d_img_off, base_ptr, cap, ra.status, st_sdec, st_senc, st_z, L.d_res, st));
-        CU(launch_image_gather(fin, fin_off, fin_len, n, img, d_img_off, st, base_ptr, L.d_res, abs));
+        if (direct_image) {
+            CU(launch_rec_pack(cur, cur_off, ra, n, sig_src, sig_src_off, direct_sig_len, sig_src_is_samples,
+                               j.out_sig != S5B_COMPRESS_NONE, img, d_img_off, st, 1, base_ptr, L.d_res, abs));
+        } else {
+            CU(launch_image_gather(fin, fin_off, fin_len, n, img, d_img_off, st, base_ptr, L.d_res, abs));
+        }
         ctx->launches += 3;
         if (j.dst_dev) {
             CU(launch_recode_advance(ctx->d_img_base, L.d_res, j.d_acc, st));

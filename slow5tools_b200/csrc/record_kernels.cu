@@ -30,6 +30,28 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
         uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
         for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
         for (uint32_t i = head + (body << 4) + lane; i < n; i += 32) dst[i] = src[i];
+    } else if (n >= 64) {
+        // different 16-byte phase: destination-aligned 128-bit stores, every quad assembled from five aligned source
+        // words with funnel shifts (the fifth word may lie up to 7 bytes past the last source byte: every slab this
+        // file copies from is padded by >= 16 bytes)
+        uint32_t head = (uint32_t)((16u - (ds & 15u)) & 15u);
+        if (lane < (int)head) dst[lane] = src[lane];
+        const uint32_t body = (n - head) >> 4;
+        const uint8_t *s0 = src + head;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s0) & 3u) * 8u;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(s0 - (sh >> 3));
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+        for (uint32_t i = lane; i < body; i += 32) {
+            const uint32_t *q = w + 4 * i;
+            const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+            uint4 v;
+            v.x = __funnelshift_r(a0, a1, sh);
+            v.y = __funnelshift_r(a1, a2, sh);
+            v.z = __funnelshift_r(a2, a3, sh);
+            v.w = __funnelshift_r(a3, a4, sh);
+            d4[i] = v;
+        }
+        for (uint32_t i = head + (body << 4) + lane; i < n; i += 32) dst[i] = src[i];
     } else if (((ds ^ ss) & 3u) == 0) {
         uint32_t head = (uint32_t)((4u - (ds & 3u)) & 3u);
         if (head > n) head = n;
@@ -112,6 +134,7 @@ __global__ void rec_plan_kernel(int mode, uint64_t n, RecArrays a, const uint32_
         case PLAN_INFLATE_GUESS: v = aux_in[r] * param + 1024u; break;
         case PLAN_SPLIT: v = a.head_len[r] + 8u + 4u + (ns + 3u) / 4u; break;       // start of the svb-zd data bytes
         case PLAN_SIG_BYTES_RAW: v = 2u * ns; break;
+        case PLAN_PACKED_IMAGE_LEN: v = a.head_len[r] + 8u + aux_in[r] + a.aux_len[r] + 8u; break;  // packed record + size prefix
     }
     out[r] = v;
 }
@@ -130,13 +153,26 @@ __global__ void __launch_bounds__(RK_WARPS * 32) rec_pack_kernel(const uint8_t *
                                                                  uint64_t n, const uint8_t *sig_src,
                                                                  const uint64_t *sig_src_off, const uint32_t *sig_src_len,
                                                                  int sig_src_is_samples, int sig_out_compressed, uint8_t *out,
-                                                                 const uint64_t *out_off) {
+                                                                 const uint64_t *out_off, int image, const uint64_t *base_ptr,
+                                                                 const uint64_t *res, uint64_t *abs_off) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * RK_WARPS + (threadIdx.x >> 5), nw = (uint64_t)gridDim.x * RK_WARPS;
+    // image mode: the packed records ARE the output ([u64 size][record] back to back at out + *base_ptr, slow5.c:4055-4060)
+    if (image && res && (int32_t)res[1] == S5B_ERR_NOSPACE && res[2] == ~0ull) return;
+    const uint64_t base = image && base_ptr ? *base_ptr : 0;
     for (uint64_t r = warp; r < n; r += nw) {
+        if (image && abs_off && lane == 0) {
+            abs_off[r] = base + out_off[r];
+            if (r == n - 1) abs_off[n] = base + out_off[n];
+        }
         if (a.status[r] != S5B_OK) continue;
         const uint8_t *in = rec + rec_off[r];
-        uint8_t *o = out + out_off[r];
+        uint8_t *o = out + base + out_off[r];
+        if (image) {
+            const uint64_t sz = out_off[r + 1] - out_off[r] - 8;
+            if (lane < 8) o[lane] = (uint8_t)(sz >> (8 * lane));
+            o += 8;
+        }
         const uint32_t head = a.head_len[r];
         warp_copy(o, in, head, lane);
         // signal source: the input record itself (pass-through, sig_src == NULL), a byte slab (svb slots, offsets in
@@ -198,10 +234,10 @@ __global__ void recode_finish_kernel(uint64_t n, const uint64_t *img_off, const 
         const uint64_t base = base_ptr ? *base_ptr : 0;
         res[0] = total;
         if (best != ~0ull) {
-            res[1] = (uint64_t)(uint32_t)(-(int32_t)(best & 0xff));
+            res[1] = (uint64_t)(int64_t)(-(int32_t)(best & 0xff));
             res[2] = best >> 8;
         } else if (cap && base + total > cap) {
-            res[1] = (uint64_t)(uint32_t)S5B_ERR_NOSPACE;
+            res[1] = (uint64_t)(int64_t)S5B_ERR_NOSPACE;
             res[2] = ~0ull;
         } else {
             res[1] = 0;
@@ -217,7 +253,7 @@ __global__ void recode_advance_kernel(uint64_t *base_ptr, const uint64_t *res, u
         if (base_ptr) *base_ptr += res[0];
         if (acc) acc[0] += res[0];
     } else if (acc && (int32_t)acc[1] == S5B_OK) {
-        acc[1] = (uint64_t)(uint32_t)e;
+        acc[1] = (uint64_t)(int64_t)e;
     }
 }
 __global__ void rebase_off_kernel(uint64_t *dst, const uint64_t *src, uint64_t n, uint64_t sub) {
@@ -299,10 +335,12 @@ cudaError_t launch_sig_extract(const uint8_t *rec, const uint64_t *rec_off, RecA
 }
 cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint8_t *sig_src,
                             const uint64_t *sig_src_off, const uint32_t *sig_src_len, int sig_src_is_samples,
-                            int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st) {
+                            int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st, int image,
+                            const uint64_t *base_ptr, const uint64_t *res, uint64_t *abs_off) {
     if (!n) return cudaSuccess;
     rec_pack_kernel<<<rk_grid(n), RK_WARPS * 32, 0, st>>>(rec, rec_off, a, n, sig_src, sig_src_off, sig_src_len,
-                                                         sig_src_is_samples, sig_out_compressed, out, out_off);
+                                                         sig_src_is_samples, sig_out_compressed, out, out_off, image, base_ptr,
+                                                         res, abs_off);
     return cudaGetLastError();
 }
 cudaError_t launch_image_gather(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n, uint8_t *img,

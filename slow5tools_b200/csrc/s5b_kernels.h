@@ -106,7 +106,7 @@ cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const
                               int sig_is_svb, RecArrays a, cudaStream_t st, const int32_t *in_status = nullptr);
 // elementwise size planning: mode selects which length is written to out[]
 enum RecPlan { PLAN_SIG_SAMPLES = 0, PLAN_SVB_BOUND = 1, PLAN_PACKED_LEN = 2, PLAN_ZLIB_BOUND = 3, PLAN_IMAGE_LEN = 4,
-               PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7, PLAN_EXZD_BOUND = 8 };
+               PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7, PLAN_EXZD_BOUND = 8, PLAN_PACKED_IMAGE_LEN = 9 };
 cudaError_t launch_rec_plan(int mode, uint64_t n, RecArrays a, const uint32_t *aux_in /*mode dependent*/, uint32_t param,
                             uint32_t *out, cudaStream_t st);
 // read ids out of (prefixes of) decompressed records: len[r] = id bytes or 0xFFFFFFFF (prefix too short), src[r] = id start
@@ -119,7 +119,10 @@ cudaError_t launch_sig_extract(const uint8_t *rec, const uint64_t *rec_off, RecA
 // packed record r = head (from the input record) + u64 len field + signal bytes + aux (from the input record)
 cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint8_t *sig_src,
                             const uint64_t *sig_src_off, const uint32_t *sig_src_len, int sig_src_is_samples,
-                            int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st);
+                            int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st, int image = 0,
+                            const uint64_t *base_ptr = nullptr, const uint64_t *res = nullptr, uint64_t *abs_off = nullptr);
+// image != 0: out_off[] is the scan of PLAN_PACKED_IMAGE_LEN (align 1) and every record is written behind its u64 size
+// prefix at out + *base_ptr: the packed records are the file image (no separate gather)
 // file image: [u64 size][bytes] per record, back to back
 // base_ptr (optional, device): added to every image offset; res (optional): the finish kernel's verdict -- an image that
 // does not fit is not written; abs_off (optional, n+1 entries): absolute image offset of every record's size prefix
