@@ -1,4 +1,4 @@
-// deflate_kernels.cu -- sm_100a zlib/DEFLATE encoder, one warp per record.
+// deflate_kernels.cu -- sm_100a zlib/DEFLATE encoder for batches of records, three kernels.
 //
 // Replaces, for whole batches, ptr_compress_zlib / ptr_compress_zlib_solo (slow5lib/src/slow5_press.c:
 // 837-913: deflateInit2(level 6, wbits 15, memLevel 8, default strategy) + deflate(Z_FINISH)), producing
@@ -9,16 +9,26 @@
 //
 // Encoder shape, chosen from what the data looks like (on svb-zd records Huffman coding is
 // where the gain is; LZ77 matching buys < 2 % and only in the zero-filled key bytes):
-//   * the record is cut into blocks (a caller-supplied split point -- the boundary between the
-//     header+key bytes and the data bytes of the svb stream -- then every DEF_BLOCK bytes); each block
-//     gets its own dynamic Huffman code;
-//   * tokens are literals plus distance-1 run matches found with warp ballots inside 32-byte strips
-//     (one byte per lane): no hash chains, no serial match search;
-//   * per block: byte histogram by shared-memory atomics -> warp bitonic sort -> two-queue Huffman
-//     construction -> 15-bit length limiting -> canonical codes -> run-length coded header (RFC 1951
-//     3.2.7) with its own 7-bit-limited code -> token bits placed by a warp prefix scan over the code
-//     lengths and OR-ed into a shared-memory bit buffer that leaves as 128-bit coalesced stores;
-//   * a block that would not shrink is emitted as stored blocks, like zlib does.
+//   * a record is cut into blocks: at a caller-supplied split point (the boundary between the header + key
+//     bytes and the data bytes of the svb stream), then every DEF_BLOCK bytes; every block gets its own
+//     dynamic Huffman code;
+//   * a block is coded in one of two modes.  LITERAL: no matches, four bytes per lane and iteration straight
+//     from global memory.  RUN: literals plus distance-1 run matches found with warp ballots inside 32-byte
+//     strips -- used for the part before the split point and for any block in which at least half the bytes
+//     repeat their predecessor;
+//   * the work is split by the shape of its parallelism:
+//       deflate_count_kernel  one warp per record: Adler-32, byte / length-symbol histogram of every block,
+//                             compaction of the used symbols, bitonic sort in registers -> sorted
+//                             (frequency, symbol) list per block in the workspace;
+//       deflate_tree_kernel   one THREAD per block: the inherently serial part of Huffman construction
+//                             (Moffat-Katajainen in-place two-queue merge, depths, 15-bit length limiting) on a
+//                             shared-memory row per thread, 32 independent trees per warp instead of one lane
+//                             working while 31 wait;
+//       deflate_emit_kernel   one warp per record: canonical codes, run-length coded header with its 7-bit
+//                             code-length code, token bits placed by a warp prefix scan and OR-ed into a
+//                             shared-memory bit buffer that leaves as 128-bit stores; stored blocks when a
+//                             block would not shrink; Adler-32 trailer.
+//     (the round-1 single kernel spent 35 % of its issue slots in lane 0's merge loop and the shared-memory sort)
 #include "s5b_kernels.h"
 #include "s5b_ptx.cuh"
 #include "huff_common.cuh"
@@ -26,42 +36,45 @@
 
 namespace s5b {
 
-namespace {
+namespace defl {
 
-constexpr int DEF_WARPS = 4;
-constexpr int DEF_BLOCK = 6144;  // max input bytes per deflate block (multiple of 32)
+constexpr int DEF_BLOCK = 6144;  // max input bytes per deflate block (multiple of 128)
+constexpr int DEF_ROW = 288;     // workspace row: entries per block
 constexpr int DEF_OUT = HC_OUT;
 constexpr int DEF_OUT_SLACK = HC_OUT_SLACK;
 constexpr uint32_t ADLER_MOD = 65521u;
+constexpr int CNT_WARPS = 4, EMIT_WARPS = 4, TREE_THREADS = 64;
+constexpr int TREE_STRIDE = 290;  // u16 entries per row: 145 words, odd -> lanes on the same index hit different banks
+enum : uint32_t { MODE_LIT = 0, MODE_RUN = 1 };
 
-struct DefTreeScratch {  // live only while a block's codes are being constructed
-    uint32_t sortbuf[512];
-    uint32_t weight[576];
-    uint16_t parent[576];
-};
-struct __align__(128) DefWarpSmem {
-    // The staged block and the code-construction scratch share their bytes: the block is staged, counted,
-    // overwritten by the scratch, and staged again (from L2 this time) for the emit pass.  Halves the shared
-    // memory per warp, i.e. doubles the resident warps of this latency-bound kernel.
-    union {
-        uint8_t in[16 + DEF_BLOCK + 16];  // block staged from the 16-byte granule below its first byte
-        DefTreeScratch k;
-    };
-    uint32_t out[(DEF_OUT + DEF_OUT_SLACK) / 4];
-    uint32_t hist[288];
-    uint16_t code[288];  // bit-reversed canonical codes (LSB-first ready)
-    uint8_t len[288];
-    uint8_t dlen[32];
-    uint8_t clsym[320];  // run-length coded code lengths: symbol 0..18
-    uint8_t clext[320];  // and its extra-bits value
-    uint32_t clhist[32];
-    uint16_t clcode[20];
-    uint8_t cllen[20];
-    alignas(4) uint16_t bl_count[16];
-    unsigned long long bar;
+struct DefWork {       // views into the caller's workspace
+    uint32_t *nblk;    // [n]      blocks per record (scanned into blk_off)
+    uint64_t *blk_off; // [n + 1]
+    uint32_t *adler;   // [n]
+    uint4 *binfo;      // [blocks] x: used | mode << 16 | has_match << 24, y: token bits (tree kernel)
+    uint32_t *keys;    // [blocks][DEF_ROW] ascending (frequency << 9 | symbol), `used` entries
+    uint8_t *lens;     // [blocks][DEF_ROW] code length of sorted entry i
+    void *scan_scratch;
+    uint64_t max_blocks;
 };
 
 __constant__ uint8_t c_def_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+__host__ __device__ inline uint32_t def_nblocks(uint32_t len, uint32_t split) {
+    const uint32_t na = split ? (split + DEF_BLOCK - 1) / DEF_BLOCK : 0;
+    const uint32_t nb = (len - split + DEF_BLOCK - 1) / DEF_BLOCK;
+    return na + nb ? na + nb : 1;  // an empty record still gets one (final, empty) block
+}
+__device__ __forceinline__ void def_block_range(uint32_t len, uint32_t split, uint32_t k, uint32_t &b0, uint32_t &b1) {
+    const uint32_t na = split ? (split + DEF_BLOCK - 1) / DEF_BLOCK : 0;
+    if (k < na) {
+        b0 = k * DEF_BLOCK;
+        b1 = min(b0 + DEF_BLOCK, split);
+    } else {
+        b0 = split + (k - na) * DEF_BLOCK;
+        b1 = min(b0 + DEF_BLOCK, len);
+    }
+}
 
 // match length 3..32 -> (code - 257, extra bits, extra value) per RFC 1951 3.2.5
 __device__ __forceinline__ void len_code(uint32_t m, uint32_t &sym, uint32_t &xbits, uint32_t &xval) {
@@ -80,48 +93,25 @@ __device__ __forceinline__ void len_code(uint32_t m, uint32_t &sym, uint32_t &xb
     }
 }
 
-// Adler-32 over n staged bytes (whole warp)
-__device__ __forceinline__ void adler_update(uint32_t &a, uint32_t &b, const uint8_t *p, uint32_t n, int lane) {
-    const uint32_t per = (n + 31) / 32;
-    const uint32_t start = min(n, per * lane), end = min(n, start + per);
-    uint32_t s1 = 0, s2 = 0;
-    for (uint32_t i = start; i < end; ++i) {
-        const uint32_t d = p[i];
-        s1 += d;
-        s2 += (end - i) * d;
-    }
-    uint32_t contrib = (uint32_t)(((uint64_t)(n - end) * s1 + s2) % ADLER_MOD);
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        s1 += __shfl_xor_sync(FULL, s1, d);
-        contrib += __shfl_xor_sync(FULL, contrib, d);
-    }
-    b = (uint32_t)((b + (uint64_t)n * a + contrib) % ADLER_MOD);
-    a = (a + s1) % ADLER_MOD;
-}
-
-// Token of lane `lane` in the 32-byte strip starting at block offset `t0`: a literal, the start of a
-// distance-1 run match of length m (3..32, entirely inside the strip), or nothing (covered by a match).
+// Token of this lane in a 32-byte strip (one byte per lane): a literal, the start of a distance-1 run match of length
+// m (3..32, entirely inside the strip), or nothing (covered by a match).  b = the lane's byte (0x100 past the end),
+// prev0 = the byte before the strip (0x200 when there is none).
 struct Token {
     uint32_t kind;  // 0 none, 1 literal, 2 match
-    uint32_t byte;
     uint32_t mlen;
 };
-__device__ __forceinline__ Token strip_token(const uint8_t *blk, uint32_t t0, uint32_t blen, bool have_prev, int lane) {
+__device__ __forceinline__ Token strip_token(uint32_t b, uint32_t prev0, int lane) {
     Token tk;
-    const uint32_t i = t0 + lane;
-    const bool valid = i < blen;
-    const uint32_t b = valid ? blk[i] : 0x100u;
     uint32_t prev = __shfl_up_sync(FULL, b, 1);
-    if (lane == 0) prev = (t0 > 0 || have_prev) ? blk[(int)t0 - 1] : 0x200u;  // blk[-1] is the byte before the block
+    if (lane == 0) prev = prev0;
+    const bool valid = b < 0x100u;
     const bool eq = valid && b == prev;
     const uint32_t mask = __ballot_sync(FULL, eq);
-    tk.byte = b;
     tk.kind = valid ? 1u : 0u;
     tk.mlen = 0;
     if (eq) {
         const uint32_t below = ~mask & ((1u << lane) - 1u);
-        const uint32_t s = below ? 32u - __clz(below) : 0u;        // first lane of this run of equal bytes
+        const uint32_t s = below ? 32u - __clz(below) : 0u;            // first lane of this run of equal bytes
         const uint32_t above = ~mask & ~((2u << lane) - 1u);
         const uint32_t e = above ? (uint32_t)__ffs(above) - 2u : 31u;  // last lane of the run
         const uint32_t m = e - s + 1;
@@ -133,42 +123,411 @@ __device__ __forceinline__ Token strip_token(const uint8_t *blk, uint32_t t0, ui
     return tk;
 }
 
-}  // namespace
-
-__global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateArgs a) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    DefWarpSmem &ws = reinterpret_cast<DefWarpSmem *>(smem_raw)[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const uint32_t bar = smem_u32(&ws.bar);
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
+// ---- reading a block four bytes per lane from global memory, any alignment --------------------------------------
+// Strip t of the block = bytes [128 t, 128 t + 128); lane l owns bytes 4 l .. 4 l + 3 of it.  Words are loaded aligned
+// and shifted into place with the neighbour lane's word; lane 31's neighbour is lane 0 of the NEXT strip, which is
+// loaded one iteration ahead anyway.
+struct WordReader {
+    const uint32_t *w;   // aligned word at or below the block's first byte
+    const uint32_t *end; // no loads at or beyond (the slab's capacity)
+    uint32_t sh;         // (first byte address & 3) * 8
+    uint32_t cur, nxt;
+    __device__ __forceinline__ uint32_t ld(uint32_t i) const {
+        const uint32_t *p = w + i;
+        return p < end ? __ldg(p) : 0u;
     }
-    __syncwarp();
-    uint32_t phase = 0;
+    __device__ __forceinline__ void start(const uint8_t *first, const uint8_t *slab_end, int lane) {
+        const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 3u);
+        w = reinterpret_cast<const uint32_t *>(first - sk);
+        end = reinterpret_cast<const uint32_t *>(slab_end);
+        sh = sk * 8u;
+        cur = ld(lane);
+        nxt = ld(32 + lane);
+    }
+    // the lane's four bytes of strip t (call with t = 0, 1, 2, ... in order)
+    __device__ __forceinline__ uint32_t next(uint32_t t, int lane) {
+        uint32_t up = __shfl_down_sync(FULL, cur, 1);
+        const uint32_t n0 = __shfl_sync(FULL, nxt, 0);
+        if (lane == 31) up = n0;
+        const uint32_t v = __funnelshift_r(cur, up, sh);
+        cur = nxt;
+        nxt = ld(32 * (t + 2) + lane);
+        return v;
+    }
+};
 
+// ---- bitonic sort of 32 * R keys held R per lane (element i = register i / 32 of lane i % 32), ascending ----------
+template <int R>
+__device__ __forceinline__ void reg_sort(uint32_t (&v)[R], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & jr) == 0) {
+                        const bool up = (((r << 5) | lane) & k) == 0;
+                        const uint32_t a = v[r], b = v[r | jr];
+                        const bool sw = (a > b) == up;
+                        v[r] = sw ? b : a;
+                        v[r | jr] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t o = __shfl_xor_sync(FULL, v[r], j);
+                    const bool up = (((r << 5) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+                }
+            }
+        }
+    }
+}
+
+struct __align__(16) CntWarpSmem {
+    uint32_t hist[4][DEF_ROW];  // four copies (lane & 3) so that common bytes do not serialise the atomics
+    uint32_t keys[512];
+};
+
+// ---- plan: blocks per record, argument checks -------------------------------------------------------------------
+__global__ void deflate_plan_kernel(const DeflateArgs a, DefWork w) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    const uint64_t ioff = a.in_off[r];
+    const uint32_t ilen = a.in_len[r];
+    const uint64_t ocap = a.out_off[r + 1] - a.out_off[r];
+    uint32_t split = a.split ? a.split[r] : 0;
+    if (split >= ilen) split = 0;
+    // worst case: stored blocks (5 bytes each) + zlib header + Adler-32 + one byte of bit padding per block
+    const uint64_t nblocks_max = (uint64_t)ilen / DEF_BLOCK + 2;
+    int32_t st = S5B_OK;
+    if (ioff + ilen > a.in_capacity) st = S5B_ERR_ARG;
+    else if (ocap < (uint64_t)ilen + 6 * nblocks_max + 8) st = S5B_ERR_NOSPACE;
+    a.status[r] = st;
+    if (st != S5B_OK) a.out_len[r] = 0;
+    w.nblk[r] = st == S5B_OK ? def_nblocks(ilen, split) : 0u;
+}
+
+// ---- kernel 1: histograms -> sorted symbol lists ------------------------------------------------------------------
+__global__ void __launch_bounds__(CNT_WARPS * 32) deflate_count_kernel(const DeflateArgs a, DefWork wk) {
+    __shared__ CntWarpSmem smem[CNT_WARPS];
+    CntWarpSmem &ws = smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint8_t *slab_end = a.in + a.in_capacity;
     for (;;) {
         unsigned long long r = 0;
         if (lane == 0) r = atomicAdd(a.work_counter, 1ULL);
         r = __shfl_sync(FULL, r, 0);
         if (r >= a.n_reads) break;
-        const uint64_t ioff = a.in_off[r];
+        if (a.status[r] != S5B_OK) continue;
+        const uint8_t *src = a.in + a.in_off[r];
         const uint32_t ilen = a.in_len[r];
-        const uint64_t ooff = a.out_off[r];
-        const uint64_t ocap = a.out_off[r + 1] - ooff;
-        // worst case: stored blocks (5 bytes each) + zlib header + Adler-32 + one byte of bit padding per block
-        const uint64_t nblocks_max = (uint64_t)ilen / DEF_BLOCK + 2;
-        if (ioff + ilen > a.in_capacity || ocap < (uint64_t)ilen + 6 * nblocks_max + 8) {
-            if (lane == 0) {
-                a.status[r] = ioff + ilen > a.in_capacity ? S5B_ERR_ARG : S5B_ERR_NOSPACE;
-                a.out_len[r] = 0;
-            }
-            continue;
-        }
-        const uint8_t *src = a.in + ioff;
-        uint8_t *dst = a.out + ooff;
         uint32_t split = a.split ? a.split[r] : 0;
         if (split >= ilen) split = 0;
+        const uint32_t nb = def_nblocks(ilen, split);
+        const uint64_t blk0 = wk.blk_off[r];
+        uint32_t ad_a = 1, ad_b = 0;
+        for (uint32_t k = 0; k < nb; ++k) {
+            uint32_t b0, b1;
+            def_block_range(ilen, split, k, b0, b1);
+            const uint32_t blen = b1 - b0;
+            uint32_t mode = (split && b1 <= split) ? MODE_RUN : MODE_LIT;
+            uint32_t nmatch = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int i = lane; i < 4 * DEF_ROW; i += 32) (&ws.hist[0][0])[i] = 0;
+                __syncwarp();
+                uint32_t s1 = 0, s2 = 0, eqc = 0;
+                nmatch = 0;
+                if (mode == MODE_LIT) {
+                    WordReader rd;
+                    rd.start(src + b0, slab_end, lane);
+                    uint32_t *h = ws.hist[lane & 3];
+                    uint32_t carry = 0;  // last byte of the previous strip (for the repeat count only)
+                    const uint32_t nstrip = (blen + 127) >> 7;
+                    for (uint32_t t = 0; t < nstrip; ++t) {
+                        uint32_t v = rd.next(t, lane);
+                        const uint32_t pos = (t << 7) + 4u * lane;
+                        const uint32_t nv = pos >= blen ? 0u : min(4u, blen - pos);
+                        if (nv < 4) v &= nv ? (1u << (8 * nv)) - 1u : 0u;
+                        // Adler-32 partial sums: s1 += sum d, s2 += sum (blen - position) d
+                        const uint32_t sum = __dp4a(v, 0x01010101u, 0u), wsum = __dp4a(v, 0x03020100u, 0u);
+                        s1 += sum;
+                        s2 += (blen - pos) * sum - wsum;
+                        if (nv == 4) {
+                            atomicAdd(&h[v & 255u], 1u);
+                            atomicAdd(&h[(v >> 8) & 255u], 1u);
+                            atomicAdd(&h[(v >> 16) & 255u], 1u);
+                            atomicAdd(&h[v >> 24], 1u);
+                        } else {
+                            for (uint32_t q = 0; q < nv; ++q) atomicAdd(&h[(v >> (8 * q)) & 255u], 1u);
+                        }
+                        // bytes equal to their predecessor (mode choice)
+                        uint32_t pv = __shfl_up_sync(FULL, v, 1);
+                        if (lane == 0) pv = carry;
+                        carry = __shfl_sync(FULL, v, 31);
+                        const uint32_t x = v ^ __funnelshift_l(pv, v, 8);
+                        eqc += nv == 4 ? (uint32_t)__popc(__vcmpeq4(x, 0u)) >> 3 : 0u;
+                    }
+                } else {
+                    uint32_t prev0 = b0 ? (uint32_t)src[b0 - 1] : 0x200u;  // the byte before the block is matchable
+                    for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
+                        const uint32_t i = t0 + lane;
+                        const uint32_t b = i < blen ? (uint32_t)src[b0 + i] : 0x100u;
+                        if (i < blen) {
+                            s1 += b;
+                            s2 += (blen - i) * b;
+                        }
+                        const Token tk = strip_token(b, prev0, lane);
+                        prev0 = __shfl_sync(FULL, b, 31);
+                        if (tk.kind == 1) {
+                            atomicAdd(&ws.hist[0][b], 1u);
+                        } else if (tk.kind == 2) {
+                            uint32_t sym, xb, xv;
+                            len_code(tk.mlen, sym, xb, xv);
+                            atomicAdd(&ws.hist[0][257 + sym], 1u);
+                            ++nmatch;
+                        }
+                    }
+                }
+                s2 %= ADLER_MOD;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    s1 += __shfl_xor_sync(FULL, s1, d);
+                    s2 += __shfl_xor_sync(FULL, s2, d);
+                    eqc += __shfl_xor_sync(FULL, eqc, d);
+                    nmatch += __shfl_xor_sync(FULL, nmatch, d);
+                }
+                if (pass == 0) {
+                    ad_b = (uint32_t)((ad_b + (uint64_t)blen * ad_a + s2) % ADLER_MOD);
+                    ad_a = (ad_a + s1) % ADLER_MOD;
+                }
+                __syncwarp();
+                // a block that mostly repeats its previous byte is better off with run matches: count it again
+                if (pass == 0 && mode == MODE_LIT && blen >= 64 && eqc * 2 > blen) {
+                    mode = MODE_RUN;
+                    continue;
+                }
+                break;
+            }
+            // ---- compact the used symbols (end of block included), sort by (frequency, symbol)
+            int used = 0;
+            for (int s0 = 0; s0 < DEF_ROW; s0 += 32) {
+                const int s = s0 + lane;
+                uint32_t f = ws.hist[0][s] + ws.hist[1][s] + ws.hist[2][s] + ws.hist[3][s];
+                if (s == 256) f = 1;
+                if (s >= 286) f = 0;
+                const uint32_t m = __ballot_sync(FULL, f != 0);
+                if (f) ws.keys[used + __popc(m & ((1u << lane) - 1u))] = (min(f, 0x7fffffu) << 9) | (uint32_t)s;
+                used += __popc(m);
+            }
+            __syncwarp();
+            if (used < 2) {
+                // zlib forces two codes so that the code is complete: a second symbol of frequency 1 (used == 1 means
+                // only the end-of-block symbol is there: an empty block)
+                if (lane == 0) ws.keys[1] = (1u << 9) | (ws.keys[0] == ((1u << 9) | 256u) ? 0u : 255u);
+                used = 2;
+                __syncwarp();
+            }
+            uint32_t *row = wk.keys + (blk0 + k) * DEF_ROW;
+            if (used <= 32) {
+                uint32_t v[1] = {lane < used ? ws.keys[lane] : 0xffffffffu};
+                reg_sort<1>(v, lane);
+                if (lane < used) row[lane] = v[0];
+            } else if (used <= 64) {
+                uint32_t v[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) v[q] = q * 32 + lane < used ? ws.keys[q * 32 + lane] : 0xffffffffu;
+                reg_sort<2>(v, lane);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (q * 32 + lane < used) row[q * 32 + lane] = v[q];
+            } else if (used <= 128) {
+                uint32_t v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = q * 32 + lane < used ? ws.keys[q * 32 + lane] : 0xffffffffu;
+                reg_sort<4>(v, lane);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q * 32 + lane < used) row[q * 32 + lane] = v[q];
+            } else {
+                const int npad = used <= 256 ? 256 : 512;
+                for (int i = used + lane; i < npad; i += 32) ws.keys[i] = 0xffffffffu;
+                __syncwarp();
+                warp_sort(ws.keys, npad, lane);
+                for (int i = lane; i < used; i += 32) row[i] = ws.keys[i];
+            }
+            if (lane == 0) wk.binfo[blk0 + k] = make_uint4((uint32_t)used | (mode << 16) | (nmatch ? 1u << 24 : 0u), 0u, 0u, 0u);
+            __syncwarp();
+        }
+        if (lane == 0) wk.adler[r] = (ad_b << 16) | ad_a;
+    }
+}
+
+// ---- kernel 2: one thread per block: code lengths from the sorted frequencies ----------------------------------------
+// Moffat & Katajainen's in-place construction on a row of 16-bit words: (1) two-queue merge leaving parent indices,
+// (2) parent indices -> internal node depths, (3) internal depths -> leaf depths (= code lengths, non-increasing along
+// the ascending frequencies).  Then zlib-style repair when a length exceeds `limit`.
+__device__ __forceinline__ void mk_lengths(uint16_t *A, int n, int limit) {
+    if (n == 2) {
+        A[0] = A[1] = 1;
+        return;
+    }
+    A[0] = (uint16_t)(A[0] + A[1]);
+    int root = 0, leaf = 2;
+    for (int next = 1; next < n - 1; ++next) {
+        uint32_t wsum;
+        if (leaf >= n || A[root] < A[leaf]) {
+            wsum = A[root];
+            A[root++] = (uint16_t)next;
+        } else {
+            wsum = A[leaf++];
+        }
+        if (leaf >= n || (root < next && A[root] < A[leaf])) {
+            wsum += A[root];
+            A[root++] = (uint16_t)next;
+        } else {
+            wsum += A[leaf++];
+        }
+        A[next] = (uint16_t)wsum;
+    }
+    A[n - 2] = 0;
+    for (int next = n - 3; next >= 0; --next) A[next] = (uint16_t)(A[A[next]] + 1);
+    int avbl = 1, used = 0, dpth = 0;
+    root = n - 2;
+    int next = n - 1;
+    while (avbl > 0) {
+        while (root >= 0 && A[root] == dpth) {
+            ++used;
+            --root;
+        }
+        while (avbl > used) {
+            A[next--] = (uint16_t)dpth;
+            --avbl;
+        }
+        avbl = 2 * used;
+        ++dpth;
+        used = 0;
+    }
+    if (A[0] <= limit) return;
+    // length limiting (rare): clamp, then repair the over-subscribed code one unit of 2^-limit at a time the way zlib's
+    // gen_bitlen does, and hand the lengths out again, longest codes to the rarest symbols
+    uint16_t cnt[16];
+    for (int b = 0; b < 16; ++b) cnt[b] = 0;
+    uint32_t kraft = 0;
+    for (int i = 0; i < n; ++i) {
+        const int l = min((int)A[i], limit);
+        ++cnt[l];
+        kraft += 1u << (limit - l);
+    }
+    int excess = (int)kraft - (1 << limit);
+    while (excess > 0) {
+        int bits = limit - 1;
+        while (cnt[bits] == 0) --bits;
+        --cnt[bits];
+        cnt[bits + 1] += 2;
+        --cnt[limit];
+        --excess;
+    }
+    int i = 0;
+    for (int bits = limit; bits >= 1; --bits)
+        for (int c = cnt[bits]; c > 0; --c) A[i++] = (uint16_t)bits;
+}
+
+__global__ void __launch_bounds__(TREE_THREADS) deflate_tree_kernel(DefWork wk, const uint64_t *n_blocks_ptr) {
+    __shared__ uint16_t rows[TREE_THREADS * TREE_STRIDE];
+    const uint64_t nblocks = *n_blocks_ptr;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t warp_first = ((uint64_t)blockIdx.x * TREE_THREADS) + (uint64_t)wib * 32;
+    if (warp_first >= nblocks) return;
+    const uint64_t t = warp_first + lane;
+    const bool live = t < nblocks;
+    const uint32_t info = live ? wk.binfo[t].x : 0u;
+    const int used = (int)(info & 0xffffu);
+    uint16_t *wrows = rows + (size_t)wib * 32 * TREE_STRIDE;
+    // stage the frequencies of the warp's 32 rows (coalesced)
+    for (int rr = 0; rr < 32; ++rr) {
+        const int u = __shfl_sync(FULL, used, rr);
+        const uint32_t *src = wk.keys + (warp_first + rr) * DEF_ROW;
+        for (int i = lane; i < u; i += 32) wrows[rr * TREE_STRIDE + i] = (uint16_t)min(src[i] >> 9, 0xffffu);
+    }
+    __syncwarp();
+    if (live && used >= 2) mk_lengths(wrows + lane * TREE_STRIDE, used, 15);
+    __syncwarp();
+    // lengths out (coalesced) and the block's token bits: sum f * (len + extra bits [+ the 1-bit distance code])
+    uint32_t my_bits = 0;
+    for (int rr = 0; rr < 32; ++rr) {
+        const int u = __shfl_sync(FULL, used, rr);
+        const uint32_t dist_len = (__shfl_sync(FULL, info, rr) >> 24) & 1u;
+        const uint32_t *src = wk.keys + (warp_first + rr) * DEF_ROW;
+        uint8_t *dst = wk.lens + (warp_first + rr) * DEF_ROW;
+        uint32_t bits = 0;
+        for (int i = lane; i < u; i += 32) {
+            const uint32_t key = src[i], l = wrows[rr * TREE_STRIDE + i];
+            const uint32_t s = key & 511u, f = key >> 9;
+            dst[i] = (uint8_t)l;
+            uint32_t xb = 0;
+            if (s >= 265 && s < 285) xb = (s - 261) >> 2;
+            bits += f * (l + xb + (s > 256 ? dist_len : 0u));
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
+        if (lane == rr) my_bits = bits;
+    }
+    if (live) wk.binfo[t].y = my_bits;
+}
+
+// ---- kernel 3: emit ------------------------------------------------------------------------------------------------
+struct DefTreeScratch {  // code-length code construction (19 symbols)
+    uint32_t sortbuf[32];
+    uint32_t weight[40];
+    uint16_t parent[40];
+    uint16_t run_start[DEF_ROW + 2];
+};
+struct __align__(128) EmitWarpSmem {
+    uint32_t out[(DEF_OUT + DEF_OUT_SLACK) / 4];
+    uint32_t tab[DEF_ROW];  // code (bit-reversed, LSB-first ready) | length << 16
+    uint16_t code[DEF_ROW];
+    uint8_t len[DEF_ROW];
+    uint8_t clsym[320];  // run-length coded code lengths: symbol 0..18
+    uint8_t clext[320];  // and its extra-bits value
+    uint32_t clhist[32];
+    uint16_t clcode[20];
+    uint8_t cllen[20];
+    alignas(4) uint16_t bl_count[16];
+    DefTreeScratch k;
+};
+
+__device__ __forceinline__ void put64(const BitOut &bo, uint32_t pos, uint64_t bits, uint32_t nbits) {
+    if (nbits == 0) return;
+    const uint32_t w = pos >> 5, sh = pos & 31u;
+    const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
+    atomicOr(&bo.buf[w], lo << sh);
+    if (sh + nbits > 32) atomicOr(&bo.buf[w + 1], __funnelshift_l(lo, hi, sh));
+    if (sh + nbits > 64) atomicOr(&bo.buf[w + 2], __funnelshift_l(hi, 0u, sh));
+}
+
+__global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const DeflateArgs a, DefWork wk) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    EmitWarpSmem &ws = reinterpret_cast<EmitWarpSmem *>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint8_t *slab_end = a.in + a.in_capacity;
+    for (;;) {
+        unsigned long long r = 0;
+        if (lane == 0) r = atomicAdd(a.work_counter, 1ULL);
+        r = __shfl_sync(FULL, r, 0);
+        if (r >= a.n_reads) break;
+        if (a.status[r] != S5B_OK) continue;
+        const uint8_t *src = a.in + a.in_off[r];
+        const uint32_t ilen = a.in_len[r];
+        uint8_t *dst = a.out + a.out_off[r];
+        uint32_t split = a.split ? a.split[r] : 0;
+        if (split >= ilen) split = 0;
+        const uint32_t nb = def_nblocks(ilen, split);
+        const uint64_t blk0 = wk.blk_off[r];
 
         BitOut bo;
         bo.buf = ws.out;
@@ -180,94 +539,57 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
         __syncwarp();
         if (lane == 0) bo.put(bo.bitpos, 0x9c78u, 16);  // CMF/FLG: deflate, 32 KiB window, default level (78 9C)
         bo.bitpos += 16;
-        uint32_t ad_a = 1, ad_b = 0;
 
-        uint32_t b0 = 0;
-        do {  // at least one block, so an empty record still gets a (final) block
-            uint32_t b1 = ilen;
-            if (split > b0) b1 = split;
-            if (b1 - b0 > DEF_BLOCK) b1 = b0 + DEF_BLOCK;
+        for (uint32_t k = 0; k < nb; ++k) {
+            uint32_t b0, b1;
+            def_block_range(ilen, split, k, b0, b1);
             const uint32_t blen = b1 - b0;
-            const bool last = b1 == ilen;
-            // ---- stage [b0 - 1, b1) : the byte before the block is wanted for distance-1 matches
-            const uint8_t *g0 = src + b0 - (b0 ? 1 : 0);
-            const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u);
-            const uint8_t *g16 = g0 - skew;
-            uint64_t bytes = ((uint64_t)skew + blen + (b0 ? 1 : 0) + 15) & ~15ull;
-            const uint64_t room = a.in_capacity - (uint64_t)(g16 - a.in);
-            if (bytes > room) bytes = room & ~15ull;
-            auto stage_block = [&]() {
-                if (!bytes) return;
-                fence_proxy_async_smem();  // every lane's earlier generic accesses to these bytes come first
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(bar, (uint32_t)bytes);
-                    bulk_g2s(smem_u32(ws.in), g16, (uint32_t)bytes, bar);
-                }
-                mbar_wait(bar, phase);
-                phase ^= 1u;
-            };
-            stage_block();
-            const uint8_t *blk = ws.in + skew + (b0 ? 1 : 0);  // blk[0] = first byte of the block, blk[-1] valid if b0 > 0
-            const bool have_prev = b0 > 0;
-            adler_update(ad_a, ad_b, blk, blen, lane);
-
-            // ---- pass 1: histogram of literal/length symbols; count matches
-            for (int s = lane; s < 288; s += 32) ws.hist[s] = 0;
+            const bool last = k + 1 == nb;
+            const uint4 info = wk.binfo[blk0 + k];
+            const int used = (int)(info.x & 0xffffu);
+            const uint32_t mode = (info.x >> 16) & 0xffu;
+            const uint32_t dist_len = (info.x >> 24) & 1u;
+            const uint32_t tok_bits = info.y;
+            // ---- the block's code lengths, in symbol order
+            for (int s = lane; s < DEF_ROW; s += 32) ws.len[s] = 0;
             __syncwarp();
-            uint32_t nmatch = 0;
-            for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
-                const Token tk = strip_token(blk, t0, blen, have_prev, lane);
-                if (tk.kind == 1) {
-                    atomicAdd(&ws.hist[tk.byte], 1u);
-                } else if (tk.kind == 2) {
-                    uint32_t sym, xb, xv;
-                    len_code(tk.mlen, sym, xb, xv);
-                    atomicAdd(&ws.hist[257 + sym], 1u);
-                    ++nmatch;
-                }
+            {
+                const uint32_t *keys = wk.keys + (blk0 + k) * DEF_ROW;
+                const uint8_t *lens = wk.lens + (blk0 + k) * DEF_ROW;
+                for (int i = lane; i < used; i += 32) ws.len[keys[i] & 511u] = lens[i];
             }
-#pragma unroll
-            for (int d = 16; d; d >>= 1) nmatch += __shfl_xor_sync(FULL, nmatch, d);
-            if (lane == 0) ws.hist[256] = 1;  // end of block
             __syncwarp();
-
-            // ---- code construction
-            huffman_lengths(ws.hist, 286, 15, ws.len, ws.k.sortbuf, ws.k.weight, ws.k.parent, ws.bl_count, lane);
             canonical_codes(ws.len, 286, ws.code, ws.bl_count, lane);
-            // distance alphabet: only distance 1 (code 0) is ever used.  One code of one bit when there are
-            // matches, one code of zero bits when the block is all literals (RFC 1951 3.2.7).
-            const uint32_t dist_len = nmatch ? 1u : 0u;
+            for (int s = lane; s < DEF_ROW; s += 32) ws.tab[s] = (uint32_t)ws.code[s] | ((uint32_t)ws.len[s] << 16);
             int hlit = 286;
             while (hlit > 257 && ws.len[hlit - 1] == 0) --hlit;
             const int hdist = 1;
-            // ---- header: run-length code the hlit + hdist code lengths (lane 0), then its 19-symbol code
+            // ---- header: run-length code the hlit + hdist code lengths (RFC 1951 3.2.7), whole warp: find the runs of
+            // equal lengths, turn every run into its symbols (16: repeat previous 3-6, 17: zeros 3-10, 18: zeros
+            // 11-138, greedy like zlib's send_tree), place them with a prefix scan over the runs
             int ncl = 0;
             if (lane < 19) ws.clhist[lane] = 0;
             __syncwarp();
             {
-                // run-length coding of the hlit + hdist code lengths (RFC 1951 3.2.7), whole warp: find the runs of
-                // equal lengths, turn every run into its symbols (16: repeat previous 3-6, 17: zeros 3-10,
-                // 18: zeros 11-138, greedy like zlib's send_tree), place them with a prefix scan over the runs
                 const int total = hlit + hdist;
-                auto length_at = [&](int k) -> uint32_t { return k < hlit ? ws.len[k] : dist_len; };
-                uint16_t *run_start = ws.k.parent;  // scratch: free once the code lengths exist
+                auto length_at = [&](int q) -> uint32_t { return q < hlit ? ws.len[q] : dist_len; };
+                uint16_t *run_start = ws.k.run_start;
                 int nruns = 0;
                 for (int k0 = 0; k0 < total; k0 += 32) {
-                    const int k = k0 + lane;
-                    const bool st = k < total && (k == 0 || length_at(k) != length_at(k - 1));
+                    const int q = k0 + lane;
+                    const bool st = q < total && (q == 0 || length_at(q) != length_at(q - 1));
                     const uint32_t m = __ballot_sync(FULL, st);
-                    if (st) run_start[nruns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+                    if (st) run_start[nruns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)q;
                     nruns += __popc(m);
                 }
                 __syncwarp();
                 for (int r0 = 0; r0 < nruns; r0 += 32) {
-                    const int r = r0 + lane;
+                    const int rr = r0 + lane;
                     uint32_t v = 0, n18 = 0, n17 = 0, n16 = 0, nlit = 0, tail = 0;
                     // n18 / n16: full-size repeat symbols; tail: size of one more, smaller repeat symbol (0 = none)
-                    if (r < nruns) {
-                        const int s0 = run_start[r];
-                        const int s1 = r + 1 < nruns ? run_start[r + 1] : total;
+                    if (rr < nruns) {
+                        const int s0 = run_start[rr];
+                        const int s1 = rr + 1 < nruns ? run_start[rr + 1] : total;
                         uint32_t left = (uint32_t)(s1 - s0);
                         v = length_at(s0);
                         if (v == 0) {
@@ -304,7 +626,7 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
                         if (lane >= d) incl += t;
                     }
                     int at = ncl + (int)(incl - cnt);
-                    if (r < nruns) {
+                    if (rr < nruns) {
                         if (v == 0) {
                             const uint32_t full18 = tail >= 11 ? n18 - 1 : n18;
                             for (uint32_t i = 0; i < full18; ++i) {
@@ -355,29 +677,20 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
             int hclen = 19;
             while (hclen > 4 && ws.cllen[order[hclen - 1]] == 0) --hclen;
 
-            // ---- size of the dynamic block in bits (header + tokens + end of block)
+            // ---- size of the dynamic block in bits (header + tokens + end of block): stored instead if that is smaller
             uint32_t hdr_bits = 0;
-            for (int k = lane; k < ncl; k += 32) {
-                const uint32_t s = ws.clsym[k];
+            for (int q = lane; q < ncl; q += 32) {
+                const uint32_t s = ws.clsym[q];
                 hdr_bits += ws.cllen[s] + (s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0);
             }
-            uint32_t tok_bits = 0;
-            for (int s = lane; s < 286; s += 32) {
-                uint32_t xb = 0;
-                if (s >= 265 && s < 285) xb = (uint32_t)(s - 261) >> 2;
-                tok_bits += ws.hist[s] * (ws.len[s] + xb + (s > 256 ? dist_len : 0));
-            }
-            // (hist[] was bumped for dummy symbols by huffman_lengths: they have no tokens, but the estimate only
-            //  has to be an upper bound for the stored-block decision; the exact positions come from the scan below)
-            uint32_t dyn_bits = tok_bits + hdr_bits;
 #pragma unroll
-            for (int d = 16; d; d >>= 1) dyn_bits += __shfl_xor_sync(FULL, dyn_bits, d);
-            dyn_bits += 3 + 5 + 5 + 4 + 3 * hclen;
+            for (int d = 16; d; d >>= 1) hdr_bits += __shfl_xor_sync(FULL, hdr_bits, d);
+            const uint32_t dyn_bits = tok_bits + hdr_bits + 3 + 5 + 5 + 4 + 3 * hclen;
             const uint32_t stored_bits = 8u * blen + 40u;
-            stage_block();  // the construction scratch overwrote the block
 
             if (dyn_bits >= stored_bits + 7u) {
                 // ---- stored block: pad to a byte boundary, LEN, NLEN, raw bytes
+                if ((bo.bitpos >> 3) + 16 > DEF_OUT) bo.flush(lane, false);
                 if (lane == 0) bo.put(bo.bitpos, last ? 1u : 0u, 3);
                 bo.bitpos = (bo.bitpos + 3 + 7) & ~7u;
                 if (lane == 0) {
@@ -388,7 +701,7 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
                 for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
                     if ((bo.bitpos >> 3) + 40 > DEF_OUT) bo.flush(lane, false);
                     const uint32_t i = t0 + lane;
-                    if (i < blen) bo.put(bo.bitpos + 8 * lane, blk[i], 8);
+                    if (i < blen) bo.put(bo.bitpos + 8 * lane, src[b0 + i], 8);
                     bo.bitpos += 8 * min(32u, blen - t0);
                 }
             } else {
@@ -404,8 +717,8 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
                     p += 5;
                     bo.put(p, (uint32_t)(hclen - 4), 4);
                     p += 4;
-                    for (int k = 0; k < hclen; ++k) {
-                        bo.put(p, ws.cllen[order[k]], 3);
+                    for (int q = 0; q < hclen; ++q) {
+                        bo.put(p, ws.cllen[order[q]], 3);
                         p += 3;
                     }
                     bo.bitpos = p;
@@ -413,96 +726,179 @@ __global__ void __launch_bounds__(DEF_WARPS * 32) deflate_kernel(const DeflateAr
                 bo.bitpos = __shfl_sync(FULL, bo.bitpos, 0);
                 for (int k0 = 0; k0 < ncl; k0 += 32) {
                     if ((bo.bitpos >> 3) + 64 > DEF_OUT) bo.flush(lane, false);
-                    const int k = k0 + lane;
-                    uint32_t bits = 0, nb = 0;
-                    if (k < ncl) {
-                        const uint32_t s = ws.clsym[k];
-                        nb = ws.cllen[s];
+                    const int q = k0 + lane;
+                    uint32_t bits = 0, nbits = 0;
+                    if (q < ncl) {
+                        const uint32_t s = ws.clsym[q];
+                        nbits = ws.cllen[s];
                         bits = ws.clcode[s];
                         const uint32_t xb = s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0;
-                        bits |= (uint32_t)ws.clext[k] << nb;
-                        nb += xb;
+                        bits |= (uint32_t)ws.clext[q] << nbits;
+                        nbits += xb;
                     }
-                    uint32_t incl = nb;
+                    uint32_t incl = nbits;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const uint32_t t = __shfl_up_sync(FULL, incl, d);
                         if (lane >= d) incl += t;
                     }
-                    bo.put(bo.bitpos + incl - nb, bits, nb);
+                    bo.put(bo.bitpos + incl - nbits, bits, nbits);
                     bo.bitpos += __shfl_sync(FULL, incl, 31);
                 }
-                // ---- pass 2: tokens.  Same tokenisation as pass 1; a warp prefix scan over the token bit counts
+                // ---- tokens.  Same tokenisation as the counting kernel; a warp prefix scan over the token bit counts
                 // places every lane's bits.
-                for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
-                    if ((bo.bitpos >> 3) + 80 > DEF_OUT) bo.flush(lane, false);
-                    const Token tk = strip_token(blk, t0, blen, have_prev, lane);
-                    uint32_t bits = 0, nb = 0;
-                    if (tk.kind == 1) {
-                        bits = ws.code[tk.byte];
-                        nb = ws.len[tk.byte];
-                    } else if (tk.kind == 2) {
-                        uint32_t sym, xb, xv;
-                        len_code(tk.mlen, sym, xb, xv);
-                        nb = ws.len[257 + sym];
-                        bits = ws.code[257 + sym] | (xv << nb);
-                        nb += xb;
-                        // distance code 0 (distance 1): its one-bit canonical code is 0
-                        nb += dist_len;
-                    }
-                    uint32_t incl = nb;
+                if (mode == MODE_LIT) {
+                    WordReader rd;
+                    rd.start(src + b0, slab_end, lane);
+                    const uint32_t nstrip = (blen + 127) >> 7;
+                    for (uint32_t t = 0; t < nstrip; ++t) {
+                        if ((bo.bitpos >> 3) + 256 > DEF_OUT) bo.flush(lane, false);
+                        const uint32_t v = rd.next(t, lane);
+                        const uint32_t pos = (t << 7) + 4u * lane;
+                        const uint32_t nv = pos >= blen ? 0u : min(4u, blen - pos);
+                        uint32_t e0 = ws.tab[v & 255u], e1 = ws.tab[(v >> 8) & 255u], e2 = ws.tab[(v >> 16) & 255u],
+                                 e3 = ws.tab[v >> 24];
+                        if (nv < 4) {
+                            if (nv < 1) e0 = 0;
+                            if (nv < 2) e1 = 0;
+                            if (nv < 3) e2 = 0;
+                            e3 = 0;
+                        }
+                        const uint32_t l0 = e0 >> 16, l1 = e1 >> 16, l2 = e2 >> 16, l3 = e3 >> 16;
+                        // two halves of at most 30 bits each, then one 64-bit word
+                        const uint32_t lo = (e0 & 0xffffu) | ((e1 & 0xffffu) << l0);
+                        const uint32_t hi = (e2 & 0xffffu) | ((e3 & 0xffffu) << l2);
+                        const uint32_t nlo = l0 + l1, nbits = nlo + l2 + l3;
+                        const uint64_t acc = (uint64_t)lo | ((uint64_t)hi << nlo);
+                        uint32_t incl = nbits;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-                        if (lane >= d) incl += t;
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t q = __shfl_up_sync(FULL, incl, d);
+                            if (lane >= d) incl += q;
+                        }
+                        put64(bo, bo.bitpos + incl - nbits, acc, nbits);
+                        bo.bitpos += __shfl_sync(FULL, incl, 31);
                     }
-                    bo.put(bo.bitpos + incl - nb, bits, nb);
-                    bo.bitpos += __shfl_sync(FULL, incl, 31);
+                } else {
+                    uint32_t prev0 = b0 ? (uint32_t)src[b0 - 1] : 0x200u;
+                    for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
+                        if ((bo.bitpos >> 3) + 80 > DEF_OUT) bo.flush(lane, false);
+                        const uint32_t i = t0 + lane;
+                        const uint32_t b = i < blen ? (uint32_t)src[b0 + i] : 0x100u;
+                        const Token tk = strip_token(b, prev0, lane);
+                        prev0 = __shfl_sync(FULL, b, 31);
+                        uint32_t bits = 0, nbits = 0;
+                        if (tk.kind == 1) {
+                            const uint32_t e = ws.tab[b];
+                            bits = e & 0xffffu;
+                            nbits = e >> 16;
+                        } else if (tk.kind == 2) {
+                            uint32_t sym, xb, xv;
+                            len_code(tk.mlen, sym, xb, xv);
+                            const uint32_t e = ws.tab[257 + sym];
+                            nbits = e >> 16;
+                            bits = (e & 0xffffu) | (xv << nbits);
+                            nbits += xb;
+                            nbits += dist_len;  // distance code 0 (distance 1): its one-bit canonical code is 0
+                        }
+                        uint32_t incl = nbits;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t q = __shfl_up_sync(FULL, incl, d);
+                            if (lane >= d) incl += q;
+                        }
+                        bo.put(bo.bitpos + incl - nbits, bits, nbits);
+                        bo.bitpos += __shfl_sync(FULL, incl, 31);
+                    }
                 }
+                if ((bo.bitpos >> 3) + 8 > DEF_OUT) bo.flush(lane, false);
                 if (lane == 0) bo.put(bo.bitpos, ws.code[256], ws.len[256]);
                 bo.bitpos += ws.len[256];
             }
-            b0 = b1;
             __syncwarp();
-        } while (b0 < ilen);
+        }
         // ---- Adler-32 trailer, big endian, byte aligned
         bo.bitpos = (bo.bitpos + 7) & ~7u;
         if ((bo.bitpos >> 3) + 8 > DEF_OUT) bo.flush(lane, false);
-        if (lane == 0) {
-            const uint32_t ad = (ad_b << 16) | ad_a;
-            bo.put(bo.bitpos, __byte_perm(ad, 0, 0x0123), 32);
-        }
+        if (lane == 0) bo.put(bo.bitpos, __byte_perm(wk.adler[r], 0, 0x0123), 32);
         bo.bitpos += 32;
         bo.flush(lane, true);
-        if (lane == 0) {
-            a.out_len[r] = (uint32_t)bo.written;
-            a.status[r] = S5B_OK;
-        }
+        if (lane == 0) a.out_len[r] = (uint32_t)bo.written;
         __syncwarp();
     }
 }
 
-int deflate_blocks_per_sm() {
-    int n = 0;
-    if (cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(DefWarpSmem) * DEF_WARPS)) != cudaSuccess)
-        return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, deflate_kernel, DEF_WARPS * 32,
-                                                      sizeof(DefWarpSmem) * DEF_WARPS) != cudaSuccess)
-        return 0;
-    return n;
+struct DefOcc {
+    int cnt = 0, emit = 0;
+    bool ready = false;
+};
+static DefOcc &def_occ() {
+    static DefOcc o;
+    if (!o.ready) {
+        if (cudaFuncSetAttribute(deflate_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(EmitWarpSmem) * EMIT_WARPS)) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o.emit, deflate_emit_kernel, EMIT_WARPS * 32,
+                                                          sizeof(EmitWarpSmem) * EMIT_WARPS) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o.cnt, deflate_count_kernel, CNT_WARPS * 32, 0) == cudaSuccess)
+            o.ready = o.cnt > 0 && o.emit > 0;
+    }
+    return o;
 }
+
+}  // namespace defl
+using namespace defl;
+
+int deflate_blocks_per_sm() { return def_occ().ready ? def_occ().emit : 0; }
 
 uint64_t deflate_bound(uint64_t len) { return len + 6 * (len / DEF_BLOCK + 2) + 8; }
 
+static uint64_t def_max_blocks(uint64_t in_capacity, uint64_t n_reads) { return in_capacity / DEF_BLOCK + 3 * n_reads + 1; }
+
+size_t deflate_work_bytes(uint64_t in_capacity, uint64_t n_reads) {
+    const uint64_t mb = def_max_blocks(in_capacity, n_reads);
+    return (size_t)(n_reads * 4 + (n_reads + 1) * 8 + n_reads * 4 + mb * 16 + mb * DEF_ROW * 5 + compact_scratch_bytes(n_reads) + 512);
+}
+
 cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
+    (void)blocks_per_sm;
+    if (a.n_reads == 0) return cudaSuccess;
+    if (!a.work || a.work_bytes < deflate_work_bytes(a.in_capacity, a.n_reads)) return cudaErrorInvalidValue;
+    DefOcc &occ = def_occ();
+    if (!occ.ready) return cudaErrorInvalidDeviceFunction;
+    // carve the workspace (16-byte aligned pieces)
+    DefWork w;
+    const uint64_t n = a.n_reads, mb = def_max_blocks(a.in_capacity, n);
+    uint8_t *p = static_cast<uint8_t *>(a.work);
+    auto take = [&](size_t bytes) {
+        uint8_t *q = p;
+        p += (bytes + 15) & ~size_t(15);
+        return q;
+    };
+    w.binfo = reinterpret_cast<uint4 *>(take(mb * 16));
+    w.blk_off = reinterpret_cast<uint64_t *>(take((n + 1) * 8));
+    w.keys = reinterpret_cast<uint32_t *>(take(mb * DEF_ROW * 4));
+    w.nblk = reinterpret_cast<uint32_t *>(take(n * 4));
+    w.adler = reinterpret_cast<uint32_t *>(take(n * 4));
+    w.lens = take(mb * DEF_ROW);
+    w.scan_scratch = take(compact_scratch_bytes(n));
+    w.max_blocks = mb;
+    deflate_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, w);
+    cudaError_t e = launch_scan(w.nblk, n, 1, w.blk_off, w.scan_scratch, st);
     if (e != cudaSuccess) return e;
-    uint64_t want = (a.n_reads + DEF_WARPS - 1) / DEF_WARPS;
-    uint64_t cap = (uint64_t)num_sms * (blocks_per_sm > 0 ? blocks_per_sm : 1);
-    unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (!grid) grid = 1;
-    deflate_kernel<<<grid, DEF_WARPS * 32, sizeof(DefWarpSmem) * DEF_WARPS, st>>>(a);
+    auto grid_for = [&](int warps, int bps) {
+        uint64_t want = (n + warps - 1) / warps;
+        uint64_t cap = (uint64_t)num_sms * (bps > 0 ? bps : 1);
+        unsigned g = (unsigned)(want < cap ? want : cap);
+        return g ? g : 1u;
+    };
+    e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    deflate_count_kernel<<<grid_for(CNT_WARPS, occ.cnt), CNT_WARPS * 32, 0, st>>>(a, w);
+    // one thread per block; the block count lives on the device (blk_off[n]): the grid covers the bound, idle warps leave
+    deflate_tree_kernel<<<(unsigned)((mb + TREE_THREADS - 1) / TREE_THREADS), TREE_THREADS, 0, st>>>(w, w.blk_off + n);
+    e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    deflate_emit_kernel<<<grid_for(EMIT_WARPS, occ.emit), EMIT_WARPS * 32, sizeof(EmitWarpSmem) * EMIT_WARPS, st>>>(a, w);
     return cudaGetLastError();
 }
 

@@ -1,5 +1,7 @@
 // blow5_io.cpp -- see blow5_io.hpp.  Host-side BLOW5/SLOW5 framing; no codec arithmetic in this file.
 #include "blow5_io.hpp"
+#include <sys/stat.h>
+#include <new>
 
 #include <algorithm>
 #include <cerrno>
@@ -231,7 +233,20 @@ bool reader_open(Reader &r, const char *path, Fmt fmt) {
         }
         uint32_t hsize;
         memcpy(&hsize, fixed + 64, 4);
-        std::string text(hsize, '\0');
+        {
+            struct stat fst;
+            if (fstat(fileno(r.fp), &fst) == 0 && S_ISREG(fst.st_mode) && (uint64_t)hsize + 68 > (uint64_t)fst.st_size) {
+                r.err = "malformed blow5 header: truncated";
+                return false;
+            }
+        }
+        std::string text;
+        try {
+            text.assign(hsize, '\0');
+        } catch (const std::bad_alloc &) {
+            r.err = "malformed blow5 header: implausible size";
+            return false;
+        }
         if (hsize && fread(&text[0], 1, hsize, r.fp) != hsize) {
             r.err = "malformed blow5 header: truncated";
             return false;
@@ -299,11 +314,23 @@ int reader_next_mem(Reader &r, std::vector<uint8_t> &mem) {
         }
         uint64_t size;
         memcpy(&size, pre, 8);
-        if (size > (1ull << 40)) {
+        // a size prefix cannot exceed what is left of a regular file: a corrupt prefix must not turn into a huge
+        // allocation (the reference reports the failed read and exits, slow5.c:3262-3271)
+        uint64_t limit = 1ull << 40;
+        struct stat fst;
+        const off_t here = ftello(r.fp);
+        if (here >= 0 && fstat(fileno(r.fp), &fst) == 0 && S_ISREG(fst.st_mode) && (uint64_t)fst.st_size >= (uint64_t)here)
+            limit = (uint64_t)fst.st_size - (uint64_t)here;
+        if (size > limit) {
             r.err = "implausible record size (corrupt file?)";
             return -1;
         }
-        mem.resize(size);
+        try {
+            mem.resize(size);
+        } catch (const std::bad_alloc &) {
+            r.err = "cannot allocate memory for a record (corrupt size prefix?)";
+            return -1;
+        }
         if (size && fread(mem.data(), 1, size, r.fp) != size) {
             r.err = "blow5 record is truncated";
             return -1;

@@ -6,6 +6,7 @@
 // the slot src/get.c:359 fills with work_db(&core, &db, work_per_single_read_get).
 #include <getopt.h>
 #include <unistd.h>
+#include <sys/stat.h>
 
 #include <cerrno>
 #include <cstdint>
@@ -267,6 +268,14 @@ int get_main(int argc, char **argv) {
             const uint64_t lead = text_in ? 0 : 8, trail = text_in ? 1 : 0;
             if (it->second.size < lead + trail) {
                 GET_ERROR("Index entry of '%s' is malformed.", id.c_str());
+                failed = true;
+                return -1;
+            }
+            // the index is untrusted input: an entry may not reach past the end of the file
+            struct stat fst;
+            if (fstat(fd, &fst) == 0 && S_ISREG(fst.st_mode) &&
+                (it->second.offset > (uint64_t)fst.st_size || it->second.size > (uint64_t)fst.st_size - it->second.offset)) {
+                GET_ERROR("Index entry of '%s' points outside the file.", id.c_str());
                 failed = true;
                 return -1;
             }

@@ -13,6 +13,8 @@
 // There is no CPU codec here: without a CUDA device the command fails.
 #include <getopt.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <cerrno>
 
 #include <atomic>
@@ -132,7 +134,14 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
     const bool timing = getenv("S5B_TIMING") != nullptr;
     const double t_begin = now_s();
     double t_gpu = 0, t_wait = 0;
-    const uint64_t target = 32ull << 20;
+    uint64_t target = 32ull << 20, slack = 8ull << 20;
+    if (const char *e = getenv("S5B_VIEW_CHUNK_KB")) {  // test hook: small chunks exercise the carry / grow paths
+        const long kb = atol(e);
+        if (kb > 0) {
+            target = (uint64_t)kb << 10;
+            slack = target / 4 + 64;
+        }
+    }
     const int NCH = 3;
     Chunk chunks[NCH];
     ChunkQueue free_q, full_q, done_q;
@@ -140,9 +149,9 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
     // chunk whose image does not fit is retried with a larger buffer
     const bool expanding = hdr.record_method != PRESS_NONE || hdr.signal_method != PRESS_NONE;
     for (int i = 0; i < NCH; ++i) {
-        chunks[i].in_cap = target + (8u << 20);
+        chunks[i].in_cap = target + slack;
         chunks[i].in = static_cast<uint8_t *>(s5b_host_alloc(chunks[i].in_cap));
-        chunks[i].out_cap = (expanding ? 3 : 1) * target + (8u << 20);
+        chunks[i].out_cap = (expanding ? 3 : 1) * target + slack;
         chunks[i].out = static_cast<uint8_t *>(s5b_host_alloc(chunks[i].out_cap));
         if (!chunks[i].in || !chunks[i].out) {
             ERROR("%s", "cannot allocate pinned staging memory");
@@ -171,9 +180,17 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
             c->eof = false;
             c->err = 0;
             uint64_t filled = carry.size();
-            if (filled > c->in_cap) {  // one record larger than a chunk: grow
+            // The carry starts at a record boundary: its size prefix says how much room that record needs.  A record
+            // larger than the chunk (ultra-long reads, uncompressed input) grows the buffer to hold it whole.
+            uint64_t need = filled;
+            if (filled >= 8) {
+                uint64_t size;
+                memcpy(&size, carry.data(), 8);
+                if (size <= (1ull << 32) - 64 && 8 + size > need) need = 8 + size;
+            }
+            if (need >= c->in_cap) {
                 s5b_host_free(c->in);
-                c->in_cap = filled + target;
+                c->in_cap = need + target;
                 c->in = static_cast<uint8_t *>(s5b_host_alloc(c->in_cap));
             }
             if (!c->in) {
@@ -259,7 +276,11 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
     const int ofd = fileno(fout);
     fflush(fout);
     const off_t wstart = lseek(ofd, 0, SEEK_CUR);
-    const bool seekable = wstart >= 0;
+    // positioned writes need a regular file that honours the offset: with O_APPEND (shell `>>`) pwrite() appends
+    // wherever the parts happen to finish, so such descriptors take the sequential path like pipes do
+    struct stat ost;
+    const int oflags = fcntl(ofd, F_GETFL);
+    const bool seekable = wstart >= 0 && fstat(ofd, &ost) == 0 && S_ISREG(ost.st_mode) && oflags >= 0 && !(oflags & O_APPEND);
     uint64_t wpos = seekable ? (uint64_t)wstart : 0;
     std::thread writer([&] {
         for (;;) {

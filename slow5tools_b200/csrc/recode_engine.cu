@@ -32,7 +32,7 @@ using namespace s5b;
 namespace s5b {
 
 void RecodeLane::release() {
-    for (DevBuf *b : {&in, &infl, &sig, &svb, &packed, &z, &img, &meta, &scratch, &zd_scratch, &tab}) b->release();
+    for (DevBuf *b : {&in, &infl, &sig, &svb, &packed, &z, &img, &meta, &scratch, &zd_scratch, &tab, &work}) b->release();
     h_tab.release();
     if (d_counter) cudaFree(d_counter);
     if (d_res) cudaFree(d_res);
@@ -361,8 +361,8 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
                            L.d_counter};
             // PLAN_ZLIB_BOUND slots also cover zstd_encode_bound() (3 bytes of header per block instead of 6)
             if (j.out_rec == S5B_COMPRESS_ZSTD) CU(launch_zstd_encode(za, ctx->num_sms, ctx->ze_bps, st));
-            else CU(launch_deflate(za, ctx->num_sms, ctx->def_bps, st));
-            ctx->launches += 3;
+            else CU(launch_deflate_ws(L.work, za, ctx->num_sms, ctx->def_bps, st));
+            ctx->launches += 9;
             st_z = d_st_z;
             fin = static_cast<const uint8_t *>(L.z.p);
             fin_off = d_z_off;

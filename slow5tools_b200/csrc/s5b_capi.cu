@@ -138,6 +138,7 @@ void s5b_ctx_destroy(s5b_ctx_t *ctx) {
         s.d_c.release();
         s.d_meta.release();
         s.d_scratch.release();
+        s.d_work.release();
         s.h_meta.release();
         if (s.d_counter) cudaFree(s.d_counter);
         if (s.done) cudaEventDestroy(s.done);
@@ -146,7 +147,7 @@ void s5b_ctx_destroy(s5b_ctx_t *ctx) {
     ctx->d_scratch.release();
     ctx->zd_scratch.release();
     for (DevBuf *b : {&ctx->r_in, &ctx->r_infl, &ctx->r_sig, &ctx->r_svb, &ctx->r_packed, &ctx->r_z, &ctx->r_img, &ctx->r_meta,
-                      &ctx->r_scratch})
+                      &ctx->r_scratch, &ctx->r_work, &ctx->def_work})
         b->release();
     recode_lanes_release(ctx);
     ctx->h_stage_in.release();
@@ -303,8 +304,8 @@ int s5b_zlib_deflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     DeflateArgs a{d_in, d_in_off, d_in_len, in_capacity, d_split, n_reads, d_out, d_out_off, d_out_len, d_status,
                   ctx->d_counter + 24};
-    CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
-    ctx->launches += 1;
+    CU(launch_deflate_ws(ctx->def_work, a, ctx->num_sms, ctx->def_bps, st));
+    ctx->launches += 7;
     return S5B_OK;
 }
 
@@ -921,7 +922,7 @@ static int entropy_compress_ptrs(s5b_ctx_t *ctx, int method, const void *const *
     DeflateArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), splits ? d_split : nullptr, n,
                   static_cast<uint8_t *>(s.d_b.p), d_out_off, d_out_len, d_status, s.d_counter};
     if (method == S5B_COMPRESS_ZSTD) CU(launch_zstd_encode(a, ctx->num_sms, ctx->ze_bps, st));
-    else CU(launch_deflate(a, ctx->num_sms, ctx->def_bps, st));
+    else CU(launch_deflate_ws(s.d_work, a, ctx->num_sms, ctx->def_bps, st));
     ctx->launches += 1;
     CU(cudaMemcpyAsync(out_len.data(), d_out_len, n * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(status.data(), d_status, n * 4, cudaMemcpyDeviceToHost, st));
@@ -1302,7 +1303,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
                            counter};
             // PLAN_ZLIB_BOUND slots also cover zstd_encode_bound() (3 bytes of header per block instead of 6)
             if (out_rec == S5B_COMPRESS_ZSTD) CU(launch_zstd_encode(za, ctx->num_sms, ctx->ze_bps, st));
-            else CU(launch_deflate(za, ctx->num_sms, ctx->def_bps, st));
+            else CU(launch_deflate_ws(ctx->r_work, za, ctx->num_sms, ctx->def_bps, st));
             ctx->launches += 3;
             if (check_status(d_st3) != S5B_OK) return S5B_ERR_DEVICE;
             if (first_err != S5B_OK) return first_err;

@@ -60,6 +60,7 @@ struct PipeSlot {
     DevBuf d_a, d_b, d_c;       // payload in / slotted out / dense out
     DevBuf d_meta;              // offsets, lengths, statuses
     DevBuf d_scratch;           // scan scratch
+    DevBuf d_work;              // deflate workspace
     PinBuf h_meta;              // pinned mirror of d_meta (both directions)
     unsigned long long *d_counter = nullptr;
 };
@@ -73,7 +74,7 @@ enum Stage { ST_H2D = 0, ST_REC_DEPRESS, ST_GLUE, ST_SIG_DEPRESS, ST_SIG_PRESS, 
 struct RecodeLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t front = nullptr;     // everything up to the (size, status) read-back of the chunk in flight
-    DevBuf in, infl, sig, svb, packed, z, img, meta, scratch, zd_scratch, tab;
+    DevBuf in, infl, sig, svb, packed, z, img, meta, scratch, zd_scratch, tab, work;
     PinBuf h_tab;                    // pinned staging of the chunk's record table (up) and image offsets (down)
     unsigned long long *d_counter = nullptr;
     uint64_t *d_res = nullptr;       // [0] image bytes of the chunk, [1] first error (int32 in the low half), [2] its record
@@ -102,7 +103,8 @@ struct s5b_ctx {
     s5b::DevBuf d_scratch;
     s5b::PipeSlot slot[s5b::NSLOT];
     s5b::PinBuf h_stage_in, h_stage_out;  // pointer-array forms
-    s5b::DevBuf r_in, r_infl, r_sig, r_svb, r_packed, r_z, r_img, r_meta, r_scratch;  // the careful (synchronous) transcoder
+    s5b::DevBuf r_in, r_infl, r_sig, r_svb, r_packed, r_z, r_img, r_meta, r_scratch, r_work;  // the careful (synchronous) transcoder
+    s5b::DevBuf def_work;                 // deflate workspace of the *_dev entry points
     s5b::RecodeLane lane[s5b::NLANE];     // the pipelined transcoder (lazily created)
     bool lanes_ready = false;
     uint64_t *d_img_base = nullptr;       // running output offset of a device-resident transcoding pass
@@ -140,6 +142,16 @@ struct DeviceGuard {
 };
 
 inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// deflate needs a workspace (sorted symbol lists, code lengths per block): reserve it in `buf` and launch
+inline cudaError_t launch_deflate_ws(DevBuf &buf, DeflateArgs a, int num_sms, int blocks_per_sm, cudaStream_t st) {
+    const size_t need = deflate_work_bytes(a.in_capacity, a.n_reads);
+    cudaError_t e = buf.reserve(need);
+    if (e != cudaSuccess) return e;
+    a.work = buf.p;
+    a.work_bytes = buf.cap;
+    return launch_deflate(a, num_sms, blocks_per_sm, st);
+}
 
 // the careful transcoder of one chunk (host syncs between stages, inflate-slot retry, exact error reporting); lives in
 // s5b_capi.cu and is the fallback of the pipelined engine

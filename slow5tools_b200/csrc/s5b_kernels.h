@@ -55,8 +55,11 @@ struct DeflateArgs {
     uint32_t *out_len;
     int32_t *status;
     unsigned long long *work_counter;
+    void *work = nullptr;        // deflate only: device workspace of >= deflate_work_bytes(in_capacity, n_reads) bytes
+    uint64_t work_bytes = 0;
 };
 int deflate_blocks_per_sm();
+size_t deflate_work_bytes(uint64_t in_capacity, uint64_t n_reads);
 uint64_t deflate_bound(uint64_t len);
 cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
 

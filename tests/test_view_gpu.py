@@ -250,3 +250,33 @@ def test_fast_path_small_last_chunk_lands_after_the_big_ones(tmp_path):
         slow = tmp_path / "slow.blow5"
         ours(str(raw), "-o", str(slow), *flags, env={"S5B_VIEW_SLOW_PATH": "1"})
         assert filecmp.cmp(z, slow, shallow=False), flags
+
+
+@have_ref
+def test_record_larger_than_a_chunk(tmp_path):
+    """blow5 -> blow5 fast path with chunks far smaller than one stored record (S5B_VIEW_CHUNK_KB test hook): the reader
+    must grow its buffer from the record's own size prefix instead of carrying the same bytes forever (round-1 advisor
+    finding: a record >= the 40 MiB chunk made `view` spin)."""
+    src = os.path.join(FIX, "exp_1_lossless_zlib_svb_v0.2.0.blow5")
+    raw, small, normal = tmp_path / "raw.blow5", tmp_path / "small.blow5", tmp_path / "normal.blow5"
+    ref(src, "-o", str(raw), "-c", "none", "-s", "none")       # uncompressed records: ~70 KB each
+    ours(str(raw), "-o", str(normal), "-c", "none", "-s", "svb-zd")
+    r = subprocess.run([CLI, "view", str(raw), "-o", str(small), "-c", "none", "-s", "svb-zd"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, env=dict(os.environ, S5B_VIEW_CHUNK_KB="4"), timeout=120)
+    assert r.returncode == 0, r.stderr.decode()
+    assert filecmp.cmp(small, normal, shallow=False)
+
+
+def test_corrupt_size_prefix_fails_cleanly(tmp_path):
+    """a record size prefix of 2^39 must give the reference's clean failure (exit 1), not an uncaught bad_alloc (rc 134)"""
+    src = os.path.join(FIX, "exp_1_lossless_zlib_svb_v0.2.0.blow5")
+    data = bytearray(open(src, "rb").read())
+    hsize = int.from_bytes(data[64:68], "little")
+    at = 68 + hsize
+    data[at:at + 8] = (1 << 39).to_bytes(8, "little")
+    bad = tmp_path / "bad.blow5"
+    bad.write_bytes(bytes(data))
+    for extra in ([], ["-K", "7"]):   # fast path and the -K slow path
+        r = subprocess.run([CLI, "view", str(bad), "-o", str(tmp_path / "o.slow5")] + extra, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, timeout=60)
+        assert r.returncode == 1, (r.returncode, r.stderr.decode())
