@@ -20,6 +20,7 @@
 // tables) -- which also owns every error / truncation verdict, so behaviour matches zlib's exactly.  All
 // lanes cooperate on table construction, LZ77 copies, the Adler-32 and the 128-bit stores of the staging
 // buffer.
+#include <cstdlib>
 #include "s5b_kernels.h"
 #include "s5b_ptx.cuh"
 #include "../../include/slow5b200.h"
@@ -503,7 +504,7 @@ __device__ __forceinline__ void adler_update(uint32_t &a, uint32_t &b, const uin
 
 }  // namespace
 
-__global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateArgs a) {
+__global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateArgs a, const uint32_t min_len) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     InfWarpSmem &ws = reinterpret_cast<InfWarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -530,6 +531,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(const InflateAr
         if (r >= a.n_reads) break;
         const uint64_t ioff = a.in_off[r];
         const uint32_t ilen = a.in_len[r];
+        if (ilen < min_len) continue;  // short streams belong to the thread-per-stream kernel (inflate_thread_kernels.cu)
         const uint64_t ooff = a.out_off[r];
         const uint64_t ocap = a.out_off[r + 1] - ooff;
         if (ioff + ilen > a.in_capacity) {
@@ -1180,14 +1182,30 @@ int inflate_blocks_per_sm() {
     return n;
 }
 
+// Streams of at most INF_THREAD_MAX_LEN bytes are decoded one per THREAD (inflate_thread_kernels.cu), longer ones one per
+// warp with the speculative window decoder above; both kernels sweep the whole batch and skip the other's streams.
+// S5B_INFLATE_THREAD_MAX (bytes, read once) moves the boundary; 0 sends everything to the warp kernel.
+static uint32_t inflate_thread_max_len() {
+    static const uint32_t v = [] {
+        const char *e = getenv("S5B_INFLATE_THREAD_MAX");
+        return e ? (uint32_t)strtoul(e, nullptr, 10) : 16384u;
+    }();
+    return v;
+}
+
 cudaError_t launch_inflate(const InflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
+    const uint32_t tmax = inflate_thread_max_len();
+    if (tmax) {
+        cudaError_t e0 = launch_inflate_threads(a, tmax, num_sms, st);
+        if (e0 != cudaSuccess) return e0;
+    }
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     uint64_t want = (a.n_reads + INF_WARPS - 1) / INF_WARPS;
     uint64_t cap = (uint64_t)num_sms * (blocks_per_sm > 0 ? blocks_per_sm : 1);
     unsigned grid = (unsigned)(want < cap ? want : cap);
     if (!grid) grid = 1;
-    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InfWarpSmem) * INF_WARPS, st>>>(a);
+    inflate_kernel<<<grid, INF_WARPS * 32, sizeof(InfWarpSmem) * INF_WARPS, st>>>(a, tmax ? tmax + 1 : 0u);
     return cudaGetLastError();
 }
 

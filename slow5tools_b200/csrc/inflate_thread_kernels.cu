@@ -1,0 +1,574 @@
+// inflate_thread_kernels.cu -- sm_100a zlib/DEFLATE decoder for SHORT streams: one THREAD per record stream.
+//
+// BLOW5 records are independent zlib streams of a few KiB (slow5.c:4046; 4096 samples -> ~3.5 KiB).  A bit stream is
+// serial by nature; the warp-per-stream decoder (inflate_kernels.cu) buys parallelism inside a stream with speculative
+// window decoding and pays for it with three decodes of every symbol plus divergence (60 k warp instructions per record).
+// A batch has 10^5..10^6 streams, so the parallelism is there without speculation: here every lane runs a serial decoder
+// on its own stream, 32 streams per warp.  Two things make that work on a GPU:
+//   * LOCK STEP.  A warp takes 32 consecutive records and all lanes move through the same loops -- block header and code
+//     construction in phases, then one symbol (or up to four match bytes, or one stored byte) per lane and iteration.
+//     Every loop is steered by a warp-wide vote or has a fixed trip count, which is also what keeps the 32 decoders
+//     converged: left to themselves, 32 data-dependent decoders diverge for good and independent thread scheduling
+//     runs them one after the other (measured: 12x slower than the warp-per-stream kernel).
+//   * NO LOOKUP TABLES.  A first-level table per lane (512 B + overflow lists) fills shared memory at 4 warps per SM and
+//     the dependent load-shift-load chain of a serial decoder then leaves the SM idle 85 % of the time.  Instead a symbol
+//     is decoded canonically: the next 15 bits, MSB first, are compared against the per-length code limits held in
+//     REGISTERS (a four-level select tree, ~20 instructions, no memory access), and the symbol comes from the list of
+//     symbols sorted by (length, symbol) that every lane keeps in a global-memory scratch row (L1 resident: the frequent
+//     symbols are its first bytes).  Per lane that leaves 160 bytes of shared memory (output ring, code bases), so the
+//     kernel runs at register-limited occupancy and hides its latencies with other warps.
+// Streams longer than the caller's threshold stay with the warp-per-stream kernel (a serial decode of a 200 KiB stream
+// would be a long tail for the 31 lanes next to it).
+//
+// Observable behaviour is that of ptr_depress_zlib_solo (slow5lib/src/slow5_press.c:973-1010) as mirrored by
+// inflate_kernels.cu: RFC 1950 header check, stored / fixed / dynamic blocks, 32 KiB window, Adler-32 check; malformed
+// data -> S5B_ERR_PRESS; input that ends early is not an error and yields the bytes decoded so far; a slot that is too
+// small -> S5B_ERR_NOSPACE with the size needed in out_len.
+#include "s5b_kernels.h"
+#include "s5b_ptx.cuh"
+#include "../../include/slow5b200.h"
+
+namespace s5b {
+
+namespace inft {
+
+constexpr int TI_WARPS = 4;
+constexpr int TI_CTAS_PER_SM = 4;   // 16 warps per SM
+constexpr int RING = 64;            // per-lane output ring (bytes): staging for 16-byte stores, source of near matches
+constexpr int FLUSH_EVERY = 8;      // iterations; a lane produces <= 4 bytes per iteration: <= 32 + 15 unflushed < RING
+constexpr uint32_t ADLER_MOD = 65521u;
+
+// per-lane shared memory
+struct TiSmem {
+    uint8_t ring[RING];
+    int16_t lit_base[16];    // sorted index of the first code of a length minus that code: sym = sorted[base[l] + code]
+    uint16_t lit_lim[16];    // end of the codes of each length, left-aligned to 15 bits
+    int16_t aux_base[16];    // the same for the code-length code (while a header is read) / the distance code (after)
+    uint16_t aux_lim[16];
+    uint16_t next[16];       // construction scratch
+};
+// per-lane global scratch row
+struct TiScratch {
+    uint16_t lit_sorted[288];
+    uint16_t aux_sorted[32];
+    uint8_t lens[320];       // literal/length code lengths at 0, distance code lengths at 288
+    uint8_t tmp[320];        // code-length code lengths / distance lengths on their way to lens[288..]
+};
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31,
+                                        35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+                                         1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8,
+                                         9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+enum : int { END_OK = 0, END_TRUNC = 1, END_ERR = 2 };
+enum : int { ST_DONE = 0, ST_BLOCK = 1, ST_SYM = 2, ST_MATCH = 3, ST_STORED = 4 };
+
+// ---- input side of one lane ---------------------------------------------------------------------------------------
+// Two aligned 32-bit words of the stream and a bit offset into the first: the next 32 bits are one funnel shift, taking
+// n bits is an add plus a word shuffle.  `avail` counts the stream bits not yet consumed, so truncation is one compare.
+// Words that hold no stream byte are never loaded.
+struct Bits {
+    const uint32_t *w;    // next word to load
+    const uint32_t *wend; // first word that holds no stream byte
+    uint32_t w0, w1;      // current and next word
+    uint32_t off;         // consumed bits of w0 (0..31)
+    uint32_t avail;       // stream bits left (from the current position)
+    __device__ __forceinline__ uint32_t ld() {
+        const uint32_t v = w < wend ? __ldg(w) : 0u;
+        ++w;
+        return v;
+    }
+    __device__ __forceinline__ void start(const uint8_t *p, uint32_t len) {
+        const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+        w = reinterpret_cast<const uint32_t *>(p - sk);
+        wend = reinterpret_cast<const uint32_t *>(p - sk + ((sk + len + 3u) & ~3u));
+        w0 = ld();
+        w1 = ld();
+        off = sk * 8u;
+        avail = len * 8u;
+    }
+    __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(w0, w1, off); }
+    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return peek32() & ((1u << n) - 1u); }
+    // n <= 32 and n <= avail
+    __device__ __forceinline__ void drop(uint32_t n) {
+        off += n;
+        avail -= n;
+        if (off >= 32) {
+            off -= 32;
+            w0 = w1;
+            w1 = ld();
+        }
+    }
+    // to the next byte boundary of the stream (the padding bits are there whenever a whole byte follows)
+    __device__ __forceinline__ void align_byte() {
+        const uint32_t pad = (8u - (off & 7u)) & 7u;
+        if (pad <= avail) drop(pad);
+        else avail = 0;
+    }
+};
+
+// ---- output side of one lane ----------------------------------------------------------------------------------------
+// Bytes go into the ring; complete 16-byte segments of the destination (absolute alignment) leave as one 128-bit store.
+// Flushing is driven by the warp (every FLUSH_EVERY iterations of the lock-step loop all lanes store what they have), so
+// that the store + Adler-32 code runs once for 32 lanes instead of on whichever lane crosses a 16-byte boundary.
+struct Out {
+    uint8_t *ring;
+    uint8_t *dst;        // slot base
+    uint32_t cap;        // slot bytes
+    uint32_t total;      // bytes produced
+    uint32_t flushed;    // bytes [0, flushed) have been stored
+    uint32_t ad_a, ad_b;
+    uint32_t bias;       // output byte i lives at ring[(i + bias) & (RING - 1)]: 16-byte segments of the destination are
+                         // 16-byte segments of the ring
+    bool store;
+    __device__ __forceinline__ void put(uint32_t byte) {
+        if (store) {
+            if (total >= cap) store = false;
+            else ring[(total + bias) & (RING - 1)] = (uint8_t)byte;
+        }
+        ++total;
+    }
+    __device__ __forceinline__ void flush_bytes(uint32_t end) {
+        for (uint32_t i = flushed; i < end; ++i) {
+            const uint32_t d = ring[(i + bias) & (RING - 1)];
+            dst[i] = (uint8_t)d;
+            ad_a += d;
+            ad_b += ad_a;
+        }
+        ad_a %= ADLER_MOD;
+        ad_b %= ADLER_MOD;
+        flushed = end;
+    }
+    // store every complete 16-byte segment (all == false) or everything (all == true)
+    __device__ __forceinline__ void flush(bool all) {
+        if (!store) return;
+        for (;;) {
+            const uint32_t seg_end = ((flushed + bias) | 15u) + 1u - bias;  // end of the destination segment holding `flushed`
+            if (seg_end > total) break;
+            if (seg_end - flushed == 16) {
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring + ((flushed + bias) & (RING - 1)));
+                const uint4 v = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+                *reinterpret_cast<uint4 *>(dst + flushed) = v;
+                // Adler-32 over 16 bytes: b += 16 a + sum (16 - i) d_i, a += sum d_i
+                const uint32_t sum = __dp4a(v.x, 0x01010101u, 0u) + __dp4a(v.y, 0x01010101u, 0u) + __dp4a(v.z, 0x01010101u, 0u) +
+                                     __dp4a(v.w, 0x01010101u, 0u);
+                const uint32_t wsum = __dp4a(v.x, 0x0d0e0f10u, 0u) + __dp4a(v.y, 0x090a0b0cu, 0u) + __dp4a(v.z, 0x05060708u, 0u) +
+                                      __dp4a(v.w, 0x01020304u, 0u);
+                ad_b = (ad_b + 16u * ad_a + wsum) % ADLER_MOD;
+                ad_a = (ad_a + sum) % ADLER_MOD;
+                flushed = seg_end;
+            } else {
+                flush_bytes(seg_end);  // ragged first segment of the slot
+            }
+        }
+        if (all && total > flushed) flush_bytes(total);
+    }
+    // one byte of a match: out[total] = out[total - dist].  Bytes not yet stored are in the ring (it holds the last RING
+    // bytes and the unflushed tail is shorter); everything older has been stored by this thread.
+    __device__ __forceinline__ void copy1(uint32_t dist) {
+        if (!store) {
+            ++total;
+            return;
+        }
+        const uint32_t from = total - dist;
+        put(from >= flushed ? (uint32_t)ring[(from + bias) & (RING - 1)] : (uint32_t)dst[from]);
+    }
+};
+
+// ---- canonical codes ------------------------------------------------------------------------------------------------
+// From lens[0..n): lim[l] = end of the codes of length l left-aligned to 15 bits (non-decreasing in l), base[l] = sorted
+// index of the first code of length l minus that code, sorted[] = symbols by (length, symbol).  All loops have fixed trip
+// counts (NMAX) and `active` lanes are merely predicated, so the warp stays converged through the call.
+// Returns 0 ok, 1 over-subscribed, 2 incomplete (zlib's inflate_table rules decide what that means); *max_len too.
+template <int NMAX>
+__device__ __forceinline__ int build_code(bool active, const uint8_t *lens, int n, uint16_t *lim, int16_t *base, uint16_t *next,
+                                          uint16_t *sorted, int *max_len) {
+    if (active) {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) next[l] = 0;  // used as the per-length count first
+    }
+    for (int s = 0; s < NMAX; ++s) {
+        if (active && s < n) {
+            const int l = lens[s];
+            if (l) ++next[l];
+        }
+    }
+    int left = 1, status = 0, maxl = 0;
+    if (active) {
+        uint32_t code = 0, at = 0;
+#pragma unroll
+        for (int l = 1; l <= 15; ++l) {
+            const uint32_t c = next[l];
+            left <<= 1;
+            left -= (int)c;
+            if (left < 0) status = 1;
+            if (c) maxl = l;
+            base[l] = (int16_t)((int)at - (int)code);
+            lim[l] = (uint16_t)min((code + c) << (15 - l), 0xffffu);
+            next[l] = (uint16_t)at;
+            at += c;
+            code = (code + c) << 1;
+        }
+        if (status == 0 && left > 0) status = 2;
+    }
+    for (int s = 0; s < NMAX; ++s) {
+        if (active && status != 1 && s < n) {
+            const int l = lens[s];
+            if (l) sorted[next[l]++] = (uint16_t)s;
+        }
+    }
+    *max_len = maxl;
+    return status;
+}
+
+// generic canonical decode from the arrays (code-length and distance codes): returns the symbol, -1 (no such code) or -2
+// (the stream ends inside the code); *used = code length
+__device__ __forceinline__ int canon_decode(const Bits &b, const uint16_t *lim, const int16_t *base, const uint16_t *sorted,
+                                            int max_len, uint32_t *used) {
+    const uint32_t c15 = __brev(b.peek32()) >> 17;
+    int l = 1;
+    while (l <= max_len && c15 >= lim[l]) ++l;
+    if (l > max_len) return b.avail < 15u ? -2 : -1;
+    if ((uint32_t)l > b.avail) return -2;
+    *used = (uint32_t)l;
+    return sorted[base[l] + (int)(c15 >> (15 - l))];
+}
+
+__global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_kernel(const InflateArgs a, uint32_t max_len,
+                                                                                        TiScratch *scratch_rows) {
+    __shared__ TiSmem smem[TI_WARPS * 32];
+    TiSmem &sm = smem[threadIdx.x];
+    TiScratch &sc = scratch_rows[(size_t)blockIdx.x * (TI_WARPS * 32) + threadIdx.x];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long rbase = 0;
+        if (lane == 0) rbase = atomicAdd(a.work_counter, 32ULL);
+        rbase = __shfl_sync(FULL, rbase, 0);
+        if (rbase >= a.n_reads) break;
+        const unsigned long long r = rbase + lane;
+        uint32_t ilen = 0;
+        bool mine = false;
+        if (r < a.n_reads) {
+            ilen = a.in_len[r];
+            mine = ilen <= max_len;  // longer streams: the warp-per-stream kernel takes them
+        }
+        Bits in;
+        Out out;
+        int end_kind = -1;  // still decoding
+        int state = ST_DONE;
+        bool last_block = false;
+        uint32_t aux = 0, m_dist = 0;  // stored bytes left / match bytes left, match distance
+        int dist_max = 0;              // longest distance code of the current block
+        // the literal/length code limits of the current block, one register per length
+        uint32_t L1 = 0, L2 = 0, L3 = 0, L4 = 0, L5 = 0, L6 = 0, L7 = 0, L8 = 0, L9 = 0, L10 = 0, L11 = 0, L12 = 0, L13 = 0,
+                 L14 = 0, L15 = 0;
+        in.w = in.wend = reinterpret_cast<const uint32_t *>(a.in);
+        in.w0 = in.w1 = in.off = in.avail = 0;
+        out.ring = sm.ring;
+        out.dst = a.out;
+        out.cap = out.total = out.flushed = out.bias = 0;
+        out.ad_a = 1;
+        out.ad_b = 0;
+        out.store = true;
+        if (mine) {
+            const uint64_t ioff = a.in_off[r];
+            if (ioff + ilen > a.in_capacity) {
+                a.status[r] = S5B_ERR_ARG;
+                a.out_len[r] = 0;
+                mine = false;
+            } else {
+                in.start(a.in + ioff, ilen);
+                out.dst = a.out + a.out_off[r];
+                const uint64_t cap64 = a.out_off[r + 1] - a.out_off[r];
+                out.cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)cap64;
+                out.bias = (uint32_t)(reinterpret_cast<uintptr_t>(out.dst) & 15u);
+                // ---- zlib header (RFC 1950)
+                if (in.avail < 16) {
+                    end_kind = END_TRUNC;
+                } else {
+                    const uint32_t cmf = in.peek(8), flg = in.peek(16) >> 8;
+                    in.drop(16);
+                    if (((cmf << 8) | flg) % 31u != 0 || (cmf & 15u) != 8 || (cmf >> 4) > 7 || (flg & 0x20u)) end_kind = END_ERR;
+                }
+                state = end_kind < 0 ? ST_BLOCK : ST_DONE;
+            }
+        }
+        while (__any_sync(FULL, state != ST_DONE)) {
+            // ================= block boundary, in phases that all 32 lanes walk through together =================
+            const bool hb = state == ST_BLOCK;
+            bool dynamic = false, tables = false;
+            int hlit = 288, hdist = 32;
+            uint32_t hclen = 0;
+            // ---- phase 1: trailer after the final block, else the 3 header bits and what follows them directly
+            if (hb) {
+                state = ST_DONE;  // every early exit below ends the stream
+                if (last_block) {
+                    // Adler-32 trailer: big endian, byte aligned, after the final block
+                    in.align_byte();
+                    if (in.avail < 32) {
+                        end_kind = END_TRUNC;
+                    } else {
+                        const uint32_t want = __byte_perm(in.peek32(), 0, 0x0123);
+                        out.flush(true);
+                        end_kind = (!out.store || ((out.ad_b << 16) | out.ad_a) == want) ? END_OK : END_ERR;  // "incorrect data check"
+                    }
+                } else if (in.avail < 3) {
+                    end_kind = END_TRUNC;
+                } else {
+                    last_block = in.peek(1);
+                    const uint32_t btype = in.peek(3) >> 1;
+                    in.drop(3);
+                    if (btype == 3) {  // "invalid block type"
+                        end_kind = END_ERR;
+                    } else if (btype == 0) {
+                        in.align_byte();
+                        if (in.avail < 32) {
+                            end_kind = END_TRUNC;
+                        } else {
+                            const uint32_t v = in.peek32();
+                            in.drop(32);
+                            aux = v & 0xffffu;
+                            if ((aux ^ 0xffffu) != (v >> 16)) end_kind = END_ERR;  // "invalid stored block lengths"
+                            else state = aux ? ST_STORED : ST_BLOCK;
+                        }
+                    } else if (btype == 1) {
+                        tables = true;
+                    } else if (in.avail < 14) {
+                        end_kind = END_TRUNC;
+                    } else {
+                        hlit = (int)in.peek(5) + 257;
+                        hdist = (int)(in.peek(10) >> 5) + 1;
+                        hclen = (in.peek(14) >> 10) + 4;
+                        in.drop(14);
+                        if (hlit > 286 || hdist > 30) end_kind = END_ERR;  // "too many length or distance symbols"
+                        else dynamic = true;
+                    }
+                }
+            }
+            if (__any_sync(FULL, tables)) {
+                // fixed code (btype 1): lengths 8/9/7/8, all 32 five-bit distance codes (30, 31: "invalid distance code")
+                for (int s = 0; s < 320; ++s)
+                    if (tables) sc.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5;
+            }
+            if (__any_sync(FULL, dynamic)) {
+                // ---- phase 2: the code-length code (3 bits per length, fixed order), its canonical arrays
+                for (int i = 0; i < 19; ++i) {
+                    if (dynamic) {
+                        uint32_t v = 0;
+                        if ((uint32_t)i < hclen) {
+                            if (in.avail < 3) {
+                                end_kind = END_TRUNC;
+                                dynamic = false;
+                            } else {
+                                v = in.peek(3);
+                                in.drop(3);
+                            }
+                        }
+                        sc.tmp[c_cl_order[i]] = (uint8_t)v;
+                    }
+                }
+                int cl_max = 0;
+                // "invalid code lengths set": the code-length code must be complete (inftrees.c, type CODES)
+                if (build_code<19>(dynamic, sc.tmp, 19, sm.aux_lim, sm.aux_base, sm.next, sc.aux_sorted, &cl_max) != 0 && dynamic) {
+                    end_kind = END_ERR;
+                    dynamic = false;
+                }
+                // ---- phase 3: the hlit + hdist code lengths, run-length coded; one length per lane and iteration
+                const int nsym = hlit + hdist;
+                int i = 0;
+                uint32_t rep = 0, val = 0;
+                while (__any_sync(FULL, dynamic && i < nsym)) {
+                    if (dynamic && i < nsym) {
+                        if (rep) {
+                            sc.lens[i++] = (uint8_t)val;
+                            --rep;
+                        } else {
+                            uint32_t l = 0;
+                            const int sym = canon_decode(in, sm.aux_lim, sm.aux_base, sc.aux_sorted, cl_max, &l);
+                            if (sym < 0) {  // complete code: a miss can only mean the bits ran out
+                                end_kind = END_TRUNC;
+                                dynamic = false;
+                            } else if (sym < 16) {
+                                in.drop(l);
+                                val = (uint32_t)sym;
+                                sc.lens[i++] = (uint8_t)sym;
+                            } else {
+                                const uint32_t need = sym == 16 ? 2 : sym == 17 ? 3 : 7;
+                                if (in.avail < l + need) {
+                                    end_kind = END_TRUNC;
+                                    dynamic = false;
+                                } else {
+                                    in.drop(l);
+                                    if (sym == 16) {
+                                        if (i == 0) {  // "invalid bit length repeat"
+                                            end_kind = END_ERR;
+                                            dynamic = false;
+                                        }
+                                        rep = 3 + in.peek(2);  // val = the previous length
+                                    } else {
+                                        val = 0;
+                                        rep = (sym == 17 ? 3 : 11) + in.peek(need);
+                                    }
+                                    in.drop(need);
+                                    if (dynamic && i + (int)rep > nsym) {  // "invalid bit length repeat"
+                                        end_kind = END_ERR;
+                                        dynamic = false;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- phase 4: distance lengths to their place, end-of-block check
+                if (dynamic && sc.lens[256] == 0) {  // "invalid code -- missing end-of-block"
+                    end_kind = END_ERR;
+                    dynamic = false;
+                }
+                for (int s = 0; s < 32; ++s) {
+                    if (dynamic) sc.tmp[s] = s < hdist ? sc.lens[hlit + s] : 0;
+                }
+                for (int s = 0; s < 32; ++s) {
+                    if (dynamic) sc.lens[288 + s] = sc.tmp[s];
+                }
+                if (dynamic) tables = true;
+            }
+            if (__any_sync(FULL, tables)) {
+                // ---- phase 5: the two codes of the block
+                int maxl = 0;
+                int st = build_code<32>(tables, sc.lens + 288, hdist, sm.aux_lim, sm.aux_base, sm.next, sc.aux_sorted, &maxl);
+                if (tables && (st == 1 || (st == 2 && maxl > 1))) {  // "invalid distances set"
+                    end_kind = END_ERR;
+                    tables = false;
+                }
+                dist_max = maxl;
+                st = build_code<288>(tables, sc.lens, hlit, sm.lit_lim, sm.lit_base, sm.next, sc.lit_sorted, &maxl);
+                // inftrees.c: over-subscribed never; incomplete only for a single 1-bit code
+                if (tables && (st == 1 || (st == 2 && maxl != 1))) {  // "invalid literal/lengths set"
+                    end_kind = END_ERR;
+                    tables = false;
+                }
+                if (tables) {
+                    L1 = sm.lit_lim[1], L2 = sm.lit_lim[2], L3 = sm.lit_lim[3], L4 = sm.lit_lim[4], L5 = sm.lit_lim[5];
+                    L6 = sm.lit_lim[6], L7 = sm.lit_lim[7], L8 = sm.lit_lim[8], L9 = sm.lit_lim[9], L10 = sm.lit_lim[10];
+                    L11 = sm.lit_lim[11], L12 = sm.lit_lim[12], L13 = sm.lit_lim[13], L14 = sm.lit_lim[14], L15 = sm.lit_lim[15];
+                    state = ST_SYM;
+                }
+            }
+            __syncwarp();
+            // ================= symbols: one step per lane and iteration until every lane has left its block =================
+            uint32_t iter = 0;
+            while (__any_sync(FULL, state >= ST_SYM)) {
+                if (state == ST_SYM) {
+                    // canonical decode: count the limits <= the next 15 bits (binary search over registers)
+                    const uint32_t c = __brev(in.peek32()) >> 17;
+                    const bool s8 = c >= L8;
+                    const bool s4 = c >= (s8 ? L12 : L4);
+                    const bool s2 = c >= (s8 ? (s4 ? L14 : L10) : (s4 ? L6 : L2));
+                    const uint32_t m1 = s8 ? (s4 ? (s2 ? L15 : L13) : (s2 ? L11 : L9)) : (s4 ? (s2 ? L7 : L5) : (s2 ? L3 : L1));
+                    const uint32_t l = 1u + (s8 ? 8u : 0u) + (s4 ? 4u : 0u) + (s2 ? 2u : 0u) + (c >= m1 ? 1u : 0u);
+                    if (l > 15u || l > in.avail) {
+                        // no such code ("invalid literal/length code" when 15 bits were there), or the stream ends inside it
+                        end_kind = (l > 15u && in.avail >= 15u) ? END_ERR : END_TRUNC;
+                        state = ST_DONE;
+                    } else {
+                        const int sym = sc.lit_sorted[sm.lit_base[l] + (int)(c >> (15u - l))];
+                        in.drop(l);
+                        if (sym < 256) {
+                            out.put((uint32_t)sym);
+                        } else if (sym == 256) {
+                            state = ST_BLOCK;
+                        } else if (sym > 285) {  // "invalid literal/length code"
+                            end_kind = END_ERR;
+                            state = ST_DONE;
+                        } else {
+                            // length / distance pair.  A pair cut by the end of the input ends the stream before it (the bytes
+                            // decoded so far are the result), so nothing needs undoing.
+                            const uint32_t li = (uint32_t)sym - 257u;
+                            const uint32_t lx = c_len_extra[li];
+                            int bad = -1;
+                            uint32_t mlen = 0, dist = 0;
+                            if (in.avail < lx) {
+                                bad = END_TRUNC;
+                            } else {
+                                mlen = c_len_base[li] + in.peek(lx);
+                                in.drop(lx);
+                                uint32_t dl = 0;
+                                const int dsym = canon_decode(in, sm.aux_lim, sm.aux_base, sc.aux_sorted, dist_max, &dl);
+                                if (dsym < 0) bad = dsym == -2 ? END_TRUNC : END_ERR;
+                                else if (dsym > 29) bad = END_ERR;  // "invalid distance code"
+                                if (bad < 0) {
+                                    in.drop(dl);
+                                    const uint32_t dx = c_dist_extra[dsym];
+                                    if (in.avail < dx) {
+                                        bad = END_TRUNC;
+                                    } else {
+                                        dist = c_dist_base[dsym] + in.peek(dx);
+                                        in.drop(dx);
+                                        if (dist > out.total) bad = END_ERR;  // "invalid distance too far back"
+                                    }
+                                }
+                            }
+                            if (bad >= 0) {
+                                end_kind = bad;
+                                state = ST_DONE;
+                            } else {
+                                aux = mlen;
+                                m_dist = dist;
+                                state = ST_MATCH;
+                            }
+                        }
+                    }
+                } else if (state == ST_MATCH) {
+                    const uint32_t n = min(aux, 4u);
+                    for (uint32_t k = 0; k < n; ++k) out.copy1(m_dist);
+                    aux -= n;
+                    if (aux == 0) state = ST_SYM;
+                } else if (state == ST_STORED) {
+                    if (in.avail < 8) {
+                        end_kind = END_TRUNC;
+                        state = ST_DONE;
+                    } else {
+                        out.put(in.peek(8));
+                        in.drop(8);
+                        if (--aux == 0) state = ST_BLOCK;
+                    }
+                }
+                if ((++iter & (FLUSH_EVERY - 1)) == 0) out.flush(false);
+            }
+            out.flush(false);
+        }
+        if (mine) {
+            if (end_kind != END_OK) out.flush(true);  // a truncated stream returns what it decoded
+            int32_t st = S5B_OK;
+            if (end_kind == END_ERR) st = S5B_ERR_PRESS;
+            else if (!out.store) st = S5B_ERR_NOSPACE;
+            a.status[r] = st;
+            // on overflow out_len reports the size the stream needs (the caller retries with a larger slot)
+            a.out_len[r] = end_kind == END_ERR ? 0u : out.total;
+        }
+    }
+}
+
+}  // namespace inft
+
+size_t inflate_work_bytes(int num_sms) {
+    return (size_t)num_sms * inft::TI_CTAS_PER_SM * inft::TI_WARPS * 32 * sizeof(inft::TiScratch) + 256;
+}
+
+cudaError_t launch_inflate_threads(const InflateArgs &a, uint32_t max_len, int num_sms, cudaStream_t st) {
+    if (!a.work || a.work_bytes < inflate_work_bytes(num_sms)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    uint64_t want = (a.n_reads + inft::TI_WARPS * 32 - 1) / (inft::TI_WARPS * 32);
+    uint64_t cap = (uint64_t)num_sms * inft::TI_CTAS_PER_SM;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (!grid) grid = 1;
+    inft::inflate_thread_kernel<<<grid, inft::TI_WARPS * 32, 0, st>>>(a, max_len, static_cast<inft::TiScratch *>(a.work));
+    return cudaGetLastError();
+}
+
+}  // namespace s5b

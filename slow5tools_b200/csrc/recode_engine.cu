@@ -32,7 +32,7 @@ using namespace s5b;
 namespace s5b {
 
 void RecodeLane::release() {
-    for (DevBuf *b : {&in, &infl, &sig, &svb, &packed, &z, &img, &meta, &scratch, &zd_scratch, &tab, &work}) b->release();
+    for (DevBuf *b : {&in, &infl, &sig, &svb, &packed, &z, &img, &meta, &scratch, &zd_scratch, &tab, &work, &iwork}) b->release();
     h_tab.release();
     if (d_counter) cudaFree(d_counter);
     if (d_res) cudaFree(d_res);
@@ -232,7 +232,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
         InflateArgs ia{cur, cur_off, cur_len, cur_cap, n, static_cast<uint8_t *>(L.infl.p), d_infl_off, d_infl_len, d_st_dep,
                        L.d_counter};
         if (j.in_rec == S5B_COMPRESS_ZLIB) {
-            CU(launch_inflate(ia, ctx->num_sms, ctx->inf_bps, st));
+            CU(launch_inflate_ws(L.iwork, ia, ctx->num_sms, ctx->inf_bps, st));
         } else {
             CU(L.zd_scratch.reserve(zstd_decode_scratch_bytes(ctx->num_sms, ctx->zd_bps)));
             CU(launch_zstd_decode(ia, ctx->num_sms, ctx->zd_bps, L.zd_scratch.p, st));

@@ -147,7 +147,7 @@ void s5b_ctx_destroy(s5b_ctx_t *ctx) {
     ctx->d_scratch.release();
     ctx->zd_scratch.release();
     for (DevBuf *b : {&ctx->r_in, &ctx->r_infl, &ctx->r_sig, &ctx->r_svb, &ctx->r_packed, &ctx->r_z, &ctx->r_img, &ctx->r_meta,
-                      &ctx->r_scratch, &ctx->r_work, &ctx->def_work})
+                      &ctx->r_scratch, &ctx->r_work, &ctx->def_work, &ctx->inf_work})
         b->release();
     recode_lanes_release(ctx);
     ctx->h_stage_in.release();
@@ -255,7 +255,7 @@ int s5b_zlib_inflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     InflateArgs a{d_in, d_in_off, d_in_len, in_capacity, n_reads, d_out, d_out_off, d_out_len, d_status,
                   ctx->d_counter + 16};
-    CU(launch_inflate(a, ctx->num_sms, ctx->inf_bps, st));
+    CU(launch_inflate_ws(ctx->inf_work, a, ctx->num_sms, ctx->inf_bps, st));
     ctx->launches += 1;
     return S5B_OK;
 }
@@ -807,7 +807,7 @@ static int zlib_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size
     CU(cudaMemcpyAsync(d_in_len, in_len.data(), n * 4, cudaMemcpyHostToDevice, st));
     InflateArgs a{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), n,
                   static_cast<uint8_t *>(s.d_b.p), d_out_off, d_out_len, d_status, s.d_counter};
-    CU(launch_inflate(a, ctx->num_sms, ctx->inf_bps, st));
+    CU(launch_inflate_ws(ctx->inf_work, a, ctx->num_sms, ctx->inf_bps, st));
     ctx->launches += 1;
     CU(cudaMemcpyAsync(out_len.data(), d_out_len, n * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(status.data(), d_status, n * 4, cudaMemcpyDeviceToHost, st));
@@ -840,7 +840,7 @@ static int zlib_depress_ptrs(s5b_ctx_t *ctx, const void *const *ptrs, const size
         CU(cudaMemcpyAsync(d_in_len, r_in_len.data(), m * 4, cudaMemcpyHostToDevice, st));
         InflateArgs b{static_cast<const uint8_t *>(s.d_a.p), d_in_off, d_in_len, round_up(tot, 16), m,
                       static_cast<uint8_t *>(s.d_c.p), d_out_off, d_out_len, d_status, s.d_counter};
-        CU(launch_inflate(b, ctx->num_sms, ctx->inf_bps, st));
+        CU(launch_inflate_ws(ctx->inf_work, b, ctx->num_sms, ctx->inf_bps, st));
         ctx->launches += 1;
         CU(cudaMemcpyAsync(r_out_len.data(), d_out_len, m * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(r_status.data(), d_status, m * 4, cudaMemcpyDeviceToHost, st));
@@ -1160,7 +1160,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
             CU(ctx->r_infl.reserve(total + 16));
             InflateArgs ia{cur, cur_off, cur_len, cur_cap, n, static_cast<uint8_t *>(ctx->r_infl.p), d_infl_off, d_infl_len,
                            d_st2, counter};
-            CU(launch_inflate(ia, ctx->num_sms, ctx->inf_bps, st));
+            CU(launch_inflate_ws(ctx->inf_work, ia, ctx->num_sms, ctx->inf_bps, st));
             ctx->launches += 2;
             CU(cudaMemcpyAsync(h_st.data(), d_st2, n * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -1409,7 +1409,7 @@ int s5b_blow5_read_ids_host(s5b_ctx_t *ctx, int in_rec, const uint8_t *h_in, uin
         InflateArgs ia{static_cast<const uint8_t *>(ctx->r_in.p), d_ioff, d_ilen, round_up(itot, 16), m,
                        static_cast<uint8_t *>(ctx->r_infl.p), d_ooff, d_olen, d_st, counter};
         if (zl) {
-            CU(launch_inflate(ia, ctx->num_sms, ctx->inf_bps, st));
+            CU(launch_inflate_ws(ctx->inf_work, ia, ctx->num_sms, ctx->inf_bps, st));
             ctx->launches += 1;
         } else {
             const int rc = zstd_launch(ctx, ia, st);

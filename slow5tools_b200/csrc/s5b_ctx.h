@@ -74,7 +74,7 @@ enum Stage { ST_H2D = 0, ST_REC_DEPRESS, ST_GLUE, ST_SIG_DEPRESS, ST_SIG_PRESS, 
 struct RecodeLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t front = nullptr;     // everything up to the (size, status) read-back of the chunk in flight
-    DevBuf in, infl, sig, svb, packed, z, img, meta, scratch, zd_scratch, tab, work;
+    DevBuf in, infl, sig, svb, packed, z, img, meta, scratch, zd_scratch, tab, work, iwork;
     PinBuf h_tab;                    // pinned staging of the chunk's record table (up) and image offsets (down)
     unsigned long long *d_counter = nullptr;
     uint64_t *d_res = nullptr;       // [0] image bytes of the chunk, [1] first error (int32 in the low half), [2] its record
@@ -105,6 +105,7 @@ struct s5b_ctx {
     s5b::PinBuf h_stage_in, h_stage_out;  // pointer-array forms
     s5b::DevBuf r_in, r_infl, r_sig, r_svb, r_packed, r_z, r_img, r_meta, r_scratch, r_work;  // the careful (synchronous) transcoder
     s5b::DevBuf def_work;                 // deflate workspace of the *_dev entry points
+    s5b::DevBuf inf_work;                 // inflate scratch rows of everything that is not a pipeline lane
     s5b::RecodeLane lane[s5b::NLANE];     // the pipelined transcoder (lazily created)
     bool lanes_ready = false;
     uint64_t *d_img_base = nullptr;       // running output offset of a device-resident transcoding pass
@@ -142,6 +143,15 @@ struct DeviceGuard {
 };
 
 inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// inflate's thread-per-stream kernel keeps its per-lane symbol lists in a scratch buffer: reserve it in `buf` and launch
+inline cudaError_t launch_inflate_ws(DevBuf &buf, InflateArgs a, int num_sms, int blocks_per_sm, cudaStream_t st) {
+    cudaError_t e = buf.reserve(inflate_work_bytes(num_sms));
+    if (e != cudaSuccess) return e;
+    a.work = buf.p;
+    a.work_bytes = buf.cap;
+    return launch_inflate(a, num_sms, blocks_per_sm, st);
+}
 
 // deflate needs a workspace (sorted symbol lists, code lengths per block): reserve it in `buf` and launch
 inline cudaError_t launch_deflate_ws(DevBuf &buf, DeflateArgs a, int num_sms, int blocks_per_sm, cudaStream_t st) {

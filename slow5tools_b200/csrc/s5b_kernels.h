@@ -41,6 +41,8 @@ struct InflateArgs {
     uint32_t *out_len;        // bytes produced (bytes NEEDED when status is S5B_ERR_NOSPACE)
     int32_t *status;
     unsigned long long *work_counter;
+    void *work = nullptr;     // inflate only: device scratch of >= inflate_work_bytes(num_sms) bytes (thread-per-stream rows)
+    uint64_t work_bytes = 0;
 };
 
 struct DeflateArgs {
@@ -76,6 +78,9 @@ cudaError_t launch_zstd_decode(const InflateArgs &a, int num_sms, int blocks_per
 // grid sizing helpers (queried once per context)
 int inflate_blocks_per_sm();
 cudaError_t launch_inflate(const InflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st);
+// thread-per-stream decoder for streams of at most max_len bytes (longer ones are left untouched)
+size_t inflate_work_bytes(int num_sms);
+cudaError_t launch_inflate_threads(const InflateArgs &a, uint32_t max_len, int num_sms, cudaStream_t st);
 int svbzd_encode_blocks_per_sm();
 int svbzd_decode_blocks_per_sm();
 
