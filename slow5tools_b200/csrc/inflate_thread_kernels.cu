@@ -32,27 +32,53 @@ namespace s5b {
 
 namespace inft {
 
-constexpr int TI_WARPS = 4;
-constexpr int TI_CTAS_PER_SM = 4;   // 16 warps per SM
-constexpr int RING = 64;            // per-lane output ring (bytes): staging for 16-byte stores, source of near matches
-constexpr int FLUSH_EVERY = 8;      // iterations; a lane produces <= 4 bytes per iteration: <= 32 + 15 unflushed < RING
+// Measured on B200 (profiles/r2_inflate_thread_variants.md): 20 warps per SM is the sweet spot -- fewer hide too little of the
+// serial decoders' latency, more shrink the L1 (shared memory grows) and worsen the tail of the 32-record rounds.
+#ifndef S5B_TI_CTAS
+#define S5B_TI_CTAS 10
+#endif
+#ifndef S5B_TI_RING
+#define S5B_TI_RING 64
+#endif
+#ifndef S5B_TI_HOT
+#define S5B_TI_HOT 128
+#endif
+constexpr int TI_WARPS = 2;
+constexpr int TI_CTAS_PER_SM = S5B_TI_CTAS;  // x 2 warps per SM
+constexpr int RING = S5B_TI_RING;            // per-lane output ring (bytes): staging for 16-byte stores, source of near matches
+constexpr int FLUSH_EVERY = RING / 8;        // iterations; a lane produces <= 4 bytes per iteration: RING / 2 + 15 unflushed < RING
 constexpr uint32_t ADLER_MOD = 65521u;
 
-// per-lane shared memory
+constexpr int HOT = S5B_TI_HOT;  // sorted symbols kept in shared memory (canonical order puts the frequent ones first)
+// per-lane shared memory: what the symbol loop touches on every iteration; the code lengths of a block header are parked
+// on the same bytes (as nibbles) while the block's codes are being built
 struct TiSmem {
     uint8_t ring[RING];
-    int16_t lit_base[16];    // sorted index of the first code of a length minus that code: sym = sorted[base[l] + code]
-    uint16_t lit_lim[16];    // end of the codes of each length, left-aligned to 15 bits
-    int16_t aux_base[16];    // the same for the code-length code (while a header is read) / the distance code (after)
-    uint16_t aux_lim[16];
-    uint16_t next[16];       // construction scratch
+    union {
+        uint8_t nib[HOT + 36 > 160 ? HOT + 36 : 160];  // code lengths, two per byte: literal/length at 0..287, distance at 288..319
+        struct {
+            uint8_t sorted8[HOT];  // literal/length symbols sorted by (length, symbol), low 8 bits of the first HOT ...
+            uint32_t hibits[9];    // ... and bit 8 of all 288 (end of block and the length symbols)
+        } s;
+    };
+    union {
+        int16_t lit_base[16];    // sorted index of the first code of a length minus that code: sym = sorted[base[l] + code]
+        uint8_t tmp[32];         // header: code-length code lengths / distance lengths on their way to nib[288..]
+    };
+    uint16_t next[16];           // construction scratch
+    __device__ __forceinline__ uint32_t len_at(int i) const { return (nib[i >> 1] >> ((i & 1) * 4)) & 15u; }
+    __device__ __forceinline__ void set_len(int i, uint32_t v) {
+        const uint32_t b = nib[i >> 1];
+        nib[i >> 1] = (uint8_t)((i & 1) ? ((b & 0x0fu) | (v << 4)) : ((b & 0xf0u) | v));
+    }
 };
-// per-lane global scratch row
+// per-lane global scratch row: code construction output and the rarely used codes
 struct TiScratch {
     uint16_t lit_sorted[288];
     uint16_t aux_sorted[32];
-    uint8_t lens[320];       // literal/length code lengths at 0, distance code lengths at 288
-    uint8_t tmp[320];        // code-length code lengths / distance lengths on their way to lens[288..]
+    uint16_t lit_lim[16];    // end of the codes of each length, left-aligned to 15 bits
+    int16_t aux_base[16];    // base / lim of the code-length code (while a header is read) / the distance code (after)
+    uint16_t aux_lim[16];
 };
 
 __constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31,
@@ -72,22 +98,24 @@ enum : int { ST_DONE = 0, ST_BLOCK = 1, ST_SYM = 2, ST_MATCH = 3, ST_STORED = 4 
 // n bits is an add plus a word shuffle.  `avail` counts the stream bits not yet consumed, so truncation is one compare.
 // Words that hold no stream byte are never loaded.
 struct Bits {
-    const uint32_t *w;    // next word to load
-    const uint32_t *wend; // first word that holds no stream byte
-    uint32_t w0, w1;      // current and next word
+    const uint32_t *base; // aligned word holding the first stream byte
+    uint32_t wi, nw;      // next word to load, number of words that hold stream bytes
+    uint32_t w0, w1, w2;  // current word, next word, and one more that is only on its way (latency hidden)
     uint32_t off;         // consumed bits of w0 (0..31)
     uint32_t avail;       // stream bits left (from the current position)
     __device__ __forceinline__ uint32_t ld() {
-        const uint32_t v = w < wend ? __ldg(w) : 0u;
-        ++w;
+        const uint32_t v = wi < nw ? __ldg(base + wi) : 0u;
+        ++wi;
         return v;
     }
     __device__ __forceinline__ void start(const uint8_t *p, uint32_t len) {
         const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
-        w = reinterpret_cast<const uint32_t *>(p - sk);
-        wend = reinterpret_cast<const uint32_t *>(p - sk + ((sk + len + 3u) & ~3u));
+        base = reinterpret_cast<const uint32_t *>(p - sk);
+        wi = 0;
+        nw = (sk + len + 3u) >> 2;
         w0 = ld();
         w1 = ld();
+        w2 = ld();
         off = sk * 8u;
         avail = len * 8u;
     }
@@ -100,7 +128,8 @@ struct Bits {
         if (off >= 32) {
             off -= 32;
             w0 = w1;
-            w1 = ld();
+            w1 = w2;
+            w2 = ld();
         }
     }
     // to the next byte boundary of the stream (the padding bits are there whenever a whole byte follows)
@@ -125,11 +154,10 @@ struct Out {
     uint32_t bias;       // output byte i lives at ring[(i + bias) & (RING - 1)]: 16-byte segments of the destination are
                          // 16-byte segments of the ring
     bool store;
+    // the ring takes every byte; whether it may be stored is decided when it is flushed (a slot that is too small only
+    // needs the final count)
     __device__ __forceinline__ void put(uint32_t byte) {
-        if (store) {
-            if (total >= cap) store = false;
-            else ring[(total + bias) & (RING - 1)] = (uint8_t)byte;
-        }
+        ring[(total + bias) & (RING - 1)] = (uint8_t)byte;
         ++total;
     }
     __device__ __forceinline__ void flush_bytes(uint32_t end) {
@@ -145,6 +173,7 @@ struct Out {
     }
     // store every complete 16-byte segment (all == false) or everything (all == true)
     __device__ __forceinline__ void flush(bool all) {
+        if (total > cap) store = false;
         if (!store) return;
         for (;;) {
             const uint32_t seg_end = ((flushed + bias) | 15u) + 1u - bias;  // end of the destination segment holding `flushed`
@@ -170,12 +199,8 @@ struct Out {
     // one byte of a match: out[total] = out[total - dist].  Bytes not yet stored are in the ring (it holds the last RING
     // bytes and the unflushed tail is shorter); everything older has been stored by this thread.
     __device__ __forceinline__ void copy1(uint32_t dist) {
-        if (!store) {
-            ++total;
-            return;
-        }
         const uint32_t from = total - dist;
-        put(from >= flushed ? (uint32_t)ring[(from + bias) & (RING - 1)] : (uint32_t)dst[from]);
+        put(from >= flushed || !store ? (uint32_t)ring[(from + bias) & (RING - 1)] : (uint32_t)dst[from]);
     }
 };
 
@@ -184,8 +209,8 @@ struct Out {
 // index of the first code of length l minus that code, sorted[] = symbols by (length, symbol).  All loops have fixed trip
 // counts (NMAX) and `active` lanes are merely predicated, so the warp stays converged through the call.
 // Returns 0 ok, 1 over-subscribed, 2 incomplete (zlib's inflate_table rules decide what that means); *max_len too.
-template <int NMAX>
-__device__ __forceinline__ int build_code(bool active, const uint8_t *lens, int n, uint16_t *lim, int16_t *base, uint16_t *next,
+template <int NMAX, typename LenAt>
+__device__ __forceinline__ int build_code(bool active, LenAt lens, int n, uint16_t *lim, int16_t *base, uint16_t *next,
                                           uint16_t *sorted, int *max_len) {
     if (active) {
 #pragma unroll
@@ -193,7 +218,7 @@ __device__ __forceinline__ int build_code(bool active, const uint8_t *lens, int 
     }
     for (int s = 0; s < NMAX; ++s) {
         if (active && s < n) {
-            const int l = lens[s];
+            const int l = (int)lens(s);
             if (l) ++next[l];
         }
     }
@@ -217,7 +242,7 @@ __device__ __forceinline__ int build_code(bool active, const uint8_t *lens, int 
     }
     for (int s = 0; s < NMAX; ++s) {
         if (active && status != 1 && s < n) {
-            const int l = lens[s];
+            const int l = (int)lens(s);
             if (l) sorted[next[l]++] = (uint16_t)s;
         }
     }
@@ -266,8 +291,8 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
         // the literal/length code limits of the current block, one register per length
         uint32_t L1 = 0, L2 = 0, L3 = 0, L4 = 0, L5 = 0, L6 = 0, L7 = 0, L8 = 0, L9 = 0, L10 = 0, L11 = 0, L12 = 0, L13 = 0,
                  L14 = 0, L15 = 0;
-        in.w = in.wend = reinterpret_cast<const uint32_t *>(a.in);
-        in.w0 = in.w1 = in.off = in.avail = 0;
+        in.base = reinterpret_cast<const uint32_t *>(a.in);
+        in.wi = in.nw = in.w0 = in.w1 = in.w2 = in.off = in.avail = 0;
         out.ring = sm.ring;
         out.dst = a.out;
         out.cap = out.total = out.flushed = out.bias = 0;
@@ -352,7 +377,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
             if (__any_sync(FULL, tables)) {
                 // fixed code (btype 1): lengths 8/9/7/8, all 32 five-bit distance codes (30, 31: "invalid distance code")
                 for (int s = 0; s < 320; ++s)
-                    if (tables) sc.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5;
+                    if (tables) sm.set_len(s, s < 144 ? 8u : s < 256 ? 9u : s < 280 ? 7u : s < 288 ? 8u : 5u);
             }
             if (__any_sync(FULL, dynamic)) {
                 // ---- phase 2: the code-length code (3 bits per length, fixed order), its canonical arrays
@@ -368,34 +393,50 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                                 in.drop(3);
                             }
                         }
-                        sc.tmp[c_cl_order[i]] = (uint8_t)v;
+                        sm.tmp[c_cl_order[i]] = (uint8_t)v;
                     }
                 }
                 int cl_max = 0;
                 // "invalid code lengths set": the code-length code must be complete (inftrees.c, type CODES)
-                if (build_code<19>(dynamic, sc.tmp, 19, sm.aux_lim, sm.aux_base, sm.next, sc.aux_sorted, &cl_max) != 0 && dynamic) {
+                if (build_code<19>(dynamic, [&](int q) { return (uint32_t)sm.tmp[q]; }, 19, sc.aux_lim, sc.aux_base, sm.next,
+                                   sc.aux_sorted, &cl_max) != 0 && dynamic) {
                     end_kind = END_ERR;
                     dynamic = false;
                 }
-                // ---- phase 3: the hlit + hdist code lengths, run-length coded; one length per lane and iteration
+                // ---- phase 3: the hlit + hdist code lengths, run-length coded; one length per lane and iteration.  The limits
+                // of the (at most 7-bit) code-length code sit in registers for the duration.
+                uint32_t C1 = 0, C2 = 0, C3 = 0, C4 = 0, C5 = 0, C6 = 0, C7 = 0;
+                int cb1 = 0, cb2 = 0, cb3 = 0, cb4 = 0, cb5 = 0, cb6 = 0, cb7 = 0;
+                if (dynamic) {
+                    C1 = sc.aux_lim[1], C2 = sc.aux_lim[2], C3 = sc.aux_lim[3], C4 = sc.aux_lim[4], C5 = sc.aux_lim[5];
+                    C6 = sc.aux_lim[6], C7 = sc.aux_lim[7];
+                    cb1 = sc.aux_base[1], cb2 = sc.aux_base[2], cb3 = sc.aux_base[3], cb4 = sc.aux_base[4], cb5 = sc.aux_base[5];
+                    cb6 = sc.aux_base[6], cb7 = sc.aux_base[7];
+                }
                 const int nsym = hlit + hdist;
                 int i = 0;
                 uint32_t rep = 0, val = 0;
                 while (__any_sync(FULL, dynamic && i < nsym)) {
                     if (dynamic && i < nsym) {
                         if (rep) {
-                            sc.lens[i++] = (uint8_t)val;
+                            sm.set_len(i++, val);
                             --rep;
                         } else {
-                            uint32_t l = 0;
-                            const int sym = canon_decode(in, sm.aux_lim, sm.aux_base, sc.aux_sorted, cl_max, &l);
+                            const uint32_t c15 = __brev(in.peek32()) >> 17;
+                            const uint32_t l = 1u + (c15 >= C1) + (c15 >= C2) + (c15 >= C3) + (c15 >= C4) + (c15 >= C5) + (c15 >= C6) +
+                                               (c15 >= C7);
+                            int sym = -1;
+                            if (l <= 7u && l <= in.avail) {
+                                const int cb = l == 1 ? cb1 : l == 2 ? cb2 : l == 3 ? cb3 : l == 4 ? cb4 : l == 5 ? cb5 : l == 6 ? cb6 : cb7;
+                                sym = sc.aux_sorted[cb + (int)(c15 >> (15u - l))];
+                            }
                             if (sym < 0) {  // complete code: a miss can only mean the bits ran out
                                 end_kind = END_TRUNC;
                                 dynamic = false;
                             } else if (sym < 16) {
                                 in.drop(l);
                                 val = (uint32_t)sym;
-                                sc.lens[i++] = (uint8_t)sym;
+                                sm.set_len(i++, (uint32_t)sym);
                             } else {
                                 const uint32_t need = sym == 16 ? 2 : sym == 17 ? 3 : 7;
                                 if (in.avail < l + need) {
@@ -424,37 +465,52 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                     }
                 }
                 // ---- phase 4: distance lengths to their place, end-of-block check
-                if (dynamic && sc.lens[256] == 0) {  // "invalid code -- missing end-of-block"
+                if (dynamic && sm.len_at(256) == 0) {  // "invalid code -- missing end-of-block"
                     end_kind = END_ERR;
                     dynamic = false;
                 }
                 for (int s = 0; s < 32; ++s) {
-                    if (dynamic) sc.tmp[s] = s < hdist ? sc.lens[hlit + s] : 0;
+                    if (dynamic) sm.tmp[s] = s < hdist ? (uint8_t)sm.len_at(hlit + s) : (uint8_t)0;
                 }
                 for (int s = 0; s < 32; ++s) {
-                    if (dynamic) sc.lens[288 + s] = sc.tmp[s];
+                    if (dynamic) sm.set_len(288 + s, sm.tmp[s]);
                 }
                 if (dynamic) tables = true;
             }
             if (__any_sync(FULL, tables)) {
                 // ---- phase 5: the two codes of the block
                 int maxl = 0;
-                int st = build_code<32>(tables, sc.lens + 288, hdist, sm.aux_lim, sm.aux_base, sm.next, sc.aux_sorted, &maxl);
+                int st = build_code<32>(tables, [&](int q) { return sm.len_at(288 + q); }, hdist, sc.aux_lim, sc.aux_base, sm.next,
+                                        sc.aux_sorted, &maxl);
                 if (tables && (st == 1 || (st == 2 && maxl > 1))) {  // "invalid distances set"
                     end_kind = END_ERR;
                     tables = false;
                 }
                 dist_max = maxl;
-                st = build_code<288>(tables, sc.lens, hlit, sm.lit_lim, sm.lit_base, sm.next, sc.lit_sorted, &maxl);
+                st = build_code<288>(tables, [&](int q) { return sm.len_at(q); }, hlit, sc.lit_lim, sm.lit_base, sm.next,
+                                     sc.lit_sorted, &maxl);
                 // inftrees.c: over-subscribed never; incomplete only for a single 1-bit code
                 if (tables && (st == 1 || (st == 2 && maxl != 1))) {  // "invalid literal/lengths set"
                     end_kind = END_ERR;
                     tables = false;
                 }
+                // the sorted symbols move next to the decoder: low bytes and a bit mask for bit 8
+                for (int q = 0; q < 9; ++q) {
+                    uint32_t hi = 0;
+                    for (int k = 0; k < 32; ++k) {
+                        const int i = q * 32 + k;
+                        if (tables) {
+                            const uint32_t v = sc.lit_sorted[i];
+                            if (i < HOT) sm.s.sorted8[i] = (uint8_t)v;   // (the code lengths parked here are done with)
+                            hi |= ((v >> 8) & 1u) << k;
+                        }
+                    }
+                    if (tables) sm.s.hibits[q] = hi;
+                }
                 if (tables) {
-                    L1 = sm.lit_lim[1], L2 = sm.lit_lim[2], L3 = sm.lit_lim[3], L4 = sm.lit_lim[4], L5 = sm.lit_lim[5];
-                    L6 = sm.lit_lim[6], L7 = sm.lit_lim[7], L8 = sm.lit_lim[8], L9 = sm.lit_lim[9], L10 = sm.lit_lim[10];
-                    L11 = sm.lit_lim[11], L12 = sm.lit_lim[12], L13 = sm.lit_lim[13], L14 = sm.lit_lim[14], L15 = sm.lit_lim[15];
+                    L1 = sc.lit_lim[1], L2 = sc.lit_lim[2], L3 = sc.lit_lim[3], L4 = sc.lit_lim[4], L5 = sc.lit_lim[5];
+                    L6 = sc.lit_lim[6], L7 = sc.lit_lim[7], L8 = sc.lit_lim[8], L9 = sc.lit_lim[9], L10 = sc.lit_lim[10];
+                    L11 = sc.lit_lim[11], L12 = sc.lit_lim[12], L13 = sc.lit_lim[13], L14 = sc.lit_lim[14], L15 = sc.lit_lim[15];
                     state = ST_SYM;
                 }
             }
@@ -475,7 +531,9 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                         end_kind = (l > 15u && in.avail >= 15u) ? END_ERR : END_TRUNC;
                         state = ST_DONE;
                     } else {
-                        const int sym = sc.lit_sorted[sm.lit_base[l] + (int)(c >> (15u - l))];
+                        const uint32_t si = (uint32_t)(sm.lit_base[l] + (int)(c >> (15u - l)));
+                        const uint32_t lo8 = si < (uint32_t)HOT ? (uint32_t)sm.s.sorted8[si] : (uint32_t)(sc.lit_sorted[si] & 0xffu);
+                        const int sym = (int)(lo8 | (((sm.s.hibits[si >> 5] >> (si & 31u)) & 1u) << 8));
                         in.drop(l);
                         if (sym < 256) {
                             out.put((uint32_t)sym);
@@ -497,7 +555,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                                 mlen = c_len_base[li] + in.peek(lx);
                                 in.drop(lx);
                                 uint32_t dl = 0;
-                                const int dsym = canon_decode(in, sm.aux_lim, sm.aux_base, sc.aux_sorted, dist_max, &dl);
+                                const int dsym = canon_decode(in, sc.aux_lim, sc.aux_base, sc.aux_sorted, dist_max, &dl);
                                 if (dsym < 0) bad = dsym == -2 ? END_TRUNC : END_ERR;
                                 else if (dsym > 29) bad = END_ERR;  // "invalid distance code"
                                 if (bad < 0) {
