@@ -503,7 +503,8 @@ def run_ours(args):
     # ---- N > 1: one batch held by rank 0, split across the GPUs -- per-GPU PCIe copies vs NCCL scatter / gather
     split = None
     if world > 1 and not args.no_split:
-        split = split_compare(torch, dist, cdc, args, rank, world, h_raw, Re, rl, barrier, max_over_ranks, shard_bounds)
+        del h_back, h_img
+        split = split_compare(torch, dist, cdc, synth, args, rank, world, min(Re, 262144), rl, barrier, max_over_ranks, shard_bounds)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -571,14 +572,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def split_compare(torch, dist, cdc, args, rank, world, h_raw, Re, rl, barrier, max_over_ranks, shard_bounds):
+def split_compare(torch, dist, cdc, synth, args, rank, world, T, rl, barrier, max_over_ranks, shard_bounds):
     """Strong-scaling view of SURVEY 8e: ONE batch of T records held by rank 0 (pinned host memory) is encoded by all
     GPUs.  (a) pcie: every rank copies its own byte-balanced shard over its own PCIe link (the shards are in host memory
     every rank can reach; here each rank uses the same bytes from its own pinned slab) and runs the host-form transcoder;
     (b) nccl: rank 0 moves the whole batch over ITS link, scatters variable-size shards with NCCL send/recv (sizes first,
     by all_gather), every rank transcodes device-resident, the images are gathered to rank 0 the same way and copied
     down.  Times are device/wall max over ranks; both produce the identical image."""
-    T = min(Re, 262144)
+    # the ONE batch: every rank holds the same bytes in its own pinned slab (standing in for host memory all ranks of the
+    # node can reach); rank 0's copy is "the" batch of the NCCL path
+    sig = synth.nanopore_signal(T * args.samples, seed=4242, device="cuda")
+    d_batch = synth.blow5_records(sig, T, args.samples, seed=4242).view(-1)
+    del sig
+    h_raw = pinned(torch, T * rl)
+    h_raw.copy_(d_batch)
+    del d_batch
+    torch.cuda.synchronize()
     tab_off = np.arange(T, dtype=np.uint64) * np.uint64(rl)
     tab_len = np.full(T, rl, np.uint32)
     bounds = shard_bounds(tab_len, world)
