@@ -1,0 +1,23 @@
+/* <slow5/slow5.h> for code written against slow5lib's low-level API (slow5lib/include/slow5/slow5.h): maps the slow5_* names
+ * this library provides onto its s5b_* entry points, so that e.g. slow5lib/examples/adv/sequential_read_pthreads.c builds
+ * unchanged with  -I include/compat -L slow5tools_b200 -lslow5b200 . */
+#ifndef S5B_COMPAT_SLOW5_H
+#define S5B_COMPAT_SLOW5_H
+#ifndef S5B_SLOW5_COMPAT
+#define S5B_SLOW5_COMPAT
+#endif
+#include "../../slow5b200_file.h"
+/* error codes, slow5lib/include/slow5/slow5_error.h + slow5_defs.h:137-154 */
+#define SLOW5_ERR_EOF      S5B_ERR_EOF
+#define SLOW5_ERR_ARG      S5B_ERR_ARG
+#define SLOW5_ERR_IO       S5B_ERR_IO
+#define SLOW5_ERR_RECPARSE S5B_ERR_RECPARSE
+#define SLOW5_ERR_MEM      S5B_ERR_MEM
+#define SLOW5_ERR_PRESS    S5B_ERR_PRESS
+/* enum slow5_press_method, slow5_press.h:61-67 */
+#define SLOW5_COMPRESS_NONE   S5B_COMPRESS_NONE
+#define SLOW5_COMPRESS_ZLIB   S5B_COMPRESS_ZLIB
+#define SLOW5_COMPRESS_SVB_ZD S5B_COMPRESS_SVB_ZD
+#define SLOW5_COMPRESS_ZSTD   S5B_COMPRESS_ZSTD
+#define SLOW5_COMPRESS_EX_ZD  S5B_COMPRESS_EX_ZD
+#endif

@@ -26,7 +26,9 @@
 #define SLOW5B200_FILE_H
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "slow5b200.h"
+#include "slow5b200_press.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -49,7 +51,30 @@ typedef struct s5b_rec {
     uint64_t aux_len;
 } s5b_rec_t;
 
-typedef struct s5b_file s5b_file_t;
+/* The leading fields of the file handle are public and laid out like the reference's slow5_file_t
+ * (slow5lib/include/slow5/slow5.h:291-318): callers read fp->compress->record_press->method, fp->format, fp->meta.pathname
+ * ... directly (src/view.c:43-49, slow5_mt.c:163).  `header` starts like slow5_hdr_t (version, num_read_groups); the
+ * attribute and auxiliary-field tables behind it are private (the reference keeps khash maps there) and are reached through
+ * this library's calls only. */
+typedef struct s5b_hdr {
+    struct { uint8_t major, minor, patch; } version;     /* struct slow5_version, slow5.h:168-172 */
+    uint32_t num_read_groups;
+} s5b_hdr_t;
+typedef struct s5b_file_meta {                           /* slow5_file_meta_t, slow5.h:291-298 */
+    const char *pathname;
+    int fd;
+    uint64_t start_rec_offset;
+    char *fread_buffer;                                  /* always NULL here */
+    const char *mode;
+} s5b_file_meta_t;
+typedef struct s5b_file {
+    FILE *fp;
+    int format;                  /* enum slow5_fmt: 0 unknown, 1 ASCII (SLOW5), 2 binary (BLOW5) */
+    s5b_press_t *compress;       /* methods of the file (read) / of the records to be written; NULL for ASCII */
+    s5b_hdr_t *header;
+    void *index;                 /* NULL: random access goes through `slow5tools-b200 get` */
+    s5b_file_meta_t meta;
+} s5b_file_t;                    /* the library's private state follows these fields */
 
 extern int s5b_errno_value(void);   /* the twin of the thread-local slow5_errno */
 
@@ -102,6 +127,19 @@ void s5b_free_batch(s5b_batch_t *batch);
 void s5b_free_mt(s5b_mt_t *mt);
 
 #ifdef S5B_SLOW5_COMPAT
+#define slow5_press_method_t s5b_press_method_t
+#define slow5_press_t s5b_press_t
+#define __slow5_press __s5b_press
+#define slow5_press s5b_press
+#define slow5_press_init s5b_press_init
+#define __slow5_press_init __s5b_press_init
+#define slow5_press_free s5b_press_free
+#define __slow5_press_free __s5b_press_free
+#define slow5_ptr_compress s5b_ptr_compress
+#define slow5_ptr_depress s5b_ptr_depress
+#define slow5_ptr_compress_solo s5b_ptr_compress_solo
+#define slow5_ptr_depress_solo s5b_ptr_depress_solo
+#define slow5_compress_footer_next s5b_compress_footer_next
 #define slow5_batch_t s5b_batch_t
 #define slow5_mt_t s5b_mt_t
 #define slow5_init_mt s5b_init_mt

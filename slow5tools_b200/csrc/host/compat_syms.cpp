@@ -1,0 +1,47 @@
+// compat_syms.cpp -> libslow5b200_compat.so: the slow5lib symbol names themselves (slow5_open, slow5_get_next_bytes,
+// slow5_decode, slow5_encode, slow5_ptr_compress_solo, slow5_get_next_batch ...), each a direct forward to its s5b_ twin in
+// libslow5b200.so.  For programs that were compiled against slow5lib's own headers and only need relinking
+// (slow5lib/include/slow5/slow5.h:345-662, slow5_press.h:97-125, slow5_mt.h:49-65); code that can be recompiled uses the
+// macro mapping of include/compat/slow5/slow5.h instead.  Kept out of libslow5b200.so so that a process may hold this
+// library and the reference's libslow5 side by side (the parity tests do).
+#include "../../../include/slow5b200_file.h"
+
+extern "C" {
+
+// slow5_errno is `(*slow5_errno_location())` in the reference (slow5_error.h:120-126)
+int *slow5_errno_location(void) {
+    static thread_local int value;
+    value = s5b_errno_value();
+    return &value;
+}
+
+s5b_file_t *slow5_open(const char *pathname, const char *mode) { return s5b_open(pathname, mode); }
+int slow5_close(s5b_file_t *fp) { return s5b_close(fp); }
+void *slow5_get_next_mem(size_t *n, const s5b_file_t *fp) { return s5b_get_next_mem(n, const_cast<s5b_file_t *>(fp)); }
+int slow5_get_next_bytes(char **mem, size_t *bytes, s5b_file_t *fp) { return s5b_get_next_bytes(mem, bytes, fp); }
+int slow5_decode(char **mem, size_t *bytes, s5b_rec_t **read, s5b_file_t *fp) { return s5b_decode(mem, bytes, read, fp); }
+int slow5_encode(char **mem, size_t *bytes, s5b_rec_t *read, s5b_file_t *fp) { return s5b_encode(mem, bytes, read, fp); }
+int slow5_write_bytes(char *mem, size_t bytes, s5b_file_t *fp) { return s5b_write_bytes(mem, bytes, fp); }
+void slow5_rec_free(s5b_rec_t *read) { s5b_rec_free(read); }
+int slow5_set_press(s5b_file_t *fp, int rec_press, int sig_press) { return s5b_set_press(fp, rec_press, sig_press); }
+int slow5_hdr_write(s5b_file_t *fp) { return s5b_hdr_write(fp); }
+
+s5b_mt_t *slow5_init_mt(int num_thread, s5b_file_t *fp) { return s5b_init_mt(num_thread, fp); }
+s5b_batch_t *slow5_init_batch(int cap) { return s5b_init_batch(cap); }
+int slow5_get_next_batch(s5b_mt_t *mt, s5b_batch_t *b, int n) { return s5b_get_next_batch(mt, b, n); }
+int slow5_encode_batch(s5b_mt_t *mt, s5b_batch_t *b, int n) { return s5b_encode_batch_mt(mt, b, n); }
+int slow5_write_batch(s5b_mt_t *mt, s5b_batch_t *b, int n) { return s5b_write_batch(mt, b, n); }
+void slow5_free_batch(s5b_batch_t *b) { s5b_free_batch(b); }
+void slow5_free_mt(s5b_mt_t *mt) { s5b_free_mt(mt); }
+
+s5b_press_t *slow5_press_init(s5b_press_method_t m) { return s5b_press_init(m); }
+struct __s5b_press *__slow5_press_init(int method) { return __s5b_press_init(method); }
+void slow5_press_free(s5b_press_t *c) { s5b_press_free(c); }
+void __slow5_press_free(struct __s5b_press *c) { __s5b_press_free(c); }
+void *slow5_ptr_compress(struct __s5b_press *c, const void *p, size_t count, size_t *n) { return s5b_ptr_compress(c, p, count, n); }
+void *slow5_ptr_depress(struct __s5b_press *c, const void *p, size_t count, size_t *n) { return s5b_ptr_depress(c, p, count, n); }
+void *slow5_ptr_compress_solo(int method, const void *p, size_t count, size_t *n) { return s5b_ptr_compress_solo(method, p, count, n); }
+void *slow5_ptr_depress_solo(int method, const void *p, size_t count, size_t *n) { return s5b_ptr_depress_solo(method, p, count, n); }
+void slow5_compress_footer_next(struct __s5b_press *c) { s5b_compress_footer_next(c); }
+
+}  // extern "C"

@@ -10,7 +10,11 @@
 
 using namespace s5b;
 
-struct s5b_file {
+// the public struct s5b_file (slow5b200_file.h) is the first member: a s5b_file_t* points at it and at this object
+struct S5bFile {
+    s5b_file pub;
+    s5b_hdr hdr_pub;
+    std::string path, mode;
     Reader rd;          // "r"
     FILE *out = nullptr;  // "w"
     bool writing = false;
@@ -19,6 +23,34 @@ struct s5b_file {
     int rec_press = PRESS_ZLIB, sig_press = PRESS_SVB_ZD;
     s5b_ctx_t *gpu = nullptr;
 };
+static inline S5bFile *impl(s5b_file_t *f) { return reinterpret_cast<S5bFile *>(f); }
+static inline const S5bFile *impl(const s5b_file_t *f) { return reinterpret_cast<const S5bFile *>(f); }
+
+// keeps the public fields in step with the private state
+static void publish(S5bFile *f) {
+    f->pub.fp = f->writing ? f->out : f->rd.fp;
+    const Fmt fmt = f->writing ? FMT_BINARY : f->rd.fmt;
+    f->pub.format = fmt == FMT_BINARY ? 2 : fmt == FMT_ASCII ? 1 : 0;
+    const Header &h = f->writing ? f->hdr : f->rd.hdr;
+    f->hdr_pub.version.major = h.version[0];
+    f->hdr_pub.version.minor = h.version[1];
+    f->hdr_pub.version.patch = h.version[2];
+    f->hdr_pub.num_read_groups = h.num_read_groups;
+    f->pub.header = &f->hdr_pub;
+    f->pub.index = nullptr;
+    f->pub.meta.pathname = f->path.c_str();
+    f->pub.meta.mode = f->mode.c_str();
+    f->pub.meta.fd = f->pub.fp ? fileno(f->pub.fp) : -1;
+    f->pub.meta.fread_buffer = nullptr;
+    if (f->pub.compress) {
+        s5b_press_free(f->pub.compress);
+        f->pub.compress = nullptr;
+    }
+    if (fmt == FMT_BINARY) {  // the reference has no press object for ASCII files (slow5.c:420-431)
+        const s5b_press_method_t m = {f->rec_press, f->sig_press};
+        f->pub.compress = s5b_press_init(m);
+    }
+}
 
 namespace {
 thread_local int tl_errno = 0;
@@ -26,7 +58,7 @@ int fail(int code) {
     tl_errno = code;
     return code;
 }
-int ensure_gpu(s5b_file *f) {
+int ensure_gpu(S5bFile *f) {
     if (f->gpu) return S5B_OK;
     return s5b_ctx_create(-1, &f->gpu);
 }
@@ -41,7 +73,10 @@ s5b_file_t *s5b_open(const char *pathname, const char *mode) {
         fail(S5B_ERR_ARG);
         return nullptr;
     }
-    s5b_file *f = new s5b_file();
+    S5bFile *f = new S5bFile();
+    memset(&f->pub, 0, sizeof f->pub);
+    f->path = pathname;
+    f->mode = mode;
     if (mode[0] == 'r') {
         if (!reader_open(f->rd, pathname, FMT_UNKNOWN)) {
             fail(S5B_ERR_IO);
@@ -51,13 +86,16 @@ s5b_file_t *s5b_open(const char *pathname, const char *mode) {
         }
         f->rec_press = f->rd.hdr.record_method;
         f->sig_press = f->rd.hdr.signal_method;
-        return f;
+        publish(f);
+        f->pub.meta.start_rec_offset = f->rd.fp ? (uint64_t)ftello(f->rd.fp) : 0;
+        return &f->pub;
     }
     if (mode[0] == 'w' && fmt_from_path(pathname) == FMT_BINARY) {
         f->out = fopen(pathname, "wb");
         if (f->out) {
             f->writing = true;
-            return f;
+            publish(f);
+            return &f->pub;
         }
     }
     fail(S5B_ERR_IO);
@@ -65,8 +103,9 @@ s5b_file_t *s5b_open(const char *pathname, const char *mode) {
     return nullptr;
 }
 
-int s5b_close(s5b_file_t *f) {
-    if (!f) return fail(S5B_ERR_ARG);
+int s5b_close(s5b_file_t *fpub) {
+    if (!fpub) return fail(S5B_ERR_ARG);
+    S5bFile *f = impl(fpub);
     int rc = 0;
     if (f->writing) {
         if (fwrite("5WOLB", 1, 5, f->out) != 5) rc = S5B_ERR_IO;  // slow5.c:522-531
@@ -75,36 +114,42 @@ int s5b_close(s5b_file_t *f) {
         reader_close(f->rd);
     }
     if (f->gpu) s5b_ctx_destroy(f->gpu);
+    if (f->pub.compress) s5b_press_free(f->pub.compress);
     delete f;
     return rc ? fail(rc) : 0;
 }
 
-int s5b_hdr_copy(s5b_file_t *dst, const s5b_file_t *src) {
-    if (!dst || !src || !dst->writing) return fail(S5B_ERR_ARG);
-    dst->hdr = src->rd.hdr;
+int s5b_hdr_copy(s5b_file_t *dstp, const s5b_file_t *srcp) {
+    if (!dstp || !srcp || !impl(dstp)->writing) return fail(S5B_ERR_ARG);
+    impl(dstp)->hdr = impl(srcp)->rd.hdr;
+    publish(impl(dstp));
     return 0;
 }
-int s5b_set_press(s5b_file_t *f, int rec_press, int sig_press) {
+int s5b_set_press(s5b_file_t *fpub, int rec_press, int sig_press) {
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !f->writing || f->hdr_written) return fail(S5B_ERR_ARG);
     if ((rec_press != PRESS_NONE && rec_press != PRESS_ZLIB && rec_press != PRESS_ZSTD) ||
         (sig_press != PRESS_NONE && sig_press != PRESS_SVB_ZD && sig_press != PRESS_EX_ZD))
         return fail(S5B_ERR_ARG);
     f->rec_press = rec_press;
     f->sig_press = sig_press;
+    publish(f);
     return 0;
 }
-int s5b_hdr_write(s5b_file_t *f) {
+int s5b_hdr_write(s5b_file_t *fpub) {
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !f->writing) return fail(S5B_ERR_ARG);
     const std::string h = header_to_mem(f->hdr, FMT_BINARY, f->rec_press, f->sig_press);
     if (fwrite(h.data(), 1, h.size(), f->out) != h.size()) return fail(S5B_ERR_IO);
     f->hdr_written = true;
     return (int)h.size();
 }
-int s5b_file_record_press(const s5b_file_t *f) { return f ? f->rec_press : S5B_ERR_ARG; }
-int s5b_file_signal_press(const s5b_file_t *f) { return f ? f->sig_press : S5B_ERR_ARG; }
+int s5b_file_record_press(const s5b_file_t *f) { return f ? impl(f)->rec_press : S5B_ERR_ARG; }
+int s5b_file_signal_press(const s5b_file_t *f) { return f ? impl(f)->sig_press : S5B_ERR_ARG; }
 
-void *s5b_get_next_mem(size_t *n, s5b_file_t *f) {
-    if (!f || !n || f->writing || f->rd.fmt != FMT_BINARY) {
+void *s5b_get_next_mem(size_t *n, s5b_file_t *fpub) {
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
+    if (!f || !n || f->writing) {
         fail(S5B_ERR_ARG);
         return nullptr;
     }
@@ -115,12 +160,13 @@ void *s5b_get_next_mem(size_t *n, s5b_file_t *f) {
         *n = 0;
         return nullptr;
     }
-    void *out = malloc(mem.size() ? mem.size() : 1);
+    void *out = malloc(mem.size() + 1);  // (+1: an ASCII line is handed out NUL-terminated, slow5.c:3216-3231)
     if (!out) {
         fail(S5B_ERR_MEM);
         return nullptr;
     }
     memcpy(out, mem.data(), mem.size());
+    static_cast<char *>(out)[mem.size()] = '\0';
     *n = mem.size();
     return out;
 }
@@ -139,10 +185,50 @@ void s5b_rec_free(s5b_rec_t *r) {
     free(r);
 }
 
-int s5b_decode_batch(s5b_file_t *f, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads) {
+// fills (or allocates) a caller-visible record from a parsed one; `sig` is handed over
+static void fill_rec(s5b_rec_t **slot, const Record &rec, void *sig, size_t sig_bytes) {
+    s5b_rec_t *r = *slot;
+    if (!r) {
+        r = static_cast<s5b_rec_t *>(calloc(1, sizeof *r));
+        *slot = r;
+    } else {  // reuse the struct, rebuild its members (slow5.c:2626-2639)
+        free(r->read_id);
+        free(r->raw_signal);
+        free(r->aux);
+    }
+    r->read_id_len = (uint16_t)rec.read_id.size();
+    r->read_id = strndup(rec.read_id.data(), rec.read_id.size());
+    r->read_group = rec.read_group;
+    r->digitisation = rec.digitisation;
+    r->offset = rec.offset;
+    r->range = rec.range;
+    r->sampling_rate = rec.sampling_rate;
+    r->len_raw_signal = sig_bytes / 2;
+    r->raw_signal = static_cast<int16_t *>(sig);
+    r->aux_len = rec.aux_nbytes;
+    r->aux = static_cast<uint8_t *>(malloc(r->aux_len ? r->aux_len : 1));
+    if (r->aux_len) memcpy(r->aux, rec.aux_bytes, r->aux_len);
+}
+
+int s5b_decode_batch(s5b_file_t *fpub, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads) {
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !mems || !bytes || !reads) return fail(S5B_ERR_ARG);
     if (n == 0) return 0;
     const Header &h = f->rd.hdr;
+    if (f->rd.fmt == FMT_ASCII) {  // SLOW5 text lines: nothing is compressed, the parse is host work (slow5.c:2641-2810)
+        for (size_t i = 0; i < n; ++i) {
+            Record rec;
+            std::vector<uint8_t> aux_store;
+            std::string err;
+            if (!record_parse_ascii(mems[i], bytes[i], h, rec, aux_store, err)) return fail(S5B_ERR_RECPARSE);
+            const size_t nb = rec.raw_signal.size() * 2;
+            void *sig = malloc(nb ? nb : 1);
+            if (!sig) return fail(S5B_ERR_MEM);
+            memcpy(sig, rec.raw_signal.data(), nb);
+            fill_rec(&reads[i], rec, sig, nb);
+        }
+        return 0;
+    }
     if (h.record_method != PRESS_NONE || h.signal_method != PRESS_NONE) {
         const int rc = ensure_gpu(f);
         if (rc != S5B_OK) return fail(rc);
@@ -196,29 +282,7 @@ int s5b_decode_batch(s5b_file_t *f, char **mems, size_t *bytes, size_t n, s5b_re
     } else {
         return fail(S5B_ERR_ARG);
     }
-    for (size_t i = 0; i < n; ++i) {
-        s5b_rec_t *r = reads[i];
-        if (!r) {
-            r = static_cast<s5b_rec_t *>(calloc(1, sizeof *r));
-            reads[i] = r;
-        } else {  // reuse the struct, rebuild its members (slow5.c:2626-2639)
-            free(r->read_id);
-            free(r->raw_signal);
-            free(r->aux);
-        }
-        r->read_id_len = (uint16_t)rec[i].read_id.size();
-        r->read_id = strndup(rec[i].read_id.data(), rec[i].read_id.size());
-        r->read_group = rec[i].read_group;
-        r->digitisation = rec[i].digitisation;
-        r->offset = rec[i].offset;
-        r->range = rec[i].range;
-        r->sampling_rate = rec[i].sampling_rate;
-        r->len_raw_signal = sig_n[i] / 2;
-        r->raw_signal = static_cast<int16_t *>(sig[i]);
-        r->aux_len = rec[i].aux_nbytes;
-        r->aux = static_cast<uint8_t *>(malloc(r->aux_len ? r->aux_len : 1));
-        if (r->aux_len) memcpy(r->aux, rec[i].aux_bytes, r->aux_len);
-    }
+    for (size_t i = 0; i < n; ++i) fill_rec(&reads[i], rec[i], sig[i], sig_n[i]);
     return 0;
 }
 
@@ -227,7 +291,8 @@ int s5b_decode(char **mem, size_t *bytes, s5b_rec_t **read, s5b_file_t *f) {
     return s5b_decode_batch(f, mem, bytes, 1, read);
 }
 
-int s5b_encode_batch(s5b_file_t *f, s5b_rec_t **reads, size_t n, char **mems, size_t *bytes) {
+int s5b_encode_batch(s5b_file_t *fpub, s5b_rec_t **reads, size_t n, char **mems, size_t *bytes) {
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !reads || !mems || !bytes) return fail(S5B_ERR_ARG);
     if (n == 0) return 0;
     if (f->rec_press != PRESS_NONE || f->sig_press != PRESS_NONE) {
@@ -308,7 +373,8 @@ int s5b_encode(char **mem, size_t *bytes, s5b_rec_t *read, s5b_file_t *f) {
     return s5b_encode_batch(f, &read, 1, mem, bytes) == 0 ? 0 : -1;
 }
 
-int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *f) {
+int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *fpub) {
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !f->writing || !mem) return fail(S5B_ERR_ARG);
     if (fwrite(mem, 1, bytes, f->out) != bytes) return fail(S5B_ERR_IO);
     return (int)bytes;

@@ -1531,6 +1531,14 @@ void *s5b_ptr_compress_solo(int method, const void *ptr, size_t count, size_t *n
     int rc = S5B_OK;
     if (!ptr || !n) {
         rc = S5B_ERR_ARG;  // slow5_press.c:334-338
+    } else if (method == S5B_COMPRESS_NONE) {  // a copy (slow5_press.c:340-349): no device involved
+        out = malloc(count ? count : 1);
+        if (out) {
+            memcpy(out, ptr, count);
+            out_n = count;
+        } else {
+            rc = S5B_ERR_MEM;
+        }
     } else if (s5b_ctx_t *ctx = thread_ctx(&rc)) {
         const void *ptrs[1] = {ptr};
         size_t counts[1] = {count};
@@ -1552,6 +1560,14 @@ void *s5b_ptr_depress_solo(int method, const void *ptr, size_t count, size_t *n)
     int rc = S5B_OK;
     if (!ptr || !n) {
         rc = S5B_ERR_ARG;  // slow5_press.c:443-447
+    } else if (method == S5B_COMPRESS_NONE) {  // a copy (slow5_press.c:449-458): no device involved
+        out = malloc(count ? count : 1);
+        if (out) {
+            memcpy(out, ptr, count);
+            out_n = count;
+        } else {
+            rc = S5B_ERR_MEM;
+        }
     } else if (s5b_ctx_t *ctx = thread_ctx(&rc)) {
         const void *ptrs[1] = {ptr};
         size_t counts[1] = {count};

@@ -1,0 +1,153 @@
+"""The drop-in boundary: the slow5lib names and struct layouts a caller of the per-record codec path sees.
+
+* the reference's own example program slow5lib/examples/adv/sequential_read_pthreads.c, UNCHANGED, compiled against
+  include/compat (our <slow5/slow5.h>) and linked with libslow5b200.so prints what the reference build prints;
+* libslow5b200_compat.so exports the slow5_* symbols themselves;
+* the public struct layouts match the reference's headers field by field (checked with offsetof on both sides);
+* the stateful press twins (slow5_press_init / slow5_ptr_compress / slow5_compress_footer_next ...) load and validate.
+CPU only.  The pieces that need the reference tree (example source, headers) skip without it."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFTREE = "/root/reference"
+LIBDIR = os.path.join(ROOT, "slow5tools_b200")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libslow5_ref.so")
+have_tree = pytest.mark.skipif(not os.path.exists(os.path.join(REFTREE, "slow5lib", "examples", "adv", "sequential_read_pthreads.c")),
+                               reason="reference tree not present")
+
+
+def _cc(args, cwd=None):
+    subprocess.check_call(["gcc"] + args, cwd=cwd)
+
+
+@have_tree
+def test_reference_example_builds_unchanged_and_prints_the_same(tmp_path):
+    src = os.path.join(REFTREE, "slow5lib", "examples", "adv", "sequential_read_pthreads.c")
+    os.makedirs(tmp_path / "examples")
+    shutil.copy(os.path.join(REFTREE, "slow5lib", "examples", "example.slow5"), tmp_path / "examples" / "example.slow5")
+    ours = str(tmp_path / "ours")
+    _cc(["-O1", "-Wall", "-I", os.path.join(ROOT, "include", "compat"), src, "-o", ours, "-L", LIBDIR, "-lslow5b200", "-lpthread",
+         "-Wl,-rpath," + LIBDIR])
+    a = subprocess.run([ours], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert a.returncode == 0, a.stderr.decode()
+    mine = sorted(a.stderr.decode().splitlines())
+    assert any("Successfully decoded the read" in ln for ln in mine) and any("Read 5 raw records" in ln for ln in mine)
+    if os.path.exists(REF_SO):
+        theirs = str(tmp_path / "theirs")
+        _cc(["-O1", "-I", os.path.join(REFTREE, "slow5lib", "include"), src, "-o", theirs, REF_SO, "-lpthread", "-lz",
+             "-Wl,-rpath," + os.path.dirname(REF_SO)])
+        b = subprocess.run([theirs], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+        assert b.returncode == 0
+        assert mine == sorted(b.stderr.decode().splitlines())   # (threads print in any order)
+
+
+def test_compat_library_exports_the_slow5_names():
+    L = C.CDLL(os.path.join(LIBDIR, "libslow5b200_compat.so"))
+    for name in ("slow5_open", "slow5_close", "slow5_get_next_mem", "slow5_get_next_bytes", "slow5_decode", "slow5_encode",
+                 "slow5_write_bytes", "slow5_rec_free", "slow5_set_press", "slow5_hdr_write", "slow5_init_mt", "slow5_init_batch",
+                 "slow5_get_next_batch", "slow5_encode_batch", "slow5_write_batch", "slow5_free_batch", "slow5_free_mt",
+                 "slow5_press_init", "__slow5_press_init", "slow5_press_free", "__slow5_press_free", "slow5_ptr_compress",
+                 "slow5_ptr_depress", "slow5_ptr_compress_solo", "slow5_ptr_depress_solo", "slow5_compress_footer_next",
+                 "slow5_errno_location"):
+        assert hasattr(L, name), name
+    # a round trip through the names (method NONE needs no GPU): open a reference fixture, read the raw records
+    fix = os.path.join(ROOT, "tests", "golden", "fixtures", "exp_1_lossless_zlib_svb_v0.2.0.blow5")
+    L.slow5_open.restype = C.c_void_p
+    L.slow5_open.argtypes = [C.c_char_p, C.c_char_p]
+    L.slow5_get_next_bytes.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p]
+    L.slow5_close.argtypes = [C.c_void_p]
+    L.slow5_errno_location.restype = C.POINTER(C.c_int)
+    sp = L.slow5_open(fix.encode(), b"r")
+    assert sp
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    n = 0
+    while True:
+        mem, nb = C.c_void_p(), C.c_size_t()
+        if L.slow5_get_next_bytes(C.byref(mem), C.byref(nb), sp) < 0:
+            assert L.slow5_errno_location()[0] == -1          # SLOW5_ERR_EOF
+            break
+        assert nb.value > 0
+        libc.free(mem)
+        n += 1
+    assert n >= 1
+    assert L.slow5_close(sp) == 0
+
+
+@have_tree
+def test_public_struct_layouts_match_the_reference_headers(tmp_path):
+    """offsetof / sizeof of every field a caller may touch, printed by one program compiled against the reference's
+    headers and one against ours"""
+    fields_rec = ["read_id_len", "read_id", "read_group", "digitisation", "offset", "range", "sampling_rate", "len_raw_signal",
+                  "raw_signal"]
+    fields_file = ["fp", "format", "compress", "header", "index", "meta.pathname", "meta.fd", "meta.start_rec_offset",
+                   "meta.fread_buffer", "meta.mode"]
+    fields_batch = ["n_rec", "capacity_rec", "mem_records", "mem_bytes", "slow5_rec", "rid"]
+    body = ["#include <stdio.h>", "#include <stddef.h>", "#include <slow5/slow5.h>", "#include <slow5/slow5_mt.h>",
+            "#include <slow5/slow5_press.h>", "int main(void){"]
+    for f in fields_rec:
+        body.append('printf("rec.%s %%zu\\n", offsetof(slow5_rec_t, %s));' % (f, f))
+    for f in fields_file:
+        body.append('printf("file.%s %%zu\\n", offsetof(slow5_file_t, %s));' % (f, f))
+    for f in fields_batch:
+        body.append('printf("batch.%s %%zu\\n", offsetof(slow5_batch_t, %s));' % (f, f))
+    body += ['printf("mt.sf %zu\\n", offsetof(slow5_mt_t, sf));', 'printf("mt.num_thread %zu\\n", offsetof(slow5_mt_t, num_thread));',
+             'printf("press.record_press %zu\\n", offsetof(slow5_press_t, record_press));',
+             'printf("press.signal_press %zu\\n", offsetof(slow5_press_t, signal_press));',
+             'printf("__press.method %zu\\n", offsetof(struct __slow5_press, method));',
+             'printf("__press.stream %zu\\n", offsetof(struct __slow5_press, stream));',
+             'printf("method_t %zu %zu\\n", sizeof(slow5_press_method_t), offsetof(slow5_press_method_t, signal_method));',
+             'printf("hdr.version %zu hdr.num_read_groups %zu\\n", offsetof(struct slow5_hdr, version), offsetof(struct slow5_hdr, num_read_groups));',
+             "return 0;}"]
+    src = tmp_path / "layout.c"
+    ours_body = "\n".join(body).replace("struct slow5_hdr", "struct s5b_hdr")
+    src.write_text("\n".join(body))
+    (tmp_path / "layout_ours.c").write_text(ours_body)
+    _cc(["-DSLOW5_ENABLE_MT", "-I", os.path.join(REFTREE, "slow5lib", "include"), str(src), "-o", str(tmp_path / "ref")])
+    _cc(["-I", os.path.join(ROOT, "include", "compat"), str(tmp_path / "layout_ours.c"), "-o", str(tmp_path / "ours")])
+    ref = subprocess.check_output([str(tmp_path / "ref")]).decode()
+    ours = subprocess.check_output([str(tmp_path / "ours")]).decode()
+    assert ref == ours, "\n" + ref + "\n---\n" + ours
+
+
+def test_stateful_press_objects():
+    L = C.CDLL(os.path.join(LIBDIR, "libslow5b200.so"))
+
+    class Method(C.Structure):
+        _fields_ = [("record_method", C.c_int), ("signal_method", C.c_int)]
+
+    class Inner(C.Structure):
+        _fields_ = [("method", C.c_int), ("stream", C.c_void_p)]
+
+    class Press(C.Structure):
+        _fields_ = [("record_press", C.POINTER(Inner)), ("signal_press", C.POINTER(Inner))]
+
+    L.s5b_press_init.restype = C.POINTER(Press)
+    L.s5b_press_init.argtypes = [Method]
+    L.s5b_press_free.argtypes = [C.POINTER(Press)]
+    L.s5b_ptr_compress.restype = C.c_void_p
+    L.s5b_ptr_compress.argtypes = [C.POINTER(Inner), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.s5b_ptr_depress.restype = C.c_void_p
+    L.s5b_ptr_depress.argtypes = [C.POINTER(Inner), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.s5b_compress_footer_next.argtypes = [C.POINTER(Inner)]
+    p = L.s5b_press_init(Method(1, 2))        # zlib records, svb-zd signals: view's default (src/view.c:43)
+    assert p and p.contents.record_press.contents.method == 1 and p.contents.signal_press.contents.method == 2
+    L.s5b_compress_footer_next(p.contents.record_press)
+    L.s5b_press_free(p)
+    assert not L.s5b_press_init(Method(9, 0))  # unknown method (slow5_press.c:282-295: SLOW5_ERR_ARG)
+    # method NONE is a copy and needs no device (slow5_press.c:340-349)
+    q = L.s5b_press_init(Method(0, 0))
+    n = C.c_size_t()
+    data = b"0123456789"
+    out = L.s5b_ptr_compress(q.contents.record_press, data, len(data), C.byref(n))
+    assert out and n.value == len(data) and C.string_at(out, n.value) == data
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(out)
+    assert not L.s5b_ptr_depress(None, data, len(data), C.byref(n)) and n.value == 0
+    L.s5b_press_free(q)

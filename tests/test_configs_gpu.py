@@ -180,3 +180,79 @@ def test_config3_recode_lognormal_lengths_sharded(cdc, tmp_path):
     out = tmp_path / "cli.blow5"
     subprocess.check_call([CLI, "view", str(ref_z), "-o", str(out), "-c", "none", "-s", "none"], stderr=subprocess.DEVNULL)
     assert _records(str(out))[1] == raw_recs
+
+
+def _refdrv():
+    from conftest import build_oracle
+    L = C.CDLL(build_oracle())
+    L.refdrv_record_pass.restype = C.c_int
+    L.refdrv_record_pass.argtypes = [C.c_char_p, C.c_char_p] + [C.c_int] * 4 + [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+        C.c_void_p, C.POINTER(C.c_double)]
+    return L
+
+
+def _ref_pass(L, ref_so, methods, src, off, length, out, out_off=None):
+    nb, sec = C.c_uint64(), C.c_double()
+    rc = L.refdrv_record_pass(ref_so, b"/tmp", *methods, src.ctypes.data, off.ctypes.data, length.ctypes.data, len(length),
+                              os.cpu_count() or 1, out.ctypes.data, out.size, C.byref(nb),
+                              out_off.ctypes.data if out_off is not None else None, C.byref(sec))
+    assert rc == 0, rc
+    return nb.value
+
+
+@pytest.mark.parametrize("R", [100000, 1000000])
+def test_config2_every_record_bit_exact_at_full_size(cdc, R):
+    """BASELINE configs[1]/[2] at their full sizes, EVERY read: (a) the svb-zd records the GPU packs equal the oracle's
+    byte for byte (the whole image is compared, not a sample); (b) the zlib + svb-zd image the GPU writes is decoded by
+    the compiled reference (slow5_decode + slow5_encode per record) back to exactly the input records; (c) the GPU decodes
+    its own image to the input."""
+    N = 4096
+    rl = synth.record_bytes(N)
+    sig = synth.nanopore_signal(R * N, seed=4321, device="cuda")
+    d_raw = synth.blow5_records(sig, R, N, seed=4321).view(-1)
+    del sig
+    h_raw = d_raw.cpu().numpy()
+    off = np.arange(R, dtype=np.uint64) * np.uint64(rl)
+    ln = np.full(R, rl, np.uint32)
+    L = _refdrv()
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libslow5_ref.so")
+    ref_so = ref_so.encode() if os.path.exists(ref_so) else None
+    d_res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    d_off = torch.zeros(R + 1, dtype=torch.int64, device="cuda")
+    # (a) none/none -> none/svb-zd: deterministic, whole image against the oracle's restatement
+    d_img = torch.zeros(R * (rl * 3 // 4) + 4096, dtype=torch.uint8, device="cuda")
+    cdc.blow5_recode_dev(METHOD.NONE, METHOD.NONE, METHOD.NONE, METHOD.SVB_ZD, d_raw, R * rl, off, ln, d_img, d_res, None)
+    cdc.sync()
+    nb, err = (int(x) for x in d_res.cpu().numpy())
+    assert err == 0
+    want = np.zeros(d_img.numel(), np.uint8)
+    nb_o = _ref_pass(L, None, (0, 0, 0, 2), h_raw, off, ln, want)          # oracle port (blow5_oracle.c + svbzd_oracle.c)
+    assert nb == nb_o
+    got = d_img[:nb].cpu().numpy()
+    assert np.array_equal(got, want[:nb])
+    del got, want, d_img
+    # (b) full encode on the GPU, decoded by the reference library, all R records
+    d_z = torch.zeros(R * (rl // 2 + 512), dtype=torch.uint8, device="cuda")
+    cdc.blow5_recode_dev(METHOD.NONE, METHOD.NONE, METHOD.ZLIB, METHOD.SVB_ZD, d_raw, R * rl, off, ln, d_z, d_res, d_off)
+    cdc.sync()
+    nbz, err = (int(x) for x in d_res.cpu().numpy())
+    assert err == 0
+    h_z = d_z[:nbz].cpu().numpy()
+    zoff_all = d_off.cpu().numpy().view(np.uint64)
+    zo = zoff_all[:-1] + np.uint64(8)
+    zl = (zoff_all[1:] - zoff_all[:-1] - np.uint64(8)).astype(np.uint32)
+    back = np.zeros(R * (rl + 8) + 64, np.uint8)
+    nb_back = _ref_pass(L, ref_so, (1, 2, 0, 0), h_z, zo, zl, back)
+    assert nb_back == R * (rl + 8)
+    b = back[:nb_back].reshape(R, rl + 8)
+    assert np.array_equal(b[:, 8:], h_raw.reshape(R, rl))
+    assert (b[:, :8] == np.frombuffer(np.uint64(rl).tobytes(), np.uint8)).all()
+    del back, b
+    # (c) and by the GPU itself
+    d_back = torch.zeros(R * (rl + 8) + 64, dtype=torch.uint8, device="cuda")
+    cdc.blow5_recode_dev(METHOD.ZLIB, METHOD.SVB_ZD, METHOD.NONE, METHOD.NONE, d_z, nbz, zo, zl, d_back, d_res, None)
+    cdc.sync()
+    nbb, err = (int(x) for x in d_res.cpu().numpy())
+    assert err == 0 and nbb == R * (rl + 8)
+    assert torch.equal(d_back[:nbb].view(R, rl + 8)[:, 8:], d_raw.view(R, rl))
