@@ -245,6 +245,17 @@ const char *s5b_stage_name(int stage);
  * h_ids[id_off[i] .. id_off[i+1]) (no terminator).  ctx may be NULL for S5B_COMPRESS_NONE. */
 int s5b_blow5_read_ids_host(s5b_ctx_t *ctx, int in_rec, const uint8_t *h_in, uint64_t in_bytes, const uint64_t *rec_off,
                             const uint32_t *rec_len, uint64_t n, uint8_t *h_ids, uint64_t ids_cap, uint64_t *id_off);
+/* The raw_signal column of SLOW5 text records, the other per-sample loop of `view` (slow5_rec_to_mem's sprintf("%d,") loop,
+ * slow5.c:3866-3878, and slow5_rec_parse's strsep + slow5_ato_int16 loop, slow5.c:2754-2778), for a batch:
+ *   s5b_signal_to_ascii_batch_host: record i's STORED signal bytes (sig_method S5B_COMPRESS_NONE = raw int16, SVB_ZD or EX_ZD:
+ *     decoded on the device first) -> malloc()'d, NUL-terminated "v0,v1,...,vN-1" (out_n[i] = characters, no trailing comma);
+ *   s5b_ascii_to_signal_batch_host: text of out_n characters -> malloc()'d int16 samples; expect[i] is the record's
+ *     len_raw_signal column, a different count or a token the reference rejects (empty, leading zero, a character other than
+ *     digits and '-', outside int16: slow5_misc.c:122-139, :303-319) gives S5B_ERR_ARG for that record (NULL pointer). */
+int s5b_signal_to_ascii_batch_host(s5b_ctx_t *ctx, int sig_method, const void *const *ptrs, const size_t *counts, size_t n,
+                                   char **out_ptrs, size_t *out_n);
+int s5b_ascii_to_signal_batch_host(s5b_ctx_t *ctx, const char *const *ptrs, const size_t *counts, const uint64_t *expect, size_t n,
+                                   int16_t **out_ptrs, size_t *out_n);
 /* page-locked host memory for the slab entry points (cudaHostAlloc / cudaFreeHost) */
 void *s5b_host_alloc(size_t bytes);
 void s5b_host_free(void *p);

@@ -496,7 +496,7 @@ static void aux_prim_to_str(const uint8_t *d, int type, std::string &out) {
     }
 }
 
-void record_to_ascii(const Record &rec, const Header &h, std::string &out) {
+void record_to_ascii(const Record &rec, const Header &h, std::string &out, const char *sig_text, size_t sig_text_len) {
     out += rec.read_id;
     out += '\t';
     put(out, (unsigned long long)rec.read_group);
@@ -511,8 +511,10 @@ void record_to_ascii(const Record &rec, const Header &h, std::string &out) {
     out += '\t';
     put(out, (unsigned long long)rec.len_raw_signal);
     out += '\t';
-    // signal: comma separated, no trailing comma (slow5.c:3866-3878)
-    {
+    // signal: comma separated, no trailing comma (slow5.c:3866-3878); already formatted (on the GPU) when sig_text is given
+    if (sig_text) {
+        out.append(sig_text, sig_text_len);
+    } else {
         const size_t n = rec.raw_signal.size();
         const size_t base = out.size();
         out.resize(base + n * 7 + 1);
@@ -642,7 +644,7 @@ static bool parse_prim(const std::string &tok, int type, uint8_t *dst) {
 }
 
 bool record_parse_ascii(const char *line, uint64_t n, const Header &h, Record &rec, std::vector<uint8_t> &aux_store,
-                        std::string &err) {
+                        std::string &err, bool defer_signal) {
     std::vector<std::string> col;
     split(std::string(line, n), '\t', col);
     if (col.size() != 8 + h.aux.size()) {
@@ -663,7 +665,15 @@ bool record_parse_ascii(const char *line, uint64_t n, const Header &h, Record &r
     if (*end) goto bad;
     rec.len_raw_signal = strtoull(col[6].c_str(), &end, 10);
     if (*end) goto bad;
-    {
+    if (defer_signal) {
+        // the caller converts the column in a batch (s5b_ascii_to_signal_batch_host): hand out where it sits in `line`
+        rec.raw_signal.clear();
+        uint64_t at = 0;
+        for (int tabs = 0; tabs < 7 && at < n; ++at)
+            if (line[at] == '\t') ++tabs;
+        rec.sig_bytes = reinterpret_cast<const uint8_t *>(line + at);
+        rec.sig_nbytes = col[7].size();
+    } else {
         rec.raw_signal.clear();
         rec.raw_signal.reserve(rec.len_raw_signal);
         const char *p = col[7].c_str();
@@ -713,8 +723,10 @@ bool record_parse_ascii(const char *line, uint64_t n, const Header &h, Record &r
     }
     rec.aux_bytes = aux_store.data();
     rec.aux_nbytes = aux_store.size();
-    rec.sig_bytes = reinterpret_cast<const uint8_t *>(rec.raw_signal.data());
-    rec.sig_nbytes = rec.raw_signal.size() * 2;
+    if (!defer_signal) {
+        rec.sig_bytes = reinterpret_cast<const uint8_t *>(rec.raw_signal.data());
+        rec.sig_nbytes = rec.raw_signal.size() * 2;
+    }
     return true;
 bad:
     err = "slow5 record does not parse";

@@ -87,11 +87,13 @@ std::string header_to_mem(const Header &h, Fmt fmt, int record_method, int signa
 // Returns false when the record is inconsistent (slow5.c:2937-2949).
 bool record_parse_binary(const uint8_t *mem, uint64_t n, const Header &h, int signal_method, Record &rec, std::string &err);
 // ASCII record parse (one SLOW5 line); aux columns are converted to the binary aux form in aux_store.
+// defer_signal: leave the raw_signal column unparsed and point rec.sig_bytes / sig_nbytes at its characters inside `line`
 bool record_parse_ascii(const char *line, uint64_t n, const Header &h, Record &rec, std::vector<uint8_t> &aux_store,
-                        std::string &err);
+                        std::string &err, bool defer_signal = false);
 
 // SLOW5 ASCII line for a record whose raw_signal is decoded (slow5.c:3824-3926), including '\n'
-void record_to_ascii(const Record &rec, const Header &h, std::string &out);
+// sig_text (optional): the already formatted raw_signal column (s5b_signal_to_ascii_batch_host); else rec.raw_signal is printed
+void record_to_ascii(const Record &rec, const Header &h, std::string &out, const char *sig_text = nullptr, size_t sig_text_len = 0);
 // packed binary record WITHOUT record compression and WITHOUT the size prefix (slow5.c:3928-4044);
 // `signal` = the bytes to store (raw int16 or svb-zd stream), `signal_is_compressed` selects the meaning of the
 // len_raw_signal field (sample count vs byte count, slow5.c:3983-3987).  *signal_at receives the offset of

@@ -440,9 +440,12 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
                 if (!record_parse_binary(packed[i], packed_n[i], hdr, hdr.signal_method, b.rec[i], e)) bad = 1;
             });
         } else {
+            // with a GPU context the raw_signal column is converted there, a batch at a time (slow5.c:2754-2778)
+            const bool defer = gpu != nullptr;
             parallel_for(n, threads, [&](size_t i) {
                 std::string e;
-                if (!record_parse_ascii(reinterpret_cast<const char *>(packed[i]), packed_n[i], hdr, b.rec[i], b.aux_store[i], e)) bad = 1;
+                if (!record_parse_ascii(reinterpret_cast<const char *>(packed[i]), packed_n[i], hdr, b.rec[i], b.aux_store[i], e, defer))
+                    bad = 1;
             });
         }
         if (bad) {
@@ -452,7 +455,36 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
         }
         // ---- signal decompression
         std::vector<const int16_t *> sig(n);
-        if (fmt_in == FMT_BINARY && hdr.signal_method != PRESS_NONE) {  // PRESS_* == S5B_COMPRESS_* (slow5_press.h:61-67)
+        // text output with a GPU context: the stored signals go straight to the device formatter (decode + sprintf loop of
+        // slow5.c:3866-3878 in one trip), nothing is decompressed to the host
+        const bool gpu_text = fmt_out == FMT_ASCII && gpu != nullptr && fmt_in == FMT_BINARY;
+        if (fmt_in == FMT_ASCII && gpu != nullptr) {
+            std::vector<const char *> tptrs(n);
+            std::vector<uint64_t> expect(n);
+            for (size_t i = 0; i < n; ++i) {
+                tptrs[i] = reinterpret_cast<const char *>(b.rec[i].sig_bytes);
+                counts[i] = b.rec[i].sig_nbytes;
+                expect[i] = b.rec[i].len_raw_signal;
+            }
+            b.sig.assign(n, nullptr);
+            b.sig_n.assign(n, 0);
+            std::vector<int16_t *> outp(n, nullptr);
+            const int rc = s5b_ascii_to_signal_batch_host(gpu, tptrs.data(), counts.data(), expect.data(), n, outp.data(), b.sig_n.data());
+            for (size_t i = 0; i < n; ++i) b.sig[i] = outp[i];
+            if (rc != S5B_OK) {
+                ERROR("%s", "a record could not be parsed");
+                ret = 1;
+                break;
+            }
+            for (size_t i = 0; i < n; ++i) {
+                sig[i] = static_cast<const int16_t *>(b.sig[i]);
+                b.sig_n[i] *= 2;  // bytes, like the codec calls report
+                b.rec[i].sig_bytes = reinterpret_cast<const uint8_t *>(b.sig[i]);
+                b.rec[i].sig_nbytes = b.sig_n[i];
+            }
+        } else if (gpu_text) {
+            for (size_t i = 0; i < n; ++i) sig[i] = nullptr;
+        } else if (fmt_in == FMT_BINARY && hdr.signal_method != PRESS_NONE) {  // PRESS_* == S5B_COMPRESS_* (slow5_press.h:61-67)
             for (size_t i = 0; i < n; ++i) {
                 ptrs[i] = b.rec[i].sig_bytes;
                 counts[i] = b.rec[i].sig_nbytes;
@@ -478,7 +510,41 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
         }
 
         // ---- output
-        if (fmt_out == FMT_ASCII) {
+        if (gpu_text) {
+            std::vector<char *> text(n, nullptr);
+            std::vector<size_t> text_n(n, 0);
+            for (size_t i = 0; i < n; ++i) {
+                ptrs[i] = b.rec[i].sig_bytes;
+                counts[i] = b.rec[i].sig_nbytes;
+            }
+            const int rc = s5b_signal_to_ascii_batch_host(gpu, hdr.signal_method, ptrs.data(), counts.data(), n, text.data(), text_n.data());
+            if (rc != S5B_OK) {
+                ERROR("signal decompression failed: %s", s5b_strerror(rc));
+                for (char *p : text) free(p);
+                ret = 1;
+                break;
+            }
+            std::vector<std::string> lines(n);
+            parallel_for(n, threads, [&](size_t i) {
+                Record &r = b.rec[i];
+                // the sample count of the len_raw_signal column: what the stored stream says it holds
+                const uint8_t *sb = r.sig_bytes;
+                uint64_t ns = r.sig_nbytes / 2;
+                if (hdr.signal_method == PRESS_SVB_ZD) {
+                    uint32_t v = 0;
+                    if (r.sig_nbytes >= 4) memcpy(&v, sb, 4);
+                    ns = v;
+                } else if (hdr.signal_method == PRESS_EX_ZD) {
+                    ns = 0;
+                    if (r.sig_nbytes >= 9) memcpy(&ns, sb + 1, 8);
+                }
+                r.len_raw_signal = ns;
+                record_to_ascii(r, hdr, lines[i], text[i], text_n[i]);
+                free(text[i]);
+            });
+            for (size_t i = 0; i < n && ret == 0; ++i)
+                if (fwrite(lines[i].data(), 1, lines[i].size(), fout) != lines[i].size()) ret = 1;
+        } else if (fmt_out == FMT_ASCII) {
             std::vector<std::string> lines(n);
             parallel_for(n, threads, [&](size_t i) {
                 Record &r = b.rec[i];

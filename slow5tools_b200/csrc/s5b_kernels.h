@@ -147,6 +147,15 @@ cudaError_t launch_rebase_off(uint64_t *dst, const uint64_t *src, uint64_t n, ui
 cudaError_t launch_zstd_sizes(const uint8_t *in, const uint64_t *off, const uint32_t *len, uint64_t n, uint32_t mul,
                               uint32_t add, uint32_t *size, int32_t *status, cudaStream_t st);
 
+// SLOW5 text raw_signal column (ascii_kernels.cu): sizes, text, and back
+cudaError_t launch_ascii_size(const int16_t *sig, const uint64_t *sig_off, const uint32_t *n_samples, uint64_t n_reads,
+                              uint32_t *text_len, cudaStream_t st);
+cudaError_t launch_ascii_format(const int16_t *sig, const uint64_t *sig_off, const uint32_t *n_samples, uint64_t n_reads,
+                                uint8_t *text, const uint64_t *text_off, cudaStream_t st);
+cudaError_t launch_ascii_parse(const uint8_t *text, const uint64_t *text_off, const uint32_t *text_len, uint64_t n_reads,
+                               int16_t *sig, const uint64_t *sig_off, const uint32_t *expect, uint32_t *n_samples, int32_t *status,
+                               cudaStream_t st);
+
 // dense gather: scratch must hold >= compact_scratch_bytes(n_reads)
 size_t compact_scratch_bytes(uint64_t n_reads);
 cudaError_t launch_compact(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t n_reads,

@@ -280,3 +280,29 @@ def test_corrupt_size_prefix_fails_cleanly(tmp_path):
         r = subprocess.run([CLI, "view", str(bad), "-o", str(tmp_path / "o.slow5")] + extra, stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE, timeout=60)
         assert r.returncode == 1, (r.returncode, r.stderr.decode())
+
+
+@have_ref
+def test_text_paths_through_the_gpu_formatter_and_parser(tmp_path):
+    """blow5 -> slow5 formats the raw_signal column on the GPU and slow5 -> blow5 parses it there (ascii_kernels.cu): both
+    must be byte-identical to the reference binary, for svb-zd, ex-zd and uncompressed signals under zlib"""
+    for name, flags in (("exp_1_lossless_zlib_svb_v0.2.0", []), ("zlib_svb-zd_multi_rg_v0.2.0", ["-t", "3", "-K", "2"]),
+                        ("exp_1_lossless_zlib_ex_zd", [])):
+        src = os.path.join(FIX, name + ".blow5")
+        if not os.path.exists(src):
+            continue
+        mine, theirs = tmp_path / "m.slow5", tmp_path / "t.slow5"
+        ours(src, "-o", str(mine), *flags)
+        ref(src, "-o", str(theirs))
+        assert filecmp.cmp(mine, theirs, shallow=False), name
+        # and back: text in, compressed blow5 out; the reference reads it to the same text
+        back = tmp_path / "back.blow5"
+        ours(str(theirs), "-o", str(back), "-c", "zlib", "-s", "svb-zd")
+        again = tmp_path / "again.slow5"
+        ref(str(back), "-o", str(again))
+        assert filecmp.cmp(again, theirs, shallow=False), name
+        # svb-zd only output from text is byte-identical to the reference's
+        a, b = tmp_path / "a.blow5", tmp_path / "b.blow5"
+        ours(str(theirs), "-o", str(a), "-c", "none", "-s", "svb-zd")
+        ref(str(theirs), "-o", str(b), "-c", "none", "-s", "svb-zd")
+        assert filecmp.cmp(a, b, shallow=False), name
