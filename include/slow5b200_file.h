@@ -112,7 +112,7 @@ typedef struct {
     char **mem_records;
     size_t *mem_bytes;
     s5b_rec_t **slow5_rec;
-    char **rid; /* get() by read id needs the index: not provided */
+    char **rid; /* the read ids of the last s5b_get_batch call (caller's array) */
 } s5b_batch_t;
 typedef struct {
     s5b_file_t *sf;
@@ -123,6 +123,12 @@ s5b_batch_t *s5b_init_batch(int batch_capacity);
 int s5b_get_next_batch(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
 int s5b_encode_batch_mt(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
 int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
+/* slow5_idx_load (slow5.h:560) / slow5_get_batch (slow5_mt.h:52, slow5_mt.c:319-333): random access by read id.  The index is
+ * FILE.idx as written by `slow5tools-b200 index` (byte-identical to the reference's); S5B_ERR_IO when it is missing.
+ * s5b_get_batch fetches the num_rid records with pread() and decodes them as ONE GPU batch into batch->slow5_rec[];
+ * returns num_rid, or S5B_ERR_ARG when an id is not in the index (the reference exits the process). */
+int s5b_idx_load(s5b_file_t *fp);
+int s5b_get_batch(s5b_mt_t *mt, s5b_batch_t *batch, char **rid, int num_rid);
 void s5b_free_batch(s5b_batch_t *batch);
 void s5b_free_mt(s5b_mt_t *mt);
 
@@ -147,6 +153,8 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_get_next_batch s5b_get_next_batch
 #define slow5_encode_batch s5b_encode_batch_mt
 #define slow5_write_batch s5b_write_batch
+#define slow5_get_batch s5b_get_batch
+#define slow5_idx_load s5b_idx_load
 #define slow5_free_batch s5b_free_batch
 #define slow5_free_mt s5b_free_mt
 #define slow5_file_t s5b_file_t

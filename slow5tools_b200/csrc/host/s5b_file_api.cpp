@@ -1,8 +1,10 @@
 // s5b_file_api.cpp -- the slow5lib low-level API slice (include/slow5b200_file.h) over blow5_io + the GPU
 // batch codec.  Every codec call goes through the C-ABI of include/slow5b200.h; nothing is computed here.
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../include/slow5b200_file.h"
@@ -22,6 +24,12 @@ struct S5bFile {
     Header hdr;         // "w": header to emit
     int rec_press = PRESS_ZLIB, sig_press = PRESS_SVB_ZD;
     s5b_ctx_t *gpu = nullptr;
+    // read id -> (offset of the record's size prefix, bytes including the prefix): FILE.idx (slow5_idx.c:360-520)
+    struct Where {
+        uint64_t offset, size;
+    };
+    std::unordered_map<std::string, Where> index;
+    bool index_loaded = false;
 };
 static inline S5bFile *impl(s5b_file_t *f) { return reinterpret_cast<S5bFile *>(f); }
 static inline const S5bFile *impl(const s5b_file_t *f) { return reinterpret_cast<const S5bFile *>(f); }
@@ -454,6 +462,72 @@ int s5b_encode_batch_mt(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5
     if (num_reads == 0) return 0;
     const int rc = s5b_encode_batch(mt->sf, b->slow5_rec, (size_t)num_reads, b->mem_records, b->mem_bytes);
     return rc < 0 ? rc : num_reads;
+}
+
+int s5b_idx_load(s5b_file_t *fpub) {  // slow5_idx_load (slow5.h:560): reads FILE.idx, written by `slow5tools-b200 index`
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
+    if (!f || f->writing) return fail(S5B_ERR_ARG);
+    if (f->index_loaded) return 0;
+    FILE *x = fopen((f->path + ".idx").c_str(), "rb");
+    if (!x) return fail(S5B_ERR_IO);
+    std::vector<uint8_t> b;
+    uint8_t tmp[1 << 16];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof tmp, x)) > 0) b.insert(b.end(), tmp, tmp + got);
+    fclose(x);
+    if (b.size() < 64 + 8 || memcmp(b.data(), "SLOW5IDX\1", 9) != 0 || memcmp(b.data() + b.size() - 8, "XDI5WOLS", 8) != 0)
+        return fail(S5B_ERR_IO);
+    size_t pos = 64;
+    const size_t end = b.size() - 8;
+    while (pos + 2 <= end) {
+        uint16_t n;
+        memcpy(&n, b.data() + pos, 2);
+        if (pos + 2 + n + 16 > end) return fail(S5B_ERR_IO);
+        S5bFile::Where w;
+        memcpy(&w.offset, b.data() + pos + 2 + n, 8);
+        memcpy(&w.size, b.data() + pos + 2 + n + 8, 8);
+        f->index.emplace(std::string(reinterpret_cast<const char *>(b.data() + pos + 2), n), w);
+        pos += 2 + (size_t)n + 16;
+    }
+    f->index_loaded = true;
+    f->pub.index = &f->index;
+    return 0;
+}
+
+// slow5_get_batch (slow5_mt.c:319-333): the records of `num_rid` read ids, fetched with pread() and decoded as one GPU batch
+int s5b_get_batch(s5b_mt_t *mt, s5b_batch_t *b, char **rid, int num_rid) {
+    if (!mt || !mt->sf || !b || !rid || num_rid < 0 || num_rid > b->capacity_rec) return fail(S5B_ERR_ARG);
+    S5bFile *f = impl(mt->sf);
+    if (f->writing || f->rd.fmt != FMT_BINARY) return fail(S5B_ERR_ARG);
+    if (!f->index_loaded) {
+        const int rc = s5b_idx_load(mt->sf);
+        if (rc < 0) return rc;
+    }
+    batch_drop_mem(b);
+    b->rid = rid;
+    b->n_rec = num_rid;
+    const int fd = fileno(f->rd.fp);
+    for (int i = 0; i < num_rid; ++i) {
+        const auto it = rid[i] ? f->index.find(rid[i]) : f->index.end();
+        if (it == f->index.end() || it->second.size < 8) return fail(S5B_ERR_ARG);  // SLOW5_ERR_NOTFOUND in the reference
+        const size_t bytes = (size_t)(it->second.size - 8);
+        char *m = static_cast<char *>(malloc(bytes ? bytes : 1));
+        if (!m) return fail(S5B_ERR_MEM);
+        size_t done = 0;
+        while (done < bytes) {
+            const ssize_t r = pread(fd, m + done, bytes - done, (off_t)(it->second.offset + 8 + done));
+            if (r <= 0) {
+                free(m);
+                return fail(S5B_ERR_IO);
+            }
+            done += (size_t)r;
+        }
+        b->mem_records[i] = m;
+        b->mem_bytes[i] = bytes;
+    }
+    if (num_rid == 0) return 0;
+    const int rc = s5b_decode_batch(mt->sf, b->mem_records, b->mem_bytes, (size_t)num_rid, b->slow5_rec);
+    return rc < 0 ? rc : num_rid;
 }
 
 int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5_mt.c:359-378

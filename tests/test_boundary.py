@@ -151,3 +151,73 @@ def test_stateful_press_objects():
     libc.free(out)
     assert not L.s5b_ptr_depress(None, data, len(data), C.byref(n)) and n.value == 0
     L.s5b_press_free(q)
+
+
+GET_BATCH_C = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <slow5/slow5.h>
+#include <slow5/slow5_mt.h>
+/* prints "id len checksum" for every record: first sequentially (slow5_get_next_batch), then by read id in reverse order
+ * through slow5_get_batch -- written against the slow5lib names only */
+static unsigned long sum(const slow5_rec_t *r) {
+    unsigned long s = 0;
+    for (uint64_t i = 0; i < r->len_raw_signal; ++i) s = s * 31 + (unsigned short) r->raw_signal[i];
+    return s;
+}
+int main(int argc, char **argv) {
+    slow5_file_t *sp = slow5_open(argv[1], "r");
+    if (!sp) return 2;
+    slow5_mt_t *mt = slow5_init_mt(4, sp);
+    slow5_batch_t *b = slow5_init_batch(64);
+    int n = slow5_get_next_batch(mt, b, 64);
+    if (n <= 0) return 3;
+    char **ids = (char **) malloc(sizeof(char *) * n);
+    for (int i = 0; i < n; ++i) {
+        printf("seq %s %lu %lu\n", b->slow5_rec[i]->read_id, (unsigned long) b->slow5_rec[i]->len_raw_signal, sum(b->slow5_rec[i]));
+        ids[n - 1 - i] = strdup(b->slow5_rec[i]->read_id);
+    }
+    if (slow5_idx_load(sp) < 0) return 4;
+    slow5_batch_t *g = slow5_init_batch(64);
+    if (slow5_get_batch(mt, g, ids, n) != n) return 5;
+    for (int i = n - 1; i >= 0; --i)
+        printf("seq %s %lu %lu\n", g->slow5_rec[i]->read_id, (unsigned long) g->slow5_rec[i]->len_raw_signal, sum(g->slow5_rec[i]));
+    char *missing[1] = {(char *) "no-such-read"};
+    printf("missing %d\n", slow5_get_batch(mt, g, missing, 1) < 0);
+    slow5_free_batch(g);
+    slow5_free_batch(b);
+    slow5_free_mt(mt);
+    slow5_close(sp);
+    return 0;
+}
+"""
+
+
+def _get_batch_program(tmp_path):
+    src = tmp_path / "getb.c"
+    src.write_text(GET_BATCH_C)
+    exe = str(tmp_path / "getb")
+    _cc(["-O1", "-I", os.path.join(ROOT, "include", "compat"), str(src), "-o", exe, "-L", LIBDIR, "-lslow5b200", "-Wl,-rpath," + LIBDIR])
+    return exe
+
+
+def _run_get_batch(tmp_path, fixture):
+    exe = _get_batch_program(tmp_path)
+    f = tmp_path / os.path.basename(fixture)
+    shutil.copy(fixture, f)
+    cli = os.path.join(LIBDIR, "bin", "slow5tools-b200")
+    subprocess.check_call([cli, "index", str(f)], stderr=subprocess.DEVNULL)
+    out = subprocess.check_output([exe, str(f)]).decode().splitlines()
+    n = (len(out) - 1) // 2
+    assert n >= 1 and out[-1] == "missing 1"
+    assert out[:n] == out[n:2 * n]          # random access by id returns what the sequential read returned
+
+
+def test_get_batch_by_read_id_uncompressed(tmp_path):
+    _run_get_batch(tmp_path, os.path.join(ROOT, "tests", "golden", "fixtures", "exp_1_lossless.blow5"))
+
+
+@pytest.mark.gpu
+def test_get_batch_by_read_id_compressed(tmp_path):
+    _run_get_batch(tmp_path, os.path.join(ROOT, "tests", "golden", "fixtures", "zlib_svb-zd_multi_rg_v0.2.0.blow5"))
