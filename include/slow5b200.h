@@ -145,7 +145,10 @@ int s5b_zstd_content_size(const void *frame, size_t len, uint64_t *size);
  * The bytes differ from zlib's (dynamic Huffman + distance-1 run matches); any zlib inflates them to the
  * exact input.  d_split (optional, may be NULL): byte offset inside record r where a new Huffman block
  * should start -- for BLOW5 records the start of the svb-zd data bytes, whose statistics differ from the
- * header + key bytes before them. */
+ * header + key bytes before them.
+ * Size contract: <= 1.03 x zlib level 6 on records whose signal is svb-zd or ex-zd coded (measured 0.98 x).  Records with
+ * an UNCOMPRESSED signal (-s none) are outside that contract: the encoder matches runs only, zlib's LZ77 finds ~13 % more
+ * there; the output is still a valid stream. */
 uint64_t s5b_zlib_bound(uint64_t len);
 int s5b_zlib_deflate_dev(s5b_ctx_t *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
                          uint64_t in_capacity, const uint32_t *d_split, uint64_t n_reads, uint8_t *d_out,

@@ -120,29 +120,19 @@ static void split(const std::string &s, char sep, std::vector<std::string> &out)
     }
 }
 
+// "%f" without the zeros a fixed six-digit fraction leaves behind, and without a bare trailing point; a value that
+// rounds to minus zero prints as "0" (what slow5_double_to_str produces, slow5_misc.c:379-406)
 std::string double_to_str(double x) {
     char buf[512];
-    int n = snprintf(buf, sizeof buf, "%f", x);
+    const int n = snprintf(buf, sizeof buf, "%f", x);
     if (n < 0) return "";
-    if (n >= (int)sizeof buf) n = (int)sizeof buf - 1;
-    for (int i = n - 1; i >= 1; --i) {
-        if (buf[i] == '.') {
-            n = i;
-            buf[n] = 0;
-            if (!strcmp(buf, "-0")) {
-                strcpy(buf, "0");
-                n = 1;
-            }
-            break;
-        } else if (buf[i] != '0') {
-            if (i != n - 1) {
-                n = i + 1;
-                buf[n] = 0;
-            }
-            break;
-        }
+    std::string s(buf, (size_t)(n < (int)sizeof buf ? n : (int)sizeof buf - 1));
+    const size_t point = s.find('.');
+    if (point != std::string::npos) {
+        const size_t last = s.find_last_not_of('0');   // at the latest the point itself
+        s.erase(last == point ? point : last + 1);
     }
-    return std::string(buf, n);
+    return s == "-0" ? std::string("0") : s;
 }
 
 static const char *MAIN_TYPES = "#char*\tuint32_t\tdouble\tdouble\tdouble\tdouble\tuint64_t\tint16_t*";
