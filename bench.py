@@ -428,7 +428,7 @@ def run_ours(args):
     packed_bytes_per_read = int(d_res_t[0]) / SMP - 8
     del d_tmp
 
-    if args.profile:
+    if args.profile and not args.e2e_only:
         if rank == 0:
             print(json.dumps({"profile_only": True, "encode_ms": enc_ms, "decode_ms": dec_ms, "ms_per_step": ms_total / K,
                               "gpu_launches": int(launches), "stage_ms": stage_ms}), flush=True)
@@ -494,6 +494,14 @@ def run_ours(args):
     e2e_seq = max_over_ranks([t1 - t0, t2 - t1])
     pool.shutdown()
     cdc2.close()
+    if args.e2e_only:
+        if rank == 0:
+            print(json.dumps({"e2e_only": True, "e2e_reads_per_s": Re * world * KE / max_over_ranks(e2e_s), "step_s": e2e_s / KE,
+                              "seq_encode_s": e2e_seq[0], "seq_decode_s": e2e_seq[1]}), flush=True)
+        cdc.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_s = max_over_ranks(e2e_s)
     h2d = Re * rl + nb_e               # records up (encode) + compressed records up (decode)
     d2h = nb_e + Re * (rl + 8)         # compressed image down + uncompressed image down
@@ -676,6 +684,7 @@ def main():
     ap.add_argument("--samples", type=int, default=4096)
     ap.add_argument("--profile", action="store_true", help="device-resident loop only (for runs under ncu)")
     ap.add_argument("--no-split", action="store_true", help="skip the N>1 pcie-vs-nccl split comparison")
+    ap.add_argument("--e2e-only", action="store_true", help="dev: one device-resident step, then only the e2e timing (prints a short line)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

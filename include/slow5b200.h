@@ -212,7 +212,7 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
                           uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
                           uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes);
 /* The same transcoding for batches of any size, as a 3-lane CUDA-stream pipeline (the replacement of the work_db pool of
- * src/thread.c:114 around src/view.c:35-57): the batch is cut into chunks of <= 64 Ki records / 256 MiB, and the H2D copy
+ * src/thread.c:114 around src/view.c:35-57): the batch is cut into chunks of <= 24 Ki records / 256 MiB, and the H2D copy
  * of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 run concurrently; between its two copies a chunk never
  * synchronises with the host.  s5b_blow5_recode_host is this call with out_img_off = NULL.  out_img_off (optional,
  * n+1 entries) receives the offset of every record's u64 size prefix inside h_out (entry n = *out_bytes): record i of the

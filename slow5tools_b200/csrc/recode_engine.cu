@@ -2,7 +2,7 @@
 // place of the reference's fork-join pool around its per-record worker (src/view.c:35-57 depress_parse_rec_to_mem run by
 // work_db, src/thread.c:114; driver loop slow5_convert_parallel src/view.c:254-301).
 //
-// A batch is cut into chunks (<= 64 Ki records / 256 MiB of stored bytes).  A chunk goes through
+// A batch is cut into chunks (<= 24 Ki records / 256 MiB of stored bytes).  A chunk goes through
 //     H2D -> record decompression (inflate | zstd) -> locate -> signal decode -> signal encode -> pack ->
 //     record compression (deflate | zstd) -> file image -> D2H
 // entirely on one stream with NO host synchronisation in between: every slab a stage needs is reserved up front from
@@ -471,6 +471,7 @@ int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_
         const int rc = lanes_init(ctx);
         if (rc != S5B_OK) return rc;
     }
+    const int NL = ctx->n_lanes;
     std::vector<Chunk> chunks;
     if (!cut_chunks(rec_off, rec_len, n, in_bytes, ctx->recode_chunk_records, ctx->recode_chunk_bytes, chunks)) return S5B_ERR_ARG;
     Job j{in_rec, in_sig, out_rec, out_sig, h_in, false, in_bytes, rec_off, rec_len, n, h_out, false, out_cap, out_img_off, nullptr,
@@ -482,7 +483,7 @@ int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_
     std::vector<uint64_t> chunk_pos(nc, 0);
     // finish(k): the chunk's verdict is in; queue its payload D2H (or redo it carefully)
     auto finish = [&](size_t k) -> int {
-        RecodeLane &L = ctx->lane[k % NLANE];
+        RecodeLane &L = ctx->lane[k % NL];
         const Chunk &c = chunks[k];
         CU(cudaEventSynchronize(L.front));
         const uint64_t total = L.h_res[0];
@@ -530,16 +531,16 @@ int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_
         pos += total;
         return S5B_OK;
     };
-    for (size_t k = 0; k < nc + (NLANE - 1); ++k) {
+    for (size_t k = 0; k < nc + (size_t)(NL - 1); ++k) {
         if (k < nc) {
-            const int rc = enqueue_chunk(ctx, ctx->lane[k % NLANE], j, chunks[k]);
+            const int rc = enqueue_chunk(ctx, ctx->lane[k % NL], j, chunks[k]);
             if (rc != S5B_OK) {
                 for (int i = 0; i < NLANE; ++i) cudaStreamSynchronize(ctx->lane[i].stream);
                 return rc;
             }
         }
-        if (k >= (size_t)(NLANE - 1)) {
-            const int rc = finish(k - (NLANE - 1));
+        if (k >= (size_t)(NL - 1)) {
+            const int rc = finish(k - (size_t)(NL - 1));
             if (rc != S5B_OK) {
                 for (int i = 0; i < NLANE; ++i) cudaStreamSynchronize(ctx->lane[i].stream);
                 return rc;
@@ -583,7 +584,7 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
     if (n == 0) return S5B_OK;
     std::vector<Chunk> chunks;
     // device-resident passes take larger chunks: there is no copy to overlap, only launch overheads to amortise
-    if (!cut_chunks(rec_off, rec_len, n, in_bytes, ctx->recode_chunk_records * 4, ctx->recode_chunk_bytes * 8, chunks))
+    if (!cut_chunks(rec_off, rec_len, n, in_bytes, ctx->recode_dev_chunk_records, ctx->recode_dev_chunk_bytes, chunks))
         return S5B_ERR_ARG;
     // the record table goes up once per call (one pageable copy = one wait for the stream), chunks slice it on the device
     CU(L.tab.reserve(n * 12 + 64));

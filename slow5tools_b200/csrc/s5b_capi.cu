@@ -115,6 +115,10 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
         long v = atol(e);
         if (v > 0) ctx->recode_chunk_records = (size_t)v;
     }
+    if (const char *e = getenv("S5B_RECODE_LANES")) {
+        long v = atol(e);
+        if (v >= 2 && v <= NLANE) ctx->n_lanes = (int)v;
+    }
     if (const char *e = getenv("S5B_RECODE_CHUNK_MB")) {
         long v = atol(e);
         if (v > 0) ctx->recode_chunk_bytes = (size_t)v << 20;

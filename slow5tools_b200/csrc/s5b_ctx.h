@@ -66,7 +66,7 @@ struct PipeSlot {
 };
 
 // ---- the record transcoder's pipeline lanes (recode_engine.cu) --------------------------------
-constexpr int NLANE = 3;
+constexpr int NLANE = 6;   // lanes that exist; s5b_ctx::n_lanes of them are used (3 unless S5B_RECODE_LANES says otherwise)
 // stages of a transcoding pass, for the optional per-stage CUDA-event timing (s5b_ctx_stage_timing)
 enum Stage { ST_H2D = 0, ST_REC_DEPRESS, ST_GLUE, ST_SIG_DEPRESS, ST_SIG_PRESS, ST_PACK, ST_REC_PRESS, ST_IMAGE, ST_D2H,
              ST_COUNT };
@@ -108,12 +108,20 @@ struct s5b_ctx {
     s5b::DevBuf inf_work;                 // inflate scratch rows of everything that is not a pipeline lane
     s5b::RecodeLane lane[s5b::NLANE];     // the pipelined transcoder (lazily created)
     bool lanes_ready = false;
+    int n_lanes = 3;
     uint64_t *d_img_base = nullptr;       // running output offset of a device-resident transcoding pass
     s5b::StageTimer timer;
     uint64_t launches = 0;
     size_t chunk_bytes = 32u << 20;  // e2e is flat between 16 and 128 MiB (PCIe bound), 32 MiB marginally best
-    size_t recode_chunk_records = 65536;  // records per pipeline chunk of the transcoder (S5B_RECODE_CHUNK)
+    // records / stored bytes per pipeline chunk of the host-form transcoder (S5B_RECODE_CHUNK, S5B_RECODE_CHUNK_MB).  Measured
+    // on the north-star step (tools/gpu_e2e_sweep2.sh, 1 M records end to end): 8 Ki 2.67e6, 16 Ki 3.28e6, 24 Ki 3.58e6,
+    // 32 Ki 3.51e6, 64 Ki 3.38e6, 128 Ki 3.06e6 reads/s -- small chunks shorten the pipeline's fill and drain, too small ones
+    // starve the kernels (a chunk must still fill the GPU with 32-record rounds).
+    size_t recode_chunk_records = 24576;
     size_t recode_chunk_bytes = 256u << 20;
+    // the device-resident form has no copies to overlap: large chunks amortise launches and kernel tails
+    size_t recode_dev_chunk_records = 262144;
+    size_t recode_dev_chunk_bytes = 2048ull << 20;
     std::string last_cuda_error;
 };
 
