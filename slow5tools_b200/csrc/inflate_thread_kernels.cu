@@ -52,26 +52,25 @@ constexpr uint32_t ADLER_MOD = 65521u;
 constexpr int HOT = S5B_TI_HOT;  // sorted symbols kept in shared memory (canonical order puts the frequent ones first)
 // per-lane shared memory: what the symbol loop touches on every iteration; the code lengths of a block header are parked
 // on the same bytes (as nibbles) while the block's codes are being built
-struct TiSmem {
+struct __align__(4) TiSmem {
     uint8_t ring[RING];
     union {
-        uint8_t nib[HOT + 36 > 160 ? HOT + 36 : 160];  // code lengths, two per byte: literal/length at 0..287, distance at 288..319
-        struct {
-            uint8_t sorted8[HOT];  // literal/length symbols sorted by (length, symbol), low 8 bits of the first HOT ...
-            uint32_t hibits[9];    // ... and bit 8 of all 288 (end of block and the length symbols)
-        } s;
+        uint8_t nib[160];      // code lengths, two per byte: literal/length at 0..287, distance at 288..319
+        uint8_t sorted8[HOT];  // after construction: low 8 bits of the first HOT literal/length symbols sorted by (length, symbol)
     };
-    union {
-        int16_t lit_base[16];    // sorted index of the first code of a length minus that code: sym = sorted[base[l] + code]
-        uint8_t tmp[32];         // header: code-length code lengths / distance lengths on their way to nib[288..]
-    };
-    uint16_t next[16];           // construction scratch
+    // After construction, as 32-bit words indexed by code length l: low half = sorted index of the first code of length l
+    // minus that code (mod 2^16), high half = sorted index of the first symbol >= 256 of that length (within one length
+    // the symbols ascend, so "literal" is one compare): sym index = (lo + code) & 0xffff, literal iff index < hi.
+    // During construction: entries 0..15 are the builders' scratch, bytes 32..63 the header's staging area.
+    uint16_t lbn[32];
+    __device__ __forceinline__ uint8_t *tmp() { return reinterpret_cast<uint8_t *>(lbn + 16); }
     __device__ __forceinline__ uint32_t len_at(int i) const { return (nib[i >> 1] >> ((i & 1) * 4)) & 15u; }
     __device__ __forceinline__ void set_len(int i, uint32_t v) {
         const uint32_t b = nib[i >> 1];
         nib[i >> 1] = (uint8_t)((i & 1) ? ((b & 0x0fu) | (v << 4)) : ((b & 0xf0u) | v));
     }
 };
+static_assert(HOT <= 160, "sorted8 lives on the parked code lengths");
 // per-lane global scratch row: code construction output and the rarely used codes
 struct TiScratch {
     uint16_t lit_sorted[288];
@@ -209,17 +208,18 @@ struct Out {
 // index of the first code of length l minus that code, sorted[] = symbols by (length, symbol).  All loops have fixed trip
 // counts (NMAX) and `active` lanes are merely predicated, so the warp stays converged through the call.
 // Returns 0 ok, 1 over-subscribed, 2 incomplete (zlib's inflate_table rules decide what that means); *max_len too.
-template <int NMAX, typename LenAt>
+template <int NMAX, int STRIDE, typename LenAt>
 __device__ __forceinline__ int build_code(bool active, LenAt lens, int n, uint16_t *lim, int16_t *base, uint16_t *next,
                                           uint16_t *sorted, int *max_len) {
+    // base[l * STRIDE], next[l * STRIDE]: the literal/length code interleaves the two (TiSmem::lbn)
     if (active) {
 #pragma unroll
-        for (int l = 0; l < 16; ++l) next[l] = 0;  // used as the per-length count first
+        for (int l = 0; l < 16; ++l) next[l * STRIDE] = 0;  // used as the per-length count first
     }
     for (int s = 0; s < NMAX; ++s) {
         if (active && s < n) {
             const int l = (int)lens(s);
-            if (l) ++next[l];
+            if (l) ++next[l * STRIDE];
         }
     }
     int left = 1, status = 0, maxl = 0;
@@ -227,14 +227,14 @@ __device__ __forceinline__ int build_code(bool active, LenAt lens, int n, uint16
         uint32_t code = 0, at = 0;
 #pragma unroll
         for (int l = 1; l <= 15; ++l) {
-            const uint32_t c = next[l];
+            const uint32_t c = next[l * STRIDE];
             left <<= 1;
             left -= (int)c;
             if (left < 0) status = 1;
             if (c) maxl = l;
-            base[l] = (int16_t)((int)at - (int)code);
+            base[l * STRIDE] = (int16_t)((int)at - (int)code);
             lim[l] = (uint16_t)min((code + c) << (15 - l), 0xffffu);
-            next[l] = (uint16_t)at;
+            next[l * STRIDE] = (uint16_t)at;
             at += c;
             code = (code + c) << 1;
         }
@@ -243,7 +243,7 @@ __device__ __forceinline__ int build_code(bool active, LenAt lens, int n, uint16
     for (int s = 0; s < NMAX; ++s) {
         if (active && status != 1 && s < n) {
             const int l = (int)lens(s);
-            if (l) sorted[next[l]++] = (uint16_t)s;
+            if (l) sorted[next[l * STRIDE]++] = (uint16_t)s;
         }
     }
     *max_len = maxl;
@@ -393,12 +393,12 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                                 in.drop(3);
                             }
                         }
-                        sm.tmp[c_cl_order[i]] = (uint8_t)v;
+                        sm.tmp()[c_cl_order[i]] = (uint8_t)v;
                     }
                 }
                 int cl_max = 0;
                 // "invalid code lengths set": the code-length code must be complete (inftrees.c, type CODES)
-                if (build_code<19>(dynamic, [&](int q) { return (uint32_t)sm.tmp[q]; }, 19, sc.aux_lim, sc.aux_base, sm.next,
+                if (build_code<19, 1>(dynamic, [&](int q) { return (uint32_t)sm.tmp()[q]; }, 19, sc.aux_lim, sc.aux_base, sm.lbn,
                                    sc.aux_sorted, &cl_max) != 0 && dynamic) {
                     end_kind = END_ERR;
                     dynamic = false;
@@ -470,82 +470,105 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                     dynamic = false;
                 }
                 for (int s = 0; s < 32; ++s) {
-                    if (dynamic) sm.tmp[s] = s < hdist ? (uint8_t)sm.len_at(hlit + s) : (uint8_t)0;
+                    if (dynamic) sm.tmp()[s] = s < hdist ? (uint8_t)sm.len_at(hlit + s) : (uint8_t)0;
                 }
                 for (int s = 0; s < 32; ++s) {
-                    if (dynamic) sm.set_len(288 + s, sm.tmp[s]);
+                    if (dynamic) sm.set_len(288 + s, sm.tmp()[s]);
                 }
                 if (dynamic) tables = true;
             }
             if (__any_sync(FULL, tables)) {
                 // ---- phase 5: the two codes of the block
                 int maxl = 0;
-                int st = build_code<32>(tables, [&](int q) { return sm.len_at(288 + q); }, hdist, sc.aux_lim, sc.aux_base, sm.next,
+                int st = build_code<32, 1>(tables, [&](int q) { return sm.len_at(288 + q); }, hdist, sc.aux_lim, sc.aux_base, sm.lbn,
                                         sc.aux_sorted, &maxl);
                 if (tables && (st == 1 || (st == 2 && maxl > 1))) {  // "invalid distances set"
                     end_kind = END_ERR;
                     tables = false;
                 }
                 dist_max = maxl;
-                st = build_code<288>(tables, [&](int q) { return sm.len_at(q); }, hlit, sc.lit_lim, sm.lit_base, sm.next,
-                                     sc.lit_sorted, &maxl);
+                st = build_code<288, 2>(tables, [&](int q) { return sm.len_at(q); }, hlit, sc.lit_lim,
+                                        reinterpret_cast<int16_t *>(sm.lbn), sm.lbn + 1, sc.lit_sorted, &maxl);
                 // inftrees.c: over-subscribed never; incomplete only for a single 1-bit code
                 if (tables && (st == 1 || (st == 2 && maxl != 1))) {  // "invalid literal/lengths set"
                     end_kind = END_ERR;
                     tables = false;
                 }
-                // the sorted symbols move next to the decoder: low bytes and a bit mask for bit 8
-                for (int q = 0; q < 9; ++q) {
-                    uint32_t hi = 0;
-                    for (int k = 0; k < 32; ++k) {
-                        const int i = q * 32 + k;
-                        if (tables) {
-                            const uint32_t v = sc.lit_sorted[i];
-                            if (i < HOT) sm.s.sorted8[i] = (uint8_t)v;   // (the code lengths parked here are done with)
-                            hi |= ((v >> 8) & 1u) << k;
-                        }
+                // lbn[2l + 1] is now the end of length l's symbols; stepping back over its symbols >= 256 (end of block, the
+                // match lengths) leaves the index of the first of them
+                for (int q = 256; q < 288; ++q) {
+                    if (tables && q < hlit) {
+                        const uint32_t l = sm.len_at(q);
+                        if (l) --sm.lbn[2 * l + 1];
                     }
-                    if (tables) sm.s.hibits[q] = hi;
+                }
+                // the frequent symbols move next to the decoder (the code lengths parked on these bytes are done with)
+                for (int i = 0; i < HOT; i += 2) {
+                    if (tables) {
+                        const uint32_t v = *reinterpret_cast<const uint32_t *>(&sc.lit_sorted[i]);
+                        *reinterpret_cast<uint16_t *>(&sm.sorted8[i]) = (uint16_t)__byte_perm(v, 0u, 0x4420);
+                    }
                 }
                 if (tables) {
-                    L1 = sc.lit_lim[1], L2 = sc.lit_lim[2], L3 = sc.lit_lim[3], L4 = sc.lit_lim[4], L5 = sc.lit_lim[5];
-                    L6 = sc.lit_lim[6], L7 = sc.lit_lim[7], L8 = sc.lit_lim[8], L9 = sc.lit_lim[9], L10 = sc.lit_lim[10];
-                    L11 = sc.lit_lim[11], L12 = sc.lit_lim[12], L13 = sc.lit_lim[13], L14 = sc.lit_lim[14], L15 = sc.lit_lim[15];
+                    // limit of length l, left-aligned to 15 bits, with l in the low 4 bits: one register names both
+                    L1 = sc.lit_lim[1] << 4 | 1u, L2 = sc.lit_lim[2] << 4 | 2u, L3 = sc.lit_lim[3] << 4 | 3u;
+                    L4 = sc.lit_lim[4] << 4 | 4u, L5 = sc.lit_lim[5] << 4 | 5u, L6 = sc.lit_lim[6] << 4 | 6u;
+                    L7 = sc.lit_lim[7] << 4 | 7u, L8 = sc.lit_lim[8] << 4 | 8u, L9 = sc.lit_lim[9] << 4 | 9u;
+                    L10 = sc.lit_lim[10] << 4 | 10u, L11 = sc.lit_lim[11] << 4 | 11u, L12 = sc.lit_lim[12] << 4 | 12u;
+                    L13 = sc.lit_lim[13] << 4 | 13u, L14 = sc.lit_lim[14] << 4 | 14u, L15 = sc.lit_lim[15] << 4 | 15u;
                     state = ST_SYM;
                 }
             }
             __syncwarp();
             // ================= symbols: one step per lane and iteration until every lane has left its block =================
             uint32_t iter = 0;
+            const uint32_t *lbn32 = reinterpret_cast<const uint32_t *>(sm.lbn);
+            // cq = the next 15 stream bits, MSB first, << 4 | 15 (compares like the bare 15 bits against limit << 4 | length)
+            auto lit_len = [&](uint32_t cq) -> uint32_t {
+                const bool s8 = cq >= L8;
+                const bool s4 = cq >= (s8 ? L12 : L4);
+                const bool s2 = cq >= (s8 ? (s4 ? L14 : L10) : (s4 ? L6 : L2));
+                const uint32_t m1 = s8 ? (s4 ? (s2 ? L15 : L13) : (s2 ? L11 : L9)) : (s4 ? (s2 ? L7 : L5) : (s2 ? L3 : L1));
+                return (m1 & 15u) + (cq >= m1 ? 1u : 0u);
+            };
             while (__any_sync(FULL, state >= ST_SYM)) {
                 if (state == ST_SYM) {
-                    // canonical decode: count the limits <= the next 15 bits (binary search over registers)
-                    const uint32_t c = __brev(in.peek32()) >> 17;
-                    const bool s8 = c >= L8;
-                    const bool s4 = c >= (s8 ? L12 : L4);
-                    const bool s2 = c >= (s8 ? (s4 ? L14 : L10) : (s4 ? L6 : L2));
-                    const uint32_t m1 = s8 ? (s4 ? (s2 ? L15 : L13) : (s2 ? L11 : L9)) : (s4 ? (s2 ? L7 : L5) : (s2 ? L3 : L1));
-                    const uint32_t l = 1u + (s8 ? 8u : 0u) + (s4 ? 4u : 0u) + (s2 ? 2u : 0u) + (c >= m1 ? 1u : 0u);
+                    // canonical decode: find the first limit above the next 15 bits (binary search over registers; the
+                    // register found carries its length)
+                    const uint32_t w32 = in.peek32();
+                    uint32_t l = lit_len((__brev(w32) >> 13) | 15u);
                     if (l > 15u || l > in.avail) {
                         // no such code ("invalid literal/length code" when 15 bits were there), or the stream ends inside it
                         end_kind = (l > 15u && in.avail >= 15u) ? END_ERR : END_TRUNC;
                         state = ST_DONE;
                     } else {
-                        const uint32_t si = (uint32_t)(sm.lit_base[l] + (int)(c >> (15u - l)));
-                        const uint32_t lo8 = si < (uint32_t)HOT ? (uint32_t)sm.s.sorted8[si] : (uint32_t)(sc.lit_sorted[si] & 0xffu);
-                        const int sym = (int)(lo8 | (((sm.s.hibits[si >> 5] >> (si & 31u)) & 1u) << 8));
-                        in.drop(l);
-                        if (sym < 256) {
-                            out.put((uint32_t)sym);
-                        } else if (sym == 256) {
+                        const uint32_t lw = lbn32[l];
+                        const uint32_t si = (lw + (__brev(w32) >> (32u - l))) & 0xffffu;
+                        const uint32_t lo8 = si < (uint32_t)HOT ? (uint32_t)sm.sorted8[si] : (uint32_t)(sc.lit_sorted[si] & 0xffu);
+                        if (si < (lw >> 16)) {
+                            // a literal -- and, most of the time, another one behind it: the 32-bit window holds two codes,
+                            // so the second is decoded on the spot (anything else is left for the next iteration)
+                            out.put(lo8);
+                            const uint32_t r2 = __brev(w32 >> l);
+                            const uint32_t l2 = lit_len((r2 >> 13) | 15u);
+                            if (l2 <= 15u && l + l2 <= in.avail) {
+                                const uint32_t lw2 = lbn32[l2];
+                                const uint32_t si2 = (lw2 + (r2 >> (32u - l2))) & 0xffffu;
+                                if (si2 < (lw2 >> 16)) {
+                                    out.put(si2 < (uint32_t)HOT ? (uint32_t)sm.sorted8[si2] : (uint32_t)(sc.lit_sorted[si2] & 0xffu));
+                                    l += l2;
+                                }
+                            }
+                            in.drop(l);
+                        } else if (in.drop(l), lo8 == 0u) {  // symbol 256
                             state = ST_BLOCK;
-                        } else if (sym > 285) {  // "invalid literal/length code"
+                        } else if (lo8 > 29u) {  // symbols 286, 287: "invalid literal/length code"
                             end_kind = END_ERR;
                             state = ST_DONE;
                         } else {
                             // length / distance pair.  A pair cut by the end of the input ends the stream before it (the bytes
                             // decoded so far are the result), so nothing needs undoing.
-                            const uint32_t li = (uint32_t)sym - 257u;
+                            const uint32_t li = lo8 - 1u;
                             const uint32_t lx = c_len_extra[li];
                             int bad = -1;
                             uint32_t mlen = 0, dist = 0;

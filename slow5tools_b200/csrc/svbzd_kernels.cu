@@ -416,8 +416,6 @@ struct DecState {
     uint32_t pos;           // data bytes consumed
     uint32_t acc;           // running sum, prev = 0 (slow5_press.c:1162)
     uint32_t nkeys;
-    uint32_t k0, k1;        // per lane: the two control bytes of the coming iteration (combined at use, so
-                            // the loads have a whole iteration to land)
 };
 
 __device__ __forceinline__ void dec_issue_block(DecState &s, uint32_t bar0, uint32_t ring0, const int lane) {
@@ -448,86 +446,153 @@ __device__ __forceinline__ void dec_wait_blocks(DecState &s, const uint32_t need
     }
 }
 
-// selector of the PRMT that widens two adjacent stream values (1 or 2 bytes each) out of a 4-byte window into
-// one packed pair (value a in the low half, value b in the high half); q = (a is 2 bytes) + 4 * (b is 2 bytes).
-// Result bytes: [w0, a2 ? w1 : 0, w[1+a2], b2 ? w[2+a2] : 0]; selector nibbles 4..7 address the zero operand.
-//   q=0: 0x6150   q=1: 0x7210   q=4: 0x2150   q=5: 0x3210      (looked up bytewise by a PRMT over the 8-byte table)
-// (raw prmt: the __byte_perm intrinsic would spend an extra AND on masking every run-time selector)
+// raw prmt: the __byte_perm intrinsic would spend an extra AND on masking every run-time selector
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
-__device__ __forceinline__ uint32_t pair_selector(uint32_t q) {
-    return prmt(0x72611050u, 0x32211050u, q * 0x11u + 0x20u);
+
+// Widening table of the common path, one entry per control byte whose four values are 1 or 2 bytes long (flag of value j at
+// bit 2j).  The four values sit in an 8-byte window (a, b):
+//   x, y  PRMT selectors that pull values (0, 1) / (2, 3) out of the window as packed pairs, two bytes each (the byte after a
+//         1-byte value comes along and is masked away below);
+//   z, w  per pair, 0x7fff in every half whose value has 2 bytes and 0x007f otherwise: the AND mask of the zigzag decode's
+//         ">> 1", which is where the stray byte disappears at no cost.
+__device__ __forceinline__ uint4 dec_lut_entry(uint32_t k) {
+    const uint32_t f0 = k & 1u, f1 = (k >> 2) & 1u, f2 = (k >> 4) & 1u, f3 = (k >> 6) & 1u;
+    const uint32_t o1 = 1 + f0, o2 = o1 + 1 + f1, o3 = o2 + 1 + f2;
+    uint4 e;
+    e.x = 0u | (1u << 4) | (o1 << 8) | ((o1 + 1) << 12);
+    e.y = o2 | ((o2 + 1) << 4) | (o3 << 8) | (((o3 + 1) & 7u) << 12);
+    e.z = (f0 ? 0x7fffu : 0x007fu) | ((f1 ? 0x7fffu : 0x007fu) << 16);
+    e.w = (f2 ? 0x7fffu : 0x007fu) | ((f3 ? 0x7fffu : 0x007fu) << 16);
+    return e;
 }
-// packed zigzag decode of two 16-bit values (exact mod 2^16, which is all the truncating int16 store keeps)
-__device__ __forceinline__ uint32_t zz_dec2(uint32_t p) {
+// packed zigzag decode of two 16-bit values (exact mod 2^16, which is all the truncating int16 store keeps); `keep` as above
+__device__ __forceinline__ uint32_t zz_dec2(uint32_t p, uint32_t keep) {
     const uint32_t m = (p & 0x00010001u) * 0xFFFFu;  // 0xFFFF in every half whose value is odd
-    return ((p >> 1) & 0x7FFF7FFFu) ^ m;
+    return ((p >> 1) & keep) ^ m;
 }
 
-// One 256-sample iteration; lane owns values 8*lane .. 8*lane+7.  Returns false when the control bytes
-// claim more data than the stream holds.
-template <bool PARTIAL>
-__device__ __forceinline__ bool dec_iteration(DecState &s, uint8_t *ring, const uint8_t *knext, const bool guard,
-                                              const uint32_t next_ki, int16_t *o, const int nvalid, const int lane,
-                                              uint32_t &phase_bits, const uint32_t bar0, const uint32_t ring0) {
-    const uint32_t k_now = s.k0 | (s.k1 << 8);
-    if (!PARTIAL) {  // prefetch the next iteration's control bytes (the last iteration has no successor)
-        if (!guard) {
-            s.k0 = __ldg(knext);
-            s.k1 = __ldg(knext + 1);
-        } else {
-            s.k0 = s.k1 = 0;
-            if (next_ki < s.nkeys) s.k0 = __ldg(knext);
-            if (next_ki + 1 < s.nkeys) s.k1 = __ldg(knext + 1);
-        }
+// inclusive warp scan of two independent 16-bit lanes per register (sums mod 2^16)
+__device__ __forceinline__ uint32_t warp_incl_scan_16x2(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t;
+        int p;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "shfl.sync.up.b32 %0|p, %2, %3, 0, 0xffffffff;\n\t"
+            "selp.s32 %1, 1, 0, p;\n\t}"
+            : "=r"(t), "=r"(p)
+            : "r"(v), "r"(d));
+        if (p) v = __vadd2(v, t);  // (folds into a predicated VIADD.16x2)
     }
+    return v;
+}
+
+// Eight values of one lane, all 1 or 2 bytes long: the lane's 8..16 data bytes start at ring position ri; k0 / k1 are its two
+// control bytes.  Returns the lane-local inclusive prefix sums of the zigzag-decoded values, two per register (mod 2^16).
+__device__ __forceinline__ void dec_unpack8(const uint8_t *ring, const uint4 *lut, const uint32_t ri, const uint32_t k0,
+                                            const uint32_t k1, const uint32_t sh4, uint32_t (&s)[4]) {
+    // realigned into four registers (five aligned word loads + funnel shifts)
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(ring) + (ri >> 2);
+    const uint32_t sh = (ri & 3u) * 8;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+    const uint4 e0 = lut[k0], e1 = lut[k1];
+    const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
+    const uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
+    // values 4..7 start at byte 4 + (2-byte values among 0..3); sh4 = 8 x that count
+    const uint32_t c0 = __funnelshift_rc(a1, a2, sh4), c1 = __funnelshift_rc(a2, a3, sh4);
+    // zigzag decode + running sum, two 16-bit lanes per register (streamvbyte_zigzag.c:23-25,34-40)
+    // x * 0x10001 = (lo, lo + hi): the pair's own prefix; the carry-in from the left is added per half
+    s[0] = zz_dec2(prmt(a0, a1, e0.x), e0.z) * 0x10001u;  // (d0, d0 + d1)
+    s[1] = __vadd2(zz_dec2(prmt(a0, a1, e0.y), e0.w) * 0x10001u, __byte_perm(s[0], 0u, 0x3232));
+    s[2] = __vadd2(zz_dec2(prmt(c0, c1, e1.x), e1.z) * 0x10001u, __byte_perm(s[1], 0u, 0x3232));
+    s[3] = __vadd2(zz_dec2(prmt(c0, c1, e1.y), e1.w) * 0x10001u, __byte_perm(s[2], 0u, 0x3232));
+}
+
+// after an iteration: every lane is done with the ring bytes it consumed, their blocks can be refilled
+__device__ __forceinline__ void dec_recycle(DecState &s, const uint32_t bar0, const uint32_t ring0, const int lane) {
+    __syncwarp();
+    const uint32_t done_blocks = (s.skew + s.pos) / DEC_BLK;
+    while (s.issued < s.nblk && s.issued < done_blocks + DEC_NB) dec_issue_block(s, bar0, ring0, lane);
+}
+
+// 512 samples, the common path twice over ("A": values 8*lane.. of the first 256, "B": the same of the second 256): one scan
+// over both halves' data lengths, one over both halves' sums.  ka / kb: the lane's control bytes (k0 | k1 << 8) of A / B, all
+// 2-bit codes <= 1.  Returns false when the control bytes claim more data than the stream holds.
+__device__ __forceinline__ bool dec_iteration512(DecState &s, uint8_t *ring, const uint4 *lut, const uint32_t ka,
+                                                 const uint32_t kb, int16_t *o, const int lane, uint32_t &phase_bits,
+                                                 const uint32_t bar0, const uint32_t ring0) {
+    const uint32_t ka0 = ka & 0xffu, ka1 = ka >> 8, kb0 = kb & 0xffu, kb1 = kb >> 8;
+    const uint32_t pa0 = __popc(ka0), pb0 = __popc(kb0);
+    const uint32_t len_a = 8 + pa0 + __popc(ka1), len_b = 8 + pb0 + __popc(kb1);
+    const uint32_t lens = len_a | (len_b << 16);                // a warp's half is <= 512 bytes
+    const uint32_t incl = warp_incl_scan(lens);                  // prefix scan over the control-byte lengths -> data offsets
+    const uint32_t tot = __shfl_sync(FULL, incl, 31);
+    const uint32_t tot_a = tot & 0xffffu, total = tot_a + (tot >> 16);
+    if (s.pos + total > s.D) return false;  // stream claims more data than it holds: never gather past it
+    dec_wait_blocks(s, (s.skew + s.pos + total + DEC_BLK - 1) / DEC_BLK, ring, phase_bits, bar0, lane);
+    const uint32_t excl = incl - lens;
+    const uint32_t at = s.skew + s.pos;
+    uint32_t sa[4], sb[4];
+    dec_unpack8(ring, lut, (at + (excl & 0xffffu)) & (DEC_RING - 1), ka0, ka1, pa0 * 8, sa);
+    dec_unpack8(ring, lut, (at + tot_a + (excl >> 16)) & (DEC_RING - 1), kb0, kb1, pb0 * 8, sb);
+    // the lanes' totals (mod 2^16), scanned for both halves at once
+    const uint32_t runs = __byte_perm(sa[3], sb[3], 0x7632);
+    const uint32_t incl_sum = warp_incl_scan_16x2(runs);
+    const uint32_t tots = __shfl_sync(FULL, incl_sum, 31);
+    // carry-in: A starts from the running sum, B from the running sum plus all of A
+    const uint32_t carry = (s.acc & 0xffffu) | ((s.acc + tots) << 16);
+    const uint32_t base = __vadd2(__vsub2(incl_sum, runs), carry);
+    s.acc += (tots & 0xffffu) + (tots >> 16);
+    const uint32_t base_a = __byte_perm(base, 0u, 0x1010), base_b = __byte_perm(base, 0u, 0x3232);
+    uint4 va, vb;
+    va.x = __vadd2(sa[0], base_a);
+    va.y = __vadd2(sa[1], base_a);
+    va.z = __vadd2(sa[2], base_a);
+    va.w = __vadd2(sa[3], base_a);
+    vb.x = __vadd2(sb[0], base_b);
+    vb.y = __vadd2(sb[1], base_b);
+    vb.z = __vadd2(sb[2], base_b);
+    vb.w = __vadd2(sb[3], base_b);
+    *reinterpret_cast<uint4 *>(o) = va;
+    *reinterpret_cast<uint4 *>(o + 256) = vb;
+    s.pos += total;
+    dec_recycle(s, bar0, ring0, lane);
+    return true;
+}
+
+// One 256-sample iteration; lane owns values 8*lane .. 8*lane+7 with control bytes k_now (k0 | k1 << 8).  Returns false when
+// the control bytes claim more data than the stream holds.
+template <bool PARTIAL>
+__device__ __forceinline__ bool dec_iteration(DecState &s, uint8_t *ring, const uint4 *lut, const uint32_t k_now, int16_t *o,
+                                              const int nvalid, const int lane, uint32_t &phase_bits, const uint32_t bar0,
+                                              const uint32_t ring0) {
     const bool wide = __any_sync(FULL, (k_now & 0xAAAAu) != 0);
     if (!PARTIAL && !wide) {
-        // ---- common path: every value of the iteration is 1 or 2 bytes; k_now holds one flag per value at bit 2j
-        const uint32_t lane_len = 8 + __popc(k_now);
-        const uint32_t incl = warp_incl_scan(lane_len);  // prefix scan over the control-byte lengths -> data offsets
+        // ---- common path: every value of the iteration is 1 or 2 bytes
+        const uint32_t k0 = k_now & 0xffu, k1 = k_now >> 8;
+        const uint32_t p0 = __popc(k0);
+        const uint32_t lane_len = 8 + p0 + __popc(k1);
+        const uint32_t incl = warp_incl_scan(lane_len);
         const uint32_t total = __shfl_sync(FULL, incl, 31);
-        if (s.pos + total > s.D) return false;  // stream claims more data than it holds: never gather past it
+        if (s.pos + total > s.D) return false;
         dec_wait_blocks(s, (s.skew + s.pos + total + DEC_BLK - 1) / DEC_BLK, ring, phase_bits, bar0, lane);
-        const uint32_t ri = (s.skew + s.pos + incl - lane_len) & (DEC_RING - 1);
-        // the lane's 8..16 bytes, realigned into four registers (five aligned word loads + funnel shifts)
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(ring) + (ri >> 2);
-        const uint32_t sh = (ri & 3u) * 8;
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
-        const uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
-        const uint32_t kf = k_now;  // flags at bits 0,2,..,14
-        // values 0..3 sit in bytes [0, 8) = (a0, a1); values 4..7 start at byte 4 + (2-byte values among 0..3)
-        const uint32_t o2 = 2 + (kf & 1u) + ((kf >> 2) & 1u);  // byte offset of value 2
-        const uint32_t o4 = __popc(kf & 0x55u);                // byte offset of value 4, minus 4
-        const uint32_t c0 = __funnelshift_rc(a1, a2, o4 * 8), c1 = __funnelshift_rc(a2, a3, o4 * 8);
-        const uint32_t o6 = 2 + ((kf >> 8) & 1u) + ((kf >> 10) & 1u);  // value 6 relative to value 4
-        const uint32_t t1 = __funnelshift_rc(a0, a1, o2 * 8);
-        const uint32_t t3 = __funnelshift_rc(c0, c1, o6 * 8);
-        const uint32_t p0 = prmt(a0, 0u, pair_selector(kf & 5u));
-        const uint32_t p1 = prmt(t1, 0u, pair_selector((kf >> 4) & 5u));
-        const uint32_t p2 = prmt(c0, 0u, pair_selector((kf >> 8) & 5u));
-        const uint32_t p3 = prmt(t3, 0u, pair_selector((kf >> 12) & 5u));
-        // zigzag decode + running sum, two 16-bit lanes per register (streamvbyte_zigzag.c:23-25,34-40)
-        // x * 0x10001 = (lo, lo + hi): the pair's own prefix; the carry-in from the left is added per half
-        // (a plain 32-bit add would leak the low half's carry into the high half)
-        const uint32_t s0 = zz_dec2(p0) * 0x10001u;  // (d0, d0 + d1)
-        const uint32_t s1 = __vadd2(zz_dec2(p1) * 0x10001u, __byte_perm(s0, 0u, 0x3232));
-        const uint32_t s2 = __vadd2(zz_dec2(p2) * 0x10001u, __byte_perm(s1, 0u, 0x3232));
-        const uint32_t s3 = __vadd2(zz_dec2(p3) * 0x10001u, __byte_perm(s2, 0u, 0x3232));
-        const uint32_t run = s3 >> 16;  // the lane's total (mod 2^16)
+        uint32_t sv[4];
+        dec_unpack8(ring, lut, (s.skew + s.pos + incl - lane_len) & (DEC_RING - 1), k0, k1, p0 * 8, sv);
+        const uint32_t run = sv[3] >> 16;  // the lane's total (mod 2^16)
         const uint32_t incl_sum = warp_incl_scan(run);
         const uint32_t base = (s.acc + incl_sum - run) & 0xFFFFu;
         s.acc += __shfl_sync(FULL, incl_sum, 31);
         const uint32_t base2 = base * 0x10001u;
         uint4 wv;
-        wv.x = __vadd2(s0, base2);
-        wv.y = __vadd2(s1, base2);
-        wv.z = __vadd2(s2, base2);
-        wv.w = __vadd2(s3, base2);
+        wv.x = __vadd2(sv[0], base2);
+        wv.y = __vadd2(sv[1], base2);
+        wv.z = __vadd2(sv[2], base2);
+        wv.w = __vadd2(sv[3], base2);
         *reinterpret_cast<uint4 *>(o) = wv;
         s.pos += total;
     } else {
@@ -584,23 +649,37 @@ __device__ __forceinline__ bool dec_iteration(DecState &s, uint8_t *ring, const 
         }
         s.pos += total;
     }
-    __syncwarp();  // all lanes have finished reading the ring before blocks are recycled
-    const uint32_t done_blocks = (s.skew + s.pos) / DEC_BLK;
-    while (s.issued < s.nblk && s.issued < done_blocks + DEC_NB) dec_issue_block(s, bar0, ring0, lane);
+    dec_recycle(s, bar0, ring0, lane);
     return true;
+}
+
+// the lane's two control bytes of a 256-sample group (k0 | k1 << 8): kp points at the first of them, ki is its index in the
+// control bytes; positions past the last control byte read as 0
+__device__ __forceinline__ uint32_t dec_load_keys(const uint8_t *kp, const uint32_t ki, const uint32_t nkeys, const bool guard) {
+    uint32_t k0 = 0, k1 = 0;
+    if (!guard) {
+        k0 = __ldg(kp);
+        k1 = __ldg(kp + 1);
+    } else {
+        if (ki < nkeys) k0 = __ldg(kp);
+        if (ki + 1 < nkeys) k1 = __ldg(kp + 1);
+    }
+    return k0 | (k1 << 8);
 }
 
 __global__ void __launch_bounds__(DEC_WARPS * 32, S5B_DEC_MIN_CTAS) svbzd_decode_kernel(const SvbDecodeArgs a) {
     __shared__ DecWarpSmem smem[DEC_WARPS];
+    __shared__ uint4 lut[256];
     const int lane = threadIdx.x & 31;
     DecWarpSmem &ws = smem[threadIdx.x >> 5];
     const uint32_t bar0 = smem_u32(&ws.bar[0]);
     const uint32_t ring0 = smem_u32(&ws.ring[0]);
+    for (uint32_t k = threadIdx.x; k < 256; k += DEC_WARPS * 32) lut[k] = dec_lut_entry(k);
     if (lane == 0) {
         for (int s = 0; s < DEC_NB; ++s) mbar_init(bar0 + 8 * s, 1);
         mbar_fence_init();
     }
-    __syncwarp();
+    __syncthreads();
     uint32_t phase_bits = 0;  // per ring slot: parity of the next completion to wait for
 
     for (;;) {
@@ -652,27 +731,39 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, S5B_DEC_MIN_CTAS) svbzd_decode
         while (s.issued < s.nblk && s.issued < DEC_NB) dec_issue_block(s, bar0, ring0, lane);
 
         int16_t *out = a.sig + soff + lane * 8;
-        // control bytes of the first iteration
-        s.k0 = s.k1 = 0;
-        {
-            const uint32_t ki = 2 * lane;
-            if (ki < nkeys) s.k0 = __ldg(keys + ki);
-            if (ki + 1 < nkeys) s.k1 = __ldg(keys + ki + 1);
-        }
-        const uint32_t full_iters = n >> 8;
-        const int tail = (int)(n & 255u);
-        const uint8_t *kp = keys + 2 * lane + 64;  // this lane's control bytes of the NEXT iteration
+        // Control bytes are fetched one 512-sample step ahead (ka / kb: first / second 256 samples of the coming step), so
+        // the loads have a whole step to land; positions past the last control byte read as 0.
+        const uint32_t steps = n >> 9;
+        const uint8_t *kp = keys + 2 * lane;  // the lane's control bytes of the step being fetched
+        uint32_t ki = 2 * lane;
+        uint32_t ka = dec_load_keys(kp, ki, nkeys, true), kb = dec_load_keys(kp + 64, ki + 64, nkeys, true);
         bool ok = true;
-        for (uint32_t it = 0; it < full_iters; ++it) {
-            // unguarded prefetch only when the next iteration is a full one as well
-            const bool guard = it + 2 > full_iters;
-            ok = dec_iteration<false>(s, ws.ring, kp, guard, (it + 1) * 64 + 2 * lane, out, 256, lane, phase_bits, bar0,
-                                      ring0);
+        for (uint32_t it = 0; it < steps; ++it) {
+            const uint32_t ka_now = ka, kb_now = kb;
+            const bool guard = it + 2 > steps;  // unguarded only when the next step is a whole one as well
+            kp += 128;
+            ki += 128;
+            ka = dec_load_keys(kp, ki, nkeys, guard);
+            kb = dec_load_keys(kp + 64, ki + 64, nkeys, guard);
+            if (!__any_sync(FULL, ((ka_now | kb_now) & 0xAAAAu) != 0)) {
+                ok = dec_iteration512(s, ws.ring, lut, ka_now, kb_now, out, lane, phase_bits, bar0, ring0);
+            } else {
+                ok = dec_iteration<false>(s, ws.ring, lut, ka_now, out, 256, lane, phase_bits, bar0, ring0) &&
+                     dec_iteration<false>(s, ws.ring, lut, kb_now, out + 256, 256, lane, phase_bits, bar0, ring0);
+            }
             if (!ok) break;
-            kp += 64;
-            out += 256;
+            out += 512;
         }
-        if (ok && tail) ok = dec_iteration<true>(s, ws.ring, kp, true, 0, out, tail, lane, phase_bits, bar0, ring0);
+        if (ok) {
+            uint32_t rest = n & 511u;
+            if (rest >= 256) {
+                ok = dec_iteration<false>(s, ws.ring, lut, ka, out, 256, lane, phase_bits, bar0, ring0);
+                ka = kb;
+                out += 256;
+                rest -= 256;
+            }
+            if (ok && rest) ok = dec_iteration<true>(s, ws.ring, lut, ka, out, (int)rest, lane, phase_bits, bar0, ring0);
+        }
         // drain copies that were issued but never needed (only possible for a malformed stream)
         while (s.waited < s.issued) {
             const uint32_t slot = s.waited % DEC_NB;
