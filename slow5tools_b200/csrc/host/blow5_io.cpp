@@ -586,23 +586,62 @@ void record_to_binary(const Record &rec, const uint8_t *signal, uint64_t signal_
 }
 
 // ---- ASCII record parse (SLOW5 -> anything) --------------------------------------------------------
-static bool parse_prim(const std::string &tok, int type, uint8_t *dst) {
-    if (tok == ".") {  // missing value -> the type's NULL representation (slow5.h:139-150)
-        switch (type) {
-            case AUX_INT8: { int8_t v = INT8_MAX; memcpy(dst, &v, 1); return true; }
-            case AUX_INT16: { int16_t v = INT16_MAX; memcpy(dst, &v, 2); return true; }
-            case AUX_INT32: { int32_t v = INT32_MAX; memcpy(dst, &v, 4); return true; }
-            case AUX_INT64: { int64_t v = INT64_MAX; memcpy(dst, &v, 8); return true; }
-            case AUX_UINT8: case AUX_ENUM: { uint8_t v = UINT8_MAX; memcpy(dst, &v, 1); return true; }
-            case AUX_UINT16: { uint16_t v = UINT16_MAX; memcpy(dst, &v, 2); return true; }
-            case AUX_UINT32: { uint32_t v = UINT32_MAX; memcpy(dst, &v, 4); return true; }
-            case AUX_UINT64: { uint64_t v = UINT64_MAX; memcpy(dst, &v, 8); return true; }
-            case AUX_FLOAT: { float v = nanf(""); memcpy(dst, &v, 4); return true; }
-            case AUX_DOUBLE: { double v = nan(""); memcpy(dst, &v, 8); return true; }
-            case AUX_CHAR: { *dst = 0; return true; }
-        }
-        return false;
+bool aux_null_value(int type, uint8_t *dst) {  // the type's NULL representation (slow5.h:139-150)
+    switch (type) {
+        case AUX_INT8: { int8_t v = INT8_MAX; memcpy(dst, &v, 1); return true; }
+        case AUX_INT16: { int16_t v = INT16_MAX; memcpy(dst, &v, 2); return true; }
+        case AUX_INT32: { int32_t v = INT32_MAX; memcpy(dst, &v, 4); return true; }
+        case AUX_INT64: { int64_t v = INT64_MAX; memcpy(dst, &v, 8); return true; }
+        case AUX_UINT8: case AUX_ENUM: { uint8_t v = UINT8_MAX; memcpy(dst, &v, 1); return true; }
+        case AUX_UINT16: { uint16_t v = UINT16_MAX; memcpy(dst, &v, 2); return true; }
+        case AUX_UINT32: { uint32_t v = UINT32_MAX; memcpy(dst, &v, 4); return true; }
+        case AUX_UINT64: { uint64_t v = UINT64_MAX; memcpy(dst, &v, 8); return true; }
+        case AUX_FLOAT: { float v = nanf(""); memcpy(dst, &v, 4); return true; }
+        case AUX_DOUBLE: { double v = nan(""); memcpy(dst, &v, 8); return true; }
+        case AUX_CHAR: { *dst = 0; return true; }
     }
+    return false;
+}
+
+// The binary auxiliary section of a record laid out for another header: field p of `out` is field src_of_out[p] of `in`
+// (copied as stored), or, when that is < 0, the "missing" form slow5_rec_to_mem writes (slow5.c:3993-4044): the type's
+// NULL value for a primitive, a zero length for an array.
+bool aux_relayout(const uint8_t *aux, uint64_t n, const std::vector<AuxField> &in, const std::vector<AuxField> &out,
+                  const std::vector<int> &src_of_out, std::vector<uint8_t> &dst) {
+    std::vector<std::pair<uint64_t, uint64_t>> at(in.size());  // (offset, bytes) of every stored field
+    uint64_t pos = 0;
+    for (size_t f = 0; f < in.size(); ++f) {
+        uint64_t len = in[f].size;
+        if (in[f].is_array()) {
+            if (n - pos < 8) return false;
+            uint64_t cnt;
+            memcpy(&cnt, aux + pos, 8);
+            if (cnt > (n - pos - 8) / (in[f].size ? in[f].size : 1)) return false;
+            len = 8 + cnt * in[f].size;
+        }
+        if (n - pos < len) return false;
+        at[f] = {pos, len};
+        pos += len;
+    }
+    if (pos != n) return false;
+    dst.clear();
+    for (size_t p = 0; p < out.size(); ++p) {
+        const int f = src_of_out[p];
+        if (f >= 0) {
+            dst.insert(dst.end(), aux + at[f].first, aux + at[f].first + at[f].second);
+        } else if (out[p].is_array()) {
+            dst.insert(dst.end(), 8, 0);
+        } else {
+            uint8_t v[8] = {0};
+            if (!aux_null_value(out[p].type, v)) return false;
+            dst.insert(dst.end(), v, v + out[p].size);
+        }
+    }
+    return true;
+}
+
+static bool parse_prim(const std::string &tok, int type, uint8_t *dst) {
+    if (tok == ".") return aux_null_value(type, dst);  // missing value
     if (tok.empty()) return false;
     char *end = nullptr;
     errno = 0;

@@ -101,6 +101,11 @@ void record_to_ascii(const Record &rec, const Header &h, std::string &out, const
 void record_to_binary(const Record &rec, const uint8_t *signal, uint64_t signal_nbytes, bool signal_is_compressed,
                       std::vector<uint8_t> &out, uint64_t *signal_at);
 
+// auxiliary section of a record re-laid for another header (merge: union of the inputs' columns); see blow5_io.cpp
+bool aux_null_value(int type, uint8_t *dst);
+bool aux_relayout(const uint8_t *aux, uint64_t n, const std::vector<AuxField> &in, const std::vector<AuxField> &out,
+                  const std::vector<int> &src_of_out, std::vector<uint8_t> &dst);
+
 std::string double_to_str(double x);  // slow5_misc.c:379-406
 
 Fmt fmt_from_path(const char *path);   // by extension (src/misc.c:178-216)

@@ -21,11 +21,11 @@
 #include "../../../include/slow5b200.h"
 #include "blow5_io.hpp"
 
+#include "cli_common.hpp"
+
 using namespace s5b;
 
 int index_main(int argc, char **argv);
-int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::vector<uint8_t> &)> &next, FILE *fout,
-                    s5b_ctx_t *gpu, Fmt fmt_out, int rec_out, int sig_out, long batch, int threads);
 
 #define GET_ERROR(fmt, ...) fprintf(stderr, "[%s::ERROR]\033[1;31m " fmt "\033[0m\n", __func__, __VA_ARGS__)
 #define GET_WARNING(fmt, ...) fprintf(stderr, "[%s::WARNING]\033[1;33m " fmt "\033[0m\n", __func__, __VA_ARGS__)

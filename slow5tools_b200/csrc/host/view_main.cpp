@@ -33,6 +33,7 @@
 
 #include "../../../include/slow5b200.h"
 #include "blow5_io.hpp"
+#include "cli_common.hpp"
 
 using namespace s5b;
 
@@ -381,9 +382,11 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
 // without the newline) placed in the buffer, 0 = no more, -1 = error already reported -- are decompressed, parsed,
 // re-encoded for (fmt_out, rec_out, sig_out) with the codec calls batched on the GPU, and written to fout in order.
 int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::vector<uint8_t> &)> &next, FILE *fout,
-                    s5b_ctx_t *gpu, Fmt fmt_out, int rec_out, int sig_out, long batch, int threads) {
+                    s5b_ctx_t *gpu, Fmt fmt_out, int rec_out, int sig_out, long batch, int threads, const ConvertHooks *hooks) {
     int ret = 0;
     Batch b;
+    const Header &hdr_o = hooks && hooks->hdr_out ? *hooks->hdr_out : hdr;  // what the output records follow
+    auto dest = [&](size_t i) { return hooks && hooks->route ? hooks->route(i) : fout; };
     bool eof = false;
     while (!eof && ret == 0) {
         // ---- load (serial)
@@ -452,6 +455,11 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
             ERROR("%s", "a record could not be parsed");
             ret = 1;
             break;
+        }
+        if (hooks && hooks->transform) {
+            for (size_t i = 0; i < n && ret == 0; ++i)
+                if (!hooks->transform(i, b.rec[i], b.aux_store[i])) ret = 1;
+            if (ret) break;
         }
         // ---- signal decompression
         std::vector<const int16_t *> sig(n);
@@ -539,22 +547,22 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
                     if (r.sig_nbytes >= 9) memcpy(&ns, sb + 1, 8);
                 }
                 r.len_raw_signal = ns;
-                record_to_ascii(r, hdr, lines[i], text[i], text_n[i]);
+                record_to_ascii(r, hdr_o, lines[i], text[i], text_n[i]);
                 free(text[i]);
             });
             for (size_t i = 0; i < n && ret == 0; ++i)
-                if (fwrite(lines[i].data(), 1, lines[i].size(), fout) != lines[i].size()) ret = 1;
+                if (fwrite(lines[i].data(), 1, lines[i].size(), dest(i)) != lines[i].size()) ret = 1;
         } else if (fmt_out == FMT_ASCII) {
             std::vector<std::string> lines(n);
             parallel_for(n, threads, [&](size_t i) {
                 Record &r = b.rec[i];
                 r.raw_signal.resize(r.len_raw_signal);
                 if (r.len_raw_signal) memcpy(r.raw_signal.data(), sig[i], r.len_raw_signal * 2);
-                record_to_ascii(r, hdr, lines[i]);
+                record_to_ascii(r, hdr_o, lines[i]);
                 std::vector<int16_t>().swap(r.raw_signal);
             });
             for (size_t i = 0; i < n && ret == 0; ++i)
-                if (fwrite(lines[i].data(), 1, lines[i].size(), fout) != lines[i].size()) ret = 1;
+                if (fwrite(lines[i].data(), 1, lines[i].size(), dest(i)) != lines[i].size()) ret = 1;
         } else {
             // signal compression
             std::vector<void *> svb(n, nullptr);
@@ -610,7 +618,8 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
             for (size_t i = 0; i < n && ret == 0; ++i) {
                 const void *p = rec_packed ? z[i] : rec_mem[i].data();
                 const uint64_t sz = rec_packed ? z_n[i] : rec_mem[i].size();
-                if (fwrite(&sz, 8, 1, fout) != 1 || (sz && fwrite(p, 1, sz, fout) != sz)) ret = 1;  // slow5.c:4055-4060
+                FILE *fo = dest(i);
+                if (fwrite(&sz, 8, 1, fo) != 1 || (sz && fwrite(p, 1, sz, fo) != sz)) ret = 1;  // slow5.c:4055-4060
             }
             for (void *p : z) free(p);
         }
@@ -769,6 +778,8 @@ int view_main(int argc, char **argv) {
 
 int index_main(int argc, char **argv);  // index_main.cpp
 int get_main(int argc, char **argv);    // get_main.cpp
+int merge_main(int argc, char **argv);  // merge_split_main.cpp
+int split_main(int argc, char **argv);
 
 int main(int argc, char **argv) {
     if (argc >= 2 && (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V"))) {
@@ -776,7 +787,7 @@ int main(int argc, char **argv) {
         return 0;
     }
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
-        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n    index   create a SLOW5/BLOW5 index file\n    get     display the read entry for each specified read id\n");
+        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n    index   create a SLOW5/BLOW5 index file\n    get     display the read entry for each specified read id\n    merge   merge multiple SLOW5/BLOW5 files to a single file\n    split   split a SLOW5/BLOW5 file by read group, number of reads or number of files\n");
         return argc < 2 ? 1 : 0;
     }
     if (!strcmp(argv[1], "get")) {
@@ -795,6 +806,14 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
+    if (!strcmp(argv[1], "merge") || !strcmp(argv[1], "split")) {
+        const int rc = argv[1][0] == 'm' ? merge_main(argc - 1, argv + 1) : split_main(argc - 1, argv + 1);
+        if (rc != 0) {
+            fprintf(stderr, "[main::ERROR] %s failed\n", argv[1]);
+            return EXIT_FAILURE;
+        }
+        return 0;
+    }
     if (!strcmp(argv[1], "view")) {
         const int rc = view_main(argc - 1, argv + 1);
         if (rc != 0) {
@@ -803,6 +822,6 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
-    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view, index, get)\n", argv[1]);
+    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view, index, get, merge, split)\n", argv[1]);
     return EXIT_FAILURE;
 }

@@ -89,6 +89,7 @@ struct StageScope {
         if (!ctx->timer.enabled) return;
         a = take();
         b = take();
+        if (ctx->timer.isolate) cudaStreamSynchronize(st);  // dev: stage boundaries with an idle GPU on both sides
         if (a && b) cudaEventRecord(a, st);
     }
     cudaEvent_t take() {
@@ -105,6 +106,7 @@ struct StageScope {
     ~StageScope() {
         if (!a || !b) return;
         cudaEventRecord(b, st);
+        if (ctx->timer.isolate) cudaStreamSynchronize(st);
         ctx->timer.marks.push_back({a, b, stage});
     }
 };
@@ -274,7 +276,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
             ctx->launches += 2;
             st_sdec = d_st_sdec;
         } else {
-            StageScope ts(ctx, st, ST_SIG_DEPRESS);
+            StageScope ts(ctx, st, ST_SIG_EXTRACT);
             CU(launch_sig_extract(cur, cur_off, ra, n, static_cast<int16_t *>(L.sig.p), d_sig_off, st));
             ctx->launches += 1;
         }
@@ -396,7 +398,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
         } else {
             CU(launch_image_gather(fin, fin_off, fin_len, n, img, d_img_off, st, base_ptr, L.d_res, abs));
         }
-        ctx->launches += 3;
+        ctx->launches += 4;
         if (j.dst_dev) {
             CU(launch_recode_advance(ctx->d_img_base, L.d_res, j.d_acc, st));
             ctx->launches += 1;
@@ -620,6 +622,7 @@ void *s5b_ctx_recode_stream(s5b_ctx_t *ctx) {
 int s5b_ctx_stage_timing(s5b_ctx_t *ctx, int enable) {
     if (!ctx) return S5B_ERR_ARG;
     ctx->timer.enabled = enable != 0;
+    ctx->timer.isolate = getenv("S5B_STAGE_ISOLATE") != nullptr;
     return S5B_OK;
 }
 
@@ -652,7 +655,7 @@ int s5b_ctx_stage_report(s5b_ctx_t *ctx, double *ms, uint64_t *count, int reset)
 int s5b_stage_count(void) { return ST_COUNT; }
 const char *s5b_stage_name(int stage) {
     static const char *names[ST_COUNT] = {"h2d", "record_depress", "glue", "signal_depress", "signal_press", "pack",
-                                          "record_press", "image", "d2h"};
+                                          "record_press", "image", "d2h", "signal_extract"};
     return stage >= 0 && stage < ST_COUNT ? names[stage] : "";
 }
 

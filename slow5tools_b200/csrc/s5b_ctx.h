@@ -69,7 +69,7 @@ struct PipeSlot {
 constexpr int NLANE = 6;   // lanes that exist; s5b_ctx::n_lanes of them are used (3 unless S5B_RECODE_LANES says otherwise)
 // stages of a transcoding pass, for the optional per-stage CUDA-event timing (s5b_ctx_stage_timing)
 enum Stage { ST_H2D = 0, ST_REC_DEPRESS, ST_GLUE, ST_SIG_DEPRESS, ST_SIG_PRESS, ST_PACK, ST_REC_PRESS, ST_IMAGE, ST_D2H,
-             ST_COUNT };
+             ST_SIG_EXTRACT, ST_COUNT };
 
 struct RecodeLane {
     cudaStream_t stream = nullptr;
@@ -84,6 +84,7 @@ struct RecodeLane {
 
 struct StageTimer {
     bool enabled = false;
+    bool isolate = false;            // S5B_STAGE_ISOLATE: synchronise the stream around every stage (development aid)
     struct Mark { cudaEvent_t a, b; int stage; };
     std::vector<Mark> marks;         // recorded, not yet read
     std::vector<cudaEvent_t> pool;   // free events
