@@ -15,7 +15,11 @@
 //   * a block is coded in one of two modes.  LITERAL: no matches, four bytes per lane and iteration straight
 //     from global memory.  RUN: literals plus distance-1 run matches found with warp ballots inside 32-byte
 //     strips -- used for the part before the split point and for any block in which at least half the bytes
-//     repeat their predecessor;
+//     repeat their predecessor.  The part before the split point (record header fields, sample count, svb-zd control
+//     bytes: the same kind of bytes in every record of every file) does not get a code of its own: it is coded RUN-style
+//     under a code fixed ahead of time (tools/gen_deflate_canned.py), still as a dynamic block whose header is the same
+//     bits every time -- no histogram, sort, tree, canonical codes or header construction for it (that cost as much as
+//     the 4x larger data part), +0.5 % in size;
 //   * the work is split by the shape of its parallelism:
 //       deflate_count_kernel  one warp per record: Adler-32, byte / length-symbol histogram of every block,
 //                             compaction of the used symbols, bitonic sort in registers -> sorted
@@ -29,6 +33,7 @@
 //                             shared-memory bit buffer that leaves as 128-bit stores; stored blocks when a
 //                             block would not shrink; Adler-32 trailer.
 //     (the round-1 single kernel spent 35 % of its issue slots in lane 0's merge loop and the shared-memory sort)
+#include <cstdlib>
 #include "s5b_kernels.h"
 #include "s5b_ptx.cuh"
 #include "huff_common.cuh"
@@ -45,7 +50,9 @@ constexpr int DEF_OUT_SLACK = HC_OUT_SLACK;
 constexpr uint32_t ADLER_MOD = 65521u;
 constexpr int CNT_WARPS = 4, EMIT_WARPS = 4, TREE_THREADS = 64;
 constexpr int TREE_STRIDE = 290;  // u16 entries per row: 145 words, odd -> lanes on the same index hit different banks
-enum : uint32_t { MODE_LIT = 0, MODE_RUN = 1 };
+enum : uint32_t { MODE_LIT = 0, MODE_RUN = 1, MODE_CANNED = 2 };
+
+#include "deflate_canned.inc"
 
 struct DefWork {       // views into the caller's workspace
     uint32_t *nblk;    // [n]      blocks per record (scanned into blk_off)
@@ -56,6 +63,7 @@ struct DefWork {       // views into the caller's workspace
     uint8_t *lens;     // [blocks][DEF_ROW] code length of sorted entry i
     void *scan_scratch;
     uint64_t max_blocks;
+    uint32_t canned;   // blocks before the split point use the canned code (S5B_DEFLATE_CANNED=0 turns it off)
 };
 
 __constant__ uint8_t c_def_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -215,9 +223,12 @@ __global__ void deflate_plan_kernel(const DeflateArgs a, DefWork w) {
 // ---- kernel 1: histograms -> sorted symbol lists ------------------------------------------------------------------
 __global__ void __launch_bounds__(CNT_WARPS * 32) deflate_count_kernel(const DeflateArgs a, DefWork wk) {
     __shared__ CntWarpSmem smem[CNT_WARPS];
+    __shared__ uint8_t canned_len[DEF_ROW];
     CntWarpSmem &ws = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint8_t *slab_end = a.in + a.in_capacity;
+    for (int s = threadIdx.x; s < DEF_ROW; s += CNT_WARPS * 32) canned_len[s] = (uint8_t)(g_canned_tab[s] >> 16);
+    __syncthreads();
     for (;;) {
         unsigned long long r = 0;
         if (lane == 0) r = atomicAdd(a.work_counter, 1ULL);
@@ -237,6 +248,39 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) deflate_count_kernel(const Def
             const uint32_t blen = b1 - b0;
             uint32_t mode = (split && b1 <= split) ? MODE_RUN : MODE_LIT;
             uint32_t nmatch = 0;
+            if (mode == MODE_RUN && wk.canned) {
+                // canned code: Adler-32 and the size of the tokens, nothing else
+                uint32_t s1 = 0, s2 = 0, bits = 0;
+                uint32_t prev0 = b0 ? (uint32_t)src[b0 - 1] : 0x200u;
+                for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
+                    const uint32_t i = t0 + lane;
+                    const uint32_t b = i < blen ? (uint32_t)src[b0 + i] : 0x100u;
+                    if (i < blen) {
+                        s1 += b;
+                        s2 += (blen - i) * b;
+                    }
+                    const Token tk = strip_token(b, prev0, lane);
+                    prev0 = __shfl_sync(FULL, b, 31);
+                    if (tk.kind == 1) {
+                        bits += canned_len[b];
+                    } else if (tk.kind == 2) {
+                        uint32_t sym, xb, xv;
+                        len_code(tk.mlen, sym, xb, xv);
+                        bits += canned_len[257 + sym] + xb + 1u;
+                    }
+                }
+                s2 %= ADLER_MOD;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    s1 += __shfl_xor_sync(FULL, s1, d);
+                    s2 += __shfl_xor_sync(FULL, s2, d);
+                    bits += __shfl_xor_sync(FULL, bits, d);
+                }
+                ad_b = (uint32_t)((ad_b + (uint64_t)blen * ad_a + s2) % ADLER_MOD);
+                ad_a = (ad_a + s1) % ADLER_MOD;
+                if (lane == 0) wk.binfo[blk0 + k] = make_uint4((MODE_CANNED << 16) | (1u << 24), bits + canned_len[256], 0u, 0u);
+                continue;
+            }
             for (int pass = 0; pass < 2; ++pass) {
                 for (int i = lane; i < 4 * DEF_ROW; i += 32) (&ws.hist[0][0])[i] = 0;
                 __syncwarp();
@@ -477,7 +521,7 @@ __global__ void __launch_bounds__(TREE_THREADS) deflate_tree_kernel(DefWork wk, 
         for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
         if (lane == rr) my_bits = bits;
     }
-    if (live) wk.binfo[t].y = my_bits;
+    if (live && ((info >> 16) & 0xffu) != MODE_CANNED) wk.binfo[t].y = my_bits;
 }
 
 // ---- kernel 3: emit ------------------------------------------------------------------------------------------------
@@ -550,142 +594,152 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
             const uint32_t mode = (info.x >> 16) & 0xffu;
             const uint32_t dist_len = (info.x >> 24) & 1u;
             const uint32_t tok_bits = info.y;
-            // ---- the block's code lengths, in symbol order
-            for (int s = lane; s < DEF_ROW; s += 32) ws.len[s] = 0;
-            __syncwarp();
-            {
-                const uint32_t *keys = wk.keys + (blk0 + k) * DEF_ROW;
-                const uint8_t *lens = wk.lens + (blk0 + k) * DEF_ROW;
-                for (int i = lane; i < used; i += 32) ws.len[keys[i] & 511u] = lens[i];
-            }
-            __syncwarp();
-            canonical_codes(ws.len, 286, ws.code, ws.bl_count, lane);
-            for (int s = lane; s < DEF_ROW; s += 32) ws.tab[s] = (uint32_t)ws.code[s] | ((uint32_t)ws.len[s] << 16);
-            int hlit = 286;
-            while (hlit > 257 && ws.len[hlit - 1] == 0) --hlit;
+            const bool canned = mode == MODE_CANNED;
+            const uint8_t *order = c_def_cl_order;
             const int hdist = 1;
-            // ---- header: run-length code the hlit + hdist code lengths (RFC 1951 3.2.7), whole warp: find the runs of
-            // equal lengths, turn every run into its symbols (16: repeat previous 3-6, 17: zeros 3-10, 18: zeros
-            // 11-138, greedy like zlib's send_tree), place them with a prefix scan over the runs
-            int ncl = 0;
-            if (lane < 19) ws.clhist[lane] = 0;
-            __syncwarp();
-            {
-                const int total = hlit + hdist;
-                auto length_at = [&](int q) -> uint32_t { return q < hlit ? ws.len[q] : dist_len; };
-                uint16_t *run_start = ws.k.run_start;
-                int nruns = 0;
-                for (int k0 = 0; k0 < total; k0 += 32) {
-                    const int q = k0 + lane;
-                    const bool st = q < total && (q == 0 || length_at(q) != length_at(q - 1));
-                    const uint32_t m = __ballot_sync(FULL, st);
-                    if (st) run_start[nruns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)q;
-                    nruns += __popc(m);
+            int hlit = 286, ncl = 0, hclen = 19;
+            uint32_t dyn_bits;
+            if (canned) {
+                // the code fixed ahead of time: its table and header are constants
+                for (int s = lane; s < DEF_ROW; s += 32) ws.tab[s] = g_canned_tab[s];
+                dyn_bits = tok_bits + 3 + CANNED_HDR_BITS;
+                __syncwarp();
+            } else {
+                // ---- the block's code lengths, in symbol order
+                for (int s = lane; s < DEF_ROW; s += 32) ws.len[s] = 0;
+                __syncwarp();
+                {
+                    const uint32_t *keys = wk.keys + (blk0 + k) * DEF_ROW;
+                    const uint8_t *lens = wk.lens + (blk0 + k) * DEF_ROW;
+                    for (int i = lane; i < used; i += 32) ws.len[keys[i] & 511u] = lens[i];
                 }
                 __syncwarp();
-                for (int r0 = 0; r0 < nruns; r0 += 32) {
-                    const int rr = r0 + lane;
-                    uint32_t v = 0, n18 = 0, n17 = 0, n16 = 0, nlit = 0, tail = 0;
-                    // n18 / n16: full-size repeat symbols; tail: size of one more, smaller repeat symbol (0 = none)
-                    if (rr < nruns) {
-                        const int s0 = run_start[rr];
-                        const int s1 = rr + 1 < nruns ? run_start[rr + 1] : total;
-                        uint32_t left = (uint32_t)(s1 - s0);
-                        v = length_at(s0);
-                        if (v == 0) {
-                            n18 = left / 138u;
-                            left -= n18 * 138u;
-                            if (left >= 11) {
-                                tail = left;
-                                ++n18;
-                                left = 0;
-                            } else if (left >= 3) {
-                                tail = left;
-                                n17 = 1;
-                                left = 0;
+                canonical_codes(ws.len, 286, ws.code, ws.bl_count, lane);
+                for (int s = lane; s < DEF_ROW; s += 32) ws.tab[s] = (uint32_t)ws.code[s] | ((uint32_t)ws.len[s] << 16);
+                hlit = 286;
+                while (hlit > 257 && ws.len[hlit - 1] == 0) --hlit;
+                // ---- header: run-length code the hlit + hdist code lengths (RFC 1951 3.2.7), whole warp: find the runs of
+                // equal lengths, turn every run into its symbols (16: repeat previous 3-6, 17: zeros 3-10, 18: zeros
+                // 11-138, greedy like zlib's send_tree), place them with a prefix scan over the runs
+                ncl = 0;
+                if (lane < 19) ws.clhist[lane] = 0;
+                __syncwarp();
+                {
+                    const int total = hlit + hdist;
+                    auto length_at = [&](int q) -> uint32_t { return q < hlit ? ws.len[q] : dist_len; };
+                    uint16_t *run_start = ws.k.run_start;
+                    int nruns = 0;
+                    for (int k0 = 0; k0 < total; k0 += 32) {
+                        const int q = k0 + lane;
+                        const bool st = q < total && (q == 0 || length_at(q) != length_at(q - 1));
+                        const uint32_t m = __ballot_sync(FULL, st);
+                        if (st) run_start[nruns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)q;
+                        nruns += __popc(m);
+                    }
+                    __syncwarp();
+                    for (int r0 = 0; r0 < nruns; r0 += 32) {
+                        const int rr = r0 + lane;
+                        uint32_t v = 0, n18 = 0, n17 = 0, n16 = 0, nlit = 0, tail = 0;
+                        // n18 / n16: full-size repeat symbols; tail: size of one more, smaller repeat symbol (0 = none)
+                        if (rr < nruns) {
+                            const int s0 = run_start[rr];
+                            const int s1 = rr + 1 < nruns ? run_start[rr + 1] : total;
+                            uint32_t left = (uint32_t)(s1 - s0);
+                            v = length_at(s0);
+                            if (v == 0) {
+                                n18 = left / 138u;
+                                left -= n18 * 138u;
+                                if (left >= 11) {
+                                    tail = left;
+                                    ++n18;
+                                    left = 0;
+                                } else if (left >= 3) {
+                                    tail = left;
+                                    n17 = 1;
+                                    left = 0;
+                                }
+                                nlit = left;
+                            } else {
+                                nlit = 1;  // the value itself first, repeats refer back to it
+                                --left;
+                                n16 = left / 6u;
+                                left -= n16 * 6u;
+                                if (left >= 3) {
+                                    tail = left;
+                                    ++n16;
+                                    left = 0;
+                                }
+                                nlit += left;
                             }
-                            nlit = left;
-                        } else {
-                            nlit = 1;  // the value itself first, repeats refer back to it
-                            --left;
-                            n16 = left / 6u;
-                            left -= n16 * 6u;
-                            if (left >= 3) {
-                                tail = left;
-                                ++n16;
-                                left = 0;
-                            }
-                            nlit += left;
                         }
-                    }
-                    const uint32_t cnt = n18 + n17 + n16 + nlit;
-                    uint32_t incl = cnt;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-                        if (lane >= d) incl += t;
-                    }
-                    int at = ncl + (int)(incl - cnt);
-                    if (rr < nruns) {
-                        if (v == 0) {
-                            const uint32_t full18 = tail >= 11 ? n18 - 1 : n18;
-                            for (uint32_t i = 0; i < full18; ++i) {
-                                ws.clsym[at] = 18;
-                                ws.clext[at++] = 138 - 11;
-                            }
-                            if (tail >= 11) {
-                                ws.clsym[at] = 18;
-                                ws.clext[at++] = (uint8_t)(tail - 11);
-                            } else if (tail >= 3) {
-                                ws.clsym[at] = 17;
-                                ws.clext[at++] = (uint8_t)(tail - 3);
-                            }
-                            if (n18) atomicAdd(&ws.clhist[18], n18);
-                            if (n17) atomicAdd(&ws.clhist[17], n17);
-                            for (uint32_t i = 0; i < nlit; ++i) {
-                                ws.clsym[at] = 0;
-                                ws.clext[at++] = 0;
-                            }
-                            if (nlit) atomicAdd(&ws.clhist[0], nlit);
-                        } else {
-                            ws.clsym[at] = (uint8_t)v;
-                            ws.clext[at++] = 0;
-                            const uint32_t full16 = tail ? n16 - 1 : n16;
-                            for (uint32_t i = 0; i < full16; ++i) {
-                                ws.clsym[at] = 16;
-                                ws.clext[at++] = 6 - 3;
-                            }
-                            if (tail) {
-                                ws.clsym[at] = 16;
-                                ws.clext[at++] = (uint8_t)(tail - 3);
-                            }
-                            if (n16) atomicAdd(&ws.clhist[16], n16);
-                            for (uint32_t i = 1; i < nlit; ++i) {
+                        const uint32_t cnt = n18 + n17 + n16 + nlit;
+                        uint32_t incl = cnt;
+    #pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                            if (lane >= d) incl += t;
+                        }
+                        int at = ncl + (int)(incl - cnt);
+                        if (rr < nruns) {
+                            if (v == 0) {
+                                const uint32_t full18 = tail >= 11 ? n18 - 1 : n18;
+                                for (uint32_t i = 0; i < full18; ++i) {
+                                    ws.clsym[at] = 18;
+                                    ws.clext[at++] = 138 - 11;
+                                }
+                                if (tail >= 11) {
+                                    ws.clsym[at] = 18;
+                                    ws.clext[at++] = (uint8_t)(tail - 11);
+                                } else if (tail >= 3) {
+                                    ws.clsym[at] = 17;
+                                    ws.clext[at++] = (uint8_t)(tail - 3);
+                                }
+                                if (n18) atomicAdd(&ws.clhist[18], n18);
+                                if (n17) atomicAdd(&ws.clhist[17], n17);
+                                for (uint32_t i = 0; i < nlit; ++i) {
+                                    ws.clsym[at] = 0;
+                                    ws.clext[at++] = 0;
+                                }
+                                if (nlit) atomicAdd(&ws.clhist[0], nlit);
+                            } else {
                                 ws.clsym[at] = (uint8_t)v;
                                 ws.clext[at++] = 0;
+                                const uint32_t full16 = tail ? n16 - 1 : n16;
+                                for (uint32_t i = 0; i < full16; ++i) {
+                                    ws.clsym[at] = 16;
+                                    ws.clext[at++] = 6 - 3;
+                                }
+                                if (tail) {
+                                    ws.clsym[at] = 16;
+                                    ws.clext[at++] = (uint8_t)(tail - 3);
+                                }
+                                if (n16) atomicAdd(&ws.clhist[16], n16);
+                                for (uint32_t i = 1; i < nlit; ++i) {
+                                    ws.clsym[at] = (uint8_t)v;
+                                    ws.clext[at++] = 0;
+                                }
+                                atomicAdd(&ws.clhist[v], nlit);
                             }
-                            atomicAdd(&ws.clhist[v], nlit);
                         }
+                        ncl += (int)__shfl_sync(FULL, incl, 31);
                     }
-                    ncl += (int)__shfl_sync(FULL, incl, 31);
                 }
-            }
-            __syncwarp();
-            huffman_lengths(ws.clhist, 19, 7, ws.cllen, ws.k.sortbuf, ws.k.weight, ws.k.parent, ws.bl_count, lane);
-            canonical_codes(ws.cllen, 19, ws.clcode, ws.bl_count, lane);
-            const uint8_t *order = c_def_cl_order;
-            int hclen = 19;
-            while (hclen > 4 && ws.cllen[order[hclen - 1]] == 0) --hclen;
+                __syncwarp();
+                huffman_lengths(ws.clhist, 19, 7, ws.cllen, ws.k.sortbuf, ws.k.weight, ws.k.parent, ws.bl_count, lane);
+                canonical_codes(ws.cllen, 19, ws.clcode, ws.bl_count, lane);
+                hclen = 19;
+                while (hclen > 4 && ws.cllen[order[hclen - 1]] == 0) --hclen;
 
-            // ---- size of the dynamic block in bits (header + tokens + end of block): stored instead if that is smaller
-            uint32_t hdr_bits = 0;
-            for (int q = lane; q < ncl; q += 32) {
-                const uint32_t s = ws.clsym[q];
-                hdr_bits += ws.cllen[s] + (s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0);
+                // ---- size of the dynamic block in bits (header + tokens + end of block): stored instead if that is smaller
+                uint32_t hdr_bits = 0;
+                for (int q = lane; q < ncl; q += 32) {
+                    const uint32_t s = ws.clsym[q];
+                    hdr_bits += ws.cllen[s] + (s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0);
+                }
+    #pragma unroll
+                for (int d = 16; d; d >>= 1) hdr_bits += __shfl_xor_sync(FULL, hdr_bits, d);
+                dyn_bits = tok_bits + hdr_bits + 3 + 5 + 5 + 4 + 3 * hclen;
             }
-#pragma unroll
-            for (int d = 16; d; d >>= 1) hdr_bits += __shfl_xor_sync(FULL, hdr_bits, d);
-            const uint32_t dyn_bits = tok_bits + hdr_bits + 3 + 5 + 5 + 4 + 3 * hclen;
             const uint32_t stored_bits = 8u * blen + 40u;
 
             if (dyn_bits >= stored_bits + 7u) {
@@ -705,45 +759,55 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
                     bo.bitpos += 8 * min(32u, blen - t0);
                 }
             } else {
-                // ---- dynamic block header (lane 0; a few hundred bits)
-                if ((bo.bitpos >> 3) + 24 > DEF_OUT) bo.flush(lane, false);
-                if (lane == 0) {
-                    uint32_t p = bo.bitpos;
-                    bo.put(p, (last ? 1u : 0u) | (2u << 1), 3);
-                    p += 3;
-                    bo.put(p, (uint32_t)(hlit - 257), 5);
-                    p += 5;
-                    bo.put(p, (uint32_t)(hdist - 1), 5);
-                    p += 5;
-                    bo.put(p, (uint32_t)(hclen - 4), 4);
-                    p += 4;
-                    for (int q = 0; q < hclen; ++q) {
-                        bo.put(p, ws.cllen[order[q]], 3);
+                if (canned) {
+                    // ---- BFINAL / BTYPE and the canned header, a word per lane
+                    if ((bo.bitpos >> 3) + 80 > DEF_OUT) bo.flush(lane, false);
+                    if (lane == 0) bo.put(bo.bitpos, (last ? 1u : 0u) | (2u << 1), 3);
+                    bo.bitpos += 3;
+                    if (lane < CANNED_HDR_WORDS)
+                        bo.put(bo.bitpos + 32u * lane, g_canned_hdr[lane], min(32u, CANNED_HDR_BITS - 32u * lane));
+                    bo.bitpos += CANNED_HDR_BITS;
+                } else {
+                    // ---- dynamic block header (lane 0; a few hundred bits)
+                    if ((bo.bitpos >> 3) + 24 > DEF_OUT) bo.flush(lane, false);
+                    if (lane == 0) {
+                        uint32_t p = bo.bitpos;
+                        bo.put(p, (last ? 1u : 0u) | (2u << 1), 3);
                         p += 3;
+                        bo.put(p, (uint32_t)(hlit - 257), 5);
+                        p += 5;
+                        bo.put(p, (uint32_t)(hdist - 1), 5);
+                        p += 5;
+                        bo.put(p, (uint32_t)(hclen - 4), 4);
+                        p += 4;
+                        for (int q = 0; q < hclen; ++q) {
+                            bo.put(p, ws.cllen[order[q]], 3);
+                            p += 3;
+                        }
+                        bo.bitpos = p;
                     }
-                    bo.bitpos = p;
-                }
-                bo.bitpos = __shfl_sync(FULL, bo.bitpos, 0);
-                for (int k0 = 0; k0 < ncl; k0 += 32) {
-                    if ((bo.bitpos >> 3) + 64 > DEF_OUT) bo.flush(lane, false);
-                    const int q = k0 + lane;
-                    uint32_t bits = 0, nbits = 0;
-                    if (q < ncl) {
-                        const uint32_t s = ws.clsym[q];
-                        nbits = ws.cllen[s];
-                        bits = ws.clcode[s];
-                        const uint32_t xb = s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0;
-                        bits |= (uint32_t)ws.clext[q] << nbits;
-                        nbits += xb;
+                    bo.bitpos = __shfl_sync(FULL, bo.bitpos, 0);
+                    for (int k0 = 0; k0 < ncl; k0 += 32) {
+                        if ((bo.bitpos >> 3) + 64 > DEF_OUT) bo.flush(lane, false);
+                        const int q = k0 + lane;
+                        uint32_t bits = 0, nbits = 0;
+                        if (q < ncl) {
+                            const uint32_t s = ws.clsym[q];
+                            nbits = ws.cllen[s];
+                            bits = ws.clcode[s];
+                            const uint32_t xb = s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0;
+                            bits |= (uint32_t)ws.clext[q] << nbits;
+                            nbits += xb;
+                        }
+                        uint32_t incl = nbits;
+    #pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                            if (lane >= d) incl += t;
+                        }
+                        bo.put(bo.bitpos + incl - nbits, bits, nbits);
+                        bo.bitpos += __shfl_sync(FULL, incl, 31);
                     }
-                    uint32_t incl = nbits;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-                        if (lane >= d) incl += t;
-                    }
-                    bo.put(bo.bitpos + incl - nbits, bits, nbits);
-                    bo.bitpos += __shfl_sync(FULL, incl, 31);
                 }
                 // ---- tokens.  Same tokenisation as the counting kernel; a warp prefix scan over the token bit counts
                 // places every lane's bits.
@@ -812,8 +876,8 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
                     }
                 }
                 if ((bo.bitpos >> 3) + 8 > DEF_OUT) bo.flush(lane, false);
-                if (lane == 0) bo.put(bo.bitpos, ws.code[256], ws.len[256]);
-                bo.bitpos += ws.len[256];
+                if (lane == 0) bo.put(bo.bitpos, ws.tab[256] & 0xffffu, ws.tab[256] >> 16);
+                bo.bitpos += ws.tab[256] >> 16;
             }
             __syncwarp();
         }
@@ -882,6 +946,13 @@ cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm,
     w.lens = take(mb * DEF_ROW);
     w.scan_scratch = take(compact_scratch_bytes(n));
     w.max_blocks = mb;
+    {
+        static const bool off = [] {
+            const char *e = getenv("S5B_DEFLATE_CANNED");
+            return e && e[0] == '0';
+        }();
+        w.canned = off ? 0u : 1u;
+    }
     deflate_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, w);
     cudaError_t e = launch_scan(w.nblk, n, 1, w.blk_off, w.scan_scratch, st);
     if (e != cudaSuccess) return e;
