@@ -205,13 +205,19 @@ struct BitOut {
         uint4 *g4 = reinterpret_cast<uint4 *>(gbase);
         for (uint32_t seg = lane; seg < wseg; seg += 32) {
             const uint32_t lo = seg * 16, hi = lo + 16;
-            if (lo >= head && hi <= nbytes) {
-                g4[seg] = s4[seg];
-            } else {
-                for (uint32_t i = max(lo, head); i < min(hi, nbytes); ++i) gbase[i] = b8[i];
-            }
+            if (lo >= head && hi <= nbytes) g4[seg] = s4[seg];
         }
         if (wseg == 0) return;
+        // the ragged ends leave a byte per lane: the front of segment 0 when the stream does not start on a 16-byte
+        // boundary, the back of the last segment at the end of the stream
+        if (head) {
+            const uint32_t i = head + lane;
+            if (i < min(16u, nbytes)) gbase[i] = b8[i];
+        }
+        if (final && (nbytes & 15u) && (wseg > 1 || !head)) {
+            const uint32_t i = (wseg - 1) * 16 + lane;
+            if (i < nbytes) gbase[i] = b8[i];
+        }
         const uint32_t full = final ? nbytes : wseg * 16;
         written += full - head;
         head = 0;

@@ -63,6 +63,10 @@ struct __align__(4) TiSmem {
     // the symbols ascend, so "literal" is one compare): sym index = (lo + code) & 0xffff, literal iff index < hi.
     // During construction: entries 0..15 are the builders' scratch, bytes 32..63 the header's staging area.
     uint16_t lbn[32];
+    // The 32 lanes of a warp touch the same member at about the same index at the same time (lock step).  With a stride of 72
+    // words lanes l and l + 4 met in one bank (8-way conflicts on every ring store and table load); 73 words is odd: the 32
+    // lanes land in 32 different banks.
+    uint32_t bank_skew;
     __device__ __forceinline__ uint8_t *tmp() { return reinterpret_cast<uint8_t *>(lbn + 16); }
     __device__ __forceinline__ uint32_t len_at(int i) const { return (nib[i >> 1] >> ((i & 1) * 4)) & 15u; }
     __device__ __forceinline__ void set_len(int i, uint32_t v) {
@@ -71,6 +75,7 @@ struct __align__(4) TiSmem {
     }
 };
 static_assert(HOT <= 160, "sorted8 lives on the parked code lengths");
+static_assert((sizeof(TiSmem) / 4) % 2 == 1 && sizeof(TiSmem) % 4 == 0, "per-lane stride must be an odd number of words");
 // per-lane global scratch row: code construction output and the rarely used codes
 struct TiScratch {
     uint16_t lit_sorted[288];
@@ -97,26 +102,47 @@ enum : int { ST_DONE = 0, ST_BLOCK = 1, ST_SYM = 2, ST_MATCH = 3, ST_STORED = 4 
 // n bits is an add plus a word shuffle.  `avail` counts the stream bits not yet consumed, so truncation is one compare.
 // Words that hold no stream byte are never loaded.
 struct Bits {
-    const uint32_t *base; // aligned word holding the first stream byte
-    uint32_t wi, nw;      // next word to load, number of words that hold stream bytes
-    uint32_t w0, w1, w2;  // current word, next word, and one more that is only on its way (latency hidden)
-    uint32_t off;         // consumed bits of w0 (0..31)
-    uint32_t avail;       // stream bits left (from the current position)
-    __device__ __forceinline__ uint32_t ld() {
-        const uint32_t v = wi < nw ? __ldg(base + wi) : 0u;
-        ++wi;
+    const uint2 *base; // aligned pair of words holding the first stream byte
+    uint32_t pi, np;   // next pair to load, number of pairs that hold stream bytes
+    uint32_t w0, w1;   // the current window: the next 32 bits are one funnel shift
+    uint32_t q0, q1, q2; // the words behind it; they arrive two at a time (one 64-bit load per 8 bytes of stream: the 32
+                         // lanes read 32 different lines, so every load instruction is up to 32 trips through the L1)
+    uint32_t off;      // consumed bits of w0 (0..31)
+    uint32_t avail;    // stream bits left (from the current position)
+    uint32_t fill;     // valid words among q0..q2 (1..3)
+    __device__ __forceinline__ uint2 ld() {
+        const uint2 v = pi < np ? __ldg(base + pi) : make_uint2(0u, 0u);
+        ++pi;
         return v;
     }
     __device__ __forceinline__ void start(const uint8_t *p, uint32_t len) {
-        const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
-        base = reinterpret_cast<const uint32_t *>(p - sk);
-        wi = 0;
-        nw = (sk + len + 3u) >> 2;
-        w0 = ld();
-        w1 = ld();
-        w2 = ld();
+        const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
+        base = reinterpret_cast<const uint2 *>(p - sk);
+        pi = 0;
+        np = (sk + len + 7u) >> 3;
+        const uint2 a = ld(), b = ld();
+        w0 = a.x, w1 = a.y, q0 = b.x, q1 = b.y, q2 = 0;
+        fill = 2;
         off = sk * 8u;
         avail = len * 8u;
+        if (off >= 32) {  // the stream starts in the second word of its pair
+            off -= 32;
+            shift();
+        }
+    }
+    // one word leaves the window; when only one word is left behind it, the next pair is requested (it is needed two
+    // shifts later: the latency hides behind the symbols decoded in between)
+    __device__ __forceinline__ void shift() {
+        w0 = w1;
+        w1 = q0;
+        q0 = q1;
+        q1 = q2;
+        if (--fill == 1) {
+            const uint2 v = ld();
+            q1 = v.x;
+            q2 = v.y;
+            fill = 3;
+        }
     }
     __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(w0, w1, off); }
     __device__ __forceinline__ uint32_t peek(uint32_t n) const { return peek32() & ((1u << n) - 1u); }
@@ -126,9 +152,7 @@ struct Bits {
         avail -= n;
         if (off >= 32) {
             off -= 32;
-            w0 = w1;
-            w1 = w2;
-            w2 = ld();
+            shift();
         }
     }
     // to the next byte boundary of the stream (the padding bits are there whenever a whole byte follows)
@@ -291,8 +315,9 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
         // the literal/length code limits of the current block, one register per length
         uint32_t L1 = 0, L2 = 0, L3 = 0, L4 = 0, L5 = 0, L6 = 0, L7 = 0, L8 = 0, L9 = 0, L10 = 0, L11 = 0, L12 = 0, L13 = 0,
                  L14 = 0, L15 = 0;
-        in.base = reinterpret_cast<const uint32_t *>(a.in);
-        in.wi = in.nw = in.w0 = in.w1 = in.w2 = in.off = in.avail = 0;
+        in.base = reinterpret_cast<const uint2 *>(a.in);
+        in.pi = in.np = in.w0 = in.w1 = in.q0 = in.q1 = in.q2 = in.off = in.avail = 0;
+        in.fill = 2;
         out.ring = sm.ring;
         out.dst = a.out;
         out.cap = out.total = out.flushed = out.bias = 0;
