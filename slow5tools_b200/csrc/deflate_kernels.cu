@@ -49,6 +49,7 @@ constexpr int DEF_OUT = HC_OUT;
 constexpr int DEF_OUT_SLACK = HC_OUT_SLACK;
 constexpr uint32_t ADLER_MOD = 65521u;
 constexpr int CNT_WARPS = 4, EMIT_WARPS = 4, TREE_THREADS = 64;
+constexpr int HDR_WORDS = 132;    // 14 + 19 * 3 + 287 * 14 bits at most
 constexpr int TREE_STRIDE = 290;  // u16 entries per row: 145 words, odd -> lanes on the same index hit different banks
 enum : uint32_t { MODE_LIT = 0, MODE_RUN = 1, MODE_CANNED = 2 };
 
@@ -60,10 +61,13 @@ struct DefWork {       // views into the caller's workspace
     uint32_t *adler;   // [n]
     uint4 *binfo;      // [blocks] x: used | mode << 16 | has_match << 24, y: token bits (tree kernel)
     uint32_t *keys;    // [blocks][DEF_ROW] ascending (frequency << 9 | symbol), `used` entries
-    uint8_t *lens;     // [blocks][DEF_ROW] code length of sorted entry i
+    uint8_t *lens;     // [blocks][DEF_ROW] code length of symbol s (tree kernel)
+    uint32_t *tab;     // [blocks][DEF_ROW] code (bit-reversed) | length << 16 of symbol s (header kernel)
+    uint32_t *hdr;     // [blocks][HDR_WORDS] the dynamic block header after BFINAL / BTYPE, binfo.z bits of it (header kernel)
     void *scan_scratch;
     uint64_t max_blocks;
     uint32_t canned;   // blocks before the split point use the canned code (S5B_DEFLATE_CANNED=0 turns it off)
+    uint32_t hdr_by_warp;  // S5B_DEFLATE_HDR=warp: block headers built inside the emit kernel (the older way, kept for A/B runs)
 };
 
 __constant__ uint8_t c_def_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(TREE_THREADS) deflate_tree_kernel(DefWork wk, 
     __syncwarp();
     if (live && used >= 2) mk_lengths(wrows + lane * TREE_STRIDE, used, 15);
     __syncwarp();
-    // lengths out (coalesced) and the block's token bits: sum f * (len + extra bits [+ the 1-bit distance code])
+    // lengths out, by symbol, and the block's token bits: sum f * (len + extra bits [+ the 1-bit distance code])
     uint32_t my_bits = 0;
     for (int rr = 0; rr < 32; ++rr) {
         const int u = __shfl_sync(FULL, used, rr);
@@ -509,10 +513,14 @@ __global__ void __launch_bounds__(TREE_THREADS) deflate_tree_kernel(DefWork wk, 
         const uint32_t *src = wk.keys + (warp_first + rr) * DEF_ROW;
         uint8_t *dst = wk.lens + (warp_first + rr) * DEF_ROW;
         uint32_t bits = 0;
+        if (u) {
+            for (int i = lane; i < DEF_ROW / 4; i += 32) reinterpret_cast<uint32_t *>(dst)[i] = 0;
+            __syncwarp();
+        }
         for (int i = lane; i < u; i += 32) {
             const uint32_t key = src[i], l = wrows[rr * TREE_STRIDE + i];
             const uint32_t s = key & 511u, f = key >> 9;
-            dst[i] = (uint8_t)l;
+            dst[s] = (uint8_t)l;
             uint32_t xb = 0;
             if (s >= 265 && s < 285) xb = (s - 261) >> 2;
             bits += f * (l + xb + (s > 256 ? dist_len : 0u));
@@ -522,6 +530,222 @@ __global__ void __launch_bounds__(TREE_THREADS) deflate_tree_kernel(DefWork wk, 
         if (lane == rr) my_bits = bits;
     }
     if (live && ((info >> 16) & 0xffu) != MODE_CANNED) wk.binfo[t].y = my_bits;
+}
+
+// ---- kernel 2b: one thread per block: canonical codes and the dynamic block header -------------------------------------
+// What a warp did for one block at a time inside the emit kernel (canonical codes with match/ballot rounds, run-length
+// coding of the code lengths, the 19-symbol code-length code built by lane 0, header bits placed by prefix scans: 4 400 warp
+// instructions per block, more than coding the block's 4 KiB of literals) is serial work on ~300 small numbers: here every
+// thread does it for its own block.  Results: tab[] (what the token loops look up) and the header bits, both in the
+// workspace.  The symbol sequence and the code-length code are the ones the warp version produced (same greedy run
+// splitting as zlib's send_tree, same two-queue merge and tie-breaking), so the streams did not change.
+struct HdrBits {
+    uint32_t *out;
+    uint64_t acc;
+    uint32_t n, words;
+    __device__ __forceinline__ void put(uint32_t bits, uint32_t nbits) {
+        acc |= (uint64_t)bits << n;
+        n += nbits;
+        if (n >= 32) {
+            out[words++] = (uint32_t)acc;
+            acc >>= 32;
+            n -= 32;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) deflate_header_kernel(DefWork wk, const uint64_t *n_blocks_ptr) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_blocks_ptr) return;
+    const uint4 info = wk.binfo[t];
+    if (((info.x >> 16) & 0xffu) == MODE_CANNED || (info.x & 0xffffu) < 2) return;
+    const uint32_t dist_len = (info.x >> 24) & 1u;
+    const uint32_t *len4 = reinterpret_cast<const uint32_t *>(wk.lens + t * DEF_ROW);
+    uint4 *tab4 = reinterpret_cast<uint4 *>(wk.tab + t * DEF_ROW);
+    uint16_t *cl = reinterpret_cast<uint16_t *>(wk.keys + t * DEF_ROW);  // the sorted keys are done with: run-length symbols
+    // ---- per-length counts, first code of every length (RFC 1951 3.2.2), number of literal/length codes
+    uint32_t next[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) next[b] = 0;
+    int hlit = 257;
+    for (int w = 0; w < DEF_ROW / 4; ++w) {
+        const uint32_t v = len4[w];
+        if (v == 0) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t l = (v >> (8 * b)) & 0xffu;
+            if (l) {
+                ++next[l];
+                if (4 * w + b >= 257) hlit = 4 * w + b + 1;
+            }
+        }
+    }
+    {
+        uint32_t code = 0, prev = 0;
+#pragma unroll
+        for (int b = 1; b <= 15; ++b) {
+            code = (code + prev) << 1;
+            prev = next[b];
+            next[b] = code;
+        }
+    }
+    // ---- codes in symbol order; the run-length coded length sequence (hlit lengths + the one distance length) on the way
+    uint32_t clfreq[19];
+#pragma unroll
+    for (int q = 0; q < 19; ++q) clfreq[q] = 0;
+    int ncl = 0;
+    auto emit = [&](uint32_t sym, uint32_t ext) {
+        cl[ncl++] = (uint16_t)(sym | (ext << 8));
+        ++clfreq[sym];
+    };
+    auto flush_run = [&](uint32_t v, uint32_t left) {
+        if (v == 0) {
+            for (; left >= 138; left -= 138) emit(18, 138 - 11);
+            if (left >= 11) {
+                emit(18, left - 11);
+                left = 0;
+            } else if (left >= 3) {
+                emit(17, left - 3);
+                left = 0;
+            }
+            for (; left; --left) emit(0, 0);
+        } else {
+            emit(v, 0);
+            --left;
+            for (; left >= 6; left -= 6) emit(16, 6 - 3);
+            if (left >= 3) {
+                emit(16, left - 3);
+                left = 0;
+            }
+            for (; left; --left) emit(v, 0);
+        }
+    };
+    uint32_t run_v = 0, run_n = 0;
+    for (int w = 0; w < DEF_ROW / 4; ++w) {
+        const uint32_t v = len4[w];
+        uint32_t e[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t l = (v >> (8 * b)) & 0xffu;
+            const int s = 4 * w + b;
+            uint32_t cw = 0;
+            if (l) cw = (__brev(next[l]++) >> (32 - l)) | (l << 16);
+            e[b] = cw;
+            if (s <= hlit) {  // entry hlit of the sequence is the distance length
+                const uint32_t x = s < hlit ? l : dist_len;
+                if (run_n && x == run_v) {
+                    ++run_n;
+                } else {
+                    if (run_n) flush_run(run_v, run_n);
+                    run_v = x;
+                    run_n = 1;
+                }
+            }
+        }
+        tab4[w] = make_uint4(e[0], e[1], e[2], e[3]);
+    }
+    flush_run(run_v, run_n);
+    // ---- the code-length code: 19 symbols, at most 7 bits (two-queue merge over the sorted frequencies, zlib's repair when a
+    // depth exceeds the limit)
+    uint8_t cllen[19];
+    {
+        int used = 0;
+#pragma unroll
+        for (int q = 0; q < 19; ++q) used += clfreq[q] != 0;
+        for (int q = 0; q < 19 && used < 2; ++q)
+            if (clfreq[q] == 0) {
+                clfreq[q] = 1;
+                ++used;
+            }
+        uint32_t key[19], weight[38];
+        uint8_t parent[38];
+        int n = 0;
+        for (int q = 0; q < 19; ++q) {
+            cllen[q] = 0;
+            if (clfreq[q]) {  // insertion sort by (frequency, symbol)
+                const uint32_t k = (clfreq[q] << 9) | (uint32_t)q;
+                int i = n++;
+                for (; i > 0 && key[i - 1] > k; --i) key[i] = key[i - 1];
+                key[i] = k;
+            }
+        }
+        for (int i = 0; i < n; ++i) weight[i] = key[i] >> 9;
+        int li = 0, ii = n, nx = n;
+        for (int j = 0; j < n - 1; ++j) {
+            int pick[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (li < n && (ii >= nx || weight[li] <= weight[ii])) pick[k] = li++;
+                else pick[k] = ii++;
+            }
+            weight[nx] = weight[pick[0]] + weight[pick[1]];
+            parent[pick[0]] = (uint8_t)nx;
+            parent[pick[1]] = (uint8_t)nx;
+            ++nx;
+        }
+        const int root = 2 * n - 2, limit = 7;
+        uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t kraft = 0;
+        bool over = false;
+        for (int i = 0; i < n; ++i) {
+            int d = 0;
+            for (int v = i; v != root; v = parent[v]) ++d;
+            if (d > limit) {
+                d = limit;
+                over = true;
+            }
+            kraft += 1u << (limit - d);
+            weight[i] = (uint32_t)d;
+            ++cnt[d];
+        }
+        if (over) {
+            int excess = (int)kraft - (1 << limit);
+            while (excess > 0) {
+                int bits = limit - 1;
+                while (cnt[bits] == 0) --bits;
+                --cnt[bits];
+                cnt[bits + 1] += 2;
+                --cnt[limit];
+                --excess;
+            }
+            int i = 0;
+            for (int bits = limit; bits >= 1; --bits)
+                for (uint32_t c = cnt[bits]; c > 0; --c) weight[i++] = (uint32_t)bits;
+        }
+        for (int i = 0; i < n; ++i) cllen[key[i] & 511u] = (uint8_t)weight[i];
+    }
+    uint32_t clcode[19];
+    {
+        uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nxt[8];
+        for (int q = 0; q < 19; ++q) ++cnt[cllen[q]];
+        cnt[0] = 0;
+        uint32_t code = 0;
+        nxt[0] = 0;
+        for (int b = 1; b <= 7; ++b) {
+            code = (code + cnt[b - 1]) << 1;
+            nxt[b] = code;
+        }
+        for (int q = 0; q < 19; ++q) {
+            const uint32_t l = cllen[q];
+            clcode[q] = l ? __brev(nxt[l]++) >> (32 - l) : 0u;
+        }
+    }
+    int hclen = 19;
+    while (hclen > 4 && cllen[c_def_cl_order[hclen - 1]] == 0) --hclen;
+    // ---- the header bits (RFC 1951 3.2.7), after BFINAL / BTYPE
+    HdrBits hb{wk.hdr + t * HDR_WORDS, 0ull, 0u, 0u};
+    hb.put((uint32_t)(hlit - 257), 5);
+    hb.put(0u, 5);  // one distance code
+    hb.put((uint32_t)(hclen - 4), 4);
+    for (int q = 0; q < hclen; ++q) hb.put(cllen[c_def_cl_order[q]], 3);
+    for (int q = 0; q < ncl; ++q) {
+        const uint32_t sym = cl[q] & 0xffu, ext = cl[q] >> 8;
+        const uint32_t l = cllen[sym];
+        hb.put(clcode[sym] | (ext << l), l + (sym == 16 ? 2u : sym == 17 ? 3u : sym == 18 ? 7u : 0u));
+    }
+    const uint32_t total = hb.words * 32 + hb.n;
+    if (hb.n) hb.out[hb.words] = (uint32_t)hb.acc;
+    wk.binfo[t].z = total;
 }
 
 // ---- kernel 3: emit ------------------------------------------------------------------------------------------------
@@ -590,7 +814,6 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
             const uint32_t blen = b1 - b0;
             const bool last = k + 1 == nb;
             const uint4 info = wk.binfo[blk0 + k];
-            const int used = (int)(info.x & 0xffffu);
             const uint32_t mode = (info.x >> 16) & 0xffu;
             const uint32_t dist_len = (info.x >> 24) & 1u;
             const uint32_t tok_bits = info.y;
@@ -599,19 +822,23 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
             const int hdist = 1;
             int hlit = 286, ncl = 0, hclen = 19;
             uint32_t dyn_bits;
+            const bool prebuilt = !canned && !wk.hdr_by_warp;  // table and header bits come from the header kernel
+            const uint32_t pre_bits = info.z;
             if (canned) {
                 // the code fixed ahead of time: its table and header are constants
                 for (int s = lane; s < DEF_ROW; s += 32) ws.tab[s] = g_canned_tab[s];
                 dyn_bits = tok_bits + 3 + CANNED_HDR_BITS;
                 __syncwarp();
+            } else if (prebuilt) {
+                const uint32_t *tab = wk.tab + (blk0 + k) * DEF_ROW;
+                for (int s = lane; s < DEF_ROW; s += 32) ws.tab[s] = tab[s];
+                dyn_bits = tok_bits + 3 + pre_bits;
+                __syncwarp();
             } else {
                 // ---- the block's code lengths, in symbol order
-                for (int s = lane; s < DEF_ROW; s += 32) ws.len[s] = 0;
-                __syncwarp();
                 {
-                    const uint32_t *keys = wk.keys + (blk0 + k) * DEF_ROW;
                     const uint8_t *lens = wk.lens + (blk0 + k) * DEF_ROW;
-                    for (int i = lane; i < used; i += 32) ws.len[keys[i] & 511u] = lens[i];
+                    for (int s = lane; s < DEF_ROW; s += 32) ws.len[s] = lens[s];
                 }
                 __syncwarp();
                 canonical_codes(ws.len, 286, ws.code, ws.bl_count, lane);
@@ -767,6 +994,14 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
                     if (lane < CANNED_HDR_WORDS)
                         bo.put(bo.bitpos + 32u * lane, g_canned_hdr[lane], min(32u, CANNED_HDR_BITS - 32u * lane));
                     bo.bitpos += CANNED_HDR_BITS;
+                } else if (prebuilt) {
+                    // ---- BFINAL / BTYPE and the header bits the header kernel left in the workspace, a word per lane
+                    if ((bo.bitpos >> 3) + HDR_WORDS * 4 + 16 > DEF_OUT) bo.flush(lane, false);
+                    if (lane == 0) bo.put(bo.bitpos, (last ? 1u : 0u) | (2u << 1), 3);
+                    bo.bitpos += 3;
+                    const uint32_t *hdr = wk.hdr + (blk0 + k) * HDR_WORDS;
+                    for (uint32_t w = lane; w * 32 < pre_bits; w += 32) bo.put(bo.bitpos + 32u * w, hdr[w], min(32u, pre_bits - 32u * w));
+                    bo.bitpos += pre_bits;
                 } else {
                     // ---- dynamic block header (lane 0; a few hundred bits)
                     if ((bo.bitpos >> 3) + 24 > DEF_OUT) bo.flush(lane, false);
@@ -916,11 +1151,13 @@ int deflate_blocks_per_sm() { return def_occ().ready ? def_occ().emit : 0; }
 
 uint64_t deflate_bound(uint64_t len) { return len + 6 * (len / DEF_BLOCK + 2) + 8; }
 
-static uint64_t def_max_blocks(uint64_t in_capacity, uint64_t n_reads) { return in_capacity / DEF_BLOCK + 3 * n_reads + 1; }
+// a record of len bytes has at most len / DEF_BLOCK + 2 blocks (one rounding up on each side of the split point)
+static uint64_t def_max_blocks(uint64_t in_capacity, uint64_t n_reads) { return in_capacity / DEF_BLOCK + 2 * n_reads + 1; }
 
 size_t deflate_work_bytes(uint64_t in_capacity, uint64_t n_reads) {
     const uint64_t mb = def_max_blocks(in_capacity, n_reads);
-    return (size_t)(n_reads * 4 + (n_reads + 1) * 8 + n_reads * 4 + mb * 16 + mb * DEF_ROW * 5 + compact_scratch_bytes(n_reads) + 512);
+    return (size_t)(n_reads * 4 + (n_reads + 1) * 8 + n_reads * 4 + mb * 16 + mb * DEF_ROW * 9 + mb * HDR_WORDS * 4 +
+                    compact_scratch_bytes(n_reads) + 512);
 }
 
 cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
@@ -944,6 +1181,8 @@ cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm,
     w.nblk = reinterpret_cast<uint32_t *>(take(n * 4));
     w.adler = reinterpret_cast<uint32_t *>(take(n * 4));
     w.lens = take(mb * DEF_ROW);
+    w.tab = reinterpret_cast<uint32_t *>(take(mb * DEF_ROW * 4));
+    w.hdr = reinterpret_cast<uint32_t *>(take(mb * HDR_WORDS * 4));
     w.scan_scratch = take(compact_scratch_bytes(n));
     w.max_blocks = mb;
     {
@@ -952,6 +1191,11 @@ cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm,
             return e && e[0] == '0';
         }();
         w.canned = off ? 0u : 1u;
+        static const bool by_warp = [] {
+            const char *e = getenv("S5B_DEFLATE_HDR");
+            return e && e[0] == 'w';
+        }();
+        w.hdr_by_warp = by_warp ? 1u : 0u;
     }
     deflate_plan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, w);
     cudaError_t e = launch_scan(w.nblk, n, 1, w.blk_off, w.scan_scratch, st);
@@ -967,6 +1211,7 @@ cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm,
     deflate_count_kernel<<<grid_for(CNT_WARPS, occ.cnt), CNT_WARPS * 32, 0, st>>>(a, w);
     // one thread per block; the block count lives on the device (blk_off[n]): the grid covers the bound, idle warps leave
     deflate_tree_kernel<<<(unsigned)((mb + TREE_THREADS - 1) / TREE_THREADS), TREE_THREADS, 0, st>>>(w, w.blk_off + n);
+    if (!w.hdr_by_warp) deflate_header_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(w, w.blk_off + n);
     e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     deflate_emit_kernel<<<grid_for(EMIT_WARPS, occ.emit), EMIT_WARPS * 32, sizeof(EmitWarpSmem) * EMIT_WARPS, st>>>(a, w);

@@ -6,7 +6,8 @@
 // A batch has 10^5..10^6 streams, so the parallelism is there without speculation: here every lane runs a serial decoder
 // on its own stream, 32 streams per warp.  Two things make that work on a GPU:
 //   * LOCK STEP.  A warp takes 32 consecutive records and all lanes move through the same loops -- block header and code
-//     construction in phases, then one symbol (or up to four match bytes, or one stored byte) per lane and iteration.
+//     construction in phases, then up to three literals (or one other symbol, or up to four match bytes, or one stored
+//     byte) per lane and iteration.
 //     Every loop is steered by a warp-wide vote or has a fixed trip count, which is also what keeps the 32 decoders
 //     converged: left to themselves, 32 data-dependent decoders diverge for good and independent thread scheduling
 //     runs them one after the other (measured: 12x slower than the warp-per-stream kernel).
@@ -146,6 +147,24 @@ struct Bits {
     }
     __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(w0, w1, off); }
     __device__ __forceinline__ uint32_t peek(uint32_t n) const { return peek32() & ((1u << n) - 1u); }
+    // the 32 bits that start `ahead` (<= 32) bits behind the current position: they may begin in the second word
+    __device__ __forceinline__ uint32_t peek32_at(uint32_t ahead) const {
+        const uint32_t o = off + ahead;  // < 64
+        return __funnelshift_r(o < 32 ? w0 : w1, o < 32 ? w1 : q0, o);  // (the shift amount is taken mod 32)
+    }
+    // n <= 64 and n <= avail
+    __device__ __forceinline__ void drop_long(uint32_t n) {
+        off += n;
+        avail -= n;
+        if (off >= 32) {
+            off -= 32;
+            shift();
+            if (off >= 32) {
+                off -= 32;
+                shift();
+            }
+        }
+    }
     // n <= 32 and n <= avail
     __device__ __forceinline__ void drop(uint32_t n) {
         off += n;
@@ -582,9 +601,20 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                                 if (si2 < (lw2 >> 16)) {
                                     out.put(si2 < (uint32_t)HOT ? (uint32_t)sm.sorted8[si2] : (uint32_t)(sc.lit_sorted[si2] & 0xffu));
                                     l += l2;
+                                    // ... and a third one from the word behind the window
+                                    const uint32_t r3 = __brev(in.peek32_at(l));
+                                    const uint32_t l3 = lit_len((r3 >> 13) | 15u);
+                                    if (l3 <= 15u && l + l3 <= in.avail) {
+                                        const uint32_t lw3 = lbn32[l3];
+                                        const uint32_t si3 = (lw3 + (r3 >> (32u - l3))) & 0xffffu;
+                                        if (si3 < (lw3 >> 16)) {
+                                            out.put(si3 < (uint32_t)HOT ? (uint32_t)sm.sorted8[si3] : (uint32_t)(sc.lit_sorted[si3] & 0xffu));
+                                            l += l3;
+                                        }
+                                    }
                                 }
                             }
-                            in.drop(l);
+                            in.drop_long(l);
                         } else if (in.drop(l), lo8 == 0u) {  // symbol 256
                             state = ST_BLOCK;
                         } else if (lo8 > 29u) {  // symbols 286, 287: "invalid literal/length code"
