@@ -154,3 +154,43 @@ def test_pointer_array_and_solo_forms(cdc):
     assert rc == 0 and [zlib.decompress(z) for z in zs] == items
     z = codec.ptr_compress_solo(METHOD.ZLIB, b"hello")
     assert zlib.decompress(z) == b"hello"
+
+
+def test_header_kernel_and_in_warp_headers_give_the_same_streams(tmp_path):
+    """deflate_header_kernel (one thread per block) took over what the emit kernel's warp did per block; the older path is still
+    there behind S5B_DEFLATE_HDR=warp (read once per process).  Both must produce the same bytes, with and without the canned
+    code for the front part of the records."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "one.py"
+    script.write_text(
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "sys.path.insert(0, %r)\n"
+        "import torch, slow5tools_b200 as s5\n"
+        "from slow5tools_b200 import synth\n"
+        "import test_deflate_gpu as t\n"
+        "from conftest import Oracle, build_oracle\n"
+        "cdc = s5.Codec(0)\n"
+        "bufs, splits = t.svb_records(Oracle(build_oracle()), 300, 4096, 5)\n"
+        "rng = np.random.default_rng(3)\n"
+        "bufs += [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (0, 1, 2, 70, 5000, 20000)]\n"
+        "bufs += [bytes(20000), b'ab' * 9000, bytes(rng.integers(0, 3, 30000, dtype=np.uint8))]\n"
+        "splits = list(splits) + [0, 0, 1, 30, 100, 7000, 1000, 0, 12000]\n"
+        "out, st = t.gpu_deflate(cdc, bufs, splits)\n"
+        "assert (st == 0).all()\n"
+        "h = hashlib.sha256()\n"
+        "for o in out: h.update(o)\n"
+        "print('DIGEST', h.hexdigest(), sum(len(o) for o in out))\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                      os.path.dirname(os.path.abspath(__file__))))
+    got = {}
+    for hdr in ("thread", "warp"):
+        for canned in ("1", "0"):
+            env = dict(os.environ, S5B_DEFLATE_HDR=hdr, S5B_DEFLATE_CANNED=canned)
+            r = subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+            assert r.returncode == 0, r.stderr.decode()[-2000:]
+            got[(hdr, canned)] = [l for l in r.stdout.decode().splitlines() if l.startswith("DIGEST")][0]
+    assert got[("thread", "1")] == got[("warp", "1")]
+    assert got[("thread", "0")] == got[("warp", "0")]
+    assert got[("thread", "1")] != got[("thread", "0")]
