@@ -485,51 +485,80 @@ __device__ __forceinline__ void mk_lengths(uint16_t *A, int n, int limit) {
         for (int c = cnt[bits]; c > 0; --c) A[i++] = (uint16_t)bits;
 }
 
+// Blocks coded under the canned code need neither a tree nor a header, and they sit between the others (block 0 of every
+// record): a warp that took 32 consecutive blocks would run with half its lanes idle.  A warp takes a window of 64 consecutive
+// blocks instead and hands the ones that need work to its lanes, 32 per round (list[]: 64 entries of warp-private shared memory).
+// Returns the number of blocks to do; round r, lane l: block first + list[32 r + l].
+__device__ __forceinline__ int window_blocks(const DefWork &wk, uint64_t first, uint64_t nblocks, int lane, uint8_t *list) {
+    int total = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint64_t b = first + 32 * h + lane;
+        bool need = false;
+        if (b < nblocks) {
+            const uint32_t x = wk.binfo[b].x;
+            need = ((x >> 16) & 0xffu) != MODE_CANNED && (x & 0xffffu) >= 2;
+        }
+        const uint32_t m = __ballot_sync(FULL, need);
+        if (need) list[total + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(32 * h + lane);
+        total += __popc(m);
+    }
+    __syncwarp();
+    return total;
+}
+
 __global__ void __launch_bounds__(TREE_THREADS) deflate_tree_kernel(DefWork wk, const uint64_t *n_blocks_ptr) {
     __shared__ uint16_t rows[TREE_THREADS * TREE_STRIDE];
+    __shared__ uint8_t lists[TREE_THREADS / 32][64];
     const uint64_t nblocks = *n_blocks_ptr;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t warp_first = ((uint64_t)blockIdx.x * TREE_THREADS) + (uint64_t)wib * 32;
+    const uint64_t warp_first = (((uint64_t)blockIdx.x * (TREE_THREADS / 32)) + (uint64_t)wib) * 64;
     if (warp_first >= nblocks) return;
-    const uint64_t t = warp_first + lane;
-    const bool live = t < nblocks;
-    const uint32_t info = live ? wk.binfo[t].x : 0u;
-    const int used = (int)(info & 0xffffu);
     uint16_t *wrows = rows + (size_t)wib * 32 * TREE_STRIDE;
-    // stage the frequencies of the warp's 32 rows (coalesced)
-    for (int rr = 0; rr < 32; ++rr) {
-        const int u = __shfl_sync(FULL, used, rr);
-        const uint32_t *src = wk.keys + (warp_first + rr) * DEF_ROW;
-        for (int i = lane; i < u; i += 32) wrows[rr * TREE_STRIDE + i] = (uint16_t)min(src[i] >> 9, 0xffffu);
-    }
-    __syncwarp();
-    if (live && used >= 2) mk_lengths(wrows + lane * TREE_STRIDE, used, 15);
-    __syncwarp();
-    // lengths out, by symbol, and the block's token bits: sum f * (len + extra bits [+ the 1-bit distance code])
-    uint32_t my_bits = 0;
-    for (int rr = 0; rr < 32; ++rr) {
-        const int u = __shfl_sync(FULL, used, rr);
-        const uint32_t dist_len = (__shfl_sync(FULL, info, rr) >> 24) & 1u;
-        const uint32_t *src = wk.keys + (warp_first + rr) * DEF_ROW;
-        uint8_t *dst = wk.lens + (warp_first + rr) * DEF_ROW;
-        uint32_t bits = 0;
-        if (u) {
-            for (int i = lane; i < DEF_ROW / 4; i += 32) reinterpret_cast<uint32_t *>(dst)[i] = 0;
-            __syncwarp();
+    const int todo = window_blocks(wk, warp_first, nblocks, lane, lists[wib]);
+    for (int r0 = 0; r0 < todo; r0 += 32) {
+        const bool live = r0 + lane < todo;
+        const uint64_t t = warp_first + (live ? lists[wib][r0 + lane] : 0);
+        const uint32_t info = live ? wk.binfo[t].x : 0u;
+        const int used = (int)(info & 0xffffu);
+        // stage the frequencies of the round's rows (coalesced)
+        for (int rr = 0; rr < 32; ++rr) {
+            const int u = __shfl_sync(FULL, used, rr);
+            const uint64_t tr = __shfl_sync(FULL, t, rr);
+            const uint32_t *src = wk.keys + tr * DEF_ROW;
+            for (int i = lane; i < u; i += 32) wrows[rr * TREE_STRIDE + i] = (uint16_t)min(src[i] >> 9, 0xffffu);
         }
-        for (int i = lane; i < u; i += 32) {
-            const uint32_t key = src[i], l = wrows[rr * TREE_STRIDE + i];
-            const uint32_t s = key & 511u, f = key >> 9;
-            dst[s] = (uint8_t)l;
-            uint32_t xb = 0;
-            if (s >= 265 && s < 285) xb = (s - 261) >> 2;
-            bits += f * (l + xb + (s > 256 ? dist_len : 0u));
-        }
+        __syncwarp();
+        if (live && used >= 2) mk_lengths(wrows + lane * TREE_STRIDE, used, 15);
+        __syncwarp();
+        // lengths out, by symbol, and the block's token bits: sum f * (len + extra bits [+ the 1-bit distance code])
+        uint32_t my_bits = 0;
+        for (int rr = 0; rr < 32; ++rr) {
+            const int u = __shfl_sync(FULL, used, rr);
+            const uint64_t tr = __shfl_sync(FULL, t, rr);
+            const uint32_t dist_len = (__shfl_sync(FULL, info, rr) >> 24) & 1u;
+            const uint32_t *src = wk.keys + tr * DEF_ROW;
+            uint8_t *dst = wk.lens + tr * DEF_ROW;
+            uint32_t bits = 0;
+            if (u) {
+                for (int i = lane; i < DEF_ROW / 4; i += 32) reinterpret_cast<uint32_t *>(dst)[i] = 0;
+                __syncwarp();
+            }
+            for (int i = lane; i < u; i += 32) {
+                const uint32_t key = src[i], l = wrows[rr * TREE_STRIDE + i];
+                const uint32_t s = key & 511u, f = key >> 9;
+                dst[s] = (uint8_t)l;
+                uint32_t xb = 0;
+                if (s >= 265 && s < 285) xb = (s - 261) >> 2;
+                bits += f * (l + xb + (s > 256 ? dist_len : 0u));
+            }
 #pragma unroll
-        for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
-        if (lane == rr) my_bits = bits;
+            for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
+            if (lane == rr) my_bits = bits;
+        }
+        if (live) wk.binfo[t].y = my_bits;
+        __syncwarp();
     }
-    if (live && ((info >> 16) & 0xffu) != MODE_CANNED) wk.binfo[t].y = my_bits;
 }
 
 // ---- kernel 2b: one thread per block: canonical codes and the dynamic block header -------------------------------------
@@ -554,11 +583,21 @@ struct HdrBits {
     }
 };
 
+__device__ __forceinline__ void block_header(const DefWork &wk, uint64_t t);
+
 __global__ void __launch_bounds__(128) deflate_header_kernel(DefWork wk, const uint64_t *n_blocks_ptr) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *n_blocks_ptr) return;
+    __shared__ uint8_t lists[4][64];
+    const uint64_t nblocks = *n_blocks_ptr;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t warp_first = (((uint64_t)blockIdx.x * 4) + (uint64_t)wib) * 64;
+    if (warp_first >= nblocks) return;
+    const int todo = window_blocks(wk, warp_first, nblocks, lane, lists[wib]);
+    for (int r0 = 0; r0 < todo; r0 += 32)
+        if (r0 + lane < todo) block_header(wk, warp_first + lists[wib][r0 + lane]);
+}
+
+__device__ __forceinline__ void block_header(const DefWork &wk, const uint64_t t) {
     const uint4 info = wk.binfo[t];
-    if (((info.x >> 16) & 0xffu) == MODE_CANNED || (info.x & 0xffffu) < 2) return;
     const uint32_t dist_len = (info.x >> 24) & 1u;
     const uint32_t *len4 = reinterpret_cast<const uint32_t *>(wk.lens + t * DEF_ROW);
     uint4 *tab4 = reinterpret_cast<uint4 *>(wk.tab + t * DEF_ROW);
@@ -1210,8 +1249,9 @@ cudaError_t launch_deflate(const DeflateArgs &a, int num_sms, int blocks_per_sm,
     if (e != cudaSuccess) return e;
     deflate_count_kernel<<<grid_for(CNT_WARPS, occ.cnt), CNT_WARPS * 32, 0, st>>>(a, w);
     // one thread per block; the block count lives on the device (blk_off[n]): the grid covers the bound, idle warps leave
-    deflate_tree_kernel<<<(unsigned)((mb + TREE_THREADS - 1) / TREE_THREADS), TREE_THREADS, 0, st>>>(w, w.blk_off + n);
-    if (!w.hdr_by_warp) deflate_header_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(w, w.blk_off + n);
+    // (a warp takes a window of 64 blocks)
+    deflate_tree_kernel<<<(unsigned)((mb + 2 * TREE_THREADS - 1) / (2 * TREE_THREADS)), TREE_THREADS, 0, st>>>(w, w.blk_off + n);
+    if (!w.hdr_by_warp) deflate_header_kernel<<<(unsigned)((mb + 255) / 256), 128, 0, st>>>(w, w.blk_off + n);
     e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     deflate_emit_kernel<<<grid_for(EMIT_WARPS, occ.emit), EMIT_WARPS * 32, sizeof(EmitWarpSmem) * EMIT_WARPS, st>>>(a, w);
