@@ -241,6 +241,13 @@ int s5b_ctx_stage_timing(s5b_ctx_t *ctx, int enable);
 int s5b_ctx_stage_report(s5b_ctx_t *ctx, double *ms, uint64_t *count, int reset);
 int s5b_stage_count(void);
 const char *s5b_stage_name(int stage);
+
+/* The auxiliary columns of the file whose records the transcoder is about to see (slow5_aux_meta_t, slow5.h:222-238): element
+ * size in bytes (1..8) of every field in header order and whether it is an array (stored as a u64 count and count elements).
+ * With a layout set, a record whose auxiliary section is not exactly these fields fails with S5B_ERR_PRESS, like
+ * slow5_rec_aux_parse does (slow5.c:3088-3166); without one (the default, or n_fields = 0xffffffff) the section is carried as it
+ * is.  Conversions that keep both methods copy the stored records without opening them either way. */
+int s5b_ctx_set_aux_layout(s5b_ctx_t *ctx, const uint8_t *elem_size, const uint8_t *is_array, uint32_t n_fields);
 /* The per-record work of index building (slow5_idx_build, slow5lib/src/slow5_idx.c:283-334) for a batch: the read_id of
  * every stored record.  Records compressed with in_rec (S5B_COMPRESS_NONE / ZLIB / ZSTD) are decompressed on the device --
  * for zlib only their first 256 bytes, like the reference's partial decompression (:290-310), with a full pass for the

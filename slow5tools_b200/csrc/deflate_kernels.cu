@@ -49,11 +49,14 @@ constexpr int DEF_OUT = HC_OUT;
 constexpr int DEF_OUT_SLACK = HC_OUT_SLACK;
 constexpr uint32_t ADLER_MOD = 65521u;
 constexpr int CNT_WARPS = 4, EMIT_WARPS = 4, TREE_THREADS = 64;
+constexpr int CANNED_MAX_BLOCK = 1152;  // canned blocks are coded first and measured afterwards: header + 12 bits per byte must
+                                       // fit the emit kernel's bit buffer without a flush in between
 constexpr int HDR_WORDS = 132;    // 14 + 19 * 3 + 287 * 14 bits at most
 constexpr int TREE_STRIDE = 290;  // u16 entries per row: 145 words, odd -> lanes on the same index hit different banks
 enum : uint32_t { MODE_LIT = 0, MODE_RUN = 1, MODE_CANNED = 2 };
 
 #include "deflate_canned.inc"
+static_assert(CANNED_MAX_LEN <= 12 && CANNED_HDR_BITS <= 512, "deflate_emit_kernel reserves 1.5 bytes per byte + 160 for a canned block");
 
 struct DefWork {       // views into the caller's workspace
     uint32_t *nblk;    // [n]      blocks per record (scanned into blk_off)
@@ -227,12 +230,9 @@ __global__ void deflate_plan_kernel(const DeflateArgs a, DefWork w) {
 // ---- kernel 1: histograms -> sorted symbol lists ------------------------------------------------------------------
 __global__ void __launch_bounds__(CNT_WARPS * 32) deflate_count_kernel(const DeflateArgs a, DefWork wk) {
     __shared__ CntWarpSmem smem[CNT_WARPS];
-    __shared__ uint8_t canned_len[DEF_ROW];
     CntWarpSmem &ws = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint8_t *slab_end = a.in + a.in_capacity;
-    for (int s = threadIdx.x; s < DEF_ROW; s += CNT_WARPS * 32) canned_len[s] = (uint8_t)(g_canned_tab[s] >> 16);
-    __syncthreads();
     for (;;) {
         unsigned long long r = 0;
         if (lane == 0) r = atomicAdd(a.work_counter, 1ULL);
@@ -252,37 +252,31 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) deflate_count_kernel(const Def
             const uint32_t blen = b1 - b0;
             uint32_t mode = (split && b1 <= split) ? MODE_RUN : MODE_LIT;
             uint32_t nmatch = 0;
-            if (mode == MODE_RUN && wk.canned) {
-                // canned code: Adler-32 and the size of the tokens, nothing else
-                uint32_t s1 = 0, s2 = 0, bits = 0;
-                uint32_t prev0 = b0 ? (uint32_t)src[b0 - 1] : 0x200u;
-                for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
-                    const uint32_t i = t0 + lane;
-                    const uint32_t b = i < blen ? (uint32_t)src[b0 + i] : 0x100u;
-                    if (i < blen) {
-                        s1 += b;
-                        s2 += (blen - i) * b;
-                    }
-                    const Token tk = strip_token(b, prev0, lane);
-                    prev0 = __shfl_sync(FULL, b, 31);
-                    if (tk.kind == 1) {
-                        bits += canned_len[b];
-                    } else if (tk.kind == 2) {
-                        uint32_t sym, xb, xv;
-                        len_code(tk.mlen, sym, xb, xv);
-                        bits += canned_len[257 + sym] + xb + 1u;
-                    }
+            if (mode == MODE_RUN && wk.canned && blen <= (uint32_t)CANNED_MAX_BLOCK) {
+                // canned code: nothing to count.  Adler-32 four bytes per lane; whether the block shrinks is seen when it is
+                // coded (the emit kernel measures it and falls back to a stored block)
+                WordReader rd;
+                rd.start(src + b0, slab_end, lane);
+                uint32_t s1 = 0, s2 = 0;
+                const uint32_t nstrip = (blen + 127) >> 7;
+                for (uint32_t t = 0; t < nstrip; ++t) {
+                    uint32_t v = rd.next(t, lane);
+                    const uint32_t pos = (t << 7) + 4u * lane;
+                    const uint32_t nv = pos >= blen ? 0u : min(4u, blen - pos);
+                    if (nv < 4) v &= nv ? (1u << (8 * nv)) - 1u : 0u;
+                    const uint32_t sum = __dp4a(v, 0x01010101u, 0u), wsum = __dp4a(v, 0x03020100u, 0u);
+                    s1 += sum;
+                    s2 += (blen - pos) * sum - wsum;
                 }
                 s2 %= ADLER_MOD;
 #pragma unroll
                 for (int d = 16; d; d >>= 1) {
                     s1 += __shfl_xor_sync(FULL, s1, d);
                     s2 += __shfl_xor_sync(FULL, s2, d);
-                    bits += __shfl_xor_sync(FULL, bits, d);
                 }
                 ad_b = (uint32_t)((ad_b + (uint64_t)blen * ad_a + s2) % ADLER_MOD);
                 ad_a = (ad_a + s1) % ADLER_MOD;
-                if (lane == 0) wk.binfo[blk0 + k] = make_uint4((MODE_CANNED << 16) | (1u << 24), bits + canned_len[256], 0u, 0u);
+                if (lane == 0) wk.binfo[blk0 + k] = make_uint4((MODE_CANNED << 16) | (1u << 24), 0u, 0u, 0u);
                 continue;
             }
             for (int pass = 0; pass < 2; ++pass) {
@@ -866,7 +860,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
             if (canned) {
                 // the code fixed ahead of time: its table and header are constants
                 for (int s = lane; s < DEF_ROW; s += 32) ws.tab[s] = g_canned_tab[s];
-                dyn_bits = tok_bits + 3 + CANNED_HDR_BITS;
+                dyn_bits = 0;  // (measured after coding)
                 __syncwarp();
             } else if (prebuilt) {
                 const uint32_t *tab = wk.tab + (blk0 + k) * DEF_ROW;
@@ -1008,7 +1002,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
             }
             const uint32_t stored_bits = 8u * blen + 40u;
 
-            if (dyn_bits >= stored_bits + 7u) {
+            auto emit_stored = [&]() {
                 // ---- stored block: pad to a byte boundary, LEN, NLEN, raw bytes
                 if ((bo.bitpos >> 3) + 16 > DEF_OUT) bo.flush(lane, false);
                 if (lane == 0) bo.put(bo.bitpos, last ? 1u : 0u, 3);
@@ -1024,10 +1018,17 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
                     if (i < blen) bo.put(bo.bitpos + 8 * lane, src[b0 + i], 8);
                     bo.bitpos += 8 * min(32u, blen - t0);
                 }
+            };
+            uint32_t canned_start = 0;
+            if (!canned && dyn_bits >= stored_bits + 7u) {
+                emit_stored();
             } else {
                 if (canned) {
-                    // ---- BFINAL / BTYPE and the canned header, a word per lane
-                    if ((bo.bitpos >> 3) + 80 > DEF_OUT) bo.flush(lane, false);
+                    // ---- BFINAL / BTYPE and the canned header, a word per lane.  Room first for the whole block (header, at
+                    // most 12 bits per byte, end of block): it is measured after it has been coded, and taking it back only
+                    // works while nothing of it has left the buffer
+                    if ((bo.bitpos >> 3) + (blen * 3u) / 2u + 160u > DEF_OUT) bo.flush(lane, false);
+                    canned_start = bo.bitpos;
                     if (lane == 0) bo.put(bo.bitpos, (last ? 1u : 0u) | (2u << 1), 3);
                     bo.bitpos += 3;
                     if (lane < CANNED_HDR_WORDS)
@@ -1152,6 +1153,17 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
                 if ((bo.bitpos >> 3) + 8 > DEF_OUT) bo.flush(lane, false);
                 if (lane == 0) bo.put(bo.bitpos, ws.tab[256] & 0xffffu, ws.tab[256] >> 16);
                 bo.bitpos += ws.tab[256] >> 16;
+                if (canned && bo.bitpos - canned_start >= stored_bits + 7u) {
+                    // the canned code did not shrink this block (not the kind of bytes it was made for): take the bits back
+                    // and store the block
+                    __syncwarp();
+                    const uint32_t w0 = canned_start >> 5, w1 = bo.bitpos >> 5;
+                    if (lane == 0) ws.out[w0] &= (1u << (canned_start & 31u)) - 1u;
+                    for (uint32_t w = w0 + 1 + lane; w <= w1; w += 32) ws.out[w] = 0;
+                    __syncwarp();
+                    bo.bitpos = canned_start;
+                    emit_stored();
+                }
             }
             __syncwarp();
         }

@@ -753,7 +753,16 @@ int view_main(int argc, char **argv) {
     int ret = 0;
     bool eof = false;
     if (rd.fmt == FMT_BINARY && fmt_out == FMT_BINARY && need_gpu && !getenv("S5B_VIEW_SLOW_PATH")) {
-        // blow5 -> blow5: whole batches stay on the device (pinned chunk pipeline)
+        // blow5 -> blow5: whole batches stay on the device (pinned chunk pipeline); the device checks every record's auxiliary
+        // section against the header's columns like record_parse_binary does on the other path
+        if (hdr.aux.size() <= 64) {
+            std::vector<uint8_t> sz(hdr.aux.size() + 1), arr(hdr.aux.size() + 1);
+            for (size_t f = 0; f < hdr.aux.size(); ++f) {
+                sz[f] = hdr.aux[f].size;
+                arr[f] = hdr.aux[f].is_array() ? 1 : 0;
+            }
+            s5b_ctx_set_aux_layout(gpu, sz.data(), arr.data(), (uint32_t)hdr.aux.size());
+        }
         ret = view_fast_binary(rd, fout, gpu, rec_out, sig_out, batch);
         eof = true;
     }

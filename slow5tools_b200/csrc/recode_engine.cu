@@ -250,7 +250,8 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     {
         StageScope ts(ctx, st, ST_GLUE);
         CU(launch_rec_locate(cur, cur_off, cur_len, n,
-                             j.in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (j.in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra, st, st_dep));
+                             j.in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (j.in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra, st, st_dep,
+                             &ctx->aux_layout));
         ctx->launches += 1;
     }
     // ---- signal stage
@@ -649,6 +650,22 @@ int s5b_ctx_stage_report(s5b_ctx_t *ctx, double *ms, uint64_t *count, int reset)
             t.count[i] = 0;
         }
     }
+    return S5B_OK;
+}
+
+int s5b_ctx_set_aux_layout(s5b_ctx_t *ctx, const uint8_t *elem_size, const uint8_t *is_array, uint32_t n_fields) {
+    if (!ctx) return S5B_ERR_ARG;
+    s5b::AuxLayout lay;
+    if (n_fields != s5b::AUX_LAYOUT_UNKNOWN) {
+        if (n_fields > (uint32_t)s5b::AUX_LAYOUT_MAX || (n_fields && (!elem_size || !is_array))) return S5B_ERR_ARG;
+        lay.n = n_fields;
+        for (uint32_t f = 0; f < n_fields; ++f) {
+            if (elem_size[f] == 0 || elem_size[f] > 8) return S5B_ERR_ARG;
+            lay.size[f] = elem_size[f];
+            if (is_array[f]) lay.array_mask |= 1ull << f;
+        }
+    }
+    ctx->aux_layout = lay;
     return S5B_OK;
 }
 

@@ -69,7 +69,7 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
 constexpr int RK_WARPS = 8;
 
 __global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
-                                  int sig_is_svb, RecArrays a, const int32_t *in_status) {
+                                  int sig_is_svb, RecArrays a, const int32_t *in_status, const AuxLayout lay) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint8_t *p = rec + rec_off[r];
@@ -108,6 +108,27 @@ __global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, c
                 // a count beyond that cannot decode, and the stages downstream size their slabs from it
                 if (sig_is_svb && ns > sb) st = S5B_ERR_PRESS;
                 aux = (uint32_t)(len - sig_at - sb);
+                // the auxiliary section must be exactly the file's columns (slow5_rec_aux_parse, slow5.c:3088-3166): a primitive
+                // takes its size, an array a u64 count and count elements
+                if (st == S5B_OK && lay.n != AUX_LAYOUT_UNKNOWN) {
+                    const uint8_t *q = p + sig_at + sb;
+                    uint64_t at = 0;
+                    bool ok = true;
+                    for (uint32_t f = 0; f < lay.n && ok; ++f) {
+                        uint64_t cnt = 1;
+                        if ((lay.array_mask >> f) & 1ull) {
+                            if (at + 8 > aux) {
+                                ok = false;
+                                break;
+                            }
+                            cnt = ld_u64_unaligned(q + at);
+                            at += 8;
+                        }
+                        if (cnt > aux || at + cnt * lay.size[f] > aux) ok = false;
+                        at += cnt * lay.size[f];
+                    }
+                    if (!ok || at != aux) st = S5B_ERR_PRESS;
+                }
             }
         }
     }
@@ -291,9 +312,10 @@ unsigned rk_grid(uint64_t n) {
 }  // namespace
 
 cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
-                              int sig_is_svb, RecArrays a, cudaStream_t st, const int32_t *in_status) {
+                              int sig_is_svb, RecArrays a, cudaStream_t st, const int32_t *in_status, const AuxLayout *aux) {
     if (!n) return cudaSuccess;
-    rec_locate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, rec_off, rec_len, n, sig_is_svb, a, in_status);
+    rec_locate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, rec_off, rec_len, n, sig_is_svb, a, in_status,
+                                                                   aux ? *aux : AuxLayout());
     return cudaGetLastError();
 }
 cudaError_t launch_recode_finish(uint64_t n, const uint64_t *img_off, const uint64_t *base_ptr, uint64_t cap, const int32_t *s0,

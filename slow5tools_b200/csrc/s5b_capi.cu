@@ -1211,7 +1211,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
     }
     // ---- where is the signal (slow5.c:2811-2927)
     CU(launch_rec_locate(cur, cur_off, cur_len, n, in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra,
-                         st));
+                         st, nullptr, &ctx->aux_layout));
     ctx->launches += 1;
     {
         int rc = check_status(ra.status);

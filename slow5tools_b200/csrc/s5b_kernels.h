@@ -109,9 +109,19 @@ struct RecArrays {           // per-record device arrays, n entries each (SoA)
     uint32_t *aux_len;
     int32_t *status;
 };
+// The auxiliary columns of the file (slow5_aux_meta_t): element size of every field and which ones are arrays (u64 count first).
+// n == AUX_LAYOUT_UNKNOWN: the caller did not say, the auxiliary section is taken as it is.
+constexpr uint32_t AUX_LAYOUT_UNKNOWN = 0xffffffffu;
+constexpr int AUX_LAYOUT_MAX = 64;
+struct AuxLayout {
+    uint32_t n = AUX_LAYOUT_UNKNOWN;
+    uint64_t array_mask = 0;
+    uint8_t size[AUX_LAYOUT_MAX] = {0};
+};
 // in_status (optional): the status the record decompression left; a failed record is marked and skipped
 cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
-                              int sig_is_svb, RecArrays a, cudaStream_t st, const int32_t *in_status = nullptr);
+                              int sig_is_svb, RecArrays a, cudaStream_t st, const int32_t *in_status = nullptr,
+                              const AuxLayout *aux = nullptr);
 // elementwise size planning: mode selects which length is written to out[]
 enum RecPlan { PLAN_SIG_SAMPLES = 0, PLAN_SVB_BOUND = 1, PLAN_PACKED_LEN = 2, PLAN_ZLIB_BOUND = 3, PLAN_IMAGE_LEN = 4,
                PLAN_INFLATE_GUESS = 5, PLAN_SPLIT = 6, PLAN_SIG_BYTES_RAW = 7, PLAN_EXZD_BOUND = 8, PLAN_PACKED_IMAGE_LEN = 9 };

@@ -306,3 +306,31 @@ def test_text_paths_through_the_gpu_formatter_and_parser(tmp_path):
         ours(str(theirs), "-o", str(a), "-c", "none", "-s", "svb-zd")
         ref(str(theirs), "-o", str(b), "-c", "none", "-s", "svb-zd")
         assert filecmp.cmp(a, b, shallow=False), name
+
+
+def test_inconsistent_aux_section_fails_on_the_device_path_too(tmp_path):
+    """A record whose auxiliary section does not match the header's columns (here: the count of the channel_number string is one too
+    large) stops a conversion with exit 1 on the -K host path (record_parse_binary) and on the device-resident blow5 -> blow5 path
+    (rec_locate_kernel walks the section against the layout `view` hands to s5b_ctx_set_aux_layout), like slow5_rec_aux_parse."""
+    src = os.path.join(FIX, "exp_1_lossless.blow5")          # uncompressed, five auxiliary fields, channel_number (char*) first
+    data = bytearray(open(src, "rb").read())
+    hsize = int.from_bytes(data[64:68], "little")
+    at = 68 + hsize
+    size = int.from_bytes(data[at:at + 8], "little")
+    rec = at + 8
+    idl = int.from_bytes(data[rec:rec + 2], "little")
+    o = rec + 2 + idl + 4 + 32
+    ns = int.from_bytes(data[o:o + 8], "little")
+    aux = o + 8 + 2 * ns
+    cnt = int.from_bytes(data[aux:aux + 8], "little")
+    assert 0 < cnt < 16 and aux + 8 + cnt + 8 + 4 + 1 + 8 == rec + size      # the layout this test assumes
+    good = tmp_path / "good.blow5"
+    ours(src, "-o", str(good), "-c", "zlib", "-s", "svb-zd")                 # the intact file converts
+    data[aux:aux + 8] = (cnt + 1).to_bytes(8, "little")
+    bad = tmp_path / "bad.blow5"
+    bad.write_bytes(bytes(data))
+    for extra in (["-c", "zlib", "-s", "svb-zd"], ["-c", "none", "-s", "svb-zd"], ["-c", "zlib", "-s", "svb-zd", "-K", "3"]):
+        env = dict(os.environ, S5B_VIEW_SLOW_PATH="1") if "-K" in extra else None
+        r = subprocess.run([CLI, "view", str(bad), "-o", str(tmp_path / "o.blow5")] + extra, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, timeout=60, env=env)
+        assert r.returncode == 1, (extra, r.returncode, r.stderr.decode())

@@ -301,6 +301,7 @@ def main():
             f.write("    " + ", ".join("0x%05x" % t for t in tab[i:i + 8]) + ",\n")
         f.write("};\n// HLIT, HDIST, HCLEN, code-length code, run-length coded lengths: the bits after BFINAL / BTYPE\n")
         f.write("constexpr uint32_t CANNED_HDR_BITS = %d;\nconstexpr int CANNED_HDR_WORDS = %d;\n" % (hdr.n, len(words)))
+        f.write("constexpr int CANNED_MAX_LEN = %d;  // longest code (the emit kernel sizes its room for a block from it)\n" % max(lens))
         f.write("__device__ const uint32_t g_canned_hdr[CANNED_HDR_WORDS] = {\n")
         for i in range(0, len(words), 6):
             f.write("    " + ", ".join("0x%08x" % w for w in words[i:i + 6]) + ",\n")

@@ -4,7 +4,7 @@
 TAG=${1:-r2p}
 mkdir -p gpurun_out
 KR='regex:s5b|svbzd|inflate|deflate|rec_|image_|zstd|scan_|exzd|recode_|rebase|ascii|gather_copy'
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 1500 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 2500 --csv \
    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --profile --reads 1000000 > gpurun_out/${TAG}_launches.log 2>&1
 tail -2 gpurun_out/${TAG}_launches.log
 python - <<PY
@@ -22,4 +22,4 @@ with open("gpurun_out/${TAG}_launch_summary.txt", "w") as f:
         line = "%-60s launches %5d  total %9.3f ms  share %5.1f %%" % (k[:60], v[0], v[1], 100 * v[1] / tot)
         print(line); f.write(line + "\n")
 PY
-COUNT=5 SKIP=15 bash tools/gpu_entropy_profile.sh ${TAG} 250000 'inflate_thread|svbzd_decode|svbzd_encode|deflate_count|deflate_emit'
+COUNT=7 SKIP=21 bash tools/gpu_entropy_profile.sh ${TAG} 250000 'inflate_thread|svbzd_decode|svbzd_encode|deflate_count|deflate_emit|deflate_header|deflate_tree'
