@@ -242,7 +242,7 @@ int s5b_ctx_stage_report(s5b_ctx_t *ctx, double *ms, uint64_t *count, int reset)
 int s5b_stage_count(void);
 const char *s5b_stage_name(int stage);
 
-/* The auxiliary columns of the file whose records the transcoder is about to see (slow5_aux_meta_t, slow5.h:222-238): element
+/* The auxiliary columns of the file whose records the transcoder is about to see (slow5_aux_meta_t, slow5.h:198-213): element
  * size in bytes (1..8) of every field in header order and whether it is an array (stored as a u64 count and count elements).
  * With a layout set, a record whose auxiliary section is not exactly these fields fails with S5B_ERR_PRESS, like
  * slow5_rec_aux_parse does (slow5.c:3088-3166); without one (the default, or n_fields = 0xffffffff) the section is carried as it

@@ -280,13 +280,13 @@ __global__ void __launch_bounds__(CNT_WARPS * 32) deflate_count_kernel(const Def
                 continue;
             }
             for (int pass = 0; pass < 2; ++pass) {
+                WordReader rd;
+                if (mode == MODE_LIT) rd.start(src + b0, slab_end, lane);  // (in flight while the histogram is cleared)
                 for (int i = lane; i < 4 * DEF_ROW; i += 32) (&ws.hist[0][0])[i] = 0;
                 __syncwarp();
                 uint32_t s1 = 0, s2 = 0, eqc = 0;
                 nmatch = 0;
                 if (mode == MODE_LIT) {
-                    WordReader rd;
-                    rd.start(src + b0, slab_end, lane);
                     uint32_t *h = ws.hist[lane & 3];
                     uint32_t carry = 0;  // last byte of the previous strip (for the repeat count only)
                     const uint32_t nstrip = (blen + 127) >> 7;
@@ -656,6 +656,11 @@ __device__ __forceinline__ void block_header(const DefWork &wk, const uint64_t t
     uint32_t run_v = 0, run_n = 0;
     for (int w = 0; w < DEF_ROW / 4; ++w) {
         const uint32_t v = len4[w];
+        if (v == 0 && run_n && run_v == 0 && 4 * w + 3 < hlit) {  // four more unused symbols inside a run of them (most words)
+            run_n += 4;
+            tab4[w] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
         uint32_t e[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -855,6 +860,11 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
             const int hdist = 1;
             int hlit = 286, ncl = 0, hclen = 19;
             uint32_t dyn_bits;
+            // the first loads of the block are issued here, so that they are in flight while the header is being written
+            WordReader rd;
+            uint32_t run_next = 0x100u;
+            if (mode == MODE_LIT) rd.start(src + b0, slab_end, lane);
+            else run_next = (uint32_t)lane < blen ? (uint32_t)src[b0 + lane] : 0x100u;
             const bool prebuilt = !canned && !wk.hdr_by_warp;  // table and header bits come from the header kernel
             const uint32_t pre_bits = info.z;
             if (canned) {
@@ -1087,8 +1097,6 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
                 // ---- tokens.  Same tokenisation as the counting kernel; a warp prefix scan over the token bit counts
                 // places every lane's bits.
                 if (mode == MODE_LIT) {
-                    WordReader rd;
-                    rd.start(src + b0, slab_end, lane);
                     const uint32_t nstrip = (blen + 127) >> 7;
                     for (uint32_t t = 0; t < nstrip; ++t) {
                         if ((bo.bitpos >> 3) + 256 > DEF_OUT) bo.flush(lane, false);
@@ -1122,8 +1130,9 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) deflate_emit_kernel(const Def
                     uint32_t prev0 = b0 ? (uint32_t)src[b0 - 1] : 0x200u;
                     for (uint32_t t0 = 0; t0 < blen; t0 += 32) {
                         if ((bo.bitpos >> 3) + 80 > DEF_OUT) bo.flush(lane, false);
-                        const uint32_t i = t0 + lane;
-                        const uint32_t b = i < blen ? (uint32_t)src[b0 + i] : 0x100u;
+                        const uint32_t b = run_next;  // (the strip after this one is requested now: one iteration to land)
+                        const uint32_t i2 = t0 + 32 + lane;
+                        run_next = i2 < blen ? (uint32_t)src[b0 + i2] : 0x100u;
                         const Token tk = strip_token(b, prev0, lane);
                         prev0 = __shfl_sync(FULL, b, 31);
                         uint32_t bits = 0, nbits = 0;
