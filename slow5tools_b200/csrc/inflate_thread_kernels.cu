@@ -42,7 +42,7 @@ namespace inft {
 #define S5B_TI_RING 64
 #endif
 #ifndef S5B_TI_HOT
-#define S5B_TI_HOT 128
+#define S5B_TI_HOT 160
 #endif
 constexpr int TI_WARPS = 2;
 constexpr int TI_CTAS_PER_SM = S5B_TI_CTAS;  // x 2 warps per SM
@@ -106,24 +106,36 @@ struct Bits {
     const uint2 *base; // aligned pair of words holding the first stream byte
     uint32_t pi, np;   // next pair to load, number of pairs that hold stream bytes
     uint32_t w0, w1;   // the current window: the next 32 bits are one funnel shift
-    uint32_t q0, q1, q2; // the words behind it; they arrive two at a time (one 64-bit load per 8 bytes of stream: the 32
-                         // lanes read 32 different lines, so every load instruction is up to 32 trips through the L1)
+    uint32_t q0;       // the word behind the window
+    // The words behind q0 arrive two at a time (one 64-bit load per 8 bytes of stream: the 32 lanes read 32 different lines,
+    // so every load instruction is up to 32 trips through the L1) into two 64-bit registers that take turns: q0 is fed from
+    // pa (low word, high word), then from pb, and a pair is requested again the moment its high word has been taken -- into
+    // the same registers, first touched two window shifts later.  (Every formulation in which the loaded value had to be
+    // moved -- unpacked into 32-bit registers, or handed from a "pending" to a "next" variable -- made the register
+    // allocator load into a temporary and copy it right behind the LDG, which waits for the load on the spot: 15 % of the
+    // kernel's stall samples.)
+    unsigned long long pa, pb;
+    uint32_t cnt;      // which word q0 takes next: 0 pa.lo, 1 pa.hi, 2 pb.lo, 3 pb.hi
     uint32_t off;      // consumed bits of w0 (0..31)
     uint32_t avail;    // stream bits left (from the current position)
-    uint32_t fill;     // valid words among q0..q2 (1..3)
-    __device__ __forceinline__ uint2 ld() {
-        const uint2 v = pi < np ? __ldg(base + pi) : make_uint2(0u, 0u);
+    // the next pair of the stream into v.  Behind the end of the stream the last pair is read again: those bits are never
+    // taken for stream bits (`avail`), and an unconditional load keeps the compiler from wrapping it in a branch.
+    __device__ __forceinline__ void ld(unsigned long long &v) {
+        const uint2 *p = base + min(pi, np - 1u);
+        asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
         ++pi;
-        return v;
     }
     __device__ __forceinline__ void start(const uint8_t *p, uint32_t len) {
         const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
         base = reinterpret_cast<const uint2 *>(p - sk);
         pi = 0;
         np = (sk + len + 7u) >> 3;
-        const uint2 a = ld(), b = ld();
-        w0 = a.x, w1 = a.y, q0 = b.x, q1 = b.y, q2 = 0;
-        fill = 2;
+        unsigned long long a;
+        ld(a);
+        ld(pa);
+        ld(pb);
+        w0 = (uint32_t)a, w1 = (uint32_t)(a >> 32), q0 = (uint32_t)pa;
+        cnt = 1;
         off = sk * 8u;
         avail = len * 8u;
         if (off >= 32) {  // the stream starts in the second word of its pair
@@ -131,19 +143,15 @@ struct Bits {
             shift();
         }
     }
-    // one word leaves the window; when only one word is left behind it, the next pair is requested (it is needed two
-    // shifts later: the latency hides behind the symbols decoded in between)
+    // one word leaves the window
     __device__ __forceinline__ void shift() {
         w0 = w1;
         w1 = q0;
-        q0 = q1;
-        q1 = q2;
-        if (--fill == 1) {
-            const uint2 v = ld();
-            q1 = v.x;
-            q2 = v.y;
-            fill = 3;
-        }
+        const unsigned long long x = (cnt & 2u) ? pb : pa;
+        q0 = (cnt & 1u) ? (uint32_t)(x >> 32) : (uint32_t)x;
+        if (cnt == 1u) ld(pa);
+        if (cnt == 3u) ld(pb);
+        cnt = (cnt + 1u) & 3u;
     }
     __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(w0, w1, off); }
     __device__ __forceinline__ uint32_t peek(uint32_t n) const { return peek32() & ((1u << n) - 1u); }
@@ -335,8 +343,10 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
         uint32_t L1 = 0, L2 = 0, L3 = 0, L4 = 0, L5 = 0, L6 = 0, L7 = 0, L8 = 0, L9 = 0, L10 = 0, L11 = 0, L12 = 0, L13 = 0,
                  L14 = 0, L15 = 0;
         in.base = reinterpret_cast<const uint2 *>(a.in);
-        in.pi = in.np = in.w0 = in.w1 = in.q0 = in.q1 = in.q2 = in.off = in.avail = 0;
-        in.fill = 2;
+        in.pi = in.np = in.w0 = in.w1 = in.q0 = in.off = in.avail = 0;
+        in.pa = in.pb = 0;
+        in.cnt = 0;
+        in.np = 1;
         out.ring = sm.ring;
         out.dst = a.out;
         out.cap = out.total = out.flushed = out.bias = 0;
