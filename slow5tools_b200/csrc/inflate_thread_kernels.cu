@@ -50,6 +50,12 @@ constexpr int RING = S5B_TI_RING;            // per-lane output ring (bytes): st
 constexpr int FLUSH_EVERY = RING / 8;        // iterations; a lane produces <= 4 bytes per iteration: RING / 2 + 15 unflushed < RING
 constexpr uint32_t ADLER_MOD = 65521u;
 
+// The deflate encoder of this library codes the front part of every record under one code fixed ahead of time
+// (deflate_kernels.cu): such a block's header is always the same 480 bits.  A lane that finds exactly those bits behind
+// BFINAL / BTYPE loads the finished decode tables below instead of reading the header and building them (one of the two
+// blocks of every record this library wrote).  Any other header -- every stream zlib wrote -- goes the general way.
+#include "inflate_canned.inc"
+
 constexpr int HOT = S5B_TI_HOT;  // sorted symbols kept in shared memory (canonical order puts the frequent ones first)
 // per-lane shared memory: what the symbol loop touches on every iteration; the code lengths of a block header are parked
 // on the same bytes (as nibbles) while the block's codes are being built
@@ -125,20 +131,22 @@ struct Bits {
         asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
         ++pi;
     }
-    __device__ __forceinline__ void start(const uint8_t *p, uint32_t len) {
+    // position the reader `bit` bits into the stream of `len` bytes at p (bit <= 8 len)
+    __device__ __forceinline__ void start(const uint8_t *p, uint32_t len, uint32_t bit = 0) {
         const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
         base = reinterpret_cast<const uint2 *>(p - sk);
-        pi = 0;
         np = (sk + len + 7u) >> 3;
+        const uint32_t b = sk * 8u + bit;
+        pi = b >> 6;
         unsigned long long a;
         ld(a);
         ld(pa);
         ld(pb);
         w0 = (uint32_t)a, w1 = (uint32_t)(a >> 32), q0 = (uint32_t)pa;
         cnt = 1;
-        off = sk * 8u;
-        avail = len * 8u;
-        if (off >= 32) {  // the stream starts in the second word of its pair
+        off = b & 63u;
+        avail = len * 8u - bit;
+        if (off >= 32) {  // the position is in the second word of its pair
             off -= 32;
             shift();
         }
@@ -314,6 +322,26 @@ __device__ __forceinline__ int canon_decode(const Bits &b, const uint16_t *lim, 
     return sorted[base[l] + (int)(c15 >> (15 - l))];
 }
 
+// do the CANNED_HDR_BITS bits that start `bit` bits into the stream at p (len bytes, all of them inside it) equal the canned header?
+__device__ __forceinline__ bool canned_header_at(const uint8_t *p, uint32_t len, uint32_t bit) {
+    const uint32_t sk = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - sk);
+    const uint32_t last = (sk + len - 1u) >> 2;  // last word that holds a stream byte
+    const uint32_t b = sk * 8u + bit;
+    const uint32_t sh = b & 31u;
+    uint32_t i = b >> 5;
+    uint32_t lo = __ldg(w + i);
+    bool same = true;
+#pragma unroll 5
+    for (int q = 0; q < CANNED_HDR_WORDS; ++q) {
+        ++i;
+        const uint32_t hi = __ldg(w + min(i, last));
+        same = same && __funnelshift_r(lo, hi, sh) == g_canned_hdr[q];
+        lo = hi;
+    }
+    return same;
+}
+
 __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_kernel(const InflateArgs a, uint32_t max_len,
                                                                                         TiScratch *scratch_rows) {
     __shared__ TiSmem smem[TI_WARPS * 32];
@@ -339,6 +367,8 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
         bool last_block = false;
         uint32_t aux = 0, m_dist = 0;  // stored bytes left / match bytes left, match distance
         int dist_max = 0;              // longest distance code of the current block
+        const uint8_t *src_p = a.in;   // first byte of the lane's stream
+        const uint16_t *rare = sc.lit_sorted;  // sorted symbols beyond the ones in shared memory: the lane's own row, or the canned table
         // the literal/length code limits of the current block, one register per length
         uint32_t L1 = 0, L2 = 0, L3 = 0, L4 = 0, L5 = 0, L6 = 0, L7 = 0, L8 = 0, L9 = 0, L10 = 0, L11 = 0, L12 = 0, L13 = 0,
                  L14 = 0, L15 = 0;
@@ -360,7 +390,8 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                 a.out_len[r] = 0;
                 mine = false;
             } else {
-                in.start(a.in + ioff, ilen);
+                src_p = a.in + ioff;
+                in.start(src_p, ilen);
                 out.dst = a.out + a.out_off[r];
                 const uint64_t cap64 = a.out_off[r + 1] - a.out_off[r];
                 out.cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)cap64;
@@ -379,7 +410,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
         while (__any_sync(FULL, state != ST_DONE)) {
             // ================= block boundary, in phases that all 32 lanes walk through together =================
             const bool hb = state == ST_BLOCK;
-            bool dynamic = false, tables = false;
+            bool dynamic = false, tables = false, canned = false;
             int hlit = 288, hdist = 32;
             uint32_t hclen = 0;
             // ---- phase 1: trailer after the final block, else the 3 header bits and what follows them directly
@@ -418,6 +449,8 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                         tables = true;
                     } else if (in.avail < 14) {
                         end_kind = END_TRUNC;
+                    } else if (in.avail >= CANNED_HDR_BITS && canned_header_at(src_p, ilen, ilen * 8u - in.avail)) {
+                        canned = true;
                     } else {
                         hlit = (int)in.peek(5) + 257;
                         hdist = (int)(in.peek(10) >> 5) + 1;
@@ -426,6 +459,27 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                         if (hlit > 286 || hdist > 30) end_kind = END_ERR;  // "too many length or distance symbols"
                         else dynamic = true;
                     }
+                }
+            }
+            if (__any_sync(FULL, canned)) {
+                // ---- the encoder's canned block: finished tables instead of phases 2 to 5
+                if (canned) {
+                    in.start(src_p, ilen, ilen * 8u - in.avail + CANNED_HDR_BITS);
+                    uint32_t *lbnw = reinterpret_cast<uint32_t *>(sm.lbn);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) lbnw[q] = g_canned_lbn[q];
+                    uint32_t *s8w = reinterpret_cast<uint32_t *>(sm.sorted8);
+                    for (int q = 0; q < HOT / 4; ++q) s8w[q] = g_canned_sorted8[q];
+                    L1 = g_canned_L[1], L2 = g_canned_L[2], L3 = g_canned_L[3], L4 = g_canned_L[4], L5 = g_canned_L[5];
+                    L6 = g_canned_L[6], L7 = g_canned_L[7], L8 = g_canned_L[8], L9 = g_canned_L[9], L10 = g_canned_L[10];
+                    L11 = g_canned_L[11], L12 = g_canned_L[12], L13 = g_canned_L[13], L14 = g_canned_L[14], L15 = g_canned_L[15];
+                    // one distance code (distance 1), one bit long
+                    sc.aux_lim[1] = 0x4000;
+                    sc.aux_base[1] = 0;
+                    sc.aux_sorted[0] = 0;
+                    dist_max = 1;
+                    rare = g_canned_sorted;
+                    state = ST_SYM;
                 }
             }
             if (__any_sync(FULL, tables)) {
@@ -540,7 +594,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                     end_kind = END_ERR;
                     tables = false;
                 }
-                dist_max = maxl;
+                if (tables) dist_max = maxl;  // (lanes that loaded canned tables in this round keep theirs)
                 st = build_code<288, 2>(tables, [&](int q) { return sm.len_at(q); }, hlit, sc.lit_lim,
                                         reinterpret_cast<int16_t *>(sm.lbn), sm.lbn + 1, sc.lit_sorted, &maxl);
                 // inftrees.c: over-subscribed never; incomplete only for a single 1-bit code
@@ -570,6 +624,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                     L7 = sc.lit_lim[7] << 4 | 7u, L8 = sc.lit_lim[8] << 4 | 8u, L9 = sc.lit_lim[9] << 4 | 9u;
                     L10 = sc.lit_lim[10] << 4 | 10u, L11 = sc.lit_lim[11] << 4 | 11u, L12 = sc.lit_lim[12] << 4 | 12u;
                     L13 = sc.lit_lim[13] << 4 | 13u, L14 = sc.lit_lim[14] << 4 | 14u, L15 = sc.lit_lim[15] << 4 | 15u;
+                    rare = sc.lit_sorted;
                     state = ST_SYM;
                 }
             }
@@ -598,7 +653,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                     } else {
                         const uint32_t lw = lbn32[l];
                         const uint32_t si = (lw + (__brev(w32) >> (32u - l))) & 0xffffu;
-                        const uint32_t lo8 = si < (uint32_t)HOT ? (uint32_t)sm.sorted8[si] : (uint32_t)(sc.lit_sorted[si] & 0xffu);
+                        const uint32_t lo8 = si < (uint32_t)HOT ? (uint32_t)sm.sorted8[si] : (uint32_t)(rare[si] & 0xffu);
                         if (si < (lw >> 16)) {
                             // a literal -- and, most of the time, another one behind it: the 32-bit window holds two codes,
                             // so the second is decoded on the spot (anything else is left for the next iteration)
@@ -609,7 +664,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                                 const uint32_t lw2 = lbn32[l2];
                                 const uint32_t si2 = (lw2 + (r2 >> (32u - l2))) & 0xffffu;
                                 if (si2 < (lw2 >> 16)) {
-                                    out.put(si2 < (uint32_t)HOT ? (uint32_t)sm.sorted8[si2] : (uint32_t)(sc.lit_sorted[si2] & 0xffu));
+                                    out.put(si2 < (uint32_t)HOT ? (uint32_t)sm.sorted8[si2] : (uint32_t)(rare[si2] & 0xffu));
                                     l += l2;
                                     // ... and a third one from the word behind the window
                                     const uint32_t r3 = __brev(in.peek32_at(l));
@@ -618,7 +673,7 @@ __global__ void __launch_bounds__(TI_WARPS * 32, TI_CTAS_PER_SM) inflate_thread_
                                         const uint32_t lw3 = lbn32[l3];
                                         const uint32_t si3 = (lw3 + (r3 >> (32u - l3))) & 0xffffu;
                                         if (si3 < (lw3 >> 16)) {
-                                            out.put(si3 < (uint32_t)HOT ? (uint32_t)sm.sorted8[si3] : (uint32_t)(sc.lit_sorted[si3] & 0xffu));
+                                            out.put(si3 < (uint32_t)HOT ? (uint32_t)sm.sorted8[si3] : (uint32_t)(rare[si3] & 0xffu));
                                             l += l3;
                                         }
                                     }

@@ -306,6 +306,53 @@ def main():
         for i in range(0, len(words), 6):
             f.write("    " + ", ".join("0x%08x" % w for w in words[i:i + 6]) + ",\n")
         f.write("};\n")
+    # ---- the decoder's side: inflate_thread_kernel recognises the header and loads these instead of building them
+    # (mirrors build_code() in inflate_thread_kernels.cu)
+    cnt = [0] * 16
+    for l in lens[:hlit]:
+        cnt[l] += l > 0
+    base, lim, start = [0] * 16, [0] * 16, [0] * 16
+    code = at = 0
+    for l in range(1, 16):
+        c = cnt[l]
+        base[l] = at - code
+        lim[l] = min((code + c) << (15 - l), 0xffff)
+        start[l] = at
+        at += c
+        code = (code + c) << 1
+    nxt = list(start)
+    srt = [0] * 288
+    hi_start = list(start)
+    for sym in range(hlit):
+        l = lens[sym]
+        if l:
+            srt[nxt[l]] = sym
+            nxt[l] += 1
+            if sym < 256:
+                hi_start[l] = nxt[l]
+    for l in range(1, 16):
+        if cnt[l] == 0:
+            hi_start[l] = start[l]
+    with open(os.path.join(ROOT, "slow5tools_b200", "csrc", "inflate_canned.inc"), "w") as f:
+        f.write("// generated by tools/gen_deflate_canned.py -- do not edit (included inside namespace s5b::inft)\n")
+        f.write("// the header bits of the encoder's canned block (after BFINAL / BTYPE) and the decode tables build_code() would\n")
+        f.write("// make from them: limit << 4 | length per code length, (base & 0xffff) | first non-literal index << 16 per code\n")
+        f.write("// length, the symbols sorted by (length, symbol), their low bytes packed four to a word\n")
+        f.write("constexpr uint32_t CANNED_HDR_BITS = %d;\nconstexpr int CANNED_HDR_WORDS = %d;\n" % (hdr.n, len(words)))
+        f.write("__device__ const uint32_t g_canned_hdr[CANNED_HDR_WORDS] = {\n")
+        for i in range(0, len(words), 6):
+            f.write("    " + ", ".join("0x%08x" % w for w in words[i:i + 6]) + ",\n")
+        f.write("};\n__device__ const uint32_t g_canned_L[16] = {" + ", ".join("0x%05x" % ((lim[l] << 4) | l) for l in range(16)) + "};\n")
+        f.write("__device__ const uint32_t g_canned_lbn[16] = {" + ", ".join("0x%08x" % ((base[l] & 0xffff) | (hi_start[l] << 16)) for l in range(16)) + "};\n")
+        f.write("__device__ const uint16_t g_canned_sorted[288] = {\n")
+        for i in range(0, 288, 16):
+            f.write("    " + ", ".join("%d" % v for v in srt[i:i + 16]) + ",\n")
+        f.write("};\n__device__ const uint32_t g_canned_sorted8[72] = {\n")
+        w8 = [(srt[4 * i] & 255) | ((srt[4 * i + 1] & 255) << 8) | ((srt[4 * i + 2] & 255) << 16) | ((srt[4 * i + 3] & 255) << 24) for i in range(72)]
+        for i in range(0, 72, 8):
+            f.write("    " + ", ".join("0x%08x" % v for v in w8[i:i + 8]) + ",\n")
+        f.write("};\n")
+
 
 if __name__ == "__main__":
     main()
