@@ -477,11 +477,22 @@ def run_ours(args):
     KE = max(2, min(K, 3))
     e2e_step()
     barrier()
+    if args.e2e_only:   # dev: where the two pipelines spend their time while they run side by side
+        cdc.stage_timing(True)
+        cdc2.stage_timing(True)
+        cdc.stage_report(reset=True)
+        cdc2.stage_report(reset=True)
     t0 = time.perf_counter()
     for _ in range(KE):
         nb_e, nb_d = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_stages = None
+    if args.e2e_only:
+        e2e_stages = {"encode_pass_ms": {k: round(v[0] / KE, 2) for k, v in cdc.stage_report(reset=True).items() if v[0] > 0},
+                      "decode_pass_ms": {k: round(v[0] / KE, 2) for k, v in cdc2.stage_report(reset=True).items() if v[0] > 0}}
+        cdc.stage_timing(False)
+        cdc2.stage_timing(False)
     hb = h_back[:Re * (rl + 8)].view(Re, rl + 8)
     assert nb_d == Re * (rl + 8) and torch.equal(hb[:, 8:], h_raw.view(Re, rl)), "e2e round trip failed"
     assert nb_e == nb0 and torch.equal(h_enc[:nb_e], h_img[:nb_e]), "e2e encode image changed between steps"
@@ -499,7 +510,7 @@ def run_ours(args):
     if args.e2e_only:
         if rank == 0:
             print(json.dumps({"e2e_only": True, "e2e_reads_per_s": Re * world * KE / max_over_ranks(e2e_s), "step_s": e2e_s / KE,
-                              "seq_encode_s": e2e_seq[0], "seq_decode_s": e2e_seq[1]}), flush=True)
+                              "seq_encode_s": e2e_seq[0], "seq_decode_s": e2e_seq[1], "stages": e2e_stages}), flush=True)
         cdc.close()
         if world > 1:
             dist.destroy_process_group()

@@ -72,7 +72,8 @@ int lanes_init(s5b_ctx *ctx) {
         CU(cudaEventCreateWithFlags(&l.front, cudaEventDisableTiming));
         CU(cudaMalloc(&l.d_counter, 256));
         CU(cudaMalloc(&l.d_res, 64));
-        CU(cudaHostAlloc(&l.h_res, 64, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&l.h_res, 64, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer(reinterpret_cast<void **>(&l.h_res_dev), l.h_res, 0));
     }
     CU(cudaMalloc(&ctx->d_img_base, 64));
     ctx->lanes_ready = true;
@@ -404,7 +405,11 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
             CU(launch_recode_advance(ctx->d_img_base, L.d_res, j.d_acc, st));
             ctx->launches += 1;
         } else {
-            CU(cudaMemcpyAsync(L.h_res, L.d_res, 24, cudaMemcpyDeviceToHost, st));
+            // the 24 bytes the host waits for go through mapped pinned memory, written by a kernel: as a D2H copy they queued
+            // behind the other lanes' payload copies on the copy engine (4 ms each), and the host, which needs the image size
+            // before it can queue this chunk's payload, learned it that much later
+            CU(launch_recode_publish(L.d_res, L.h_res_dev, st));
+            ctx->launches += 1;
             if (j.abs_off) {
                 // image offsets relative to the chunk (pinned staging, behind the table that has been consumed by now);
                 // finish() adds the chunk's position once it is known

@@ -329,6 +329,16 @@ cudaError_t launch_recode_finish(uint64_t n, const uint64_t *img_off, const uint
     recode_finish_kernel<<<1, 1, 0, st>>>(n, img_off, base_ptr, cap, res);
     return cudaGetLastError();
 }
+__global__ void recode_publish_kernel(const uint64_t *res, volatile uint64_t *host) {
+    host[0] = res[0];
+    host[1] = res[1];
+    host[2] = res[2];
+    __threadfence_system();
+}
+cudaError_t launch_recode_publish(const uint64_t *res, uint64_t *host_mapped, cudaStream_t st) {
+    recode_publish_kernel<<<1, 1, 0, st>>>(res, host_mapped);
+    return cudaGetLastError();
+}
 cudaError_t launch_recode_advance(uint64_t *base_ptr, const uint64_t *res, uint64_t *acc, cudaStream_t st) {
     recode_advance_kernel<<<1, 1, 0, st>>>(base_ptr, res, acc);
     return cudaGetLastError();

@@ -78,7 +78,8 @@ struct RecodeLane {
     PinBuf h_tab;                    // pinned staging of the chunk's record table (up) and image offsets (down)
     unsigned long long *d_counter = nullptr;
     uint64_t *d_res = nullptr;       // [0] image bytes of the chunk, [1] first error (int32 in the low half), [2] its record
-    uint64_t *h_res = nullptr;       // pinned mirror
+    uint64_t *h_res = nullptr;       // pinned mirror (mapped: the device writes it through h_res_dev)
+    uint64_t *h_res_dev = nullptr;
     void release();
 };
 

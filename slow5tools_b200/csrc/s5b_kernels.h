@@ -148,6 +148,8 @@ cudaError_t launch_image_gather(const uint8_t *src, const uint64_t *src_off, con
                                 const uint64_t *img_off, cudaStream_t st, const uint64_t *base_ptr = nullptr,
                                 const uint64_t *res = nullptr, uint64_t *abs_off = nullptr);
 // the sync-free end of a transcoding pass over one chunk (record_kernels.cu)
+// res[0..2] -> mapped pinned host memory (the host reads it after the stream's next event)
+cudaError_t launch_recode_publish(const uint64_t *res, uint64_t *host_mapped, cudaStream_t st);
 cudaError_t launch_recode_finish(uint64_t n, const uint64_t *img_off, const uint64_t *base_ptr, uint64_t cap, const int32_t *s0,
                                  const int32_t *s1, const int32_t *s2, const int32_t *s3, uint64_t *res, cudaStream_t st);
 cudaError_t launch_recode_advance(uint64_t *base_ptr, const uint64_t *res, uint64_t *acc, cudaStream_t st);
