@@ -40,8 +40,8 @@ M_NONE, M_ZLIB, M_SVB_ZD = 0, 1, 2
 # dram__bytes_read.sum + dram__bytes_write.sum per 100 000 records from the committed `ncu --set full` capture
 # (profiles/r2_ncu_full_v2.md: one 250 000-record chunk); bench.py cannot run under a profiler, so the figure is carried and
 # scaled to the launch size
-NCU_TRAFFIC_PER_100K = {"record_press": ((1337.8e6 + 210.9e6) + (241.1e6 + 59.1e6) + (866.5e6 + 981.8e6) + (1730.8e6 + 875.9e6)) / 2.5,
-                        "record_depress": (1373.9e6 + 1788.7e6) / 2.5}    # count + tree + header + emit / inflate_thread
+NCU_TRAFFIC_PER_100K = {"record_press": ((1338.1e6 + 212.4e6) + (240.4e6 + 59.4e6) + (866.6e6 + 984.5e6) + (1729.4e6 + 867.3e6)) / 2.5,
+                        "record_depress": (1338.4e6 + 1609.8e6) / 2.5}    # count + tree + header + emit / inflate_thread
 NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_full_v2.md (ncu --set full, one 250k-record chunk of the same workload), scaled by launch size"
 STAGE_KERNELS = {"record_press": "deflate_count_kernel + deflate_tree_kernel + deflate_header_kernel + deflate_emit_kernel "
                                  "(one launch group per chunk)",
