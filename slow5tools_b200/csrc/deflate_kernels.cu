@@ -1,4 +1,4 @@
-// deflate_kernels.cu -- sm_100a zlib/DEFLATE encoder for batches of records, three kernels.
+// deflate_kernels.cu -- sm_100a zlib/DEFLATE encoder for batches of records, four kernels.
 //
 // Replaces, for whole batches, ptr_compress_zlib / ptr_compress_zlib_solo (slow5lib/src/slow5_press.c:
 // 837-913: deflateInit2(level 6, wbits 15, memLevel 8, default strategy) + deflate(Z_FINISH)), producing
@@ -19,7 +19,7 @@
 //     bytes: the same kind of bytes in every record of every file) does not get a code of its own: it is coded RUN-style
 //     under a code fixed ahead of time (tools/gen_deflate_canned.py), still as a dynamic block whose header is the same
 //     bits every time -- no histogram, sort, tree, canonical codes or header construction for it (that cost as much as
-//     the 4x larger data part), +0.5 % in size;
+//     the 4x larger data part), +0.6 % in size;
 //   * the work is split by the shape of its parallelism:
 //       deflate_count_kernel  one warp per record: Adler-32, byte / length-symbol histogram of every block,
 //                             compaction of the used symbols, bitonic sort in registers -> sorted
@@ -28,10 +28,14 @@
 //                             (Moffat-Katajainen in-place two-queue merge, depths, 15-bit length limiting) on a
 //                             shared-memory row per thread, 32 independent trees per warp instead of one lane
 //                             working while 31 wait;
-//       deflate_emit_kernel   one warp per record: canonical codes, run-length coded header with its 7-bit
-//                             code-length code, token bits placed by a warp prefix scan and OR-ed into a
-//                             shared-memory bit buffer that leaves as 128-bit stores; stored blocks when a
-//                             block would not shrink; Adler-32 trailer.
+//       deflate_header_kernel one THREAD per block: canonical codes (the table the token loops look up), run-length
+//                             coding of the code lengths, the 19-symbol code-length code, the header bits -- into the
+//                             workspace (a warp used to do this for one block at a time inside the emit kernel:
+//                             4 400 warp instructions per block);
+//       deflate_emit_kernel   one warp per record: block header copied from the workspace (or the canned constant),
+//                             token bits placed by a warp prefix scan and OR-ed into a shared-memory bit buffer that
+//                             leaves as 128-bit stores; stored blocks when a block would not shrink (canned blocks are
+//                             measured after they have been coded and taken back if they did not); Adler-32 trailer.
 //     (the round-1 single kernel spent 35 % of its issue slots in lane 0's merge loop and the shared-memory sort)
 #include <cstdlib>
 #include "s5b_kernels.h"
