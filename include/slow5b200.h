@@ -248,6 +248,12 @@ const char *s5b_stage_name(int stage);
  * slow5_rec_aux_parse does (slow5.c:3088-3166); without one (the default, or n_fields = 0xffffffff) the section is carried as it
  * is.  Conversions that keep both methods copy the stored records without opening them either way. */
 int s5b_ctx_set_aux_layout(s5b_ctx_t *ctx, const uint8_t *elem_size, const uint8_t *is_array, uint32_t n_fields);
+
+/* merge (src/merge.c:52, `read->read_group = list[file][read->read_group]`): while a table is set, s5b_blow5_recode_batch_host /
+ * s5b_blow5_recode_host write every record with read_group map[read_group]; a record whose read_group is >= n fails with
+ * S5B_ERR_PRESS.  n = 0 clears the table.  Not available to s5b_blow5_recode_dev (the renumbering is done in the library's own
+ * copy of the records): S5B_ERR_ARG there. */
+int s5b_ctx_set_rg_map(s5b_ctx_t *ctx, const uint32_t *map, uint32_t n);
 /* The per-record work of index building (slow5_idx_build, slow5lib/src/slow5_idx.c:283-334) for a batch: the read_id of
  * every stored record.  Records compressed with in_rec (S5B_COMPRESS_NONE / ZLIB / ZSTD) are decompressed on the device --
  * for zlib only their first 256 bytes, like the reference's partial decompression (:290-310), with a full pass for the

@@ -84,6 +84,7 @@ _SIGS = {
     "s5b_stage_count": (C.c_int, []),
     "s5b_stage_name": (C.c_char_p, [C.c_int]),
     "s5b_ctx_set_aux_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "s5b_ctx_set_rg_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "s5b_ptr_compress_solo": (_vp, [C.c_int, _vp, _sz, _P(_sz)]),
     "s5b_ptr_depress_solo": (_vp, [C.c_int, _vp, _sz, _P(_sz)]),
     "s5b_last_error": (C.c_int, []),

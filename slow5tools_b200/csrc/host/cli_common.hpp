@@ -22,3 +22,8 @@ struct ConvertHooks {
 int convert_records(const s5b::Header &hdr, s5b::Fmt fmt_in, const std::function<int(std::vector<uint8_t> &)> &next, FILE *fout,
                     s5b_ctx_t *gpu, s5b::Fmt fmt_out, int rec_out, int sig_out, long batch, int threads,
                     const ConvertHooks *hooks = nullptr);
+
+// blow5 -> blow5 with whole batches resident on the device (view_main.cpp: pinned chunk pipeline around s5b_blow5_recode_host):
+// converts the records of `rd` (positioned behind its header) to (rec_out, sig_out) and appends them to fout.  The context's
+// auxiliary layout / read-group table (s5b_ctx_set_aux_layout, s5b_ctx_set_rg_map) apply.  0 = ok.
+int blow5_fast_convert(s5b::Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int sig_out);

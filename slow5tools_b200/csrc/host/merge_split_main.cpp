@@ -415,6 +415,25 @@ int merge_main(int argc, char **argv) {
         bool same_layout = src.size() == h.aux.size();
         for (size_t p = 0; same_layout && p < src.size(); ++p) same_layout = src[p] == (int)p;
         const std::vector<uint32_t> &map = rg_map[fi];
+        if (rd.fmt == FMT_BINARY && o.fmt_out == FMT_BINARY && need_gpu && !o.lossy && same_layout && h.aux.size() <= 64 &&
+            !getenv("S5B_VIEW_SLOW_PATH")) {
+            // blow5 -> blow5 and nothing to re-lay: whole batches stay on the device, which renumbers the read groups and
+            // checks every record against the header (read group in range, auxiliary section = the header's columns)
+            std::vector<uint8_t> sz(h.aux.size() + 1), arr(h.aux.size() + 1);
+            for (size_t f = 0; f < h.aux.size(); ++f) {
+                sz[f] = h.aux[f].size;
+                arr[f] = h.aux[f].is_array() ? 1 : 0;
+            }
+            if (s5b_ctx_set_aux_layout(gpu, sz.data(), arr.data(), (uint32_t)h.aux.size()) != S5B_OK ||
+                s5b_ctx_set_rg_map(gpu, map.data(), (uint32_t)map.size()) != S5B_OK) {
+                MS_ERROR("%s", "cannot hand the header's layout to the GPU codec");
+                return 1;
+            }
+            ret = blow5_fast_convert(rd, fout, gpu, o.rec_out, o.sig_out);
+            s5b_ctx_set_rg_map(gpu, nullptr, 0);
+            reader_close(rd);
+            continue;
+        }
         ConvertHooks hooks;
         hooks.hdr_out = &out;
         hooks.transform = [&](size_t, Record &rec, std::vector<uint8_t> &aux_store) {

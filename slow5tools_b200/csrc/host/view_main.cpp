@@ -377,6 +377,10 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
 
 }  // namespace
 
+int blow5_fast_convert(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int sig_out) {
+    return view_fast_binary(rd, fout, gpu, rec_out, sig_out, 0);
+}
+
 // The general conversion loop (the body of slow5_convert_parallel, src/view.c:254-301, and of `get`'s per-batch work,
 // src/get.c:37-66): records come from `next` -- 1 = one stored record (binary: without its size prefix; text: one line
 // without the newline) placed in the buffer, 0 = no more, -1 = error already reported -- are decompressed, parsed,

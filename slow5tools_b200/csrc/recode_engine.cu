@@ -50,6 +50,9 @@ void recode_lanes_release(s5b_ctx *ctx) {
     for (int i = 0; i < NLANE; ++i) ctx->lane[i].release();
     if (ctx->d_img_base) cudaFree(ctx->d_img_base);
     ctx->d_img_base = nullptr;
+    if (ctx->d_rg_map) cudaFree(ctx->d_rg_map);
+    ctx->d_rg_map = nullptr;
+    ctx->rg_map_n = 0;
     for (auto &m : ctx->timer.marks) {
         cudaEventDestroy(m.a);
         cudaEventDestroy(m.b);
@@ -127,6 +130,7 @@ struct Job {
     uint64_t *d_acc;      // device form: [0] total image bytes, [1] first error
     const uint64_t *d_tab_off;  // device form: the whole record table, uploaded once per call
     const uint32_t *d_tab_len;
+    bool edits = false;   // the records themselves change (read groups renumbered): stored records cannot be passed through
 };
 
 struct Chunk {
@@ -152,9 +156,10 @@ Bounds chunk_bounds(const Job &j, uint64_t span, uint64_t n) {
         b.packed = D + sig_out + 32 * n + 64;
     }
     const uint64_t P = j.in_sig != j.out_sig ? b.packed : D;
-    if ((j.out_rec == S5B_COMPRESS_ZLIB || j.out_rec == S5B_COMPRESS_ZSTD) && !(j.in_rec == j.out_rec && j.in_sig == j.out_sig))
+    const bool untouched = j.in_rec == j.out_rec && j.in_sig == j.out_sig && !j.edits;  // stored records are the answer
+    if ((j.out_rec == S5B_COMPRESS_ZLIB || j.out_rec == S5B_COMPRESS_ZSTD) && !untouched)
         b.z = P + 6 * (P / 6144 + 2 * n) + 48 * n + 64;
-    const uint64_t F = b.z ? b.z : (j.in_rec == j.out_rec && j.in_sig == j.out_sig ? span : P);
+    const uint64_t F = b.z ? b.z : (untouched ? span : P);
     b.img = F + 8 * n + 64;
     if (j.in_sig != j.out_sig && j.out_rec == S5B_COMPRESS_NONE) b.img = b.packed + 8 * n + 64;
     return b;
@@ -250,10 +255,16 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     // ---- where is the signal (slow5.c:2811-2927)
     {
         StageScope ts(ctx, st, ST_GLUE);
+        s5b::AuxLayout lay = ctx->aux_layout;
+        lay.rg_n = ctx->rg_map_n;
         CU(launch_rec_locate(cur, cur_off, cur_len, n,
-                             j.in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (j.in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra, st, st_dep,
-                             &ctx->aux_layout));
+                             j.in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (j.in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra, st, st_dep, &lay));
         ctx->launches += 1;
+        if (ctx->rg_map_n) {
+            // in place: `cur` is this lane's own copy of the records (inflated, or the uploaded input)
+            CU(launch_rec_rg_remap(const_cast<uint8_t *>(cur), cur_off, ra, n, ctx->d_rg_map, st));
+            ctx->launches += 1;
+        }
     }
     // ---- signal stage
     const uint8_t *sig_src = nullptr;  // nullptr = pass the stored bytes through
@@ -345,7 +356,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     }
     // ---- record compression (slow5.c:4050)
     if (j.out_rec == S5B_COMPRESS_ZLIB || j.out_rec == S5B_COMPRESS_ZSTD) {
-        if (j.in_rec == j.out_rec && j.in_sig == j.out_sig) {
+        if (j.in_rec == j.out_rec && j.in_sig == j.out_sig && !j.edits) {
             // nothing changed inside the records: the stored compressed records are the answer
             fin = j.src_dev ? j.src + (c.span0 - (c.span0 & 15u)) : static_cast<const uint8_t *>(L.in.p);
             fin_off = d_rec_off;
@@ -484,6 +495,7 @@ int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_
     if (!cut_chunks(rec_off, rec_len, n, in_bytes, ctx->recode_chunk_records, ctx->recode_chunk_bytes, chunks)) return S5B_ERR_ARG;
     Job j{in_rec, in_sig, out_rec, out_sig, h_in, false, in_bytes, rec_off, rec_len, n, h_out, false, out_cap, out_img_off, nullptr,
           nullptr, nullptr};
+    j.edits = ctx->rg_map_n != 0;
     const size_t nc = chunks.size();
     uint64_t pos = 0;           // image bytes placed so far
     bool overflow = false;      // the image outgrew out_cap: keep sizing, stop copying
@@ -600,6 +612,7 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
     uint32_t *d_tab_len = reinterpret_cast<uint32_t *>(d_tab_off + n);
     CU(cudaMemcpyAsync(d_tab_off, rec_off, n * 8, cudaMemcpyHostToDevice, L.stream));
     CU(cudaMemcpyAsync(d_tab_len, rec_len, n * 4, cudaMemcpyHostToDevice, L.stream));
+    if (ctx->rg_map_n) return S5B_ERR_ARG;  // renumbering works on the library's own copy of the records: host form only
     Job j{in_rec, in_sig, out_rec, out_sig, d_in, true, in_bytes, rec_off, rec_len, n, d_out, true, out_cap, d_img_off, d_result,
           d_tab_off, d_tab_len};
     for (const Chunk &c : chunks) {
@@ -654,6 +667,23 @@ int s5b_ctx_stage_report(s5b_ctx_t *ctx, double *ms, uint64_t *count, int reset)
             t.ms[i] = 0;
             t.count[i] = 0;
         }
+    }
+    return S5B_OK;
+}
+
+int s5b_ctx_set_rg_map(s5b_ctx_t *ctx, const uint32_t *map, uint32_t n) {
+    if (!ctx || (n && !map)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    if (ctx->d_rg_map) {
+        // transcodes that use the old table have been waited for by their callers (the host form returns when its image is complete)
+        cudaFree(ctx->d_rg_map);
+        ctx->d_rg_map = nullptr;
+    }
+    ctx->rg_map_n = 0;
+    if (n) {
+        CU(cudaMalloc(&ctx->d_rg_map, (size_t)n * 4));
+        CU(cudaMemcpy(ctx->d_rg_map, map, (size_t)n * 4, cudaMemcpyHostToDevice));
+        ctx->rg_map_n = n;
     }
     return S5B_OK;
 }

@@ -87,6 +87,11 @@ __global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, c
         } else {
             const uint64_t lrs = ld_u64_unaligned(p + head);
             sig_at = head + 8;
+            if (lay.rg_n) {  // the record's read group must be one the header names (it is renumbered through a table later)
+                const uint8_t *g = p + head - 36;
+                const uint32_t rg = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
+                if (rg >= lay.rg_n) st = S5B_ERR_PRESS;
+            }
             // the field counts samples for a raw signal and bytes for a compressed one (slow5.c:3983-3987)
             // sig_is_svb: 0 raw int16, 1 svb-zd stream (u32 sample count first), 2 ex-zd stream (u64 count at byte 1)
             const uint64_t sb = sig_is_svb ? lrs : lrs * 2;
@@ -368,6 +373,18 @@ cudaError_t launch_sig_extract(const uint8_t *rec, const uint64_t *rec_off, RecA
                                const uint64_t *sig_off, cudaStream_t st) {
     if (!n) return cudaSuccess;
     sig_extract_kernel<<<rk_grid(n), RK_WARPS * 32, 0, st>>>(rec, rec_off, a, n, sig, sig_off);
+    return cudaGetLastError();
+}
+__global__ void rec_rg_remap_kernel(uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint32_t *rg_map) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || a.status[r] != S5B_OK) return;
+    uint8_t *g = rec + rec_off[r] + a.head_len[r] - 36;  // the field in front of the four doubles
+    const uint32_t rg = rg_map[(uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24)];
+    g[0] = (uint8_t)rg, g[1] = (uint8_t)(rg >> 8), g[2] = (uint8_t)(rg >> 16), g[3] = (uint8_t)(rg >> 24);
+}
+cudaError_t launch_rec_rg_remap(uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint32_t *rg_map, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    rec_rg_remap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, rec_off, a, n, rg_map);
     return cudaGetLastError();
 }
 cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint8_t *sig_src,

@@ -1210,9 +1210,17 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
         cur_cap = round_up(total, 16);
     }
     // ---- where is the signal (slow5.c:2811-2927)
-    CU(launch_rec_locate(cur, cur_off, cur_len, n, in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra,
-                         st, nullptr, &ctx->aux_layout));
-    ctx->launches += 1;
+    {
+        s5b::AuxLayout lay = ctx->aux_layout;
+        lay.rg_n = ctx->rg_map_n;
+        CU(launch_rec_locate(cur, cur_off, cur_len, n, in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra,
+                             st, nullptr, &lay));
+        ctx->launches += 1;
+        if (ctx->rg_map_n) {  // merge: read groups renumbered in the context's own copy of the records
+            CU(launch_rec_rg_remap(const_cast<uint8_t *>(cur), cur_off, ra, n, ctx->d_rg_map, st));
+            ctx->launches += 1;
+        }
+    }
     {
         int rc = check_status(ra.status);
         if (rc != S5B_OK) return cuda_fail(ctx, cudaGetLastError());
@@ -1288,7 +1296,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
     }
     // ---- record compression (slow5.c:4050)
     if (out_rec == S5B_COMPRESS_ZLIB || out_rec == S5B_COMPRESS_ZSTD) {
-        if (in_rec == out_rec && in_sig == out_sig) {
+        if (in_rec == out_rec && in_sig == out_sig && !ctx->rg_map_n) {
             // nothing changed inside the records: the stored compressed records are the answer
             fin = static_cast<const uint8_t *>(ctx->r_in.p);
             fin_off = d_rec_off;

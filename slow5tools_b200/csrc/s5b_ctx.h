@@ -113,6 +113,8 @@ struct s5b_ctx {
     int n_lanes = 3;
     uint64_t *d_img_base = nullptr;       // running output offset of a device-resident transcoding pass
     s5b::StageTimer timer;
+    uint32_t *d_rg_map = nullptr;     // read_group renumbering of the file being transcoded (s5b_ctx_set_rg_map), rg_map_n entries
+    uint32_t rg_map_n = 0;
     s5b::AuxLayout aux_layout;        // auxiliary columns of the file being transcoded (s5b_ctx_set_aux_layout), unknown by default
     uint64_t launches = 0;
     size_t chunk_bytes = 32u << 20;  // e2e is flat between 16 and 128 MiB (PCIe bound), 32 MiB marginally best

@@ -114,6 +114,7 @@ struct RecArrays {           // per-record device arrays, n entries each (SoA)
 constexpr uint32_t AUX_LAYOUT_UNKNOWN = 0xffffffffu;
 constexpr int AUX_LAYOUT_MAX = 64;
 struct AuxLayout {
+    uint32_t rg_n = 0;   // > 0: read groups the file's header names (a record's read_group must be below it); 0: not checked
     uint32_t n = AUX_LAYOUT_UNKNOWN;
     uint64_t array_mask = 0;
     uint8_t size[AUX_LAYOUT_MAX] = {0};
@@ -139,6 +140,8 @@ cudaError_t launch_rec_pack(const uint8_t *rec, const uint64_t *rec_off, RecArra
                             const uint64_t *sig_src_off, const uint32_t *sig_src_len, int sig_src_is_samples,
                             int sig_out_compressed, uint8_t *out, const uint64_t *out_off, cudaStream_t st, int image = 0,
                             const uint64_t *base_ptr = nullptr, const uint64_t *res = nullptr, uint64_t *abs_off = nullptr);
+// merge (src/merge.c:52): every good record's read_group renumbered in place through a device table (range checked by rec_locate)
+cudaError_t launch_rec_rg_remap(uint8_t *rec, const uint64_t *rec_off, RecArrays a, uint64_t n, const uint32_t *rg_map, cudaStream_t st);
 // image != 0: out_off[] is the scan of PLAN_PACKED_IMAGE_LEN (align 1) and every record is written behind its u64 size
 // prefix at out + *base_ptr: the packed records are the file image (no separate gather)
 // file image: [u64 size][bytes] per record, back to back

@@ -244,3 +244,56 @@ def test_split_to_compressed_outputs_round_trip(fx, tmp_path):
         s = tmp_path / (f + ".slow5")
         assert run(["view", str(out / f), "-o", str(s)]).returncode == 0
         assert filecmp.cmp(s, os.path.join(exp, f.replace(".blow5", ".slow5")), shallow=False), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rec,sig", [("zlib", "svb-zd"), ("none", "svb-zd"), ("zlib", "none")])
+def test_merge_of_blow5_inputs_on_the_device_path(fx, tmp_path, rec, sig):
+    """BLOW5 inputs whose auxiliary columns need no re-laying stay on the device (read groups renumbered by rec_rg_remap_kernel):
+    same records as the host record loop (S5B_VIEW_SLOW_PATH=1) and as the merge of the SLOW5 originals; the reference reads
+    the result."""
+    a_txt = os.path.join(fx, "merge", "raw", "rg0.slow5")
+    # a second input with the same columns but another run_id: a new read group, 0 -> 1
+    b_txt = tmp_path / "other.slow5"
+    lines = open(os.path.join(fx, "merge", "raw", "rg0_1.slow5"), "rb").read().split(b"\n")
+    b_txt.write_bytes(b"\n".join(l + b"_other" if l.startswith(b"@run_id\t") else l for l in lines))
+    want = tmp_path / "want.slow5"
+    assert run(["merge", a_txt, str(b_txt), "-o", str(want)]).returncode == 0
+    assert b"#num_read_groups\t2" in open(want, "rb").read()
+    ins = []
+    for k, t in enumerate((a_txt, str(b_txt))):
+        b = tmp_path / ("in%d.blow5" % k)
+        assert run(["view", t, "-o", str(b), "-c", rec, "-s", sig]).returncode == 0
+        ins.append(str(b))
+    outs = {}
+    for name, env in (("device", {}), ("host", {"S5B_VIEW_SLOW_PATH": "1"})):
+        out = tmp_path / (name + ".blow5")
+        r = subprocess.run([CLI, "merge"] + ins + ["-o", str(out), "-c", "zlib", "-s", "svb-zd"], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, env=dict(os.environ, **env), timeout=120)
+        assert r.returncode == 0, r.stderr.decode()
+        txt = tmp_path / (name + ".slow5")
+        assert run(["view", str(out), "-o", str(txt)]).returncode == 0
+        outs[name] = txt
+        if os.path.exists(REF):
+            rtxt = tmp_path / (name + ".ref.slow5")
+            subprocess.check_call([REF, "view", str(out), "-o", str(rtxt)], stderr=subprocess.DEVNULL, timeout=60)
+            assert filecmp.cmp(rtxt, want, shallow=False)
+    assert filecmp.cmp(outs["device"], want, shallow=False)
+    assert filecmp.cmp(outs["host"], want, shallow=False)
+    # same methods in and out: the records still have to be rewritten (their read groups change)
+    same = tmp_path / "same.blow5"
+    assert run(["merge"] + ins + ["-o", str(same), "-c", rec, "-s", sig]).returncode == 0
+    stxt = tmp_path / "same.slow5"
+    assert run(["view", str(same), "-o", str(stxt)]).returncode == 0
+    assert filecmp.cmp(stxt, want, shallow=False)
+    # a record whose read group is not in its file's header stops the merge
+    data = bytearray(open(ins[1], "rb").read())
+    if rec == "none":
+        hsize = int.from_bytes(data[64:68], "little")
+        at = 68 + hsize + 8
+        idl = int.from_bytes(data[at:at + 2], "little")
+        data[at + 2 + idl:at + 2 + idl + 4] = (7).to_bytes(4, "little")
+        bad = tmp_path / "bad.blow5"
+        bad.write_bytes(bytes(data))
+        r = run(["merge", ins[0], str(bad), "-o", str(tmp_path / "x.blow5")])
+        assert r.returncode != 0
