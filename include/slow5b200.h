@@ -33,6 +33,7 @@ extern "C" {
 #define S5B_ERR_PRESS    (-13)  /* == SLOW5_ERR_PRESS stream is not a valid svb-zd / zlib stream   */
 #define S5B_ERR_NOSPACE  (-40)  /* output slot smaller than the worst case for that read           */
 #define S5B_ERR_DEVICE   (-41)  /* no CUDA device, no sm_100a image, or a CUDA runtime error       */
+#define S5B_ERR_DATASET  (-42)  /* degrade: a record's digitisation / sampling rate is not the dataset's (s5b_ctx_set_degrade) */
 
 /* enum slow5_press_method (slow5_press.h:61-67): library enum, NOT the file byte */
 #define S5B_COMPRESS_NONE   0
@@ -254,6 +255,21 @@ int s5b_ctx_set_aux_layout(s5b_ctx_t *ctx, const uint8_t *elem_size, const uint8
  * S5B_ERR_PRESS.  n = 0 clears the table.  Not available to s5b_blow5_recode_dev (the renumbering is done in the library's own
  * copy of the records): S5B_ERR_ARG there. */
 int s5b_ctx_set_rg_map(s5b_ctx_t *ctx, const uint32_t *map, uint32_t n);
+
+/* degrade (src/degrade.c:240-263: the view worker with slow5_rec_qts_round between decode and re-encode).  While bits is 1..16,
+ * s5b_blow5_recode_batch_host / _host / _dev round the `bits` least significant bits of every sample away (slow5_arr_qts_round,
+ * slow5lib/src/slow5_press.c:1965-2005: to the nearest multiple of 2^bits, halves up, stored back as int16) before the signal is
+ * re-encoded -- also when the signal method stays the same.  check_dataset != 0 is the reference's `-b auto` rule
+ * (slow5_reccmp, src/degrade.c:195-211): a record whose digitisation or sampling_rate differs from the given values fails with
+ * S5B_ERR_DATASET.  bits = 0 switches the step off. */
+int s5b_ctx_set_degrade(s5b_ctx_t *ctx, int bits, int check_dataset, float digitisation, float sampling_rate);
+/* slow5_arr_qts_round (slow5lib/src/slow5_extra.h:152, slow5_press.c:1991-2005) for a sample slab in HBM, in place, enqueued on
+ * `stream` (a cudaStream_t; NULL = the context's stream); bits 1..16 (0: nothing to do, like the reference). */
+int s5b_qts_round_dev(s5b_ctx_t *ctx, int16_t *d_sig, uint64_t n_samples, int bits, void *stream);
+/* The same for a batch of host arrays: array i holds counts[i] BYTES of int16 samples (any alignment); out_ptrs[i] receives a
+ * malloc'd array of the same size (the caller frees), out_n[i] its size in bytes.  One H2D, one launch, one D2H. */
+int s5b_qts_round_batch_host(s5b_ctx_t *ctx, int bits, const void *const *ptrs, const size_t *counts, size_t n, void **out_ptrs,
+                             size_t *out_n);
 /* The per-record work of index building (slow5_idx_build, slow5lib/src/slow5_idx.c:283-334) for a batch: the read_id of
  * every stored record.  Records compressed with in_rec (S5B_COMPRESS_NONE / ZLIB / ZSTD) are decompressed on the device --
  * for zlib only their first 256 bytes, like the reference's partial decompression (:290-310), with a full pass for the

@@ -71,6 +71,11 @@ int orc_exzd_depress(const uint8_t *in, size_t count, int16_t *out, size_t out_c
 int orc_blow5_recode_record(int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *in, size_t in_len,
                             uint8_t **out, size_t *out_len);
 
+/* ---- lossy degradation (oracle/qts_oracle.c), slow5_press.c:1965-2005 (slow5tools degrade) ----------------------------
+ * bits in 1..16 (0: nothing happens); the int result is truncated into the int16 like the reference's store */
+int orc_qts_round_sample(int sample, int bits);
+void orc_qts_round(int16_t *samples, uint64_t n, int bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ class ERR:
     PRESS = -13
     NOSPACE = -40
     DEVICE = -41
+    DATASET = -42
 
 
 class METHOD:  # enum slow5_press_method, slow5_press.h:61-67
@@ -85,6 +86,9 @@ _SIGS = {
     "s5b_stage_name": (C.c_char_p, [C.c_int]),
     "s5b_ctx_set_aux_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "s5b_ctx_set_rg_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "s5b_ctx_set_degrade": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]),
+    "s5b_qts_round_dev": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp]),
+    "s5b_qts_round_batch_host": (C.c_int, [_vp, C.c_int, _P(_vp), _P(_sz), _sz, _P(_vp), _P(_sz)]),
     "s5b_ptr_compress_solo": (_vp, [C.c_int, _vp, _sz, _P(_sz)]),
     "s5b_ptr_depress_solo": (_vp, [C.c_int, _vp, _sz, _P(_sz)]),
     "s5b_last_error": (C.c_int, []),

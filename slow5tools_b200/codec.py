@@ -234,6 +234,20 @@ class Codec:
         self._check(lib.s5b_ctx_stage_report(self._h, ms, cnt, 1 if reset else 0), "s5b_ctx_stage_report")
         return {lib.s5b_stage_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k)}
 
+    def set_degrade(self, bits, check_dataset=False, digitisation=0.0, sampling_rate=0.0):
+        """src/degrade.c:240-263: while bits > 0 every transcoding pass rounds that many low bits of each sample away"""
+        self._check(lib.s5b_ctx_set_degrade(self._h, int(bits), int(bool(check_dataset)), float(digitisation),
+                                            float(sampling_rate)), "s5b_ctx_set_degrade")
+
+    def qts_round_dev(self, sig, bits, n_samples=None):
+        """slow5_arr_qts_round (slow5_press.c:1991-2005) on an int16 CUDA tensor, in place"""
+        n = sig.numel() if n_samples is None else int(n_samples)
+        self._check(lib.s5b_qts_round_dev(self._h, _ptr(sig), n, int(bits), self._stream()), "s5b_qts_round_dev")
+
+    def qts_round_batch(self, bits, bufs):
+        """host arrays of int16 samples (bytes) -> degraded copies"""
+        return self._batch(lambda h, m, *a: lib.s5b_qts_round_batch_host(h, int(bits), *a), 0, bufs)
+
     def compress_batch(self, method, bufs):
         return self._batch(lib.s5b_compress_batch_host, method, bufs)
 

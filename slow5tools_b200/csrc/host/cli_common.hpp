@@ -17,6 +17,8 @@ struct ConvertHooks {
     std::function<bool(size_t i, s5b::Record &rec, std::vector<uint8_t> &aux_store)> transform;
     // destination of record i of the batch; nullptr: fout
     std::function<FILE *(size_t i)> route;
+    // degrade (src/degrade.c:255): > 0 rounds this many low bits of every sample away before the record is re-encoded
+    int qts_bits = 0;
 };
 
 int convert_records(const s5b::Header &hdr, s5b::Fmt fmt_in, const std::function<int(std::vector<uint8_t> &)> &next, FILE *fout,

@@ -469,7 +469,8 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
         std::vector<const int16_t *> sig(n);
         // text output with a GPU context: the stored signals go straight to the device formatter (decode + sprintf loop of
         // slow5.c:3866-3878 in one trip), nothing is decompressed to the host
-        const bool gpu_text = fmt_out == FMT_ASCII && gpu != nullptr && fmt_in == FMT_BINARY;
+        const int qts = hooks ? hooks->qts_bits : 0;  // degrade needs the samples themselves in between
+        const bool gpu_text = fmt_out == FMT_ASCII && gpu != nullptr && fmt_in == FMT_BINARY && !qts;
         if (fmt_in == FMT_ASCII && gpu != nullptr) {
             std::vector<const char *> tptrs(n);
             std::vector<uint64_t> expect(n);
@@ -521,8 +522,52 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
             }
         }
 
+        // ---- degrade: slow5_rec_qts_round on every record of the batch (src/degrade.c:255), one trip to the device
+        std::vector<void *> degraded;
+        struct FreeAll {
+            std::vector<void *> &v;
+            ~FreeAll() { for (void *p : v) free(p); }
+        } free_degraded{degraded};
+        if (qts) {
+            degraded.assign(n, nullptr);
+            std::vector<size_t> got(n, 0);
+            for (size_t i = 0; i < n; ++i) {
+                ptrs[i] = sig[i];
+                counts[i] = b.rec[i].len_raw_signal * 2;
+            }
+            const int rc = gpu ? s5b_qts_round_batch_host(gpu, qts, ptrs.data(), counts.data(), n, degraded.data(), got.data()) : S5B_ERR_DEVICE;
+            if (rc != S5B_OK) {
+                ERROR("signal degradation failed: %s", s5b_strerror(rc));
+                ret = 1;
+                break;
+            }
+            for (size_t i = 0; i < n; ++i) sig[i] = static_cast<const int16_t *>(degraded[i]);
+        }
+
         // ---- output
-        if (gpu_text) {
+        if (qts && fmt_out == FMT_ASCII) {
+            // the degraded samples go back to the device formatter as raw int16 (slow5.c:3866-3878)
+            std::vector<char *> text(n, nullptr);
+            std::vector<size_t> text_n(n, 0);
+            for (size_t i = 0; i < n; ++i) {
+                ptrs[i] = sig[i];
+                counts[i] = b.rec[i].len_raw_signal * 2;
+            }
+            const int rc = s5b_signal_to_ascii_batch_host(gpu, PRESS_NONE, ptrs.data(), counts.data(), n, text.data(), text_n.data());
+            if (rc != S5B_OK) {
+                ERROR("signal formatting failed: %s", s5b_strerror(rc));
+                for (char *p : text) free(p);
+                ret = 1;
+                break;
+            }
+            std::vector<std::string> lines(n);
+            parallel_for(n, threads, [&](size_t i) {
+                record_to_ascii(b.rec[i], hdr_o, lines[i], text[i], text_n[i]);
+                free(text[i]);
+            });
+            for (size_t i = 0; i < n && ret == 0; ++i)
+                if (fwrite(lines[i].data(), 1, lines[i].size(), dest(i)) != lines[i].size()) ret = 1;
+        } else if (gpu_text) {
             std::vector<char *> text(n, nullptr);
             std::vector<size_t> text_n(n, 0);
             for (size_t i = 0; i < n; ++i) {
@@ -793,6 +838,7 @@ int index_main(int argc, char **argv);  // index_main.cpp
 int get_main(int argc, char **argv);    // get_main.cpp
 int merge_main(int argc, char **argv);  // merge_split_main.cpp
 int split_main(int argc, char **argv);
+int degrade_main(int argc, char **argv);  // degrade_main.cpp
 
 int main(int argc, char **argv) {
     if (argc >= 2 && (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V"))) {
@@ -800,7 +846,7 @@ int main(int argc, char **argv) {
         return 0;
     }
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
-        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n    index   create a SLOW5/BLOW5 index file\n    get     display the read entry for each specified read id\n    merge   merge multiple SLOW5/BLOW5 files to a single file\n    split   split a SLOW5/BLOW5 file by read group, number of reads or number of files\n");
+        fprintf(argc < 2 ? stderr : stdout, "Usage: slow5tools-b200 <command> [options]\n\nCOMMANDS:\n    view    view the contents of a SLOW5/BLOW5 file or convert between different formats and compressions\n    index   create a SLOW5/BLOW5 index file\n    get     display the read entry for each specified read id\n    merge   merge multiple SLOW5/BLOW5 files to a single file\n    split   split a SLOW5/BLOW5 file by read group, number of reads or number of files\n    degrade irreversibly degrade the signals (lossy) and convert a SLOW5/BLOW5 file\n");
         return argc < 2 ? 1 : 0;
     }
     if (!strcmp(argv[1], "get")) {
@@ -827,6 +873,14 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
+    if (!strcmp(argv[1], "degrade")) {
+        const int rc = degrade_main(argc - 1, argv + 1);
+        if (rc != 0) {
+            fprintf(stderr, "[main::ERROR] degrade failed\n");
+            return EXIT_FAILURE;
+        }
+        return 0;
+    }
     if (!strcmp(argv[1], "view")) {
         const int rc = view_main(argc - 1, argv + 1);
         if (rc != 0) {
@@ -835,6 +889,6 @@ int main(int argc, char **argv) {
         }
         return 0;
     }
-    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view, index, get, merge, split)\n", argv[1]);
+    fprintf(stderr, "[main::ERROR] unrecognised command '%s' (this build provides the hot path only: view, index, get, merge, split, degrade)\n", argv[1]);
     return EXIT_FAILURE;
 }

@@ -130,7 +130,9 @@ struct Job {
     uint64_t *d_acc;      // device form: [0] total image bytes, [1] first error
     const uint64_t *d_tab_off;  // device form: the whole record table, uploaded once per call
     const uint32_t *d_tab_len;
-    bool edits = false;   // the records themselves change (read groups renumbered): stored records cannot be passed through
+    bool edits = false;   // the records themselves change (read groups renumbered, samples degraded): stored records cannot be passed through
+    int qts = 0;          // > 0: slow5_rec_qts_round with this many bits between signal decode and encode (s5b_ctx_set_degrade)
+    bool resig() const { return in_sig != out_sig || qts > 0; }  // the signal is decoded and stored anew
 };
 
 struct Chunk {
@@ -148,20 +150,20 @@ Bounds chunk_bounds(const Job &j, uint64_t span, uint64_t n) {
     b.infl = j.in_rec == S5B_COMPRESS_NONE ? 0 : D + 64;
     const uint64_t samples = j.in_sig == S5B_COMPRESS_NONE ? D / 2 : D;
     uint64_t sig_out = D;  // signal bytes inside the output records
-    if (j.in_sig != j.out_sig) {
+    if (j.resig()) {
         b.sig_samples = samples + 8 * n + 64;
         if (j.out_sig == S5B_COMPRESS_SVB_ZD) b.svb = 3 * samples + samples / 4 + 40 * n + 64;
         else if (j.out_sig == S5B_COMPRESS_EX_ZD) b.svb = 2 * samples + 1040 * n + 64;
         sig_out = j.out_sig == S5B_COMPRESS_NONE ? 2 * samples : b.svb;
         b.packed = D + sig_out + 32 * n + 64;
     }
-    const uint64_t P = j.in_sig != j.out_sig ? b.packed : D;
-    const bool untouched = j.in_rec == j.out_rec && j.in_sig == j.out_sig && !j.edits;  // stored records are the answer
+    const uint64_t P = j.resig() ? b.packed : D;
+    const bool untouched = j.in_rec == j.out_rec && !j.resig() && !j.edits;  // stored records are the answer
     if ((j.out_rec == S5B_COMPRESS_ZLIB || j.out_rec == S5B_COMPRESS_ZSTD) && !untouched)
         b.z = P + 6 * (P / 6144 + 2 * n) + 48 * n + 64;
     const uint64_t F = b.z ? b.z : (untouched ? span : P);
     b.img = F + 8 * n + 64;
-    if (j.in_sig != j.out_sig && j.out_rec == S5B_COMPRESS_NONE) b.img = b.packed + 8 * n + 64;
+    if (j.resig() && j.out_rec == S5B_COMPRESS_NONE) b.img = b.packed + 8 * n + 64;
     return b;
 }
 
@@ -257,6 +259,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
         StageScope ts(ctx, st, ST_GLUE);
         s5b::AuxLayout lay = ctx->aux_layout;
         lay.rg_n = ctx->rg_map_n;
+        if (!j.qts) lay.ds_check = 0;
         CU(launch_rec_locate(cur, cur_off, cur_len, n,
                              j.in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (j.in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra, st, st_dep, &lay));
         ctx->launches += 1;
@@ -271,7 +274,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     const uint64_t *sig_src_off = nullptr;
     const uint32_t *sig_src_len = ra.sig_bytes;
     int sig_src_is_samples = 0;
-    if (j.in_sig != j.out_sig) {
+    if (j.resig()) {
         CU(L.sig.reserve(B.sig_samples * 2 + 32));
         {
             StageScope ts(ctx, st, ST_GLUE);
@@ -291,6 +294,12 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
         } else {
             StageScope ts(ctx, st, ST_SIG_EXTRACT);
             CU(launch_sig_extract(cur, cur_off, ra, n, static_cast<int16_t *>(L.sig.p), d_sig_off, st));
+            ctx->launches += 1;
+        }
+        if (j.qts) {
+            // degrade (src/degrade.c:255): the whole sample slab in one streaming pass, its length read on the device
+            StageScope ts(ctx, st, ST_SIG_DEGRADE);
+            CU(launch_qts_round(static_cast<int16_t *>(L.sig.p), 0, d_sig_off + n, j.qts, ctx->num_sms, st));
             ctx->launches += 1;
         }
         if (j.out_sig == S5B_COMPRESS_NONE) {
@@ -326,9 +335,9 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     const uint32_t *fin_len = cur_len;
     uint64_t fin_cap = cur_cap;
     // when the packed records are the output (no record compression), they are written straight into the file image
-    const bool direct_image = j.in_sig != j.out_sig && j.out_rec == S5B_COMPRESS_NONE;
+    const bool direct_image = j.resig() && j.out_rec == S5B_COMPRESS_NONE;
     const uint32_t *direct_sig_len = nullptr;
-    if (j.in_sig != j.out_sig && direct_image) {
+    if (direct_image) {
         if (sig_src_is_samples) {
             StageScope ts(ctx, st, ST_PACK);
             CU(launch_rec_plan(PLAN_SIG_BYTES_RAW, n, ra, nullptr, 0, d_svb_len, st));
@@ -336,7 +345,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
             ctx->launches += 1;
         }
         direct_sig_len = sig_src_len;
-    } else if (j.in_sig != j.out_sig) {
+    } else if (j.resig()) {
         StageScope ts(ctx, st, ST_PACK);
         CU(L.packed.reserve(B.packed + 32));
         if (sig_src_is_samples) {  // raw signal goes into the record: 2 * n_samples bytes
@@ -356,7 +365,7 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     }
     // ---- record compression (slow5.c:4050)
     if (j.out_rec == S5B_COMPRESS_ZLIB || j.out_rec == S5B_COMPRESS_ZSTD) {
-        if (j.in_rec == j.out_rec && j.in_sig == j.out_sig && !j.edits) {
+        if (j.in_rec == j.out_rec && !j.resig() && !j.edits) {
             // nothing changed inside the records: the stored compressed records are the answer
             fin = j.src_dev ? j.src + (c.span0 - (c.span0 & 15u)) : static_cast<const uint8_t *>(L.in.p);
             fin_off = d_rec_off;
@@ -496,6 +505,7 @@ int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_
     Job j{in_rec, in_sig, out_rec, out_sig, h_in, false, in_bytes, rec_off, rec_len, n, h_out, false, out_cap, out_img_off, nullptr,
           nullptr, nullptr};
     j.edits = ctx->rg_map_n != 0;
+    j.qts = ctx->qts_bits;
     const size_t nc = chunks.size();
     uint64_t pos = 0;           // image bytes placed so far
     bool overflow = false;      // the image outgrew out_cap: keep sizing, stop copying
@@ -615,6 +625,7 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
     if (ctx->rg_map_n) return S5B_ERR_ARG;  // renumbering works on the library's own copy of the records: host form only
     Job j{in_rec, in_sig, out_rec, out_sig, d_in, true, in_bytes, rec_off, rec_len, n, d_out, true, out_cap, d_img_off, d_result,
           d_tab_off, d_tab_len};
+    j.qts = ctx->qts_bits;
     for (const Chunk &c : chunks) {
         const int rc = enqueue_chunk(ctx, L, j, c);
         if (rc != S5B_OK) return rc;
@@ -688,9 +699,21 @@ int s5b_ctx_set_rg_map(s5b_ctx_t *ctx, const uint32_t *map, uint32_t n) {
     return S5B_OK;
 }
 
+int s5b_ctx_set_degrade(s5b_ctx_t *ctx, int bits, int check_dataset, float digitisation, float sampling_rate) {
+    if (!ctx || bits < 0 || bits > 16) return S5B_ERR_ARG;
+    ctx->qts_bits = bits;
+    ctx->aux_layout.ds_check = bits && check_dataset ? 1u : 0u;
+    ctx->aux_layout.ds_digitisation = digitisation;
+    ctx->aux_layout.ds_sampling_rate = sampling_rate;
+    return S5B_OK;
+}
+
 int s5b_ctx_set_aux_layout(s5b_ctx_t *ctx, const uint8_t *elem_size, const uint8_t *is_array, uint32_t n_fields) {
     if (!ctx) return S5B_ERR_ARG;
     s5b::AuxLayout lay;
+    lay.ds_check = ctx->aux_layout.ds_check;  // the degrade rule is set on its own (s5b_ctx_set_degrade)
+    lay.ds_digitisation = ctx->aux_layout.ds_digitisation;
+    lay.ds_sampling_rate = ctx->aux_layout.ds_sampling_rate;
     if (n_fields != s5b::AUX_LAYOUT_UNKNOWN) {
         if (n_fields > (uint32_t)s5b::AUX_LAYOUT_MAX || (n_fields && (!elem_size || !is_array))) return S5B_ERR_ARG;
         lay.n = n_fields;
@@ -707,7 +730,7 @@ int s5b_ctx_set_aux_layout(s5b_ctx_t *ctx, const uint8_t *elem_size, const uint8
 int s5b_stage_count(void) { return ST_COUNT; }
 const char *s5b_stage_name(int stage) {
     static const char *names[ST_COUNT] = {"h2d", "record_depress", "glue", "signal_depress", "signal_press", "pack",
-                                          "record_press", "image", "d2h", "signal_extract"};
+                                          "record_press", "image", "d2h", "signal_extract", "signal_degrade"};
     return stage >= 0 && stage < ST_COUNT ? names[stage] : "";
 }
 

@@ -134,6 +134,13 @@ __global__ void rec_locate_kernel(const uint8_t *rec, const uint64_t *rec_off, c
                     }
                     if (!ok || at != aux) st = S5B_ERR_PRESS;
                 }
+                // degrade, bit count chosen from the header: the record itself must belong to that dataset (slow5_reccmp,
+                // src/degrade.c:195-211).  digitisation sits 32 bytes in front of the length field, sampling_rate 8.
+                if (st == S5B_OK && lay.ds_check) {
+                    const double dig = __longlong_as_double((long long)ld_u64_unaligned(p + head - 32));
+                    const double rate = __longlong_as_double((long long)ld_u64_unaligned(p + head - 8));
+                    if (dig != (double)lay.ds_digitisation || rate != (double)lay.ds_sampling_rate) st = S5B_ERR_DATASET;
+                }
             }
         }
     }

@@ -37,6 +37,7 @@ const char *s5b_strerror(int err) {
         case S5B_ERR_PRESS: return "malformed compressed stream";
         case S5B_ERR_NOSPACE: return "output slot too small";
         case S5B_ERR_DEVICE: return "CUDA device unavailable or CUDA error";
+        case S5B_ERR_DATASET: return "a record's digitisation / sampling rate does not match the dataset";
         default: return "unknown error";
     }
 }
@@ -763,6 +764,45 @@ static int exzd_ptrs(s5b_ctx_t *ctx, bool compress, const void *const *ptrs, con
     return first;
 }
 
+// slow5_arr_qts_round for a batch of host arrays: packed back to back (even offsets), one H2D, one launch over the whole slab,
+// one D2H
+static int qts_ptrs(s5b_ctx_t *ctx, int bits, const void *const *ptrs, const size_t *counts, size_t n, void **out_ptrs,
+                    size_t *out_n) {
+    std::vector<uint64_t> off(n + 1);
+    uint64_t tot = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if ((!ptrs[i] && counts[i]) || (counts[i] & 1)) return S5B_ERR_ARG;
+        off[i] = tot;
+        tot += counts[i];
+    }
+    off[n] = tot;
+    DeviceGuard g(ctx->device);
+    PipeSlot &s = ctx->slot[0];
+    CU(ctx->h_stage_in.reserve(tot + 16));
+    uint8_t *h = static_cast<uint8_t *>(ctx->h_stage_in.p);
+    for (size_t i = 0; i < n; ++i) memcpy(h + off[i], ptrs[i], counts[i]);
+    CU(s.d_a.reserve(tot + 16));
+    CU(cudaMemcpyAsync(s.d_a.p, h, tot, cudaMemcpyHostToDevice, s.stream));
+    if (tot) {
+        CU(launch_qts_round(static_cast<int16_t *>(s.d_a.p), tot / 2, nullptr, bits, ctx->num_sms, s.stream));
+        ctx->launches += 1;
+    }
+    CU(cudaMemcpyAsync(h, s.d_a.p, tot, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    int first = S5B_OK;
+    for (size_t i = 0; i < n; ++i) {
+        out_n[i] = 0;
+        out_ptrs[i] = malloc(counts[i] ? counts[i] : 1);
+        if (!out_ptrs[i]) {
+            if (first == S5B_OK) first = S5B_ERR_MEM;
+            continue;
+        }
+        memcpy(out_ptrs[i], h + off[i], counts[i]);
+        out_n[i] = counts[i];
+    }
+    return first;
+}
+
 // zlib streams: the inflated size is not stored anywhere (slow5_press.c:985-1003 grows its buffer in 256 KiB
 // steps), so slots are sized from a guess and the (rare) streams that overflow are run again with the exact
 // size the first pass reported.
@@ -1051,6 +1091,25 @@ int s5b_compress_batch_host(s5b_ctx_t *ctx, int method, const void *const *ptrs,
     }
 }
 
+int s5b_qts_round_batch_host(s5b_ctx_t *ctx, int bits, const void *const *ptrs, const size_t *counts, size_t n, void **out_ptrs,
+                             size_t *out_n) {
+    if (!ctx || bits < 0 || bits > 16 || (n && (!ptrs || !counts || !out_ptrs || !out_n))) return S5B_ERR_ARG;
+    if (n == 0) return S5B_OK;
+    if (bits == 0) return copy_ptrs(ptrs, counts, n, out_ptrs, out_n);  // slow5_press.c:1995-1996
+    return qts_ptrs(ctx, bits, ptrs, counts, n, out_ptrs, out_n);
+}
+
+int s5b_qts_round_dev(s5b_ctx_t *ctx, int16_t *d_sig, uint64_t n_samples, int bits, void *stream) {
+    if (!ctx || bits < 0 || bits > 16) return S5B_ERR_ARG;
+    if (bits == 0 || n_samples == 0) return S5B_OK;
+    if (!d_sig || (reinterpret_cast<uintptr_t>(d_sig) & 1u)) return S5B_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    CU(launch_qts_round(d_sig, n_samples, nullptr, bits, ctx->num_sms, st));
+    ctx->launches += 1;
+    return S5B_OK;
+}
+
 int s5b_compress_records_host(s5b_ctx_t *ctx, int method, const void *const *ptrs, const size_t *counts,
                               const uint32_t *splits, size_t n, void **out_ptrs, size_t *out_n) {
     if (!ctx || (n && (!ptrs || !counts || !out_ptrs || !out_n))) return S5B_ERR_ARG;
@@ -1108,6 +1167,8 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
     if (!rec_ok(in_rec) || !rec_ok(out_rec) || !sig_ok(in_sig) || !sig_ok(out_sig))
         return S5B_ERR_ARG;
     DeviceGuard g(ctx->device);
+    const int qts = ctx->qts_bits;                 // degrade: the samples change, so the signal is stored anew in any case
+    const bool resig = in_sig != out_sig || qts > 0;
     cudaStream_t st = ctx->slot[0].stream;
     unsigned long long *counter = ctx->slot[0].d_counter;
     // ---- per-record arrays: 16 x u32[n] and 8 x u64[n+1]
@@ -1213,6 +1274,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
     {
         s5b::AuxLayout lay = ctx->aux_layout;
         lay.rg_n = ctx->rg_map_n;
+        if (!qts) lay.ds_check = 0;
         CU(launch_rec_locate(cur, cur_off, cur_len, n, in_sig == S5B_COMPRESS_SVB_ZD ? 1 : (in_sig == S5B_COMPRESS_EX_ZD ? 2 : 0), ra,
                              st, nullptr, &lay));
         ctx->launches += 1;
@@ -1231,7 +1293,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
     const uint64_t *sig_src_off = nullptr;
     const uint32_t *sig_src_len = ra.sig_bytes;
     int sig_src_is_samples = 0;
-    if (in_sig != out_sig) {
+    if (resig) {
         uint64_t total = 0;
         CU(launch_rec_plan(PLAN_SIG_SAMPLES, n, ra, nullptr, 0, d_tmp, st));
         CU(scan_total(d_tmp, 8, d_sig_off, &total));
@@ -1249,6 +1311,10 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
             if (first_err != S5B_OK) return first_err;
         } else {
             CU(launch_sig_extract(cur, cur_off, ra, n, static_cast<int16_t *>(ctx->r_sig.p), d_sig_off, st));
+            ctx->launches += 1;
+        }
+        if (qts) {  // src/degrade.c:255
+            CU(launch_qts_round(static_cast<int16_t *>(ctx->r_sig.p), total, nullptr, qts, ctx->num_sms, st));
             ctx->launches += 1;
         }
         if (out_sig == S5B_COMPRESS_NONE) {
@@ -1277,7 +1343,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
     const uint64_t *fin_off = cur_off;
     const uint32_t *fin_len = cur_len;
     uint64_t fin_cap = cur_cap;
-    if (in_sig != out_sig) {
+    if (resig) {
         uint64_t total = 0;
         if (sig_src_is_samples) {  // raw signal goes into the record: 2 * n_samples bytes
             CU(launch_rec_plan(PLAN_SIG_BYTES_RAW, n, ra, nullptr, 0, d_svb_len, st));
@@ -1296,7 +1362,7 @@ int s5b::recode_chunk_sync(s5b_ctx *ctx, int in_rec, int in_sig, int out_rec, in
     }
     // ---- record compression (slow5.c:4050)
     if (out_rec == S5B_COMPRESS_ZLIB || out_rec == S5B_COMPRESS_ZSTD) {
-        if (in_rec == out_rec && in_sig == out_sig && !ctx->rg_map_n) {
+        if (in_rec == out_rec && !resig && !ctx->rg_map_n) {
             // nothing changed inside the records: the stored compressed records are the answer
             fin = static_cast<const uint8_t *>(ctx->r_in.p);
             fin_off = d_rec_off;

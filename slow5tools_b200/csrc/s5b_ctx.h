@@ -69,7 +69,7 @@ struct PipeSlot {
 constexpr int NLANE = 6;   // lanes that exist; s5b_ctx::n_lanes of them are used (3 unless S5B_RECODE_LANES says otherwise)
 // stages of a transcoding pass, for the optional per-stage CUDA-event timing (s5b_ctx_stage_timing)
 enum Stage { ST_H2D = 0, ST_REC_DEPRESS, ST_GLUE, ST_SIG_DEPRESS, ST_SIG_PRESS, ST_PACK, ST_REC_PRESS, ST_IMAGE, ST_D2H,
-             ST_SIG_EXTRACT, ST_COUNT };
+             ST_SIG_EXTRACT, ST_SIG_DEGRADE, ST_COUNT };
 
 struct RecodeLane {
     cudaStream_t stream = nullptr;
@@ -115,6 +115,7 @@ struct s5b_ctx {
     s5b::StageTimer timer;
     uint32_t *d_rg_map = nullptr;     // read_group renumbering of the file being transcoded (s5b_ctx_set_rg_map), rg_map_n entries
     uint32_t rg_map_n = 0;
+    int qts_bits = 0;                 // > 0: the transcoder degrades every signal by this many bits (s5b_ctx_set_degrade)
     s5b::AuxLayout aux_layout;        // auxiliary columns of the file being transcoded (s5b_ctx_set_aux_layout), unknown by default
     uint64_t launches = 0;
     size_t chunk_bytes = 32u << 20;  // e2e is flat between 16 and 128 MiB (PCIe bound), 32 MiB marginally best

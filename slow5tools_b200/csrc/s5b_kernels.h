@@ -118,6 +118,10 @@ struct AuxLayout {
     uint32_t n = AUX_LAYOUT_UNKNOWN;
     uint64_t array_mask = 0;
     uint8_t size[AUX_LAYOUT_MAX] = {0};
+    // degrade with an automatically chosen bit count (src/degrade.c:195-211, :249-253): every record must carry the dataset's
+    // digitisation and sampling rate (compared as the reference does: the record's double against a float), else S5B_ERR_DATASET
+    uint32_t ds_check = 0;
+    float ds_digitisation = 0.f, ds_sampling_rate = 0.f;
 };
 // in_status (optional): the status the record decompression left; a failed record is marked and skipped
 cudaError_t launch_rec_locate(const uint8_t *rec, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
@@ -161,6 +165,10 @@ cudaError_t launch_rebase_off(uint64_t *dst, const uint64_t *src, uint64_t n, ui
 // carries none; sizes above len * mul + add get S5B_ERR_NOSPACE and size 0 (the careful path sizes those exactly)
 cudaError_t launch_zstd_sizes(const uint8_t *in, const uint64_t *off, const uint32_t *len, uint64_t n, uint32_t mul,
                               uint32_t add, uint32_t *size, int32_t *status, cudaStream_t st);
+
+// lossy degradation (qts_kernels.cu; slow5_arr_qts_round, slow5_press.c:1991-2005): the `bits` low bits of every sample rounded
+// away, in place.  The sample count is n_samples, or *d_n_samples (device) when that is given.
+cudaError_t launch_qts_round(int16_t *sig, uint64_t n_samples, const uint64_t *d_n_samples, int bits, int num_sms, cudaStream_t st);
 
 // SLOW5 text raw_signal column (ascii_kernels.cu): sizes, text, and back
 cudaError_t launch_ascii_size(const int16_t *sig, const uint64_t *sig_off, const uint32_t *n_samples, uint64_t n_reads,
