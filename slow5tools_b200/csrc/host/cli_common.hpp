@@ -17,6 +17,9 @@ struct ConvertHooks {
     std::function<bool(size_t i, s5b::Record &rec, std::vector<uint8_t> &aux_store)> transform;
     // destination of record i of the batch; nullptr: fout
     std::function<FILE *(size_t i)> route;
+    // demultiplexing (src/demux.c:562-590): every file record i goes to -- none (the record is dropped), one or several; takes
+    // precedence over route
+    std::function<const std::vector<FILE *> *(size_t i)> route_many;
     // degrade (src/degrade.c:255): > 0 rounds this many low bits of every sample away before the record is re-encoded
     int qts_bits = 0;
 };

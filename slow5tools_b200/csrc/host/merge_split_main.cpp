@@ -4,9 +4,10 @@
 //                                read_group is renumbered (merge.c:52) and its auxiliary section is laid out for the union
 //                                of the inputs' columns (enum columns first, the others sorted by name: merge.c:231-271,325-332);
 //   split (src/split.c:110-660)  one input -> several outputs: by read group (-g: every record goes to the file of its group
-//                                with read_group 0, split.c:88-89,520), by record count (-r) or into -f files (split.c:379-456).
+//                                with read_group 0, split.c:88-89,520), by record count (-r), into -f files (split.c:379-456),
+//                                or by the categories a table gives the read ids (-x: demultiplexing, src/demux.c).
 // Records go through convert_records (view_main.cpp): decompression and compression are batch calls on the GPU; there is no
-// CPU codec here.  What is not carried over: lossy output is (--lossless false), demultiplexing by barcode (-x) is not, and an
+// CPU codec here.  What is not carried over: lossy output is (--lossless false), and an
 // auxiliary column that changes TYPE between inputs is refused (the reference writes such records with the bytes of one type
 // under the header of another, merge.c:262 / test 4.3).
 #include <dirent.h>
@@ -468,6 +469,188 @@ int merge_main(int argc, char **argv) {
     return ret;
 }
 
+namespace {
+
+// ---- demultiplexing (src/demux.c) ---------------------------------------------------------------------------------------------
+// A tab-separated table (guppy / dorado barcoding summary, or any table with a read id column and a category column) says which
+// category -- barcode -- every read belongs to.  Each category gets its own output file, named after the input with "_<category>"
+// in front of the extension (path_spawn, demux.c:261-279), created when its first record arrives (demux_write, :562-590) and
+// carrying the input's whole header (slow5_birth, :1100-1130).  A read listed under several categories is written to each of
+// them, or only to the -u category when one is named (update_db, :815-836); a read the table does not list is dropped with a
+// warning, or goes to the -m category (:842-892); a table that lists more reads than the file holds is an error (:520-523).
+struct DemuxOpts {
+    const char *table = nullptr;
+    const char *code_col = "barcode_arrangement", *rid_col = "parent_read_id";  // demux.h:8-9
+    const char *multi = nullptr, *missing = nullptr;
+};
+struct DemuxPlan {
+    std::vector<std::string> names;                        // categories in order of first appearance, then multi, then missing
+    std::map<std::string, std::vector<uint16_t>> of_read;  // read id -> categories, each once, in table order
+    int multi = -1, missing = -1;                          // their indices in names, -1: not asked for
+};
+
+// the non-empty tab-separated fields of a line (the reference walks the line with strtok: runs of tabs count once)
+void tab_fields(const std::string &line, std::vector<std::string> &out) {
+    out.clear();
+    size_t at = 0;
+    while (at < line.size()) {
+        const size_t end = std::min(line.find('\t', at), line.size());
+        if (end > at) out.push_back(line.substr(at, end - at));
+        at = end + 1;
+    }
+}
+
+bool demux_read_table(const DemuxOpts &d, DemuxPlan &plan) {
+    FILE *fp = fopen(d.table, "r");
+    if (!fp) {
+        MS_ERROR("Failed to open '%s': %s", d.table, strerror(errno));
+        return false;
+    }
+    std::string text;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, fp)) > 0) text.append(buf, got);
+    fclose(fp);
+    std::vector<std::string> f;
+    size_t at = 0, rid_pos = 0, code_pos = 0;  // 1-based field numbers, 0: not found
+    bool first = true;
+    std::map<std::string, uint16_t> index_of;
+    while (at < text.size() || first) {
+        const size_t end = std::min(text.find('\n', at), text.size());
+        tab_fields(text.substr(at, end - at), f);
+        at = end + 1;
+        if (first) {  // bsum_parsehdr, demux.c:431-470: the first column of either name counts
+            first = false;
+            for (size_t i = 0; i < f.size() && (!rid_pos || !code_pos); ++i) {
+                if (!rid_pos && f[i] == d.rid_col) rid_pos = i + 1;
+                else if (!code_pos && f[i] == d.code_col) code_pos = i + 1;
+            }
+            if (!rid_pos) {
+                MS_ERROR("Invalid demux TSV header: missing '%s'", d.rid_col);
+                return false;
+            }
+            if (!code_pos) {
+                MS_ERROR("Invalid demux TSV header: missing '%s'", d.code_col);
+                return false;
+            }
+            continue;
+        }
+        if (f.size() < rid_pos || f.size() < code_pos) continue;  // (a blank or short line names nothing)
+        const std::string &rid = f[rid_pos - 1], &code = f[code_pos - 1];
+        auto it = index_of.find(code);
+        if (it == index_of.end()) {
+            if (plan.names.size() >= 65533) {
+                MS_ERROR("Too many categories (%zu)", plan.names.size() + 3);
+                return false;
+            }
+            it = index_of.emplace(code, (uint16_t)plan.names.size()).first;
+            plan.names.push_back(code);
+        }
+        std::vector<uint16_t> &v = plan.of_read[rid];
+        if (std::find(v.begin(), v.end(), it->second) == v.end()) v.push_back(it->second);
+    }
+    // the two special categories must not collide with a category of the table or with each other (getcodes, demux.c:226-255)
+    if (d.multi) {
+        if (index_of.count(d.multi)) {
+            MS_ERROR("Multi-category '%s' already exists in demux TSV", d.multi);
+            return false;
+        }
+        plan.multi = (int)plan.names.size();
+        plan.names.push_back(d.multi);
+    }
+    if (d.missing) {
+        if (index_of.count(d.missing) || (d.multi && !strcmp(d.multi, d.missing))) {
+            MS_ERROR("Uncategorised reads category '%s' already exists", d.missing);
+            return false;
+        }
+        plan.missing = (int)plan.names.size();
+        plan.names.push_back(d.missing);
+    }
+    return true;
+}
+
+// <dir>/<input file name with "_<category>" in front of its extension>, extension = the output format's
+std::string demux_path(const std::string &in_path, const char *dir, const std::string &category, Fmt fmt) {
+    const size_t slash = in_path.find_last_of('/');
+    std::string name = in_path.substr(slash == std::string::npos ? 0 : slash + 1);
+    const size_t dot = name.find_last_of('.');
+    name = name.substr(0, dot) + "_" + category + (fmt == FMT_ASCII ? ".slow5" : ".blow5");
+    return dir && *dir ? std::string(dir) + "/" + name : name;
+}
+
+int demux_file(const std::string &path, Reader &rd, const Opts &o, const DemuxPlan &plan_in, s5b_ctx_t *gpu) {
+    DemuxPlan plan = plan_in;  // (-m adds the reads it catches to the table, demux.c:876-885)
+    const Header &h = rd.hdr;
+    Header hdr_out = h;
+    if (o.lossy) hdr_out.aux.clear();
+    std::vector<Output> outs(plan.names.size());
+    std::vector<std::vector<FILE *>> dest;  // of the records of the batch being converted
+    uint64_t n_records = 0;
+    bool failed = false;
+    auto file_of = [&](uint16_t k) -> FILE * {
+        Output &out = outs[k];
+        if (out.fp) return out.fp;
+        out.path = demux_path(path, o.arg_dir, plan.names[k], o.fmt_out);
+        out.fp = fopen(out.path.c_str(), "wb");
+        if (!out.fp) {
+            MS_ERROR("Failed to open '%s' for writing: %s", out.path.c_str(), strerror(errno));
+            return nullptr;
+        }
+        setvbuf(out.fp, nullptr, _IOFBF, 1 << 20);
+        const std::string hm = header_to_mem(hdr_out, o.fmt_out, o.rec_out, o.sig_out);
+        if (fwrite(hm.data(), 1, hm.size(), out.fp) != hm.size()) {
+            MS_ERROR("Failed to write the header to '%s'", out.path.c_str());
+            return nullptr;
+        }
+        return out.fp;
+    };
+    ConvertHooks hooks;
+    hooks.hdr_out = &hdr_out;
+    hooks.transform = [&](size_t i, Record &rec, std::vector<uint8_t> &) {
+        if (dest.size() <= i) dest.resize(i + 1);
+        dest[i].clear();
+        ++n_records;
+        if (o.lossy) rec.aux_bytes = nullptr, rec.aux_nbytes = 0;
+        auto it = plan.of_read.find(rec.read_id);
+        std::vector<uint16_t> cats;
+        if (it == plan.of_read.end()) {
+            if (plan.missing < 0) {
+                MS_WARNING("Read ID '%s' is missing from demux TSV", rec.read_id.c_str());
+                return true;  // written nowhere
+            }
+            cats = plan.of_read[rec.read_id] = {(uint16_t)plan.missing};
+        } else if (plan.multi >= 0 && it->second.size() > 1) {
+            cats = {(uint16_t)plan.multi};
+        } else {
+            cats = it->second;
+        }
+        for (uint16_t k : cats) {
+            FILE *f = file_of(k);
+            if (!f) {
+                failed = true;
+                return false;
+            }
+            dest[i].push_back(f);
+        }
+        return true;
+    };
+    hooks.route_many = [&](size_t i) { return &dest[i]; };
+    int ret = convert_records(h, rd.fmt, [&](std::vector<uint8_t> &mem) {
+        const int rc = reader_next_mem(rd, mem);
+        if (rc < 0) MS_ERROR("Could not read file %s", path.c_str());
+        return rc;
+    }, nullptr, gpu, o.fmt_out, o.rec_out, o.sig_out, o.batch, o.threads, &hooks);
+    if (ret == 0 && n_records < plan.of_read.size()) {
+        MS_ERROR("Extra read(s) in demux TSV%s", "");
+        ret = 1;
+    }
+    for (Output &out : outs)
+        if (out.fp && !finish_output(out.fp, o.fmt_out, true)) ret = 1;
+    return ret || failed ? 1 : 0;
+}
+
+}  // namespace
+
 int split_main(int argc, char **argv) {
     static const struct option long_opts[] = {
         {"help", no_argument, nullptr, 'h'},           {"to", required_argument, nullptr, 'b'},
@@ -476,13 +659,16 @@ int split_main(int argc, char **argv) {
         {"lossless", required_argument, nullptr, 'l'}, {"groups", no_argument, nullptr, 'g'},
         {"files", required_argument, nullptr, 'f'},    {"reads", required_argument, nullptr, 'r'},
         {"batchsize", required_argument, nullptr, 'K'}, {"demux", required_argument, nullptr, 'x'},
+        {"demux-code", required_argument, nullptr, 1000}, {"demux-rid", required_argument, nullptr, 1001},
+        {"demux-uniq", required_argument, nullptr, 'u'}, {"demux-missing", required_argument, nullptr, 'm'},
         {nullptr, 0, nullptr, 0}};
     Opts o;
-    enum { BY_READS, BY_FILES, BY_GROUPS } how = BY_READS;
+    DemuxOpts dx;
+    enum { BY_READS, BY_FILES, BY_GROUPS, BY_TABLE } how = BY_READS;
     long count = 0;
     int opt;
     optind = 1;
-    while ((opt = getopt_long(argc, argv, "hb:c:s:gl:f:r:d:t:K:x:", long_opts, nullptr)) != -1) {
+    while ((opt = getopt_long(argc, argv, "hb:c:s:gl:f:r:d:t:K:x:u:m:", long_opts, nullptr)) != -1) {
         switch (opt) {
             case 'b': o.arg_to = optarg; break;
             case 'c': o.arg_rec = optarg; break;
@@ -496,13 +682,18 @@ int split_main(int argc, char **argv) {
             case 'l':
                 if (!parse_lossless(optarg, o.lossy)) return 1;
                 break;
-            case 'x':
-                MS_ERROR("%s", "demultiplexing (-x) is outside this build (hot path only)");
-                return 1;
+            case 'x': how = BY_TABLE; dx.table = optarg; break;
+            case 'u': dx.multi = optarg; break;
+            case 'm': dx.missing = optarg; break;
+            case 1000: dx.code_col = optarg; break;
+            case 1001: dx.rid_col = optarg; break;
             case 'h':
                 printf("Usage: slow5tools-b200 split [OPTIONS] [SLOW5_FILE/DIR] ...\nSplit a single SLOW5/BLOW5 file into multiple separate files (GPU codec).\n\n"
                        "OPTIONS:\n    -d, --out-dir DIR             output to directory DIR\n    -g, --groups                  split multi read group file into single read group files\n"
                        "    -r, --reads INT               split into INT reads per file\n    -f, --files INT               split reads into INT files evenly\n"
+                       "    -x, --demux TSV_PATH          split reads according to TSV file\n        --demux-code STR          categories column name ['barcode_arrangement']\n"
+                       "        --demux-rid STR           read IDs column name ['parent_read_id']\n    -m, --demux-missing STR       uncategorised reads to category named STR\n"
+                       "    -u, --demux-uniq STR          multi-category reads to category named STR\n"
                        "    --to FORMAT, -c REC_MTD, -s SIG_MTD, -t INT, -K INT, -l STR as for merge\n");
                 return 0;
             default: return 1;
@@ -550,6 +741,8 @@ int split_main(int argc, char **argv) {
     }
     const std::string ext = o.fmt_out == FMT_ASCII ? ".slow5" : ".blow5";
     s5b_ctx_t *gpu = nullptr;
+    DemuxPlan plan;
+    bool have_plan = false;
     for (const std::string &path : files) {
         Reader rd;
         if (!reader_open(rd, path.c_str(), FMT_UNKNOWN)) {
@@ -562,7 +755,7 @@ int split_main(int argc, char **argv) {
             MS_ERROR("The file %s already has a single read group", path.c_str());
             return 1;
         }
-        if (h.num_read_groups > 1 && how != BY_GROUPS) {
+        if (h.num_read_groups > 1 && how != BY_GROUPS && how != BY_TABLE) {
             MS_ERROR("The file %s contains multiple read groups. You must first separate the read groups using -g. See https://slow5.bioinf.science/faq for more info.",
                      path.c_str());
             return 1;
@@ -574,6 +767,16 @@ int split_main(int argc, char **argv) {
         const bool need_gpu = h.record_method != PRESS_NONE || h.signal_method != PRESS_NONE || o.rec_out != PRESS_NONE ||
                               o.sig_out != PRESS_NONE;
         if (need_gpu && !gpu && !(gpu = open_gpu())) return 1;
+        if (how == BY_TABLE) {
+            if (!have_plan) {
+                if (!demux_read_table(dx, plan)) return 1;
+                have_plan = true;
+            }
+            const int rc = demux_file(path, rd, o, plan, gpu);
+            reader_close(rd);
+            if (rc) return 1;
+            continue;
+        }
 
         // <out-dir>/<input name without its extension>_<index><ext>, header = one read group of the input (create_output_slow5,
         // split.c:586-653)

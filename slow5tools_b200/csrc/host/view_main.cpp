@@ -390,7 +390,16 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
     int ret = 0;
     Batch b;
     const Header &hdr_o = hooks && hooks->hdr_out ? *hooks->hdr_out : hdr;  // what the output records follow
-    auto dest = [&](size_t i) { return hooks && hooks->route ? hooks->route(i) : fout; };
+    // record i of the batch goes to fout, to the file its route names, or to every file of route_many (none: it is dropped)
+    std::vector<FILE *> one(1);
+    auto put = [&](size_t i, const void *head, size_t head_n, const void *body, size_t body_n) -> bool {
+        const std::vector<FILE *> *to = &one;
+        if (hooks && hooks->route_many) to = hooks->route_many(i);
+        else one[0] = hooks && hooks->route ? hooks->route(i) : fout;
+        for (FILE *f : *to)
+            if ((head_n && fwrite(head, 1, head_n, f) != head_n) || (body_n && fwrite(body, 1, body_n, f) != body_n)) return false;
+        return true;
+    };
     bool eof = false;
     while (!eof && ret == 0) {
         // ---- load (serial)
@@ -566,7 +575,7 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
                 free(text[i]);
             });
             for (size_t i = 0; i < n && ret == 0; ++i)
-                if (fwrite(lines[i].data(), 1, lines[i].size(), dest(i)) != lines[i].size()) ret = 1;
+                if (!put(i, nullptr, 0, lines[i].data(), lines[i].size())) ret = 1;
         } else if (gpu_text) {
             std::vector<char *> text(n, nullptr);
             std::vector<size_t> text_n(n, 0);
@@ -600,7 +609,7 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
                 free(text[i]);
             });
             for (size_t i = 0; i < n && ret == 0; ++i)
-                if (fwrite(lines[i].data(), 1, lines[i].size(), dest(i)) != lines[i].size()) ret = 1;
+                if (!put(i, nullptr, 0, lines[i].data(), lines[i].size())) ret = 1;
         } else if (fmt_out == FMT_ASCII) {
             std::vector<std::string> lines(n);
             parallel_for(n, threads, [&](size_t i) {
@@ -611,7 +620,7 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
                 std::vector<int16_t>().swap(r.raw_signal);
             });
             for (size_t i = 0; i < n && ret == 0; ++i)
-                if (fwrite(lines[i].data(), 1, lines[i].size(), dest(i)) != lines[i].size()) ret = 1;
+                if (!put(i, nullptr, 0, lines[i].data(), lines[i].size())) ret = 1;
         } else {
             // signal compression
             std::vector<void *> svb(n, nullptr);
@@ -667,8 +676,7 @@ int convert_records(const Header &hdr, Fmt fmt_in, const std::function<int(std::
             for (size_t i = 0; i < n && ret == 0; ++i) {
                 const void *p = rec_packed ? z[i] : rec_mem[i].data();
                 const uint64_t sz = rec_packed ? z_n[i] : rec_mem[i].size();
-                FILE *fo = dest(i);
-                if (fwrite(&sz, 8, 1, fo) != 1 || (sz && fwrite(p, 1, sz, fo) != sz)) ret = 1;  // slow5.c:4055-4060
+                if (!put(i, &sz, 8, p, sz)) ret = 1;  // slow5.c:4055-4060
             }
             for (void *p : z) free(p);
         }
