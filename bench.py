@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "BLOW5 svb-zd+zlib reads/sec (encode+decode)"
 UNIT = "reads/s"
-M_NONE, M_ZLIB, M_SVB_ZD = 0, 1, 2
+M_NONE, M_ZLIB, M_SVB_ZD, M_EX_ZD = 0, 1, 2, 4
 # dram__bytes_read.sum + dram__bytes_write.sum per 100 000 records from the committed `ncu --set full` capture
 # (profiles/r2_ncu_full_v2.md: one 250 000-record chunk); bench.py cannot run under a profiler, so the figure is carried and
 # scaled to the launch size
@@ -430,6 +430,49 @@ def run_ours(args):
     packed_bytes_per_read = int(d_res_t[0]) / SMP - 8
     del d_tmp
 
+    # ---- extra (not part of the step): one `degrade` pass over a slice of the batch -- zlib + svb-zd records in, 3 low bits of
+    # every sample rounded away (src/degrade.c:255), zlib + ex-zd records out -- with the rounding kernel's own stage time
+    degrade = None
+    if not args.profile and not args.e2e_only:
+        DG, BITS = min(R, 262144), 3
+        d_dg = torch.zeros(DG * (rl // 2 + 512), dtype=torch.uint8, device="cuda")
+        d_dg_off = torch.zeros(DG + 1, dtype=torch.int64, device="cuda")
+        d_dg_back = torch.zeros(DG * (rl + 8) + 64, dtype=torch.uint8, device="cuda")
+        d_res_g = torch.zeros(2, dtype=torch.int64, device="cuda")
+        cdc.set_degrade(BITS)
+        cdc.blow5_recode_dev(M_ZLIB, M_SVB_ZD, M_ZLIB, M_EX_ZD, d_enc, enc_bytes, z_off[:DG], z_len[:DG], d_dg, d_res_g, d_dg_off)
+        cdc.sync()
+        cdc.stage_timing(True)
+        cdc.stage_report(reset=True)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        cdc.blow5_recode_dev(M_ZLIB, M_SVB_ZD, M_ZLIB, M_EX_ZD, d_enc, enc_bytes, z_off[:DG], z_len[:DG], d_dg, d_res_g, d_dg_off)
+        g1.record(stream)
+        cdc.sync()
+        dg_stages = cdc.stage_report(reset=True)
+        cdc.stage_timing(False)
+        cdc.set_degrade(0)
+        assert int(d_res_g[1]) == 0, "degrade pass failed"
+        dg_bytes = int(d_res_g[0])
+        go = d_dg_off.cpu().numpy().view(np.uint64)
+        cdc.blow5_recode_dev(M_ZLIB, M_EX_ZD, M_NONE, M_NONE, d_dg, dg_bytes, go[:-1] + np.uint64(8),
+                             (go[1:] - go[:-1] - np.uint64(8)).astype(np.uint32), d_dg_back, d_res_g, None)
+        cdc.sync()
+        assert int(d_res_g[1]) == 0 and int(d_res_g[0]) == DG * (rl + 8), "reading the degraded records back failed"
+        hs = rl - 2 * N   # bytes of a record in front of its samples (no auxiliary fields in this batch)
+        got = d_dg_back[:DG * (rl + 8)].view(DG, rl + 8)[:, 8 + hs:].contiguous().view(torch.int16)
+        src = d_raw[:DG * rl].view(DG, rl)[:, hs:].contiguous().view(torch.int16)
+        want = ((src.to(torch.int32) + (1 << (BITS - 1))) & ~((1 << BITS) - 1)).to(torch.int16)
+        assert torch.equal(got, want), "degrade: samples are not round(signal, 3 bits)"
+        qms = dg_stages["signal_degrade"][0]
+        degrade = {"what": "zlib+svb-zd records -> qts round (3 bits) -> zlib+ex-zd records, device resident, checked against "
+                           "(x + 4) & ~7 on the input samples", "reads": DG, "pass_ms": g0.elapsed_time(g1),
+                   "reads_per_s": DG / (g0.elapsed_time(g1) * 1e-3), "bytes_per_read_out": dg_bytes / DG,
+                   "size_vs_lossless_zlib_svbzd": (dg_bytes / DG) / (enc_bytes / R),
+                   "qts_round_kernel_ms": qms, "qts_algorithmic_bytes": 4 * N * DG,
+                   "qts_GBps": 4 * N * DG / (qms * 1e-3) / 1e9 if qms > 0 else None}
+        del d_dg, d_dg_back, got, src, want
+
     if args.profile and not args.e2e_only:
         if rank == 0:
             print(json.dumps({"profile_only": True, "encode_ms": enc_ms, "decode_ms": dec_ms, "ms_per_step": ms_total / K,
@@ -587,6 +630,10 @@ def run_ours(args):
                                    "sample": "timed at N=1 only (see the --impl reference arm)"}
         if split is not None:
             out["split_compare"] = split
+        if degrade is not None:
+            if degrade["qts_GBps"]:
+                degrade["qts_frac_of_hbm_peak"] = degrade["qts_GBps"] / peak
+            out["degrade"] = degrade
         print(json.dumps(out), flush=True)
     cdc.close()
     if world > 1:
