@@ -50,6 +50,11 @@ void recode_lanes_release(s5b_ctx *ctx) {
     for (int i = 0; i < NLANE; ++i) ctx->lane[i].release();
     if (ctx->d_img_base) cudaFree(ctx->d_img_base);
     ctx->d_img_base = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        ctx->dev_tab[i].release();
+        if (ctx->dev_tab_done[i]) cudaEventDestroy(ctx->dev_tab_done[i]);
+        ctx->dev_tab_done[i] = nullptr;
+    }
     if (ctx->d_rg_map) cudaFree(ctx->d_rg_map);
     ctx->d_rg_map = nullptr;
     ctx->rg_map_n = 0;
@@ -79,6 +84,7 @@ int lanes_init(s5b_ctx *ctx) {
         CU(cudaHostGetDevicePointer(reinterpret_cast<void **>(&l.h_res_dev), l.h_res, 0));
     }
     CU(cudaMalloc(&ctx->d_img_base, 64));
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&ctx->dev_tab_done[i], cudaEventDisableTiming));
     ctx->lanes_ready = true;
     return S5B_OK;
 }
@@ -134,6 +140,8 @@ struct Job {
     int qts = 0;          // > 0: slow5_rec_qts_round with this many bits between signal decode and encode (s5b_ctx_set_degrade)
     bool resig() const { return in_sig != out_sig || qts > 0; }  // the signal is decoded and stored anew
 };
+
+constexpr uint64_t DEV_CHUNK_RECORDS_MAX = 4u << 20;  // records per chunk of the device-resident form, at most
 
 struct Chunk {
     uint64_t first = 0, count = 0;
@@ -613,15 +621,58 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
     CU(cudaMemsetAsync(ctx->d_img_base, 0, 8, L.stream));
     if (n == 0) return S5B_OK;
     std::vector<Chunk> chunks;
-    // device-resident passes take larger chunks: there is no copy to overlap, only launch overheads to amortise
-    if (!cut_chunks(rec_off, rec_len, n, in_bytes, ctx->recode_dev_chunk_records, ctx->recode_dev_chunk_bytes, chunks))
-        return S5B_ERR_ARG;
-    // the record table goes up once per call (one pageable copy = one wait for the stream), chunks slice it on the device
+    // Device-resident passes take the largest chunks the card has room for: there is no copy to overlap, and every chunk ends
+    // with a tail -- the entropy kernels hand out records in rounds of 32 per warp that take the same few milliseconds whether
+    // the GPU is full or not, so a 1 M-record pass cut into four chunks pays four partly empty last rounds (measured on the
+    // north-star step, tools/dev/dev_chunk_sweep.sh: 262 144-record chunks 84.6 ms, one chunk 78.5 ms).  The workspace a
+    // chunk needs follows from its stored bytes (chunk_bounds); half of the memory that is free now, plus what this lane
+    // already holds, is the budget.  S5B_RECODE_DEV_CHUNK / S5B_RECODE_DEV_CHUNK_MB fix the caps instead.
+    uint64_t max_records = ctx->recode_dev_chunk_records, max_bytes = ctx->recode_dev_chunk_bytes;
+    if (!max_records || !max_bytes) {
+        Job probe{in_rec, in_sig, out_rec, out_sig, d_in, true, in_bytes, rec_off, rec_len, n, d_out, true, out_cap, d_img_off, d_result,
+                  nullptr, nullptr};
+        probe.qts = ctx->qts_bits;
+        // the stored bytes a single chunk would span (records and whatever lies between them)
+        uint64_t lo = ~0ull, hi = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            if (rec_off[i] < lo) lo = rec_off[i];
+            if (rec_off[i] + rec_len[i] > hi) hi = rec_off[i] + rec_len[i];
+        }
+        const uint64_t stored = hi > lo ? hi - lo : 0;
+        const Bounds b = chunk_bounds(probe, stored, n);
+        // + the deflate workspace (0.45 B per packed byte) and the per-record tables
+        const double need = (double)b.infl + 2.0 * b.sig_samples + b.svb + b.packed + 1.45 * b.z + 256.0 * n;
+        uint64_t parts = 1;
+        // (a lane that has done this pass before holds the slabs already: nothing to ask the driver)
+        const bool holds_it = L.infl.cap >= b.infl && L.sig.cap >= 2 * b.sig_samples + 32 && L.svb.cap >= b.svb + 32 &&
+                              L.packed.cap >= b.packed + 32 && L.z.cap >= b.z + 32;
+        if (!holds_it) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            uint64_t held = 0;
+            for (const DevBuf *d : {&L.infl, &L.sig, &L.svb, &L.packed, &L.z, &L.work, &L.iwork, &L.meta}) held += d->cap;
+            const double budget = 0.5 * (double)free_b + (double)held;
+            if (need > budget) parts = (uint64_t)(need / budget) + 1;
+        }
+        const uint64_t by_cap = (n + DEV_CHUNK_RECORDS_MAX - 1) / DEV_CHUNK_RECORDS_MAX;  // (per-record tables stay 32-bit friendly)
+        if (parts < by_cap) parts = by_cap;
+        if (!max_records) max_records = (n + parts - 1) / parts;
+        if (!max_bytes) max_bytes = (uint64_t)((double)stored / parts * 1.02) + (64u << 20);
+    }
+    if (!cut_chunks(rec_off, rec_len, n, in_bytes, max_records, max_bytes, chunks)) return S5B_ERR_ARG;
+    // the record table goes up once per call, chunks slice it on the device
     CU(L.tab.reserve(n * 12 + 64));
     uint64_t *d_tab_off = static_cast<uint64_t *>(L.tab.p);
     uint32_t *d_tab_len = reinterpret_cast<uint32_t *>(d_tab_off + n);
-    CU(cudaMemcpyAsync(d_tab_off, rec_off, n * 8, cudaMemcpyHostToDevice, L.stream));
-    CU(cudaMemcpyAsync(d_tab_len, rec_len, n * 4, cudaMemcpyHostToDevice, L.stream));
+    {
+        const unsigned t = ctx->dev_tab_next++ & 1u;
+        CU(cudaEventSynchronize(ctx->dev_tab_done[t]));  // its upload of two calls ago (a fresh event counts as complete)
+        CU(ctx->dev_tab[t].reserve(n * 12));
+        memcpy(ctx->dev_tab[t].p, rec_off, n * 8);
+        memcpy(static_cast<uint8_t *>(ctx->dev_tab[t].p) + n * 8, rec_len, n * 4);
+        CU(cudaMemcpyAsync(d_tab_off, ctx->dev_tab[t].p, n * 12, cudaMemcpyHostToDevice, L.stream));
+        CU(cudaEventRecord(ctx->dev_tab_done[t], L.stream));
+    }
     if (ctx->rg_map_n) return S5B_ERR_ARG;  // renumbering works on the library's own copy of the records: host form only
     Job j{in_rec, in_sig, out_rec, out_sig, d_in, true, in_bytes, rec_off, rec_len, n, d_out, true, out_cap, d_img_off, d_result,
           d_tab_off, d_tab_len};

@@ -120,6 +120,14 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
         long v = atol(e);
         if (v >= 2 && v <= NLANE) ctx->n_lanes = (int)v;
     }
+    if (const char *e = getenv("S5B_RECODE_DEV_CHUNK")) {
+        long v = atol(e);
+        if (v > 0) ctx->recode_dev_chunk_records = (size_t)v;
+    }
+    if (const char *e = getenv("S5B_RECODE_DEV_CHUNK_MB")) {
+        long v = atol(e);
+        if (v > 0) ctx->recode_dev_chunk_bytes = (size_t)v << 20;
+    }
     if (const char *e = getenv("S5B_RECODE_CHUNK_MB")) {
         long v = atol(e);
         if (v > 0) ctx->recode_chunk_bytes = (size_t)v << 20;

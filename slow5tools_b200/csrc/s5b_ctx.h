@@ -112,6 +112,11 @@ struct s5b_ctx {
     bool lanes_ready = false;
     int n_lanes = 3;
     uint64_t *d_img_base = nullptr;       // running output offset of a device-resident transcoding pass
+    // the device-resident form uploads the caller's record table through pinned staging (a copy from pageable memory waits for
+    // the stream to drain and leaves the GPU idle meanwhile); two buffers take turns, each guarded by the event of its last upload
+    s5b::PinBuf dev_tab[2];
+    cudaEvent_t dev_tab_done[2] = {nullptr, nullptr};
+    unsigned dev_tab_next = 0;
     s5b::StageTimer timer;
     uint32_t *d_rg_map = nullptr;     // read_group renumbering of the file being transcoded (s5b_ctx_set_rg_map), rg_map_n entries
     uint32_t rg_map_n = 0;
@@ -125,9 +130,10 @@ struct s5b_ctx {
     // starve the kernels (a chunk must still fill the GPU with 32-record rounds).
     size_t recode_chunk_records = 24576;
     size_t recode_chunk_bytes = 256u << 20;
-    // the device-resident form has no copies to overlap: large chunks amortise launches and kernel tails
-    size_t recode_dev_chunk_records = 262144;
-    size_t recode_dev_chunk_bytes = 2048ull << 20;
+    // the device-resident form has no copies to overlap: large chunks amortise launches and kernel tails.  0 = as large as the
+    // free device memory allows (recode_engine.cu, s5b_blow5_recode_dev)
+    size_t recode_dev_chunk_records = 0;
+    size_t recode_dev_chunk_bytes = 0;
     std::string last_cuda_error;
 };
 

@@ -24,12 +24,15 @@ def ro():
 
 @pytest.fixture(scope="module")
 def codecs():
-    """two contexts: default chunking, and 37-record chunks so that small batches exercise the 3-lane pipeline"""
+    """two contexts: default chunking, and 37-record chunks so that small batches exercise the 3-lane pipeline of the host form
+    and the running image offset of the device-resident form"""
     import slow5tools_b200 as s5
     big = s5.Codec(0)
     os.environ["S5B_RECODE_CHUNK"] = "37"
+    os.environ["S5B_RECODE_DEV_CHUNK"] = "37"   # (the device-resident form sizes its chunks from the free memory otherwise)
     small = s5.Codec(0)
     del os.environ["S5B_RECODE_CHUNK"]
+    del os.environ["S5B_RECODE_DEV_CHUNK"]
     yield big, small
     big.close()
     small.close()
