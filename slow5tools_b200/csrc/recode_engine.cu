@@ -282,15 +282,22 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
     const uint64_t *sig_src_off = nullptr;
     const uint32_t *sig_src_len = ra.sig_bytes;
     int sig_src_is_samples = 0;
+    // raw samples that go straight into the svb-zd encoder are read where they lie inside the records (any byte alignment):
+    // no copy to an aligned sample slab in between
+    const bool encode_in_place = j.in_sig == S5B_COMPRESS_NONE && j.out_sig == S5B_COMPRESS_SVB_ZD && !j.qts;
     if (j.resig()) {
-        CU(L.sig.reserve(B.sig_samples * 2 + 32));
-        {
+        if (!encode_in_place) {
+            CU(L.sig.reserve(B.sig_samples * 2 + 32));
             StageScope ts(ctx, st, ST_GLUE);
             CU(launch_rec_plan(PLAN_SIG_SAMPLES, n, ra, nullptr, 0, d_tmp, st));
             CU(scan(d_tmp, 8, d_sig_off));
             ctx->launches += 1;
         }
-        if (j.in_sig != S5B_COMPRESS_NONE) {
+        if (encode_in_place) {
+            StageScope ts(ctx, st, ST_GLUE);
+            CU(launch_rec_sig_abs(cur_off, ra, n, d_sigabs, st));
+            ctx->launches += 1;
+        } else if (j.in_sig != S5B_COMPRESS_NONE) {
             StageScope ts(ctx, st, ST_SIG_DEPRESS);
             CU(launch_rec_sig_abs(cur_off, ra, n, d_sigabs, st));
             SvbDecodeArgs da{cur, d_sigabs, ra.sig_bytes, cur_cap, n, static_cast<int16_t *>(L.sig.p), d_sig_off, d_ns2, d_st_sdec,
@@ -328,6 +335,14 @@ int enqueue_chunk(s5b_ctx *ctx, RecodeLane &L, const Job &j, const Chunk &c) {
             // the chunk is flagged through st_sdec and redone or reported
             SvbEncodeArgs ea{static_cast<const int16_t *>(L.sig.p), d_sig_off, ra.n_samples, n, static_cast<uint8_t *>(L.svb.p),
                              d_svb_off, d_svb_len, d_st_senc, L.d_counter};
+            if (encode_in_place) {
+                // (a record the locate kernel refused has n_samples = 0 and is flagged through its own status)
+                ea.sig = nullptr;
+                ea.sig_off = nullptr;
+                ea.src_bytes = cur;
+                ea.src_byte_off = d_sigabs;
+                ea.src_capacity = cur_cap;
+            }
             if (svb) CU(launch_svbzd_encode(ea, ctx->num_sms, ctx->enc_bps, st));
             else CU(launch_exzd_encode(ea, ctx->num_sms, ctx->xe_bps, st));
             ctx->launches += 1;
@@ -625,7 +640,7 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
     // with a tail -- the entropy kernels hand out records in rounds of 32 per warp that take the same few milliseconds whether
     // the GPU is full or not, so a 1 M-record pass cut into four chunks pays four partly empty last rounds (measured on the
     // north-star step, tools/dev/dev_chunk_sweep.sh: 262 144-record chunks 84.6 ms, one chunk 78.5 ms).  The workspace a
-    // chunk needs follows from its stored bytes (chunk_bounds); half of the memory that is free now, plus what this lane
+    // chunk needs follows from its stored bytes (chunk_bounds); 60 % of the memory that is free now, plus what this lane
     // already holds, is the budget.  S5B_RECODE_DEV_CHUNK / S5B_RECODE_DEV_CHUNK_MB fix the caps instead.
     uint64_t max_records = ctx->recode_dev_chunk_records, max_bytes = ctx->recode_dev_chunk_bytes;
     if (!max_records || !max_bytes) {
@@ -651,7 +666,7 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
             CU(cudaMemGetInfo(&free_b, &total_b));
             uint64_t held = 0;
             for (const DevBuf *d : {&L.infl, &L.sig, &L.svb, &L.packed, &L.z, &L.work, &L.iwork, &L.meta}) held += d->cap;
-            const double budget = 0.5 * (double)free_b + (double)held;
+            const double budget = 0.6 * (double)free_b + (double)held;
             if (need > budget) parts = (uint64_t)(need / budget) + 1;
         }
         const uint64_t by_cap = (n + DEV_CHUNK_RECORDS_MAX - 1) / DEV_CHUNK_RECORDS_MAX;  // (per-record tables stay 32-bit friendly)

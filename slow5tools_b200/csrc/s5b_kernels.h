@@ -15,6 +15,11 @@ struct SvbEncodeArgs {
     uint32_t *svb_len;        // n_reads
     int32_t *status;          // n_reads
     unsigned long long *work_counter;  // zeroed before launch
+    // Alternative source (sig == nullptr): the samples of read r are the 2 * n_samples[r] bytes at src_bytes + src_byte_off[r],
+    // any byte alignment -- the raw signal where it lies inside a packed record (record path: no copy to an aligned slab first).
+    const uint8_t *src_bytes = nullptr;
+    const uint64_t *src_byte_off = nullptr;  // n_reads
+    uint64_t src_capacity = 0;               // bytes of src_bytes that may be read (multiple of 16)
 };
 
 struct SvbDecodeArgs {

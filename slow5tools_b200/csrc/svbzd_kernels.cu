@@ -86,8 +86,10 @@ constexpr int ENC_STAGES = 2;
 // and appends at most 768: 15 + 3*512 + 768 = 2319.
 constexpr int ENC_DB = 2320;
 
+constexpr int ENC_STAGE_BYTES = ENC_CH_BYTES + 32;  // a chunk of a source that starts up to 15 bytes into its 16-byte granule, and the
+                                                    // word behind it that a realigning load touches
 struct __align__(128) EncWarpSmem {
-    uint8_t in[ENC_STAGES][ENC_CH_BYTES];  // staged signal
+    uint8_t in[ENC_STAGES][ENC_STAGE_BYTES];  // staged signal
     uint8_t dbuf[S5B_ENC_NDBUF][ENC_DB];   // data-stream double buffer; dbuf[x][0] <-> 16-byte aligned global address
     uint8_t kbuf[ENC_CH_SAMPLES / 4];      // key bytes of one chunk, natural index
     unsigned long long bar[ENC_STAGES];
@@ -261,7 +263,21 @@ __device__ __forceinline__ void enc_iteration(const uint2 wa, const uint2 wb, in
     }
 }
 
-__global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode_kernel(const SvbEncodeArgs a) {
+// the lane's quad idx (8 bytes) of a staged chunk whose first sample sits `mis` bytes into the stage (BYTE_SRC), else aligned
+template <bool BYTE_SRC>
+__device__ __forceinline__ uint2 enc_load_quad(const uint8_t *stage, uint32_t mis, uint32_t idx) {
+    if (!BYTE_SRC) return reinterpret_cast<const uint2 *>(stage)[idx];
+    const uint32_t bo = mis + idx * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(stage) + (bo >> 2);
+    const uint32_t sh = (bo & 3u) * 8u;
+    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2];
+    return make_uint2(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh));
+}
+
+// BYTE_SRC: the samples are read where they lie, at any byte alignment (a.src_bytes / a.src_byte_off); staging starts at the
+// 16-byte granule below the first sample and the lanes realign their quads with funnel shifts (two more instructions per quad)
+template <bool BYTE_SRC>
+__device__ __forceinline__ void svbzd_encode_body(const SvbEncodeArgs &a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EncWarpSmem *smem = reinterpret_cast<EncWarpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -283,14 +299,29 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode
         const uint64_t r = next_work(a.work_counter, lane);
         if (r >= a.n_reads) break;
         const uint32_t n = a.n_samples[r];
-        const uint64_t soff = a.sig_off[r];
-        const uint64_t scap = a.sig_off[r + 1] - soff;
         const uint64_t ooff = a.svb_off[r];
         const uint64_t ocap = a.svb_off[r + 1] - ooff;
         const uint32_t nkeys = (n + 3) >> 2;
         int32_t st = S5B_OK;
-        if ((soff & 7) || scap < n) st = S5B_ERR_ARG;
-        else if (ocap < 4ull + nkeys + 3ull * n) st = S5B_ERR_NOSPACE;
+        const uint8_t *src;        // 16-byte aligned start of the staged bytes
+        uint32_t mis = 0;          // bytes from there to the first sample
+        uint64_t slot_bytes16;     // bytes that may be bulk-copied from src: whole 16-byte granules inside the slab
+        if (!BYTE_SRC) {
+            const uint64_t soff = a.sig_off[r];
+            const uint64_t scap = a.sig_off[r + 1] - soff;
+            if ((soff & 7) || scap < n) st = S5B_ERR_ARG;
+            src = reinterpret_cast<const uint8_t *>(a.sig + soff);
+            // (the slot is a multiple of 8 samples except possibly the last one of the slab)
+            slot_bytes16 = (scap * 2) & ~15ull;
+        } else {
+            const uint64_t boff = a.src_byte_off[r];
+            if (boff + 2ull * n > a.src_capacity) st = S5B_ERR_ARG;
+            const uint8_t *first = a.src_bytes + boff;
+            mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 15u);
+            src = first - mis;
+            slot_bytes16 = st == S5B_OK ? (a.src_capacity - (boff - mis)) & ~15ull : 0;
+        }
+        if (st == S5B_OK && ocap < 4ull + nkeys + 3ull * n) st = S5B_ERR_NOSPACE;
         if (st != S5B_OK) {
             if (lane == 0) {
                 a.status[r] = st;
@@ -298,12 +329,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode
             }
             continue;
         }
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.sig + soff);
         uint8_t *dst = a.svb + ooff;
-        // bytes that may be bulk-copied for this read: whole 16-byte granules inside the read's slot
-        // (the slot is a multiple of 8 samples except possibly the last one of the slab)
-        const uint64_t slot_bytes16 = (scap * 2) & ~15ull;
-        const uint64_t n_bytes = (uint64_t)n * 2;
+        const uint64_t n_bytes = (uint64_t)mis + (uint64_t)n * 2;  // staged bytes that hold the read
 
         if (lane < 4) dst[lane] = (uint8_t)(n >> (8 * lane));  // u32 LE header, slow5_press.c:1074
         uint8_t *kdst = dst + 4;
@@ -312,19 +339,22 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode
         d.gbase = ddst - d.head;
 
         const uint32_t nchunks = (n + ENC_CH_SAMPLES - 1) / ENC_CH_SAMPLES;
-        // bulk-copyable bytes of the read, split into whole chunks and one last piece (32-bit from here on)
+        // Bulk-copyable bytes of the read.  Stage byte 0 of chunk k is src + k * ENC_CH_BYTES; a chunk whose samples start `mis`
+        // bytes into the stage needs one more granule behind its ENC_CH_BYTES (the next chunk copies that granule again).
         uint64_t copyable = (n_bytes + 15) & ~15ull;
         if (copyable > slot_bytes16) copyable = slot_bytes16;
+        // split into whole chunks and one last piece (32-bit from here on)
         const uint32_t copy_full = (uint32_t)(copyable / ENC_CH_BYTES);
         const uint32_t copy_last = (uint32_t)(copyable % ENC_CH_BYTES);
         auto issue = [&](uint32_t k, uint32_t qq) {
             // chunk k of this read -> stage qq & 1
-            const uint32_t bytes = k < copy_full ? (uint32_t)ENC_CH_BYTES : (k == copy_full ? copy_last : 0u);
+            uint32_t bytes = k < copy_full ? (uint32_t)ENC_CH_BYTES : (k == copy_full ? copy_last : 0u);
+            if (BYTE_SRC && mis && k < copy_full && (k + 1 < copy_full || copy_last)) bytes += 16;
             const uint32_t stage = qq & 1;
             if (lane == 0) {
                 if (bytes) {
                     mbar_arrive_expect_tx(bar0 + 8 * stage, bytes);
-                    bulk_g2s(in0 + stage * ENC_CH_BYTES, src + (size_t)k * ENC_CH_BYTES, bytes, bar0 + 8 * stage);
+                    bulk_g2s(in0 + stage * ENC_STAGE_BYTES, src + (size_t)k * ENC_CH_BYTES, bytes, bar0 + 8 * stage);
                 } else {
                     // nothing bulk-copyable (a < 8-sample tail in the last slot): complete the phase by hand
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * stage) : "memory");
@@ -340,21 +370,28 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode
             const uint32_t stage = q & 1;
             mbar_wait(bar0 + 8 * stage, (q >> 1) & 1);
             const uint32_t chunk_samples = min((uint32_t)ENC_CH_SAMPLES, n - k * ENC_CH_SAMPLES);
-            if (bytes_cur < chunk_samples * 2) {
+            if (bytes_cur < mis + chunk_samples * 2) {
                 // ragged end of the slab: the bulk copy could not take the last (< 16 byte) piece
-                const int16_t *g = a.sig + soff + (uint64_t)k * ENC_CH_SAMPLES;
-                int16_t *s = reinterpret_cast<int16_t *>(ws.in[stage]);
-                for (uint32_t i = bytes_cur / 2 + lane; i < chunk_samples; i += 32) s[i] = g[i];
+                if (!BYTE_SRC) {
+                    const int16_t *g = reinterpret_cast<const int16_t *>(src) + (uint64_t)k * ENC_CH_SAMPLES;
+                    int16_t *s = reinterpret_cast<int16_t *>(ws.in[stage]);
+                    for (uint32_t i = bytes_cur / 2 + lane; i < chunk_samples; i += 32) s[i] = g[i];
+                } else {
+                    const uint8_t *g = src + (uint64_t)k * ENC_CH_BYTES;
+                    for (uint32_t i = bytes_cur + lane; i < mis + chunk_samples * 2; i += 32) ws.in[stage][i] = g[i];
+                }
                 __syncwarp();
             }
-            const uint2 *in2 = reinterpret_cast<const uint2 *>(ws.in[stage]);
+            const uint8_t *in2 = ws.in[stage];
             const uint32_t full_iters = chunk_samples >> 8;
             for (uint32_t it = 0; it < full_iters; ++it)
-                enc_iteration<false>(in2[it * 64 + lane], in2[it * 64 + 32 + lane], carry, lane, rot_src, 256, d,
+                enc_iteration<false>(enc_load_quad<BYTE_SRC>(in2, mis, it * 64 + lane),
+                                     enc_load_quad<BYTE_SRC>(in2, mis, it * 64 + 32 + lane), carry, lane, rot_src, 256, d,
                                      ws.kbuf + it * 64);
             const int tail = chunk_samples & 255;
             if (tail)
-                enc_iteration<true>(in2[full_iters * 64 + lane], in2[full_iters * 64 + 32 + lane], carry, lane, rot_src,
+                enc_iteration<true>(enc_load_quad<BYTE_SRC>(in2, mis, full_iters * 64 + lane),
+                                    enc_load_quad<BYTE_SRC>(in2, mis, full_iters * 64 + 32 + lane), carry, lane, rot_src,
                                     tail, d, ws.kbuf + full_iters * 64);
             __syncwarp();
             // ---- end of chunk: key bytes out, data segments out
@@ -386,6 +423,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode
         __syncwarp();
     }
     if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk copy's reads
+}
+
+__global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode_kernel(const SvbEncodeArgs a) {
+    svbzd_encode_body<false>(a);
+}
+// the samples where they lie inside packed records (the transcoder's encode pass: no copy to an aligned slab first)
+__global__ void __launch_bounds__(ENC_WARPS * 32, S5B_ENC_MIN_CTAS) svbzd_encode_bytes_kernel(const SvbEncodeArgs a) {
+    svbzd_encode_body<true>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -892,10 +937,16 @@ int svbzd_encode_blocks_per_sm() {
     if (cudaFuncSetAttribute(svbzd_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(sizeof(EncWarpSmem) * ENC_WARPS)) != cudaSuccess)
         return 0;
+    if (cudaFuncSetAttribute(svbzd_encode_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(EncWarpSmem) * ENC_WARPS)) != cudaSuccess)
+        return 0;
+    int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, svbzd_encode_kernel, ENC_WARPS * 32,
+                                                      sizeof(EncWarpSmem) * ENC_WARPS) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, svbzd_encode_bytes_kernel, ENC_WARPS * 32,
                                                       sizeof(EncWarpSmem) * ENC_WARPS) != cudaSuccess)
         return 0;
-    return n;
+    return n < nb ? n : nb;  // one grid size for both forms
 }
 int svbzd_decode_blocks_per_sm() {
     int n = 0;
@@ -914,8 +965,9 @@ static unsigned persistent_grid(uint64_t n_reads, int warps, int num_sms, int bl
 cudaError_t launch_svbzd_encode(const SvbEncodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    svbzd_encode_kernel<<<persistent_grid(a.n_reads, ENC_WARPS, num_sms, blocks_per_sm), ENC_WARPS * 32,
-                          sizeof(EncWarpSmem) * ENC_WARPS, st>>>(a);
+    const unsigned grid = persistent_grid(a.n_reads, ENC_WARPS, num_sms, blocks_per_sm);
+    if (a.sig) svbzd_encode_kernel<<<grid, ENC_WARPS * 32, sizeof(EncWarpSmem) * ENC_WARPS, st>>>(a);
+    else svbzd_encode_bytes_kernel<<<grid, ENC_WARPS * 32, sizeof(EncWarpSmem) * ENC_WARPS, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_svbzd_decode(const SvbDecodeArgs &a, int num_sms, int blocks_per_sm, cudaStream_t st) {
