@@ -33,10 +33,13 @@ namespace s5b {
 
 namespace inft {
 
-// Measured on B200 (profiles/r2_inflate_thread_variants.md): 20 warps per SM is the sweet spot -- fewer hide too little of the
-// serial decoders' latency, more shrink the L1 (shared memory grows) and worsen the tail of the 32-record rounds.
+// Measured on B200: 22 warps per SM.  Fewer hide too little of the serial decoders' latency, more shrink the L1 (shared memory
+// grows) and cost registers (the launch bound forces spills from 11 CTAs on).  The first sweep (profiles/
+// r2_inflate_thread_variants.md) was taken on 262 144-record chunks, where 18..24 warps per SM all need three 32-record rounds per
+// chunk and 20 looked best; on one 1 M-record chunk (tools/dev/ti_ctas_sweep.sh, profiles/r2_ti_ctas_sweep.txt) the records per
+// round and the time of a round give 9: 29.7, 10: 31.4, 11: 33.0, 12: 32.6 M records/s.
 #ifndef S5B_TI_CTAS
-#define S5B_TI_CTAS 10
+#define S5B_TI_CTAS 11
 #endif
 #ifndef S5B_TI_RING
 #define S5B_TI_RING 64

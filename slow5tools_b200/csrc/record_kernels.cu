@@ -28,8 +28,18 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
         const uint32_t body = (n - head) >> 4;
         const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
         uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
-        for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
-        for (uint32_t i = head + (body << 4) + lane; i < n; i += 32) dst[i] = src[i];
+        // four loads in flight per lane before the first store (source and destination may alias as far as the compiler knows,
+        // so it keeps the order written here)
+        uint32_t i = lane;
+        for (; i + 96 < body; i += 128) {
+            const uint4 v0 = s4[i], v1 = s4[i + 32], v2 = s4[i + 64], v3 = s4[i + 96];
+            d4[i] = v0;
+            d4[i + 32] = v1;
+            d4[i + 64] = v2;
+            d4[i + 96] = v3;
+        }
+        for (; i < body; i += 32) d4[i] = s4[i];
+        for (uint32_t t = head + (body << 4) + lane; t < n; t += 32) dst[t] = src[t];
     } else if (n >= 64) {
         // different 16-byte phase: destination-aligned 128-bit stores, every quad assembled from five aligned source
         // words with funnel shifts (the fifth word may lie up to 7 bytes past the last source byte: every slab this
@@ -41,7 +51,24 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
         const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s0) & 3u) * 8u;
         const uint32_t *w = reinterpret_cast<const uint32_t *>(s0 - (sh >> 3));
         uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
-        for (uint32_t i = lane; i < body; i += 32) {
+        uint32_t i = lane;
+        for (; i + 32 < body; i += 64) {  // two quads per lane in flight
+            const uint32_t *q = w + 4 * i, *p = q + 128;
+            const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+            const uint32_t b0 = p[0], b1 = p[1], b2 = p[2], b3 = p[3], b4 = p[4];
+            uint4 v, u;
+            v.x = __funnelshift_r(a0, a1, sh);
+            v.y = __funnelshift_r(a1, a2, sh);
+            v.z = __funnelshift_r(a2, a3, sh);
+            v.w = __funnelshift_r(a3, a4, sh);
+            u.x = __funnelshift_r(b0, b1, sh);
+            u.y = __funnelshift_r(b1, b2, sh);
+            u.z = __funnelshift_r(b2, b3, sh);
+            u.w = __funnelshift_r(b3, b4, sh);
+            d4[i] = v;
+            d4[i + 32] = u;
+        }
+        for (; i < body; i += 32) {
             const uint32_t *q = w + 4 * i;
             const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
             uint4 v;
@@ -51,7 +78,7 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
             v.w = __funnelshift_r(a3, a4, sh);
             d4[i] = v;
         }
-        for (uint32_t i = head + (body << 4) + lane; i < n; i += 32) dst[i] = src[i];
+        for (uint32_t t = head + (body << 4) + lane; t < n; t += 32) dst[t] = src[t];
     } else if (((ds ^ ss) & 3u) == 0) {
         uint32_t head = (uint32_t)((4u - (ds & 3u)) & 3u);
         if (head > n) head = n;
