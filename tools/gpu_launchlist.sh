@@ -2,7 +2,7 @@
 # launch list of the north-star step: every kernel of the library, gpu__time_duration only.  usage: bash tools/gpu_launchlist.sh <tag> [reads]
 TAG=${1:-ll}; READS=${2:-1000000}
 mkdir -p gpurun_out
-KR='regex:s5b|svbzd|inflate|deflate|rec_|image_|zstd|scan_|exzd|recode_|rebase|ascii|gather_copy|sig_extract'
+KR='regex:s5b|svbzd|inflate|deflate|rec_|image_|zstd|scan_|exzd|recode_|rebase|ascii|gather_copy|sig_extract|qts'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 2500 --csv \
    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --profile --reads $READS > gpurun_out/${TAG}_launches.log 2>&1
 tail -1 gpurun_out/${TAG}_launches.log | cut -c1-300
