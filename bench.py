@@ -38,11 +38,12 @@ METRIC = "BLOW5 svb-zd+zlib reads/sec (encode+decode)"
 UNIT = "reads/s"
 M_NONE, M_ZLIB, M_SVB_ZD, M_EX_ZD = 0, 1, 2, 4
 # dram__bytes_read.sum + dram__bytes_write.sum per 100 000 records from the committed `ncu --set full` capture
-# (profiles/r2_ncu_full_v2.md: one 250 000-record chunk); bench.py cannot run under a profiler, so the figure is carried and
+# (profiles/r2_ncu_full_v2.md, r2_ncu_full_final2.md: one 250 000-record chunk); bench.py cannot run under a profiler, so the figure is carried and
 # scaled to the launch size
 NCU_TRAFFIC_PER_100K = {"record_press": ((1338.1e6 + 212.4e6) + (240.4e6 + 59.4e6) + (866.6e6 + 984.5e6) + (1729.4e6 + 867.3e6)) / 2.5,
-                        "record_depress": (1338.4e6 + 1609.8e6) / 2.5}    # count + tree + header + emit / inflate_thread
-NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_full_v2.md (ncu --set full, one 250k-record chunk of the same workload), scaled by launch size"
+                        "record_depress": (1423.4e6 + 1642.1e6) / 2.5}    # count + tree + header + emit / inflate_thread
+NCU_TRAFFIC_SOURCE = ("profiles/r2_ncu_full_v2.md (deflate kernels) and profiles/r2_ncu_full_final2.md (inflate_thread_kernel): ncu --set full, "
+                      "one 250k-record chunk of the same workload, scaled by launch size")
 STAGE_KERNELS = {"record_press": "deflate_count_kernel + deflate_tree_kernel + deflate_header_kernel + deflate_emit_kernel "
                                  "(one launch group per chunk)",
                  "record_depress": "inflate_thread_kernel (+ the warp-per-stream inflate_kernel's sweep for long streams)"}

@@ -15,7 +15,8 @@
 //     (4*lane.. and 128+4*lane..) so that the byte scatter into shared memory is nearly free of bank
 //     conflicts; one warp prefix scan over both quads' byte counts gives every lane its data offsets;
 //     the data stream leaves once per 1024-sample chunk as one bulk shared->global copy (UBLKCP.G.S),
-//     the key bytes as two word stores per lane;
+//     the key bytes as two word stores per lane; svbzd_encode_bytes_kernel is the same body for samples at any byte
+//     alignment (inside packed records): staging starts at the 16-byte granule below, lanes realign with funnel shifts;
 //   * decode: the variable-length data stream is staged by bulk async copies into a 4 x 1 KiB
 //     per-warp ring (mirrored at its end so word loads never wrap); a warp prefix scan over the
 //     control-byte lengths resolves the per-lane data offsets; values are widened pairwise with PRMT,
