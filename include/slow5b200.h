@@ -231,6 +231,13 @@ int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_
 int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *d_in,
                          uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n, uint8_t *d_out,
                          uint64_t out_cap, uint64_t *d_result, uint64_t *d_img_off);
+/* Workspace of the device-resident form.  A pass is cut into chunks, and every chunk ends with a partly idle GPU (the entropy
+ * kernels hand out records in rounds of 32 per warp), so s5b_blow5_recode_dev takes the largest chunks its workspace budget
+ * allows: by default 60 % of the device memory that is free at the call plus what the context already holds (the slabs stay with
+ * the context until s5b_ctx_destroy).  Worst-case slabs are sized from the stored bytes alone: about 65 KB per 4096-sample record
+ * in the none -> zlib + svb-zd direction, 46 KB in the opposite one.  max_bytes > 0 fixes the budget instead; 0 = automatic.
+ * (The environment variables S5B_RECODE_DEV_CHUNK / S5B_RECODE_DEV_CHUNK_MB, read at s5b_ctx_create, fix the chunk caps.) */
+int s5b_ctx_set_recode_workspace(s5b_ctx_t *ctx, uint64_t max_bytes);
 /* waits for everything the context has enqueued */
 int s5b_ctx_sync(s5b_ctx_t *ctx);
 /* the cudaStream_t the device-resident transcoder enqueues on (for callers that order their own work against it) */

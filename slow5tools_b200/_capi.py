@@ -86,6 +86,7 @@ _SIGS = {
     "s5b_stage_name": (C.c_char_p, [C.c_int]),
     "s5b_ctx_set_aux_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "s5b_ctx_set_rg_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "s5b_ctx_set_recode_workspace": (C.c_int, [C.c_void_p, C.c_uint64]),
     "s5b_ctx_set_degrade": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]),
     "s5b_qts_round_dev": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp]),
     "s5b_qts_round_batch_host": (C.c_int, [_vp, C.c_int, _P(_vp), _P(_sz), _sz, _P(_vp), _P(_sz)]),

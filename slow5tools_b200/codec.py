@@ -234,6 +234,10 @@ class Codec:
         self._check(lib.s5b_ctx_stage_report(self._h, ms, cnt, 1 if reset else 0), "s5b_ctx_stage_report")
         return {lib.s5b_stage_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k)}
 
+    def set_recode_workspace(self, max_bytes):
+        """workspace budget of blow5_recode_dev in bytes (0 = sized from the free device memory)"""
+        self._check(lib.s5b_ctx_set_recode_workspace(self._h, int(max_bytes)), "s5b_ctx_set_recode_workspace")
+
     def set_degrade(self, bits, check_dataset=False, digitisation=0.0, sampling_rate=0.0):
         """src/degrade.c:240-263: while bits > 0 every transcoding pass rounds that many low bits of each sample away"""
         self._check(lib.s5b_ctx_set_degrade(self._h, int(bits), int(bool(check_dataset)), float(digitisation),

@@ -661,7 +661,9 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
         // (a lane that has done this pass before holds the slabs already: nothing to ask the driver)
         const bool holds_it = L.infl.cap >= b.infl && L.sig.cap >= 2 * b.sig_samples + 32 && L.svb.cap >= b.svb + 32 &&
                               L.packed.cap >= b.packed + 32 && L.z.cap >= b.z + 32;
-        if (!holds_it) {
+        if (ctx->recode_dev_workspace) {
+            if (need > (double)ctx->recode_dev_workspace) parts = (uint64_t)(need / (double)ctx->recode_dev_workspace) + 1;
+        } else if (!holds_it) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
             uint64_t held = 0;
@@ -762,6 +764,12 @@ int s5b_ctx_set_rg_map(s5b_ctx_t *ctx, const uint32_t *map, uint32_t n) {
         CU(cudaMemcpy(ctx->d_rg_map, map, (size_t)n * 4, cudaMemcpyHostToDevice));
         ctx->rg_map_n = n;
     }
+    return S5B_OK;
+}
+
+int s5b_ctx_set_recode_workspace(s5b_ctx_t *ctx, uint64_t max_bytes) {
+    if (!ctx) return S5B_ERR_ARG;
+    ctx->recode_dev_workspace = max_bytes;
     return S5B_OK;
 }
 

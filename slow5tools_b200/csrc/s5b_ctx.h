@@ -134,6 +134,7 @@ struct s5b_ctx {
     // free device memory allows (recode_engine.cu, s5b_blow5_recode_dev)
     size_t recode_dev_chunk_records = 0;
     size_t recode_dev_chunk_bytes = 0;
+    uint64_t recode_dev_workspace = 0;    // s5b_ctx_set_recode_workspace: the budget in bytes, 0 = from the free memory
     std::string last_cuda_error;
 };
 

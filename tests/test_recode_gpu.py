@@ -127,6 +127,13 @@ def test_device_form_equals_host_form(ro, codecs):
         rc, raw, _ = host_recode(cdc, back, stored)
         err, draw, _ = dev_recode(cdc, back, stored)
         assert rc == 0 and err == 0 and raw == draw and walk_image(raw) == use
+    # a workspace budget far below what one chunk over the batch needs: the default context cuts the pass into many chunks
+    big = codecs[0]
+    big.set_recode_workspace(1 << 20)
+    err, dimg2, doff2 = dev_recode(big, (M_NONE, M_NONE, M_ZLIB, M_SVB_ZD), recs, gap=8)
+    big.set_recode_workspace(0)
+    rc, img, off = host_recode(big, (M_NONE, M_NONE, M_ZLIB, M_SVB_ZD), recs, gap=8)
+    assert err == 0 and rc == 0 and dimg2 == img and np.array_equal(doff2, off)
 
 
 def test_exzd_and_zstd_records(ro, codecs):

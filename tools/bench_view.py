@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--dir", default="/dev/shm")
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--methods", default="zlib:svb-zd", help="comma separated REC:SIG output methods to time")
+    ap.add_argument("--degrade", type=int, default=0, help="also time `degrade -b BITS` of the zlib:svb-zd file with both tools")
     a = ap.parse_args()
     from slow5tools_b200 import synth
     cores = os.cpu_count() or 1
@@ -92,6 +93,22 @@ def main():
             res["encode_speedup"] = res["reference"]["encode_s"] / res["ours"]["encode_s"]
             res["decode_speedup"] = res["reference"]["decode_s"] / res["ours"]["decode_s"]
         out["methods"][combo] = res
+    if a.degrade and "zlib:svb-zd" in out["methods"] and os.path.exists(REF):
+        # `degrade -b BITS` (lossy; default output zlib + ex-zd) of the reference-written zlib + svb-zd file, both tools; the two
+        # outputs must decode to the same samples
+        subprocess.check_call([REF, "view", "-t", str(cores), raw, "-o", z_ref], stderr=subprocess.DEVNULL)
+        d_ref, d_ours = os.path.join(a.dir, "s5b_dg_ref.blow5"), os.path.join(a.dir, "s5b_dg_ours.blow5")
+        t_ref = min(timed([REF, "degrade", "-t", str(cores), "-b", str(a.degrade), z_ref, "-o", d_ref]) for _ in range(a.repeat))
+        t_ours = min(timed([CLI, "degrade", "-t", str(cores), "-b", str(a.degrade), z_ref, "-o", d_ours]) for _ in range(a.repeat))
+        flat = []
+        for f in (d_ref, d_ours):
+            subprocess.check_call([CLI, "view", f, "-c", "none", "-s", "ex-zd", "-o", back], stderr=subprocess.DEVNULL)
+            flat.append(open(back, "rb").read())
+        out["degrade"] = {"bits": a.degrade, "reference_s": t_ref, "ours_s": t_ours, "speedup": t_ref / t_ours,
+                          "reference_bytes": os.path.getsize(d_ref), "ours_bytes": os.path.getsize(d_ours),
+                          "records_identical_once_unwrapped": flat[0] == flat[1]}
+        for p in (d_ref, d_ours):
+            os.remove(p)
     for p in (raw, z_ref, z_ours, back):
         if os.path.exists(p):
             os.remove(p)
