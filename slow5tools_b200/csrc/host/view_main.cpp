@@ -149,18 +149,32 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
     // output is at most ~2.4x the input when decompressing zlib+svb-zd records and smaller when compressing; a
     // chunk whose image does not fit is retried with a larger buffer
     const bool expanding = hdr.record_method != PRESS_NONE || hdr.signal_method != PRESS_NONE;
-    for (int i = 0; i < NCH; ++i) {
+    auto alloc_chunk = [&](int i) -> bool {
         chunks[i].in_cap = target + slack;
         chunks[i].in = static_cast<uint8_t *>(s5b_host_alloc(chunks[i].in_cap));
         chunks[i].out_cap = (expanding ? 3 : 1) * target + slack;
         chunks[i].out = static_cast<uint8_t *>(s5b_host_alloc(chunks[i].out_cap));
-        if (!chunks[i].in || !chunks[i].out) {
-            ERROR("%s", "cannot allocate pinned staging memory");
-            return 1;
-        }
-        free_q.push(&chunks[i]);
+        return chunks[i].in && chunks[i].out;
+    };
+    // page-locking ~140 MB per chunk takes ~0.1 s: the first chunk is made here, the others while it is being read and transcoded
+    // (a chunk that cannot be had just leaves the pipeline with fewer buffers)
+    if (!alloc_chunk(0)) {
+        ERROR("%s", "cannot allocate pinned staging memory");
+        return 1;
     }
-    if (timing) fprintf(stderr, "[timing] pinned alloc %.3f s\n", now_s() - t_begin);
+    free_q.push(&chunks[0]);
+    std::thread more_chunks([&] {
+        for (int i = 1; i < NCH; ++i)
+            if (alloc_chunk(i)) free_q.push(&chunks[i]);
+        if (timing) fprintf(stderr, "[timing] pinned staging complete %.3f s after the start\n", now_s() - t_begin);
+    });
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } join_more_chunks{more_chunks};
+    if (timing) fprintf(stderr, "[timing] first pinned chunk %.3f s\n", now_s() - t_begin);
     // the header was consumed through stdio; continue with plain read() from the same position
     const int fd = fileno(rd.fp);
     const off_t start = ftello(rd.fp);
@@ -848,7 +862,18 @@ int merge_main(int argc, char **argv);  // merge_split_main.cpp
 int split_main(int argc, char **argv);
 int degrade_main(int argc, char **argv);  // degrade_main.cpp
 
+static int run_command(int argc, char **argv);
+
 int main(int argc, char **argv) {
+    const int rc = run_command(argc, argv);
+    // Every output file has been closed by its sub-command.  The CUDA runtime's orderly teardown at exit (primary context,
+    // page-locked buffers, device slabs) costs a few tenths of a second and buys nothing here: leave it to the kernel.
+    fflush(nullptr);
+    if (!getenv("S5B_ORDERLY_EXIT")) _exit(rc);
+    return rc;
+}
+
+static int run_command(int argc, char **argv) {
     if (argc >= 2 && (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V"))) {
         printf("slow5tools-b200 %s\n", s5b_version());
         return 0;

@@ -78,12 +78,13 @@ int s5b_ctx_create(int device, s5b_ctx_t **out) {
     if (!ctx) return S5B_ERR_MEM;
     ctx->device = device;
     DeviceGuard g(device);
-    cudaDeviceProp prop;
-    if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    // (one attribute, not cudaGetDeviceProperties: that call fills in dozens of fields and takes tens of milliseconds)
+    int n_sm = 0;
+    if (!g.ok || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n_sm <= 0) {
         delete ctx;
         return S5B_ERR_DEVICE;
     }
-    ctx->num_sms = prop.multiProcessorCount;
+    ctx->num_sms = n_sm;
     lap("set device / properties");
     ctx->enc_bps = svbzd_encode_blocks_per_sm();
     ctx->dec_bps = svbzd_decode_blocks_per_sm();
