@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 #include <cerrno>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cinttypes>
@@ -182,6 +183,13 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
         ERROR("%s", "cannot seek in the input file");
         return 1;
     }
+    // size of a regular input file (-1: a pipe or the like, read sequentially) and the read position in it
+    int64_t in_size = -1;
+    uint64_t rpos = (uint64_t)start;
+    {
+        struct stat ist;
+        if (fstat(fd, &ist) == 0 && S_ISREG(ist.st_mode)) in_size = (int64_t)ist.st_size;
+    }
     std::string rerr;
     std::thread reader([&] {
         // big sequential read()s straight into the pinned chunk; records are walked in place (u64 size chain,
@@ -218,7 +226,41 @@ int view_fast_binary(Reader &rd, FILE *fout, s5b_ctx_t *gpu, int rec_out, int si
             if (filled) memcpy(c->in, carry.data(), filled);
             carry.clear();
             bool file_end = false;
-            while (filled < c->in_cap) {
+            if (in_size >= 0 && rpos <= (uint64_t)in_size) {
+                // a regular file: the chunk's bytes are known in advance and come in through a few positioned reads side by side
+                // (one read() copies out of the page cache at ~3-5 GB/s on one core)
+                const uint64_t want = std::min<uint64_t>(c->in_cap - filled, (uint64_t)in_size - rpos);
+                const int parts = want >= (8u << 20) ? 4 : 1;
+                std::atomic<int> bad(0);
+                std::thread th[4];
+                for (int k = 0; k < parts; ++k) {
+                    const uint64_t a0 = want * k / parts, a1 = want * (k + 1) / parts;
+                    auto work = [&, a0, a1] {
+                        uint64_t done = a0;
+                        while (done < a1) {
+                            const ssize_t got = pread(fd, c->in + filled + done, a1 - done, (off_t)(rpos + done));
+                            if (got <= 0) {  // (0: the file shrank under us)
+                                bad = got < 0 ? errno : EIO;
+                                return;
+                            }
+                            done += (uint64_t)got;
+                        }
+                    };
+                    if (k + 1 < parts) th[k] = std::thread(work);
+                    else work();
+                }
+                for (int k = 0; k + 1 < parts; ++k) th[k].join();
+                if (bad) {
+                    rerr = std::string("read failed: ") + strerror(bad);
+                    c->err = 1;
+                    file_end = true;
+                } else {
+                    filled += want;
+                    rpos += want;
+                    file_end = rpos == (uint64_t)in_size;
+                }
+            }
+            while (in_size < 0 && filled < c->in_cap) {
                 const ssize_t got = read(fd, c->in + filled, c->in_cap - filled);
                 if (got < 0) {
                     rerr = std::string("read failed: ") + strerror(errno);
