@@ -222,8 +222,8 @@ int s5b_blow5_recode_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, i
 int s5b_blow5_recode_batch_host(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *h_in,
                                 uint64_t in_bytes, const uint64_t *rec_off, const uint32_t *rec_len, uint64_t n,
                                 uint8_t *h_out, uint64_t out_cap, uint64_t *out_bytes, uint64_t *out_img_off);
-/* Device-resident form: payload d_in and image d_out live in HBM (d_in's allocation must extend to in_bytes rounded up to
- * 16), the record table rec_off / rec_len is HOST memory (metadata the caller produced when it laid the batch out).  The
+/* Device-resident form: payload d_in and image d_out live in HBM (d_in must be 16-byte aligned -- S5B_ERR_ARG otherwise -- and
+ * its allocation must extend to in_bytes rounded up to 16), the record table rec_off / rec_len is HOST memory (metadata the caller produced when it laid the batch out).  The
  * call only enqueues work on the context's transcoding stream (s5b_ctx_recode_stream) and returns; after s5b_ctx_sync
  * d_result[0] = image bytes written, d_result[1] = first error as a sign-extended S5B_ERR_* (0 = none; S5B_ERR_NOSPACE also
  * when a record inflates to more than 4x + 1 KiB of its stored size -- the host form retries those, this form cannot --

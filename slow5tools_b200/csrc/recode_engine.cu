@@ -626,6 +626,8 @@ int s5b_blow5_recode_dev(s5b_ctx_t *ctx, int in_rec, int in_sig, int out_rec, in
     if (!ctx || !d_result) return S5B_ERR_ARG;
     if (!methods_ok(in_rec, in_sig, out_rec, out_sig)) return S5B_ERR_ARG;
     if (n && (!d_in || !rec_off || !rec_len || !d_out)) return S5B_ERR_ARG;
+    // bulk copies and realigning loads work on the 16-byte granules of the payload: its base must be a granule boundary
+    if (n && (reinterpret_cast<uintptr_t>(d_in) & 15u)) return S5B_ERR_ARG;
     DeviceGuard g(ctx->device);
     {
         const int rc = lanes_init(ctx);
