@@ -72,6 +72,26 @@ def test_category_name_collisions_and_bad_tables(fx, tmp_path):
     assert sorted(os.listdir(tmp_path / "w")) == ["example2_0_multi_1.slow5"]
 
 
+REF = os.path.join(ROOT, "oracle", "_ref", "slow5tools_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/slow5tools_ref not present")
+@pytest.mark.parametrize("table,src,flags", [
+    ("demux3/bs.txt", "demux3/example2_0.slow5", []),
+    ("demux3/bs.txt", "demux3/example2_0.slow5", ["-u", "mixed"]),
+    ("demux9/barcode_summary.txt", "demux10/example2_0_multi.slow5", ["--demux-rid", "rid", "--demux-code", "code", "-m", "rest"]),
+])
+def test_uncompressed_blow5_output_equals_the_reference_binary(fx, tmp_path, table, src, flags):
+    """no codec involved (-c none -s none): the files must be the reference's byte for byte, names included"""
+    ours, theirs = tmp_path / "ours", tmp_path / "theirs"
+    r = split(fx, ours, table, src, "--to", "blow5", "-c", "none", "-s", "none", *flags)
+    assert r.returncode == 0, r.stderr.decode()
+    q = subprocess.run([REF, "split", "-x", os.path.join(fx, "raw", table), os.path.join(fx, "raw", src), "-d", str(theirs),
+                        "--to", "blow5", "-c", "none", "-s", "none"] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert q.returncode == 0, q.stderr.decode()
+    assert same_dir(str(ours), str(theirs))
+
+
 def view_none(src, dst):
     r = subprocess.run([CLI, "view", src, "-o", dst, "-c", "none", "-s", "svb-zd"], stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()
