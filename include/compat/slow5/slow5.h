@@ -14,6 +14,9 @@
 #define SLOW5_ERR_RECPARSE S5B_ERR_RECPARSE
 #define SLOW5_ERR_MEM      S5B_ERR_MEM
 #define SLOW5_ERR_PRESS    S5B_ERR_PRESS
+#define SLOW5_ERR_NOAUX    S5B_ERR_NOAUX
+#define SLOW5_ERR_NOFLD    S5B_ERR_NOFLD
+#define SLOW5_ERR_TYPE     S5B_ERR_TYPE
 /* enum slow5_press_method, slow5_press.h:61-67 */
 #define SLOW5_COMPRESS_NONE   S5B_COMPRESS_NONE
 #define SLOW5_COMPRESS_ZLIB   S5B_COMPRESS_ZLIB

@@ -17,8 +17,8 @@
  *                                             (slow5_mt.c:124-181), one GPU batch instead of a pthread pool
  *
  * Differences a caller can see: slow5_rec_t's aux_map (a khash) is replaced by the record's binary auxiliary
- * section kept as-is (aux / aux_len); the leading fields have the reference's names, types and order
- * (slow5.h:274-287).  Ownership rules are the reference's: s5b_decode frees *mem and replaces it when the
+ * section kept as-is (aux / aux_len) -- the slow5_aux_get_* accessors work on it as they do on the map --; the leading fields
+ * have the reference's names, types and order (slow5.h:274-287).  Ownership rules are the reference's: s5b_decode frees *mem and replaces it when the
  * record was compressed (slow5.c:2595-2597); s5b_encode output carries the 8-byte size prefix, s5b_get_next_mem
  * output does not; everything returned is malloc()'d.
  */
@@ -35,7 +35,10 @@ extern "C" {
 
 #define S5B_ERR_EOF       (-1)   /* == SLOW5_ERR_EOF */
 #define S5B_ERR_IO        (-5)   /* == SLOW5_ERR_IO */
-#define S5B_ERR_RECPARSE  (-7)   /* == SLOW5_ERR_RECPARSE */
+#define S5B_ERR_RECPARSE  (-4)   /* == SLOW5_ERR_RECPARSE (slow5_defs.h:140) */
+#define S5B_ERR_NOAUX     (-11)  /* == SLOW5_ERR_NOAUX: the record has no auxiliary fields */
+#define S5B_ERR_NOFLD     (-12)  /* == SLOW5_ERR_NOFLD: no auxiliary field of that name */
+#define S5B_ERR_TYPE      (-17)  /* == SLOW5_ERR_TYPE: the field has another type */
 
 typedef struct s5b_rec {
     uint16_t read_id_len;
@@ -49,6 +52,7 @@ typedef struct s5b_rec {
     int16_t *raw_signal;
     uint8_t *aux;      /* binary auxiliary section of the record, header order (slow5.c:3993-4044) */
     uint64_t aux_len;
+    void *aux_meta;    /* private: where the fields of `aux` lie (set by s5b_decode*; NULL in records a caller builds) */
 } s5b_rec_t;
 
 /* The leading fields of the file handle are public and laid out like the reference's slow5_file_t
@@ -93,6 +97,38 @@ int s5b_decode(char **mem, size_t *bytes, s5b_rec_t **read, s5b_file_t *fp);
 int s5b_encode(char **mem, size_t *bytes, s5b_rec_t *read, s5b_file_t *fp);
 int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *fp);
 void s5b_rec_free(s5b_rec_t *read);
+
+/* Auxiliary fields of a decoded record and header attributes -- the accessors that stand in for slow5_rec_t's aux_map
+ * (slow5lib/include/slow5/slow5.h:396, :469-508; slow5.c:1383-1400, :3493-3660).  Same names, arguments and results: a primitive
+ * comes back by value (the type's NULL value -- INT8_MAX ... UINT64_MAX, NaN, 0 -- on error), an array as a pointer into the
+ * record with *len elements (strings NUL-terminated; NULL with *len = 0 for a value marked missing, which is not an error);
+ * *err (optional) and the thread's errno receive 0 or S5B_ERR_ARG / _NOAUX / _NOFLD / _TYPE.  The pointers live as long as the
+ * record does; s5b_hdr_get's as long as the file. */
+int8_t s5b_aux_get_int8(const s5b_rec_t *read, const char *field, int *err);
+int16_t s5b_aux_get_int16(const s5b_rec_t *read, const char *field, int *err);
+int32_t s5b_aux_get_int32(const s5b_rec_t *read, const char *field, int *err);
+int64_t s5b_aux_get_int64(const s5b_rec_t *read, const char *field, int *err);
+uint8_t s5b_aux_get_uint8(const s5b_rec_t *read, const char *field, int *err);
+uint16_t s5b_aux_get_uint16(const s5b_rec_t *read, const char *field, int *err);
+uint32_t s5b_aux_get_uint32(const s5b_rec_t *read, const char *field, int *err);
+uint64_t s5b_aux_get_uint64(const s5b_rec_t *read, const char *field, int *err);
+float s5b_aux_get_float(const s5b_rec_t *read, const char *field, int *err);
+double s5b_aux_get_double(const s5b_rec_t *read, const char *field, int *err);
+char s5b_aux_get_char(const s5b_rec_t *read, const char *field, int *err);
+uint8_t s5b_aux_get_enum(const s5b_rec_t *read, const char *field, int *err);
+int8_t *s5b_aux_get_int8_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+int16_t *s5b_aux_get_int16_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+int32_t *s5b_aux_get_int32_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+int64_t *s5b_aux_get_int64_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+uint8_t *s5b_aux_get_uint8_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+uint16_t *s5b_aux_get_uint16_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+uint32_t *s5b_aux_get_uint32_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+uint64_t *s5b_aux_get_uint64_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+float *s5b_aux_get_float_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+double *s5b_aux_get_double_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+char *s5b_aux_get_string(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+uint8_t *s5b_aux_get_enum_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
+char *s5b_hdr_get(const char *attr, uint32_t read_group, const s5b_hdr_t *header);
 
 /* n records at once: mems[i]/bytes[i] as returned by s5b_get_next_mem; reads[i] allocated when NULL */
 int s5b_decode_batch(s5b_file_t *fp, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads);
@@ -169,6 +205,32 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_rec_free s5b_rec_free
 #define slow5_set_press s5b_set_press
 #define slow5_hdr_write s5b_hdr_write
+#define slow5_aux_get_int8 s5b_aux_get_int8
+#define slow5_aux_get_int16 s5b_aux_get_int16
+#define slow5_aux_get_int32 s5b_aux_get_int32
+#define slow5_aux_get_int64 s5b_aux_get_int64
+#define slow5_aux_get_uint8 s5b_aux_get_uint8
+#define slow5_aux_get_uint16 s5b_aux_get_uint16
+#define slow5_aux_get_uint32 s5b_aux_get_uint32
+#define slow5_aux_get_uint64 s5b_aux_get_uint64
+#define slow5_aux_get_float s5b_aux_get_float
+#define slow5_aux_get_double s5b_aux_get_double
+#define slow5_aux_get_char s5b_aux_get_char
+#define slow5_aux_get_enum s5b_aux_get_enum
+#define slow5_aux_get_int8_array s5b_aux_get_int8_array
+#define slow5_aux_get_int16_array s5b_aux_get_int16_array
+#define slow5_aux_get_int32_array s5b_aux_get_int32_array
+#define slow5_aux_get_int64_array s5b_aux_get_int64_array
+#define slow5_aux_get_uint8_array s5b_aux_get_uint8_array
+#define slow5_aux_get_uint16_array s5b_aux_get_uint16_array
+#define slow5_aux_get_uint32_array s5b_aux_get_uint32_array
+#define slow5_aux_get_uint64_array s5b_aux_get_uint64_array
+#define slow5_aux_get_float_array s5b_aux_get_float_array
+#define slow5_aux_get_double_array s5b_aux_get_double_array
+#define slow5_aux_get_string s5b_aux_get_string
+#define slow5_aux_get_enum_array s5b_aux_get_enum_array
+#define slow5_hdr_get s5b_hdr_get
+#define slow5_hdr_t s5b_hdr_t
 #define slow5_errno (s5b_errno_value())
 #endif
 

@@ -68,7 +68,7 @@ static uint8_t *zlib_unpack(const uint8_t *in, size_t n, size_t *out_n) {
 }
 
 /* One stored record (size prefix excluded) in, one output record INCLUDING its u64 size prefix out (malloc'd).
- * Returns 0, -13 (SLOW5_ERR_PRESS), -7 (SLOW5_ERR_RECPARSE), -10 (SLOW5_ERR_MEM) or -2 (unsupported method). */
+ * Returns 0, -13 (SLOW5_ERR_PRESS), -4 (SLOW5_ERR_RECPARSE, slow5_defs.h:140), -10 (SLOW5_ERR_MEM) or -2 (unsupported method). */
 int orc_blow5_recode_record(int in_rec, int in_sig, int out_rec, int out_sig, const uint8_t *in, size_t in_len,
                             uint8_t **out, size_t *out_len) {
     *out = NULL;
@@ -86,14 +86,14 @@ int orc_blow5_recode_record(int in_rec, int in_sig, int out_rec, int out_sig, co
     uint8_t *sig_new = NULL, *packed = NULL, *final = NULL;
     int16_t *samples = NULL;
     /* ---- field walk, slow5.c:2811-2927 */
-    if (len < 2) { rc = -7; goto done; }
+    if (len < 2) { rc = -4; goto done; }
     uint16_t idlen; memcpy(&idlen, rec, 2);
     size_t head = 2 + (size_t) idlen + 4 + 32;
-    if (head + 8 > len) { rc = -7; goto done; }
+    if (head + 8 > len) { rc = -4; goto done; }
     uint64_t lrs = rd_u64(rec + head);
     size_t sig_at = head + 8;
     uint64_t sig_bytes = in_sig == M_NONE ? lrs * 2 : lrs;
-    if (sig_bytes > len - sig_at) { rc = -7; goto done; }
+    if (sig_bytes > len - sig_at) { rc = -4; goto done; }
     const uint8_t *aux = rec + sig_at + sig_bytes;
     size_t aux_len = len - sig_at - (size_t) sig_bytes;
     /* ---- signal: decode (slow5.c:2913-2925) */

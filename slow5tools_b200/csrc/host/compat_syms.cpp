@@ -46,4 +46,32 @@ void *slow5_ptr_compress_solo(int method, const void *p, size_t count, size_t *n
 void *slow5_ptr_depress_solo(int method, const void *p, size_t count, size_t *n) { return s5b_ptr_depress_solo(method, p, count, n); }
 void slow5_compress_footer_next(struct __s5b_press *c) { s5b_compress_footer_next(c); }
 
+
+// auxiliary field accessors and header attributes (slow5.h:396, :469-508)
+int8_t slow5_aux_get_int8(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_int8(r, f, err); }
+int16_t slow5_aux_get_int16(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_int16(r, f, err); }
+int32_t slow5_aux_get_int32(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_int32(r, f, err); }
+int64_t slow5_aux_get_int64(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_int64(r, f, err); }
+uint8_t slow5_aux_get_uint8(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_uint8(r, f, err); }
+uint16_t slow5_aux_get_uint16(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_uint16(r, f, err); }
+uint32_t slow5_aux_get_uint32(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_uint32(r, f, err); }
+uint64_t slow5_aux_get_uint64(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_uint64(r, f, err); }
+float slow5_aux_get_float(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_float(r, f, err); }
+double slow5_aux_get_double(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_double(r, f, err); }
+char slow5_aux_get_char(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_char(r, f, err); }
+uint8_t slow5_aux_get_enum(const s5b_rec_t *r, const char *f, int *err) { return s5b_aux_get_enum(r, f, err); }
+int8_t *slow5_aux_get_int8_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_int8_array(r, f, len, err); }
+int16_t *slow5_aux_get_int16_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_int16_array(r, f, len, err); }
+int32_t *slow5_aux_get_int32_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_int32_array(r, f, len, err); }
+int64_t *slow5_aux_get_int64_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_int64_array(r, f, len, err); }
+uint8_t *slow5_aux_get_uint8_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_uint8_array(r, f, len, err); }
+uint16_t *slow5_aux_get_uint16_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_uint16_array(r, f, len, err); }
+uint32_t *slow5_aux_get_uint32_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_uint32_array(r, f, len, err); }
+uint64_t *slow5_aux_get_uint64_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_uint64_array(r, f, len, err); }
+float *slow5_aux_get_float_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_float_array(r, f, len, err); }
+double *slow5_aux_get_double_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_double_array(r, f, len, err); }
+char *slow5_aux_get_string(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_string(r, f, len, err); }
+uint8_t *slow5_aux_get_enum_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_enum_array(r, f, len, err); }
+char *slow5_hdr_get(const char *attr, uint32_t rg, const s5b_hdr_t *h) { return s5b_hdr_get(attr, rg, h); }
+
 }  // extern "C"

@@ -1,6 +1,8 @@
 // s5b_file_api.cpp -- the slow5lib low-level API slice (include/slow5b200_file.h) over blow5_io + the GPU
 // batch codec.  Every codec call goes through the C-ABI of include/slow5b200.h; nothing is computed here.
 #include <unistd.h>
+#include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -12,10 +14,36 @@
 
 using namespace s5b;
 
+// The auxiliary columns of a file (name, type, element size in header order), shared by the file and the records decoded from
+// it: a record may outlive its file (slow5lib's records carry their own field map), so the table is reference counted.
+struct AuxTable {
+    std::atomic<long> refs{1};
+    std::vector<AuxField> fields;
+};
+static void aux_table_unref(AuxTable *t) {
+    if (t && --t->refs == 0) delete t;
+}
+// What s5b_rec_t::aux_meta points at: where every field of this record's auxiliary section lies.  Arrays are kept as aligned
+// copies (strings NUL-terminated, slow5.c:3112-3121) because slow5_aux_get_*_array hands out typed pointers.
+struct AuxView {
+    AuxTable *table = nullptr;
+    std::vector<uint64_t> len;   // elements of field f (1 for a primitive)
+    std::vector<uint64_t> at;    // primitives: offset of the value inside s5b_rec_t::aux
+    std::vector<void *> arr;     // arrays: the copy, nullptr when len == 0
+};
+struct S5bFile;
+// the public header struct first, the way back to the file behind it (s5b_hdr_get)
+struct HdrPriv {
+    s5b_hdr pub;
+    S5bFile *owner;
+};
+
 // the public struct s5b_file (slow5b200_file.h) is the first member: a s5b_file_t* points at it and at this object
 struct S5bFile {
     s5b_file pub;
-    s5b_hdr hdr_pub;
+    HdrPriv hdr_priv;
+    s5b_hdr &hdr_pub = hdr_priv.pub;
+    AuxTable *aux_table = nullptr;   // "r" files with auxiliary columns
     std::string path, mode;
     Reader rd;          // "r"
     FILE *out = nullptr;  // "w"
@@ -44,7 +72,8 @@ static void publish(S5bFile *f) {
     f->hdr_pub.version.minor = h.version[1];
     f->hdr_pub.version.patch = h.version[2];
     f->hdr_pub.num_read_groups = h.num_read_groups;
-    f->pub.header = &f->hdr_pub;
+    f->hdr_priv.owner = f;
+    f->pub.header = &f->hdr_priv.pub;
     f->pub.index = nullptr;
     f->pub.meta.pathname = f->path.c_str();
     f->pub.meta.mode = f->mode.c_str();
@@ -94,6 +123,10 @@ s5b_file_t *s5b_open(const char *pathname, const char *mode) {
         }
         f->rec_press = f->rd.hdr.record_method;
         f->sig_press = f->rd.hdr.signal_method;
+        if (!f->rd.hdr.aux.empty()) {
+            f->aux_table = new AuxTable();
+            f->aux_table->fields = f->rd.hdr.aux;
+        }
         publish(f);
         f->pub.meta.start_rec_offset = f->rd.fp ? (uint64_t)ftello(f->rd.fp) : 0;
         return &f->pub;
@@ -123,6 +156,7 @@ int s5b_close(s5b_file_t *fpub) {
     }
     if (f->gpu) s5b_ctx_destroy(f->gpu);
     if (f->pub.compress) s5b_press_free(f->pub.compress);
+    aux_table_unref(f->aux_table);
     delete f;
     return rc ? fail(rc) : 0;
 }
@@ -185,8 +219,68 @@ int s5b_get_next_bytes(char **mem, size_t *bytes, s5b_file_t *f) {
     return *mem ? 0 : tl_errno;
 }
 
+static void aux_view_free(s5b_rec_t *r) {
+    AuxView *v = static_cast<AuxView *>(r->aux_meta);
+    if (!v) return;
+    for (void *p : v->arr) free(p);
+    aux_table_unref(v->table);
+    delete v;
+    r->aux_meta = nullptr;
+}
+// walks the record's auxiliary section against the file's columns (slow5_rec_aux_parse, slow5.c:3088-3166); a section that does
+// not fit them leaves the record without a view (the accessors then report S5B_ERR_NOAUX)
+static void aux_view_build(s5b_rec_t *r, AuxTable *t) {
+    if (!t) return;
+    AuxView *v = new AuxView();
+    const size_t nf = t->fields.size();
+    v->len.assign(nf, 1);
+    v->at.assign(nf, 0);
+    v->arr.assign(nf, nullptr);
+    uint64_t at = 0;
+    bool ok = true;
+    for (size_t i = 0; i < nf && ok; ++i) {
+        const AuxField &fd = t->fields[i];
+        uint64_t cnt = 1;
+        if (fd.is_array()) {
+            if (at + 8 > r->aux_len) {
+                ok = false;
+                break;
+            }
+            memcpy(&cnt, r->aux + at, 8);
+            at += 8;
+        }
+        if (cnt > r->aux_len || at + cnt * fd.size > r->aux_len) {
+            ok = false;
+            break;
+        }
+        v->len[i] = cnt;
+        v->at[i] = at;
+        if (fd.is_array() && cnt) {
+            const uint64_t bytes = cnt * fd.size;
+            uint8_t *copy = static_cast<uint8_t *>(malloc(bytes + 1));
+            if (!copy) {
+                ok = false;
+                break;
+            }
+            memcpy(copy, r->aux + at, bytes);
+            copy[bytes] = 0;
+            v->arr[i] = copy;
+        }
+        at += cnt * fd.size;
+    }
+    if (!ok || at != r->aux_len) {
+        for (void *p : v->arr) free(p);
+        delete v;
+        return;
+    }
+    ++t->refs;
+    v->table = t;
+    r->aux_meta = v;
+}
+
 void s5b_rec_free(s5b_rec_t *r) {
     if (!r) return;
+    aux_view_free(r);
     free(r->read_id);
     free(r->raw_signal);
     free(r->aux);
@@ -194,12 +288,13 @@ void s5b_rec_free(s5b_rec_t *r) {
 }
 
 // fills (or allocates) a caller-visible record from a parsed one; `sig` is handed over
-static void fill_rec(s5b_rec_t **slot, const Record &rec, void *sig, size_t sig_bytes) {
+static void fill_rec(s5b_rec_t **slot, const Record &rec, void *sig, size_t sig_bytes, AuxTable *table) {
     s5b_rec_t *r = *slot;
     if (!r) {
         r = static_cast<s5b_rec_t *>(calloc(1, sizeof *r));
         *slot = r;
     } else {  // reuse the struct, rebuild its members (slow5.c:2626-2639)
+        aux_view_free(r);
         free(r->read_id);
         free(r->raw_signal);
         free(r->aux);
@@ -216,6 +311,7 @@ static void fill_rec(s5b_rec_t **slot, const Record &rec, void *sig, size_t sig_
     r->aux_len = rec.aux_nbytes;
     r->aux = static_cast<uint8_t *>(malloc(r->aux_len ? r->aux_len : 1));
     if (r->aux_len) memcpy(r->aux, rec.aux_bytes, r->aux_len);
+    aux_view_build(r, table);
 }
 
 int s5b_decode_batch(s5b_file_t *fpub, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads) {
@@ -233,7 +329,7 @@ int s5b_decode_batch(s5b_file_t *fpub, char **mems, size_t *bytes, size_t n, s5b
             void *sig = malloc(nb ? nb : 1);
             if (!sig) return fail(S5B_ERR_MEM);
             memcpy(sig, rec.raw_signal.data(), nb);
-            fill_rec(&reads[i], rec, sig, nb);
+            fill_rec(&reads[i], rec, sig, nb, f->aux_table);
         }
         return 0;
     }
@@ -290,7 +386,7 @@ int s5b_decode_batch(s5b_file_t *fpub, char **mems, size_t *bytes, size_t n, s5b
     } else {
         return fail(S5B_ERR_ARG);
     }
-    for (size_t i = 0; i < n; ++i) fill_rec(&reads[i], rec[i], sig[i], sig_n[i]);
+    for (size_t i = 0; i < n; ++i) fill_rec(&reads[i], rec[i], sig[i], sig_n[i], f->aux_table);
     return 0;
 }
 
@@ -536,6 +632,88 @@ int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5_mt.
     for (int i = 0; i < num_reads; ++i)
         if (s5b_write_bytes(b->mem_records[i], b->mem_bytes[i], mt->sf) < 0) return s5b_errno_value();
     return num_reads;
+}
+
+
+}  // extern "C"
+
+// ---- auxiliary field accessors and header attributes (slow5.h:396, :469-508; slow5.c:1383-1400, :3493-3660) -------------
+namespace {
+// the field's position in the record's view, or a negative S5B_ERR_* (slow5.c:3496-3522)
+int aux_find(const s5b_rec_t *read, const char *field, int want_type, const AuxView **view) {
+    if (!read || !field) return S5B_ERR_ARG;
+    const AuxView *v = static_cast<const AuxView *>(read->aux_meta);
+    if (!v) return S5B_ERR_NOAUX;
+    const std::vector<AuxField> &fs = v->table->fields;
+    for (size_t i = 0; i < fs.size(); ++i)
+        if (fs[i].name == field) {
+            if (fs[i].type != want_type) return S5B_ERR_TYPE;
+            *view = v;
+            return (int)i;
+        }
+    return S5B_ERR_NOFLD;
+}
+template <typename T>
+T aux_prim(const s5b_rec_t *read, const char *field, int *err, int type, T null_value) {
+    const AuxView *v = nullptr;
+    const int i = aux_find(read, field, type, &v);
+    T val = null_value;
+    if (i >= 0) memcpy(&val, read->aux + v->at[i], sizeof(T));
+    else fail(i);
+    if (err) *err = i >= 0 ? 0 : i;
+    return val;
+}
+template <typename T>
+T *aux_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err, int type) {
+    const AuxView *v = nullptr;
+    const int i = aux_find(read, field, type, &v);
+    T *val = nullptr;
+    if (i >= 0) {
+        val = static_cast<T *>(v->arr[i]);   // NULL with *len = 0 for a value marked missing: not an error
+        if (len) *len = v->len[i];
+    } else {
+        fail(i);
+    }
+    if (err) *err = i >= 0 ? 0 : i;
+    return val;
+}
+}  // namespace
+
+extern "C" {
+
+int8_t s5b_aux_get_int8(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<int8_t>(r, f, err, AUX_INT8, INT8_MAX); }
+int16_t s5b_aux_get_int16(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<int16_t>(r, f, err, AUX_INT16, INT16_MAX); }
+int32_t s5b_aux_get_int32(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<int32_t>(r, f, err, AUX_INT32, INT32_MAX); }
+int64_t s5b_aux_get_int64(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<int64_t>(r, f, err, AUX_INT64, INT64_MAX); }
+uint8_t s5b_aux_get_uint8(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<uint8_t>(r, f, err, AUX_UINT8, UINT8_MAX); }
+uint16_t s5b_aux_get_uint16(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<uint16_t>(r, f, err, AUX_UINT16, UINT16_MAX); }
+uint32_t s5b_aux_get_uint32(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<uint32_t>(r, f, err, AUX_UINT32, UINT32_MAX); }
+uint64_t s5b_aux_get_uint64(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<uint64_t>(r, f, err, AUX_UINT64, UINT64_MAX); }
+float s5b_aux_get_float(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<float>(r, f, err, AUX_FLOAT, nanf("")); }
+double s5b_aux_get_double(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<double>(r, f, err, AUX_DOUBLE, nan("")); }
+char s5b_aux_get_char(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<char>(r, f, err, AUX_CHAR, 0); }
+uint8_t s5b_aux_get_enum(const s5b_rec_t *r, const char *f, int *err) { return aux_prim<uint8_t>(r, f, err, AUX_ENUM, UINT8_MAX); }
+
+int8_t *s5b_aux_get_int8_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<int8_t>(r, f, len, err, AUX_INT8_ARRAY); }
+int16_t *s5b_aux_get_int16_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<int16_t>(r, f, len, err, AUX_INT16_ARRAY); }
+int32_t *s5b_aux_get_int32_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<int32_t>(r, f, len, err, AUX_INT32_ARRAY); }
+int64_t *s5b_aux_get_int64_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<int64_t>(r, f, len, err, AUX_INT64_ARRAY); }
+uint8_t *s5b_aux_get_uint8_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<uint8_t>(r, f, len, err, AUX_UINT8_ARRAY); }
+uint16_t *s5b_aux_get_uint16_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<uint16_t>(r, f, len, err, AUX_UINT16_ARRAY); }
+uint32_t *s5b_aux_get_uint32_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<uint32_t>(r, f, len, err, AUX_UINT32_ARRAY); }
+uint64_t *s5b_aux_get_uint64_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<uint64_t>(r, f, len, err, AUX_UINT64_ARRAY); }
+float *s5b_aux_get_float_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<float>(r, f, len, err, AUX_FLOAT_ARRAY); }
+double *s5b_aux_get_double_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<double>(r, f, len, err, AUX_DOUBLE_ARRAY); }
+char *s5b_aux_get_string(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<char>(r, f, len, err, AUX_STRING); }
+uint8_t *s5b_aux_get_enum_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<uint8_t>(r, f, len, err, AUX_ENUM_ARRAY); }
+
+char *s5b_hdr_get(const char *attr, uint32_t read_group, const s5b_hdr_t *header) {
+    if (!attr || !header || read_group >= header->num_read_groups) return nullptr;
+    const S5bFile *f = reinterpret_cast<const HdrPriv *>(header)->owner;
+    const Header &h = f->writing ? f->hdr : f->rd.hdr;
+    for (const auto &kv : h.attrs)
+        if (kv.first == attr) return read_group < kv.second.size() ? const_cast<char *>(kv.second[read_group].c_str()) : nullptr;
+    return nullptr;
 }
 
 }  // extern "C"

@@ -221,3 +221,79 @@ def test_get_batch_by_read_id_uncompressed(tmp_path):
 @pytest.mark.gpu
 def test_get_batch_by_read_id_compressed(tmp_path):
     _run_get_batch(tmp_path, os.path.join(ROOT, "tests", "golden", "fixtures", "zlib_svb-zd_multi_rg_v0.2.0.blow5"))
+
+
+# ---- auxiliary field accessors, header attributes, error codes: ours next to the compiled reference (CPU: uncompressed file) ----
+AUX_PROG = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <inttypes.h>
+#include <slow5/slow5.h>
+int main(int argc, char **argv) {
+    slow5_file_t *sp = slow5_open(argv[1], "r");
+    if (!sp) return 2;
+    printf("hdr run_id=%s asic_id=%s nosuch=%s rg9=%s\n", slow5_hdr_get("run_id", 0, sp->header), slow5_hdr_get("asic_id", 0, sp->header),
+           slow5_hdr_get("no_such_attribute", 0, sp->header) ? "set" : "NULL", slow5_hdr_get("run_id", 9, sp->header) ? "set" : "NULL");
+    char *mem = NULL; size_t bytes = 0; slow5_rec_t *rec = NULL; int n = 0;
+    while (slow5_get_next_bytes(&mem, &bytes, sp) == 0) {
+        if (slow5_decode(&mem, &bytes, &rec, sp) != 0) return 3;
+        free(mem);
+        int e1, e2, e3, e4, e5, e6, e7, e8; uint64_t len = 77, l2 = 77;
+        char *ch = slow5_aux_get_string(rec, "channel_number", &len, &e1);
+        double mb = slow5_aux_get_double(rec, "median_before", &e2);
+        int32_t rn = slow5_aux_get_int32(rec, "read_number", &e3);
+        uint8_t mux = slow5_aux_get_uint8(rec, "start_mux", &e4);
+        uint64_t st = slow5_aux_get_uint64(rec, "start_time", &e5);
+        int64_t wrong = slow5_aux_get_int64(rec, "read_number", &e6);      /* int32 field asked for as int64 */
+        uint16_t none = slow5_aux_get_uint16(rec, "no_such_field", &e7);
+        int8_t *arr = slow5_aux_get_int8_array(rec, "channel_number", &l2, &e8);   /* string asked for as int8 array */
+        printf("%s ch=%s/%" PRIu64 "/%d mb=%.6f/%d rn=%" PRId32 "/%d mux=%u/%d st=%" PRIu64 "/%d wrong=%" PRId64 "/%d none=%u/%d arr=%s/%" PRIu64 "/%d\n",
+               rec->read_id, ch, len, e1, mb, e2, rn, e3, (unsigned)mux, e4, st, e5, wrong, e6, (unsigned)none, e7, arr ? "set" : "NULL", l2, e8);
+        ++n;
+    }
+    slow5_rec_free(rec);
+    slow5_close(sp);
+    printf("records %d\n", n);
+    return 0;
+}
+"""
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+def test_aux_accessors_and_header_attributes_match_the_reference(tmp_path):
+    """slow5_aux_get_* / slow5_hdr_get (slow5.h:396, :469-508) on the reference's own fixture with five auxiliary columns: one
+    program, compiled against the reference's headers + library and against include/compat + libslow5b200.so, prints the same --
+    values, lengths, and the error codes for a wrong type, a missing field and a missing attribute"""
+    fixture = os.path.join(ROOT, "tests", "golden", "fixtures", "exp_1_lossless.blow5")   # none / none: no codec, no device
+    src = tmp_path / "aux.c"
+    src.write_text(AUX_PROG)
+    inc = os.path.join(REFTREE, "slow5lib", "include")
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "theirs")
+    _cc(["-O1", "-I", os.path.join(ROOT, "include", "compat"), str(src), "-o", ours, "-L", LIBDIR, "-lslow5b200", "-Wl,-rpath," + LIBDIR])
+    refdir = os.path.dirname(REF_SO)
+    _cc(["-O1", "-I", inc, str(src), "-o", theirs, "-L", refdir, "-l:libslow5_ref.so", "-Wl,-rpath," + refdir, "-lm", "-lz"])
+    a = subprocess.run([ours, fixture], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    b = subprocess.run([theirs, fixture], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr.decode(), b.stderr.decode())
+    assert a.stdout == b.stdout
+    out = a.stdout.decode()
+    assert "records 1" in out or "records" in out
+    assert "/-17" in out and "/-12" in out and "nosuch=NULL" in out   # SLOW5_ERR_TYPE, SLOW5_ERR_NOFLD
+
+
+def test_error_codes_carry_the_reference_values():
+    """slow5_defs.h:137-154"""
+    text = open(os.path.join(ROOT, "include", "slow5b200_file.h")).read() + open(os.path.join(ROOT, "include", "slow5b200.h")).read()
+    want = {"S5B_ERR_EOF": -1, "S5B_ERR_ARG": -2, "S5B_ERR_RECPARSE": -4, "S5B_ERR_IO": -5, "S5B_ERR_MEM": -10, "S5B_ERR_NOAUX": -11,
+            "S5B_ERR_NOFLD": -12, "S5B_ERR_PRESS": -13, "S5B_ERR_TYPE": -17}
+    import re
+    for name, value in want.items():
+        m = re.search(r"#define\s+%s\s+\((-?\d+)\)" % name, text)
+        assert m and int(m.group(1)) == value, name
+    defs = os.path.join(REFTREE, "slow5lib", "include", "slow5", "slow5_defs.h")
+    if os.path.exists(defs):
+        ref = open(defs).read()
+        for name, value in want.items():
+            m = re.search(r"#define\s+%s\s+\((-?\d+)\)" % name.replace("S5B_", "SLOW5_"), ref)
+            assert m and int(m.group(1)) == value, name
