@@ -14,6 +14,8 @@
 #define SLOW5_ERR_RECPARSE S5B_ERR_RECPARSE
 #define SLOW5_ERR_MEM      S5B_ERR_MEM
 #define SLOW5_ERR_PRESS    S5B_ERR_PRESS
+#define SLOW5_ERR_NOIDX    S5B_ERR_NOIDX
+#define SLOW5_ERR_NOTFOUND S5B_ERR_NOTFOUND
 #define SLOW5_ERR_NOAUX    S5B_ERR_NOAUX
 #define SLOW5_ERR_NOFLD    S5B_ERR_NOFLD
 #define SLOW5_ERR_TYPE     S5B_ERR_TYPE

@@ -10,6 +10,8 @@
  *   s5b_decode          slow5_decode          slow5.h:658                            (slow5.c:2613)
  *   s5b_encode          slow5_encode          slow5.h:660                            (slow5.c:4083)
  *   s5b_write_bytes     slow5_write_bytes     slow5.h:662                            (slow5.c:3785)
+ *   s5b_get_next / s5b_get / s5b_write        slow5_get_next / slow5_get / slow5_write   slow5.h:440 / :423 / :600 (one record each)
+ *   s5b_aux_get_* / s5b_hdr_get               slow5_aux_get_* / slow5_hdr_get            slow5.h:469-508 / :396
  *   s5b_rec_free        slow5_rec_free        slow5.h:454
  *   s5b_set_press       slow5_set_press       slow5.h:612
  *   s5b_hdr_write       slow5_hdr_write       slow5.h:586
@@ -36,6 +38,8 @@ extern "C" {
 #define S5B_ERR_EOF       (-1)   /* == SLOW5_ERR_EOF */
 #define S5B_ERR_IO        (-5)   /* == SLOW5_ERR_IO */
 #define S5B_ERR_RECPARSE  (-4)   /* == SLOW5_ERR_RECPARSE (slow5_defs.h:140) */
+#define S5B_ERR_NOIDX     (-6)   /* == SLOW5_ERR_NOIDX: s5b_get before s5b_idx_load */
+#define S5B_ERR_NOTFOUND  (-7)   /* == SLOW5_ERR_NOTFOUND: read id not in the index */
 #define S5B_ERR_NOAUX     (-11)  /* == SLOW5_ERR_NOAUX: the record has no auxiliary fields */
 #define S5B_ERR_NOFLD     (-12)  /* == SLOW5_ERR_NOFLD: no auxiliary field of that name */
 #define S5B_ERR_TYPE      (-17)  /* == SLOW5_ERR_TYPE: the field has another type */
@@ -95,8 +99,13 @@ void *s5b_get_next_mem(size_t *n, s5b_file_t *fp);
 int s5b_get_next_bytes(char **mem, size_t *bytes, s5b_file_t *fp);
 int s5b_decode(char **mem, size_t *bytes, s5b_rec_t **read, s5b_file_t *fp);
 int s5b_encode(char **mem, size_t *bytes, s5b_rec_t *read, s5b_file_t *fp);
-int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *fp);
+int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *fp);   /* 0, or negative (slow5.c:3785-3794) */
 void s5b_rec_free(s5b_rec_t *read);
+/* the single-record conveniences (slow5.h:423, :440, :600): slow5_get_next = get_next_bytes + decode, slow5_get = index lookup
+ * (after s5b_idx_load; S5B_ERR_NOIDX / S5B_ERR_NOTFOUND) + pread + decode, slow5_write = encode + write_bytes (bytes written or -1) */
+int s5b_get_next(s5b_rec_t **read, s5b_file_t *fp);
+int s5b_get(const char *read_id, s5b_rec_t **read, s5b_file_t *fp);
+int s5b_write(s5b_rec_t *read, s5b_file_t *fp);
 
 /* Auxiliary fields of a decoded record and header attributes -- the accessors that stand in for slow5_rec_t's aux_map
  * (slow5lib/include/slow5/slow5.h:396, :469-508; slow5.c:1383-1400, :3493-3660).  Same names, arguments and results: a primitive
@@ -202,6 +211,9 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_decode s5b_decode
 #define slow5_encode s5b_encode
 #define slow5_write_bytes s5b_write_bytes
+#define slow5_get_next s5b_get_next
+#define slow5_get s5b_get
+#define slow5_write s5b_write
 #define slow5_rec_free s5b_rec_free
 #define slow5_set_press s5b_set_press
 #define slow5_hdr_write s5b_hdr_write

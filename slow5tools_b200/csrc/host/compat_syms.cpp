@@ -23,6 +23,9 @@ int slow5_decode(char **mem, size_t *bytes, s5b_rec_t **read, s5b_file_t *fp) { 
 int slow5_encode(char **mem, size_t *bytes, s5b_rec_t *read, s5b_file_t *fp) { return s5b_encode(mem, bytes, read, fp); }
 int slow5_write_bytes(char *mem, size_t bytes, s5b_file_t *fp) { return s5b_write_bytes(mem, bytes, fp); }
 void slow5_rec_free(s5b_rec_t *read) { s5b_rec_free(read); }
+int slow5_get_next(s5b_rec_t **read, s5b_file_t *fp) { return s5b_get_next(read, fp); }
+int slow5_get(const char *read_id, s5b_rec_t **read, s5b_file_t *fp) { return s5b_get(read_id, read, fp); }
+int slow5_write(s5b_rec_t *read, s5b_file_t *fp) { return s5b_write(read, fp); }
 int slow5_set_press(s5b_file_t *fp, int rec_press, int sig_press) { return s5b_set_press(fp, rec_press, sig_press); }
 int slow5_hdr_write(s5b_file_t *fp) { return s5b_hdr_write(fp); }
 

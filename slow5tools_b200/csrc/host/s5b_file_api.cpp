@@ -481,7 +481,30 @@ int s5b_write_bytes(char *mem, size_t bytes, s5b_file_t *fpub) {
     S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !f->writing || !mem) return fail(S5B_ERR_ARG);
     if (fwrite(mem, 1, bytes, f->out) != bytes) return fail(S5B_ERR_IO);
-    return (int)bytes;
+    return 0;  // slow5.c:3785-3794
+}
+
+// The single-record conveniences of slow5.h over the calls above (a batch of one each: correct, latency-bound; callers that care
+// about throughput use the batch forms).
+int s5b_get_next(s5b_rec_t **read, s5b_file_t *f) {  // slow5_get_next, slow5.c:3339-3361
+    if (!read || !f) return fail(S5B_ERR_ARG);
+    char *mem = nullptr;
+    size_t bytes = 0;
+    const int rc = s5b_get_next_bytes(&mem, &bytes, f);
+    if (rc < 0) return rc;
+    const int rd = s5b_decode(&mem, &bytes, read, f);
+    free(mem);
+    return rd;
+}
+
+int s5b_write(s5b_rec_t *read, s5b_file_t *f) {  // slow5_write -> slow5_rec_fwrite, slow5.c:3765-3799: bytes written or -1
+    if (!read || !f) return -1;
+    char *mem = nullptr;
+    size_t bytes = 0;
+    if (s5b_encode(&mem, &bytes, read, f) != 0) return -1;
+    const int rc = s5b_write_bytes(mem, bytes, f);
+    free(mem);
+    return rc < 0 ? -1 : (int)bytes;
 }
 
 }  // extern "C"
@@ -624,6 +647,30 @@ int s5b_get_batch(s5b_mt_t *mt, s5b_batch_t *b, char **rid, int num_rid) {
     if (num_rid == 0) return 0;
     const int rc = s5b_decode_batch(mt->sf, b->mem_records, b->mem_bytes, (size_t)num_rid, b->slow5_rec);
     return rc < 0 ? rc : num_rid;
+}
+
+int s5b_get(const char *read_id, s5b_rec_t **read, s5b_file_t *fpub) {  // slow5_get, slow5.c:2517-2578
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
+    if (!read_id || !read || !f || f->writing) return fail(S5B_ERR_ARG);
+    if (!f->index_loaded) return fail(S5B_ERR_NOIDX);
+    const auto it = f->index.find(read_id);
+    if (it == f->index.end() || it->second.size < 8) return fail(S5B_ERR_NOTFOUND);
+    size_t bytes = (size_t)(it->second.size - 8);
+    char *m = static_cast<char *>(malloc(bytes ? bytes : 1));
+    if (!m) return fail(S5B_ERR_MEM);
+    const int fd = fileno(f->rd.fp);
+    size_t done = 0;
+    while (done < bytes) {
+        const ssize_t r = pread(fd, m + done, bytes - done, (off_t)(it->second.offset + 8 + done));
+        if (r <= 0) {
+            free(m);
+            return fail(S5B_ERR_IO);
+        }
+        done += (size_t)r;
+    }
+    const int rc = s5b_decode(&m, &bytes, read, fpub);
+    free(m);
+    return rc;
 }
 
 int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5_mt.c:359-378

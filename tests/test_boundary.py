@@ -53,7 +53,13 @@ def test_compat_library_exports_the_slow5_names():
                  "slow5_get_next_batch", "slow5_encode_batch", "slow5_write_batch", "slow5_free_batch", "slow5_free_mt",
                  "slow5_press_init", "__slow5_press_init", "slow5_press_free", "__slow5_press_free", "slow5_ptr_compress",
                  "slow5_ptr_depress", "slow5_ptr_compress_solo", "slow5_ptr_depress_solo", "slow5_compress_footer_next",
-                 "slow5_errno_location"):
+                 "slow5_errno_location", "slow5_get_next", "slow5_get", "slow5_write", "slow5_get_batch", "slow5_idx_load",
+                 "slow5_hdr_get", "slow5_aux_get_int8", "slow5_aux_get_int16", "slow5_aux_get_int32", "slow5_aux_get_int64",
+                 "slow5_aux_get_uint8", "slow5_aux_get_uint16", "slow5_aux_get_uint32", "slow5_aux_get_uint64", "slow5_aux_get_float",
+                 "slow5_aux_get_double", "slow5_aux_get_char", "slow5_aux_get_enum", "slow5_aux_get_string",
+                 "slow5_aux_get_int8_array", "slow5_aux_get_int16_array", "slow5_aux_get_int32_array", "slow5_aux_get_int64_array",
+                 "slow5_aux_get_uint8_array", "slow5_aux_get_uint16_array", "slow5_aux_get_uint32_array",
+                 "slow5_aux_get_uint64_array", "slow5_aux_get_float_array", "slow5_aux_get_double_array", "slow5_aux_get_enum_array"):
         assert hasattr(L, name), name
     # a round trip through the names (method NONE needs no GPU): open a reference fixture, read the raw records
     fix = os.path.join(ROOT, "tests", "golden", "fixtures", "exp_1_lossless_zlib_svb_v0.2.0.blow5")
@@ -297,3 +303,85 @@ def test_error_codes_carry_the_reference_values():
         for name, value in want.items():
             m = re.search(r"#define\s+%s\s+\((-?\d+)\)" % name.replace("S5B_", "SLOW5_"), ref)
             assert m and int(m.group(1)) == value, name
+
+
+GET_PROG = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <inttypes.h>
+#include <slow5/slow5.h>
+int main(int argc, char **argv) {
+    slow5_file_t *sp = slow5_open(argv[1], "r");
+    if (!sp) return 2;
+    slow5_rec_t *rec = NULL;
+    int rc, n = 0;
+    rc = slow5_get(argv[2], &rec, sp);
+    printf("get before idx_load -> %d\n", rc);
+    while ((rc = slow5_get_next(&rec, sp)) >= 0) {
+        printf("next %s %" PRIu64 " %d\n", rec->read_id, rec->len_raw_signal, (int)rec->raw_signal[rec->len_raw_signal - 1]);
+        ++n;
+    }
+    printf("end %d after %d\n", rc, n);
+    if (slow5_idx_load(sp) < 0) return 3;
+    for (int i = 2; i < argc; ++i) {
+        rc = slow5_get(argv[i], &rec, sp);
+        if (rc == 0) printf("get %s %" PRIu64 " %d\n", rec->read_id, rec->len_raw_signal, (int)rec->raw_signal[0]);
+        else printf("get %s -> %d\n", argv[i], rc);
+    }
+    slow5_rec_free(rec);
+    slow5_close(sp);
+    return 0;
+}
+"""
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+def test_single_record_calls_match_the_reference(tmp_path):
+    """slow5_get_next / slow5_get (slow5.h:423, :440) on an uncompressed BLOW5 made from the reference's example.slow5 (5 reads):
+    the same program against both libraries prints the same, including SLOW5_ERR_NOIDX, SLOW5_ERR_NOTFOUND and SLOW5_ERR_EOF;
+    slow5_write writes the records back byte for byte"""
+    cli = os.path.join(ROOT, "slow5tools_b200", "bin", "slow5tools-b200")
+    text = os.path.join(REFTREE, "slow5lib", "examples", "example.slow5")
+    blow = str(tmp_path / "example.blow5")
+    subprocess.check_call([cli, "view", text, "-o", blow, "-c", "none", "-s", "none"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([cli, "index", blow], stderr=subprocess.DEVNULL)
+    ids = [l.split(b"\t")[0].decode() for l in open(text, "rb").read().split(b"\n") if l and l[:1] not in (b"#", b"@")]
+    assert len(ids) == 5
+    src = tmp_path / "get.c"
+    src.write_text(GET_PROG)
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "theirs")
+    _cc(["-O1", "-I", os.path.join(ROOT, "include", "compat"), str(src), "-o", ours, "-L", LIBDIR, "-lslow5b200", "-Wl,-rpath," + LIBDIR])
+    refdir = os.path.dirname(REF_SO)
+    _cc(["-O1", "-I", os.path.join(REFTREE, "slow5lib", "include"), str(src), "-o", theirs, "-L", refdir, "-l:libslow5_ref.so",
+         "-Wl,-rpath," + refdir, "-lm", "-lz"])
+    args = [blow, ids[3], ids[0], "no-such-read"]
+    a = subprocess.run([ours] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    b = subprocess.run([theirs] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr.decode(), b.stderr.decode())
+    assert a.stdout == b.stdout
+    out = a.stdout.decode()
+    assert "get before idx_load -> -6" in out and "end -1 after 5" in out and "get no-such-read -> -7" in out
+    # slow5_write: every record back into a new none / none file = the input file
+    L = C.CDLL(os.path.join(LIBDIR, "libslow5b200.so"))
+    vp = C.c_void_p
+    L.s5b_open.restype = vp
+    L.s5b_open.argtypes = [C.c_char_p, C.c_char_p]
+    L.s5b_get_next.argtypes = [C.POINTER(vp), vp]
+    L.s5b_write.argtypes = [vp, vp]
+    L.s5b_hdr_copy.argtypes = [vp, vp]
+    L.s5b_set_press.argtypes = [vp, C.c_int, C.c_int]
+    for f in (L.s5b_close, L.s5b_hdr_write, L.s5b_rec_free):
+        f.argtypes = [vp]
+    back = str(tmp_path / "back.blow5")
+    fin, fout = L.s5b_open(blow.encode(), b"r"), L.s5b_open(back.encode(), b"w")
+    assert fin and fout and L.s5b_hdr_copy(fout, fin) == 0 and L.s5b_set_press(fout, 0, 0) == 0 and L.s5b_hdr_write(fout) > 0
+    rec = vp()
+    total = 0
+    while L.s5b_get_next(C.byref(rec), fin) == 0:
+        k = L.s5b_write(rec, fout)
+        assert k > 8
+        total += k
+    L.s5b_rec_free(rec)
+    assert L.s5b_close(fin) == 0 and L.s5b_close(fout) == 0
+    assert open(back, "rb").read() == open(blow, "rb").read() and total > 0
