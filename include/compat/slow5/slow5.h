@@ -19,6 +19,14 @@
 #define SLOW5_ERR_NOAUX    S5B_ERR_NOAUX
 #define SLOW5_ERR_NOFLD    S5B_ERR_NOFLD
 #define SLOW5_ERR_TYPE     S5B_ERR_TYPE
+/* enum slow5_aux_type, slow5.h:106-133 (what slow5_get_aux_types hands out) */
+enum slow5_aux_type {
+    SLOW5_INT8_T = 0, SLOW5_INT16_T, SLOW5_INT32_T, SLOW5_INT64_T, SLOW5_UINT8_T, SLOW5_UINT16_T, SLOW5_UINT32_T, SLOW5_UINT64_T,
+    SLOW5_FLOAT, SLOW5_DOUBLE, SLOW5_CHAR, SLOW5_ENUM,
+    SLOW5_INT8_T_ARRAY, SLOW5_INT16_T_ARRAY, SLOW5_INT32_T_ARRAY, SLOW5_INT64_T_ARRAY, SLOW5_UINT8_T_ARRAY, SLOW5_UINT16_T_ARRAY,
+    SLOW5_UINT32_T_ARRAY, SLOW5_UINT64_T_ARRAY, SLOW5_FLOAT_ARRAY, SLOW5_DOUBLE_ARRAY, SLOW5_STRING, SLOW5_ENUM_ARRAY
+};
+#define SLOW5_IS_PTR(type) ((type) >= SLOW5_INT8_T_ARRAY)
 /* enum slow5_press_method, slow5_press.h:61-67 */
 #define SLOW5_COMPRESS_NONE   S5B_COMPRESS_NONE
 #define SLOW5_COMPRESS_ZLIB   S5B_COMPRESS_ZLIB

@@ -138,6 +138,14 @@ double *s5b_aux_get_double_array(const s5b_rec_t *read, const char *field, uint6
 char *s5b_aux_get_string(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
 uint8_t *s5b_aux_get_enum_array(const s5b_rec_t *read, const char *field, uint64_t *len, int *err);
 char *s5b_hdr_get(const char *attr, uint32_t read_group, const s5b_hdr_t *header);
+/* header / index introspection (slow5.h:633-654): the attribute keys (sorted; a malloc()'d array the caller frees, the strings
+ * stay the library's), the auxiliary column names and types (enum slow5_aux_type values; the library's arrays), the labels of an
+ * enum column, the read ids of a loaded index in index order (S5B_ERR_NOIDX before s5b_idx_load) */
+const char **s5b_get_hdr_keys(const s5b_hdr_t *header, uint64_t *len);
+char **s5b_get_aux_names(const s5b_hdr_t *header, uint64_t *len);
+int *s5b_get_aux_types(const s5b_hdr_t *header, uint64_t *len);
+char **s5b_get_aux_enum_labels(const s5b_hdr_t *header, const char *field, uint8_t *n);
+char **s5b_get_rids(const s5b_file_t *fp, uint64_t *len);
 
 /* n records at once: mems[i]/bytes[i] as returned by s5b_get_next_mem; reads[i] allocated when NULL */
 int s5b_decode_batch(s5b_file_t *fp, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads);
@@ -242,6 +250,11 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_aux_get_string s5b_aux_get_string
 #define slow5_aux_get_enum_array s5b_aux_get_enum_array
 #define slow5_hdr_get s5b_hdr_get
+#define slow5_get_hdr_keys s5b_get_hdr_keys
+#define slow5_get_aux_names s5b_get_aux_names
+#define slow5_get_aux_types(h, n) ((enum slow5_aux_type *)s5b_get_aux_types(h, n))
+#define slow5_get_aux_enum_labels s5b_get_aux_enum_labels
+#define slow5_get_rids s5b_get_rids
 #define slow5_hdr_t s5b_hdr_t
 #define slow5_errno (s5b_errno_value())
 #endif

@@ -76,5 +76,10 @@ double *slow5_aux_get_double_array(const s5b_rec_t *r, const char *f, uint64_t *
 char *slow5_aux_get_string(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_string(r, f, len, err); }
 uint8_t *slow5_aux_get_enum_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return s5b_aux_get_enum_array(r, f, len, err); }
 char *slow5_hdr_get(const char *attr, uint32_t rg, const s5b_hdr_t *h) { return s5b_hdr_get(attr, rg, h); }
+const char **slow5_get_hdr_keys(const s5b_hdr_t *h, uint64_t *len) { return s5b_get_hdr_keys(h, len); }
+char **slow5_get_aux_names(const s5b_hdr_t *h, uint64_t *len) { return s5b_get_aux_names(h, len); }
+int *slow5_get_aux_types(const s5b_hdr_t *h, uint64_t *len) { return s5b_get_aux_types(h, len); }
+char **slow5_get_aux_enum_labels(const s5b_hdr_t *h, const char *field, uint8_t *n) { return s5b_get_aux_enum_labels(h, field, n); }
+char **slow5_get_rids(const s5b_file_t *fp, uint64_t *len) { return s5b_get_rids(fp, len); }
 
 }  // extern "C"

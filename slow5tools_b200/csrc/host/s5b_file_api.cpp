@@ -1,6 +1,7 @@
 // s5b_file_api.cpp -- the slow5lib low-level API slice (include/slow5b200_file.h) over blow5_io + the GPU
 // batch codec.  Every codec call goes through the C-ABI of include/slow5b200.h; nothing is computed here.
 #include <unistd.h>
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -58,6 +59,12 @@ struct S5bFile {
     };
     std::unordered_map<std::string, Where> index;
     bool index_loaded = false;
+    // what the header / index introspection calls hand out (pointers into this object, valid while the file is open)
+    std::vector<std::string> rid_order;                // read ids in index order
+    std::vector<char *> rids_c, aux_names_c;
+    std::vector<int> aux_types_c;
+    std::vector<std::vector<std::string>> enum_labels; // per auxiliary column, empty for non-enum columns
+    std::vector<std::vector<char *>> enum_labels_c;
 };
 static inline S5bFile *impl(s5b_file_t *f) { return reinterpret_cast<S5bFile *>(f); }
 static inline const S5bFile *impl(const s5b_file_t *f) { return reinterpret_cast<const S5bFile *>(f); }
@@ -606,6 +613,7 @@ int s5b_idx_load(s5b_file_t *fpub) {  // slow5_idx_load (slow5.h:560): reads FIL
         memcpy(&w.offset, b.data() + pos + 2 + n, 8);
         memcpy(&w.size, b.data() + pos + 2 + n + 8, 8);
         f->index.emplace(std::string(reinterpret_cast<const char *>(b.data() + pos + 2), n), w);
+        f->rid_order.emplace_back(reinterpret_cast<const char *>(b.data() + pos + 2), n);
         pos += 2 + (size_t)n + 16;
     }
     f->index_loaded = true;
@@ -753,6 +761,114 @@ float *s5b_aux_get_float_array(const s5b_rec_t *r, const char *f, uint64_t *len,
 double *s5b_aux_get_double_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<double>(r, f, len, err, AUX_DOUBLE_ARRAY); }
 char *s5b_aux_get_string(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<char>(r, f, len, err, AUX_STRING); }
 uint8_t *s5b_aux_get_enum_array(const s5b_rec_t *r, const char *f, uint64_t *len, int *err) { return aux_array<uint8_t>(r, f, len, err, AUX_ENUM_ARRAY); }
+
+// ---- header / index introspection (slow5.h:633-654; slow5.c:907-928, :1402-1490, :2549-2569) ----------------------------
+static S5bFile *owner_of(const s5b_hdr_t *header) {
+    return header ? reinterpret_cast<const HdrPriv *>(header)->owner : nullptr;
+}
+
+const char **s5b_get_hdr_keys(const s5b_hdr_t *header, uint64_t *len) {   // malloc()'d array (the caller frees it), keys sorted
+    S5bFile *f = owner_of(header);
+    if (len) *len = 0;
+    if (!f) return nullptr;
+    const Header &h = f->writing ? f->hdr : f->rd.hdr;
+    if (len) *len = h.attrs.size();
+    if (h.attrs.empty()) return nullptr;
+    const char **keys = static_cast<const char **>(malloc(h.attrs.size() * sizeof *keys));
+    if (!keys) {
+        fail(S5B_ERR_MEM);
+        return nullptr;
+    }
+    for (size_t i = 0; i < h.attrs.size(); ++i) keys[i] = h.attrs[i].first.c_str();
+    std::stable_sort(keys, keys + h.attrs.size(), [](const char *a, const char *b) { return strcmp(a, b) < 0; });
+    return keys;
+}
+
+char **s5b_get_aux_names(const s5b_hdr_t *header, uint64_t *len) {   // the library's own array: not to be freed
+    S5bFile *f = owner_of(header);
+    if (len) *len = 0;
+    if (!f) return nullptr;
+    const Header &h = f->writing ? f->hdr : f->rd.hdr;
+    if (len) *len = h.aux.size();
+    if (h.aux.empty()) return nullptr;
+    f->aux_names_c.clear();
+    for (const AuxField &a : h.aux) f->aux_names_c.push_back(const_cast<char *>(a.name.c_str()));
+    return f->aux_names_c.data();
+}
+
+int *s5b_get_aux_types(const s5b_hdr_t *header, uint64_t *len) {   // enum slow5_aux_type values (slow5.h:104-131)
+    S5bFile *f = owner_of(header);
+    if (len) *len = 0;
+    if (!f) return nullptr;
+    const Header &h = f->writing ? f->hdr : f->rd.hdr;
+    if (len) *len = h.aux.size();
+    if (h.aux.empty()) return nullptr;
+    f->aux_types_c.clear();
+    for (const AuxField &a : h.aux) f->aux_types_c.push_back(a.type);
+    return f->aux_types_c.data();
+}
+
+char **s5b_get_aux_enum_labels(const s5b_hdr_t *header, const char *field, uint8_t *n) {
+    S5bFile *f = owner_of(header);
+    if (!f || !field) {
+        fail(S5B_ERR_ARG);
+        return nullptr;
+    }
+    const Header &h = f->writing ? f->hdr : f->rd.hdr;
+    if (h.aux.empty()) {
+        fail(S5B_ERR_NOAUX);
+        return nullptr;
+    }
+    bool any_enum = false;
+    for (const AuxField &a : h.aux) any_enum |= a.type == AUX_ENUM || a.type == AUX_ENUM_ARRAY;
+    if (!any_enum) {
+        fail(S5B_ERR_TYPE);
+        return nullptr;
+    }
+    for (size_t i = 0; i < h.aux.size(); ++i) {
+        if (h.aux[i].name != field) continue;
+        if (h.aux[i].type != AUX_ENUM && h.aux[i].type != AUX_ENUM_ARRAY) {
+            fail(S5B_ERR_TYPE);
+            return nullptr;
+        }
+        if (f->enum_labels.size() != h.aux.size()) {
+            f->enum_labels.assign(h.aux.size(), {});
+            f->enum_labels_c.assign(h.aux.size(), {});
+        }
+        if (f->enum_labels[i].empty()) {  // "enum{a,b,c}" / "enum*{a,b,c}" as written in the header (slow5.c:1159-1258)
+            const std::string &t = h.aux[i].type_str;
+            const size_t open = t.find('{'), close = t.rfind('}');
+            if (open != std::string::npos && close != std::string::npos && close > open) {
+                size_t at = open + 1;
+                while (at <= close) {
+                    const size_t end = std::min(t.find(',', at), close);
+                    f->enum_labels[i].push_back(t.substr(at, end - at));
+                    at = end + 1;
+                }
+            }
+            for (std::string &l : f->enum_labels[i]) f->enum_labels_c[i].push_back(const_cast<char *>(l.c_str()));
+        }
+        if (n) *n = (uint8_t)f->enum_labels_c[i].size();
+        return f->enum_labels_c[i].data();
+    }
+    fail(S5B_ERR_NOFLD);
+    return nullptr;
+}
+
+char **s5b_get_rids(const s5b_file_t *fpub, uint64_t *len) {   // read ids in index order; the library's own array
+    S5bFile *f = fpub ? const_cast<S5bFile *>(impl(fpub)) : nullptr;
+    if (len) *len = 0;
+    if (!f || !f->index_loaded) {
+        fail(f ? S5B_ERR_NOIDX : S5B_ERR_ARG);
+        return nullptr;
+    }
+    if (f->rids_c.size() != f->rid_order.size()) {
+        f->rids_c.clear();
+        for (std::string &r : f->rid_order) f->rids_c.push_back(const_cast<char *>(r.c_str()));
+    }
+    if (len) *len = f->rids_c.size();
+    return f->rids_c.data();
+}
 
 char *s5b_hdr_get(const char *attr, uint32_t read_group, const s5b_hdr_t *header) {
     if (!attr || !header || read_group >= header->num_read_groups) return nullptr;

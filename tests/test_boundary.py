@@ -385,3 +385,72 @@ def test_single_record_calls_match_the_reference(tmp_path):
     L.s5b_rec_free(rec)
     assert L.s5b_close(fin) == 0 and L.s5b_close(fout) == 0
     assert open(back, "rb").read() == open(blow, "rb").read() and total > 0
+
+
+INTRO_PROG = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <inttypes.h>
+#include <slow5/slow5.h>
+int main(int argc, char **argv) {
+    slow5_file_t *sp = slow5_open(argv[1], "r");
+    if (!sp) return 2;
+    uint64_t n = 0;
+    const char **keys = slow5_get_hdr_keys(sp->header, &n);
+    printf("keys %" PRIu64 ":", n);
+    for (uint64_t i = 0; i < n; ++i) printf(" %s", keys[i]);
+    printf("\n");
+    free(keys);
+    char **names = slow5_get_aux_names(sp->header, &n);
+    enum slow5_aux_type *types = slow5_get_aux_types(sp->header, &n);
+    printf("aux %" PRIu64 ":", n);
+    for (uint64_t i = 0; i < n; ++i) printf(" %s=%d%s", names[i], (int)types[i], SLOW5_IS_PTR(types[i]) ? "*" : "");
+    printf("\n");
+    if (argc > 2) {
+        uint8_t k = 0;
+        char **labels = slow5_get_aux_enum_labels(sp->header, argv[2], &k);
+        printf("labels of %s: %u", argv[2], (unsigned)k);
+        for (uint8_t i = 0; labels && i < k; ++i) printf(" %s", labels[i]);
+        printf("\n");
+    }
+    uint64_t nr = 0;
+    char **rids = slow5_get_rids(sp, &nr);
+    printf("rids before idx_load: %s\n", rids ? "set" : "NULL");
+    if (slow5_idx_load(sp) == 0) {
+        rids = slow5_get_rids(sp, &nr);
+        printf("rids %" PRIu64 ":", nr);
+        for (uint64_t i = 0; i < nr; ++i) printf(" %s", rids[i]);
+        printf("\n");
+    }
+    slow5_close(sp);
+    return 0;
+}
+"""
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+def test_header_and_index_introspection_matches_the_reference(tmp_path):
+    """slow5_get_hdr_keys / _get_aux_names / _get_aux_types / _get_aux_enum_labels / _get_rids (slow5.h:633-654) on the
+    reference's example file and on its enum fixture: one program against both libraries prints the same"""
+    cli = os.path.join(ROOT, "slow5tools_b200", "bin", "slow5tools-b200")
+    src = tmp_path / "intro.c"
+    src.write_text(INTRO_PROG)
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "theirs")
+    _cc(["-O1", "-I", os.path.join(ROOT, "include", "compat"), str(src), "-o", ours, "-L", LIBDIR, "-lslow5b200", "-Wl,-rpath," + LIBDIR])
+    refdir = os.path.dirname(REF_SO)
+    _cc(["-O1", "-I", os.path.join(REFTREE, "slow5lib", "include"), str(src), "-o", theirs, "-L", refdir, "-l:libslow5_ref.so",
+         "-Wl,-rpath," + refdir, "-lm", "-lz"])
+    cases = [(os.path.join(REFTREE, "slow5lib", "examples", "example.slow5"), [])]
+    enum_file = os.path.join(REFTREE, "test", "data", "raw", "merge", "aux_enum.slow5")
+    if os.path.exists(enum_file):
+        cases.append((enum_file, ["end_reason"]))
+    for text, extra in cases:
+        blow = str(tmp_path / (os.path.basename(text) + ".blow5"))
+        subprocess.check_call([cli, "view", text, "-o", blow, "-c", "none", "-s", "none"], stderr=subprocess.DEVNULL)
+        subprocess.check_call([cli, "index", blow], stderr=subprocess.DEVNULL)
+        a = subprocess.run([ours, blow] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+        b = subprocess.run([theirs, blow] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+        assert a.returncode == 0 and b.returncode == 0, (a.stderr.decode(), b.stderr.decode())
+        assert a.stdout == b.stdout, (a.stdout.decode(), b.stdout.decode())
+        assert b"rids before idx_load: NULL" in a.stdout and b"rids " in a.stdout
