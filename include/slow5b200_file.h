@@ -181,6 +181,7 @@ int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
  * s5b_get_batch fetches the num_rid records with pread() and decodes them as ONE GPU batch into batch->slow5_rec[];
  * returns num_rid, or S5B_ERR_ARG when an id is not in the index (the reference exits the process). */
 int s5b_idx_load(s5b_file_t *fp);
+void s5b_idx_unload(s5b_file_t *fp);   /* slow5_idx_unload, slow5.h:382 */
 int s5b_get_batch(s5b_mt_t *mt, s5b_batch_t *batch, char **rid, int num_rid);
 void s5b_free_batch(s5b_batch_t *batch);
 void s5b_free_mt(s5b_mt_t *mt);
@@ -208,6 +209,7 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_write_batch s5b_write_batch
 #define slow5_get_batch s5b_get_batch
 #define slow5_idx_load s5b_idx_load
+#define slow5_idx_unload s5b_idx_unload
 #define slow5_free_batch s5b_free_batch
 #define slow5_free_mt s5b_free_mt
 #define slow5_file_t s5b_file_t

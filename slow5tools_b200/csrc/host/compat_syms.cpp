@@ -36,6 +36,7 @@ int slow5_encode_batch(s5b_mt_t *mt, s5b_batch_t *b, int n) { return s5b_encode_
 int slow5_write_batch(s5b_mt_t *mt, s5b_batch_t *b, int n) { return s5b_write_batch(mt, b, n); }
 int slow5_get_batch(s5b_mt_t *mt, s5b_batch_t *b, char **rid, int n) { return s5b_get_batch(mt, b, rid, n); }
 int slow5_idx_load(s5b_file_t *fp) { return s5b_idx_load(fp); }
+void slow5_idx_unload(s5b_file_t *fp) { s5b_idx_unload(fp); }
 void slow5_free_batch(s5b_batch_t *b) { s5b_free_batch(b); }
 void slow5_free_mt(s5b_mt_t *mt) { s5b_free_mt(mt); }
 

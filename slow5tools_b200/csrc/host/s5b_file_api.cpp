@@ -621,6 +621,16 @@ int s5b_idx_load(s5b_file_t *fpub) {  // slow5_idx_load (slow5.h:560): reads FIL
     return 0;
 }
 
+void s5b_idx_unload(s5b_file_t *fpub) {  // slow5_idx_unload, slow5.c:4191-4195
+    S5bFile *f = fpub ? impl(fpub) : nullptr;
+    if (!f) return;
+    f->index.clear();
+    f->rid_order.clear();
+    f->rids_c.clear();
+    f->index_loaded = false;
+    f->pub.index = nullptr;
+}
+
 // slow5_get_batch (slow5_mt.c:319-333): the records of `num_rid` read ids, fetched with pread() and decoded as one GPU batch
 int s5b_get_batch(s5b_mt_t *mt, s5b_batch_t *b, char **rid, int num_rid) {
     if (!mt || !mt->sf || !b || !rid || num_rid < 0 || num_rid > b->capacity_rec) return fail(S5B_ERR_ARG);

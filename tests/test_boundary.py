@@ -421,6 +421,9 @@ int main(int argc, char **argv) {
         printf("rids %" PRIu64 ":", nr);
         for (uint64_t i = 0; i < nr; ++i) printf(" %s", rids[i]);
         printf("\n");
+        slow5_idx_unload(sp);
+        slow5_rec_t *rec = NULL;
+        printf("get after unload -> %d\n", slow5_get("x", &rec, sp));
     }
     slow5_close(sp);
     return 0;
