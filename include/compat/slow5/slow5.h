@@ -27,6 +27,20 @@ enum slow5_aux_type {
     SLOW5_UINT32_T_ARRAY, SLOW5_UINT64_T_ARRAY, SLOW5_FLOAT_ARRAY, SLOW5_DOUBLE_ARRAY, SLOW5_STRING, SLOW5_ENUM_ARRAY
 };
 #define SLOW5_IS_PTR(type) ((type) >= SLOW5_INT8_T_ARRAY)
+/* what a primitive auxiliary field holds when its value is missing (slow5.h:139-150) */
+#include <math.h>
+#define SLOW5_INT8_T_NULL   INT8_MAX
+#define SLOW5_INT16_T_NULL  INT16_MAX
+#define SLOW5_INT32_T_NULL  INT32_MAX
+#define SLOW5_INT64_T_NULL  INT64_MAX
+#define SLOW5_UINT8_T_NULL  UINT8_MAX
+#define SLOW5_UINT16_T_NULL UINT16_MAX
+#define SLOW5_UINT32_T_NULL UINT32_MAX
+#define SLOW5_UINT64_T_NULL UINT64_MAX
+#define SLOW5_FLOAT_NULL    nanf("")
+#define SLOW5_DOUBLE_NULL   nan("")
+#define SLOW5_CHAR_NULL     0
+#define SLOW5_ENUM_NULL     SLOW5_UINT8_T_NULL
 /* enum slow5_press_method, slow5_press.h:61-67 */
 #define SLOW5_COMPRESS_NONE   S5B_COMPRESS_NONE
 #define SLOW5_COMPRESS_ZLIB   S5B_COMPRESS_ZLIB

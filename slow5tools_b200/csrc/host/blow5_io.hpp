@@ -108,6 +108,9 @@ bool aux_relayout(const uint8_t *aux, uint64_t n, const std::vector<AuxField> &i
 
 std::string double_to_str(double x);  // slow5_misc.c:379-406
 
+// FILE.idx for a SLOW5 / BLOW5 file (index_main.cpp; slow5_idx_create, slow5.c:4138-4150); 0 = written, errors are reported on stderr
+int index_build_file(const char *path);
+
 Fmt fmt_from_path(const char *path);   // by extension (src/misc.c:178-216)
 Fmt fmt_from_name(const char *name);   // "slow5" / "blow5"
 

@@ -1,4 +1,5 @@
-// index_main.cpp -- `slow5tools-b200 index FILE`: writes FILE.idx, byte-identical to the reference's index
+// index_main.cpp -- `slow5tools-b200 index FILE` and the library's index builder (part of libslow5b200.so): writes FILE.idx,
+// byte-identical to the reference's index
 // (src/index.c -> slow5_idx_create / slow5_idx_build / slow5_idx_write, slow5lib/src/slow5_idx.c:155-414).
 //
 // Index file (slow5_idx.c:360-412): "SLOW5IDX\1", the data file's version (3 bytes), zero padding up to byte 64, then per
@@ -75,6 +76,12 @@ int index_main(int argc, char **argv) {
         IDX_ERROR("missing slow5 or blow5 file%s", "");
         return 1;
     }
+    return s5b::index_build_file(path);
+}
+
+// slow5_idx_create (slow5.c:4138-4150): builds PATH.idx; also what s5b_idx_load falls back to when the index file is missing,
+// like the reference's slow5_idx_init does (slow5_idx.c:60-110).  0 = written.
+int s5b::index_build_file(const char *path) {
     Reader rd;
     if (!reader_open(rd, path, FMT_UNKNOWN)) {
         IDX_ERROR("File '%s' could not be opened - %s.", path, rd.err.c_str());

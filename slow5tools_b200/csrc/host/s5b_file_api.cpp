@@ -595,6 +595,12 @@ int s5b_idx_load(s5b_file_t *fpub) {  // slow5_idx_load (slow5.h:560): reads FIL
     if (!f || f->writing) return fail(S5B_ERR_ARG);
     if (f->index_loaded) return 0;
     FILE *x = fopen((f->path + ".idx").c_str(), "rb");
+    if (!x) {
+        // "Creates the index if not found" (slow5.c:4152-4169, slow5_idx.c:60-110): the same builder as `slow5tools-b200 index`
+        fprintf(stderr, "[slow5_idx_init::INFO]\033[1;34m Index file not found. Creating an index at '%s.idx'.\033[0m\n", f->path.c_str());
+        if (index_build_file(f->path.c_str()) != 0) return fail(S5B_ERR_IO);
+        x = fopen((f->path + ".idx").c_str(), "rb");
+    }
     if (!x) return fail(S5B_ERR_IO);
     std::vector<uint8_t> b;
     uint8_t tmp[1 << 16];
@@ -672,14 +678,18 @@ int s5b_get(const char *read_id, s5b_rec_t **read, s5b_file_t *fpub) {  // slow5
     if (!read_id || !read || !f || f->writing) return fail(S5B_ERR_ARG);
     if (!f->index_loaded) return fail(S5B_ERR_NOIDX);
     const auto it = f->index.find(read_id);
-    if (it == f->index.end() || it->second.size < 8) return fail(S5B_ERR_NOTFOUND);
-    size_t bytes = (size_t)(it->second.size - 8);
-    char *m = static_cast<char *>(malloc(bytes ? bytes : 1));
+    // an index entry covers the record's size prefix (BLOW5) or its line with the newline (SLOW5), slow5_idx.c:207-334
+    const bool text = f->rd.fmt == FMT_ASCII;
+    const uint64_t skip = text ? 0 : 8, drop = text ? 1 : 8;
+    if (it == f->index.end() || it->second.size < drop) return fail(S5B_ERR_NOTFOUND);
+    size_t bytes = (size_t)(it->second.size - drop);
+    char *m = static_cast<char *>(malloc(bytes + 1));
     if (!m) return fail(S5B_ERR_MEM);
+    m[bytes] = '\0';
     const int fd = fileno(f->rd.fp);
     size_t done = 0;
     while (done < bytes) {
-        const ssize_t r = pread(fd, m + done, bytes - done, (off_t)(it->second.offset + 8 + done));
+        const ssize_t r = pread(fd, m + done, bytes - done, (off_t)(it->second.offset + skip + done));
         if (r <= 0) {
             free(m);
             return fail(S5B_ERR_IO);

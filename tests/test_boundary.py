@@ -457,3 +457,37 @@ def test_header_and_index_introspection_matches_the_reference(tmp_path):
         assert a.returncode == 0 and b.returncode == 0, (a.stderr.decode(), b.stderr.decode())
         assert a.stdout == b.stdout, (a.stdout.decode(), b.stdout.decode())
         assert b"rids before idx_load: NULL" in a.stdout and b"rids " in a.stdout
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+@pytest.mark.parametrize("example", ["sequential_read", "random_read", "header_attribute", "auxiliary_field"])
+def test_reference_examples_build_unchanged(tmp_path, example):
+    """slow5lib/examples/*.c (the programs the reference's documentation walks through: slow5_get_next, slow5_idx_load +
+    slow5_get with the index created on the fly, slow5_hdr_get, slow5_aux_get_*), compiled UNCHANGED against include/compat and
+    linked with libslow5b200.so, print what the reference build prints and leave the same index file behind.  Their inputs are
+    SLOW5 text files: no codec, no device."""
+    src = os.path.join(REFTREE, "slow5lib", "examples", example + ".c")
+    refdir = os.path.dirname(REF_SO)
+    results = []
+    for who in ("ours", "theirs"):
+        d = tmp_path / who
+        os.makedirs(d / "examples")
+        for f in ("example.slow5", "example2.slow5"):
+            shutil.copy(os.path.join(REFTREE, "slow5lib", "examples", f), d / "examples" / f)
+        exe = str(d / "prog")
+        if who == "ours":
+            _cc(["-O1", "-w", "-I", os.path.join(ROOT, "include", "compat"), src, "-o", exe, "-L", LIBDIR, "-lslow5b200",
+                 "-Wl,-rpath," + LIBDIR])
+        else:
+            _cc(["-O1", "-w", "-I", os.path.join(REFTREE, "slow5lib", "include"), src, "-o", exe, "-L", refdir, "-l:libslow5_ref.so",
+                 "-Wl,-rpath," + refdir, "-lm", "-lz"])
+        r = subprocess.run([exe], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+        idx = {f: open(d / "examples" / f, "rb").read() for f in sorted(os.listdir(d / "examples")) if f.endswith(".idx")}
+        results.append((r.returncode, r.stdout, r.stderr, idx))
+    assert results[0][0] == 0 and results[1][0] == 0, (results[0][2].decode(), results[1][2].decode())
+    assert results[0][1] == results[1][1] and len(results[0][1]) > 0
+    assert results[0][2] == results[1][2]
+    assert results[0][3] == results[1][3]
+    if example == "random_read":
+        assert list(results[0][3]) == ["example.slow5.idx"]
