@@ -177,7 +177,8 @@ int s5b_get_next_batch(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
 int s5b_encode_batch_mt(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
 int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *batch, int num_reads);
 /* slow5_idx_load (slow5.h:560) / slow5_get_batch (slow5_mt.h:52, slow5_mt.c:319-333): random access by read id.  The index is
- * FILE.idx as written by `slow5tools-b200 index` (byte-identical to the reference's); S5B_ERR_IO when it is missing.
+ * FILE.idx as written by `slow5tools-b200 index` (byte-identical to the reference's); a missing one is created first, like the
+ * reference does (slow5.c:4152-4169; for a compressed file that is a pass over the GPU), S5B_ERR_IO when that fails.
  * s5b_get_batch fetches the num_rid records with pread() and decodes them as ONE GPU batch into batch->slow5_rec[];
  * returns num_rid, or S5B_ERR_ARG when an id is not in the index (the reference exits the process). */
 int s5b_idx_load(s5b_file_t *fp);
