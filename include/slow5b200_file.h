@@ -146,6 +146,20 @@ char **s5b_get_aux_names(const s5b_hdr_t *header, uint64_t *len);
 int *s5b_get_aux_types(const s5b_hdr_t *header, uint64_t *len);
 char **s5b_get_aux_enum_labels(const s5b_hdr_t *header, const char *field, uint8_t *n);
 char **s5b_get_rids(const s5b_file_t *fp, uint64_t *len);
+/* Building a file from scratch (slow5.h:404-447, :510-545), the calls slow5lib/examples/write.c makes: header attributes and
+ * auxiliary columns are added to the header of a file opened with "w" before s5b_hdr_write; a record is made with s5b_rec_init,
+ * its public fields are filled in by the caller (read_id and raw_signal malloc()'d: s5b_rec_free frees them), its auxiliary values
+ * are set one by one -- a column that gets none is written as the type's NULL value / an empty array -- and s5b_write encodes
+ * and appends it.  Return values are the reference's: 0, or -1 (bad argument), -2 (attribute / column exists, or no such
+ * column), -3 (enum columns: not supported here; array / primitive mismatch). */
+s5b_rec_t *s5b_rec_init(void);
+int s5b_hdr_add(const char *attr, s5b_hdr_t *header);
+int s5b_hdr_set(const char *attr, const char *value, uint32_t read_group, s5b_hdr_t *header);
+int64_t s5b_hdr_add_rg(s5b_hdr_t *header);
+int s5b_aux_add(const char *field, int type /* enum slow5_aux_type */, s5b_hdr_t *header);
+int s5b_aux_set(s5b_rec_t *read, const char *field, const void *data, s5b_hdr_t *header);
+int s5b_aux_set_array(s5b_rec_t *read, const char *field, const void *data, size_t len, s5b_hdr_t *header);
+int s5b_aux_set_string(s5b_rec_t *read, const char *field, const char *data, s5b_hdr_t *header);
 
 /* n records at once: mems[i]/bytes[i] as returned by s5b_get_next_mem; reads[i] allocated when NULL */
 int s5b_decode_batch(s5b_file_t *fp, char **mems, size_t *bytes, size_t n, s5b_rec_t **reads);
@@ -258,6 +272,13 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_get_aux_types(h, n) ((enum slow5_aux_type *)s5b_get_aux_types(h, n))
 #define slow5_get_aux_enum_labels s5b_get_aux_enum_labels
 #define slow5_get_rids s5b_get_rids
+#define slow5_rec_init s5b_rec_init
+#define slow5_hdr_add s5b_hdr_add
+#define slow5_hdr_set s5b_hdr_set
+#define slow5_hdr_add_rg s5b_hdr_add_rg
+#define slow5_aux_add s5b_aux_add
+#define slow5_aux_set s5b_aux_set
+#define slow5_aux_set_string s5b_aux_set_string
 #define slow5_hdr_t s5b_hdr_t
 #define slow5_errno (s5b_errno_value())
 #endif

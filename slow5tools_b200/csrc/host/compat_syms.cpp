@@ -82,5 +82,12 @@ char **slow5_get_aux_names(const s5b_hdr_t *h, uint64_t *len) { return s5b_get_a
 int *slow5_get_aux_types(const s5b_hdr_t *h, uint64_t *len) { return s5b_get_aux_types(h, len); }
 char **slow5_get_aux_enum_labels(const s5b_hdr_t *h, const char *field, uint8_t *n) { return s5b_get_aux_enum_labels(h, field, n); }
 char **slow5_get_rids(const s5b_file_t *fp, uint64_t *len) { return s5b_get_rids(fp, len); }
+s5b_rec_t *slow5_rec_init(void) { return s5b_rec_init(); }
+int slow5_hdr_add(const char *attr, s5b_hdr_t *h) { return s5b_hdr_add(attr, h); }
+int slow5_hdr_set(const char *attr, const char *value, uint32_t rg, s5b_hdr_t *h) { return s5b_hdr_set(attr, value, rg, h); }
+int64_t slow5_hdr_add_rg(s5b_hdr_t *h) { return s5b_hdr_add_rg(h); }
+int slow5_aux_add(const char *field, int type, s5b_hdr_t *h) { return s5b_aux_add(field, type, h); }
+int slow5_aux_set(s5b_rec_t *r, const char *field, const void *data, s5b_hdr_t *h) { return s5b_aux_set(r, field, data, h); }
+int slow5_aux_set_string(s5b_rec_t *r, const char *field, const char *data, s5b_hdr_t *h) { return s5b_aux_set_string(r, field, data, h); }
 
 }  // extern "C"

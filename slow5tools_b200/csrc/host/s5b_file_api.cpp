@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -31,6 +32,18 @@ struct AuxView {
     std::vector<uint64_t> len;   // elements of field f (1 for a primitive)
     std::vector<uint64_t> at;    // primitives: offset of the value inside s5b_rec_t::aux
     std::vector<void *> arr;     // arrays: the copy, nullptr when len == 0
+};
+// what slow5_aux_set* has given a record a caller is building (slow5_rec_set*, slow5.c:3363-3492): field name -> element count and
+// bytes; the record's binary section is laid out from it for the header's columns after every call
+struct AuxPending {
+    int type;
+    uint64_t len;
+    std::vector<uint8_t> data;
+};
+// what s5b_rec_t::aux_meta points at
+struct RecPriv {
+    AuxView *view = nullptr;                            // decoded records
+    std::map<std::string, AuxPending> *pending = nullptr;  // records under construction
 };
 struct S5bFile;
 // the public header struct first, the way back to the file behind it (s5b_hdr_get)
@@ -142,6 +155,7 @@ s5b_file_t *s5b_open(const char *pathname, const char *mode) {
         f->out = fopen(pathname, "wb");
         if (f->out) {
             f->writing = true;
+            f->hdr.version[0] = 0, f->hdr.version[1] = 2, f->hdr.version[2] = 0;  // SLOW5_VERSION_STRUCT, slow5_defs.h:51-53
             publish(f);
             return &f->pub;
         }
@@ -227,11 +241,15 @@ int s5b_get_next_bytes(char **mem, size_t *bytes, s5b_file_t *f) {
 }
 
 static void aux_view_free(s5b_rec_t *r) {
-    AuxView *v = static_cast<AuxView *>(r->aux_meta);
-    if (!v) return;
-    for (void *p : v->arr) free(p);
-    aux_table_unref(v->table);
-    delete v;
+    RecPriv *pr = static_cast<RecPriv *>(r->aux_meta);
+    if (!pr) return;
+    if (AuxView *v = pr->view) {
+        for (void *p : v->arr) free(p);
+        aux_table_unref(v->table);
+        delete v;
+    }
+    delete pr->pending;
+    delete pr;
     r->aux_meta = nullptr;
 }
 // walks the record's auxiliary section against the file's columns (slow5_rec_aux_parse, slow5.c:3088-3166); a section that does
@@ -282,7 +300,9 @@ static void aux_view_build(s5b_rec_t *r, AuxTable *t) {
     }
     ++t->refs;
     v->table = t;
-    r->aux_meta = v;
+    RecPriv *pr = new RecPriv();
+    pr->view = v;
+    r->aux_meta = pr;
 }
 
 void s5b_rec_free(s5b_rec_t *r) {
@@ -717,7 +737,8 @@ namespace {
 // the field's position in the record's view, or a negative S5B_ERR_* (slow5.c:3496-3522)
 int aux_find(const s5b_rec_t *read, const char *field, int want_type, const AuxView **view) {
     if (!read || !field) return S5B_ERR_ARG;
-    const AuxView *v = static_cast<const AuxView *>(read->aux_meta);
+    const RecPriv *pr = static_cast<const RecPriv *>(read->aux_meta);
+    const AuxView *v = pr ? pr->view : nullptr;
     if (!v) return S5B_ERR_NOAUX;
     const std::vector<AuxField> &fs = v->table->fields;
     for (size_t i = 0; i < fs.size(); ++i)
@@ -888,6 +909,131 @@ char **s5b_get_rids(const s5b_file_t *fpub, uint64_t *len) {   // read ids in in
     }
     if (len) *len = f->rids_c.size();
     return f->rids_c.data();
+}
+
+// ---- building a file from scratch (slow5.h:404-447, :510-545; slow5.c:1502-1640, :2160-2220, :3363-3492) -----------------
+s5b_rec_t *s5b_rec_init(void) { return static_cast<s5b_rec_t *>(calloc(1, sizeof(s5b_rec_t))); }
+
+int s5b_hdr_add(const char *attr, s5b_hdr_t *header) {   // 0, -1 (NULL argument), -2 (the attribute exists)
+    S5bFile *f = owner_of(header);
+    if (!attr || !f || !f->writing) return -1;
+    for (const auto &kv : f->hdr.attrs)
+        if (kv.first == attr) return -2;
+    f->hdr.attrs.emplace_back(attr, std::vector<std::string>(f->hdr.num_read_groups));
+    return 0;
+}
+
+int s5b_hdr_set(const char *attr, const char *value, uint32_t read_group, s5b_hdr_t *header) {   // 0 / -1
+    S5bFile *f = owner_of(header);
+    if (!attr || !value || !f || !f->writing || read_group >= f->hdr.num_read_groups) return -1;
+    for (auto &kv : f->hdr.attrs)
+        if (kv.first == attr) {
+            kv.second.resize(f->hdr.num_read_groups);
+            kv.second[read_group] = value;
+            return 0;
+        }
+    return -1;
+}
+
+int64_t s5b_hdr_add_rg(s5b_hdr_t *header) {   // the new read group's number, -1 on error
+    S5bFile *f = owner_of(header);
+    if (!f || !f->writing) return -1;
+    const int64_t rg = f->hdr.num_read_groups++;
+    for (auto &kv : f->hdr.attrs) kv.second.resize(f->hdr.num_read_groups);
+    f->hdr_priv.pub.num_read_groups = f->hdr.num_read_groups;
+    return rg;
+}
+
+int s5b_aux_add(const char *field, int type, s5b_hdr_t *header) {   // 0, -1 (bad argument), -2 (exists), -3 (enum: needs labels)
+    S5bFile *f = owner_of(header);
+    if (!field || !f || !f->writing || type < AUX_INT8 || type > AUX_ENUM_ARRAY) return -1;
+    if (type == AUX_ENUM || type == AUX_ENUM_ARRAY) return -3;
+    for (const AuxField &a : f->hdr.aux)
+        if (a.name == field) return -2;
+    static const struct {
+        const char *name;
+        uint8_t size;
+    } prim[] = {{"int8_t", 1}, {"int16_t", 2}, {"int32_t", 4}, {"int64_t", 8}, {"uint8_t", 1}, {"uint16_t", 2},
+                {"uint32_t", 4}, {"uint64_t", 8}, {"float", 4}, {"double", 8}, {"char", 1}};
+    AuxField a;
+    a.name = field;
+    a.type = type;
+    const bool arr = type >= AUX_INT8_ARRAY;
+    const int base = arr ? (type == AUX_STRING ? AUX_CHAR : type - AUX_INT8_ARRAY) : type;
+    a.size = prim[base].size;
+    a.type_str = std::string(prim[base].name) + (arr ? "*" : "");
+    f->hdr.aux.push_back(a);
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+// lays the record's binary auxiliary section out for the header's columns from what has been set so far: a column without a
+// value gets the type's NULL value, an array without one a zero count (slow5.c:3993-4044)
+void aux_relay_pending(s5b_rec_t *r, const std::map<std::string, AuxPending> &pending, const std::vector<AuxField> &cols) {
+    std::vector<uint8_t> out;
+    for (const AuxField &c : cols) {
+        const auto it = pending.find(c.name);
+        const bool have = it != pending.end() && it->second.type == c.type;
+        if (c.is_array()) {
+            const uint64_t n = have ? it->second.len : 0;
+            const uint8_t *p = reinterpret_cast<const uint8_t *>(&n);
+            out.insert(out.end(), p, p + 8);
+            if (have) out.insert(out.end(), it->second.data.begin(), it->second.data.end());
+        } else if (have) {
+            out.insert(out.end(), it->second.data.begin(), it->second.data.end());
+        } else {
+            uint8_t v[8] = {0};
+            aux_null_value(c.type, v);
+            out.insert(out.end(), v, v + c.size);
+        }
+    }
+    free(r->aux);
+    r->aux_len = out.size();
+    r->aux = static_cast<uint8_t *>(malloc(out.size() ? out.size() : 1));
+    if (r->aux && !out.empty()) memcpy(r->aux, out.data(), out.size());
+}
+// 0, -1 (bad argument), -2 (no such column), -3 (array / primitive mismatch)
+int aux_set_any(s5b_rec_t *r, const char *field, const void *data, uint64_t len, bool want_array, bool want_string, s5b_hdr_t *header) {
+    S5bFile *f = header ? reinterpret_cast<HdrPriv *>(header)->owner : nullptr;
+    if (!r || !field || !data || !f) return -1;
+    const std::vector<AuxField> &cols = f->writing ? f->hdr.aux : f->rd.hdr.aux;
+    if (cols.empty()) return -1;
+    const AuxField *col = nullptr;
+    for (const AuxField &c : cols)
+        if (c.name == field) col = &c;
+    if (!col) return -2;
+    if (col->is_array() != want_array || (want_string && col->type != AUX_STRING)) return -3;
+    RecPriv *pr = static_cast<RecPriv *>(r->aux_meta);
+    if (pr && pr->view) {  // a decoded record that is being edited: its stored values are the starting point
+        aux_view_free(r);
+        pr = nullptr;
+    }
+    if (!pr) {
+        pr = new RecPriv();
+        r->aux_meta = pr;
+    }
+    if (!pr->pending) pr->pending = new std::map<std::string, AuxPending>();
+    AuxPending &p = (*pr->pending)[field];
+    p.type = col->type;
+    p.len = len;
+    p.data.assign(static_cast<const uint8_t *>(data), static_cast<const uint8_t *>(data) + len * col->size);
+    aux_relay_pending(r, *pr->pending, cols);
+    return r->aux ? 0 : -1;
+}
+}  // namespace
+
+extern "C" {
+
+int s5b_aux_set(s5b_rec_t *read, const char *field, const void *data, s5b_hdr_t *header) {
+    return aux_set_any(read, field, data, 1, false, false, header);
+}
+int s5b_aux_set_array(s5b_rec_t *read, const char *field, const void *data, size_t len, s5b_hdr_t *header) {
+    return aux_set_any(read, field, data, len, true, false, header);
+}
+int s5b_aux_set_string(s5b_rec_t *read, const char *field, const char *data, s5b_hdr_t *header) {
+    return aux_set_any(read, field, data, data ? strlen(data) : 0, true, true, header);
 }
 
 char *s5b_hdr_get(const char *attr, uint32_t read_group, const s5b_hdr_t *header) {

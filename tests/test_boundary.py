@@ -491,3 +491,81 @@ def test_reference_examples_build_unchanged(tmp_path, example):
     assert results[0][3] == results[1][3]
     if example == "random_read":
         assert list(results[0][3]) == ["example.slow5.idx"]
+
+
+WRITE_PROG = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <slow5/slow5.h>
+/* slow5lib/examples/write.c with two read groups, three records, values left unset, and no compression */
+int main(int argc, char **argv) {
+    slow5_file_t *sp = slow5_open(argv[1], "w");
+    if (!sp) return 2;
+    if (slow5_set_press(sp, SLOW5_COMPRESS_NONE, SLOW5_COMPRESS_NONE) < 0) return 3;
+    slow5_hdr_t *h = sp->header;
+    int rc = 0;
+    rc |= slow5_hdr_add("run_id", h) | slow5_hdr_add("asic_id", h) | slow5_hdr_add("zeta", h);
+    printf("add again -> %d\n", slow5_hdr_add("run_id", h));
+    printf("add_rg -> %d\n", (int)slow5_hdr_add_rg(h));
+    rc |= slow5_hdr_set("run_id", "run_0", 0, h) | slow5_hdr_set("asic_id", "asic_id_0", 0, h) | slow5_hdr_set("run_id", "run_1", 1, h);
+    printf("set unknown -> %d, set rg 7 -> %d\n", slow5_hdr_set("nope", "x", 0, h), slow5_hdr_set("run_id", "x", 7, h));
+    rc |= slow5_aux_add("channel_number", SLOW5_STRING, h) | slow5_aux_add("median_before", SLOW5_DOUBLE, h);
+    rc |= slow5_aux_add("read_number", SLOW5_INT32_T, h) | slow5_aux_add("start_mux", SLOW5_UINT8_T, h);
+    rc |= slow5_aux_add("start_time", SLOW5_UINT64_T, h);
+    printf("aux_add again -> %d\n", slow5_aux_add("start_mux", SLOW5_UINT8_T, h));
+    if (rc || slow5_hdr_write(sp) < 0) return 4;
+    for (int r = 0; r < 3; ++r) {
+        slow5_rec_t *rec = slow5_rec_init();
+        char id[32];
+        snprintf(id, sizeof id, "read_%d", r);
+        rec->read_id = strdup(id);
+        rec->read_id_len = strlen(id);
+        rec->read_group = r & 1;
+        rec->digitisation = 4096.0; rec->offset = 3.0 + r; rec->range = 10.0; rec->sampling_rate = 4000.0;
+        rec->len_raw_signal = 10 + r;
+        rec->raw_signal = (int16_t *)malloc(sizeof(int16_t) * rec->len_raw_signal);
+        for (uint64_t i = 0; i < rec->len_raw_signal; ++i) rec->raw_signal[i] = (int16_t)(i * 7 - 20 * r);
+        double mb = 0.1 + r; int32_t rn = 10 + r; uint8_t mux = 1; uint64_t st = 100 + r;
+        if (r != 1 && slow5_aux_set_string(rec, "channel_number", r ? "512" : "0", h) < 0) return 5;   /* record 1: left unset */
+        if (slow5_aux_set(rec, "median_before", &mb, h) < 0 || slow5_aux_set(rec, "read_number", &rn, h) < 0) return 6;
+        if (r != 2 && slow5_aux_set(rec, "start_mux", &mux, h) < 0) return 7;                             /* record 2: left unset */
+        if (slow5_aux_set(rec, "start_time", &st, h) < 0) return 8;
+        if (r == 0) printf("set unknown field -> %d, set string as primitive -> %d, primitive as string -> %d\n",
+                           slow5_aux_set(rec, "nope", &mb, h), slow5_aux_set(rec, "channel_number", &mb, h),
+                           slow5_aux_set_string(rec, "start_mux", "1", h));
+        if (slow5_write(rec, sp) < 0) return 10;
+        slow5_rec_free(rec);
+    }
+    slow5_close(sp);
+    return 0;
+}
+"""
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+def test_writing_a_file_from_scratch_matches_the_reference(tmp_path):
+    """slow5_hdr_add / _hdr_set / _hdr_add_rg / _aux_add / slow5_rec_init / slow5_aux_set[_array,_string] / slow5_write (the calls
+    of slow5lib/examples/write.c): one program against both libraries writes the same uncompressed BLOW5 file, byte for byte,
+    and prints the same return codes"""
+    src = tmp_path / "write.c"
+    src.write_text(WRITE_PROG)
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "theirs")
+    _cc(["-O1", "-w", "-I", os.path.join(ROOT, "include", "compat"), str(src), "-o", ours, "-L", LIBDIR, "-lslow5b200", "-Wl,-rpath," + LIBDIR])
+    refdir = os.path.dirname(REF_SO)
+    _cc(["-O1", "-w", "-I", os.path.join(REFTREE, "slow5lib", "include"), str(src), "-o", theirs, "-L", refdir, "-l:libslow5_ref.so",
+         "-Wl,-rpath," + refdir, "-lm", "-lz"])
+    fa, fb = str(tmp_path / "ours.blow5"), str(tmp_path / "theirs.blow5")
+    a = subprocess.run([ours, fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    b = subprocess.run([theirs, fb], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert a.returncode == 0 and b.returncode == 0, (a.returncode, a.stderr.decode(), b.returncode, b.stderr.decode())
+    assert a.stdout == b.stdout, (a.stdout.decode(), b.stdout.decode())
+    assert open(fa, "rb").read() == open(fb, "rb").read()
+    # and the file reads back as SLOW5 text through both CLIs identically
+    cli = os.path.join(LIBDIR, "bin", "slow5tools-b200")
+    mine = subprocess.check_output([cli, "view", fa], stderr=subprocess.DEVNULL)
+    ref_cli = os.path.join(refdir, "slow5tools_ref")
+    if os.path.exists(ref_cli):
+        assert mine == subprocess.check_output([ref_cli, "view", fb], stderr=subprocess.DEVNULL)
+    assert b"read_2" in mine and b"\t512\t" in mine
