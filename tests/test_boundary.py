@@ -569,3 +569,31 @@ def test_writing_a_file_from_scratch_matches_the_reference(tmp_path):
     if os.path.exists(ref_cli):
         assert mine == subprocess.check_output([ref_cli, "view", fb], stderr=subprocess.DEVNULL)
     assert b"read_2" in mine and b"\t512\t" in mine
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+def test_reference_example_get_all_read_ids_unchanged(tmp_path):
+    """slow5lib/examples/adv/get_all_read_ids.c (slow5_idx_load + slow5_get_rids), unchanged, on an uncompressed BLOW5 without an
+    index file: both builds create the same index and print the same ids"""
+    cli = os.path.join(LIBDIR, "bin", "slow5tools-b200")
+    src = os.path.join(REFTREE, "slow5lib", "examples", "adv", "get_all_read_ids.c")
+    refdir = os.path.dirname(REF_SO)
+    out = []
+    for who in ("ours", "theirs"):
+        d = tmp_path / who
+        os.makedirs(d)
+        blow = str(d / "in.blow5")
+        subprocess.check_call([cli, "view", os.path.join(REFTREE, "slow5lib", "examples", "example.slow5"), "-o", blow, "-c", "none",
+                               "-s", "none"], stderr=subprocess.DEVNULL)
+        exe = str(d / "prog")
+        if who == "ours":
+            _cc(["-O1", "-w", "-I", os.path.join(ROOT, "include", "compat"), src, "-o", exe, "-L", LIBDIR, "-lslow5b200",
+                 "-Wl,-rpath," + LIBDIR])
+        else:
+            _cc(["-O1", "-w", "-I", os.path.join(REFTREE, "slow5lib", "include"), src, "-o", exe, "-L", refdir, "-l:libslow5_ref.so",
+                 "-Wl,-rpath," + refdir, "-lm", "-lz"])
+        r = subprocess.run([exe, "in.blow5"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+        assert r.returncode == 0, r.stderr.decode()
+        out.append((r.stdout, open(blow + ".idx", "rb").read()))
+    assert out[0] == out[1] and out[0][0].count(b"\n") >= 5
