@@ -151,12 +151,14 @@ char **s5b_get_rids(const s5b_file_t *fp, uint64_t *len);
  * its public fields are filled in by the caller (read_id and raw_signal malloc()'d: s5b_rec_free frees them), its auxiliary values
  * are set one by one -- a column that gets none is written as the type's NULL value / an empty array -- and s5b_write encodes
  * and appends it.  Return values are the reference's: 0, or -1 (bad argument), -2 (attribute / column exists, or no such
- * column), -3 (enum columns: not supported here; array / primitive mismatch). */
+ * column), -3 (s5b_aux_add with an enum type: use s5b_aux_add_enum; array / primitive mismatch), -4 (an enum value beyond the
+ * column's labels, a label that is not a C identifier). */
 s5b_rec_t *s5b_rec_init(void);
 int s5b_hdr_add(const char *attr, s5b_hdr_t *header);
 int s5b_hdr_set(const char *attr, const char *value, uint32_t read_group, s5b_hdr_t *header);
 int64_t s5b_hdr_add_rg(s5b_hdr_t *header);
 int s5b_aux_add(const char *field, int type /* enum slow5_aux_type */, s5b_hdr_t *header);
+int s5b_aux_add_enum(const char *field, const char **enum_labels, uint8_t num_labels, s5b_hdr_t *header);   /* -4: bad label */
 int s5b_aux_set(s5b_rec_t *read, const char *field, const void *data, s5b_hdr_t *header);
 int s5b_aux_set_array(s5b_rec_t *read, const char *field, const void *data, size_t len, s5b_hdr_t *header);
 int s5b_aux_set_string(s5b_rec_t *read, const char *field, const char *data, s5b_hdr_t *header);
@@ -277,6 +279,7 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_hdr_set s5b_hdr_set
 #define slow5_hdr_add_rg s5b_hdr_add_rg
 #define slow5_aux_add s5b_aux_add
+#define slow5_aux_add_enum s5b_aux_add_enum
 #define slow5_aux_set s5b_aux_set
 #define slow5_aux_set_string s5b_aux_set_string
 #define slow5_hdr_t s5b_hdr_t

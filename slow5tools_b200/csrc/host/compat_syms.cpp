@@ -87,6 +87,7 @@ int slow5_hdr_add(const char *attr, s5b_hdr_t *h) { return s5b_hdr_add(attr, h);
 int slow5_hdr_set(const char *attr, const char *value, uint32_t rg, s5b_hdr_t *h) { return s5b_hdr_set(attr, value, rg, h); }
 int64_t slow5_hdr_add_rg(s5b_hdr_t *h) { return s5b_hdr_add_rg(h); }
 int slow5_aux_add(const char *field, int type, s5b_hdr_t *h) { return s5b_aux_add(field, type, h); }
+int slow5_aux_add_enum(const char *field, const char **labels, uint8_t n, s5b_hdr_t *h) { return s5b_aux_add_enum(field, labels, n, h); }
 int slow5_aux_set(s5b_rec_t *r, const char *field, const void *data, s5b_hdr_t *h) { return s5b_aux_set(r, field, data, h); }
 int slow5_aux_set_string(s5b_rec_t *r, const char *field, const char *data, s5b_hdr_t *h) { return s5b_aux_set_string(r, field, data, h); }
 

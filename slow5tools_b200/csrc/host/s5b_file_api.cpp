@@ -966,9 +966,42 @@ int s5b_aux_add(const char *field, int type, s5b_hdr_t *header) {   // 0, -1 (ba
     return 0;
 }
 
+// an enum column with its labels (slow5_aux_add_enum, slow5.c:2222-2334): 0, -1 (bad argument), -2 (exists), -4 (a label is not a C identifier)
+int s5b_aux_add_enum(const char *field, const char **labels, uint8_t n_labels, s5b_hdr_t *header) {
+    S5bFile *f = owner_of(header);
+    if (!field || !labels || !f || !f->writing) return -1;
+    for (const AuxField &a : f->hdr.aux)
+        if (a.name == field) return -2;
+    std::string type = "enum{";
+    for (uint8_t i = 0; i < n_labels; ++i) {
+        const char *l = labels[i];
+        if (!l || !*l || (l[0] >= '0' && l[0] <= '9')) return -4;
+        for (const char *c = l; *c; ++c)
+            if (!((*c >= 'a' && *c <= 'z') || (*c >= 'A' && *c <= 'Z') || (*c >= '0' && *c <= '9') || *c == '_')) return -4;
+        if (i) type += ',';
+        type += l;
+    }
+    type += '}';
+    AuxField a;
+    a.name = field;
+    a.type = AUX_ENUM;
+    a.size = 1;
+    a.type_str = type;
+    f->hdr.aux.push_back(a);
+    return 0;
+}
+
 }  // extern "C"
 
 namespace {
+// number of labels of an enum column, from its type as written in the header ("enum{a,b,c}")
+size_t enum_label_count(const AuxField &c) {
+    const size_t open = c.type_str.find('{'), close = c.type_str.rfind('}');
+    if (open == std::string::npos || close == std::string::npos || close <= open + 1) return 0;
+    size_t n = 1;
+    for (size_t i = open + 1; i < close; ++i) n += c.type_str[i] == ',';
+    return n;
+}
 // lays the record's binary auxiliary section out for the header's columns from what has been set so far: a column without a
 // value gets the type's NULL value, an array without one a zero count (slow5.c:3993-4044)
 void aux_relay_pending(s5b_rec_t *r, const std::map<std::string, AuxPending> &pending, const std::vector<AuxField> &cols) {
@@ -1005,6 +1038,11 @@ int aux_set_any(s5b_rec_t *r, const char *field, const void *data, uint64_t len,
         if (c.name == field) col = &c;
     if (!col) return -2;
     if (col->is_array() != want_array || (want_string && col->type != AUX_STRING)) return -3;
+    if (col->type == AUX_ENUM || col->type == AUX_ENUM_ARRAY) {  // a value beyond the labels (slow5.c:3388-3396, :3440-3451)
+        const size_t nl = enum_label_count(*col);
+        for (uint64_t i = 0; i < len; ++i)
+            if (static_cast<const uint8_t *>(data)[i] >= nl) return -4;
+    }
     RecPriv *pr = static_cast<RecPriv *>(r->aux_meta);
     if (pr && pr->view) {  // a decoded record that is being edited: its stored values are the starting point
         aux_view_free(r);

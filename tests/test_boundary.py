@@ -513,6 +513,11 @@ int main(int argc, char **argv) {
     rc |= slow5_aux_add("channel_number", SLOW5_STRING, h) | slow5_aux_add("median_before", SLOW5_DOUBLE, h);
     rc |= slow5_aux_add("read_number", SLOW5_INT32_T, h) | slow5_aux_add("start_mux", SLOW5_UINT8_T, h);
     rc |= slow5_aux_add("start_time", SLOW5_UINT64_T, h);
+    const char *labels[] = {"unknown", "partial", "mux_change", "signal_positive"};
+    const char *bad[] = {"ok", "9lives"};
+    printf("add_enum bad label -> %d, add enum through aux_add -> %d\n", slow5_aux_add_enum("oops", bad, 2, h),
+           slow5_aux_add("oops2", SLOW5_ENUM, h));
+    rc |= slow5_aux_add_enum("end_reason", labels, 4, h);
     printf("aux_add again -> %d\n", slow5_aux_add("start_mux", SLOW5_UINT8_T, h));
     if (rc || slow5_hdr_write(sp) < 0) return 4;
     for (int r = 0; r < 3; ++r) {
@@ -531,6 +536,9 @@ int main(int argc, char **argv) {
         if (slow5_aux_set(rec, "median_before", &mb, h) < 0 || slow5_aux_set(rec, "read_number", &rn, h) < 0) return 6;
         if (r != 2 && slow5_aux_set(rec, "start_mux", &mux, h) < 0) return 7;                             /* record 2: left unset */
         if (slow5_aux_set(rec, "start_time", &st, h) < 0) return 8;
+        uint8_t why = (uint8_t)(r + 1), beyond = 4;
+        if (r != 1 && slow5_aux_set(rec, "end_reason", &why, h) < 0) return 9;
+        if (r == 1) printf("enum value beyond the labels -> %d\n", slow5_aux_set(rec, "end_reason", &beyond, h));
         if (r == 0) printf("set unknown field -> %d, set string as primitive -> %d, primitive as string -> %d\n",
                            slow5_aux_set(rec, "nope", &mb, h), slow5_aux_set(rec, "channel_number", &mb, h),
                            slow5_aux_set_string(rec, "start_mux", "1", h));
