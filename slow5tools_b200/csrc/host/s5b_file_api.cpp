@@ -151,6 +151,32 @@ s5b_file_t *s5b_open(const char *pathname, const char *mode) {
         f->pub.meta.start_rec_offset = f->rd.fp ? (uint64_t)ftello(f->rd.fp) : 0;
         return &f->pub;
     }
+    if (mode[0] == 'a' && fmt_from_path(pathname) == FMT_BINARY) {
+        // append (slow5_open_with "a", slow5.c:330-417): header, columns and compression come from the file; new records go where
+        // its end-of-file marker is, and s5b_close writes the marker behind them
+        Reader rd;
+        if (reader_open(rd, pathname, FMT_BINARY)) {
+            f->hdr = rd.hdr;
+            f->rec_press = rd.hdr.record_method;
+            f->sig_press = rd.hdr.signal_method;
+            reader_close(rd);
+            f->out = fopen(pathname, "r+b");
+            char tail[5];
+            if (f->out && fseeko(f->out, -5, SEEK_END) == 0 && fread(tail, 1, 5, f->out) == 5 && memcmp(tail, "5WOLB", 5) == 0 &&
+                fseeko(f->out, -5, SEEK_END) == 0) {
+                f->writing = true;
+                f->hdr_written = true;
+                publish(f);
+                return &f->pub;
+            }
+            if (f->out) fclose(f->out);
+        } else {
+            reader_close(rd);
+        }
+        fail(S5B_ERR_IO);
+        delete f;
+        return nullptr;
+    }
     if (mode[0] == 'w' && fmt_from_path(pathname) == FMT_BINARY) {
         f->out = fopen(pathname, "wb");
         if (f->out) {

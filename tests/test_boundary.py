@@ -570,6 +570,23 @@ def test_writing_a_file_from_scratch_matches_the_reference(tmp_path):
     assert a.returncode == 0 and b.returncode == 0, (a.returncode, a.stderr.decode(), b.returncode, b.stderr.decode())
     assert a.stdout == b.stdout, (a.stdout.decode(), b.stdout.decode())
     assert open(fa, "rb").read() == open(fb, "rb").read()
+    # slow5lib/examples/append.c, UNCHANGED (it appends read_1 to "test.blow5" in the working directory): run on copies of the file
+    # just written -- the columns it sets (channel_number ... start_time) exist there -- both builds leave the same file
+    app = os.path.join(REFTREE, "slow5lib", "examples", "append.c")
+    if os.path.exists(app):
+        got = []
+        for who, inc_lib in (("ours", ["-I", os.path.join(ROOT, "include", "compat"), app, "-L", LIBDIR, "-lslow5b200", "-Wl,-rpath," + LIBDIR]),
+                             ("theirs", ["-I", os.path.join(REFTREE, "slow5lib", "include"), app, "-L", refdir, "-l:libslow5_ref.so",
+                                         "-Wl,-rpath," + refdir, "-lm", "-lz"])):
+            d = tmp_path / ("append_" + who)
+            os.makedirs(d)
+            shutil.copy(fa, d / "test.blow5")
+            exe = str(d / "append")
+            _cc(["-O1", "-w"] + inc_lib[:3] + ["-o", exe] + inc_lib[3:])
+            r = subprocess.run([exe], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+            assert r.returncode == 0, (who, r.stderr.decode())
+            got.append(open(d / "test.blow5", "rb").read())
+        assert got[0] == got[1] and len(got[0]) > os.path.getsize(fa) and got[0].endswith(b"5WOLB")
     # and the file reads back as SLOW5 text through both CLIs identically
     cli = os.path.join(LIBDIR, "bin", "slow5tools-b200")
     mine = subprocess.check_output([cli, "view", fa], stderr=subprocess.DEVNULL)
