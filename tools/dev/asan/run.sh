@@ -25,6 +25,9 @@ run aux ./AUX_PROG $R/tests/golden/fixtures/exp_1_lossless.blow5
 run get ./GET_PROG ex.blow5 $(grep -v '^[#@]' $EX | cut -f1 | head -2) no-such-read
 run intro ./INTRO_PROG enum.blow5 end_reason
 run write ./WRITE_PROG w.blow5
+gcc -g -O1 -w -fsanitize=address,undefined -I $R/include/compat $REF/slow5lib/examples/append.c -o append -L . -lslow5b200 -Wl,-rpath,$T
+cp w.blow5 test.blow5
+run append ./append
 run index ./cli index ex.blow5
 run cli_get ./cli get ex.blow5 $(grep -v '^[#@]' $EX | cut -f1 | head -1) --to slow5
 run demux ./cli split -x $D/raw/split/demux9/barcode_summary.txt $D/raw/split/demux10/example2_0_multi.slow5 -d o1 --to slow5 --demux-rid rid --demux-code code
