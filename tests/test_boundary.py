@@ -291,7 +291,8 @@ def test_aux_accessors_and_header_attributes_match_the_reference(tmp_path):
 def test_error_codes_carry_the_reference_values():
     """slow5_defs.h:137-154"""
     text = open(os.path.join(ROOT, "include", "slow5b200_file.h")).read() + open(os.path.join(ROOT, "include", "slow5b200.h")).read()
-    want = {"S5B_ERR_EOF": -1, "S5B_ERR_ARG": -2, "S5B_ERR_RECPARSE": -4, "S5B_ERR_IO": -5, "S5B_ERR_MEM": -10, "S5B_ERR_NOAUX": -11,
+    want = {"S5B_ERR_EOF": -1, "S5B_ERR_ARG": -2, "S5B_ERR_RECPARSE": -4, "S5B_ERR_IO": -5, "S5B_ERR_NOIDX": -6, "S5B_ERR_NOTFOUND": -7,
+            "S5B_ERR_MEM": -10, "S5B_ERR_NOAUX": -11,
             "S5B_ERR_NOFLD": -12, "S5B_ERR_PRESS": -13, "S5B_ERR_TYPE": -17}
     import re
     for name, value in want.items():
