@@ -86,7 +86,7 @@ typedef struct s5b_file {
 
 extern int s5b_errno_value(void);   /* the twin of the thread-local slow5_errno */
 
-s5b_file_t *s5b_open(const char *pathname, const char *mode /* "r", "w" (BLOW5) or "a" (append to a BLOW5 file) */);
+s5b_file_t *s5b_open(const char *pathname, const char *mode /* "r", "w" (.blow5 or .slow5) or "a" (append to a BLOW5 file) */);
 int s5b_close(s5b_file_t *fp);                     /* "w": appends the end-of-file marker first */
 /* "w" files: take the header (attributes, aux columns, version) from an opened input, choose the methods */
 int s5b_hdr_copy(s5b_file_t *dst, const s5b_file_t *src);

@@ -62,6 +62,7 @@ struct S5bFile {
     Reader rd;          // "r"
     FILE *out = nullptr;  // "w"
     bool writing = false;
+    Fmt out_fmt = FMT_BINARY;   // "w": what the path's extension says (.blow5 / .slow5)
     bool hdr_written = false;
     Header hdr;         // "w": header to emit
     int rec_press = PRESS_ZLIB, sig_press = PRESS_SVB_ZD;
@@ -85,7 +86,7 @@ static inline const S5bFile *impl(const s5b_file_t *f) { return reinterpret_cast
 // keeps the public fields in step with the private state
 static void publish(S5bFile *f) {
     f->pub.fp = f->writing ? f->out : f->rd.fp;
-    const Fmt fmt = f->writing ? FMT_BINARY : f->rd.fmt;
+    const Fmt fmt = f->writing ? f->out_fmt : f->rd.fmt;
     f->pub.format = fmt == FMT_BINARY ? 2 : fmt == FMT_ASCII ? 1 : 0;
     const Header &h = f->writing ? f->hdr : f->rd.hdr;
     f->hdr_pub.version.major = h.version[0];
@@ -177,10 +178,12 @@ s5b_file_t *s5b_open(const char *pathname, const char *mode) {
         delete f;
         return nullptr;
     }
-    if (mode[0] == 'w' && fmt_from_path(pathname) == FMT_BINARY) {
+    if (mode[0] == 'w' && fmt_from_path(pathname) != FMT_UNKNOWN) {
         f->out = fopen(pathname, "wb");
         if (f->out) {
             f->writing = true;
+            f->out_fmt = fmt_from_path(pathname);
+            if (f->out_fmt == FMT_ASCII) f->rec_press = f->sig_press = PRESS_NONE;  // text records are not compressed
             f->hdr.version[0] = 0, f->hdr.version[1] = 2, f->hdr.version[2] = 0;  // SLOW5_VERSION_STRUCT, slow5_defs.h:51-53
             publish(f);
             return &f->pub;
@@ -196,7 +199,7 @@ int s5b_close(s5b_file_t *fpub) {
     S5bFile *f = impl(fpub);
     int rc = 0;
     if (f->writing) {
-        if (fwrite("5WOLB", 1, 5, f->out) != 5) rc = S5B_ERR_IO;  // slow5.c:522-531
+        if (f->out_fmt == FMT_BINARY && fwrite("5WOLB", 1, 5, f->out) != 5) rc = S5B_ERR_IO;  // slow5.c:522-531
         if (fclose(f->out) != 0) rc = S5B_ERR_IO;
     } else {
         reader_close(f->rd);
@@ -217,6 +220,7 @@ int s5b_hdr_copy(s5b_file_t *dstp, const s5b_file_t *srcp) {
 int s5b_set_press(s5b_file_t *fpub, int rec_press, int sig_press) {
     S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !f->writing || f->hdr_written) return fail(S5B_ERR_ARG);
+    if (f->out_fmt != FMT_BINARY) return fail(S5B_ERR_ARG);  // "File should be in binary format (blow5)", slow5.c:585-589
     if ((rec_press != PRESS_NONE && rec_press != PRESS_ZLIB && rec_press != PRESS_ZSTD) ||
         (sig_press != PRESS_NONE && sig_press != PRESS_SVB_ZD && sig_press != PRESS_EX_ZD))
         return fail(S5B_ERR_ARG);
@@ -228,7 +232,7 @@ int s5b_set_press(s5b_file_t *fpub, int rec_press, int sig_press) {
 int s5b_hdr_write(s5b_file_t *fpub) {
     S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !f->writing) return fail(S5B_ERR_ARG);
-    const std::string h = header_to_mem(f->hdr, FMT_BINARY, f->rec_press, f->sig_press);
+    const std::string h = header_to_mem(f->hdr, f->out_fmt, f->rec_press, f->sig_press);
     if (fwrite(h.data(), 1, h.size(), f->out) != h.size()) return fail(S5B_ERR_IO);
     f->hdr_written = true;
     return (int)h.size();
@@ -452,6 +456,31 @@ int s5b_encode_batch(s5b_file_t *fpub, s5b_rec_t **reads, size_t n, char **mems,
     S5bFile *f = fpub ? impl(fpub) : nullptr;
     if (!f || !reads || !mems || !bytes) return fail(S5B_ERR_ARG);
     if (n == 0) return 0;
+    if (f->writing && f->out_fmt == FMT_ASCII) {  // SLOW5 text lines (slow5.c:3837-3926): host formatting, nothing to compress
+        for (size_t i = 0; i < n; ++i) {
+            const s5b_rec_t *r = reads[i];
+            Record rec;
+            rec.read_id.assign(r->read_id ? r->read_id : "", r->read_id ? r->read_id_len : 0);
+            rec.read_group = r->read_group;
+            rec.digitisation = r->digitisation;
+            rec.offset = r->offset;
+            rec.range = r->range;
+            rec.sampling_rate = r->sampling_rate;
+            rec.len_raw_signal = r->len_raw_signal;
+            rec.raw_signal.assign(r->raw_signal, r->raw_signal + r->len_raw_signal);
+            rec.aux_bytes = r->aux;
+            rec.aux_nbytes = r->aux_len;
+            std::string line;
+            record_to_ascii(rec, f->hdr, line);
+            char *m = static_cast<char *>(malloc(line.size() + 1));
+            if (!m) return fail(S5B_ERR_MEM);
+            memcpy(m, line.data(), line.size());
+            m[line.size()] = '\0';
+            mems[i] = m;
+            bytes[i] = line.size();
+        }
+        return 0;
+    }
     if (f->rec_press != PRESS_NONE || f->sig_press != PRESS_NONE) {
         const int rc = ensure_gpu(f);
         if (rc != S5B_OK) return fail(rc);
