@@ -25,6 +25,7 @@ run aux ./AUX_PROG $R/tests/golden/fixtures/exp_1_lossless.blow5
 run get ./GET_PROG ex.blow5 $(grep -v '^[#@]' $EX | cut -f1 | head -2) no-such-read
 run intro ./INTRO_PROG enum.blow5 end_reason
 run write ./WRITE_PROG w.blow5
+run write_text ./WRITE_PROG w.slow5
 gcc -g -O1 -w -fsanitize=address,undefined -I $R/include/compat $REF/slow5lib/examples/append.c -o append -L . -lslow5b200 -Wl,-rpath,$T
 cp w.blow5 test.blow5
 run append ./append
