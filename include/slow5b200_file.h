@@ -202,6 +202,12 @@ void s5b_idx_unload(s5b_file_t *fp);   /* slow5_idx_unload, slow5.h:382 */
 int s5b_get_batch(s5b_mt_t *mt, s5b_batch_t *batch, char **rid, int num_rid);
 void s5b_free_batch(s5b_batch_t *batch);
 void s5b_free_mt(s5b_mt_t *mt);
+/* the "lazy" forms pyslow5 calls (slow5_mt.h:59-65): no mt / batch objects to keep; *read receives a malloc()'d array of batch_size
+ * (num_rid) record pointers of which the first <return value> are set, to be released with s5b_free_batch_lazy */
+int s5b_get_next_batch_lazy(s5b_rec_t ***read, s5b_file_t *fp, int batch_size, int num_threads);
+int s5b_get_batch_lazy(s5b_rec_t ***read, s5b_file_t *fp, char **rid, int num_rid, int num_threads);
+int s5b_write_batch_lazy(s5b_rec_t **read, s5b_file_t *fp, int batch_size, int num_threads);
+void s5b_free_batch_lazy(s5b_rec_t ***read, int num_rec);
 
 #ifdef S5B_SLOW5_COMPAT
 #define slow5_press_method_t s5b_press_method_t
@@ -229,6 +235,10 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_idx_unload s5b_idx_unload
 #define slow5_free_batch s5b_free_batch
 #define slow5_free_mt s5b_free_mt
+#define slow5_get_next_batch_lazy s5b_get_next_batch_lazy
+#define slow5_get_batch_lazy s5b_get_batch_lazy
+#define slow5_write_batch_lazy s5b_write_batch_lazy
+#define slow5_free_batch_lazy s5b_free_batch_lazy
 #define slow5_file_t s5b_file_t
 #define slow5_rec_t s5b_rec_t
 #define slow5_open s5b_open
@@ -276,6 +286,7 @@ void s5b_free_mt(s5b_mt_t *mt);
 #define slow5_get_rids s5b_get_rids
 #define slow5_rec_init s5b_rec_init
 #define slow5_hdr_add s5b_hdr_add
+#define slow5_hdr_add_attr s5b_hdr_add
 #define slow5_hdr_set s5b_hdr_set
 #define slow5_hdr_add_rg s5b_hdr_add_rg
 #define slow5_aux_add s5b_aux_add

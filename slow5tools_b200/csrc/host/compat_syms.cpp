@@ -39,6 +39,11 @@ int slow5_idx_load(s5b_file_t *fp) { return s5b_idx_load(fp); }
 void slow5_idx_unload(s5b_file_t *fp) { s5b_idx_unload(fp); }
 void slow5_free_batch(s5b_batch_t *b) { s5b_free_batch(b); }
 void slow5_free_mt(s5b_mt_t *mt) { s5b_free_mt(mt); }
+int slow5_get_next_batch_lazy(s5b_rec_t ***read, s5b_file_t *fp, int n, int t) { return s5b_get_next_batch_lazy(read, fp, n, t); }
+int slow5_get_batch_lazy(s5b_rec_t ***read, s5b_file_t *fp, char **rid, int n, int t) { return s5b_get_batch_lazy(read, fp, rid, n, t); }
+int slow5_write_batch_lazy(s5b_rec_t **read, s5b_file_t *fp, int n, int t) { return s5b_write_batch_lazy(read, fp, n, t); }
+void slow5_free_batch_lazy(s5b_rec_t ***read, int n) { s5b_free_batch_lazy(read, n); }
+int slow5_hdr_add_attr(const char *attr, s5b_hdr_t *h) { return s5b_hdr_add(attr, h); }
 
 s5b_press_t *slow5_press_init(s5b_press_method_t m) { return s5b_press_init(m); }
 struct __s5b_press *__slow5_press_init(int method) { return __s5b_press_init(method); }

@@ -776,6 +776,64 @@ int s5b_get(const char *read_id, s5b_rec_t **read, s5b_file_t *fpub) {  // slow5
     return rc;
 }
 
+// the "even lazier" forms pyslow5 uses (slow5_mt.h:59-65, slow5_mt.c:390-447): the mt / batch objects live for one call, the
+// records are handed over as a bare array
+int s5b_get_next_batch_lazy(s5b_rec_t ***read, s5b_file_t *fp, int batch_size, int num_threads) {
+    if (!read) return fail(S5B_ERR_ARG);
+    s5b_mt_t *mt = s5b_init_mt(num_threads, fp);
+    s5b_batch_t *b = s5b_init_batch(batch_size);
+    if (!mt || !b) {
+        s5b_free_batch(b);
+        s5b_free_mt(mt);
+        return fail(S5B_ERR_MEM);
+    }
+    const int ret = s5b_get_next_batch(mt, b, batch_size);
+    *read = b->slow5_rec;
+    b->slow5_rec = nullptr;
+    s5b_free_batch(b);
+    s5b_free_mt(mt);
+    return ret;
+}
+int s5b_get_batch_lazy(s5b_rec_t ***read, s5b_file_t *fp, char **rid, int num_rid, int num_threads) {
+    if (!read) return fail(S5B_ERR_ARG);
+    s5b_mt_t *mt = s5b_init_mt(num_threads, fp);
+    s5b_batch_t *b = s5b_init_batch(num_rid);
+    if (!mt || !b) {
+        s5b_free_batch(b);
+        s5b_free_mt(mt);
+        return fail(S5B_ERR_MEM);
+    }
+    const int ret = s5b_get_batch(mt, b, rid, num_rid);
+    *read = b->slow5_rec;
+    b->slow5_rec = nullptr;
+    s5b_free_batch(b);
+    s5b_free_mt(mt);
+    return ret;
+}
+int s5b_write_batch_lazy(s5b_rec_t **read, s5b_file_t *fp, int batch_size, int num_threads) {
+    if (!read) return fail(S5B_ERR_ARG);
+    s5b_mt_t *mt = s5b_init_mt(num_threads, fp);
+    s5b_batch_t *b = s5b_init_batch(batch_size);
+    if (!mt || !b) {
+        s5b_free_batch(b);
+        s5b_free_mt(mt);
+        return fail(S5B_ERR_MEM);
+    }
+    free(b->slow5_rec);
+    b->slow5_rec = read;          // the caller's records: written, not taken over
+    const int ret = s5b_write_batch(mt, b, batch_size);
+    b->slow5_rec = nullptr;
+    s5b_free_batch(b);
+    s5b_free_mt(mt);
+    return ret;
+}
+void s5b_free_batch_lazy(s5b_rec_t ***read, int num_rec) {
+    if (!read || !*read) return;
+    for (int i = 0; i < num_rec; ++i) s5b_rec_free((*read)[i]);
+    free(*read);
+    *read = nullptr;
+}
+
 int s5b_write_batch(s5b_mt_t *mt, s5b_batch_t *b, int num_reads) {  // slow5_mt.c:359-378
     const int rc = s5b_encode_batch_mt(mt, b, num_reads);
     if (rc < 0) return rc;

@@ -633,3 +633,39 @@ def test_reference_example_get_all_read_ids_unchanged(tmp_path):
         assert r.returncode == 0, r.stderr.decode()
         out.append((r.stdout, open(blow + ".idx", "rb").read()))
     assert out[0] == out[1] and out[0][0].count(b"\n") >= 5
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+@pytest.mark.parametrize("example", ["mt", "lazymt"])
+def test_reference_mt_examples(tmp_path, example):
+    """slow5lib/examples/mt/{mt,lazymt}.c -- the batch API as pyslow5 drives it: 4000 records written with slow5_write_batch[_lazy],
+    read back with slow5_get_next_batch[_lazy] and by id with slow5_get_batch[_lazy].  The sources are used as they are except for
+    ONE inserted line that switches compression off (the examples write zlib + svb-zd, which needs a device here; the unchanged
+    sources are only compiled).  Both builds print the same and leave the same test.blow5 and index behind."""
+    src = open(os.path.join(REFTREE, "slow5lib", "examples", "mt", example + ".c")).read()
+    anchor = "    //set zstd record compression, svb-zd signal compression\n"
+    assert src.count(anchor) == 1
+    patched = src.replace(anchor, "    if (slow5_set_press(sf, SLOW5_COMPRESS_NONE, SLOW5_COMPRESS_NONE) < 0) exit(EXIT_FAILURE);\n" + anchor)
+    refdir = os.path.dirname(REF_SO)
+    got = []
+    for who in ("ours", "theirs"):
+        d = tmp_path / who
+        os.makedirs(d)
+        (d / "prog.c").write_text(patched)
+        exe = str(d / "prog")
+        if who == "ours":
+            inc = ["-I", os.path.join(ROOT, "include", "compat")]
+            lib = ["-L", LIBDIR, "-lslow5b200", "-lpthread", "-Wl,-rpath," + LIBDIR]
+            # the unchanged source builds as well
+            _cc(["-O1", "-w"] + inc + [os.path.join(REFTREE, "slow5lib", "examples", "mt", example + ".c"), "-o", str(d / "unchanged")] + lib)
+        else:
+            inc = ["-I", os.path.join(REFTREE, "slow5lib", "include")]
+            lib = ["-L", refdir, "-l:libslow5_ref.so", "-Wl,-rpath," + refdir, "-lm", "-lz", "-lpthread"]
+        _cc(["-O1", "-w"] + inc + [str(d / "prog.c"), "-o", exe] + lib)
+        r = subprocess.run([exe], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert r.returncode == 0, (who, r.stderr.decode()[-2000:])
+        files = {f: open(d / f, "rb").read() for f in sorted(os.listdir(d)) if f.startswith("test.blow5")}
+        got.append((r.stdout, files))
+    assert got[0][0] == got[1][0] and got[0][0].count(b"\n") > 4000
+    assert got[0][1] == got[1][1] and "test.blow5" in got[0][1]
