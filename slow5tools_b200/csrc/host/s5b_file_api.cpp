@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -67,6 +68,9 @@ struct S5bFile {
     Header hdr;         // "w": header to emit
     int rec_press = PRESS_ZLIB, sig_press = PRESS_SVB_ZD;
     s5b_ctx_t *gpu = nullptr;
+    // slow5_get / slow5_decode may be called from several threads on one file (slow5lib/examples/random_read_pthreads.c): the file's
+    // GPU context serves one batch at a time
+    std::mutex gpu_mu;
     // read id -> (offset of the record's size prefix, bytes including the prefix): FILE.idx (slow5_idx.c:360-520)
     struct Where {
         uint64_t offset, size;
@@ -390,7 +394,9 @@ int s5b_decode_batch(s5b_file_t *fpub, char **mems, size_t *bytes, size_t n, s5b
         }
         return 0;
     }
+    std::unique_lock<std::mutex> gpu_lock(f->gpu_mu, std::defer_lock);
     if (h.record_method != PRESS_NONE || h.signal_method != PRESS_NONE) {
+        gpu_lock.lock();
         const int rc = ensure_gpu(f);
         if (rc != S5B_OK) return fail(rc);
     }
@@ -481,7 +487,9 @@ int s5b_encode_batch(s5b_file_t *fpub, s5b_rec_t **reads, size_t n, char **mems,
         }
         return 0;
     }
+    std::unique_lock<std::mutex> gpu_lock(f->gpu_mu, std::defer_lock);
     if (f->rec_press != PRESS_NONE || f->sig_press != PRESS_NONE) {
+        gpu_lock.lock();
         const int rc = ensure_gpu(f);
         if (rc != S5B_OK) return fail(rc);
     }

@@ -669,3 +669,30 @@ def test_reference_mt_examples(tmp_path, example):
         got.append((r.stdout, files))
     assert got[0][0] == got[1][0] and got[0][0].count(b"\n") > 4000
     assert got[0][1] == got[1][1] and "test.blow5" in got[0][1]
+
+
+@have_tree
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libslow5_ref.so not present")
+@pytest.mark.parametrize("example", ["random_read_pthreads", "random_read_openmp", "adv/sequential_read_openmp"])
+def test_reference_threaded_examples_build_unchanged(tmp_path, example):
+    """the reference's user-threaded examples (slow5_get from several threads after slow5_idx_load; slow5_get_next_bytes + slow5_decode
+    under OpenMP), UNCHANGED: the same lines from both builds (compared sorted: the thread order is not fixed)"""
+    src = os.path.join(REFTREE, "slow5lib", "examples", example + ".c")
+    refdir = os.path.dirname(REF_SO)
+    out = []
+    for who in ("ours", "theirs"):
+        d = tmp_path / who
+        os.makedirs(d / "examples")
+        for f in ("example.slow5", "example2.slow5"):
+            shutil.copy(os.path.join(REFTREE, "slow5lib", "examples", f), d / "examples" / f)
+        exe = str(d / "prog")
+        if who == "ours":
+            _cc(["-O1", "-w", "-fopenmp", "-I", os.path.join(ROOT, "include", "compat"), src, "-o", exe, "-L", LIBDIR, "-lslow5b200",
+                 "-lpthread", "-Wl,-rpath," + LIBDIR])
+        else:
+            _cc(["-O1", "-w", "-fopenmp", "-I", os.path.join(REFTREE, "slow5lib", "include"), src, "-o", exe, "-L", refdir,
+                 "-l:libslow5_ref.so", "-Wl,-rpath," + refdir, "-lm", "-lz", "-lpthread"])
+        r = subprocess.run([exe], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=120)
+        assert r.returncode == 0, r.stdout.decode()
+        out.append(sorted(r.stdout.splitlines()))
+    assert out[0] == out[1] and len(out[0]) >= 5
